@@ -1,0 +1,2 @@
+"""B200-native backend for the sparse-identification hot path of DataDrivenDiffEq.jl."""
+from . import _lib  # noqa: F401

@@ -1,0 +1,297 @@
+// extern "C" entry points of libddb200.so (declared in include/ddb.h): context, library, data and
+// the stage wrappers.  Kernels live in gram.cu / sweep.cu / rss.cu / generate.cu / dmd.cu.
+#include "common.cuh"
+#include <cstdarg>
+#include <cstring>
+#include <cmath>
+
+namespace ddb {
+
+static thread_local char g_error[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+int DevBuf::reserve(size_t need) {
+    if (need <= bytes && p) return DDB_OK;
+    if (p) {
+        cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    if (need == 0) need = 16;
+    cudaError_t e = cudaMalloc(&p, need);
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc(%zu bytes) failed: %s", need, cudaGetErrorString(e));
+        p = nullptr;
+        return e == cudaErrorMemoryAllocation ? DDB_OUT_OF_MEMORY : DDB_CUDA_ERROR;
+    }
+    bytes = need;
+    return DDB_OK;
+}
+void DevBuf::release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+}
+
+int gram_run(ddb_ctx* ctx, double* dPacked);
+int generate_run(ddb_ctx* ctx, int system_id, int n_states, int64_t m, int64_t first_sample, uint64_t seed,
+                 double noise_std);
+void sweep_free(ddb_ctx* ctx);
+
+}  // namespace ddb
+
+using namespace ddb;
+
+#define CHECK_CTX(ctx)                                     \
+    do {                                                   \
+        if (!(ctx)) {                                      \
+            set_error("%s: null context", __func__);       \
+            return DDB_INVALID_ARG;                        \
+        }                                                  \
+        DDB_CUDA_TRY(cudaSetDevice((ctx)->device));        \
+    } while (0)
+
+extern "C" {
+
+const char* ddb_last_error(void) { return g_error; }
+const char* ddb_version(void) { return "ddb200 0.1 (sm_100a)"; }
+
+int ddb_ctx_create(int device, ddb_ctx** out) {
+    if (!out) {
+        set_error("ddb_ctx_create: out is null");
+        return DDB_INVALID_ARG;
+    }
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_error("ddb_ctx_create: no CUDA device available (%s); this backend has no CPU fallback",
+                  cudaGetErrorString(e));
+        return DDB_CUDA_ERROR;
+    }
+    if (device < 0 || device >= count) {
+        set_error("ddb_ctx_create: device %d out of range (have %d)", device, count);
+        return DDB_INVALID_ARG;
+    }
+    DDB_CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    DDB_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("ddb_ctx_create: device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major,
+                  prop.minor);
+        return DDB_UNSUPPORTED;
+    }
+    ddb_ctx* ctx = new ddb_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    DDB_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    for (auto& ev : ctx->ev) DDB_CUDA_TRY(cudaEventCreate(&ev));
+    *out = ctx;
+    return DDB_OK;
+}
+
+int ddb_ctx_destroy(ddb_ctx* ctx) {
+    if (!ctx) return DDB_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    sweep_free(ctx);
+    ctx->d_factors.release();
+    ctx->own_X.release();
+    ctx->own_Y.release();
+    ctx->d_packed.release();
+    ctx->d_partials.release();
+    ctx->d_plan.release();
+    for (auto& ev : ctx->ev)
+        if (ev) cudaEventDestroy(ev);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return DDB_OK;
+}
+
+int ddb_set_library_monomial(ddb_ctx* ctx, int n, int k, const uint8_t* exps) {
+    CHECK_CTX(ctx);
+    if (n <= 0 || k <= 0 || !exps) {
+        set_error("ddb_set_library_monomial: n and k must be positive and exps non-null");
+        return DDB_INVALID_ARG;
+    }
+    int maxdeg = 0;
+    for (int j = 0; j < k; ++j) {
+        int d = 0;
+        for (int i = 0; i < n; ++i) d += exps[(size_t)i + (size_t)n * j];
+        if (d > maxdeg) maxdeg = d;
+    }
+    if (maxdeg > kMaxFactors) {
+        set_error("ddb_set_library_monomial: total degree %d exceeds the supported maximum %d", maxdeg, kMaxFactors);
+        return DDB_UNSUPPORTED;
+    }
+    ctx->n = n;
+    ctx->k = k;
+    ctx->max_degree = maxdeg;
+    ctx->exps.assign(exps, exps + (size_t)n * k);
+    ctx->factors_nt = -1;
+    ctx->plan_m = -1;
+    ctx->have_gram = false;
+    return DDB_OK;
+}
+
+static int check_data_args(ddb_ctx* ctx, const void* X, const void* Y, int n_t, int64_t m, const char* who) {
+    if (ctx->n <= 0) {
+        set_error("%s: install the library first (the number of states comes from it)", who);
+        return DDB_BAD_STATE;
+    }
+    if (!X || !Y || n_t <= 0 || m <= 0) {
+        set_error("%s: X, Y must be non-null and n_t, m positive", who);
+        return DDB_INVALID_ARG;
+    }
+    return DDB_OK;
+}
+
+int ddb_upload(ddb_ctx* ctx, const double* X, const double* Y, int n_t, int64_t m) {
+    CHECK_CTX(ctx);
+    DDB_TRY(check_data_args(ctx, X, Y, n_t, m, "ddb_upload"));
+    const size_t xb = (size_t)ctx->n * m * sizeof(double), yb = (size_t)n_t * m * sizeof(double);
+    DDB_TRY(ctx->own_X.reserve(xb));
+    DDB_TRY(ctx->own_Y.reserve(yb));
+    DDB_CUDA_TRY(cudaEventRecord(ctx->ev[2], ctx->stream));
+    DDB_CUDA_TRY(cudaMemcpyAsync(ctx->own_X.p, X, xb, cudaMemcpyHostToDevice, ctx->stream));
+    DDB_CUDA_TRY(cudaMemcpyAsync(ctx->own_Y.p, Y, yb, cudaMemcpyHostToDevice, ctx->stream));
+    DDB_CUDA_TRY(cudaEventRecord(ctx->ev[3], ctx->stream));
+    DDB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    DDB_CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
+    ctx->timings.h2d_ms = ms;
+    ctx->dX = ctx->own_X.as<double>();
+    ctx->dY = ctx->own_Y.as<double>();
+    ctx->n_t = n_t;
+    ctx->m = m;
+    ctx->have_gram = false;
+    return DDB_OK;
+}
+
+int ddb_bind_device(ddb_ctx* ctx, const double* dX, const double* dY, int n_t, int64_t m) {
+    CHECK_CTX(ctx);
+    DDB_TRY(check_data_args(ctx, dX, dY, n_t, m, "ddb_bind_device"));
+    ctx->dX = dX;
+    ctx->dY = dY;
+    ctx->n_t = n_t;
+    ctx->m = m;
+    ctx->have_gram = false;
+    return DDB_OK;
+}
+
+int ddb_generate(ddb_ctx* ctx, int system_id, int n_states, int64_t m, int64_t first_sample, uint64_t seed,
+                 double noise_std) {
+    CHECK_CTX(ctx);
+    return generate_run(ctx, system_id, n_states, m, first_sample, seed, noise_std);
+}
+
+int ddb_download_data(ddb_ctx* ctx, double* X, double* Y) {
+    CHECK_CTX(ctx);
+    if (!ctx->dX || !ctx->dY) {
+        set_error("ddb_download_data: no data bound");
+        return DDB_BAD_STATE;
+    }
+    if (X)
+        DDB_CUDA_TRY(cudaMemcpyAsync(X, ctx->dX, (size_t)ctx->n * ctx->m * sizeof(double), cudaMemcpyDeviceToHost,
+                                     ctx->stream));
+    if (Y)
+        DDB_CUDA_TRY(cudaMemcpyAsync(Y, ctx->dY, (size_t)ctx->n_t * ctx->m * sizeof(double), cudaMemcpyDeviceToHost,
+                                     ctx->stream));
+    DDB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return DDB_OK;
+}
+
+int64_t ddb_gram_count(const ddb_ctx* ctx) {
+    if (!ctx) return 0;
+    return (int64_t)ctx->k * ctx->k + (int64_t)ctx->k * ctx->n_t + ctx->n_t;
+}
+
+int ddb_gram(ddb_ctx* ctx, double* dPacked) {
+    CHECK_CTX(ctx);
+    return gram_run(ctx, dPacked);
+}
+
+int ddb_gram_buffer(ddb_ctx* ctx, double** dPacked) {
+    CHECK_CTX(ctx);
+    if (!dPacked) {
+        set_error("ddb_gram_buffer: null output");
+        return DDB_INVALID_ARG;
+    }
+    if (ctx->k <= 0 || ctx->n_t <= 0) {
+        set_error("ddb_gram_buffer: library and data must be set first");
+        return DDB_BAD_STATE;
+    }
+    DDB_TRY(ctx->d_packed.reserve((size_t)ddb_gram_count(ctx) * sizeof(double)));
+    *dPacked = ctx->d_packed.as<double>();
+    return DDB_OK;
+}
+
+int ddb_gram_download(ddb_ctx* ctx, double* G, double* R, double* yy) {
+    CHECK_CTX(ctx);
+    if (!ctx->d_packed.p) {
+        set_error("ddb_gram_download: no normal-equation blocks in the context");
+        return DDB_BAD_STATE;
+    }
+    const size_t k = ctx->k, nt = ctx->n_t;
+    const double* p = ctx->d_packed.as<double>();
+    if (G) DDB_CUDA_TRY(cudaMemcpyAsync(G, p, k * k * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (R) DDB_CUDA_TRY(cudaMemcpyAsync(R, p + k * k, k * nt * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (yy)
+        DDB_CUDA_TRY(cudaMemcpyAsync(yy, p + k * k + k * nt, nt * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    DDB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return DDB_OK;
+}
+
+int ddb_gram_upload(ddb_ctx* ctx, const double* G, const double* R, const double* yy, int n_t) {
+    CHECK_CTX(ctx);
+    if (ctx->k <= 0 || !G || !R || !yy || n_t <= 0) {
+        set_error("ddb_gram_upload: library must be installed and G, R, yy non-null");
+        return DDB_INVALID_ARG;
+    }
+    if (ctx->n_t != n_t) {
+        ctx->n_t = n_t;
+        ctx->factors_nt = -1;
+        ctx->plan_m = -1;
+    }
+    const size_t k = ctx->k, nt = n_t;
+    DDB_TRY(ctx->d_packed.reserve((size_t)ddb_gram_count(ctx) * sizeof(double)));
+    double* p = ctx->d_packed.as<double>();
+    DDB_CUDA_TRY(cudaMemcpyAsync(p, G, k * k * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    DDB_CUDA_TRY(cudaMemcpyAsync(p + k * k, R, k * nt * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    DDB_CUDA_TRY(cudaMemcpyAsync(p + k * k + k * nt, yy, nt * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    DDB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    ctx->have_gram = true;
+    return DDB_OK;
+}
+
+int ddb_get_timings(const ddb_ctx* ctx, ddb_timings* out) {
+    if (!ctx || !out) {
+        set_error("ddb_get_timings: null argument");
+        return DDB_INVALID_ARG;
+    }
+    *out = ctx->timings;
+    return DDB_OK;
+}
+
+int ddb_get_stream(ddb_ctx* ctx, void** stream) {
+    if (!ctx || !stream) {
+        set_error("ddb_get_stream: null argument");
+        return DDB_INVALID_ARG;
+    }
+    *stream = (void*)ctx->stream;
+    return DDB_OK;
+}
+
+int ddb_synchronize(ddb_ctx* ctx) {
+    CHECK_CTX(ctx);
+    DDB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return DDB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,104 @@
+// Internal declarations shared by the translation units of libddb200.so.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+#include "../../include/ddb.h"
+
+namespace ddb {
+
+void set_error(const char* fmt, ...);
+
+#define DDB_CUDA_TRY(expr)                                                                        \
+    do {                                                                                          \
+        cudaError_t e__ = (expr);                                                                 \
+        if (e__ != cudaSuccess) {                                                                 \
+            ::ddb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__,   \
+                             __LINE__);                                                           \
+            return (e__ == cudaErrorMemoryAllocation) ? DDB_OUT_OF_MEMORY : DDB_CUDA_ERROR;       \
+        }                                                                                         \
+    } while (0)
+
+#define DDB_TRY(expr)                 \
+    do {                              \
+        int s__ = (expr);             \
+        if (s__ != DDB_OK) return s__; \
+    } while (0)
+
+// A device allocation that grows on demand and is released with the context.
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int reserve(size_t need);
+    void release();
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Gram stage
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxFactors = 8;       // maximum total degree of a library term
+constexpr uint16_t kNoFactor = 0xFFFF;
+constexpr uint16_t kFactorIsY = 0x8000;
+
+// One contiguous piece of work of the Gram kernel: a block pair (bi >= bj) over a stage range.
+struct GramSegment {
+    int32_t bi, bj;          // block-row / block-column of the augmented library
+    int32_t slot;            // partial-tile slot the accumulators are flushed to
+    int32_t pad;
+    int64_t stage_begin, stage_end;
+};
+
+struct GramPlan {
+    int bt = 0;              // block tile (64 or 128)
+    int ks = 0;              // samples per stage
+    int nblk = 0;            // blocks per dimension of the augmented library
+    int npairs = 0;          // lower-triangular block pairs
+    int nctas = 0;
+    int nslots = 0;
+    int64_t nstages = 0;
+    std::vector<GramSegment> segments;     // sorted by CTA
+    std::vector<int32_t> cta_seg_begin;    // nctas + 1
+    std::vector<int32_t> pair_slot_begin;  // npairs + 1  (slots of one pair are contiguous)
+    std::vector<int32_t> slot_order;       // slots grouped by pair, fixed summation order
+};
+
+void build_gram_plan(GramPlan& plan, int kaug, int64_t m, int nctas, int bt, int ks);
+
+}  // namespace ddb
+
+struct ddb_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8] = {};
+
+    // library
+    int n = 0, k = 0, max_degree = 0;
+    std::vector<uint8_t> exps;           // n x k
+    ddb::DevBuf d_factors;               // (k + n_t) x kMaxFactors uint16, built when n_t is known
+    int factors_nt = -1;
+
+    // data
+    const double* dX = nullptr;
+    const double* dY = nullptr;
+    int n_t = 0;
+    int64_t m = 0;
+    ddb::DevBuf own_X, own_Y;
+
+    // gram
+    ddb::DevBuf d_packed;                // [G | R | yy]
+    ddb::DevBuf d_partials;              // partial tiles
+    ddb::DevBuf d_plan;                  // device copy of segments etc.
+    ddb::GramPlan plan;
+    int64_t plan_m = -1;
+    int plan_kaug = -1;
+    bool have_gram = false;
+
+    // sweep / rss / select state lives in sweep.cu
+    struct SweepState* sweep = nullptr;
+
+    ddb_timings timings = {};
+};

@@ -1,0 +1,219 @@
+/* ddb.h — C ABI of the B200-native sparse-identification backend for DataDrivenDiffEq.jl.
+ *
+ * This is the drop-in boundary.  The reference has no FFI of its own — it is
+ * pure Julia — so each entry point below names the reference code it REPLACES (paths relative to the
+ * reference checkout).  A Julia maintainer binds these with `ccall` from two methods
+ * (`DataDrivenDiffEq.get_fit_targets`, src/commonsolve.jl:74-81 and `CommonSolve.solve!`,
+ * lib/DataDrivenSparse/src/commonsolve.jl:1-24); see INTEGRATION.md for the stub.
+ *
+ * Conventions
+ *   - All matrices are column-major (Julia layout).  States are n x m (one sample per column, so one
+ *     sample's values are contiguous), targets n_t x m, coefficients n_t x k.
+ *   - Every function returns DDB_OK (0) or a negative ddb_status; the message of the last error of
+ *     the calling thread is available from ddb_last_error().  No C++ exception crosses the boundary.
+ *   - The caller owns every host buffer and every device buffer it passes in and keeps it alive for
+ *     the duration of the call; the library neither frees nor retains them after returning, except
+ *     ddb_bind_device (retains the two data pointers until the next bind/upload/destroy).
+ *   - A ddb_ctx is bound to ONE GPU (one process per GPU) and is not thread-safe; distinct contexts
+ *     are independent.  Calls are synchronous unless the name ends in _async.
+ *   - There is NO CPU fallback: without a CUDA device every entry point that computes fails with
+ *     DDB_CUDA_ERROR.
+ */
+#ifndef DDB_H
+#define DDB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ddb_ctx ddb_ctx;
+
+typedef enum ddb_status {
+    DDB_OK = 0,
+    DDB_INVALID_ARG = -1,
+    DDB_UNSUPPORTED = -2,
+    DDB_CUDA_ERROR = -3,
+    DDB_NCCL_ERROR = -4,
+    DDB_NOT_POSITIVE_DEFINITE = -5,
+    DDB_NONFINITE_INPUT = -6,
+    DDB_OUT_OF_MEMORY = -7,
+    DDB_BAD_STATE = -8
+} ddb_status;
+
+/* Which sparse-regression algorithm the sweep runs (lib/DataDrivenSparse/src/algorithms/). */
+typedef enum ddb_algorithm {
+    DDB_ALG_STLSQ = 0, /* STLSQ.jl:48-140 */
+    DDB_ALG_ADMM = 1,  /* ADMM.jl:32-139  */
+    DDB_ALG_SR3 = 2    /* SR3.jl:45-141   */
+} ddb_algorithm;
+
+/* Proximal operator of SR3 (algorithms/proximals.jl). STLSQ and ADMM always use SOFT's mask. */
+typedef enum ddb_proximal {
+    DDB_PROX_SOFT = 0, /* SoftThreshold            proximals.jl:36-65   */
+    DDB_PROX_HARD = 1, /* HardThreshold            proximals.jl:88-117  */
+    DDB_PROX_CAD = 2   /* ClippedAbsoluteDeviation proximals.jl:156-195 */
+} ddb_proximal;
+
+/* Model-selection score evaluated after every step (options.selector, solver.jl:100). */
+typedef enum ddb_selector {
+    DDB_SEL_BIC = 0, /* default, src/utils/common_options.jl:48 */
+    DDB_SEL_AIC = 1,
+    DDB_SEL_AICC = 2,
+    DDB_SEL_RSS = 3
+} ddb_selector;
+
+/* Mirrors the fields of DataDrivenCommonOptions (src/utils/common_options.jl:22-54) and of the
+ * algorithm structs that the sweep reads. */
+typedef struct ddb_sweep_params {
+    int32_t algorithm; /* ddb_algorithm */
+    int32_t proximal;  /* ddb_proximal (SR3 only) */
+    int32_t selector;  /* ddb_selector */
+    int32_t maxiters;  /* per threshold (solver.jl:95); reference default 100 */
+    double abstol;     /* reference default sqrt(eps) */
+    double reltol;     /* reference default sqrt(eps) */
+    double rho;        /* STLSQ ridge (0 = plain least squares) / ADMM rho / SR3 nu */
+    double cad_rho;    /* ClippedAbsoluteDeviation upper cut; NaN = 5*lambda (proximals.jl:169) */
+} ddb_sweep_params;
+
+/* Stage timings of the last ddb_solve_sparse / stage calls, milliseconds, CUDA events. */
+typedef struct ddb_timings {
+    double h2d_ms;
+    double gram_ms;
+    double factor_ms;
+    double sweep_ms;
+    double rss_ms;
+    double select_ms;
+    double d2h_ms;
+    int32_t gram_launches;  /* kernels launched by the Gram stage */
+    int32_t sweep_launches; /* kernels launched by the sweep + rss + select stages */
+    int32_t big_steps;      /* sweep steps that needed the blocked (global-memory) Cholesky */
+    int32_t candidates;     /* unique (equation, support, coefficients) candidates scored */
+} ddb_timings;
+
+/* ---- context ---------------------------------------------------------------------------------- */
+
+/* Create a context on CUDA device `device`.  Owns its stream, workspaces and tables. */
+int ddb_ctx_create(int device, ddb_ctx** out);
+int ddb_ctx_destroy(ddb_ctx* ctx);
+const char* ddb_last_error(void);
+/* Library version string, e.g. "ddb200 0.1 (sm_100a)". */
+const char* ddb_version(void);
+
+/* ---- candidate library (replaces Basis code generation + evaluation) ------------------------- */
+
+/* Install a monomial library: k terms over n states, exps is n x k column-major,
+ * exps[i + n*j] = power of state i in term j, in the reference's term order
+ * (polynomial_basis / monomial_basis, src/utils/basis_generators.jl:84-149; evaluated by
+ * (b::Basis)(prob), src/problem/type.jl:404-407 -> src/basis/build_function.jl:186-205).
+ * Total degree of a term must be <= 8. */
+int ddb_set_library_monomial(ddb_ctx* ctx, int n, int k, const uint8_t* exps);
+
+/* ---- data ------------------------------------------------------------------------------------- */
+
+/* Copy host data to the device (replaces nothing in the reference; it is the host->device edge).
+ * X: n x m, Y: n_t x m, column-major.  m is this context's LOCAL sample count (its row shard). */
+int ddb_upload(ddb_ctx* ctx, const double* X, const double* Y, int n_t, int64_t m);
+
+/* Use data already resident on the device (device pointers, 16-byte aligned). */
+int ddb_bind_device(ddb_ctx* ctx, const double* dX, const double* dY, int n_t, int64_t m);
+
+/* Generate synthetic trajectories on the device and bind them.
+ * system_id: 0 = Lorenz (n=3), 1 = Lorenz-96 (n = n_states).  Y = exact right-hand side.
+ * noise_std > 0 adds N(0, noise_std^2) to Y.  Sample index offset `first_sample` lets each rank
+ * generate its own shard of one global data set. */
+int ddb_generate(ddb_ctx* ctx, int system_id, int n_states, int64_t m, int64_t first_sample,
+                 uint64_t seed, double noise_std);
+
+/* Copy the bound device data back to the host (for tests and the end-to-end bench). */
+int ddb_download_data(ddb_ctx* ctx, double* X, double* Y);
+
+/* ---- stage 1+2: fused library evaluation + normal-equation blocks ----------------------------- */
+
+/* Number of doubles in the packed normal-equation buffer [G (k*k) | R (k*n_t) | yy (n_t)]. */
+int64_t ddb_gram_count(const ddb_ctx* ctx);
+
+/* Compute this context's partial blocks from its bound samples:
+ *   G = Theta Theta' (k x k), R = Theta Y' (k x n_t), yy[i] = sum_s Y[i,s]^2,
+ * Theta never written to memory.  Replaces the per-target `A*A'`, `B*A'` of
+ * STLSQ.jl:90-91 / ADMM.jl:77-79 / SR3.jl:108-109 and the library evaluation feeding them.
+ * dPacked: device buffer of ddb_gram_count() doubles, or NULL to use the context's own buffer. */
+int ddb_gram(ddb_ctx* ctx, double* dPacked);
+
+/* Device pointer of the context's own packed buffer (for an all-reduce by the caller:
+ * torch.distributed / NCCL over NVLink; one sum all-reduce of ddb_gram_count() doubles). */
+int ddb_gram_buffer(ddb_ctx* ctx, double** dPacked);
+
+/* Copy the packed blocks to the host; any output may be NULL.  G k x k, R k x n_t, yy n_t. */
+int ddb_gram_download(ddb_ctx* ctx, double* G, double* R, double* yy);
+/* Install blocks computed elsewhere (restart / tests).  n_t and m_total describe the data set. */
+int ddb_gram_upload(ddb_ctx* ctx, const double* G, const double* R, const double* yy, int n_t);
+
+/* ---- stage 3: thresholded sweep ---------------------------------------------------------------- */
+
+/* Run the warm-started threshold sweep of SparseLinearSolver (solver.jl:72-118) for all n_t targets
+ * on the normal-equation blocks currently in the context (after ddb_gram [+ all-reduce]).
+ * lambdas: L thresholds exactly as the algorithm struct stores them (for SR3+HardThreshold the
+ * caller passes thr^2/2, SR3.jl:63), sorted ascending by the library if they are not.
+ * m_total: number of observations over ALL ranks (nobs of the statistics).
+ * Produces the device-resident candidate list; nothing is returned to the host yet. */
+int ddb_sweep(ddb_ctx* ctx, const ddb_sweep_params* params, const double* lambdas, int L,
+              int64_t m_total);
+
+/* Number of doubles of the candidate-rss table (one per unique candidate + n_t for the zero model). */
+int64_t ddb_rss_count(const ddb_ctx* ctx);
+/* Exact residual sums of squares of every candidate over this context's bound samples (second
+ * streaming pass; replaces rss(cache), DataDrivenSparse.jl:173-176, called by the selector at
+ * solver.jl:100).  dRss: device buffer of ddb_rss_count() doubles or NULL for the context's own. */
+int ddb_rss(ddb_ctx* ctx, double* dRss);
+int ddb_rss_buffer(ddb_ctx* ctx, double** dRss);
+
+/* Apply the selector along each target's step sequence (solver.jl:100-107 semantics incl. the
+ * `<=` tie-break and the `j == 1` rule) and copy the results to the host.  Outputs (any may be
+ * NULL): coef n_t x k column-major = SparseRegressionResult.coefficients (un-rounded);
+ * lambda_opt n_t; iters n_t (total iteration counter, solver.jl:117); rss n_t; dof n_t;
+ * support_path n_t x L x ceil(k/32) uint32 words (converged support at every threshold,
+ * index ((i*L + j)*W + w)); coef_path n_t x L x k doubles (coefficients of the cache when the
+ * inner loop of threshold j stopped, index ((i*L + j)*k + t)); iters_path n_t x L;
+ * flags n_t (bit 0: a factorisation broke down for that target). */
+int ddb_select(ddb_ctx* ctx, double* coef, double* lambda_opt, int32_t* iters, double* rss,
+               int32_t* dof, uint32_t* support_path, double* coef_path, int32_t* iters_path,
+               int32_t* flags);
+
+/* ---- one-call host path (what `solve!` ccalls on a single GPU) -------------------------------- */
+
+/* upload + gram + sweep + rss + select, host buffers in, host buffers out.  Replaces
+ * `alg(X, Y; options)` (DataDrivenSparse.jl:258-277) together with the library evaluation that
+ * `init` performs before it (src/commonsolve.jl:92-139).  trainerror (n_t... summed to a scalar by
+ * the caller) is rss of the selected model per target = sum(abs2, Y - C*Theta) rows
+ * (lib/DataDrivenSparse/src/commonsolve.jl:37). */
+int ddb_solve_sparse(ddb_ctx* ctx, const double* X, const double* Y, int n_t, int64_t m,
+                     const ddb_sweep_params* params, const double* lambdas, int L, double* coef,
+                     double* lambda_opt, int32_t* iters, double* rss, int32_t* dof,
+                     uint32_t* support_path);
+
+/* ---- DataDrivenDMD Gram path ------------------------------------------------------------------- */
+
+/* P = X X' and Q = Y X' (lib/DataDrivenDMD/src/solve.jl:128-129) for snapshot matrices X, Y
+ * (n x m, device pointers; for a discrete problem Y = X shifted by one column, pass dY = dX + n).
+ * dP, dQ: n x n device buffers (column-major), partial sums of this context's samples. */
+int ddb_dmd_gram(ddb_ctx* ctx, const double* dX, const double* dY, int n, int64_t m, double* dP,
+                 double* dQ);
+
+/* K = Q P^-1 (DMDPINV, lib/DataDrivenDMD/src/algorithms.jl:80-83, K = Y / X through the normal
+ * equations) from reduced device blocks dP, dQ; K n x n written to dK (device). */
+int ddb_dmd_operator(ddb_ctx* ctx, const double* dP, const double* dQ, int n, double* dK);
+
+/* ---- introspection ----------------------------------------------------------------------------- */
+
+int ddb_get_timings(const ddb_ctx* ctx, ddb_timings* out);
+/* The context's CUDA stream (cudaStream_t) so a caller can order its own work after ours. */
+int ddb_get_stream(ddb_ctx* ctx, void** stream);
+/* Block the host until everything queued on the context's stream has finished. */
+int ddb_synchronize(ddb_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DDB_H */

@@ -1,0 +1,80 @@
+"""Oracle: candidate-library generators and evaluation (test infrastructure only).
+
+Follows ``src/utils/basis_generators.jl:84-149`` (term enumeration) and
+``src/problem/type.jl:404-407`` -> ``src/basis/build_function.jl:186-205`` (evaluation of every
+library term at every sample; the reference calls a Symbolics-generated scalar function once per
+column and ``hcat``s the results, which is the same k x m matrix computed here in one shot).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+
+def bounded_exponents(n_variables: int, degree: int) -> list[list[int]]:
+    """All exponent vectors with total degree <= ``degree`` in the reference's order.
+
+    ``_append_exponents!`` (``src/utils/basis_generators.jl:84-97``) recurses from the LAST
+    variable down to the first, so the first variable's exponent varies fastest and the constant
+    term comes first.  ``_bounded_exponents`` is ``:99-103``.
+    """
+    out: list[list[int]] = []
+    current = [0] * n_variables
+
+    def rec(index: int, remaining: int) -> None:
+        if index == 0:
+            out.append(list(current))
+            return
+        for e in range(remaining + 1):
+            current[index - 1] = e
+            rec(index - 1, remaining - e)
+
+    rec(n_variables, degree)
+    return out
+
+
+def polynomial_exponents(n_variables: int, degree: int) -> np.ndarray:
+    """Exponent table (n x k, uint8) of ``polynomial_basis`` (``basis_generators.jl:111-126``).
+
+    Column j holds the powers of term j; ``exps[i, j]`` is the power of state i.  The order is
+    pinned by ``test/Core/generators.jl:12-18``.
+    """
+    assert degree > 0
+    e = np.asarray(bounded_exponents(n_variables, degree), dtype=np.uint8)
+    return np.ascontiguousarray(e.T)
+
+
+def monomial_exponents(n_variables: int, degree: int) -> np.ndarray:
+    """Exponent table of ``monomial_basis`` (``basis_generators.jl:134-149``):
+    ``[1, x1, x1^2, ..., x1^d, x2, ...]``."""
+    assert degree > 0
+    k = n_variables * degree + 1
+    e = np.zeros((n_variables, k), dtype=np.uint8)
+    for i in range(n_variables):
+        for j in range(degree):
+            e[i, i * degree + j + 1] = j + 1
+    return e
+
+
+def evaluate_library(exps: np.ndarray, X: np.ndarray) -> np.ndarray:
+    """Theta (k x m) = every monomial of ``exps`` (n x k) at every column of ``X`` (n x m).
+
+    ``(b::Basis)(prob)`` (``src/problem/type.jl:404-407``) -> ``_apply_vec_function``
+    (``src/basis/build_function.jl:186-205``).  Each factor is ``x_i ^ e`` exactly as
+    ``polynomial_basis`` writes it (``term *= xi^exponent``, ``basis_generators.jl:117-123``).
+    """
+    exps = np.asarray(exps)
+    X = np.asarray(X, dtype=np.float64)
+    n, k = exps.shape
+    assert X.shape[0] == n
+    m = X.shape[1]
+    theta = np.ones((k, m), dtype=np.float64)
+    for j in range(k):
+        row = theta[j]
+        for i in range(n):
+            e = int(exps[i, j])
+            if e == 1:
+                row *= X[i]
+            elif e > 1:
+                row *= np.power(X[i], e)
+    return theta
