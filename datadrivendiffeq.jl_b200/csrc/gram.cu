@@ -10,23 +10,29 @@
 // Z Z' = sum_s z z' holds G = Theta Theta' (k x k), R' = Y Theta' (n_t x k) and diag(Y Y').
 // It is tiled into BT x BT block pairs (bi >= bj); the contraction index is the SAMPLE.
 //
-// Per CTA (persistent, one per SM; the host plan hands it a list of (block pair, stage range)):
-//   stage = KS consecutive samples
-//   1. TMA (cp.async.bulk) brings the X tile (KS x n doubles, contiguous in memory because the
-//      reference layout is sample-contiguous) and the Y tile into shared memory, double buffered,
-//      signalled through an mbarrier.
-//   2. Every thread owns one library term (its monomial factor list sits in registers) and
-//      multiplies it out for a few samples: Theta_I' and Theta_J' tiles (KS x BT, sample-major,
-//      padded to a conflict-free pitch) are built in shared memory only -- Theta never reaches HBM.
-//   3. Each warp owns a 32 x 32 patch of the BT x BT block and accumulates it with
-//      mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4 -- the only FP64 tensor shape sm_100a implements),
-//      16 independent accumulator tiles per warp, A and B fragments read from the two Theta tiles.
-//   Accumulators stay in registers across all stages of a segment and are flushed once to a
-//   partial-tile slot; a second kernel adds the slots of each block pair in a fixed order
-//   (bit-reproducible: no floating-point atomics) and scatters into the packed [G | R | yy].
+// Per CTA (persistent; the host plan hands it a list of (block pair, stage range) segments),
+// warp-specialised, stage = 16 consecutive samples:
+//   * TMA ring (3 deep): one producer thread issues cp.async.bulk copies of the X tile (16 x n
+//     doubles, contiguous because the reference layout is sample-contiguous) and the Y tile into
+//     shared memory, completion signalled on an mbarrier, running ahead across segment boundaries.
+//   * Producer warps: thread p owns column p of the block row and of the block column; its two
+//     monomial factor lists sit in registers; per stage it multiplies the factors out for the 16
+//     samples and writes Theta_I' / Theta_J' (16 x BT, sample-major, pitch BT+4 -> conflict-free
+//     fragment loads) into a 4-deep shared-memory ring.  Theta never reaches HBM.
+//   * MMA warps: each owns a 64 x 32 patch of the BT x BT block (32 independent 8x8 accumulator
+//     tiles in registers for the whole segment) and issues mma.sync.m8n8k4.f64 -- SASS DMMA.8x8x4,
+//     the only FP64 tensor shape sm_100a implements -- with A/B fragments read from the ring.
+//     Sub-tiles above the diagonal of a diagonal block pair and rows/columns past the end of the
+//     library are skipped (bit mask per warp); the warp->patch map balances that over the four
+//     SM sub-partitions.
+//   Full/empty mbarriers connect the three roles; there is no CTA-wide barrier in steady state.
+//   Accumulators are flushed once per segment to a partial-tile slot; a second kernel adds the
+//   slots of each block pair in a fixed order (bit-reproducible: no floating-point atomics) and
+//   scatters into the packed [G | R | yy].
 #include "common.cuh"
 #include <algorithm>
 #include <cstring>
+#include <cstdlib>
 
 namespace ddb {
 
@@ -82,184 +88,344 @@ struct GramArgs {
     double* partials;
 };
 
+constexpr int kKS = 16;   // samples per stage
+constexpr int kNVS = 3;   // depth of the raw-sample (TMA) ring
+constexpr int kNTS = 2;   // depth of the Theta-tile ring
 template <int BT>
 struct GramCfg {
-    static constexpr int kWarpsPerDim = BT / 32;
-    static constexpr int kWarps = kWarpsPerDim * kWarpsPerDim;
+    static constexpr int kWarpCols = BT / 32;            // warp grid (BT/64) x (BT/32), warp patch 64 x 32
+    static constexpr int kWarpRows = BT / 64;
+    static constexpr int kWarps = kWarpRows * kWarpCols;  // 8 (BT=128) or 2 (BT=64)
     static constexpr int kThreads = kWarps * 32;
+    static constexpr int kJobs = 2 * BT / kThreads;       // Theta columns built per thread: 1 or 2
     static constexpr int kPitch = BT + 4;  // doubles; pitch % 16 == 4 -> fragment loads hit 16 distinct banks
+    static constexpr int kStageDoubles = 2 * kKS * kPitch;  // Theta_I' and Theta_J' tiles of one stage
+    static constexpr int kMinBlocks = (BT == 128) ? 1 : 3;
 };
 
-__host__ __device__ inline size_t gram_smem_bytes(int bt, int ks, int n, int n_t) {
-    size_t v = (size_t)ks * (n + n_t) * sizeof(double);
-    v = (v + 127) & ~size_t(127);
-    size_t th = (size_t)ks * (bt + 4) * sizeof(double);
-    return 128 + 2 * v + 4 * th;
+// One raw-sample slot (doubles): [ones(16) | 0.0 | pad | X tile 16 x n | Y tile 16 x n_t].
+// ones[s] is 1.0 for a real sample and 0.0 for the zero padding of a ragged last stage, so a monomial
+// with fewer than NF factors reads ones[s] for the missing ones (stride 1) and a padding row of the
+// library reads the 0.0 (stride 0): every Theta entry is a product of exactly NF shared-memory values,
+// no predicates in the hot loop.
+constexpr int kVOnes = 0, kVZero = 16, kVX = 18;
+__host__ __device__ inline size_t gram_vbytes(int n, int n_t) {
+    size_t v = (size_t)(kVX + kKS * (n + n_t)) * sizeof(double);
+    return (v + 127) & ~size_t(127);
+}
+template <int BT>
+inline size_t gram_smem_bytes(int n, int n_t) {
+    return 128 + kNVS * gram_vbytes(n, n_t) + (size_t)kNTS * GramCfg<BT>::kStageDoubles * sizeof(double);
 }
 
-template <int BT, int KS, int NF>
-__global__ void __launch_bounds__(GramCfg<BT>::kThreads, 1) gram_kernel(const GramArgs args) {
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Which 8x8 accumulator sub-tiles of a warp's 64x32 patch are live for a segment.  Bit (i*4+j):
+// rows row0+8i.., columns col0+8j...  Dead sub-tiles: rows/columns past the end of the augmented
+// library, and (diagonal block pairs) sub-tiles strictly above the diagonal.
+__device__ __forceinline__ uint32_t live_mask(int row0, int col0, int rows_valid, int cols_valid, bool same,
+                                              int jmax) {
+    uint32_t mask = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = row0 + 8 * i, c = col0 + 8 * j;
+            const bool live = (j < jmax) && (r < rows_valid) && (c < cols_valid) && !(same && c > r + 7);
+            mask |= (live ? 1u : 0u) << (i * 4 + j);
+        }
+    return mask;
+}
+
+// The per-thread share of building the next stage's Theta tiles: NJ columns (library terms), each a
+// product of NF staged values per sample.
+template <int NJ, int NF>
+struct BuildJobs {
+    int off[NJ][NF];  // offset of factor d at sample 0 inside a raw-sample slot
+    int str[NJ][NF];  // per-sample stride of factor d
+    int dst[NJ];      // offset of the column inside a Theta stage
+    int s0;           // first sample this thread builds
+};
+
+// One stage (16 samples): 4 k-steps of {build SPK samples of the next stage, load fragments, DMMAs}.
+// Straight-line code so that ptxas can software-pipeline the shared-memory loads under the DMMAs.
+template <int BT, int NF, bool FULL, bool SAME>
+__device__ __forceinline__ void stage_body(double (&acc)[8][4][2], const double* __restrict__ pa,
+                                           const double* __restrict__ pb, uint32_t mask, uint32_t colmask,
+                                           const double* __restrict__ v, double* __restrict__ tnext,
+                                           const BuildJobs<GramCfg<BT>::kJobs, NF>& jb) {
+    constexpr int LDT = GramCfg<BT>::kPitch;
+    constexpr int NJ = (BT == 128) ? 1 : (SAME ? 1 : 2);   // columns this thread builds
+    constexpr int SPK = (BT == 128 && SAME) ? 2 : 4;        // samples per column per k-step
+#pragma unroll
+    for (int kk = 0; kk < kKS / 4; ++kk) {
+        double fv[NJ][SPK][NF];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+#pragma unroll
+            for (int q = 0; q < SPK; ++q)
+#pragma unroll
+                for (int d = 0; d < NF; ++d) fv[j][q][d] = v[jb.off[j][d] + (jb.s0 + kk * SPK + q) * jb.str[j][d]];
+        double a[8], b[4];
+        if (FULL) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = pa[kk * 4 * LDT + 8 * i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = pb[kk * 4 * LDT + 8 * j];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = ((mask >> (4 * i)) & 0xF) ? pa[kk * 4 * LDT + 8 * i] : 0.0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = ((colmask >> j) & 1) ? pb[kk * 4 * LDT + 8 * j] : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+#pragma unroll
+            for (int q = 0; q < SPK; ++q) {
+                double p = fv[j][q][0];
+#pragma unroll
+                for (int d = 1; d < NF; ++d) p *= fv[j][q][d];
+                tnext[jb.dst[j] + (jb.s0 + kk * SPK + q) * LDT] = p;
+            }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (FULL)
+                    dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                else if ((mask >> (i * 4 + j)) & 1)
+                    dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            }
+    }
+}
+
+template <int BT, int NF>
+__global__ void __launch_bounds__(GramCfg<BT>::kThreads, GramCfg<BT>::kMinBlocks) gram_kernel(const GramArgs args) {
     using Cfg = GramCfg<BT>;
-    constexpr int NT = Cfg::kThreads;
     constexpr int LDT = Cfg::kPitch;
+    constexpr int KS = kKS;
+    constexpr int NJ = Cfg::kJobs;
     extern __shared__ __align__(128) unsigned char smem_raw[];
 
     const int n = args.n, n_t = args.n_t;
-    const size_t xbytes = (size_t)KS * n * sizeof(double);
-    const size_t ybytes = (size_t)KS * n_t * sizeof(double);
-    size_t vbytes = (xbytes + ybytes + 127) & ~size_t(127);
+    const uint32_t xbytes = (uint32_t)(KS * n * sizeof(double));
+    const uint32_t ybytes = (uint32_t)(KS * n_t * sizeof(double));
+    const int vdoubles = (int)(gram_vbytes(n, n_t) / sizeof(double));
 
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);  // 2 mbarriers
-    unsigned char* vbase = smem_raw + 128;
-    double* theta = reinterpret_cast<double*>(vbase + 2 * vbytes);  // [buf 2][tile 2][KS][LDT]
-    constexpr int kTileDoubles = KS * LDT;
+    uint64_t* vfull = reinterpret_cast<uint64_t*>(smem_raw);  // [kNVS] raw samples landed
+    uint64_t* tfull = vfull + kNVS;                           // [kNTS] Theta stage built by all warps
+    double* vring = reinterpret_cast<double*>(smem_raw + 128);
+    double* tring = vring + kNVS * vdoubles;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int wm = warp / Cfg::kWarpsPerDim;
-    const int wn = warp % Cfg::kWarpsPerDim;
+    const int g = lane >> 2, t = lane & 3;
 
     if (tid == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
+        for (int i = 0; i < kNVS; ++i) mbar_init(&vfull[i], 1);
+        for (int i = 0; i < kNTS; ++i) mbar_init(&tfull[i], Cfg::kWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    for (int e = tid; e < kNVS * kVX; e += Cfg::kThreads) {
+        const int w = e % kVX;
+        vring[(e / kVX) * vdoubles + w] = (w < kVZero) ? 1.0 : 0.0;
+    }
     __syncthreads();
-    uint32_t phase0 = 0, phase1 = 0;  // parity to wait for on each buffer's barrier
 
     const int64_t nstages_total = (args.m + KS - 1) / KS;
     const int seg_begin = args.cta_seg_begin[blockIdx.x];
     const int seg_end = args.cta_seg_begin[blockIdx.x + 1];
+    int total = 0;
+    for (int sg = seg_begin; sg < seg_end; ++sg) total += (int)(args.segs[sg].stage_end - args.segs[sg].stage_begin);
+    if (total == 0) return;
 
+    // ---- raw-sample cursor (warp 0): TMA tiles in item order, across segment boundaries -------------
+    int tma_seg = seg_begin;
+    int64_t tma_stage = args.segs[seg_begin].stage_begin, tma_seg_end = args.segs[seg_begin].stage_end;
+    int tma_item = 0;
+    uint32_t ragged_slots = 0;  // slots whose ones column currently carries zero padding
+    auto request_samples = [&]() {  // all lanes of warp 0; requests the raw samples of item `tma_item`
+        if (tma_item >= total) return;
+        const int slot = tma_item % kNVS;
+        double* dst = vring + slot * vdoubles;
+        const int64_t s0 = tma_stage * KS;
+        const bool full = (tma_stage + 1 < nstages_total) || (args.m - s0 == KS);
+        if (full) {
+            if ((ragged_slots >> slot) & 1) {  // restore the ones column a ragged stage overwrote
+                if (lane < KS) dst[kVOnes + lane] = 1.0;
+                ragged_slots &= ~(1u << slot);
+                __syncwarp();
+            }
+            if (lane == 0) {
+                mbar_expect_tx(&vfull[slot], xbytes + ybytes);
+                bulk_g2s(dst + kVX, args.X + s0 * n, xbytes, &vfull[slot]);
+                bulk_g2s(dst + kVX + KS * n, args.Y + s0 * n_t, ybytes, &vfull[slot]);
+            }
+        } else {
+            // ragged last stage of the shard: plain loads with zero fill (a bulk copy needs 16-byte
+            // multiples), ones[s] = 0 for the padding samples
+            const int valid = (int)(args.m - s0);
+            for (int e = lane; e < KS * n; e += 32) dst[kVX + e] = (e < valid * n) ? args.X[s0 * n + e] : 0.0;
+            for (int e = lane; e < KS * n_t; e += 32)
+                dst[kVX + KS * n + e] = (e < valid * n_t) ? args.Y[s0 * n_t + e] : 0.0;
+            if (lane < KS) dst[kVOnes + lane] = (lane < valid) ? 1.0 : 0.0;
+            ragged_slots |= 1u << slot;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&vfull[slot]);
+        }
+        ++tma_item;
+        if (++tma_stage == tma_seg_end && ++tma_seg < seg_end) {
+            tma_stage = args.segs[tma_seg].stage_begin;
+            tma_seg_end = args.segs[tma_seg].stage_end;
+        }
+    };
+
+    // ---- build cursor: this thread's share of the Theta tiles of the NEXT item -----------------------
+    int bseg = seg_begin;
+    int64_t bstage = 0, bseg_end = 0;
+    bool bsame = false;
+    BuildJobs<NJ, NF> jb;
+    auto load_jobs = [&]() {
+        const GramSegment seg = args.segs[bseg];
+        bstage = seg.stage_begin;
+        bseg_end = seg.stage_end;
+        bsame = (seg.bi == seg.bj);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            int tile, col;
+            if (BT == 128) {  // 256 threads: one column each; diagonal pairs split the samples instead
+                tile = bsame ? 0 : tid / BT;
+                col = tid % BT;
+                jb.s0 = bsame ? (tid / BT) * (KS / 2) : 0;
+            } else {  // 64 threads: column tid of the block row (job 0) and of the block column (job 1)
+                tile = j;
+                col = tid;
+                jb.s0 = 0;
+            }
+            jb.dst[j] = tile * KS * LDT + col;
+            const int term = (tile == 0 ? seg.bi : seg.bj) * BT + col;
+            const uint4 q = *reinterpret_cast<const uint4*>(args.factors + (size_t)term * kMaxFactors);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+            const bool dead = term >= args.kaug;
+#pragma unroll
+            for (int d = 0; d < NF; ++d) {
+                const uint32_t f = (w[d >> 1] >> (16 * (d & 1))) & 0xFFFFu;
+                int off = kVOnes, str = 1;  // missing factor -> ones[s]
+                if (f != kNoFactor) {
+                    const bool isy = (f & kFactorIsY) != 0;
+                    off = isy ? kVX + KS * n + (int)(f & 0x7FFF) : kVX + (int)f;
+                    str = isy ? n_t : n;
+                }
+                if (dead) off = kVZero, str = 0;  // padding row of the library -> 0.0
+                jb.off[j][d] = off;
+                jb.str[j][d] = str;
+            }
+        }
+    };
+    auto advance_build = [&]() {
+        if (++bstage == bseg_end && ++bseg < seg_end) load_jobs();
+    };
+
+    // ---- prologue: request the first raw tiles, build Theta(0) completely -----------------------------
+    if (warp == 0) {
+        request_samples();
+        request_samples();
+        request_samples();
+    }
+    load_jobs();
+    mbar_wait(&vfull[0], 0);
+    {
+        const int njobs = (BT == 128 || bsame) ? 1 : 2;
+        const int cnt = (BT == 128 && bsame) ? KS / 2 : KS;
+        for (int j = 0; j < njobs; ++j)
+            for (int s = jb.s0; s < jb.s0 + cnt; ++s) {
+                double p = vring[jb.off[j][0] + s * jb.str[j][0]];
+#pragma unroll
+                for (int d = 1; d < NF; ++d) p *= vring[jb.off[j][d] + s * jb.str[j][d]];
+                tring[jb.dst[j] + s * LDT] = p;
+            }
+    }
+    advance_build();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tfull[0]);
+
+    // ---- MMA cursor --------------------------------------------------------------------------------------
+    // warp -> (wm, wn): permuted so that on diagonal block pairs, where sub-tiles above the diagonal
+    // are skipped, the live work is balanced over the four SM sub-partitions.
+    int wm, wn;
+    if (BT == 128) {
+        wm = (0x4B >> warp) & 1;  // warps 0..7 -> (1,0)(1,1)(0,0)(1,2)(0,2)(0,3)(1,3)(0,1)
+        wn = (0x7E84 >> (2 * warp)) & 3;
+    } else {
+        wm = 0;
+        wn = warp;
+    }
+    int item = 0;
     for (int sg = seg_begin; sg < seg_end; ++sg) {
         const GramSegment seg = args.segs[sg];
         const bool same = (seg.bi == seg.bj);
-        const int nslots = same ? BT : 2 * BT;
-        const int groups = NT / nslots;
-        const int spg = KS / groups;  // samples per thread per stage
-        const int slot = tid % nslots;
-        const int grp = tid / nslots;
-        const int tile = slot / BT;   // 0 -> block row bi, 1 -> block column bj
-        const int col = slot % BT;
-        const int term = (tile == 0 ? seg.bi : seg.bj) * BT + col;
+        const int rows_valid = min(BT, args.kaug - seg.bi * BT);
+        const int cols_valid = min(BT, args.kaug - seg.bj * BT);
+        // block rows with at most 64 live rows: lay all warps side by side (64 x 16 patches)
+        const bool flat = (BT == 128) && (rows_valid <= 64);
+        const int row0 = flat ? 0 : wm * 64;
+        const int col0 = flat ? warp * 16 : wn * 32;
+        const uint32_t mask = live_mask(row0, col0, rows_valid, cols_valid, same, flat ? 2 : 4);
+        uint32_t colmask = mask | (mask >> 16);
+        colmask |= colmask >> 8;
+        colmask = (colmask | (colmask >> 4)) & 0xFu;  // bit j: some live sub-tile in column group j
+        // one code variant per segment; `any_full` must be CTA-uniform because it decides nothing but speed
+        const bool full_mask = (mask == 0xFFFFFFFFu);
 
-        // factor list of this thread's term: up to NF offsets into the staged sample row
-        uint16_t fac[NF];
-        {
-            const uint16_t* f = args.factors + (size_t)term * kMaxFactors;
+        double acc[8][4][2];
 #pragma unroll
-            for (int d = 0; d < NF; ++d) fac[d] = f[d];
-        }
-        const double init = (term < args.kaug) ? 1.0 : 0.0;
-
-        double acc[4][4][2];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 8; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-        // ---- staging helpers --------------------------------------------------------------
-        auto load_stage = [&](int64_t st, int buf) {
-            const int64_t s0 = st * KS;
-            unsigned char* dst = vbase + (size_t)buf * vbytes;
-            const bool full = (st + 1 < nstages_total) || (args.m - s0 == KS);
-            if (full) {
-                if (tid == 0) {
-                    mbar_expect_tx(&bars[buf], (uint32_t)(xbytes + ybytes));
-                    bulk_g2s(dst, args.X + s0 * n, (uint32_t)xbytes, &bars[buf]);
-                    bulk_g2s(dst + xbytes, args.Y + s0 * n_t, (uint32_t)ybytes, &bars[buf]);
-                }
-            } else {
-                // ragged last stage of the shard: plain loads, zero fill (TMA needs 16-byte multiples)
-                const int valid = (int)(args.m - s0);
-                double* vx = reinterpret_cast<double*>(dst);
-                double* vy = reinterpret_cast<double*>(dst + xbytes);
-                for (int e = tid; e < KS * n; e += NT) vx[e] = (e < valid * n) ? args.X[s0 * n + e] : 0.0;
-                for (int e = tid; e < KS * n_t; e += NT) vy[e] = (e < valid * n_t) ? args.Y[s0 * n_t + e] : 0.0;
-            }
-        };
-        auto wait_stage = [&](int64_t st, int buf) {
-            const int64_t s0 = st * KS;
-            const bool full = (st + 1 < nstages_total) || (args.m - s0 == KS);
-            if (full) {
-                if (buf == 0) {
-                    mbar_wait(&bars[0], phase0);
-                    phase0 ^= 1;
-                } else {
-                    mbar_wait(&bars[1], phase1);
-                    phase1 ^= 1;
-                }
-            }
-        };
-        auto build_stage = [&](int64_t st, int buf) {
-            const int64_t s0 = st * KS;
-            const int valid = (int)min((int64_t)KS, args.m - s0);
-            const double* vx = reinterpret_cast<const double*>(vbase + (size_t)buf * vbytes);
-            const double* vy = reinterpret_cast<const double*>(vbase + (size_t)buf * vbytes + xbytes);
-            double* out = theta + (size_t)(buf * 2 + tile) * kTileDoubles + col;
-            for (int q = 0; q < spg; ++q) {
-                const int s = grp * spg + q;
-                double p = (s < valid) ? init : 0.0;
-#pragma unroll
-                for (int d = 0; d < NF; ++d) {
-                    const uint16_t f = fac[d];
-                    if (f != kNoFactor) {
-                        const double v = (f & kFactorIsY) ? vy[s * n_t + (f & 0x7FFF)] : vx[s * n + f];
-                        p *= v;
-                    }
-                }
-                out[s * LDT] = p;
-            }
-        };
-        auto mma_stage = [&](int buf) {
-            const double* tI = theta + (size_t)(buf * 2 + 0) * kTileDoubles;
-            const double* tJ = same ? tI : theta + (size_t)(buf * 2 + 1) * kTileDoubles;
-            const double* pa = tI + (lane & 3) * LDT + wm * 32 + (lane >> 2);
-            const double* pb = tJ + (lane & 3) * LDT + wn * 32 + (lane >> 2);
-#pragma unroll
-            for (int kk = 0; kk < KS / 4; ++kk) {
-                double a[4], b[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) a[i] = pa[kk * 4 * LDT + 8 * i];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) b[j] = pb[kk * 4 * LDT + 8 * j];
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-            }
-        };
+        const int nst = (int)(seg.stage_end - seg.stage_begin);
+        for (int q = 0; q < nst; ++q, ++item) {
+            const int tslot = item % kNTS;
+            mbar_wait(&tfull[tslot], (uint32_t)((item / kNTS) & 1));
+            // the raw tile of item+3 reuses the slot of item, which build(item) finished reading
+            if (warp == 0) request_samples();
+            const bool have_next = (item + 1 < total);
+            if (have_next) mbar_wait(&vfull[(item + 1) % kNVS], (uint32_t)(((item + 1) / kNVS) & 1));
 
-        // ---- software pipeline: TMA two stages ahead, Theta build one stage ahead of the MMAs --
-        const int64_t b = seg.stage_begin, e = seg.stage_end;
-        __syncthreads();  // previous segment's smem fully consumed
-        load_stage(b, 0);
-        if (b + 1 < e) load_stage(b + 1, 1);
-        wait_stage(b, 0);
-        __syncthreads();  // manual (ragged) loads visible
-        build_stage(b, 0);
-        __syncthreads();
-        for (int64_t st = b; st < e; ++st) {
-            const int cur = (int)((st - b) & 1);
-            if (st + 2 < e) load_stage(st + 2, cur);  // v buffer `cur` was consumed by build(st)
-            if (st + 1 < e) {
-                wait_stage(st + 1, cur ^ 1);
-                build_stage(st + 1, cur ^ 1);
+            const double* tI = tring + tslot * Cfg::kStageDoubles;
+            const double* tJ = same ? tI : tI + KS * LDT;
+            const double* pa = tI + t * LDT + row0 + g;
+            const double* pb = tJ + t * LDT + col0 + g;
+            const double* v = vring + ((item + 1) % kNVS) * vdoubles;       // raw samples of the next item
+            double* tnext = tring + ((item + 1) % kNTS) * Cfg::kStageDoubles;  // (stale but harmless at the end)
+            // the build share belongs to the NEXT item, whose pair may differ from this segment's
+            if (bsame) {
+                if (full_mask) stage_body<BT, NF, true, true>(acc, pa, pb, mask, colmask, v, tnext, jb);
+                else stage_body<BT, NF, false, true>(acc, pa, pb, mask, colmask, v, tnext, jb);
+            } else {
+                if (full_mask) stage_body<BT, NF, true, false>(acc, pa, pb, mask, colmask, v, tnext, jb);
+                else stage_body<BT, NF, false, false>(acc, pa, pb, mask, colmask, v, tnext, jb);
             }
-            mma_stage(cur);
-            __syncthreads();
+            if (have_next) {
+                advance_build();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tfull[(item + 1) % kNTS]);
+            }
         }
 
-        // ---- flush the 32x32 warp patch to this segment's partial-tile slot -----------------
+        // flush the live sub-tiles to this segment's partial-tile slot (row-major BT x BT)
         double* out = args.partials + (size_t)seg.slot * BT * BT;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int row = wm * 32 + 8 * i + (lane >> 2);
+        for (int i = 0; i < 8; ++i) {
+            const int row = row0 + 8 * i + g;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int c = wn * 32 + 8 * j + 2 * (lane & 3);
-                *reinterpret_cast<double2*>(out + (size_t)row * BT + c) = make_double2(acc[i][j][0], acc[i][j][1]);
+                const int c = col0 + 8 * j + 2 * t;
+                if ((mask >> (i * 4 + j)) & 1)
+                    *reinterpret_cast<double2*>(out + (size_t)row * BT + c) = make_double2(acc[i][j][0], acc[i][j][1]);
             }
         }
     }
@@ -377,9 +543,9 @@ void build_gram_plan(GramPlan& plan, int kaug, int64_t m, int nctas, int bt, int
 // ---------------------------------------------------------------------------------------------
 // Host side: launch
 // ---------------------------------------------------------------------------------------------
-template <int BT, int KS, int NF>
+template <int BT, int NF>
 static int launch_gram(ddb_ctx* ctx, const GramArgs& args, size_t smem) {
-    auto kern = gram_kernel<BT, KS, NF>;
+    auto kern = gram_kernel<BT, NF>;
     DDB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<ctx->plan.nctas, GramCfg<BT>::kThreads, smem, ctx->stream>>>(args);
     DDB_CUDA_TRY(cudaGetLastError());
@@ -416,12 +582,12 @@ int gram_run(ddb_ctx* ctx, double* dPacked) {
     const int k = ctx->k, n = ctx->n, n_t = ctx->n_t;
     const int kaug = k + n_t;
     const int bt = (kaug <= 64) ? 64 : 128;
-    const int ks = 16;
+    const int ks = kKS;
     if (n >= 0x7FFF || n_t >= 0x7FFF) {
         set_error("ddb_gram: more than 32766 states/targets are not supported by the monomial evaluator");
         return DDB_UNSUPPORTED;
     }
-    const size_t smem = gram_smem_bytes(bt, ks, n, n_t);
+    const size_t smem = (bt == 64) ? gram_smem_bytes<64>(n, n_t) : gram_smem_bytes<128>(n, n_t);
     if (smem > 227 * 1024) {
         set_error("ddb_gram: n + n_t = %d is too wide to stage a sample tile in shared memory (%zu bytes)", n + n_t,
                   smem);
@@ -431,9 +597,30 @@ int gram_run(ddb_ctx* ctx, double* dPacked) {
         set_error("ddb_gram: device data pointers must be 16-byte aligned");
         return DDB_INVALID_ARG;
     }
+    // persistent grid: CTAs per SM from the occupancy calculator (1 for BT=128, up to 3 for BT=64)
+    int occ = 1;
+    {
+        const bool sd = ctx->max_degree <= 2;
+        cudaError_t oe;
+        if (bt == 64) {
+            auto kern = sd ? gram_kernel<64, 2> : gram_kernel<64, 8>;
+            DDB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, GramCfg<64>::kThreads, smem);
+        } else {
+            auto kern = sd ? gram_kernel<128, 2> : gram_kernel<128, 8>;
+            DDB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, GramCfg<128>::kThreads, smem);
+        }
+        DDB_CUDA_TRY(oe);
+        if (occ < 1) {
+            set_error("ddb_gram: kernel does not fit on an SM (smem %zu bytes)", smem);
+            return DDB_UNSUPPORTED;
+        }
+    }
+    const int nctas = ctx->sm_count * occ;
     // plan (cached per shape)
-    if (ctx->plan_m != ctx->m || ctx->plan_kaug != kaug || ctx->plan.bt != bt) {
-        build_gram_plan(ctx->plan, kaug, ctx->m, ctx->sm_count, bt, ks);
+    if (ctx->plan_m != ctx->m || ctx->plan_kaug != kaug || ctx->plan.bt != bt || ctx->plan.nctas != nctas) {
+        build_gram_plan(ctx->plan, kaug, ctx->m, nctas, bt, ks);
         const GramPlan& pl = ctx->plan;
         std::vector<int2> pairs;
         for (int bi = 0; bi < pl.nblk; ++bi)
@@ -484,9 +671,9 @@ int gram_run(ddb_ctx* ctx, double* dPacked) {
     const bool small_deg = ctx->max_degree <= 2;
     int st;
     if (bt == 64)
-        st = small_deg ? launch_gram<64, 16, 2>(ctx, args, smem) : launch_gram<64, 16, 8>(ctx, args, smem);
+        st = small_deg ? launch_gram<64, 2>(ctx, args, smem) : launch_gram<64, 8>(ctx, args, smem);
     else
-        st = small_deg ? launch_gram<128, 16, 2>(ctx, args, smem) : launch_gram<128, 16, 8>(ctx, args, smem);
+        st = small_deg ? launch_gram<128, 2>(ctx, args, smem) : launch_gram<128, 8>(ctx, args, smem);
     DDB_TRY(st);
     dim3 rgrid(pl.npairs, (bt * bt + 255) / 256);
     gram_reduce_kernel<<<rgrid, 256, 0, ctx->stream>>>(ctx->d_partials.as<double>(),

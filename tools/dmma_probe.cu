@@ -1,0 +1,209 @@
+// Probe: what limits DMMA issue on sm_100a?  (A) register-only DMMA with 32 accumulators at 1..4 warps
+// per SM sub-partition; (B) the Gram kernel's MMA loop in isolation (fragments from shared memory,
+// no barriers, no Theta build).
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1);} } while (0)
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <int NA, int NB>
+__global__ void __launch_bounds__(512) k_reg(double* out, int iters) {
+    double a[NA], b[NB], acc[NA][NB][2];
+    for (int i = 0; i < NA; ++i) a[i] = 1e-3 * (threadIdx.x + i);
+    for (int j = 0; j < NB; ++j) b[j] = 1e-3 * (threadIdx.x - j);
+    for (int i = 0; i < NA; ++i) for (int j = 0; j < NB; ++j) acc[i][j][0] = acc[i][j][1] = 0;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < NA; ++i)
+#pragma unroll
+            for (int j = 0; j < NB; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+    double s = 0;
+    for (int i = 0; i < NA; ++i) for (int j = 0; j < NB; ++j) s += acc[i][j][0] + acc[i][j][1];
+    if (s == 12345.678) out[0] = s;
+}
+
+// (B) 8 warps, 64x32 patch each, 128x128 block, fragments from a [16][132] sample-major tile pair
+template <int WARPS, int NA, int NB>
+__global__ void __launch_bounds__(WARPS * 32) k_smem(double* out, int stages) {
+    constexpr int LDT = 132, KS = 16;
+    __shared__ double tile[1][2 * KS * LDT];
+    for (int e = threadIdx.x; e < 2 * KS * LDT; e += blockDim.x) (&tile[0][0])[e] = 1e-3 * e;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const int wm = warp & 1, wn = (warp >> 1) & 3;
+    double acc[NA][NB][2];
+    for (int i = 0; i < NA; ++i) for (int j = 0; j < NB; ++j) acc[i][j][0] = acc[i][j][1] = 0;
+    for (int st = 0; st < stages; ++st) {
+        const double* tI = tile[0] + ((st & 1) ? 0 : 0);
+        const double* tJ = tI + KS * LDT;
+        const double* pa = tI + t * LDT + wm * (8 * NA) + g;
+        const double* pb = tJ + t * LDT + wn * (8 * NB) + g;
+#pragma unroll
+        for (int kk = 0; kk < KS / 4; ++kk) {
+            double a[NA], b[NB];
+#pragma unroll
+            for (int i = 0; i < NA; ++i) a[i] = pa[kk * 4 * LDT + 8 * i];
+#pragma unroll
+            for (int j = 0; j < NB; ++j) b[j] = pb[kk * 4 * LDT + 8 * j];
+#pragma unroll
+            for (int i = 0; i < NA; ++i)
+#pragma unroll
+                for (int j = 0; j < NB; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+    }
+    double s = 0;
+    for (int i = 0; i < NA; ++i) for (int j = 0; j < NB; ++j) s += acc[i][j][0] + acc[i][j][1];
+    if (s == 12345.678) out[0] = s;
+}
+
+
+// (C) as (B) plus ND independent DMULs per k-step (MODE 0: spread, one group per k-step; MODE 1: all 4*ND at stage start)
+template <int ND, int MODE>
+__global__ void __launch_bounds__(256) k_mix(double* out, int stages, double mulv) {
+    constexpr int LDT = 132, KS = 16, NA = 8, NB = 4;
+    __shared__ double tile[2 * KS * LDT];
+    for (int e = threadIdx.x; e < 2 * KS * LDT; e += blockDim.x) tile[e] = 1e-3 * e;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const int wm = warp & 1, wn = (warp >> 1) & 3;
+    double acc[NA][NB][2];
+    for (int i = 0; i < NA; ++i) for (int j = 0; j < NB; ++j) acc[i][j][0] = acc[i][j][1] = 0;
+    double prod[ND > 0 ? ND : 1];
+    for (int d = 0; d < ND; ++d) prod[d] = 1.0 + 1e-9 * (threadIdx.x + d);
+    for (int st = 0; st < stages; ++st) {
+        const double* tI = tile;
+        const double* tJ = tI + KS * LDT;
+        const double* pa = tI + t * LDT + wm * (8 * NA) + g;
+        const double* pb = tJ + t * LDT + wn * (8 * NB) + g;
+        if (MODE == 1) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int d = 0; d < ND; ++d) asm volatile("mul.rn.f64 %0, %0, %1;" : "+d"(prod[d]) : "d"(mulv));
+        }
+#pragma unroll
+        for (int kk = 0; kk < KS / 4; ++kk) {
+            if (MODE == 0) {
+#pragma unroll
+                for (int d = 0; d < ND; ++d) asm volatile("mul.rn.f64 %0, %0, %1;" : "+d"(prod[d]) : "d"(mulv));
+            }
+            double a[NA], b[NB];
+#pragma unroll
+            for (int i = 0; i < NA; ++i) a[i] = pa[kk * 4 * LDT + 8 * i];
+#pragma unroll
+            for (int j = 0; j < NB; ++j) b[j] = pb[kk * 4 * LDT + 8 * j];
+#pragma unroll
+            for (int i = 0; i < NA; ++i)
+#pragma unroll
+                for (int j = 0; j < NB; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+    }
+    double s = 0;
+    for (int i = 0; i < NA; ++i) for (int j = 0; j < NB; ++j) s += acc[i][j][0] + acc[i][j][1];
+    for (int d = 0; d < ND; ++d) s += prod[d];
+    if (s == 12345.678) out[0] = s;
+}
+
+
+// (D) as (B) plus one CTA-wide synchronisation per stage: SYNC 1 = __syncthreads, 2 = mbarrier arrive (one lane per
+// warp) + try_wait.parity, 3 = mbarrier arrive + test_wait spin
+__device__ __forceinline__ unsigned s32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+template <int SYNC>
+__global__ void __launch_bounds__(256) k_sync(double* out, int stages) {
+    constexpr int LDT = 132, KS = 16, NA = 8, NB = 4;
+    __shared__ double tile[2 * KS * LDT];
+    __shared__ unsigned long long bar[2];
+    for (int e = threadIdx.x; e < 2 * KS * LDT; e += blockDim.x) tile[e] = 1e-3 * e;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(&bar[0])), "r"(8));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(&bar[1])), "r"(8));
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const int wm = warp & 1, wn = (warp >> 1) & 3;
+    double acc[NA][NB][2];
+    for (int i = 0; i < NA; ++i) for (int j = 0; j < NB; ++j) acc[i][j][0] = acc[i][j][1] = 0;
+    for (int st = 0; st < stages; ++st) {
+        const double* pa = tile + t * LDT + wm * (8 * NA) + g;
+        const double* pb = tile + KS * LDT + t * LDT + wn * (8 * NB) + g;
+#pragma unroll
+        for (int kk = 0; kk < KS / 4; ++kk) {
+            double a[NA], b[NB];
+#pragma unroll
+            for (int i = 0; i < NA; ++i) a[i] = pa[kk * 4 * LDT + 8 * i];
+#pragma unroll
+            for (int j = 0; j < NB; ++j) b[j] = pb[kk * 4 * LDT + 8 * j];
+#pragma unroll
+            for (int i = 0; i < NA; ++i)
+#pragma unroll
+                for (int j = 0; j < NB; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+        if (SYNC == 1) __syncthreads();
+        if (SYNC == 2 || SYNC == 3) {
+            unsigned long long* b = &bar[st & 1];
+            const unsigned parity = (st >> 1) & 1;
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(b)) : "memory");
+            unsigned done;
+            do {
+                if (SYNC == 2)
+                    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(s32(b)), "r"(parity) : "memory");
+                else
+                    asm volatile("{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(s32(b)), "r"(parity) : "memory");
+            } while (!done);
+        }
+    }
+    double s = 0;
+    for (int i = 0; i < NA; ++i) for (int j = 0; j < NB; ++j) s += acc[i][j][0] + acc[i][j][1];
+    if (s == 12345.678) out[0] = s;
+}
+
+template <class F> float time_ms(F f) {
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    f(); f(); CK(cudaDeviceSynchronize());
+    float best = 1e30f;
+    for (int r = 0; r < 3; ++r) { CK(cudaEventRecord(e0)); f(); CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); best = ms < best ? ms : best; }
+    return best;
+}
+
+int main() {
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
+    const int sms = prop.multiProcessorCount;
+    double* out; CK(cudaMalloc(&out, 1024));
+    printf("{");
+    const int iters = 2000;
+    for (int warps : {4, 8, 12, 16}) {
+        float ms = time_ms([&] { k_reg<4, 4><<<sms, warps * 32>>>(out, iters); });
+        printf("\"reg_4x4_w%d\": %.2f, ", warps, 512.0 * 16 * iters * sms * warps / ms * 1e-9);
+    }
+    for (int warps : {4, 8}) {
+        float ms = time_ms([&] { k_reg<8, 4><<<sms, warps * 32>>>(out, iters); });
+        printf("\"reg_8x4_w%d\": %.2f, ", warps, 512.0 * 32 * iters * sms * warps / ms * 1e-9);
+    }
+    const int stages = 4000;
+    { float ms = time_ms([&] { k_smem<8, 8, 4><<<sms, 256>>>(out, stages); });
+      printf("\"smem_8w_64x32\": %.2f, ", 512.0 * 32 * 4 * stages * sms * 8 / ms * 1e-9); }
+    { float ms = time_ms([&] { k_smem<16, 4, 4><<<sms, 512>>>(out, stages); });
+      printf("\"smem_16w_32x32\": %.2f, ", 512.0 * 16 * 4 * stages * sms * 16 / ms * 1e-9); }
+    { float ms = time_ms([&] { k_smem<4, 8, 4><<<sms, 128>>>(out, stages); });
+      printf("\"smem_4w_64x32\": %.2f, ", 512.0 * 32 * 4 * stages * sms * 4 / ms * 1e-9); }
+    { float ms = time_ms([&] { k_smem<4, 8, 4><<<sms * 2, 128>>>(out, stages); });
+      printf("\"smem_4w_64x32_2cta\": %.2f, ", 512.0 * 32 * 4 * stages * sms * 2 * 4 / ms * 1e-9); }
+    { float ms = time_ms([&] { k_mix<1, 0><<<sms, 256>>>(out, stages, 1.0000001); }); printf("\"mix_1_spread\": %.2f, ", 512.0 * 32 * 4 * stages * sms * 8 / ms * 1e-9); }
+    { float ms = time_ms([&] { k_mix<2, 0><<<sms, 256>>>(out, stages, 1.0000001); }); printf("\"mix_2_spread\": %.2f, ", 512.0 * 32 * 4 * stages * sms * 8 / ms * 1e-9); }
+    { float ms = time_ms([&] { k_mix<4, 0><<<sms, 256>>>(out, stages, 1.0000001); }); printf("\"mix_4_spread\": %.2f, ", 512.0 * 32 * 4 * stages * sms * 8 / ms * 1e-9); }
+    { float ms = time_ms([&] { k_mix<8, 0><<<sms, 256>>>(out, stages, 1.0000001); }); printf("\"mix_8_spread\": %.2f, ", 512.0 * 32 * 4 * stages * sms * 8 / ms * 1e-9); }
+    { float ms = time_ms([&] { k_mix<4, 1><<<sms, 256>>>(out, stages, 1.0000001); }); printf("\"mix_16_front\": %.2f, ", 512.0 * 32 * 4 * stages * sms * 8 / ms * 1e-9); }
+    { float ms = time_ms([&] { k_mix<8, 1><<<sms, 256>>>(out, stages, 1.0000001); }); printf("\"mix_32_front\": %.2f, ", 512.0 * 32 * 4 * stages * sms * 8 / ms * 1e-9); }
+    { float ms = time_ms([&] { k_sync<0><<<sms, 256>>>(out, stages); }); printf("\"sync_none\": %.2f, ", 512.0 * 32 * 4 * stages * sms * 8 / ms * 1e-9); }
+    { float ms = time_ms([&] { k_sync<1><<<sms, 256>>>(out, stages); }); printf("\"sync_bar\": %.2f, ", 512.0 * 32 * 4 * stages * sms * 8 / ms * 1e-9); }
+    { float ms = time_ms([&] { k_sync<2><<<sms, 256>>>(out, stages); }); printf("\"sync_mbar_try\": %.2f, ", 512.0 * 32 * 4 * stages * sms * 8 / ms * 1e-9); }
+    { float ms = time_ms([&] { k_sync<3><<<sms, 256>>>(out, stages); }); printf("\"sync_mbar_test\": %.2f, ", 512.0 * 32 * 4 * stages * sms * 8 / ms * 1e-9); }
+    printf("\"sms\": %d}\n", sms);
+    return 0;
+}
