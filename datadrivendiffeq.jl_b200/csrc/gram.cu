@@ -89,8 +89,9 @@ struct GramArgs {
 };
 
 constexpr int kKS = 16;   // samples per stage
-constexpr int kNVS = 3;   // depth of the raw-sample (TMA) ring
-constexpr int kNTS = 2;   // depth of the Theta-tile ring
+constexpr int kNVS = 4;   // depth of the raw-sample (TMA) ring
+constexpr int kNTS = 4;   // depth of the Theta-tile ring (tiles are built kAhead stages before use)
+constexpr int kAhead = 2; // build distance: barrier arrivals precede the matching wait by a whole stage
 template <int BT>
 struct GramCfg {
     static constexpr int kWarpCols = BT / 32;            // warp grid (BT/64) x (BT/32), warp patch 64 x 32
@@ -122,24 +123,25 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// Which 8x8 accumulator sub-tiles of a warp's 64x32 patch are live for a segment.  Bit (i*4+j):
-// rows row0+8i.., columns col0+8j...  Dead sub-tiles: rows/columns past the end of the augmented
-// library, and (diagonal block pairs) sub-tiles strictly above the diagonal.
-__device__ __forceinline__ uint32_t live_mask(int row0, int col0, int rows_valid, int cols_valid, bool same,
-                                              int jmax) {
-    uint32_t mask = 0;
-#pragma unroll
+// Static shapes of live 8x8 accumulator sub-tiles inside a warp's 64x32 patch (bit i*4+j: rows 8i..,
+// columns 8j..).  A diagonal block pair only needs sub-tiles on or below the diagonal; with 64x32
+// patches every warp's patch is one of: entirely below (FULL), straddling with offset 0 (sub-tile
+// column j live for rows i >= j), straddling with offset -4 (live for i >= j + 4), or entirely above
+// (EMPTY).  FLAT is the 64x16 patch used when a block row has at most 64 live rows.
+constexpr uint32_t shape_mask(int d, int jmax) {  // live iff j <= i + d and j < jmax
+    uint32_t m = 0;
     for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int r = row0 + 8 * i, c = col0 + 8 * j;
-            const bool live = (j < jmax) && (r < rows_valid) && (c < cols_valid) && !(same && c > r + 7);
-            mask |= (live ? 1u : 0u) << (i * 4 + j);
-        }
-    return mask;
+        for (int j = 0; j < 4; ++j)
+            if (j <= i + d && j < jmax) m |= 1u << (i * 4 + j);
+    return m;
 }
+constexpr uint32_t kShapeFull = shape_mask(8, 4);
+constexpr uint32_t kShapeDiag0 = shape_mask(0, 4);
+constexpr uint32_t kShapeDiagM4 = shape_mask(-4, 4);
+constexpr uint32_t kShapeEmpty = 0u;
+constexpr uint32_t kShapeFlat = shape_mask(8, 2);
 
-// The per-thread share of building the next stage's Theta tiles: NJ columns (library terms), each a
+// The per-thread share of building a later stage's Theta tiles: NJ columns (library terms), each a
 // product of NF staged values per sample.
 template <int NJ, int NF>
 struct BuildJobs {
@@ -149,12 +151,13 @@ struct BuildJobs {
     int s0;           // first sample this thread builds
 };
 
-// One stage (16 samples): 4 k-steps of {build SPK samples of the next stage, load fragments, DMMAs}.
-// Straight-line code so that ptxas can software-pipeline the shared-memory loads under the DMMAs.
-template <int BT, int NF, bool FULL, bool SAME>
+// One stage (16 samples): 4 k-steps of {build SPK samples of a later stage, load fragments, DMMAs}.
+// Straight-line code (the live sub-tiles are a template parameter) so that ptxas can software-
+// pipeline the shared-memory loads under the DMMAs and no DMMA is predicated.
+template <int BT, int NF, uint32_t MASK, bool SAME>
 __device__ __forceinline__ void stage_body(double (&acc)[8][4][2], const double* __restrict__ pa,
-                                           const double* __restrict__ pb, uint32_t mask, uint32_t colmask,
-                                           const double* __restrict__ v, double* __restrict__ tnext,
+                                           const double* __restrict__ pb, const double* __restrict__ v,
+                                           double* __restrict__ tnext,
                                            const BuildJobs<GramCfg<BT>::kJobs, NF>& jb) {
     constexpr int LDT = GramCfg<BT>::kPitch;
     constexpr int NJ = (BT == 128) ? 1 : (SAME ? 1 : 2);   // columns this thread builds
@@ -169,17 +172,12 @@ __device__ __forceinline__ void stage_body(double (&acc)[8][4][2], const double*
 #pragma unroll
                 for (int d = 0; d < NF; ++d) fv[j][q][d] = v[jb.off[j][d] + (jb.s0 + kk * SPK + q) * jb.str[j][d]];
         double a[8], b[4];
-        if (FULL) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) a[i] = pa[kk * 4 * LDT + 8 * i];
+        for (int i = 0; i < 8; ++i)
+            if ((MASK >> (4 * i)) & 0xFu) a[i] = pa[kk * 4 * LDT + 8 * i];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = pb[kk * 4 * LDT + 8 * j];
-        } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) a[i] = ((mask >> (4 * i)) & 0xF) ? pa[kk * 4 * LDT + 8 * i] : 0.0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = ((colmask >> j) & 1) ? pb[kk * 4 * LDT + 8 * j] : 0.0;
-        }
+        for (int j = 0; j < 4; ++j)
+            if ((MASK >> j) & 0x11111111u) b[j] = pb[kk * 4 * LDT + 8 * j];
 #pragma unroll
         for (int j = 0; j < NJ; ++j)
 #pragma unroll
@@ -192,12 +190,8 @@ __device__ __forceinline__ void stage_body(double (&acc)[8][4][2], const double*
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (FULL)
-                    dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-                else if ((mask >> (i * 4 + j)) & 1)
-                    dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-            }
+            for (int j = 0; j < 4; ++j)
+                if ((MASK >> (i * 4 + j)) & 1u) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
 }
 
@@ -249,7 +243,7 @@ __global__ void __launch_bounds__(GramCfg<BT>::kThreads, GramCfg<BT>::kMinBlocks
     uint32_t ragged_slots = 0;  // slots whose ones column currently carries zero padding
     auto request_samples = [&]() {  // all lanes of warp 0; requests the raw samples of item `tma_item`
         if (tma_item >= total) return;
-        const int slot = tma_item % kNVS;
+        const int slot = tma_item & (kNVS - 1);
         double* dst = vring + slot * vdoubles;
         const int64_t s0 = tma_stage * KS;
         const bool full = (tma_stage + 1 < nstages_total) || (args.m - s0 == KS);
@@ -329,28 +323,30 @@ __global__ void __launch_bounds__(GramCfg<BT>::kThreads, GramCfg<BT>::kMinBlocks
         if (++bstage == bseg_end && ++bseg < seg_end) load_jobs();
     };
 
-    // ---- prologue: request the first raw tiles, build Theta(0) completely -----------------------------
+    // ---- prologue: request the first raw tiles, build Theta(0..kAhead-1) completely -------------------
     if (warp == 0) {
-        request_samples();
-        request_samples();
-        request_samples();
+#pragma unroll 1
+        for (int i = 0; i < kNVS; ++i) request_samples();
     }
     load_jobs();
-    mbar_wait(&vfull[0], 0);
-    {
+#pragma unroll 1
+    for (int it = 0; it < kAhead && it < total; ++it) {
+        mbar_wait(&vfull[it], 0);
+        const double* v = vring + it * vdoubles;
+        double* dstt = tring + it * Cfg::kStageDoubles;
         const int njobs = (BT == 128 || bsame) ? 1 : 2;
         const int cnt = (BT == 128 && bsame) ? KS / 2 : KS;
         for (int j = 0; j < njobs; ++j)
             for (int s = jb.s0; s < jb.s0 + cnt; ++s) {
-                double p = vring[jb.off[j][0] + s * jb.str[j][0]];
+                double p = v[jb.off[j][0] + s * jb.str[j][0]];
 #pragma unroll
-                for (int d = 1; d < NF; ++d) p *= vring[jb.off[j][d] + s * jb.str[j][d]];
-                tring[jb.dst[j] + s * LDT] = p;
+                for (int d = 1; d < NF; ++d) p *= v[jb.off[j][d] + s * jb.str[j][d]];
+                dstt[jb.dst[j] + s * LDT] = p;
             }
+        advance_build();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tfull[it]);
     }
-    advance_build();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&tfull[0]);
 
     // ---- MMA cursor --------------------------------------------------------------------------------------
     // warp -> (wm, wn): permuted so that on diagonal block pairs, where sub-tiles above the diagonal
@@ -368,17 +364,22 @@ __global__ void __launch_bounds__(GramCfg<BT>::kThreads, GramCfg<BT>::kMinBlocks
         const GramSegment seg = args.segs[sg];
         const bool same = (seg.bi == seg.bj);
         const int rows_valid = min(BT, args.kaug - seg.bi * BT);
-        const int cols_valid = min(BT, args.kaug - seg.bj * BT);
         // block rows with at most 64 live rows: lay all warps side by side (64 x 16 patches)
         const bool flat = (BT == 128) && (rows_valid <= 64);
         const int row0 = flat ? 0 : wm * 64;
         const int col0 = flat ? warp * 16 : wn * 32;
-        const uint32_t mask = live_mask(row0, col0, rows_valid, cols_valid, same, flat ? 2 : 4);
-        uint32_t colmask = mask | (mask >> 16);
-        colmask |= colmask >> 8;
-        colmask = (colmask | (colmask >> 4)) & 0xFu;  // bit j: some live sub-tile in column group j
-        // one code variant per segment; `any_full` must be CTA-uniform because it decides nothing but speed
-        const bool full_mask = (mask == 0xFFFFFFFFu);
+        // shape of this warp's patch: 0 full, 1 diagonal offset 0, 2 diagonal offset -4, 3 empty, 4 flat
+        int shape = 0;
+        if (flat) shape = 4;
+        else if (same) {
+            const int d = (row0 - col0) / 8;
+            shape = (d >= 3) ? 0 : (d == 0 ? 1 : (d == -4 ? 2 : 3));
+        }
+        const uint32_t mask = shape == 0 ? kShapeFull
+                              : shape == 1 ? kShapeDiag0
+                              : shape == 2 ? kShapeDiagM4
+                              : shape == 3 ? kShapeEmpty
+                                           : kShapeFlat;
 
         double acc[8][4][2];
 #pragma unroll
@@ -388,31 +389,38 @@ __global__ void __launch_bounds__(GramCfg<BT>::kThreads, GramCfg<BT>::kMinBlocks
 
         const int nst = (int)(seg.stage_end - seg.stage_begin);
         for (int q = 0; q < nst; ++q, ++item) {
-            const int tslot = item % kNTS;
+            const int tslot = item & (kNTS - 1);
             mbar_wait(&tfull[tslot], (uint32_t)((item / kNTS) & 1));
-            // the raw tile of item+3 reuses the slot of item, which build(item) finished reading
+            // the raw tile of item+kNVS reuses the slot of item, which build(item) finished reading
             if (warp == 0) request_samples();
-            const bool have_next = (item + 1 < total);
-            if (have_next) mbar_wait(&vfull[(item + 1) % kNVS], (uint32_t)(((item + 1) / kNVS) & 1));
+            const int nitem = item + kAhead;  // the item whose Theta tiles this stage builds
+            const bool have_next = (nitem < total);
+            if (have_next) mbar_wait(&vfull[nitem & (kNVS - 1)], (uint32_t)((nitem / kNVS) & 1));
 
             const double* tI = tring + tslot * Cfg::kStageDoubles;
             const double* tJ = same ? tI : tI + KS * LDT;
             const double* pa = tI + t * LDT + row0 + g;
             const double* pb = tJ + t * LDT + col0 + g;
-            const double* v = vring + ((item + 1) % kNVS) * vdoubles;       // raw samples of the next item
-            double* tnext = tring + ((item + 1) % kNTS) * Cfg::kStageDoubles;  // (stale but harmless at the end)
-            // the build share belongs to the NEXT item, whose pair may differ from this segment's
-            if (bsame) {
-                if (full_mask) stage_body<BT, NF, true, true>(acc, pa, pb, mask, colmask, v, tnext, jb);
-                else stage_body<BT, NF, false, true>(acc, pa, pb, mask, colmask, v, tnext, jb);
-            } else {
-                if (full_mask) stage_body<BT, NF, true, false>(acc, pa, pb, mask, colmask, v, tnext, jb);
-                else stage_body<BT, NF, false, false>(acc, pa, pb, mask, colmask, v, tnext, jb);
+            const double* v = vring + (nitem & (kNVS - 1)) * vdoubles;          // raw samples of item+kAhead
+            double* tnext = tring + (nitem & (kNTS - 1)) * Cfg::kStageDoubles;  // (stale but harmless at the end)
+            // the build share belongs to a LATER item, whose pair may differ from this segment's
+#define DDB_STAGE(M)                                                                     \
+    do {                                                                                 \
+        if (bsame) stage_body<BT, NF, M, true>(acc, pa, pb, v, tnext, jb);               \
+        else stage_body<BT, NF, M, false>(acc, pa, pb, v, tnext, jb);                    \
+    } while (0)
+            switch (shape) {
+                case 0: DDB_STAGE(kShapeFull); break;
+                case 1: DDB_STAGE(kShapeDiag0); break;
+                case 2: DDB_STAGE(kShapeDiagM4); break;
+                case 3: DDB_STAGE(kShapeEmpty); break;
+                default: DDB_STAGE(kShapeFlat); break;
             }
+#undef DDB_STAGE
             if (have_next) {
                 advance_build();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tfull[(item + 1) % kNTS]);
+                if (lane == 0) mbar_arrive(&tfull[nitem & (kNTS - 1)]);
             }
         }
 
@@ -472,51 +480,86 @@ void build_gram_plan(GramPlan& plan, int kaug, int64_t m, int nctas, int bt, int
     plan.nstages = (m + ks - 1) / ks;
     const int64_t ns = plan.nstages;
 
+    // pair index -> (bi, bj), row-major over the lower triangle, and its cost per stage relative to a
+    // full block pair (tensor-pipe time of the slowest SM sub-partition, see the shapes in the kernel)
+    std::vector<std::pair<int, int>> pairs;
+    std::vector<double> cost;
+    for (int bi = 0; bi < plan.nblk; ++bi)
+        for (int bj = 0; bj <= bi; ++bj) {
+            pairs.push_back({bi, bj});
+            const int rows_valid = std::min(bt, kaug - bi * bt);
+            double c = 1.0;
+            if (bt == 128 && rows_valid <= 64) c = 0.53;       // flat: 64 x 128 patch
+            else if (bi == bj) c = (bt == 128) ? 0.60 : 0.85;  // diagonal: 36/64 (+ build) resp. 26/32
+            cost.push_back(c);
+        }
+
     struct Tmp {
         int cta, pair;
         int64_t b, e;
     };
     std::vector<Tmp> tmp;
-    const int q = plan.npairs / nctas, r = plan.npairs % nctas;
-    // full rounds: every CTA owns one block pair and all CTAs walk the sample stream in lockstep,
-    // so each X/Y tile is fetched from HBM once and served to the other CTAs from L2.
-    for (int c = 0; c < nctas; ++c)
-        for (int i = 0; i < q; ++i) tmp.push_back({c, i * nctas + c, 0, ns});
-    // remainder pairs: the (pair, stage) space is cut into nctas equal contiguous ranges.
-    if (r > 0 && ns > 0) {
-        const int64_t total = (int64_t)r * ns;
-        for (int c = 0; c < nctas; ++c) {
-            int64_t lo = total * c / nctas, hi = total * (c + 1) / nctas;
-            while (lo < hi) {
-                const int pr = (int)(lo / ns);
-                const int64_t sb = lo % ns;
-                const int64_t se = std::min<int64_t>(ns, sb + (hi - lo));
-                tmp.push_back({c, q * nctas + pr, sb, se});
-                lo += se - sb;
+    double total = 0.0;
+    for (double c : cost) total += c * (double)ns;
+    const double budget = total / nctas;
+    std::vector<double> used(nctas, 0.0);
+    // (1) whole pairs, most expensive first, dealt round-robin to CTAs that can still fit one: these
+    // CTAs walk the sample stream in lockstep, so each X/Y tile is fetched from HBM once and served
+    // to the other CTAs from L2.
+    std::vector<int> order(plan.npairs);
+    for (int p = 0; p < plan.npairs; ++p) order[p] = p;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+    std::vector<int> rest;
+    int next_cta = 0;
+    for (int p : order) {
+        const double need = cost[p] * (double)ns;
+        int found = -1;
+        for (int probe = 0; probe < nctas && ns > 0; ++probe) {
+            const int c = (next_cta + probe) % nctas;
+            if (used[c] + need <= budget * (1.0 + 1e-9)) {
+                found = c;
+                break;
+            }
+        }
+        if (found < 0) {
+            rest.push_back(p);
+            continue;
+        }
+        tmp.push_back({found, p, 0, ns});
+        used[found] += need;
+        next_cta = (found + 1) % nctas;
+    }
+    // (2) the remaining (pair, stage) stream fills every CTA up to the common budget, contiguously.
+    {
+        int c = 0;
+        for (int p : rest) {
+            int64_t st = 0;
+            while (st < ns) {
+                while (c < nctas - 1 && budget - used[c] < 0.5 * cost[p]) ++c;
+                int64_t take = (c == nctas - 1) ? (ns - st) : (int64_t)((budget - used[c]) / cost[p] + 0.5);
+                take = std::max<int64_t>(1, std::min<int64_t>(take, ns - st));
+                tmp.push_back({c, p, st, st + take});
+                used[c] += cost[p] * (double)take;
+                st += take;
             }
         }
     }
     // slots: grouped by pair, inside a pair ordered by CTA (fixed summation order)
-    std::vector<int> order(tmp.size());
-    for (size_t i = 0; i < tmp.size(); ++i) order[i] = (int)i;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+    std::vector<int> sorder(tmp.size());
+    for (size_t i = 0; i < tmp.size(); ++i) sorder[i] = (int)i;
+    std::stable_sort(sorder.begin(), sorder.end(), [&](int a, int b) {
         if (tmp[a].pair != tmp[b].pair) return tmp[a].pair < tmp[b].pair;
         if (tmp[a].cta != tmp[b].cta) return tmp[a].cta < tmp[b].cta;
         return tmp[a].b < tmp[b].b;
     });
     std::vector<int> slot_of(tmp.size());
     plan.pair_slot_begin.assign(plan.npairs + 1, 0);
-    for (size_t i = 0; i < order.size(); ++i) {
-        slot_of[order[i]] = (int)i;
-        plan.pair_slot_begin[tmp[order[i]].pair + 1]++;
+    for (size_t i = 0; i < sorder.size(); ++i) {
+        slot_of[sorder[i]] = (int)i;
+        plan.pair_slot_begin[tmp[sorder[i]].pair + 1]++;
     }
     for (int p = 0; p < plan.npairs; ++p) plan.pair_slot_begin[p + 1] += plan.pair_slot_begin[p];
     plan.nslots = (int)tmp.size();
-
-    // pair index -> (bi, bj), row-major over the lower triangle
-    std::vector<std::pair<int, int>> pairs;
-    for (int bi = 0; bi < plan.nblk; ++bi)
-        for (int bj = 0; bj <= bi; ++bj) pairs.push_back({bi, bj});
 
     // segments sorted by CTA (tmp is already CTA-major for the full rounds, then CTA-major again for
     // the remainder -> stable sort by CTA keeps full rounds first)
