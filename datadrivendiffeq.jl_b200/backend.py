@@ -1,0 +1,221 @@
+"""Thin object wrapper over the C ABI (``include/ddb.h``): one ``Context`` per GPU.
+
+Everything numerical happens in ``libddb200.so``; this module only marshals NumPy arrays / device
+pointers.  Layout conventions are Julia's: matrices are column-major, states ``n x m`` with one
+sample per column.  A NumPy array of shape ``(n, m)`` in Fortran order has exactly that layout.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+
+ALG = {"STLSQ": 0, "ADMM": 1, "SR3": 2}
+PROX = {"SoftThreshold": 0, "HardThreshold": 1, "ClippedAbsoluteDeviation": 2}
+SELECTOR = {"bic": 0, "aic": 1, "aicc": 2, "rss": 3}
+
+
+def _f(a: np.ndarray) -> np.ndarray:
+    """Column-major float64 view/copy of a 2-D array."""
+    return np.asfortranarray(a, dtype=np.float64)
+
+
+@dataclass
+class SweepOutput:
+    """What ``ddb_select`` returns (un-rounded ``SparseRegressionResult`` content + paths)."""
+
+    coefficients: np.ndarray  # n_t x k
+    lambda_opt: np.ndarray  # n_t
+    iterations: np.ndarray  # n_t  (total iteration counter, solver.jl:117)
+    rss: np.ndarray  # n_t  rss of the selected model
+    dof: np.ndarray  # n_t
+    flags: np.ndarray  # n_t
+    support_path: Optional[np.ndarray] = None  # n_t x L x k bool
+    coef_path: Optional[np.ndarray] = None  # n_t x L x k
+    iters_path: Optional[np.ndarray] = None  # n_t x L
+
+
+class Context:
+    """One ``ddb_ctx`` (one GPU).  Raises ``DDBError`` on any failure; there is no CPU fallback."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load()
+        self._ctx = C.c_void_p()
+        _lib.check(self._lib.ddb_ctx_create(int(device), C.byref(self._ctx)))
+        self.device = int(device)
+        self.n = self.k = self.n_t = 0
+        self.m = 0
+        self._keep = []  # keeps arrays the library retains pointers to alive
+
+    # -- lifetime ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            self._lib.ddb_ctx_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- library ----------------------------------------------------------------------------
+    def set_library(self, exponents: np.ndarray):
+        """``exponents``: integer array (n x k), entry [i, j] = power of state i in term j."""
+        e = np.asfortranarray(exponents, dtype=np.uint8)
+        self.n, self.k = e.shape
+        _lib.check(self._lib.ddb_set_library_monomial(self._ctx, self.n, self.k, _lib.ptr(e)))
+
+    # -- data -------------------------------------------------------------------------------
+    def upload(self, X: np.ndarray, Y: np.ndarray):
+        X, Y = _f(X), _f(Y)
+        assert X.shape[0] == self.n and X.shape[1] == Y.shape[1]
+        self.n_t, self.m = Y.shape
+        _lib.check(self._lib.ddb_upload(self._ctx, _lib.ptr(X), _lib.ptr(Y), self.n_t, self.m))
+
+    def upload_raw(self, x_ptr: int, y_ptr: int, n_t: int, m: int):
+        """Host pointers (e.g. pinned torch tensors) of column-major X (n x m) and Y (n_t x m)."""
+        self.n_t, self.m = int(n_t), int(m)
+        _lib.check(self._lib.ddb_upload(self._ctx, C.c_void_p(x_ptr), C.c_void_p(y_ptr), self.n_t, self.m))
+
+    def bind_device(self, dX: int, dY: int, n_t: int, m: int):
+        """Device pointers (e.g. ``torch.Tensor.data_ptr()``); the caller keeps the memory alive."""
+        self.n_t, self.m = int(n_t), int(m)
+        _lib.check(self._lib.ddb_bind_device(self._ctx, C.c_void_p(dX), C.c_void_p(dY), self.n_t, self.m))
+
+    def generate(self, system_id: int, n_states: int, m: int, first_sample: int = 0, seed: int = 0, noise_std: float = 0.0):
+        _lib.check(
+            self._lib.ddb_generate(self._ctx, system_id, n_states, int(m), int(first_sample), int(seed), float(noise_std))
+        )
+        self.n_t = 3 if system_id == 0 else n_states
+        self.m = int(m)
+
+    def download_data(self):
+        X = np.empty((self.n, self.m), order="F")
+        Y = np.empty((self.n_t, self.m), order="F")
+        _lib.check(self._lib.ddb_download_data(self._ctx, _lib.ptr(X), _lib.ptr(Y)))
+        return X, Y
+
+    # -- normal-equation blocks -------------------------------------------------------------
+    def gram_count(self) -> int:
+        return int(self._lib.ddb_gram_count(self._ctx))
+
+    def gram(self, d_packed: Optional[int] = None):
+        _lib.check(self._lib.ddb_gram(self._ctx, C.c_void_p(d_packed) if d_packed else None))
+
+    def gram_buffer(self) -> int:
+        p = C.c_void_p()
+        _lib.check(self._lib.ddb_gram_buffer(self._ctx, C.byref(p)))
+        return int(p.value)
+
+    def gram_download(self):
+        G = np.empty((self.k, self.k), order="F")
+        R = np.empty((self.k, self.n_t), order="F")
+        yy = np.empty(self.n_t)
+        _lib.check(self._lib.ddb_gram_download(self._ctx, _lib.ptr(G), _lib.ptr(R), _lib.ptr(yy)))
+        return G, R, yy
+
+    def gram_upload(self, G: np.ndarray, R: np.ndarray, yy: np.ndarray):
+        G, R, yy = _f(G), _f(R), np.ascontiguousarray(yy, dtype=np.float64)
+        self.n_t = R.shape[1]
+        _lib.check(self._lib.ddb_gram_upload(self._ctx, _lib.ptr(G), _lib.ptr(R), _lib.ptr(yy), self.n_t))
+
+    # -- sweep ------------------------------------------------------------------------------
+    @staticmethod
+    def make_params(algorithm="STLSQ", rho=0.0, proximal="SoftThreshold", selector="bic", maxiters=100,
+                    abstol=math.sqrt(np.finfo(float).eps), reltol=math.sqrt(np.finfo(float).eps),
+                    cad_rho=float("nan")) -> _lib.SweepParams:
+        p = _lib.SweepParams()
+        p.algorithm = ALG[algorithm]
+        p.proximal = PROX[proximal]
+        p.selector = SELECTOR[selector]
+        p.maxiters = int(maxiters)
+        p.abstol = float(abstol)
+        p.reltol = float(reltol)
+        p.rho = float(rho)
+        p.cad_rho = float(cad_rho)
+        return p
+
+    def sweep(self, params: _lib.SweepParams, lambdas: Sequence[float], m_total: Optional[int] = None):
+        lam = np.ascontiguousarray(lambdas, dtype=np.float64)
+        self._L = lam.size
+        _lib.check(self._lib.ddb_sweep(self._ctx, C.byref(params), _lib.ptr(lam), lam.size, int(m_total or self.m)))
+
+    def rss_count(self) -> int:
+        return int(self._lib.ddb_rss_count(self._ctx))
+
+    def rss(self, d_rss: Optional[int] = None):
+        _lib.check(self._lib.ddb_rss(self._ctx, C.c_void_p(d_rss) if d_rss else None))
+
+    def rss_buffer(self) -> int:
+        p = C.c_void_p()
+        _lib.check(self._lib.ddb_rss_buffer(self._ctx, C.byref(p)))
+        return int(p.value)
+
+    def select(self, paths: bool = False) -> SweepOutput:
+        n_t, k, L = self.n_t, self.k, self._L
+        W = (k + 31) // 32
+        coef = np.zeros((n_t, k), order="F")
+        lam = np.zeros(n_t)
+        iters = np.zeros(n_t, dtype=np.int32)
+        rss = np.zeros(n_t)
+        dof = np.zeros(n_t, dtype=np.int32)
+        flags = np.zeros(n_t, dtype=np.int32)
+        sp = np.zeros((n_t, L, W), dtype=np.uint32) if paths else None
+        cp = np.zeros((n_t, L, k)) if paths else None
+        ip = np.zeros((n_t, L), dtype=np.int32) if paths else None
+        _lib.check(
+            self._lib.ddb_select(self._ctx, _lib.ptr(coef), _lib.ptr(lam), _lib.ptr(iters), _lib.ptr(rss), _lib.ptr(dof),
+                                 _lib.ptr(sp), _lib.ptr(cp), _lib.ptr(ip), _lib.ptr(flags))
+        )
+        out = SweepOutput(np.ascontiguousarray(coef), lam, iters, rss, dof, flags)
+        if paths:
+            bits = np.unpackbits(sp.view(np.uint8).reshape(n_t, L, W * 4), axis=-1, bitorder="little")
+            out.support_path = bits[:, :, :k].astype(bool)
+            out.coef_path = cp
+            out.iters_path = ip
+        return out
+
+    def solve_sparse(self, X: np.ndarray, Y: np.ndarray, params: _lib.SweepParams, lambdas: Sequence[float]) -> SweepOutput:
+        """The one-call host path ``ddb_solve_sparse`` (host buffers in and out)."""
+        X, Y = _f(X), _f(Y)
+        lam_in = np.ascontiguousarray(lambdas, dtype=np.float64)
+        n_t, m = Y.shape
+        self.n_t, self.m, self._L = n_t, m, lam_in.size
+        coef = np.zeros((n_t, self.k), order="F")
+        lam = np.zeros(n_t)
+        iters = np.zeros(n_t, dtype=np.int32)
+        rss = np.zeros(n_t)
+        dof = np.zeros(n_t, dtype=np.int32)
+        _lib.check(
+            self._lib.ddb_solve_sparse(self._ctx, _lib.ptr(X), _lib.ptr(Y), n_t, m, C.byref(params), _lib.ptr(lam_in),
+                                       lam_in.size, _lib.ptr(coef), _lib.ptr(lam), _lib.ptr(iters), _lib.ptr(rss),
+                                       _lib.ptr(dof), None)
+        )
+        return SweepOutput(np.ascontiguousarray(coef), lam, iters, rss, dof, np.zeros(n_t, dtype=np.int32))
+
+    # -- introspection ----------------------------------------------------------------------
+    def timings(self) -> dict:
+        t = _lib.Timings()
+        _lib.check(self._lib.ddb_get_timings(self._ctx, C.byref(t)))
+        return t.as_dict()
+
+    def stream(self) -> int:
+        p = C.c_void_p()
+        _lib.check(self._lib.ddb_get_stream(self._ctx, C.byref(p)))
+        return int(p.value or 0)
+
+    def synchronize(self):
+        _lib.check(self._lib.ddb_synchronize(self._ctx))

@@ -67,6 +67,8 @@ struct GramPlan {
 
 void build_gram_plan(GramPlan& plan, int kaug, int64_t m, int nctas, int bt, int ks);
 
+struct SweepState;
+
 }  // namespace ddb
 
 struct ddb_ctx {
@@ -98,7 +100,7 @@ struct ddb_ctx {
     bool have_gram = false;
 
     // sweep / rss / select state lives in sweep.cu
-    struct SweepState* sweep = nullptr;
+    ddb::SweepState* sweep = nullptr;
 
     ddb_timings timings = {};
 };

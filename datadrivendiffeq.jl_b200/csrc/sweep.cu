@@ -1,16 +1,1253 @@
+// Thresholded sweep of DataDrivenSparse on the normal-equation blocks, device resident.
+//
+// Replaces `SparseLinearSolver` (reference lib/DataDrivenSparse/src/solver.jl:72-118) and the
+// `init_cache` / `step!` methods of STLSQ (algorithms/STLSQ.jl:81-140), ADMM (ADMM.jl:68-121, skinny
+// branch) and SR3 (SR3.jl:98-141) for ALL targets at once, working on G = Theta Theta', R = Theta Y'
+// instead of Theta itself:
+//   * the system matrix A = G (+ rho I) is equilibrated, As = D^-1 A D^-1 with D = sqrt(diag A)
+//     (mandatory: cond(G) = cond(Theta)^2); thresholds act on the un-scaled
+//     coefficients;
+//   * one blocked Cholesky of As is shared by every target (initial full least squares of STLSQ,
+//     every iteration of ADMM / SR3);
+//   * STLSQ's per-target active-set solves run in ONE persistent kernel, one CTA per target, looping
+//     thresholds and inner iterations on the device: the masked system is gathered into shared
+//     memory, factorised and solved there, the support is re-thresholded, convergence and the
+//     candidate bookkeeping for the selector are done in place.  Supports with more than
+//     kSmallMax active terms fall back to a batched blocked Cholesky in global memory;
+//   * every distinct (support, coefficients) a target visits is recorded as a sparse candidate; a
+//     second streaming pass over the samples (rss.cu) scores them exactly and `select` replays the
+//     selector along the recorded step sequence (solver.jl:100-107, incl. `<=` and `j == 1`).
 #include "common.cuh"
+#include "sweep.cuh"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
 namespace ddb {
-void sweep_free(ddb_ctx* ctx) { (void)ctx; }
+
+// ---------------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum(double v, double* red) {  // blockDim.x multiple of 32, <= 1024
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    double s = 0.0;
+    for (int w = 0; w < nw; ++w) s += red[w];  // fixed order: deterministic
+    return s;
 }
+__device__ __forceinline__ int block_sum_int(int v, int* red) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    int s = 0;
+    for (int w = 0; w < nw; ++w) s += red[w];
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// preparation: A = G + rho I, equilibrate, scaled right-hand sides
+// ---------------------------------------------------------------------------------------------
+__global__ void prep_diag_kernel(const double* __restrict__ G, int k, double rho, double* __restrict__ dinv) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= k) return;
+    const double a = G[(size_t)j * k + j] + rho;
+    dinv[j] = (a > 0.0) ? 1.0 / sqrt(a) : 0.0;  // an identically-zero library term gets coefficient 0
+}
+__global__ void prep_scale_kernel(const double* __restrict__ G, int k, double rho, const double* __restrict__ dinv,
+                                  double* __restrict__ As) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (size_t)k * k) return;
+    const int i = (int)(e / k), j = (int)(e % k);
+    double a = G[e] + (i == j ? rho : 0.0);
+    a *= dinv[i] * dinv[j];
+    if (i == j && dinv[i] == 0.0) a = 1.0;
+    As[e] = a;
+}
+// rs[e][j] = dinv[j] * R[j + k e]
+__global__ void prep_rhs_kernel(const double* __restrict__ R, int k, int n_t, const double* __restrict__ dinv,
+                                double* __restrict__ rs) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (size_t)k * n_t) return;
+    rs[e] = R[e] * dinv[e % k];
+}
+
+// ---------------------------------------------------------------------------------------------
+// batched blocked Cholesky, row-major lower triangle in place (leading dimension ld)
+//   matrix b lives at base + b * stride; its order is na[b] (or `na_all` when na == nullptr).
+// ---------------------------------------------------------------------------------------------
+constexpr int kNB = 32;
+
+__global__ void __launch_bounds__(256) chol_panel_kernel(double* base, size_t stride, int ld, const int* na_arr,
+                                                         int na_all, int j0, int* fail) {
+    const int b = blockIdx.x;
+    const int na = na_arr ? na_arr[b] : na_all;
+    if (j0 >= na) return;
+    double* A = base + (size_t)b * stride;
+    const int nb = min(kNB, na - j0);
+    __shared__ double D[kNB][kNB + 1];
+    const int tid = threadIdx.x;
+    for (int e = tid; e < kNB * kNB; e += blockDim.x) {
+        const int i = e / kNB, j = e % kNB;
+        double v = (i == j) ? 1.0 : 0.0;
+        if (i < nb && j < nb && j <= i) v = A[(size_t)(j0 + i) * ld + j0 + j];
+        D[i][j] = v;
+    }
+    __syncthreads();
+    for (int c = 0; c < nb; ++c) {
+        if (tid == 0) {
+            const double d = D[c][c];
+            if (!(d > 0.0)) {
+                atomicExch(&fail[b], 1);
+                D[c][c] = 1.0;  // keep going with a harmless pivot; the flag invalidates the result
+            } else {
+                D[c][c] = sqrt(d);
+            }
+        }
+        __syncthreads();
+        if (tid > c && tid < nb) D[tid][c] /= D[c][c];
+        __syncthreads();
+        for (int e = tid; e < nb * nb; e += blockDim.x) {
+            const int i = e / nb, j = e % nb;
+            if (j > c && i >= j) D[i][j] -= D[i][c] * D[j][c];
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < nb * nb; e += blockDim.x) {
+        const int i = e / nb, j = e % nb;
+        if (j <= i) A[(size_t)(j0 + i) * ld + j0 + j] = D[i][j];
+    }
+    // panel below the diagonal block: row i <- row i * L_jj^-T  (forward substitution per row)
+    for (int i = j0 + nb + tid; i < na; i += blockDim.x) {
+        double a[kNB];
+        double* row = A + (size_t)i * ld + j0;
+#pragma unroll
+        for (int c = 0; c < kNB; ++c) a[c] = (c < nb) ? row[c] : 0.0;
+#pragma unroll
+        for (int c = 0; c < kNB; ++c) {
+            double s = a[c];
+#pragma unroll
+            for (int t = 0; t < c; ++t) s -= a[t] * D[c][t];
+            a[c] = s / D[c][c];
+        }
+#pragma unroll
+        for (int c = 0; c < kNB; ++c)
+            if (c < nb) row[c] = a[c];
+    }
+}
+
+// trailing update C[i][j] -= sum_t P[i][t] P[j][t] for i >= j >= j0 + kNB, 64x64 tiles, lower tiles only
+__global__ void __launch_bounds__(256) chol_update_kernel(double* base, size_t stride, int ld, const int* na_arr,
+                                                          int na_all, int j0) {
+    const int b = blockIdx.z;
+    const int na = na_arr ? na_arr[b] : na_all;
+    const int t0 = j0 + kNB;
+    if (t0 >= na) return;
+    const int ti = blockIdx.y, tj = blockIdx.x;
+    if (tj > ti) return;
+    const int r0 = t0 + ti * 64, c0 = t0 + tj * 64;
+    if (r0 >= na) return;
+    double* A = base + (size_t)b * stride;
+    __shared__ double Pi[64][kNB + 1];
+    __shared__ double Pj[64][kNB + 1];
+    const int tid = threadIdx.x;
+    for (int e = tid; e < 64 * kNB; e += blockDim.x) {
+        const int r = e / kNB, c = e % kNB;
+        Pi[r][c] = (r0 + r < na) ? A[(size_t)(r0 + r) * ld + j0 + c] : 0.0;
+        Pj[r][c] = (c0 + r < na) ? A[(size_t)(c0 + r) * ld + j0 + c] : 0.0;
+    }
+    __syncthreads();
+    const int tr = (tid / 16) * 4, tc = (tid % 16) * 4;
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+#pragma unroll 8
+    for (int t = 0; t < kNB; ++t) {
+        double a[4], bb[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = Pi[tr + i][t];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bb[j] = Pj[tc + j][t];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], bb[j], acc[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = r0 + tr + i, c = c0 + tc + j;
+            if (r < na && c <= r) A[(size_t)r * ld + c] -= acc[i][j];
+        }
+}
+
+static int chol_batched(ddb_ctx* ctx, double* base, size_t stride, int ld, const int* d_na, int na_max, int batch,
+                        int* d_fail, int* launches) {
+    for (int j0 = 0; j0 < na_max; j0 += kNB) {
+        chol_panel_kernel<<<batch, 256, 0, ctx->stream>>>(base, stride, ld, d_na, na_max, j0, d_fail);
+        ++*launches;
+        const int rem = na_max - j0 - kNB;
+        if (rem > 0) {
+            const int T = (rem + 63) / 64;
+            dim3 grid(T, T, batch);
+            chol_update_kernel<<<grid, 256, 0, ctx->stream>>>(base, stride, ld, d_na, na_max, j0);
+            ++*launches;
+        }
+    }
+    DDB_CUDA_TRY(cudaGetLastError());
+    return DDB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// triangular solves with a row-major lower factor: z <- L^-T L^-1 z, one CTA per (rhs, matrix)
+//   z vector b, r lives at zbase + (b * nrhs + r) * zstride
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) chol_solve_kernel(const double* Lbase, size_t lstride, int ld,
+                                                         const int* na_arr, int na_all, double* zbase, size_t zstride,
+                                                         int nrhs, const int* active_matrix, const int* zmap) {
+    const int b = blockIdx.y, r = blockIdx.x;
+    if (active_matrix && !active_matrix[b]) return;
+    const int na = na_arr ? na_arr[b] : na_all;
+    if (na <= 0) return;
+    const double* L = Lbase + (size_t)b * lstride;
+    double* zg = zbase + ((size_t)(zmap ? zmap[b] : b) * nrhs + r) * zstride;
+    extern __shared__ double sm[];
+    double* z = sm;                 // na
+    double* blk = sm + ((na + 31) / 32) * 32;  // 32 x 33
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < na; i += blockDim.x) z[i] = zg[i];
+    __syncthreads();
+    // forward: L y = z
+    for (int j0 = 0; j0 < na; j0 += 32) {
+        const int nb = min(32, na - j0);
+        for (int e = tid; e < 32 * 32; e += blockDim.x) {
+            const int i = e / 32, j = e % 32;
+            blk[i * 33 + j] = (i < nb && j <= i) ? L[(size_t)(j0 + i) * ld + j0 + j] : (i == j ? 1.0 : 0.0);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            double zi = (lane < nb) ? z[j0 + lane] : 0.0;
+            for (int c = 0; c < nb; ++c) {
+                const double zc = __shfl_sync(0xffffffffu, zi, c) / blk[c * 33 + c];
+                if (lane == c) zi = zc;
+                if (lane > c) zi -= blk[lane * 33 + c] * zc;
+            }
+            if (lane < nb) z[j0 + lane] = zi;
+        }
+        __syncthreads();
+        for (int i = j0 + nb + tid; i < na; i += blockDim.x) {
+            const double* row = L + (size_t)i * ld + j0;
+            double s = 0.0;
+            for (int c = 0; c < nb; ++c) s = fma(row[c], z[j0 + c], s);
+            z[i] -= s;
+        }
+        __syncthreads();
+    }
+    // backward: L' x = y
+    for (int j0 = ((na - 1) / 32) * 32; j0 >= 0; j0 -= 32) {
+        const int nb = min(32, na - j0);
+        for (int e = tid; e < 32 * 32; e += blockDim.x) {
+            const int i = e / 32, j = e % 32;
+            blk[i * 33 + j] = (i < nb && j <= i) ? L[(size_t)(j0 + i) * ld + j0 + j] : (i == j ? 1.0 : 0.0);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            double zi = (lane < nb) ? z[j0 + lane] : 0.0;
+            for (int c = nb - 1; c >= 0; --c) {
+                const double zc = __shfl_sync(0xffffffffu, zi, c) / blk[c * 33 + c];
+                if (lane == c) zi = zc;
+                if (lane < c) zi -= blk[c * 33 + lane] * zc;
+            }
+            if (lane < nb) z[j0 + lane] = zi;
+        }
+        __syncthreads();
+        for (int j = tid; j < j0; j += blockDim.x) {
+            double s = 0.0;
+            for (int c = 0; c < nb; ++c) s = fma(L[(size_t)(j0 + c) * ld + j], z[j0 + c], s);
+            z[j] -= s;
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < na; i += blockDim.x) zg[i] = z[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-target state and the shared post-solve step logic
+// ---------------------------------------------------------------------------------------------
+struct SweepDev {
+    // problem
+    int k, n_t, L, W, maxiters, algorithm, proximal;
+    double abstol, reltol, rho, cad_rho;
+    const double* lambdas;  // L, sorted
+    const double* As;       // k x k equilibrated system matrix (symmetric)
+    const double* dinv;     // k
+    const double* rs;       // n_t x k scaled right-hand sides
+    const double* rraw;     // n_t x k unscaled right-hand sides (R, column e = target e)
+    // per target
+    double* x;              // n_t x k
+    double* xprev;          // n_t x k
+    double* aux1;           // n_t x k  (ADMM alpha / SR3 W)
+    double* aux2;           // n_t x k  (ADMM w)
+    double* znew;           // n_t x k  solve results (scaled unknowns) for the global-memory paths
+    uint32_t* active;       // n_t x W
+    EqState* eq;            // n_t
+    // candidates
+    int32_t* cand_idx;
+    double* cand_val;
+    int64_t* cand_off;
+    int32_t* cand_nnz;
+    int32_t* cand_dof;
+    int32_t* cand_eq;
+    int64_t pool_cap;
+    int cand_cap;
+    int* counters;  // [0] ncand, [1] overflow flag, [2] pool used (low), [3] need_big count, [4] running count
+    unsigned long long* pool_used;
+    // runs (steps with an unchanged candidate are merged)
+    int32_t* run_cand;
+    int32_t* run_jfirst;  // threshold index of the run's first step
+    int32_t* run_j;       // threshold index of the run's last step
+    int run_cap;
+    // path
+    uint32_t* path_support;  // n_t x L x W
+    double* path_coef;       // n_t x L x k
+    int32_t* path_iters;     // n_t x L
+};
+
+__device__ __forceinline__ double threshold_cut(const SweepDev& S, double lam) {
+    // value an entry must exceed (strictly) to stay active
+    if (S.algorithm == DDB_ALG_STLSQ) return lam;
+    if (S.algorithm == DDB_ALG_ADMM) return lam / S.rho;
+    if (S.proximal == DDB_PROX_HARD) return sqrt(2.0 * lam);
+    if (S.proximal == DDB_PROX_CAD) return isnan(S.cad_rho) ? 5.0 * lam : S.cad_rho;
+    return lam;
+}
+
+// Append / merge the candidate described by the CURRENT x of target e (sparse: entries != 0) with
+// dof = number of active entries.  Consecutive identical candidates extend the current run.
+// Called by all threads of the CTA; `red`/`redi` are shared scratch of >= 32 entries.
+__device__ void record_candidate(const SweepDev& S, int e, int j, int dof, double* red, int* redi, int* s_tmp) {
+    const int k = S.k;
+    const double* x = S.x + (size_t)e * k;
+    EqState& st = S.eq[e];
+    // number of nonzeros
+    int cnt = 0;
+    for (int i = threadIdx.x; i < k; i += blockDim.x) cnt += (x[i] != 0.0);
+    const int nnz = block_sum_int(cnt, redi);
+    // compare with the last candidate of this target
+    int same = 0;
+    const int last = st.last_cand;
+    if (last >= 0 && S.cand_nnz[last] == nnz && S.cand_dof[last] == dof) {
+        const int64_t off = S.cand_off[last];
+        int diff = 0;
+        for (int t = threadIdx.x; t < nnz; t += blockDim.x) {
+            const int idx = S.cand_idx[off + t];
+            const double v = S.cand_val[off + t];
+            diff |= (__double_as_longlong(x[idx]) != __double_as_longlong(v));
+        }
+        same = (block_sum_int(diff, redi) == 0);
+    }
+    if (same) {
+        if (threadIdx.x == 0) S.run_j[(size_t)e * S.run_cap + st.nruns - 1] = j;
+        __syncthreads();
+        return;
+    }
+    // new candidate: reserve id and pool space
+    if (threadIdx.x == 0) {
+        const int id = atomicAdd(&S.counters[0], 1);
+        const unsigned long long off = atomicAdd(S.pool_used, (unsigned long long)nnz);
+        int ok = 1;
+        if (id >= S.cand_cap || off + (unsigned long long)nnz > (unsigned long long)S.pool_cap || st.nruns >= S.run_cap) {
+            atomicExch(&S.counters[1], 1);
+            ok = 0;
+        }
+        s_tmp[0] = ok ? id : -1;
+        if (ok) {
+            S.cand_off[id] = (int64_t)off;
+            S.cand_nnz[id] = nnz;
+            S.cand_dof[id] = dof;
+            S.cand_eq[id] = e;
+            S.run_cand[(size_t)e * S.run_cap + st.nruns] = id;
+            S.run_jfirst[(size_t)e * S.run_cap + st.nruns] = j;
+            S.run_j[(size_t)e * S.run_cap + st.nruns] = j;
+            st.nruns += 1;
+            st.last_cand = id;
+        }
+    }
+    __syncthreads();
+    const int id = s_tmp[0];
+    if (id < 0) return;
+    const int64_t off = S.cand_off[id];
+    // ordered compaction: warp-level prefix over chunks of blockDim.x entries
+    __shared__ int s_base;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < k; i0 += blockDim.x) {
+        const int i = i0 + threadIdx.x;
+        const int flag = (i < k) && (x[i] != 0.0);
+        // block-wide exclusive scan of flag
+        const unsigned ball = __ballot_sync(0xffffffffu, flag);
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        if (lane == 0) redi[warp] = __popc(ball);
+        __syncthreads();
+        int wbase = 0, tot = 0;
+        for (int w = 0; w < nw; ++w) {
+            if (w < warp) wbase += redi[w];
+            tot += redi[w];
+        }
+        const int pos = s_base + wbase + __popc(ball & ((1u << lane) - 1u));
+        if (flag) {
+            S.cand_idx[off + pos] = i;
+            S.cand_val[off + pos] = x[i];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_base += tot;
+        __syncthreads();
+    }
+}
+
+// After the solve of one step wrote the new coefficients into x (entries of the old active set),
+// finish the step exactly as `step!` + the body of the solver loop do.  xprev must already hold the
+// pre-step x.  Returns nothing; updates the target's state machine.
+__device__ void finish_step(const SweepDev& S, int e, double* red, int* redi, int* s_tmp) {
+    const int k = S.k, W = S.W;
+    EqState& st = S.eq[e];
+    double* x = S.x + (size_t)e * k;
+    const double* xp = S.xprev + (size_t)e * k;
+    uint32_t* act = S.active + (size_t)e * W;
+    const int j = st.j;
+    const double lam = S.lambdas[j];
+    const double cut = threshold_cut(S, lam);
+    // active = |x| > cut ; x[!active] = 0   (_apply_active_set!, proximals.jl:1-13)
+    // SR3 keeps x as produced by the proximal operator and only recomputes the mask (SR3.jl:138-139)
+    int cnt = 0;
+    double d2 = 0.0, n2 = 0.0;
+    for (int w = threadIdx.x; w < W; w += blockDim.x) {
+        uint32_t bits = 0;
+        for (int b = 0; b < 32; ++b) {
+            const int i = w * 32 + b;
+            if (i < k) {
+                double v = x[i];
+                const bool a = fabs(v) > cut;
+                if (!a && S.algorithm != DDB_ALG_SR3) {
+                    v = 0.0;
+                    x[i] = 0.0;
+                }
+                bits |= (a ? 1u : 0u) << b;
+                cnt += a;
+                const double d = v - xp[i];
+                d2 += d * d;
+                n2 += v * v;
+            }
+        }
+        act[w] = bits;
+    }
+    const int na = block_sum_int(cnt, redi);
+    const double delta = sqrt(block_sum(d2, red));
+    const double nx = sqrt(block_sum(n2, red));
+    __syncthreads();
+    record_candidate(S, e, j, na, red, redi, s_tmp);
+    // convergence (_is_converged, DataDrivenSparse.jl:160-168)
+    bool conv = (na == 0) || (delta < S.abstol) || (delta / nx < S.reltol);
+    if (threadIdx.x == 0) {
+        st.na = na;
+        st.counter += 1;
+        st.iter += 1;
+    }
+    __syncthreads();
+    if (conv || st.iter >= S.maxiters) {
+        // end of this threshold's inner loop: record the path entry, advance to the next threshold
+        uint32_t* ps = S.path_support + ((size_t)e * S.L + j) * W;
+        for (int w = threadIdx.x; w < W; w += blockDim.x) ps[w] = act[w];
+        if (S.path_coef) {
+            double* pc = S.path_coef + ((size_t)e * S.L + j) * k;
+            for (int i = threadIdx.x; i < k; i += blockDim.x) pc[i] = x[i];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            S.path_iters[(size_t)e * S.L + j] = st.iter;
+            st.j = j + 1;
+            st.iter = 0;
+            if (st.j >= S.L) st.status = kEqDone;
+        }
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// init: x0 from the shared full solve, initial mask, zero-model bookkeeping
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sweep_init_kernel(SweepDev S) {
+    const int e = blockIdx.x;
+    const int k = S.k, W = S.W;
+    __shared__ double red[32];
+    __shared__ int redi[32];
+    EqState& st = S.eq[e];
+    double* x = S.x + (size_t)e * k;
+    double* xp = S.xprev + (size_t)e * k;
+    const double* z = S.znew + (size_t)e * k;
+    uint32_t* act = S.active + (size_t)e * W;
+    const double cut = threshold_cut(S, S.lambdas[0]);  // lambdas sorted: [0] is the minimum
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        const double v = z[i] * S.dinv[i];
+        x[i] = v;
+        xp[i] = (S.algorithm == DDB_ALG_SR3) ? v : 0.0;  // SR3.jl:122 copies, STLSQ/ADMM start from zero
+        if (S.aux1) S.aux1[(size_t)e * k + i] = 0.0;
+        if (S.aux2) S.aux2[(size_t)e * k + i] = 0.0;
+    }
+    __syncthreads();
+    int cnt = 0;
+    for (int w = threadIdx.x; w < W; w += blockDim.x) {
+        uint32_t bits = 0;
+        for (int b = 0; b < 32; ++b) {
+            const int i = w * 32 + b;
+            if (i < k && fabs(x[i]) > cut) bits |= 1u << b, ++cnt;
+        }
+        act[w] = bits;
+    }
+    const int na = block_sum_int(cnt, redi);
+    if (threadIdx.x == 0) {
+        st.j = 0;
+        st.iter = 0;
+        st.counter = 0;
+        st.na = na;
+        st.status = kEqRunning;
+        st.nruns = 0;
+        st.last_cand = -1;
+        st.dof0 = na;  // dof of the zeroed best cache = mask of the initial solution (solver.jl:82-83)
+        st.flags = 0;
+        // candidate e is the zero model of target e
+        S.cand_off[e] = 0;
+        S.cand_nnz[e] = 0;
+        S.cand_dof[e] = na;
+        S.cand_eq[e] = e;
+    }
+    (void)red;
+}
+
+// ---------------------------------------------------------------------------------------------
+// STLSQ: persistent small-support kernel (one CTA per target)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) stlsq_small_kernel(SweepDev S, int small_max) {
+    const int e = blockIdx.x;
+    const int k = S.k, W = S.W;
+    extern __shared__ double smem[];
+    double* M = smem;                                    // small_max x (small_max + 1)
+    double* rhs = M + (size_t)small_max * (small_max + 1);  // small_max
+    int* idx = reinterpret_cast<int*>(rhs + small_max);  // small_max
+    __shared__ double red[32];
+    __shared__ int redi[32];
+    __shared__ int s_tmp[4];
+    EqState& st = S.eq[e];
+    double* x = S.x + (size_t)e * k;
+    double* xp = S.xprev + (size_t)e * k;
+    const uint32_t* act = S.active + (size_t)e * W;
+    const double* rs = S.rs + (size_t)e * k;
+    const int ldm = small_max + 1;
+
+    while (true) {
+        __syncthreads();
+        if (st.status != kEqRunning) break;
+        const int na = st.na;
+        if (na > small_max) {
+            if (threadIdx.x == 0) {
+                st.status = kEqNeedBig;
+                atomicAdd(&S.counters[3], 1);
+            }
+            break;
+        }
+        // X_prev .= X   (STLSQ.jl:120)
+        for (int i = threadIdx.x; i < k; i += blockDim.x) xp[i] = x[i];
+        // ordered list of active indices
+        if (threadIdx.x == 0) s_tmp[1] = 0;
+        __syncthreads();
+        for (int w0 = 0; w0 < W; w0 += blockDim.x) {
+            const int w = w0 + threadIdx.x;
+            const uint32_t bits = (w < W) ? act[w] : 0u;
+            const int c = __popc(bits);
+            // block exclusive scan of c
+            int v = c;
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, v, o);
+                if (lane >= o) v += t;
+            }
+            if (lane == 31) redi[warp] = v;
+            __syncthreads();
+            int wbase = 0, tot = 0;
+            for (int q = 0; q < nw; ++q) {
+                if (q < warp) wbase += redi[q];
+                tot += redi[q];
+            }
+            int pos = s_tmp[1] + wbase + v - c;
+            uint32_t bb = bits;
+            while (bb) {
+                const int b = __ffs(bb) - 1;
+                bb &= bb - 1;
+                idx[pos++] = w * 32 + b;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) s_tmp[1] += tot;
+            __syncthreads();
+        }
+        // gather the masked, equilibrated system into shared memory (lower triangle) and the rhs
+        for (int t = threadIdx.x; t < na * na; t += blockDim.x) {
+            const int i = t / na, j = t % na;
+            if (j <= i) M[i * ldm + j] = S.As[(size_t)idx[i] * k + idx[j]];
+        }
+        for (int i = threadIdx.x; i < na; i += blockDim.x) rhs[i] = rs[idx[i]];
+        __syncthreads();
+        // Cholesky in shared memory (right-looking, column at a time)
+        int bad = 0;
+        for (int c = 0; c < na; ++c) {
+            const double d = M[c * ldm + c];
+            if (!(d > 0.0)) bad = 1;
+            const double piv = (d > 0.0) ? sqrt(d) : 1.0;
+            __syncthreads();
+            if (threadIdx.x == 0) M[c * ldm + c] = piv;
+            for (int i = c + 1 + threadIdx.x; i < na; i += blockDim.x) M[i * ldm + c] /= piv;
+            __syncthreads();
+            const int rem = na - c - 1;
+            for (int t = threadIdx.x; t < rem * rem; t += blockDim.x) {
+                const int i = c + 1 + t / rem, j = c + 1 + t % rem;
+                if (j <= i) M[i * ldm + j] -= M[i * ldm + c] * M[j * ldm + c];
+            }
+            __syncthreads();
+        }
+        if (bad && threadIdx.x == 0) st.flags |= 1;
+        // forward / backward substitution by warp 0 (na <= small_max: serial over columns, lanes over rows)
+        if (threadIdx.x < 32) {
+            const int lane = threadIdx.x;
+            for (int c = 0; c < na; ++c) {
+                const double zc = rhs[c] / M[c * ldm + c];
+                __syncwarp();
+                if (lane == 0) rhs[c] = zc;
+                for (int i = c + 1 + lane; i < na; i += 32) rhs[i] -= M[i * ldm + c] * zc;
+                __syncwarp();
+            }
+            for (int c = na - 1; c >= 0; --c) {
+                const double zc = rhs[c] / M[c * ldm + c];
+                __syncwarp();
+                if (lane == 0) rhs[c] = zc;
+                for (int i = lane; i < c; i += 32) rhs[i] -= M[c * ldm + i] * zc;
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        // X[p] = solution (un-scaled)   (STLSQ.jl:128-140)
+        for (int i = threadIdx.x; i < na; i += blockDim.x) x[idx[i]] = rhs[i] * S.dinv[idx[i]];
+        __syncthreads();
+        finish_step(S, e, red, redi, s_tmp);
+    }
+}
+
+// big path, STLSQ: gather masked systems of the flagged targets into global workspaces
+// grid (row splits, number of flagged targets); dynamic shared memory: k ints
+__global__ void __launch_bounds__(256) stlsq_big_gather_kernel(SweepDev S, const int* big_list, double* ws,
+                                                               size_t ws_stride, int* idx_all, int* na_out) {
+    const int slot = blockIdx.y;
+    const int e = big_list[slot];
+    const int k = S.k, W = S.W;
+    const uint32_t* act = S.active + (size_t)e * W;
+    extern __shared__ int sidx[];
+    __shared__ int s_na;
+    if (threadIdx.x == 0) {  // ordered list of active indices (every CTA of the slot rebuilds it)
+        int pos = 0;
+        for (int w = 0; w < W; ++w) {
+            uint32_t bb = act[w];
+            while (bb) {
+                const int b = __ffs(bb) - 1;
+                bb &= bb - 1;
+                sidx[pos++] = w * 32 + b;
+            }
+        }
+        s_na = pos;
+    }
+    __syncthreads();
+    const int na = s_na;
+    double* A = ws + (size_t)slot * ws_stride;
+    for (int i = blockIdx.x; i < na; i += gridDim.x) {
+        const double* src = S.As + (size_t)sidx[i] * k;
+        for (int j = threadIdx.x; j <= i; j += blockDim.x) A[(size_t)i * k + j] = src[sidx[j]];
+    }
+    if (blockIdx.x == 0) {
+        int* idx = idx_all + (size_t)slot * k;
+        double* x = S.x + (size_t)e * k;
+        double* xp = S.xprev + (size_t)e * k;
+        double* z = S.znew + (size_t)e * k;
+        const double* rs = S.rs + (size_t)e * k;
+        if (threadIdx.x == 0) na_out[slot] = na;
+        for (int i = threadIdx.x; i < na; i += blockDim.x) idx[i] = sidx[i];
+        for (int i = threadIdx.x; i < k; i += blockDim.x) xp[i] = x[i];  // X_prev .= X
+        for (int i = threadIdx.x; i < na; i += blockDim.x) z[i] = rs[sidx[i]];
+    }
+}
+
+__global__ void __launch_bounds__(256) stlsq_big_finish_kernel(SweepDev S, const int* big_list, const int* idx_all,
+                                                               const int* na_arr, const int* fail) {
+    const int slot = blockIdx.x;
+    const int e = big_list[slot];
+    const int k = S.k;
+    __shared__ double red[32];
+    __shared__ int redi[32];
+    __shared__ int s_tmp[4];
+    const int* idx = idx_all + (size_t)slot * k;
+    const int na = na_arr[slot];
+    double* x = S.x + (size_t)e * k;
+    const double* z = S.znew + (size_t)e * k;
+    for (int i = threadIdx.x; i < na; i += blockDim.x) x[idx[i]] = z[i] * S.dinv[idx[i]];
+    if (threadIdx.x == 0) {
+        if (fail[slot]) S.eq[e].flags |= 1;
+        S.eq[e].status = kEqRunning;
+    }
+    __syncthreads();
+    finish_step(S, e, red, redi, s_tmp);
+}
+
+// ---------------------------------------------------------------------------------------------
+// ADMM / SR3: one iteration = shared-factor solve for every running target + fused prox step
+// ---------------------------------------------------------------------------------------------
+// rhs (scaled) for the next solve:  ADMM  b = r + rho (alpha - w);  SR3  b = r + nu x
+__global__ void __launch_bounds__(256) relax_rhs_kernel(SweepDev S, int* active_matrix) {
+    const int e = blockIdx.x;
+    const int k = S.k;
+    EqState& st = S.eq[e];
+    if (threadIdx.x == 0) active_matrix[e] = (st.status == kEqRunning);
+    if (st.status != kEqRunning) return;
+    double* x = S.x + (size_t)e * k;
+    double* xp = S.xprev + (size_t)e * k;
+    double* z = S.znew + (size_t)e * k;
+    const double* r = S.rraw + (size_t)e * k;
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        const double xi = x[i];
+        xp[i] = xi;  // X_prev .= X
+        double b;
+        if (S.algorithm == DDB_ALG_ADMM)
+            b = r[i] + S.rho * (S.aux1[(size_t)e * k + i] - S.aux2[(size_t)e * k + i]);
+        else
+            b = r[i] + xi * S.rho;
+        z[i] = b * S.dinv[i];
+    }
+}
+
+__device__ __forceinline__ double soft(double v, double lam) {
+    const double a = fabs(v) - lam;
+    const double sgn = (v > 0.0) ? 1.0 : ((v < 0.0) ? -1.0 : 0.0);
+    return sgn * (a > 0.0 ? a : 0.0);
+}
+
+__global__ void __launch_bounds__(256) relax_finish_kernel(SweepDev S) {
+    const int e = blockIdx.x;
+    const int k = S.k;
+    __shared__ double red[32];
+    __shared__ int redi[32];
+    __shared__ int s_tmp[4];
+    EqState& st = S.eq[e];
+    if (st.status != kEqRunning) return;
+    double* x = S.x + (size_t)e * k;
+    const double* z = S.znew + (size_t)e * k;
+    const double lam = S.lambdas[st.j];
+    if (S.algorithm == DDB_ALG_ADMM) {
+        double* alpha = S.aux1 + (size_t)e * k;
+        double* w = S.aux2 + (size_t)e * k;
+        const double t = lam / S.rho;
+        for (int i = threadIdx.x; i < k; i += blockDim.x) {
+            const double xi = z[i] * S.dinv[i];       // X = (B + rho (alpha - w)) / A
+            const double a = soft(xi + w[i], t);      // alpha = prox(X + w, lambda/rho)
+            alpha[i] = a;
+            w[i] += xi - a;                           // w += X - alpha
+            x[i] = xi;                                // thresholded by finish_step
+        }
+    } else {
+        double* Wv = S.aux1 + (size_t)e * k;
+        const double cadr = isnan(S.cad_rho) ? 5.0 * lam : S.cad_rho;
+        for (int i = threadIdx.x; i < k; i += blockDim.x) {
+            const double wi = z[i] * S.dinv[i];       // W = (B + nu X) / A
+            Wv[i] = wi;
+            double xi;
+            if (S.proximal == DDB_PROX_HARD) xi = (fabs(wi) > sqrt(2.0 * lam)) ? wi : 0.0;
+            else if (S.proximal == DDB_PROX_SOFT) xi = soft(wi, lam);
+            else xi = (fabs(wi) > cadr) ? wi : soft(wi, lam);
+            x[i] = xi;                                // X = prox(W, lambda)
+        }
+    }
+    __syncthreads();
+    finish_step(S, e, red, redi, s_tmp);
+}
+
+__global__ void count_status_kernel(const EqState* eq, int n_t, int* counters) {
+    int running = 0, big = 0;
+    for (int e = threadIdx.x; e < n_t; e += blockDim.x) {
+        running += (eq[e].status == kEqRunning);
+        big += (eq[e].status == kEqNeedBig);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        running += __shfl_xor_sync(0xffffffffu, running, o);
+        big += __shfl_xor_sync(0xffffffffu, big, o);
+    }
+    if (threadIdx.x == 0) {
+        counters[4] = running;
+        counters[3] = big;
+    }
+}
+
+__global__ void list_big_kernel(const EqState* eq, int n_t, int* big_list, int* nbig) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        int c = 0;
+        for (int e = 0; e < n_t; ++e)
+            if (eq[e].status == kEqNeedBig) big_list[c++] = e;
+        *nbig = c;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// selection along the recorded step sequence (solver.jl:94-115)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double score_of(int selector, double rss, int dof, double nobs) {
+    if (selector == DDB_SEL_RSS) return rss;
+    const double m2ll = nobs * log(rss / nobs);  // -2 loglikelihood  (DataDrivenSparse.jl:188-192)
+    if (selector == DDB_SEL_BIC) return m2ll + dof * log(nobs);
+    const double aic = m2ll + 2.0 * dof;
+    if (selector == DDB_SEL_AIC) return aic;
+    return aic + (2.0 * dof * (dof + 1.0)) / (nobs - dof - 1.0);
+}
+
+__global__ void __launch_bounds__(256) select_kernel(SweepDev S, const double* __restrict__ rss, int selector,
+                                                     double nobs, double* coef /* n_t x k col-major */,
+                                                     double* lambda_opt, int32_t* iters, double* rss_out,
+                                                     int32_t* dof_out, int32_t* flags) {
+    const int e = blockIdx.x;
+    const int k = S.k;
+    __shared__ int s_best;
+    __shared__ int s_bestj;
+    const EqState& st = S.eq[e];
+    if (threadIdx.x == 0) {
+        int best = e;  // zero model
+        int bestj = 0;
+        double best_score = score_of(selector, rss[e], S.cand_dof[e], nobs);
+        for (int r = 0; r < st.nruns; ++r) {
+            const int c = S.run_cand[(size_t)e * S.run_cap + r];
+            const int jfirst = S.run_jfirst[(size_t)e * S.run_cap + r];
+            const int jlast = S.run_j[(size_t)e * S.run_cap + r];
+            const double sc = score_of(selector, rss[c], S.cand_dof[c], nobs);
+            // A run is a maximal sequence of steps whose cache content did not change.  Its first step is
+            // taken unconditionally when it belongs to the first threshold (`j == 1` in the reference),
+            // otherwise iff score <= best; once taken, the remaining steps of the run tie with themselves
+            // and `<=` moves the optimal threshold to the run's last one.
+            if (jfirst == 0 || sc <= best_score) {
+                best = c;
+                bestj = jlast;
+                best_score = sc;
+            }
+        }
+        s_best = best;
+        s_bestj = bestj;
+        if (lambda_opt) lambda_opt[e] = S.lambdas[bestj < S.L ? bestj : S.L - 1];
+        if (iters) iters[e] = st.counter;
+        if (rss_out) rss_out[e] = rss[best];
+        if (dof_out) dof_out[e] = S.cand_dof[best];
+        if (flags) flags[e] = st.flags;
+    }
+    __syncthreads();
+    if (coef) {
+        for (int i = threadIdx.x; i < k; i += blockDim.x) coef[(size_t)e + (size_t)S.n_t * i] = 0.0;
+        __syncthreads();
+        const int c = s_best;
+        const int64_t off = S.cand_off[c];
+        for (int t = threadIdx.x; t < S.cand_nnz[c]; t += blockDim.x)
+            coef[(size_t)e + (size_t)S.n_t * S.cand_idx[off + t]] = S.cand_val[off + t];
+    }
+}
+
+}  // namespace ddb
+
+// =============================================================================================
+// Host side
+// =============================================================================================
+namespace ddb {
+
+void SweepState::release_all() {
+    DevBuf* all[] = {&As, &Lfac, &dinv, &rs, &x, &xprev, &aux1, &aux2, &znew, &active, &eq, &lambdas_d, &cand_idx,
+                     &cand_val, &cand_off, &cand_nnz, &cand_dof, &cand_eq, &counters, &pool_used_d, &run_cand,
+                     &run_jfirst, &run_j, &path_support, &path_coef, &path_iters, &big_ws, &big_idx, &big_na,
+                     &big_list, &big_fail, &active_matrix, &shared_fail, &rss, &rss_partials, &out_tmp, &cand_terms};
+    for (DevBuf* b : all) b->release();
+}
+
+void sweep_free(ddb_ctx* ctx) {
+    if (ctx->sweep) {
+        ctx->sweep->release_all();
+        delete ctx->sweep;
+        ctx->sweep = nullptr;
+    }
+}
+
+static SweepDev make_dev(ddb_ctx* ctx, SweepState* S) {
+    SweepDev D;
+    memset(&D, 0, sizeof(D));
+    D.k = S->k;
+    D.n_t = S->n_t;
+    D.L = S->L;
+    D.W = S->W;
+    D.maxiters = S->prm.maxiters;
+    D.algorithm = S->prm.algorithm;
+    D.proximal = S->prm.proximal;
+    D.abstol = S->prm.abstol;
+    D.reltol = S->prm.reltol;
+    D.rho = S->prm.rho;
+    D.cad_rho = S->prm.cad_rho;
+    D.lambdas = S->lambdas_d.as<double>();
+    D.As = S->As.as<double>();
+    D.dinv = S->dinv.as<double>();
+    D.rs = S->rs.as<double>();
+    D.rraw = ctx->d_packed.as<double>() + (size_t)S->k * S->k;
+    D.x = S->x.as<double>();
+    D.xprev = S->xprev.as<double>();
+    D.aux1 = S->prm.algorithm == DDB_ALG_STLSQ ? nullptr : S->aux1.as<double>();
+    D.aux2 = S->prm.algorithm == DDB_ALG_ADMM ? S->aux2.as<double>() : nullptr;
+    D.znew = S->znew.as<double>();
+    D.active = S->active.as<uint32_t>();
+    D.eq = S->eq.as<EqState>();
+    D.cand_idx = S->cand_idx.as<int32_t>();
+    D.cand_val = S->cand_val.as<double>();
+    D.cand_off = S->cand_off.as<int64_t>();
+    D.cand_nnz = S->cand_nnz.as<int32_t>();
+    D.cand_dof = S->cand_dof.as<int32_t>();
+    D.cand_eq = S->cand_eq.as<int32_t>();
+    D.pool_cap = S->pool_cap;
+    D.cand_cap = S->cand_cap;
+    D.counters = S->counters.as<int>();
+    D.pool_used = S->pool_used_d.as<unsigned long long>();
+    D.run_cand = S->run_cand.as<int32_t>();
+    D.run_jfirst = S->run_jfirst.as<int32_t>();
+    D.run_j = S->run_j.as<int32_t>();
+    D.run_cap = S->run_cap;
+    D.path_support = S->path_support.as<uint32_t>();
+    D.path_coef = S->path_coef.as<double>();
+    D.path_iters = S->path_iters.as<int32_t>();
+    return D;
+}
+
+constexpr int kSmallMax = 128;
+
+int sweep_run(ddb_ctx* ctx, const ddb_sweep_params* prm, const double* lambdas, int L, int64_t m_total) {
+    if (!prm || !lambdas || L <= 0 || m_total <= 0) {
+        set_error("ddb_sweep: params, lambdas must be non-null and L, m_total positive");
+        return DDB_INVALID_ARG;
+    }
+    if (!ctx->d_packed.p || ctx->k <= 0 || ctx->n_t <= 0) {
+        set_error("ddb_sweep: no normal-equation blocks in the context (run ddb_gram or ddb_gram_upload first)");
+        return DDB_BAD_STATE;
+    }
+    if (prm->algorithm < DDB_ALG_STLSQ || prm->algorithm > DDB_ALG_SR3 || prm->maxiters <= 0 || !(prm->rho >= 0.0)) {
+        set_error("ddb_sweep: invalid algorithm / maxiters / rho");
+        return DDB_INVALID_ARG;
+    }
+    if (prm->algorithm != DDB_ALG_STLSQ && !(prm->rho > 0.0)) {
+        set_error("ddb_sweep: ADMM rho / SR3 nu must be positive");
+        return DDB_INVALID_ARG;
+    }
+    for (int j = 0; j < L; ++j)
+        if (!(lambdas[j] > 0.0)) {
+            set_error("ddb_sweep: thresholds must be positive (STLSQ.jl:56)");
+            return DDB_INVALID_ARG;
+        }
+    if (!ctx->sweep) ctx->sweep = new SweepState();
+    SweepState* S = ctx->sweep;
+    S->valid = false;
+    S->have_rss = false;
+    const int k = ctx->k, n_t = ctx->n_t;
+    const int W = (k + 31) / 32;
+    S->k = k;
+    S->n_t = n_t;
+    S->L = L;
+    S->W = W;
+    S->m_total = m_total;
+    S->prm = *prm;
+    S->lambdas.assign(lambdas, lambdas + L);
+    std::sort(S->lambdas.begin(), S->lambdas.end());  // solver.jl:77-79
+    const int64_t steps_bound = (int64_t)L * prm->maxiters;
+    S->run_cap = (int)std::min<int64_t>(steps_bound, 1 << 16) + 1;
+    S->cand_cap = n_t + n_t * (int)std::min<int64_t>(steps_bound, 8192);
+    S->pool_cap = std::max<int64_t>((int64_t)8 << 20, (int64_t)4 * n_t * k);
+
+    const size_t kk = (size_t)k * k, nk = (size_t)n_t * k;
+    DDB_TRY(S->As.reserve(kk * 8));
+    DDB_TRY(S->Lfac.reserve(kk * 8));
+    DDB_TRY(S->dinv.reserve((size_t)k * 8));
+    DDB_TRY(S->rs.reserve(nk * 8));
+    DDB_TRY(S->x.reserve(nk * 8));
+    DDB_TRY(S->xprev.reserve(nk * 8));
+    DDB_TRY(S->znew.reserve(nk * 8));
+    if (prm->algorithm != DDB_ALG_STLSQ) DDB_TRY(S->aux1.reserve(nk * 8));
+    if (prm->algorithm == DDB_ALG_ADMM) DDB_TRY(S->aux2.reserve(nk * 8));
+    DDB_TRY(S->active.reserve((size_t)n_t * W * 4));
+    DDB_TRY(S->eq.reserve((size_t)n_t * sizeof(EqState)));
+    DDB_TRY(S->lambdas_d.reserve((size_t)L * 8));
+    DDB_TRY(S->cand_idx.reserve((size_t)S->pool_cap * 4));
+    DDB_TRY(S->cand_val.reserve((size_t)S->pool_cap * 8));
+    DDB_TRY(S->cand_off.reserve((size_t)S->cand_cap * 8));
+    DDB_TRY(S->cand_nnz.reserve((size_t)S->cand_cap * 4));
+    DDB_TRY(S->cand_dof.reserve((size_t)S->cand_cap * 4));
+    DDB_TRY(S->cand_eq.reserve((size_t)S->cand_cap * 4));
+    DDB_TRY(S->counters.reserve(64));
+    DDB_TRY(S->pool_used_d.reserve(16));
+    DDB_TRY(S->run_cand.reserve((size_t)n_t * S->run_cap * 4));
+    DDB_TRY(S->run_jfirst.reserve((size_t)n_t * S->run_cap * 4));
+    DDB_TRY(S->run_j.reserve((size_t)n_t * S->run_cap * 4));
+    DDB_TRY(S->path_support.reserve((size_t)n_t * L * W * 4));
+    DDB_TRY(S->path_coef.reserve((size_t)n_t * L * k * 8));
+    DDB_TRY(S->path_iters.reserve((size_t)n_t * L * 4));
+    DDB_TRY(S->big_list.reserve((size_t)n_t * 4 + 16));
+    DDB_TRY(S->big_na.reserve((size_t)n_t * 4));
+    DDB_TRY(S->big_fail.reserve((size_t)n_t * 4));
+    DDB_TRY(S->active_matrix.reserve((size_t)n_t * 4));
+    DDB_TRY(S->shared_fail.reserve(16));
+
+    cudaStream_t st = ctx->stream;
+    int launches = 0, big_steps = 0;
+    DDB_CUDA_TRY(cudaMemcpyAsync(S->lambdas_d.p, S->lambdas.data(), (size_t)L * 8, cudaMemcpyHostToDevice, st));
+    int h_counters[8] = {n_t, 0, 0, 0, 0, 0, 0, 0};  // candidates 0..n_t-1 are the zero models
+    DDB_CUDA_TRY(cudaMemcpyAsync(S->counters.p, h_counters, sizeof(h_counters), cudaMemcpyHostToDevice, st));
+    DDB_CUDA_TRY(cudaMemsetAsync(S->pool_used_d.p, 0, 16, st));
+    DDB_CUDA_TRY(cudaMemsetAsync(S->shared_fail.p, 0, 16, st));
+    DDB_CUDA_TRY(cudaMemsetAsync(S->path_iters.p, 0, (size_t)n_t * L * 4, st));
+    DDB_CUDA_TRY(cudaMemsetAsync(S->path_support.p, 0, (size_t)n_t * L * W * 4, st));
+
+    DDB_CUDA_TRY(cudaEventRecord(ctx->ev[4], st));
+    // ---- preparation + shared factorisation --------------------------------------------------
+    const double* G = ctx->d_packed.as<double>();
+    const double* R = G + kk;
+    const double rho = prm->rho;  // 0 for plain STLSQ
+    prep_diag_kernel<<<(k + 255) / 256, 256, 0, st>>>(G, k, rho, S->dinv.as<double>());
+    prep_scale_kernel<<<(unsigned)((kk + 255) / 256), 256, 0, st>>>(G, k, rho, S->dinv.as<double>(), S->As.as<double>());
+    prep_rhs_kernel<<<(unsigned)((nk + 255) / 256), 256, 0, st>>>(R, k, n_t, S->dinv.as<double>(), S->rs.as<double>());
+    launches += 3;
+    DDB_CUDA_TRY(cudaMemcpyAsync(S->Lfac.p, S->As.p, kk * 8, cudaMemcpyDeviceToDevice, st));
+    DDB_TRY(chol_batched(ctx, S->Lfac.as<double>(), 0, k, nullptr, k, 1, S->shared_fail.as<int>(), &launches));
+    DDB_CUDA_TRY(cudaMemcpyAsync(S->znew.p, S->rs.p, nk * 8, cudaMemcpyDeviceToDevice, st));
+    const size_t solve_smem = ((size_t)((k + 31) / 32) * 32 + 32 * 33) * sizeof(double);
+    if (solve_smem > 200 * 1024) {
+        set_error("ddb_sweep: library of %d terms exceeds the shared-memory triangular solver (max ~24000)", k);
+        return DDB_UNSUPPORTED;
+    }
+    DDB_CUDA_TRY(cudaFuncSetAttribute(chol_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
+    chol_solve_kernel<<<dim3(n_t, 1), 256, solve_smem, st>>>(S->Lfac.as<double>(), 0, k, nullptr, k,
+                                                             S->znew.as<double>(), (size_t)k, n_t, nullptr, nullptr);
+    ++launches;
+    SweepDev D = make_dev(ctx, S);
+    sweep_init_kernel<<<n_t, 256, 0, st>>>(D);
+    ++launches;
+    DDB_CUDA_TRY(cudaGetLastError());
+    DDB_CUDA_TRY(cudaEventRecord(ctx->ev[5], st));
+
+    // ---- the sweep -----------------------------------------------------------------------------
+    int h_shared_fail = 0;
+    if (prm->algorithm == DDB_ALG_STLSQ) {
+        const size_t small_smem = ((size_t)kSmallMax * (kSmallMax + 1) + kSmallMax) * sizeof(double) + kSmallMax * sizeof(int);
+        DDB_CUDA_TRY(cudaFuncSetAttribute(stlsq_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem));
+        for (int round = 0;; ++round) {
+            stlsq_small_kernel<<<n_t, 256, small_smem, st>>>(D, kSmallMax);
+            count_status_kernel<<<1, 32, 0, st>>>(D.eq, n_t, D.counters);
+            launches += 2;
+            DDB_CUDA_TRY(cudaMemcpyAsync(h_counters, S->counters.p, sizeof(h_counters), cudaMemcpyDeviceToHost, st));
+            DDB_CUDA_TRY(cudaStreamSynchronize(st));
+            if (h_counters[1]) {
+                set_error("ddb_sweep: candidate storage overflow (%d candidates); too many distinct iterates", h_counters[0]);
+                return DDB_OUT_OF_MEMORY;
+            }
+            const int nbig = h_counters[3];
+            if (nbig == 0) break;
+            // ---- big step: targets whose active set does not fit the shared-memory solver ----------
+            ++big_steps;
+            DDB_TRY(S->big_ws.reserve((size_t)nbig * kk * 8));
+            DDB_TRY(S->big_idx.reserve((size_t)nbig * k * 4));
+            list_big_kernel<<<1, 32, 0, st>>>(D.eq, n_t, S->big_list.as<int>(), S->big_list.as<int>() + n_t);
+            DDB_CUDA_TRY(cudaMemsetAsync(S->big_fail.p, 0, (size_t)n_t * 4, st));
+            stlsq_big_gather_kernel<<<dim3(64, nbig), 256, (size_t)k * sizeof(int), st>>>(
+                D, S->big_list.as<int>(), S->big_ws.as<double>(), kk, S->big_idx.as<int>(), S->big_na.as<int>());
+            launches += 2;
+            DDB_TRY(chol_batched(ctx, S->big_ws.as<double>(), kk, k, S->big_na.as<int>(), k, nbig,
+                                 S->big_fail.as<int>(), &launches));
+            chol_solve_kernel<<<dim3(1, nbig), 256, solve_smem, st>>>(S->big_ws.as<double>(), kk, k,
+                                                                      S->big_na.as<int>(), k, S->znew.as<double>(),
+                                                                      (size_t)k, 1, nullptr, S->big_list.as<int>());
+            stlsq_big_finish_kernel<<<nbig, 256, 0, st>>>(D, S->big_list.as<int>(), S->big_idx.as<int>(),
+                                                          S->big_na.as<int>(), S->big_fail.as<int>());
+            launches += 2;
+            DDB_CUDA_TRY(cudaGetLastError());
+        }
+    } else {
+        const int64_t max_steps = steps_bound;
+        for (int64_t it = 0; it < max_steps; ++it) {
+            relax_rhs_kernel<<<n_t, 256, 0, st>>>(D, S->active_matrix.as<int>());
+            chol_solve_kernel<<<dim3(1, n_t), 256, solve_smem, st>>>(S->Lfac.as<double>(), 0, k, nullptr, k,
+                                                                     S->znew.as<double>(), (size_t)k, 1,
+                                                                     S->active_matrix.as<int>(), nullptr);
+            relax_finish_kernel<<<n_t, 256, 0, st>>>(D);
+            launches += 3;
+            if ((it & 7) == 7 || it + 1 == max_steps) {
+                count_status_kernel<<<1, 32, 0, st>>>(D.eq, n_t, D.counters);
+                ++launches;
+                DDB_CUDA_TRY(cudaMemcpyAsync(h_counters, S->counters.p, sizeof(h_counters), cudaMemcpyDeviceToHost, st));
+                DDB_CUDA_TRY(cudaStreamSynchronize(st));
+                if (h_counters[1]) {
+                    set_error("ddb_sweep: candidate storage overflow (%d candidates)", h_counters[0]);
+                    return DDB_OUT_OF_MEMORY;
+                }
+                if (h_counters[4] == 0) break;
+            }
+        }
+        DDB_CUDA_TRY(cudaGetLastError());
+    }
+    DDB_CUDA_TRY(cudaEventRecord(ctx->ev[6], st));
+    unsigned long long h_pool = 0;
+    DDB_CUDA_TRY(cudaMemcpyAsync(h_counters, S->counters.p, sizeof(h_counters), cudaMemcpyDeviceToHost, st));
+    DDB_CUDA_TRY(cudaMemcpyAsync(&h_pool, S->pool_used_d.p, 8, cudaMemcpyDeviceToHost, st));
+    DDB_CUDA_TRY(cudaMemcpyAsync(&h_shared_fail, S->shared_fail.p, 4, cudaMemcpyDeviceToHost, st));
+    DDB_CUDA_TRY(cudaStreamSynchronize(st));
+    if (h_counters[1]) {
+        set_error("ddb_sweep: candidate storage overflow");
+        return DDB_OUT_OF_MEMORY;
+    }
+    float ms_f = 0.f, ms_s = 0.f;
+    DDB_CUDA_TRY(cudaEventElapsedTime(&ms_f, ctx->ev[4], ctx->ev[5]));
+    DDB_CUDA_TRY(cudaEventElapsedTime(&ms_s, ctx->ev[5], ctx->ev[6]));
+    ctx->timings.factor_ms = ms_f;
+    ctx->timings.sweep_ms = ms_s;
+    ctx->timings.sweep_launches = launches;
+    ctx->timings.big_steps = big_steps;
+    ctx->timings.candidates = h_counters[0];
+    S->ncand = h_counters[0];
+    S->pool_used = (int64_t)h_pool;
+    S->valid = true;
+    if (h_shared_fail) {
+        set_error("ddb_sweep: the equilibrated normal matrix is not positive definite (rank-deficient library "
+                  "or fewer samples than terms); this backend solves through the Gram matrix and has no QR fallback");
+        return DDB_NOT_POSITIVE_DEFINITE;
+    }
+    return DDB_OK;
+}
+
+int select_run(ddb_ctx* ctx, double* coef, double* lambda_opt, int32_t* iters, double* rss, int32_t* dof,
+               uint32_t* support_path, double* coef_path, int32_t* iters_path, int32_t* flags) {
+    SweepState* S = ctx->sweep;
+    if (!S || !S->valid || !S->have_rss) {
+        set_error("ddb_select: run ddb_sweep and ddb_rss first");
+        return DDB_BAD_STATE;
+    }
+    const int k = S->k, n_t = S->n_t, L = S->L, W = S->W;
+    cudaStream_t st = ctx->stream;
+    // device staging: coef (n_t*k) | lambda (n_t) | rss (n_t) | iters (n_t) | dof (n_t) | flags (n_t)
+    const size_t nk = (size_t)n_t * k;
+    DDB_TRY(S->out_tmp.reserve(nk * 8 + (size_t)n_t * (8 + 8 + 4 + 4 + 4) + 64));
+    double* d_coef = S->out_tmp.as<double>();
+    double* d_lam = d_coef + nk;
+    double* d_rss = d_lam + n_t;
+    int32_t* d_it = reinterpret_cast<int32_t*>(d_rss + n_t);
+    int32_t* d_dof = d_it + n_t;
+    int32_t* d_fl = d_dof + n_t;
+    DDB_CUDA_TRY(cudaEventRecord(ctx->ev[4], st));
+    SweepDev D = make_dev(ctx, S);
+    select_kernel<<<n_t, 256, 0, st>>>(D, S->rss_ptr, S->prm.selector, (double)S->m_total, d_coef, d_lam, d_it, d_rss,
+                                       d_dof, d_fl);
+    DDB_CUDA_TRY(cudaGetLastError());
+    DDB_CUDA_TRY(cudaEventRecord(ctx->ev[5], st));
+    if (coef) DDB_CUDA_TRY(cudaMemcpyAsync(coef, d_coef, nk * 8, cudaMemcpyDeviceToHost, st));
+    if (lambda_opt) DDB_CUDA_TRY(cudaMemcpyAsync(lambda_opt, d_lam, (size_t)n_t * 8, cudaMemcpyDeviceToHost, st));
+    if (rss) DDB_CUDA_TRY(cudaMemcpyAsync(rss, d_rss, (size_t)n_t * 8, cudaMemcpyDeviceToHost, st));
+    if (iters) DDB_CUDA_TRY(cudaMemcpyAsync(iters, d_it, (size_t)n_t * 4, cudaMemcpyDeviceToHost, st));
+    if (dof) DDB_CUDA_TRY(cudaMemcpyAsync(dof, d_dof, (size_t)n_t * 4, cudaMemcpyDeviceToHost, st));
+    if (flags) DDB_CUDA_TRY(cudaMemcpyAsync(flags, d_fl, (size_t)n_t * 4, cudaMemcpyDeviceToHost, st));
+    if (support_path)
+        DDB_CUDA_TRY(cudaMemcpyAsync(support_path, S->path_support.p, (size_t)n_t * L * W * 4, cudaMemcpyDeviceToHost, st));
+    if (coef_path)
+        DDB_CUDA_TRY(cudaMemcpyAsync(coef_path, S->path_coef.p, (size_t)n_t * L * k * 8, cudaMemcpyDeviceToHost, st));
+    if (iters_path)
+        DDB_CUDA_TRY(cudaMemcpyAsync(iters_path, S->path_iters.p, (size_t)n_t * L * 4, cudaMemcpyDeviceToHost, st));
+    DDB_CUDA_TRY(cudaEventRecord(ctx->ev[6], st));
+    DDB_CUDA_TRY(cudaStreamSynchronize(st));
+    float a = 0.f, b = 0.f;
+    DDB_CUDA_TRY(cudaEventElapsedTime(&a, ctx->ev[4], ctx->ev[5]));
+    DDB_CUDA_TRY(cudaEventElapsedTime(&b, ctx->ev[5], ctx->ev[6]));
+    ctx->timings.select_ms = a;
+    ctx->timings.d2h_ms = b;
+    ctx->timings.sweep_launches += 1;
+    return DDB_OK;
+}
+
+}  // namespace ddb
+
 using namespace ddb;
-#define NOT_YET(name) set_error(name ": not implemented yet"); return DDB_UNSUPPORTED
+
 extern "C" {
-int ddb_sweep(ddb_ctx*, const ddb_sweep_params*, const double*, int, int64_t) { NOT_YET("ddb_sweep"); }
-int64_t ddb_rss_count(const ddb_ctx*) { return 0; }
-int ddb_rss(ddb_ctx*, double*) { NOT_YET("ddb_rss"); }
-int ddb_rss_buffer(ddb_ctx*, double**) { NOT_YET("ddb_rss_buffer"); }
-int ddb_select(ddb_ctx*, double*, double*, int32_t*, double*, int32_t*, uint32_t*, double*, int32_t*, int32_t*) { NOT_YET("ddb_select"); }
-int ddb_solve_sparse(ddb_ctx*, const double*, const double*, int, int64_t, const ddb_sweep_params*, const double*, int, double*, double*, int32_t*, double*, int32_t*, uint32_t*) { NOT_YET("ddb_solve_sparse"); }
-int ddb_dmd_gram(ddb_ctx*, const double*, const double*, int, int64_t, double*, double*) { NOT_YET("ddb_dmd_gram"); }
-int ddb_dmd_operator(ddb_ctx*, const double*, const double*, int, double*) { NOT_YET("ddb_dmd_operator"); }
+
+int ddb_sweep(ddb_ctx* ctx, const ddb_sweep_params* params, const double* lambdas, int L, int64_t m_total) {
+    if (!ctx) {
+        set_error("ddb_sweep: null context");
+        return DDB_INVALID_ARG;
+    }
+    DDB_CUDA_TRY(cudaSetDevice(ctx->device));
+    return sweep_run(ctx, params, lambdas, L, m_total);
 }
+
+int64_t ddb_rss_count(const ddb_ctx* ctx) {
+    if (!ctx || !ctx->sweep || !ctx->sweep->valid) return 0;
+    return ctx->sweep->ncand;
+}
+
+int ddb_rss(ddb_ctx* ctx, double* dRss) {
+    if (!ctx) {
+        set_error("ddb_rss: null context");
+        return DDB_INVALID_ARG;
+    }
+    DDB_CUDA_TRY(cudaSetDevice(ctx->device));
+    if (!ctx->sweep || !ctx->sweep->valid) {
+        set_error("ddb_rss: run ddb_sweep first");
+        return DDB_BAD_STATE;
+    }
+    return rss_run(ctx, ctx->sweep, dRss);
+}
+
+int ddb_rss_buffer(ddb_ctx* ctx, double** dRss) {
+    if (!ctx || !dRss) {
+        set_error("ddb_rss_buffer: null argument");
+        return DDB_INVALID_ARG;
+    }
+    if (!ctx->sweep || !ctx->sweep->valid) {
+        set_error("ddb_rss_buffer: run ddb_sweep first");
+        return DDB_BAD_STATE;
+    }
+    DDB_CUDA_TRY(cudaSetDevice(ctx->device));
+    DDB_TRY(ctx->sweep->rss.reserve((size_t)std::max(1, ctx->sweep->ncand) * 8));
+    *dRss = ctx->sweep->rss.as<double>();
+    return DDB_OK;
+}
+
+int ddb_select(ddb_ctx* ctx, double* coef, double* lambda_opt, int32_t* iters, double* rss, int32_t* dof,
+               uint32_t* support_path, double* coef_path, int32_t* iters_path, int32_t* flags) {
+    if (!ctx) {
+        set_error("ddb_select: null context");
+        return DDB_INVALID_ARG;
+    }
+    DDB_CUDA_TRY(cudaSetDevice(ctx->device));
+    return select_run(ctx, coef, lambda_opt, iters, rss, dof, support_path, coef_path, iters_path, flags);
+}
+
+int ddb_solve_sparse(ddb_ctx* ctx, const double* X, const double* Y, int n_t, int64_t m,
+                     const ddb_sweep_params* params, const double* lambdas, int L, double* coef, double* lambda_opt,
+                     int32_t* iters, double* rss, int32_t* dof, uint32_t* support_path) {
+    DDB_TRY(ddb_upload(ctx, X, Y, n_t, m));
+    DDB_TRY(ddb_gram(ctx, nullptr));
+    DDB_TRY(ddb_sweep(ctx, params, lambdas, L, m));
+    DDB_TRY(ddb_rss(ctx, nullptr));
+    return ddb_select(ctx, coef, lambda_opt, iters, rss, dof, support_path, nullptr, nullptr, nullptr);
+}
+
+}  // extern "C"
