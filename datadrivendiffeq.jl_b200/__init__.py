@@ -1,3 +1,31 @@
-"""B200-native backend for the sparse-identification hot path of DataDrivenDiffEq.jl."""
+"""B200-native backend for the sparse-identification hot path of DataDrivenDiffEq.jl.
+
+``import ddb200`` (root shim) loads this directory as a package.  The numerical work is done by
+``libddb200.so`` (``csrc/``, sm_100a only) behind the C ABI of ``include/ddb.h``; this package is
+the host-side mirror of the reference's plug-in interface.  There is no CPU fallback.
+"""
 from . import _lib  # noqa: F401
 from .backend import Context, SweepOutput  # noqa: F401
+from .api import (  # noqa: F401
+    ADMM,
+    B200Sparse,
+    Basis,
+    ClippedAbsoluteDeviation,
+    ContinuousDataDrivenProblem,
+    DataDrivenCommonOptions,
+    DataDrivenProblem,
+    DataDrivenSolution,
+    DirectDataDrivenProblem,
+    DiscreteDataDrivenProblem,
+    HardThreshold,
+    SR3,
+    STLSQ,
+    SoftThreshold,
+    SparseRegressionResult,
+    construct_coefficients,
+    get_fit_targets,
+    monomial_basis,
+    polynomial_basis,
+    solve,
+)
+from . import dist, systems  # noqa: F401

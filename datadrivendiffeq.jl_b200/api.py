@@ -1,0 +1,424 @@
+"""Host-side mirror of the reference's plug-in interface for the sparse-identification path.
+
+The reference is Julia; its toolchain is absent from the build image and the GPU box, so the host
+side above the C ABI is written in Python with the reference's names, argument meaning and error
+behaviour, and the Julia glue (``julia/DataDrivenB200.jl``) mirrors this file one to one:
+
+=============================  ================================================================
+here                           reference
+=============================  ================================================================
+``Basis``, ``polynomial_basis``  ``src/basis/type.jl:50-89``, ``src/utils/basis_generators.jl:84-149``
+``ContinuousDataDrivenProblem``  ``src/problem/type.jl:92-113`` (+ ``get_implicit_data`` ``:433-435``)
+``DataDrivenCommonOptions``      ``src/utils/common_options.jl:22-54``
+``STLSQ`` / ``ADMM`` / ``SR3``   ``lib/DataDrivenSparse/src/algorithms/*.jl``
+``B200Sparse``                   the new ``AbstractSparseRegressionAlgorithm`` subtype
+``get_fit_targets``              ``src/commonsolve.jl:74-81`` (returns raw (X, Y): Theta is never built)
+``solve``                        ``solve!`` ``lib/DataDrivenSparse/src/commonsolve.jl:1-56``
+``SparseRegressionResult``       ``lib/DataDrivenSparse/src/result.jl:1-26``
+``construct_coefficients``       ``src/utils/build_basis.jl:154-157``
+=============================  ================================================================
+
+Options the backend cannot honour raise ``ValueError`` (the reference's ``ArgumentError``); nothing
+falls back to a CPU path.
+"""
+
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from .backend import Context, SweepOutput
+
+EPS = float(np.finfo(np.float64).eps)
+
+
+# ----------------------------------------------------------------------------------------------
+# Basis (monomial libraries only; SURVEY.md 8f/f3 lists general terms as "next")
+# ----------------------------------------------------------------------------------------------
+def _exponent_table(n: int, degree: int) -> np.ndarray:
+    """Exponent vectors of total degree <= ``degree`` with the LAST variable as the most significant
+    key and the first variable varying fastest, constant term first: the term order pinned by
+    ``test/Core/generators.jl:12-18``."""
+    vecs = []
+
+    def rec(idx: int, remaining: int, cur: list):
+        if idx < 0:
+            vecs.append(list(cur))
+            return
+        for p in range(remaining + 1):
+            cur[idx] = p
+            rec(idx - 1, remaining - p, cur)
+
+    rec(n - 1, degree, [0] * n)
+    return np.ascontiguousarray(np.asarray(vecs, dtype=np.uint8).T)
+
+
+@dataclass
+class Basis:
+    """A monomial candidate library over ``n`` states: ``exponents[i, j]`` = power of state i in
+    term j.  Duplicate and zero terms are removed without reordering, as ``__preprocess_basis``
+    does (``src/basis/type.jl:91-135``)."""
+
+    exponents: np.ndarray
+    names: Optional[List[str]] = None
+
+    def __post_init__(self):
+        e = np.asarray(self.exponents)
+        if e.ndim != 2:
+            raise ValueError("exponents must be an (n_states x n_terms) integer table")
+        if np.any(e < 0) or np.any(e != np.floor(e)):
+            raise ValueError("only monomial terms with non-negative integer powers are supported by the B200 backend")
+        e = e.astype(np.uint8)
+        keep, seen = [], set()
+        for j in range(e.shape[1]):
+            key = e[:, j].tobytes()
+            if key not in seen:
+                seen.add(key)
+                keep.append(j)
+        self.exponents = np.ascontiguousarray(e[:, keep])
+
+    @property
+    def n_states(self) -> int:
+        return self.exponents.shape[0]
+
+    def __len__(self) -> int:
+        return self.exponents.shape[1]
+
+    def term_strings(self) -> List[str]:
+        out = []
+        for j in range(len(self)):
+            parts = []
+            for i in range(self.n_states):
+                p = int(self.exponents[i, j])
+                if p == 1:
+                    parts.append(f"x{i + 1}")
+                elif p > 1:
+                    parts.append(f"x{i + 1}^{p}")
+            out.append("*".join(parts) if parts else "1")
+        return out
+
+
+def polynomial_basis(n_states: int, degree: int = 1) -> Basis:
+    """``polynomial_basis(x, c)`` (``src/utils/basis_generators.jl:111-126``)."""
+    if degree <= 0:
+        raise ValueError("degree must be positive")
+    return Basis(_exponent_table(int(n_states), int(degree)))
+
+
+def monomial_basis(n_states: int, degree: int = 1) -> Basis:
+    """``monomial_basis(x, c)`` = ``[1, x1, x1^2, ..., x1^c, x2, ...]`` (``basis_generators.jl:134-149``)."""
+    if degree <= 0:
+        raise ValueError("degree must be positive")
+    n = int(n_states)
+    e = np.zeros((n, n * degree + 1), dtype=np.uint8)
+    for i in range(n):
+        for j in range(degree):
+            e[i, i * degree + j + 1] = j + 1
+    return Basis(e)
+
+
+# ----------------------------------------------------------------------------------------------
+# Problems
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class DataDrivenProblem:
+    """``DataDrivenProblem{T, ctrl, probType}`` (``src/problem/type.jl:92-113``) without controls /
+    parameters (the backend rejects them)."""
+
+    X: np.ndarray
+    kind: str  # "continuous" | "discrete" | "direct"
+    DX: Optional[np.ndarray] = None
+    Y: Optional[np.ndarray] = None
+    t: Optional[np.ndarray] = None
+
+    def __post_init__(self):
+        self.X = np.asarray(self.X, dtype=np.float64)
+        for nm in ("DX", "Y"):
+            v = getattr(self, nm)
+            if v is not None:
+                v = np.atleast_2d(np.asarray(v, dtype=np.float64))
+                if v.shape[1] != self.X.shape[1]:
+                    raise ValueError("One or more measurements are not sized equally.")  # check_lengths, type.jl:421
+                setattr(self, nm, v)
+        for v in (self.X, self.DX, self.Y):  # check_domain, type.jl:418-420
+            if v is not None and not np.all(np.isfinite(v)):
+                raise ValueError("One or more measurements contain `NaN` or `Inf`.")
+
+    # get_implicit_data (type.jl:433-435) and get_oop_args (:444-455)
+    def fit_inputs(self):
+        if self.kind == "continuous":
+            return self.X, self.DX
+        if self.kind == "direct":
+            return self.X, self.Y
+        return self.X[:, :-1], self.X[:, 1:]
+
+
+def ContinuousDataDrivenProblem(X, t=None, DX=None) -> DataDrivenProblem:
+    if DX is None:
+        raise ValueError("the B200 backend needs DX (collocation is out of scope: SURVEY.md section 2)")
+    return DataDrivenProblem(X=X, kind="continuous", DX=DX, t=t)
+
+
+def DiscreteDataDrivenProblem(X, t=None) -> DataDrivenProblem:
+    return DataDrivenProblem(X=X, kind="discrete", t=t)
+
+
+def DirectDataDrivenProblem(X, Y, t=None) -> DataDrivenProblem:
+    return DataDrivenProblem(X=X, kind="direct", Y=Y, t=t)
+
+
+# ----------------------------------------------------------------------------------------------
+# Options and algorithms
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class DataDrivenCommonOptions:
+    """``src/utils/common_options.jl:22-54``.  Fields the backend cannot honour must keep their
+    defaults."""
+
+    maxiters: int = 100
+    abstol: float = math.sqrt(EPS)
+    reltol: float = math.sqrt(EPS)
+    progress: bool = False
+    verbose: bool = False
+    denoise: bool = False
+    normalize: Optional[str] = None  # DataNormalization{Nothing}
+    split: float = 1.0  # DataProcessing.split
+    batchsize: int = 0  # DataProcessing.batchsize
+    roundingmode: str = "RoundToZero"
+    digits: int = 10
+    selector: str = "bic"
+
+
+class SoftThreshold:
+    name = "SoftThreshold"
+
+
+class HardThreshold:
+    name = "HardThreshold"
+
+
+class ClippedAbsoluteDeviation:
+    name = "ClippedAbsoluteDeviation"
+
+    def __init__(self, rho: float = float("nan")):
+        self.rho = float(rho)
+
+
+def _thr(t) -> np.ndarray:
+    a = np.atleast_1d(np.asarray(t, dtype=np.float64)).copy()
+    if not np.all(a > 0):
+        raise AssertionError("Threshold must be positive definite")
+    return a
+
+
+class STLSQ:
+    """``STLSQ(thresholds, rho = 0)`` (``algorithms/STLSQ.jl:48-60``)"""
+
+    name = "STLSQ"
+
+    def __init__(self, thresholds=1e-1, rho: float = 0.0):
+        self.thresholds = _thr(thresholds)
+        if rho < 0:
+            raise AssertionError("Ridge regression parameter must be positive definite!")
+        self.rho = float(rho)
+        self.proximal = SoftThreshold()
+
+
+class ADMM:
+    """``ADMM(thresholds, rho = 1)`` (``algorithms/ADMM.jl:32-43``)"""
+
+    name = "ADMM"
+
+    def __init__(self, thresholds=1e-1, rho: float = 1.0):
+        self.thresholds = _thr(thresholds)
+        if not rho > 0:
+            raise AssertionError("Augmented Lagrangian parameter should be positive definite")
+        self.rho = float(rho)
+        self.proximal = SoftThreshold()
+
+
+class SR3:
+    """``SR3(thresholds, nu = 1, R = HardThreshold())`` (``algorithms/SR3.jl:45-73``): with the hard
+    threshold the stored thresholds are ``thr^2 / 2``."""
+
+    name = "SR3"
+
+    def __init__(self, thresholds=1e-1, nu: float = 1.0, proximal=None):
+        proximal = HardThreshold() if proximal is None else proximal
+        t = _thr(thresholds)
+        if not nu > 0:
+            raise AssertionError("Relaxation must be positive definite")
+        self.thresholds = t**2 / 2 if isinstance(proximal, HardThreshold) else t
+        self.rho = float(nu)
+        self.proximal = proximal
+
+
+class B200Sparse:
+    """The drop-in algorithm type: wraps one of the reference's sparse regression algorithms and runs
+    it on B200 GPUs.  ``group``: an initialised ``torch.distributed`` process group (one process per
+    GPU); every rank passes ITS row shard of the samples to ``solve`` and receives the full result.
+    """
+
+    def __init__(self, inner, device: int = 0, group=None):
+        if not isinstance(inner, (STLSQ, ADMM, SR3)):
+            raise ValueError("B200Sparse wraps STLSQ, ADMM or SR3")
+        self.inner = inner
+        self.device = int(device)
+        self.group = group
+        self._ctx: Optional[Context] = None
+
+    def context(self) -> Context:
+        if self._ctx is None:
+            self._ctx = Context(self.device)
+        return self._ctx
+
+
+# ----------------------------------------------------------------------------------------------
+# Results
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class SparseRegressionResult:
+    """``lib/DataDrivenSparse/src/result.jl:1-17``"""
+
+    coefficients: np.ndarray
+    dof: int
+    lambda_: np.ndarray
+    iterations: np.ndarray
+    testerror: Optional[float]
+    trainerror: float
+    retcode: int = 1
+
+
+@dataclass
+class DataDrivenSolution:
+    """The numeric content of ``DataDrivenSolution`` (``src/solution.jl:30-68``): the recovered model
+    as a rounded coefficient matrix over the input basis, plus the statistics StatsAPI exposes."""
+
+    basis: Basis
+    coefficients: np.ndarray  # after __construct_basis rounding
+    results: List[SparseRegressionResult]
+    rss: float
+    dof: int
+    nobs: int
+    retcode: int
+    timings: dict = field(default_factory=dict)
+    paths: Optional[SweepOutput] = None
+
+    def get_parameter_values(self) -> np.ndarray:
+        """Non-zero coefficients in equation-major order (``__build_eqs`` numbering)."""
+        out = []
+        for i in range(self.coefficients.shape[0]):
+            out.extend(self.coefficients[i][self.coefficients[i] != 0.0].tolist())
+        return np.asarray(out)
+
+    def equations(self) -> List[str]:
+        names = self.basis.term_strings()
+        eqs = []
+        for i in range(self.coefficients.shape[0]):
+            terms = [f"{self.coefficients[i, j]:.10g}*{names[j]}" for j in np.nonzero(self.coefficients[i])[0]]
+            eqs.append(" + ".join(terms) if terms else "0")
+        return eqs
+
+
+def construct_coefficients(C: np.ndarray, digits: int = 10) -> np.ndarray:
+    """``round.(X, RoundToZero, digits = digits)`` then zero ``abs <= eps``
+    (``src/utils/build_basis.jl:154-157``)."""
+    og = 10.0**digits
+    out = np.trunc(np.asarray(C, dtype=np.float64) * og) / og
+    out[np.abs(out) <= EPS] = 0.0
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# get_fit_targets / solve
+# ----------------------------------------------------------------------------------------------
+def get_fit_targets(alg: B200Sparse, prob: DataDrivenProblem, basis: Basis):
+    """``DataDrivenDiffEq.get_fit_targets`` for the B200 backend (``src/commonsolve.jl:74-81``):
+    returns the RAW states and targets instead of (Theta, Y) so that Theta is never built."""
+    X, Y = prob.fit_inputs()
+    if X.shape[0] != basis.n_states:
+        raise ValueError(f"basis has {basis.n_states} states but the problem has {X.shape[0]}")
+    return X, Y
+
+
+def _check_options(options: DataDrivenCommonOptions):
+    if options.denoise:
+        raise ValueError("B200Sparse: denoise=true (optimal shrinkage of Theta) is not supported: Theta is never materialised")
+    if options.normalize is not None:
+        raise ValueError("B200Sparse: only DataNormalization{Nothing} is supported (the Gram path equilibrates internally)")
+    if options.split != 1.0 or options.batchsize > 0:
+        raise ValueError("B200Sparse: train/test split and mini-batches are not supported")
+    if options.roundingmode != "RoundToZero":
+        raise ValueError("B200Sparse: only RoundToZero post-processing is supported")
+    if options.selector not in ("bic", "aic", "aicc", "rss"):
+        raise ValueError("B200Sparse: selector must be one of bic, aic, aicc, rss")
+
+
+def _params_for(ctx: Context, inner, options: DataDrivenCommonOptions):
+    prox = inner.proximal
+    return ctx.make_params(
+        algorithm=inner.name,
+        rho=inner.rho,
+        proximal=prox.name,
+        selector=options.selector,
+        maxiters=options.maxiters,
+        abstol=options.abstol,
+        reltol=options.reltol,
+        cad_rho=getattr(prox, "rho", float("nan")),
+    )
+
+
+def solve(prob: DataDrivenProblem, basis: Basis, alg: B200Sparse, options: Optional[DataDrivenCommonOptions] = None,
+          paths: bool = False) -> DataDrivenSolution:
+    """``solve(prob, basis, alg; options)`` = ``solve!(init(...))`` for the B200 backend.
+
+    Single GPU: one ``ddb_solve_sparse`` call with host buffers.  With ``alg.group`` set, every rank
+    passes its own row shard; the packed normal-equation blocks and the candidate-rss table are
+    summed with one all-reduce each (``dist.py``)."""
+    options = options or DataDrivenCommonOptions()
+    _check_options(options)
+    X, Y = get_fit_targets(alg, prob, basis)
+    ctx = alg.context()
+    ctx.set_library(basis.exponents)
+    prm = _params_for(ctx, alg.inner, options)
+    lambdas = alg.inner.thresholds
+    if alg.group is None:
+        if paths:
+            ctx.upload(X, Y)
+            ctx.gram()
+            ctx.sweep(prm, lambdas)
+            ctx.rss()
+            out = ctx.select(paths=True)
+        else:
+            out = ctx.solve_sparse(X, Y, prm, lambdas)
+        m_total = X.shape[1]
+    else:
+        from . import dist
+
+        out, m_total = dist.solve_sharded(ctx, X, Y, prm, lambdas, alg.group, paths=paths)
+    C = out.coefficients
+    # __sparse_regression (commonsolve.jl:37-55): trainerror = sum(abs2, Y - C*Theta) = sum of the selected rss
+    res = SparseRegressionResult(
+        coefficients=C,
+        dof=int(np.sum(np.abs(C) > 0.0)),
+        lambda_=out.lambda_opt,
+        iterations=out.iterations,
+        testerror=None,
+        trainerror=float(np.sum(out.rss)),
+        retcode=1 if not np.any(out.flags & 1) else 2,
+    )
+    Cr = construct_coefficients(C, options.digits)
+    return DataDrivenSolution(
+        basis=basis,
+        coefficients=Cr,
+        results=[res],
+        rss=res.trainerror,
+        dof=int(np.sum(Cr != 0.0)),
+        nobs=int(Y.size if alg.group is None else Y.shape[0] * m_total),
+        retcode=res.retcode,
+        timings=ctx.timings(),
+        paths=out if paths else None,
+    )

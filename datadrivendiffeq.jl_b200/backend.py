@@ -132,6 +132,11 @@ class Context:
         self.n_t = R.shape[1]
         _lib.check(self._lib.ddb_gram_upload(self._ctx, _lib.ptr(G), _lib.ptr(R), _lib.ptr(yy), self.n_t))
 
+    def gram_upload_ptr(self, pG: int, pR: int, pyy: int, n_t: int):
+        """Install blocks from raw (host or device) pointers, e.g. an all-reduced torch tensor."""
+        self.n_t = int(n_t)
+        _lib.check(self._lib.ddb_gram_upload(self._ctx, C.c_void_p(pG), C.c_void_p(pR), C.c_void_p(pyy), self.n_t))
+
     # -- sweep ------------------------------------------------------------------------------
     @staticmethod
     def make_params(algorithm="STLSQ", rho=0.0, proximal="SoftThreshold", selector="bic", maxiters=100,

@@ -262,12 +262,37 @@ int ddb_gram_upload(ddb_ctx* ctx, const double* G, const double* R, const double
     const size_t k = ctx->k, nt = n_t;
     DDB_TRY(ctx->d_packed.reserve((size_t)ddb_gram_count(ctx) * sizeof(double)));
     double* p = ctx->d_packed.as<double>();
-    DDB_CUDA_TRY(cudaMemcpyAsync(p, G, k * k * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    DDB_CUDA_TRY(cudaMemcpyAsync(p + k * k, R, k * nt * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    DDB_CUDA_TRY(cudaMemcpyAsync(p + k * k + k * nt, yy, nt * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    // cudaMemcpyDefault: the three sources may be host or device pointers (e.g. an all-reduced device buffer)
+    DDB_CUDA_TRY(cudaMemcpyAsync(p, G, k * k * sizeof(double), cudaMemcpyDefault, ctx->stream));
+    DDB_CUDA_TRY(cudaMemcpyAsync(p + k * k, R, k * nt * sizeof(double), cudaMemcpyDefault, ctx->stream));
+    DDB_CUDA_TRY(cudaMemcpyAsync(p + k * k + k * nt, yy, nt * sizeof(double), cudaMemcpyDefault, ctx->stream));
     DDB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     ctx->have_gram = true;
     return DDB_OK;
+}
+
+int64_t ddb_gram_plan_describe(int kaug, int64_t m, int nctas, int64_t* segments, int64_t cap, int64_t* info) {
+    if (kaug <= 0 || m <= 0 || nctas < 0) {
+        set_error("ddb_gram_plan_describe: kaug, m must be positive");
+        return DDB_INVALID_ARG;
+    }
+    const int bt = (kaug <= 64) ? 64 : 128;
+    if (nctas == 0) nctas = (bt == 64) ? 148 * 3 : 148;
+    GramPlan pl;
+    build_gram_plan(pl, kaug, m, nctas, bt, 16);
+    if (info) {
+        info[0] = pl.bt, info[1] = pl.ks, info[2] = pl.nblk, info[3] = pl.npairs, info[4] = pl.nstages, info[5] = pl.nslots;
+    }
+    int64_t w = 0;
+    for (int c = 0; c < pl.nctas; ++c)
+        for (int sg = pl.cta_seg_begin[c]; sg < pl.cta_seg_begin[c + 1]; ++sg, ++w) {
+            if (segments && w < cap) {
+                const GramSegment& g = pl.segments[sg];
+                int64_t* o = segments + 6 * w;
+                o[0] = c, o[1] = g.bi, o[2] = g.bj, o[3] = g.slot, o[4] = g.stage_begin, o[5] = g.stage_end;
+            }
+        }
+    return w;
 }
 
 int ddb_get_timings(const ddb_ctx* ctx, ddb_timings* out) {

@@ -529,19 +529,36 @@ void build_gram_plan(GramPlan& plan, int kaug, int64_t m, int nctas, int bt, int
         used[found] += need;
         next_cta = (found + 1) % nctas;
     }
-    // (2) the remaining (pair, stage) stream fills every CTA up to the common budget, contiguously.
-    {
+    // (2) the remaining (pair, stage) stream fills every CTA up to the common budget, contiguously:
+    // CTA c owns the part of the stream whose cumulative cost lies in (cap[c-1], cap[c]].
+    if (!rest.empty() && ns > 0) {
+        double rest_total = 0.0;
+        for (int p : rest) rest_total += cost[p] * (double)ns;
+        std::vector<double> cap(nctas);
+        double free_total = 0.0;
+        for (int c = 0; c < nctas; ++c) free_total += std::max(0.0, budget - used[c]);
+        double acc = 0.0;
+        for (int c = 0; c < nctas; ++c) {
+            acc += std::max(0.0, budget - used[c]) * (free_total > 0.0 ? rest_total / free_total : 0.0);
+            cap[c] = acc;
+        }
+        cap[nctas - 1] = rest_total * (1.0 + 1e-9) + 1.0;
         int c = 0;
+        double cum = 0.0;  // cost of the stream before the current pair
         for (int p : rest) {
             int64_t st = 0;
             while (st < ns) {
-                while (c < nctas - 1 && budget - used[c] < 0.5 * cost[p]) ++c;
-                int64_t take = (c == nctas - 1) ? (ns - st) : (int64_t)((budget - used[c]) / cost[p] + 0.5);
-                take = std::max<int64_t>(1, std::min<int64_t>(take, ns - st));
-                tmp.push_back({c, p, st, st + take});
-                used[c] += cost[p] * (double)take;
-                st += take;
+                // last stage (exclusive) of pair p whose midpoint still falls into CTA c's share
+                int64_t end = (int64_t)std::floor((cap[c] - cum) / cost[p] + 0.5);
+                end = std::min<int64_t>(std::max<int64_t>(end, st), ns);
+                if (end > st) {
+                    tmp.push_back({c, p, st, end});
+                    st = end;
+                }
+                if (st < ns) ++c;  // CTA c is full
+                if (c >= nctas) c = nctas - 1;
             }
+            cum += cost[p] * (double)ns;
         }
     }
     // slots: grouped by pair, inside a pair ordered by CTA (fixed summation order)

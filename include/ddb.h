@@ -147,7 +147,8 @@ int ddb_gram_buffer(ddb_ctx* ctx, double** dPacked);
 
 /* Copy the packed blocks to the host; any output may be NULL.  G k x k, R k x n_t, yy n_t. */
 int ddb_gram_download(ddb_ctx* ctx, double* G, double* R, double* yy);
-/* Install blocks computed elsewhere (restart / tests).  n_t and m_total describe the data set. */
+/* Install blocks computed elsewhere (restart, tests, or the all-reduced sum of the ranks' partial
+ * blocks).  G, R, yy may be host or device pointers. */
 int ddb_gram_upload(ddb_ctx* ctx, const double* G, const double* R, const double* yy, int n_t);
 
 /* ---- stage 3: thresholded sweep ---------------------------------------------------------------- */
@@ -206,6 +207,13 @@ int ddb_dmd_gram(ddb_ctx* ctx, const double* dX, const double* dY, int n, int64_
 int ddb_dmd_operator(ddb_ctx* ctx, const double* dP, const double* dQ, int n, double* dK);
 
 /* ---- introspection ----------------------------------------------------------------------------- */
+
+/* Host-only: the work plan the Gram stage would use for an augmented library of kaug = k + n_t rows,
+ * m local samples and nctas persistent CTAs (0 = choose as the library would for 148 SMs).  Writes up
+ * to cap segments as 6 int64 each: {cta, block_row, block_col, slot, stage_begin, stage_end}; returns
+ * the number of segments (or a negative status).  info (may be NULL) receives {block_tile,
+ * samples_per_stage, blocks_per_dim, block_pairs, stages, slots}.  Needs no GPU. */
+int64_t ddb_gram_plan_describe(int kaug, int64_t m, int nctas, int64_t* segments, int64_t cap, int64_t* info);
 
 int ddb_get_timings(const ddb_ctx* ctx, ddb_timings* out);
 /* The context's CUDA stream (cudaStream_t) so a caller can order its own work after ours. */

@@ -1,0 +1,363 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the committed golden
+fixtures.  Criteria of BASELINE.json: identical support at every threshold, coefficients within 1e-10
+relative in FP64 (un-rounded SparseRegressionResult.coefficients)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import ddb200
+import oracle
+from ddb200 import systems
+
+pytestmark = pytest.mark.gpu
+
+COEF_RTOL = 1e-10  # north star: coefficients agree within 1e-10 relative
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = ddb200.Context(0)
+    yield c
+    c.close()
+
+
+def _gram_ref(ex, X, Y):
+    Th = oracle.evaluate_library(ex, X)
+    return Th @ Th.T, Th @ Y.T, (Y * Y).sum(1)
+
+
+# ------------------------------------------------------------------------------------------------
+# stage 1+2: fused library evaluation + normal-equation blocks
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize(
+    "n,deg,n_t,m",
+    [(3, 2, 3, 1001), (3, 5, 3, 1001), (3, 5, 3, 16), (3, 5, 1, 17), (1, 8, 2, 333), (5, 3, 5, 5000), (2, 1, 7, 64),
+     (14, 2, 8, 4096), (14, 2, 14, 1000), (20, 2, 20, 3001), (64, 2, 64, 2500), (64, 2, 64, 15)],
+)
+def test_gram_matches_oracle(ctx, n, deg, n_t, m):
+    rng = np.random.default_rng(n * 1000 + deg * 100 + m)
+    X = rng.standard_normal((n, m))
+    Y = rng.standard_normal((n_t, m))
+    ex = oracle.polynomial_exponents(n, deg)
+    ctx.set_library(ex)
+    ctx.upload(X, Y)
+    ctx.gram()
+    G, R, yy = ctx.gram_download()
+    G0, R0, yy0 = _gram_ref(ex, X, Y)
+    sc = np.sqrt(np.outer(np.diag(G0), np.diag(G0)))
+    assert np.max(np.abs(G - G0) / sc) < 1e-13  # summation-order differences only
+    assert np.max(np.abs(R - R0)) < 1e-13 * np.sqrt(np.max(np.diag(G0)) * np.max(yy0))
+    np.testing.assert_allclose(yy, yy0, rtol=1e-13)
+    np.testing.assert_array_equal(G, G.T)  # exactly symmetric by construction
+
+
+def test_gram_is_bit_reproducible(ctx):
+    rng = np.random.default_rng(7)
+    X = rng.standard_normal((64, 4000))
+    Y = rng.standard_normal((64, 4000))
+    ctx.set_library(oracle.polynomial_exponents(64, 2))
+    ctx.upload(X, Y)
+    ctx.gram()
+    a = ctx.gram_download()
+    ctx.gram()
+    b = ctx.gram_download()
+    for u, v in zip(a, b):
+        np.testing.assert_array_equal(u, v)  # fixed-order tile reduction, no floating-point atomics
+
+
+def test_gram_monomial_library_and_golden(ctx, golden_dir):
+    g = np.load(f"{golden_dir}/c1_readme_lorenz_stlsq.npz")
+    ctx.set_library(g["exps"])
+    ctx.upload(g["X"], g["Y"])
+    ctx.gram()
+    G, R, yy = ctx.gram_download()
+    sc = np.sqrt(np.outer(np.diag(g["G"]), np.diag(g["G"])))
+    assert np.max(np.abs(G - g["G"]) / sc) < 1e-13
+    # monomial_basis library (powers of single states)
+    ex = oracle.monomial_exponents(3, 4)
+    ctx.set_library(ex)
+    ctx.upload(g["X"], g["Y"])
+    ctx.gram()
+    G, R, yy = ctx.gram_download()
+    G0, R0, _ = _gram_ref(ex, g["X"], g["Y"])
+    assert np.max(np.abs(G - G0) / np.sqrt(np.outer(np.diag(G0), np.diag(G0)))) < 1e-13
+
+
+def test_gram_linearity_over_sample_shards(ctx):
+    """Row sharding property: blocks of the whole = sum of the blocks of contiguous shards."""
+    rng = np.random.default_rng(11)
+    m = 30011
+    X = rng.standard_normal((8, m))
+    Y = rng.standard_normal((8, m))
+    ctx.set_library(oracle.polynomial_exponents(8, 3))
+    ctx.upload(X, Y)
+    ctx.gram()
+    G, R, yy = ctx.gram_download()
+    Gs = Rs = ys = 0.0
+    for r in range(3):
+        lo, hi = ddb200.dist.shard_range(m, r, 3)
+        ctx.upload(X[:, lo:hi], Y[:, lo:hi])
+        ctx.gram()
+        g_, r_, y_ = ctx.gram_download()
+        Gs, Rs, ys = Gs + g_, Rs + r_, ys + y_
+    np.testing.assert_allclose(Gs, G, rtol=1e-12, atol=1e-9)
+    np.testing.assert_allclose(Rs, R, rtol=1e-12, atol=1e-9)
+    np.testing.assert_allclose(ys, yy, rtol=1e-13)
+
+
+# ------------------------------------------------------------------------------------------------
+# stage 3: thresholded sweep (+ exact rss pass + selection) against the golden fixtures
+# ------------------------------------------------------------------------------------------------
+def _run(ctx, g, alg_name, rho=0.0, prox="SoftThreshold", thresholds=None, maxiters=100):
+    ctx.set_library(g["exps"])
+    ctx.upload(g["X"], g["Y"])
+    ctx.gram()
+    prm = ctx.make_params(alg_name, rho=rho, proximal=prox, maxiters=maxiters)
+    ctx.sweep(prm, g["thresholds"] if thresholds is None else thresholds)
+    ctx.rss()
+    return ctx.select(paths=True)
+
+
+def _check_against_golden(out, g, rtol, strict_lambda=True):
+    k = int(g["k"])
+    sp = np.unpackbits(g["support_path"], axis=-1)[:, :, :k].astype(bool)
+    np.testing.assert_array_equal(out.support_path, sp)  # identical support at EVERY threshold
+    np.testing.assert_array_equal(out.coefficients != 0, g["coefficients"] != 0)
+    nz = g["coefficients"] != 0
+    if nz.any():
+        rel = np.abs(out.coefficients[nz] - g["coefficients"][nz]) / np.abs(g["coefficients"][nz])
+        assert rel.max() <= rtol, rel.max()
+    if strict_lambda:
+        np.testing.assert_allclose(out.lambda_opt, g["lambda_opt"], rtol=1e-15)
+    else:
+        # ADMM / SR3 iterates of neighbouring thresholds converge to the same point up to reltol ~ 1e-8, so
+        # their rss differ by ~1e-16 relative -- below the rounding of ANY rss evaluation (the reference's
+        # BLAS dot products included).  Which of those numerically tied iterates the selector keeps is
+        # rounding noise; the optimal threshold must then name an equivalent iterate.
+        lams = np.sort(g["thresholds"])
+        for i in range(out.coefficients.shape[0]):
+            if np.isclose(out.lambda_opt[i], g["lambda_opt"][i], rtol=1e-15):
+                continue
+            j = int(np.argmin(np.abs(lams - out.lambda_opt[i])))
+            assert np.isclose(lams[j], out.lambda_opt[i], rtol=1e-15)
+            ref_at_j = g["coef_path"][i, j]
+            np.testing.assert_array_equal(ref_at_j != 0, g["coefficients"][i] != 0)
+            np.testing.assert_allclose(ref_at_j, g["coefficients"][i], rtol=1e-6, atol=0)
+    # converged coefficients at every threshold
+    cp = g["coef_path"]
+    nzp = cp != 0
+    if nzp.any():
+        assert (np.abs(out.coef_path[nzp] - cp[nzp]) / np.abs(cp[nzp])).max() <= rtol
+    assert not np.any(out.flags)
+
+
+@pytest.mark.parametrize("name", ["c1_readme_lorenz_stlsq", "lorenz_noisy_deg3_stlsq", "l96_n8_noisy_stlsq"])
+def test_stlsq_golden(ctx, golden_dir, name):
+    g = np.load(f"{golden_dir}/{name}.npz")
+    out = _run(ctx, g, "STLSQ")
+    _check_against_golden(out, g, COEF_RTOL)
+    # the reference solves rho = 0 by pivoted QR on Theta, we solve the equilibrated normal equations:
+    # the initial full least squares can differ by ~1e-7 absolute, which may shift the inner
+    # iteration count by one; supports and converged coefficients above are compared strictly
+    assert np.max(np.abs(out.iterations - g["iterations"])) <= 1
+    assert np.max(np.abs(out.iters_path - g["iters_path"])) <= 1
+
+
+def test_stlsq_ridge_golden(ctx, golden_dir):
+    g = np.load(f"{golden_dir}/lorenz_noisy_deg3_stlsq_ridge.npz")
+    out = _run(ctx, g, "STLSQ", rho=1e-4)
+    _check_against_golden(out, g, COEF_RTOL)
+    np.testing.assert_array_equal(out.iterations, g["iterations"])
+
+
+@pytest.mark.parametrize(
+    "name,alg,prox",
+    [("gauss_deg2_admm", "ADMM", "SoftThreshold"), ("gauss_deg2_sr3_hard", "SR3", "HardThreshold"),
+     ("gauss_deg2_sr3_soft", "SR3", "SoftThreshold"), ("gauss_deg2_sr3_cad", "SR3", "ClippedAbsoluteDeviation")],
+)
+def test_admm_sr3_golden(ctx, golden_dir, name, alg, prox):
+    g = np.load(f"{golden_dir}/{name}.npz")
+    out = _run(ctx, g, alg, rho=1.0, prox=prox)
+    _check_against_golden(out, g, COEF_RTOL if alg == "ADMM" else 1e-7, strict_lambda=False)
+    np.testing.assert_array_equal(out.iterations, g["iterations"])
+    np.testing.assert_array_equal(out.iters_path, g["iters_path"])
+
+
+def test_unsorted_thresholds_are_sorted(ctx, golden_dir):
+    g = np.load(f"{golden_dir}/lorenz_noisy_deg3_stlsq.npz")
+    out = _run(ctx, g, "STLSQ", thresholds=g["thresholds"][::-1].copy())  # solver.jl:77-79
+    _check_against_golden(out, g, COEF_RTOL)
+
+
+@pytest.mark.parametrize("selector", ["aic", "aicc", "rss"])
+def test_other_selectors(ctx, golden_dir, selector):
+    g = np.load(f"{golden_dir}/lorenz_noisy_deg3_stlsq.npz")
+    sel = {"aic": oracle.aic, "aicc": oracle.aicc, "rss": oracle.rss}[selector]
+    Th = oracle.evaluate_library(g["exps"], g["X"])
+    ref = oracle.sparse_regression(oracle.STLSQ(g["thresholds"]), Th, g["Y"], oracle.CommonOptions(selector=sel))
+    ctx.set_library(g["exps"])
+    ctx.upload(g["X"], g["Y"])
+    ctx.gram()
+    prm = ctx.make_params("STLSQ", selector=selector)
+    ctx.sweep(prm, g["thresholds"])
+    ctx.rss()
+    out = ctx.select()
+    np.testing.assert_array_equal(out.coefficients != 0, ref.coefficients != 0)
+    np.testing.assert_allclose(out.lambda_opt, ref.lambdas, rtol=1e-15)
+    np.testing.assert_allclose(out.coefficients, ref.coefficients, rtol=COEF_RTOL, atol=0)
+
+
+def test_maxiters_limits_the_inner_loop(ctx, golden_dir):
+    g = np.load(f"{golden_dir}/gauss_deg2_admm.npz")
+    Th = oracle.evaluate_library(g["exps"], g["X"])
+    ref = oracle.sparse_regression(oracle.ADMM(g["thresholds"], 1.0), Th, g["Y"], oracle.CommonOptions(maxiters=3))
+    out = _run(ctx, g, "ADMM", rho=1.0, maxiters=3)
+    np.testing.assert_array_equal(out.iterations, ref.iterations)
+    np.testing.assert_array_equal(out.coefficients != 0, ref.coefficients != 0)
+    np.testing.assert_allclose(out.coefficients, ref.coefficients, rtol=COEF_RTOL, atol=0)
+
+
+def test_large_active_sets_use_the_blocked_path(ctx):
+    """Noisy Lorenz-96 (n = 16, 153 terms): at tiny thresholds almost every term stays active, which
+    exceeds the 128-term shared-memory solver and exercises the batched blocked Cholesky."""
+    rng = np.random.default_rng(5)
+    X, D = systems.lorenz96_ensemble(2000, n=16, seed=2, samples_per_traj=500)
+    D = D + 5e-2 * rng.standard_normal(D.shape)
+    ex = oracle.polynomial_exponents(16, 2)
+    lams = 10.0 ** np.arange(-7, 0.01, 0.5)
+    Th = oracle.evaluate_library(ex, X)
+    traces = []
+    ref = oracle.sparse_regression(oracle.STLSQ(lams), Th[:, :], D[:4], traces=traces)
+    ctx.set_library(ex)
+    ctx.upload(X, D[:4])
+    ctx.gram()
+    ctx.sweep(ctx.make_params("STLSQ"), lams)
+    ctx.rss()
+    out = ctx.select(paths=True)
+    assert ctx.timings()["big_steps"] > 0
+    for i in range(4):
+        np.testing.assert_array_equal(out.support_path[i], np.stack(traces[i].support_path))
+    nz = ref.coefficients != 0
+    np.testing.assert_array_equal(out.coefficients != 0, nz)
+    assert (np.abs(out.coefficients[nz] - ref.coefficients[nz]) / np.abs(ref.coefficients[nz])).max() <= COEF_RTOL
+
+
+def test_zero_target_and_zero_library_term(ctx):
+    """Zero-coefficient regression must not throw (sparse_linear_solve.jl:148-181); an identically
+    zero library column gets coefficient 0 (minimum-norm solution of the reference's pivoted QR)."""
+    rng = np.random.default_rng(3)
+    X = rng.standard_normal((2, 500))
+    X[1] = 0.0  # every term containing x2 is identically zero
+    Y = np.vstack([np.zeros(500), 2.0 * X[0]])
+    ex = oracle.polynomial_exponents(2, 2)
+    ctx.set_library(ex)
+    ctx.upload(X, Y)
+    ctx.gram()
+    ctx.sweep(ctx.make_params("STLSQ"), np.array([0.1, 0.2]))
+    ctx.rss()
+    out = ctx.select()
+    assert np.all(out.coefficients[0] == 0.0)
+    assert np.count_nonzero(out.coefficients[1]) == 1 and abs(out.coefficients[1, 1] - 2.0) < 1e-12
+
+
+def test_rank_deficient_library_is_reported(ctx):
+    rng = np.random.default_rng(4)
+    X = rng.standard_normal((2, 10))  # 15 terms, 10 samples: Gram matrix singular
+    ctx.set_library(oracle.polynomial_exponents(2, 4))
+    ctx.upload(X, X.copy())
+    ctx.gram()
+    with pytest.raises(ddb200._lib.DDBError) as ei:
+        ctx.sweep(ctx.make_params("STLSQ"), np.array([0.1]))
+    assert ei.value.status == -5  # DDB_NOT_POSITIVE_DEFINITE, never a silent fallback
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference-facing call: solve(prob, basis, B200Sparse(STLSQ(...)))
+# ------------------------------------------------------------------------------------------------
+def test_solve_readme_lorenz(golden_dir):
+    g = np.load(f"{golden_dir}/c1_readme_lorenz_stlsq.npz")
+    prob = ddb200.ContinuousDataDrivenProblem(g["X"], DX=g["Y"])
+    basis = ddb200.polynomial_basis(3, 5)
+    sol = ddb200.solve(prob, basis, ddb200.B200Sparse(ddb200.STLSQ(g["thresholds"])))
+    res = sol.results[0]
+    np.testing.assert_array_equal(res.coefficients != 0, g["coefficients"] != 0)
+    nz = g["coefficients"] != 0
+    assert (np.abs(res.coefficients[nz] - g["coefficients"][nz]) / np.abs(g["coefficients"][nz])).max() <= COEF_RTOL
+    # __construct_basis truncates to 10 digits (RoundToZero): values 1e-13 apart can land on neighbouring
+    # 1e-10 grid points, so the post-processed matrices agree to one grid step
+    np.testing.assert_allclose(sol.coefficients, oracle.construct_coefficients(g["coefficients"]), rtol=0, atol=1.01e-10)
+    np.testing.assert_array_equal(sol.coefficients != 0, g["coefficients"] != 0)
+    np.testing.assert_allclose(sol.get_parameter_values(), [-10.0, 10.0, 28.0, -1.0, -1.0, 1.0, -2.6666666666], rtol=1e-9)
+    assert sol.dof == 7 and sol.retcode == 1
+    # trainerror = sum(abs2, Y - C*Theta)  (lib/DataDrivenSparse/src/commonsolve.jl:37)
+    Th = oracle.evaluate_library(g["exps"], g["X"])
+    assert abs(res.trainerror - np.sum((g["Y"] - res.coefficients @ Th) ** 2)) <= 1e-6 * max(res.trainerror, 1e-20) + 1e-18
+
+
+def test_solve_discrete_problem():
+    rng = np.random.default_rng(9)
+    A = np.array([[0.9, -0.2], [0.1, 0.7]])
+    x = [rng.standard_normal(2)]
+    for _ in range(300):
+        x.append(A @ x[-1] + 1e-6 * rng.standard_normal(2))
+    X = np.stack(x, axis=1)
+    sol = ddb200.solve(ddb200.DiscreteDataDrivenProblem(X), ddb200.polynomial_basis(2, 2),
+                       ddb200.B200Sparse(ddb200.STLSQ(np.array([0.01, 0.05]))))
+    C = sol.results[0].coefficients
+    np.testing.assert_allclose(C[:, [1, 3]], A, atol=1e-4)
+    assert sol.dof == 4
+
+
+# ------------------------------------------------------------------------------------------------
+# full-size properties (BASELINE.json configs C2 / C3), data generated on the device
+# ------------------------------------------------------------------------------------------------
+def test_c3_full_size_lorenz96_recovers_the_model(ctx):
+    n, m = 64, 10_000_000
+    ex = oracle.polynomial_exponents(n, 2)
+    ctx.set_library(ex)
+    try:
+        ctx.generate(1, n, m, 0, 0, 0.0)
+    except ddb200._lib.DDBError as e:  # pragma: no cover
+        if e.status == -7:
+            pytest.skip("not enough device memory for 10^7 x 128 doubles")
+        raise
+    ctx.gram()
+    lams = 10.0 ** np.arange(-5, -1 + 1e-9, 0.1)
+    ctx.sweep(ctx.make_params("STLSQ"), lams)
+    ctx.rss()
+    out = ctx.select(paths=True)
+    term = {tuple(np.nonzero(ex[:, j])[0].tolist()) if ex[:, j].max() < 2 else (int(np.argmax(ex[:, j])),) * 2: j
+            for j in range(ex.shape[1])}
+    for i in range(n):
+        ip, im1, im2 = (i + 1) % n, (i - 1) % n, (i - 2) % n
+        want = {term[()]: 8.0, term[(i,)]: -1.0, term[tuple(sorted((im1, ip)))]: 1.0, term[tuple(sorted((im2, im1)))]: -1.0}
+        got = {int(j): float(out.coefficients[i, j]) for j in np.nonzero(out.coefficients[i])[0]}
+        assert set(got) == set(want), (i, got)
+        for j, v in want.items():
+            assert abs(got[j] - v) <= 1e-9 * abs(v)
+        # support is the true model at every threshold of the grid (all true coefficients exceed 0.1)
+        assert np.all(out.support_path[i].sum(axis=1) == 4)
+    assert np.all(out.dof == 4) and np.all(out.rss < 1e-12 * m)
+    # bic ties between identical candidates resolve to the LAST threshold (solver.jl:100 uses <=)
+    np.testing.assert_allclose(out.lambda_opt, lams[-1], rtol=1e-15)
+
+
+def test_c2_full_size_lorenz_recovers_the_model(ctx):
+    m = 10_000_000
+    ex = oracle.polynomial_exponents(3, 5)
+    ctx.set_library(ex)
+    ctx.generate(0, 3, m, 0, 0, 0.0)
+    ctx.gram()
+    G, R, yy = ctx.gram_download()
+    np.testing.assert_array_equal(G, G.T)
+    assert G[0, 0] == m  # constant term: sum of ones, exact
+    lams = 10.0 ** np.arange(-5, -1 + 1e-9, 0.1)
+    ctx.sweep(ctx.make_params("STLSQ"), lams)
+    ctx.rss()
+    out = ctx.select()
+    assert out.dof.tolist() == [2, 3, 2]
+    terms = {tuple(ex[:, j]): j for j in range(ex.shape[1])}
+    np.testing.assert_allclose(out.coefficients[0, [terms[(1, 0, 0)], terms[(0, 1, 0)]]], [-10.0, 10.0], rtol=1e-8)
+    np.testing.assert_allclose(out.coefficients[2, [terms[(1, 1, 0)], terms[(0, 0, 1)]]], [1.0, -8.0 / 3.0], rtol=1e-8)
