@@ -1,0 +1,116 @@
+# DataDrivenB200.jl — Julia glue for libddb200.so (C ABI in include/ddb.h).
+#
+# UNTESTED IN THIS REPOSITORY: neither the build container nor the GPU box has a Julia toolchain
+# (probed: no `julia` binary, no ~/.julia).  The file mirrors, call for call, the Python host layer
+# `datadrivendiffeq.jl_b200/api.py` + `backend.py`, which IS tested against the same shared library.
+#
+# Usage (drop-in, the reference's `solve` API is unchanged):
+#
+#     using DataDrivenDiffEq, DataDrivenSparse, DataDrivenB200
+#     res = solve(prob, basis, B200Sparse(STLSQ(exp10.(-5:0.1:-1))))
+#
+# The backend is a new algorithm type.  It defines exactly the two methods the reference's plug-in
+# mechanism dispatches on (SURVEY.md section 8b): `get_fit_targets` (src/commonsolve.jl:74-81) so that
+# `init` never evaluates the basis on the data, and `solve!` (more specific than
+# lib/DataDrivenSparse/src/commonsolve.jl:1-5).
+module DataDrivenB200
+
+using DataDrivenDiffEq, DataDrivenSparse, CommonSolve
+using DataDrivenDiffEq: InternalDataDrivenProblem, DataDrivenSolution, DDReturnCode, get_implicit_data,
+                        get_oop_args, __construct_basis, states, equations
+import Symbolics
+
+const LIB = get(ENV, "DDB200_LIB", joinpath(@__DIR__, "..", "libddb200.so"))
+
+struct SweepParams            # ddb_sweep_params
+    algorithm::Int32; proximal::Int32; selector::Int32; maxiters::Int32
+    abstol::Float64; reltol::Float64; rho::Float64; cad_rho::Float64
+end
+
+struct B200Sparse{A <: Union{STLSQ, ADMM, SR3}} <: DataDrivenSparse.AbstractSparseRegressionAlgorithm
+    inner::A
+    device::Int
+end
+B200Sparse(inner) = B200Sparse(inner, 0)
+Base.summary(x::B200Sparse) = "B200(" * summary(x.inner) * ")"
+
+function check(status::Cint)
+    status == 0 && return
+    msg = unsafe_string(ccall((:ddb_last_error, LIB), Cstring, ()))
+    throw(ErrorException("ddb status $status: $msg"))   # never a silent CPU fallback
+end
+
+# HOOK 1: hand `init` the RAW states and targets; Theta is never built (the default
+# DataNormalization{Nothing} then is a no-op, src/utils/data_processing.jl:64-66,114-115).
+function DataDrivenDiffEq.get_fit_targets(::B200Sparse, prob::DataDrivenDiffEq.AbstractDataDrivenProblem,
+        basis::DataDrivenDiffEq.AbstractBasis)
+    X = first(get_oop_args(prob))
+    Y = get_implicit_data(prob)
+    return X, Y
+end
+
+# exponent table of a monomial basis, n x k, in the basis' own term order
+function exponent_table(basis)
+    xs = states(basis)
+    eqs = [eq.rhs for eq in equations(basis)]
+    E = zeros(UInt8, length(xs), length(eqs))
+    for (j, term) in enumerate(eqs), (i, x) in enumerate(xs)
+        d = Symbolics.degree(term, x)
+        E[i, j] = d
+    end
+    # reject anything that is not a pure monomial of the states
+    for (j, term) in enumerate(eqs)
+        rebuilt = prod(xs[i]^Int(E[i, j]) for i in eachindex(xs); init = Symbolics.Num(1))
+        isequal(Symbolics.simplify(term - rebuilt), 0) ||
+            throw(ArgumentError("B200Sparse supports monomial library terms only; term $j is $(term)"))
+    end
+    return E
+end
+
+prox_id(::SoftThreshold) = Int32(0)
+prox_id(::HardThreshold) = Int32(1)
+prox_id(::ClippedAbsoluteDeviation) = Int32(2)
+alg_id(::STLSQ) = Int32(0); alg_id(::ADMM) = Int32(1); alg_id(::SR3) = Int32(2)
+relax(a::STLSQ) = Float64(a.rho); relax(a::ADMM) = Float64(a.rho); relax(a::SR3) = Float64(a.nu)
+selector_id(f) = f === DataDrivenDiffEq.bic ? Int32(0) : f === DataDrivenDiffEq.aic ? Int32(1) :
+                 f === DataDrivenDiffEq.aicc ? Int32(2) : f === DataDrivenDiffEq.rss ? Int32(3) :
+                 throw(ArgumentError("B200Sparse: selector must be bic, aic, aicc or rss"))
+
+# HOOK 2
+function CommonSolve.solve!(ps::InternalDataDrivenProblem{<:B200Sparse})
+    (; alg, basis, traindata, testdata, problem, options) = ps
+    options.denoise && throw(ArgumentError("B200Sparse: denoise=true is not supported"))
+    options.data_processing.split == 1.0 && options.data_processing.batchsize <= 0 ||
+        throw(ArgumentError("B200Sparse: train/test split and mini-batches are not supported"))
+    X, Y = first(traindata)          # single batch; column order is irrelevant to the Gram sums
+    X = Matrix{Float64}(X); Y = Matrix{Float64}(Y)
+    n, m = size(X); n_t = size(Y, 1)
+    E = exponent_table(basis); k = size(E, 2)
+    inner = alg.inner
+    lambdas = collect(Float64, DataDrivenSparse.get_thresholds(inner))
+    prox = DataDrivenSparse.get_proximal(inner)
+    prm = Ref(SweepParams(alg_id(inner), prox_id(prox), selector_id(options.selector), options.maxiters,
+        options.abstol, options.reltol, relax(inner), prox isa ClippedAbsoluteDeviation ? Float64(prox.ρ) : NaN))
+    coef = zeros(n_t, k); lam = zeros(n_t); iters = zeros(Int32, n_t); rss = zeros(n_t); dof = zeros(Int32, n_t)
+    ctx = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:ddb_ctx_create, LIB), Cint, (Cint, Ptr{Ptr{Cvoid}}), alg.device, ctx))
+    try
+        GC.@preserve X Y E lambdas coef lam iters rss dof begin
+            check(ccall((:ddb_set_library_monomial, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}), ctx[], n, k, E))
+            check(ccall((:ddb_solve_sparse, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cint, Int64, Ptr{SweepParams}, Ptr{Float64}, Cint,
+                 Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Float64}, Ptr{Int32}, Ptr{UInt32}),
+                ctx[], X, Y, n_t, m, prm, lambdas, length(lambdas), coef, lam, iters, rss, dof, C_NULL))
+        end
+    finally
+        ccall((:ddb_ctx_destroy, LIB), Cint, (Ptr{Cvoid},), ctx[])
+    end
+    # finish exactly like the reference (lib/DataDrivenSparse/src/commonsolve.jl:13-24, 37-55)
+    result = DataDrivenSparse.SparseRegressionResult(coef, sum(abs.(coef) .> 0.0), lam, Int.(iters), nothing,
+        sum(rss), DDReturnCode(1))
+    new_basis = __construct_basis(copy(coef), basis, problem, options)
+    return DataDrivenSolution(new_basis, problem, alg, [result], ps, result.retcode)
+end
+
+export B200Sparse
+end # module

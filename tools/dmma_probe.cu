@@ -185,6 +185,7 @@ __global__ void __launch_bounds__(256) k_build(double* out, int stages, int n) {
     const int col = threadIdx.x & 127, tl = threadIdx.x >> 7;
     const int o0 = col & 63, o1 = (col * 7) & 63;
     double acc[NA][NB][2];
+    long long xacc = 0; double cmul = 1.0000001 + 1e-9 * n;
     for (int i = 0; i < NA; ++i) for (int j = 0; j < NB; ++j) acc[i][j][0] = acc[i][j][1] = 0;
     for (int st = 0; st < stages; ++st) {
         const double* pa = tile + t * LDT + wm * (8 * NA) + g;
@@ -209,11 +210,23 @@ __global__ void __launch_bounds__(256) k_build(double* out, int stages, int n) {
             for (int i = 0; i < NA; ++i) a[i] = pa[kk * 4 * LDT + 8 * i];
 #pragma unroll
             for (int j = 0; j < NB; ++j) b[j] = pb[kk * 4 * LDT + 8 * j];
-            if (!(MODE & 8)) {
+            if (MODE & 128) {
+                // all products of the k-step in ONE asm block (back-to-back DMULs), then the stores
+                double p0, p1, p2, p3;
+                asm volatile("mul.rn.f64 %0, %4, %8;\n\tmul.rn.f64 %1, %5, %9;\n\tmul.rn.f64 %2, %6, %10;\n\tmul.rn.f64 %3, %7, %11;"
+                             : "=d"(p0), "=d"(p1), "=d"(p2), "=d"(p3)
+                             : "d"(f0[0]), "d"(f0[1]), "d"(f0[2]), "d"(f0[3]), "d"(f1[0]), "d"(f1[1]), "d"(f1[2]), "d"(f1[3]));
+                dst[(kk * 4 + 0) * LDT] = p0; dst[(kk * 4 + 1) * LDT] = p1; dst[(kk * 4 + 2) * LDT] = p2; dst[(kk * 4 + 3) * LDT] = p3;
+            } else if (!(MODE & 8)) {
 #pragma unroll
             for (int q = 0; q < NL / 2; ++q) {
                 double p = f0[q];
-                if (MODE & 2) asm volatile("mul.rn.f64 %0, %0, %1;" : "+d"(p) : "d"(f1[q])); else p = f1[q];
+                if (MODE & 64) {
+                    // loads are consumed by integer ops only; the multiply works on register constants
+                    xacc ^= __double_as_longlong(f0[q]) + __double_as_longlong(f1[q]);
+                    p = 1.0 + q;
+                    if (MODE & 2) asm volatile("mul.rn.f64 %0, %0, %1;" : "+d"(p) : "d"(cmul));
+                } else if (MODE & 2) asm volatile("mul.rn.f64 %0, %0, %1;" : "+d"(p) : "d"(f1[q])); else p = f1[q];
                 if (MODE & 4) dst[(kk * (NL / 2) + q) * LDT] = p; else if (p == 12345.678) out[1] = p;
             }
             }
@@ -237,6 +250,163 @@ __global__ void __launch_bounds__(256) k_build(double* out, int stages, int n) {
                 dst[(kk * (NL / 2) + q) * LDT] = p;
             }
             }
+        }
+        {
+            unsigned long long* b = &bar[st & 1];
+            const unsigned parity = (st >> 1) & 1;
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(b)) : "memory");
+            unsigned done;
+            do {
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(s32(b)), "r"(parity) : "memory");
+            } while (!done);
+        }
+    }
+    double s = 0;
+    for (int i = 0; i < NA; ++i) for (int j = 0; j < NB; ++j) s += acc[i][j][0] + acc[i][j][1];
+    if (s == 12345.678 || xacc == 77) out[0] = s;
+}
+
+// (E16) 16 warps of 32x32: as (D, mbarrier) plus the Theta build traffic: per k-step NL LDS.64 from a raw region, NL/2 DMUL, NL/2 STS.64
+// into a scratch tile.  MODE bit0: loads, bit1: muls, bit2: stores.
+template <int NL, int MODE>
+__global__ void __launch_bounds__(512) k_build16(double* out, int stages, int n) {
+    constexpr int LDT = 132, KS = 16, NA = 4, NB = 4;
+    extern __shared__ double sm[];
+    double* tile = sm;                       // 2 * KS * LDT
+    double* scratch = tile + 2 * KS * LDT;   // 2 * KS * LDT
+    double* raw = scratch + 2 * KS * LDT;    // KS * 2n
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(raw + KS * 2 * n);
+    for (int e = threadIdx.x; e < 4 * KS * LDT + KS * 2 * n; e += blockDim.x) sm[e] = 1.0 + 1e-6 * e;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(&bar[0])), "r"(16));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(&bar[1])), "r"(16));
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const int wm = warp & 3, wn = (warp >> 2) & 3;
+    const int col = threadIdx.x & 127, tl = (threadIdx.x >> 7) & 1, half = threadIdx.x >> 8;
+    const int o0 = col & 63, o1 = (col * 7) & 63;
+    double acc[NA][NB][2];
+    for (int i = 0; i < NA; ++i) for (int j = 0; j < NB; ++j) acc[i][j][0] = acc[i][j][1] = 0;
+    for (int st = 0; st < stages; ++st) {
+        const double* pa = tile + t * LDT + wm * (8 * NA) + g;
+        const double* pb = tile + KS * LDT + t * LDT + wn * (8 * NB) + g;
+        double* dst = scratch + tl * KS * LDT + col;
+#pragma unroll
+        for (int kk = 0; kk < KS / 4; ++kk) {
+            double f0[NL / 2], f1[NL / 2];
+#pragma unroll
+            for (int q = 0; q < NL / 2; ++q) {
+                const int sidx = half * 8 + kk * (NL / 2) + q;
+                if (MODE & 32) {
+                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(f0[q]) : "r"(s32(raw + o0 + sidx * n)));
+                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(f1[q]) : "r"(s32(raw + o1 + sidx * n)));
+                } else {
+                f0[q] = (MODE & 1) ? raw[o0 + sidx * n] : 1.0 + q;
+                f1[q] = (MODE & 1) ? raw[o1 + sidx * n] : 2.0 + q + st;
+                }
+            }
+            double a[NA], b[NB];
+#pragma unroll
+            for (int i = 0; i < NA; ++i) a[i] = pa[kk * 4 * LDT + 8 * i];
+#pragma unroll
+            for (int j = 0; j < NB; ++j) b[j] = pb[kk * 4 * LDT + 8 * j];
+            if (!(MODE & 8)) {
+#pragma unroll
+            for (int q = 0; q < NL / 2; ++q) {
+                double p = f0[q];
+                if (MODE & 2) asm volatile("mul.rn.f64 %0, %0, %1;" : "+d"(p) : "d"(f1[q])); else p = f1[q];
+                if (MODE & 4) dst[(half * 8 + kk * (NL / 2) + q) * LDT] = p; else if (p == 12345.678) out[1] = p;
+            }
+            }
+#pragma unroll
+            for (int i = 0; i < NA; ++i)
+#pragma unroll
+                for (int j = 0; j < NB; ++j) {
+                    dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                    if ((MODE & 16) && j == 3 && (i & 1) == 1 && i / 2 < NL / 2) {  // sprinkle: one product every 8 DMMAs
+                        const int q = i / 2;
+                        double p = f0[q];
+                        asm volatile("mul.rn.f64 %0, %0, %1;" : "+d"(p) : "d"(f1[q]));
+                        dst[(half * 8 + kk * (NL / 2) + q) * LDT] = p;
+                    }
+                }
+            if ((MODE & 8) && !(MODE & 16)) {
+#pragma unroll
+            for (int q = 0; q < NL / 2; ++q) {
+                double p = f0[q];
+                asm volatile("mul.rn.f64 %0, %0, %1;" : "+d"(p) : "d"(f1[q]));
+                dst[(half * 8 + kk * (NL / 2) + q) * LDT] = p;
+            }
+            }
+        }
+        {
+            unsigned long long* b = &bar[st & 1];
+            const unsigned parity = (st >> 1) & 1;
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(b)) : "memory");
+            unsigned done;
+            do {
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(s32(b)), "r"(parity) : "memory");
+            } while (!done);
+        }
+    }
+    double s = 0;
+    for (int i = 0; i < NA; ++i) for (int j = 0; j < NB; ++j) s += acc[i][j][0] + acc[i][j][1];
+    if (s == 12345.678) out[0] = s;
+}
+
+
+
+// (F) build phase for the whole stage FIRST (own basic block, closed by a warp barrier), then the 4 MMA k-steps
+template <int CHUNK>
+__global__ void __launch_bounds__(256) k_phase(double* out, int stages, int n) {
+    constexpr int LDT = 132, KS = 16, NA = 8, NB = 4;
+    extern __shared__ double sm[];
+    double* tile = sm;
+    double* scratch = tile + 2 * KS * LDT;
+    double* raw = scratch + 2 * KS * LDT;
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(raw + KS * 2 * n);
+    for (int e = threadIdx.x; e < 4 * KS * LDT + KS * 2 * n; e += blockDim.x) sm[e] = 1.0 + 1e-6 * e;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(&bar[0])), "r"(8));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(&bar[1])), "r"(8));
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const int wm = warp & 1, wn = (warp >> 1) & 3;
+    const int col = threadIdx.x & 127, tl = threadIdx.x >> 7;
+    const int o0 = col & 63, o1 = (col * 7) & 63;
+    double acc[NA][NB][2];
+    for (int i = 0; i < NA; ++i) for (int j = 0; j < NB; ++j) acc[i][j][0] = acc[i][j][1] = 0;
+    for (int st = 0; st < stages; ++st) {
+        const double* pa = tile + t * LDT + wm * (8 * NA) + g;
+        const double* pb = tile + KS * LDT + t * LDT + wn * (8 * NB) + g;
+        double* dst = scratch + tl * KS * LDT + col;
+#pragma unroll
+        for (int c0 = 0; c0 < KS; c0 += CHUNK) {
+            double f0[CHUNK], f1[CHUNK];
+#pragma unroll
+            for (int q = 0; q < CHUNK; ++q) {
+                f0[q] = raw[o0 + (c0 + q) * n];
+                f1[q] = raw[o1 + (c0 + q) * n];
+            }
+#pragma unroll
+            for (int q = 0; q < CHUNK; ++q) dst[(c0 + q) * LDT] = f0[q] * f1[q];
+        }
+        asm volatile("bar.warp.sync 0xffffffff;" ::: "memory");
+#pragma unroll
+        for (int kk = 0; kk < KS / 4; ++kk) {
+            double a[NA], b[NB];
+#pragma unroll
+            for (int i = 0; i < NA; ++i) a[i] = pa[kk * 4 * LDT + 8 * i];
+#pragma unroll
+            for (int j = 0; j < NB; ++j) b[j] = pb[kk * 4 * LDT + 8 * j];
+#pragma unroll
+            for (int i = 0; i < NA; ++i)
+#pragma unroll
+                for (int j = 0; j < NB; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
         {
             unsigned long long* b = &bar[st & 1];
@@ -299,7 +469,15 @@ int main() {
         const int n = 64; const size_t smem = (4 * 16 * 132 + 16 * 2 * n) * 8 + 64;
 #define RUNB(NL, MODE, name) { auto k = k_build<NL, MODE>; CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         float ms = time_ms([&] { k<<<sms, 256, smem>>>(out, stages, n); }); printf("\"" name "\": %.2f, ", 512.0 * 32 * 4 * stages * sms * 8 / ms * 1e-9); }
-        RUNB(8, 0, "build_none") RUNB(8, 1, "build_lds") RUNB(8, 3, "build_lds_mul") RUNB(8, 4, "build_sts") RUNB(8, 6, "build_mul_sts") RUNB(8, 7, "build_all") RUNB(8, 15, "build_all_after") RUNB(8, 31, "build_all_sprinkle") RUNB(8, 47, "build_vol_after") RUNB(8, 63, "build_vol_sprinkle")
+        RUNB(8, 0, "build_none") RUNB(8, 1, "build_lds") RUNB(8, 3, "build_lds_mul") RUNB(8, 4, "build_sts") RUNB(8, 6, "build_mul_sts") RUNB(8, 7, "build_all") RUNB(8, 15, "build_all_after") RUNB(8, 31, "build_all_sprinkle") { auto k = k_build16<4, 7>; CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          float ms = time_ms([&] { k<<<sms, 512, smem>>>(out, stages, n); }); printf("\"build16_all\": %.2f, ", 512.0 * 16 * 4 * stages * sms * 16 / ms * 1e-9); }
+        { auto k = k_build16<4, 0>; CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          float ms = time_ms([&] { k<<<sms, 512, smem>>>(out, stages, n); }); printf("\"build16_none\": %.2f, ", 512.0 * 16 * 4 * stages * sms * 16 / ms * 1e-9); }
+        RUNB(8, 71, "build_lds_int_mulconst_sts") RUNB(8, 69, "build_lds_int_sts") RUNB(8, 135, "build_all_grouped") { auto k = k_phase<8>; CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          float ms = time_ms([&] { k<<<sms, 256, smem>>>(out, stages, n); }); printf("\"phase_chunk8\": %.2f, ", 512.0 * 32 * 4 * stages * sms * 8 / ms * 1e-9); }
+        { auto k = k_phase<16>; CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          float ms = time_ms([&] { k<<<sms, 256, smem>>>(out, stages, n); }); printf("\"phase_chunk16\": %.2f, ", 512.0 * 32 * 4 * stages * sms * 8 / ms * 1e-9); }
+        RUNB(8, 47, "build_vol_after") RUNB(8, 63, "build_vol_sprinkle")
     }
     printf("\"sms\": %d}\n", sms);
     return 0;
