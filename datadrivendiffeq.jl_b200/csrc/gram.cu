@@ -63,6 +63,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "memory");
     } while (!done);
 }
+// non-blocking phase test (the result comes back through the scoreboard: issue early, consume late)
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n"
+        "  .reg .pred p;\n"
+        "  mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "  selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return done != 0;
+}
 // 1-D bulk asynchronous copy global -> shared through the TMA unit (SASS UBLKCP).
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -236,44 +250,53 @@ __global__ void __launch_bounds__(GramCfg<BT>::kThreads, GramCfg<BT>::kMinBlocks
     for (int sg = seg_begin; sg < seg_end; ++sg) total += (int)(args.segs[sg].stage_end - args.segs[sg].stage_begin);
     if (total == 0) return;
 
-    // ---- raw-sample cursor (warp 0): TMA tiles in item order, across segment boundaries -------------
+    // ---- raw-sample cursor: TMA tiles in item order, across segment boundaries.  Every warp tracks the
+    // (uniform) cursor; the warp whose turn it is (item mod #warps) issues the copies, so that no single
+    // warp carries the issue cost every stage.
     int tma_seg = seg_begin;
-    int64_t tma_stage = args.segs[seg_begin].stage_begin, tma_seg_end = args.segs[seg_begin].stage_end;
+    int tma_stage = (int)args.segs[seg_begin].stage_begin, tma_seg_end = (int)args.segs[seg_begin].stage_end;
     int tma_item = 0;
     uint32_t ragged_slots = 0;  // slots whose ones column currently carries zero padding
-    auto request_samples = [&]() {  // all lanes of warp 0; requests the raw samples of item `tma_item`
+    const int ragged_stage = (args.m % KS) ? (int)(nstages_total - 1) : -1;
+    auto request_samples = [&]() {  // all warps; requests the raw samples of item `tma_item`
         if (tma_item >= total) return;
         const int slot = tma_item & (kNVS - 1);
-        double* dst = vring + slot * vdoubles;
-        const int64_t s0 = tma_stage * KS;
-        const bool full = (tma_stage + 1 < nstages_total) || (args.m - s0 == KS);
-        if (full) {
+        const bool mine = (tma_item % Cfg::kWarps) == warp;
+        if (tma_stage != ragged_stage) {
             if ((ragged_slots >> slot) & 1) {  // restore the ones column a ragged stage overwrote
-                if (lane < KS) dst[kVOnes + lane] = 1.0;
                 ragged_slots &= ~(1u << slot);
-                __syncwarp();
+                if (mine) {
+                    if (lane < KS) vring[slot * vdoubles + kVOnes + lane] = 1.0;
+                    __syncwarp();
+                }
             }
-            if (lane == 0) {
+            if (mine && lane == 0) {
+                double* dst = vring + slot * vdoubles + kVX;
+                const int64_t s0 = (int64_t)tma_stage * KS;
                 mbar_expect_tx(&vfull[slot], xbytes + ybytes);
-                bulk_g2s(dst + kVX, args.X + s0 * n, xbytes, &vfull[slot]);
-                bulk_g2s(dst + kVX + KS * n, args.Y + s0 * n_t, ybytes, &vfull[slot]);
+                bulk_g2s(dst, args.X + s0 * n, xbytes, &vfull[slot]);
+                bulk_g2s(dst + KS * n, args.Y + s0 * n_t, ybytes, &vfull[slot]);
             }
         } else {
             // ragged last stage of the shard: plain loads with zero fill (a bulk copy needs 16-byte
             // multiples), ones[s] = 0 for the padding samples
-            const int valid = (int)(args.m - s0);
-            for (int e = lane; e < KS * n; e += 32) dst[kVX + e] = (e < valid * n) ? args.X[s0 * n + e] : 0.0;
-            for (int e = lane; e < KS * n_t; e += 32)
-                dst[kVX + KS * n + e] = (e < valid * n_t) ? args.Y[s0 * n_t + e] : 0.0;
-            if (lane < KS) dst[kVOnes + lane] = (lane < valid) ? 1.0 : 0.0;
             ragged_slots |= 1u << slot;
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&vfull[slot]);
+            if (mine) {
+                double* dst = vring + slot * vdoubles;
+                const int64_t s0 = (int64_t)tma_stage * KS;
+                const int valid = (int)(args.m - s0);
+                for (int e = lane; e < KS * n; e += 32) dst[kVX + e] = (e < valid * n) ? args.X[s0 * n + e] : 0.0;
+                for (int e = lane; e < KS * n_t; e += 32)
+                    dst[kVX + KS * n + e] = (e < valid * n_t) ? args.Y[s0 * n_t + e] : 0.0;
+                if (lane < KS) dst[kVOnes + lane] = (lane < valid) ? 1.0 : 0.0;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&vfull[slot]);
+            }
         }
         ++tma_item;
         if (++tma_stage == tma_seg_end && ++tma_seg < seg_end) {
-            tma_stage = args.segs[tma_seg].stage_begin;
-            tma_seg_end = args.segs[tma_seg].stage_end;
+            tma_stage = (int)args.segs[tma_seg].stage_begin;
+            tma_seg_end = (int)args.segs[tma_seg].stage_end;
         }
     };
 
@@ -324,10 +347,8 @@ __global__ void __launch_bounds__(GramCfg<BT>::kThreads, GramCfg<BT>::kMinBlocks
     };
 
     // ---- prologue: request the first raw tiles, build Theta(0..kAhead-1) completely -------------------
-    if (warp == 0) {
 #pragma unroll 1
-        for (int i = 0; i < kNVS; ++i) request_samples();
-    }
+    for (int i = 0; i < kNVS; ++i) request_samples();
     load_jobs();
 #pragma unroll 1
     for (int it = 0; it < kAhead && it < total; ++it) {
@@ -360,6 +381,7 @@ __global__ void __launch_bounds__(GramCfg<BT>::kThreads, GramCfg<BT>::kMinBlocks
         wn = warp;
     }
     int item = 0;
+    bool ready_t = false, ready_v = false;
     for (int sg = seg_begin; sg < seg_end; ++sg) {
         const GramSegment seg = args.segs[sg];
         const bool same = (seg.bi == seg.bj);
@@ -390,12 +412,17 @@ __global__ void __launch_bounds__(GramCfg<BT>::kThreads, GramCfg<BT>::kMinBlocks
         const int nst = (int)(seg.stage_end - seg.stage_begin);
         for (int q = 0; q < nst; ++q, ++item) {
             const int tslot = item & (kNTS - 1);
-            mbar_wait(&tfull[tslot], (uint32_t)((item / kNTS) & 1));
+            if (!ready_t) mbar_wait(&tfull[tslot], (uint32_t)((item / kNTS) & 1));
             // the raw tile of item+kNVS reuses the slot of item, which build(item) finished reading
-            if (warp == 0) request_samples();
+            request_samples();
             const int nitem = item + kAhead;  // the item whose Theta tiles this stage builds
             const bool have_next = (nitem < total);
-            if (have_next) mbar_wait(&vfull[nitem & (kNVS - 1)], (uint32_t)((nitem / kNVS) & 1));
+            if (have_next && !ready_v) mbar_wait(&vfull[nitem & (kNVS - 1)], (uint32_t)((nitem / kNVS) & 1));
+            // test the NEXT stage's barriers now; the answers travel back while this stage computes.  A
+            // warp that is ahead of the others sees "not yet" and blocks at the top of the next stage,
+            // the slowest warp (the one that sets the pace) never waits for the round trip.
+            ready_t = (item + 1 < total) ? mbar_test(&tfull[(item + 1) & (kNTS - 1)], (uint32_t)(((item + 1) / kNTS) & 1)) : true;
+            ready_v = (nitem + 1 < total) ? mbar_test(&vfull[(nitem + 1) & (kNVS - 1)], (uint32_t)(((nitem + 1) / kNVS) & 1)) : true;
 
             const double* tI = tring + tslot * Cfg::kStageDoubles;
             const double* tJ = same ? tI : tI + KS * LDT;
