@@ -82,14 +82,8 @@ __global__ void prep_rhs_kernel(const double* __restrict__ R, int k, int n_t, co
 // ---------------------------------------------------------------------------------------------
 constexpr int kNB = 32;
 
-__global__ void __launch_bounds__(256) chol_panel_kernel(double* base, size_t stride, int ld, const int* na_arr,
-                                                         int na_all, int j0, int* fail) {
-    const int b = blockIdx.x;
-    const int na = na_arr ? na_arr[b] : na_all;
-    if (j0 >= na) return;
-    double* A = base + (size_t)b * stride;
-    const int nb = min(kNB, na - j0);
-    __shared__ double D[kNB][kNB + 1];
+// Factor the nb x nb diagonal block at (j0, j0) in place (whole CTA, D is shared scratch).
+__device__ void factor_diag_block(double* A, int ld, int j0, int nb, int* fail_flag, double (*D)[kNB + 1]) {
     const int tid = threadIdx.x;
     for (int e = tid; e < kNB * kNB; e += blockDim.x) {
         const int i = e / kNB, j = e % kNB;
@@ -102,7 +96,7 @@ __global__ void __launch_bounds__(256) chol_panel_kernel(double* base, size_t st
         if (tid == 0) {
             const double d = D[c][c];
             if (!(d > 0.0)) {
-                atomicExch(&fail[b], 1);
+                atomicExch(fail_flag, 1);
                 D[c][c] = 1.0;  // keep going with a harmless pivot; the flag invalidates the result
             } else {
                 D[c][c] = sqrt(d);
@@ -121,28 +115,67 @@ __global__ void __launch_bounds__(256) chol_panel_kernel(double* base, size_t st
         const int i = e / nb, j = e % nb;
         if (j <= i) A[(size_t)(j0 + i) * ld + j0 + j] = D[i][j];
     }
-    // panel below the diagonal block: row i <- row i * L_jj^-T  (forward substitution per row)
-    for (int i = j0 + nb + tid; i < na; i += blockDim.x) {
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) chol_diag_kernel(double* base, size_t stride, int ld, const int* na_arr,
+                                                        int na_all, int j0, int* fail) {
+    const int b = blockIdx.x;
+    const int na = na_arr ? na_arr[b] : na_all;
+    if (j0 >= na) return;
+    __shared__ double D[kNB][kNB + 1];
+    factor_diag_block(base + (size_t)b * stride, ld, j0, min(kNB, na - j0), &fail[b], D);
+}
+
+// Panel below an already factored diagonal block: row i <- row i * L_jj^-T.  grid (row tiles of 256, batch);
+// rows are staged through shared memory so that global accesses are coalesced (256 contiguous bytes per row).
+__global__ void __launch_bounds__(256) chol_panel_kernel(double* base, size_t stride, int ld, const int* na_arr,
+                                                         int na_all, int j0) {
+    const int b = blockIdx.y;
+    const int na = na_arr ? na_arr[b] : na_all;
+    if (j0 >= na) return;
+    double* A = base + (size_t)b * stride;
+    const int nb = min(kNB, na - j0);
+    const int r0 = j0 + nb + blockIdx.x * 256;
+    if (r0 >= na) return;
+    __shared__ double D[kNB][kNB + 1];
+    extern __shared__ double rows_sm[];  // 256 x (kNB + 1)
+    const int tid = threadIdx.x;
+    for (int e = tid; e < kNB * kNB; e += blockDim.x) {
+        const int i = e / kNB, j = e % kNB;
+        D[i][j] = (i < nb && j < nb && j <= i) ? A[(size_t)(j0 + i) * ld + j0 + j] : (i == j ? 1.0 : 0.0);
+    }
+    const int nrows = min(256, na - r0);
+    for (int e = tid; e < nrows * kNB; e += blockDim.x) {
+        const int r = e / kNB, c = e % kNB;
+        rows_sm[r * (kNB + 1) + c] = (c < nb) ? A[(size_t)(r0 + r) * ld + j0 + c] : 0.0;
+    }
+    __syncthreads();
+    if (tid < nrows) {
         double a[kNB];
-        double* row = A + (size_t)i * ld + j0;
+        double* row = rows_sm + tid * (kNB + 1);
 #pragma unroll
-        for (int c = 0; c < kNB; ++c) a[c] = (c < nb) ? row[c] : 0.0;
+        for (int c = 0; c < kNB; ++c) a[c] = row[c];
 #pragma unroll
         for (int c = 0; c < kNB; ++c) {
-            double s = a[c];
+            double sacc = a[c];
 #pragma unroll
-            for (int t = 0; t < c; ++t) s -= a[t] * D[c][t];
-            a[c] = s / D[c][c];
+            for (int t = 0; t < c; ++t) sacc -= a[t] * D[c][t];
+            a[c] = sacc / D[c][c];
         }
 #pragma unroll
-        for (int c = 0; c < kNB; ++c)
-            if (c < nb) row[c] = a[c];
+        for (int c = 0; c < kNB; ++c) row[c] = a[c];
+    }
+    __syncthreads();
+    for (int e = tid; e < nrows * kNB; e += blockDim.x) {
+        const int r = e / kNB, c = e % kNB;
+        if (c < nb) A[(size_t)(r0 + r) * ld + j0 + c] = rows_sm[r * (kNB + 1) + c];
     }
 }
 
 // trailing update C[i][j] -= sum_t P[i][t] P[j][t] for i >= j >= j0 + kNB, 64x64 tiles, lower tiles only
 __global__ void __launch_bounds__(256) chol_update_kernel(double* base, size_t stride, int ld, const int* na_arr,
-                                                          int na_all, int j0) {
+                                                          int na_all, int j0, int* fail) {
     const int b = blockIdx.z;
     const int na = na_arr ? na_arr[b] : na_all;
     const int t0 = j0 + kNB;
@@ -186,20 +219,29 @@ __global__ void __launch_bounds__(256) chol_update_kernel(double* base, size_t s
             const int r = r0 + tr + i, c = c0 + tc + j;
             if (r < na && c <= r) A[(size_t)r * ld + c] -= acc[i][j];
         }
+    // the CTA that just finished the top-left trailing tile also factors the NEXT diagonal block, so the
+    // next panel kernel finds it ready (saves one launch per block column)
+    if (ti == 0 && tj == 0) {
+        __threadfence_block();
+        __syncthreads();
+        double(*D)[kNB + 1] = reinterpret_cast<double(*)[kNB + 1]>(&Pi[0][0]);
+        factor_diag_block(A, ld, t0, min(kNB, na - t0), &fail[b], D);
+    }
 }
 
 static int chol_batched(ddb_ctx* ctx, double* base, size_t stride, int ld, const int* d_na, int na_max, int batch,
                         int* d_fail, int* launches) {
+    const size_t panel_smem = 256 * (kNB + 1) * sizeof(double);
+    DDB_CUDA_TRY(cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem));
+    chol_diag_kernel<<<batch, 256, 0, ctx->stream>>>(base, stride, ld, d_na, na_max, 0, d_fail);
+    ++*launches;
     for (int j0 = 0; j0 < na_max; j0 += kNB) {
-        chol_panel_kernel<<<batch, 256, 0, ctx->stream>>>(base, stride, ld, d_na, na_max, j0, d_fail);
-        ++*launches;
         const int rem = na_max - j0 - kNB;
-        if (rem > 0) {
-            const int T = (rem + 63) / 64;
-            dim3 grid(T, T, batch);
-            chol_update_kernel<<<grid, 256, 0, ctx->stream>>>(base, stride, ld, d_na, na_max, j0);
-            ++*launches;
-        }
+        if (rem <= 0) break;
+        chol_panel_kernel<<<dim3((rem + 255) / 256, batch), 256, panel_smem, ctx->stream>>>(base, stride, ld, d_na, na_max, j0);
+        const int T = (rem + 63) / 64;
+        chol_update_kernel<<<dim3(T, T, batch), 256, 0, ctx->stream>>>(base, stride, ld, d_na, na_max, j0, d_fail);
+        *launches += 2;
     }
     DDB_CUDA_TRY(cudaGetLastError());
     return DDB_OK;
