@@ -211,6 +211,16 @@ class Context:
         )
         return SweepOutput(np.ascontiguousarray(coef), lam, iters, rss, dof, np.zeros(n_t, dtype=np.int32))
 
+    # -- DataDrivenDMD Gram path ------------------------------------------------------------
+    def dmd_gram(self, dX: int, dY: int, n: int, m: int, dP: int, dQ: int):
+        """P = X X', Q = Y X' for device snapshot matrices (n x m, column-major) into device n x n buffers."""
+        _lib.check(self._lib.ddb_dmd_gram(self._ctx, C.c_void_p(dX), C.c_void_p(dY), int(n), int(m), C.c_void_p(dP),
+                                          C.c_void_p(dQ)))
+
+    def dmd_operator(self, dP: int, dQ: int, n: int, dK: int):
+        """K = Q P^-1 (DMDPINV through the normal equations), all device n x n column-major buffers."""
+        _lib.check(self._lib.ddb_dmd_operator(self._ctx, C.c_void_p(dP), C.c_void_p(dQ), int(n), C.c_void_p(dK)))
+
     # -- introspection ----------------------------------------------------------------------
     def timings(self) -> dict:
         t = _lib.Timings()

@@ -43,6 +43,7 @@ int gram_run(ddb_ctx* ctx, double* dPacked);
 int generate_run(ddb_ctx* ctx, int system_id, int n_states, int64_t m, int64_t first_sample, uint64_t seed,
                  double noise_std);
 void sweep_free(ddb_ctx* ctx);
+void dmd_free(ddb_ctx* ctx);
 
 }  // namespace ddb
 
@@ -101,6 +102,7 @@ int ddb_ctx_destroy(ddb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     sweep_free(ctx);
+    dmd_free(ctx);
     ctx->d_factors.release();
     ctx->own_X.release();
     ctx->own_Y.release();

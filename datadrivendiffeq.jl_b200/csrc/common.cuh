@@ -3,6 +3,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <string>
+#include <utility>
 #include <vector>
 #include <cuda_runtime.h>
 #include "../../include/ddb.h"
@@ -63,11 +64,15 @@ struct GramPlan {
     std::vector<int32_t> cta_seg_begin;    // nctas + 1
     std::vector<int32_t> pair_slot_begin;  // npairs + 1  (slots of one pair are contiguous)
     std::vector<int32_t> slot_order;       // slots grouped by pair, fixed summation order
+    std::vector<std::pair<int, int>> pairs; // pair index -> (block row, block column)
 };
 
 void build_gram_plan(GramPlan& plan, int kaug, int64_t m, int nctas, int bt, int ks);
+void build_plan_from_pairs(GramPlan& plan, const std::vector<std::pair<int, int>>& pairs,
+                           const std::vector<double>& cost, int64_t m, int nctas, int bt, int ks);
 
 struct SweepState;
+struct DmdState;
 
 }  // namespace ddb
 
@@ -101,6 +106,7 @@ struct ddb_ctx {
 
     // sweep / rss / select state lives in sweep.cu
     ddb::SweepState* sweep = nullptr;
+    ddb::DmdState* dmd = nullptr;
 
     ddb_timings timings = {};
 };

@@ -30,65 +30,12 @@
 //   slots of each block pair in a fixed order (bit-reproducible: no floating-point atomics) and
 //   scatters into the packed [G | R | yy].
 #include "common.cuh"
+#include "mma_common.cuh"
 #include <algorithm>
 #include <cstring>
 #include <cstdlib>
 
 namespace ddb {
-
-// ---------------------------------------------------------------------------------------------
-// PTX helpers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n"
-            "  .reg .pred p;\n"
-            "  mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "  selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-// non-blocking phase test (the result comes back through the scoreboard: issue early, consume late)
-__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    asm volatile(
-        "{\n"
-        "  .reg .pred p;\n"
-        "  mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "  selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return done != 0;
-}
-// 1-D bulk asynchronous copy global -> shared through the TMA unit (SASS UBLKCP).
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(c0), "+d"(c1)
-                 : "d"(a), "d"(b));
-}
 
 struct GramArgs {
     const double* X;
@@ -102,7 +49,6 @@ struct GramArgs {
     double* partials;
 };
 
-constexpr int kKS = 16;   // samples per stage
 constexpr int kNVS = 4;   // depth of the raw-sample (TMA) ring
 constexpr int kNTS = 4;   // depth of the Theta-tile ring (tiles are built kAhead stages before use)
 constexpr int kAhead = 2; // build distance: barrier arrivals precede the matching wait by a whole stage
@@ -132,28 +78,6 @@ template <int BT>
 inline size_t gram_smem_bytes(int n, int n_t) {
     return 128 + kNVS * gram_vbytes(n, n_t) + (size_t)kNTS * GramCfg<BT>::kStageDoubles * sizeof(double);
 }
-
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-// Static shapes of live 8x8 accumulator sub-tiles inside a warp's 64x32 patch (bit i*4+j: rows 8i..,
-// columns 8j..).  A diagonal block pair only needs sub-tiles on or below the diagonal; with 64x32
-// patches every warp's patch is one of: entirely below (FULL), straddling with offset 0 (sub-tile
-// column j live for rows i >= j), straddling with offset -4 (live for i >= j + 4), or entirely above
-// (EMPTY).  FLAT is the 64x16 patch used when a block row has at most 64 live rows.
-constexpr uint32_t shape_mask(int d, int jmax) {  // live iff j <= i + d and j < jmax
-    uint32_t m = 0;
-    for (int i = 0; i < 8; ++i)
-        for (int j = 0; j < 4; ++j)
-            if (j <= i + d && j < jmax) m |= 1u << (i * 4 + j);
-    return m;
-}
-constexpr uint32_t kShapeFull = shape_mask(8, 4);
-constexpr uint32_t kShapeDiag0 = shape_mask(0, 4);
-constexpr uint32_t kShapeDiagM4 = shape_mask(-4, 4);
-constexpr uint32_t kShapeEmpty = 0u;
-constexpr uint32_t kShapeFlat = shape_mask(8, 2);
 
 // The per-thread share of building a later stage's Theta tiles: NJ columns (library terms), each a
 // product of NF staged values per sample.
@@ -498,20 +422,12 @@ __global__ void __launch_bounds__(256) gram_reduce_kernel(const double* __restri
 // Host side: work plan
 // ---------------------------------------------------------------------------------------------
 void build_gram_plan(GramPlan& plan, int kaug, int64_t m, int nctas, int bt, int ks) {
-    plan = GramPlan();
-    plan.bt = bt;
-    plan.ks = ks;
-    plan.nblk = (kaug + bt - 1) / bt;
-    plan.npairs = plan.nblk * (plan.nblk + 1) / 2;
-    plan.nctas = nctas;
-    plan.nstages = (m + ks - 1) / ks;
-    const int64_t ns = plan.nstages;
-
     // pair index -> (bi, bj), row-major over the lower triangle, and its cost per stage relative to a
     // full block pair (tensor-pipe time of the slowest SM sub-partition, see the shapes in the kernel)
+    const int nblk = (kaug + bt - 1) / bt;
     std::vector<std::pair<int, int>> pairs;
     std::vector<double> cost;
-    for (int bi = 0; bi < plan.nblk; ++bi)
+    for (int bi = 0; bi < nblk; ++bi)
         for (int bj = 0; bj <= bi; ++bj) {
             pairs.push_back({bi, bj});
             const int rows_valid = std::min(bt, kaug - bi * bt);
@@ -520,6 +436,21 @@ void build_gram_plan(GramPlan& plan, int kaug, int64_t m, int nctas, int bt, int
             else if (bi == bj) c = (bt == 128) ? 0.60 : 0.85;  // diagonal: 36/64 (+ build) resp. 26/32
             cost.push_back(c);
         }
+    build_plan_from_pairs(plan, pairs, cost, m, nctas, bt, ks);
+    plan.nblk = nblk;
+}
+
+void build_plan_from_pairs(GramPlan& plan, const std::vector<std::pair<int, int>>& pairs,
+                           const std::vector<double>& cost, int64_t m, int nctas, int bt, int ks) {
+    plan = GramPlan();
+    plan.bt = bt;
+    plan.ks = ks;
+    plan.nblk = 0;
+    plan.npairs = (int)pairs.size();
+    plan.nctas = nctas;
+    plan.nstages = (m + ks - 1) / ks;
+    plan.pairs = pairs;
+    const int64_t ns = plan.nstages;
 
     struct Tmp {
         int cta, pair;

@@ -320,6 +320,22 @@ __global__ void __launch_bounds__(256) chol_solve_kernel(const double* Lbase, si
     for (int i = tid; i < na; i += blockDim.x) zg[i] = z[i];
 }
 
+// Entry points for other translation units (dmd.cu): one matrix, many right-hand sides.
+int chol_factor_shared(ddb_ctx* ctx, double* A, int k, int* d_fail, int* launches) {
+    return chol_batched(ctx, A, 0, k, nullptr, k, 1, d_fail, launches);
+}
+int chol_solve_many(ddb_ctx* ctx, const double* L, int k, double* Z, int nrhs) {
+    const size_t solve_smem = ((size_t)((k + 31) / 32) * 32 + 32 * 33) * sizeof(double);
+    if (solve_smem > 200 * 1024) {
+        set_error("triangular solver: order %d exceeds the shared-memory right-hand-side buffer", k);
+        return DDB_UNSUPPORTED;
+    }
+    DDB_CUDA_TRY(cudaFuncSetAttribute(chol_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
+    chol_solve_kernel<<<dim3(nrhs, 1), 256, solve_smem, ctx->stream>>>(L, 0, k, nullptr, k, Z, (size_t)k, nrhs, nullptr, nullptr);
+    DDB_CUDA_TRY(cudaGetLastError());
+    return DDB_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // per-target state and the shared post-solve step logic
 // ---------------------------------------------------------------------------------------------

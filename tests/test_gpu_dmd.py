@@ -1,0 +1,74 @@
+"""GPU parity of the DataDrivenDMD Gram path (P = X X', Q = Y X', K = Q P^-1) against the oracle."""
+import numpy as np
+import pytest
+
+import ddb200
+import oracle
+from ddb200 import systems
+
+pytestmark = pytest.mark.gpu
+
+
+def _snapshots(A, x0, steps):
+    y = [np.asarray(x0, dtype=float)]
+    for _ in range(steps):
+        y.append(A @ y[-1])
+    return np.stack(y, axis=1)
+
+
+@pytest.mark.parametrize("inner", [ddb200.DMDPINV(), ddb200.DMDSVD()])
+def test_linear_discrete_groundtruth(inner):
+    # lib/DataDrivenDMD/test/Core/linear_autonomous.jl:11-37
+    A = np.array([[0.9, -0.2], [0.0, 0.2]])
+    x = _snapshots(A, [10.0, -10.0], 10)
+    res = ddb200.solve_dmd(ddb200.DiscreteDataDrivenProblem(x), ddb200.B200DMD(inner))
+    ref = oracle.koopman_solve(oracle.DMDPINV() if inner.name == "DMDPINV" else oracle.DMDSVD(), x)
+    np.testing.assert_allclose(res.P, ref.P, rtol=1e-13)
+    np.testing.assert_allclose(res.Q, ref.Q, rtol=1e-13)
+    np.testing.assert_allclose(np.real(res.K), A, atol=1e-9)
+    np.testing.assert_allclose(np.real(res.K), ref.K, atol=1e-9)
+    np.testing.assert_allclose(np.sort(np.real(res.eigenvalues)), [0.2, 0.9], atol=1e-9)
+    assert res.rss <= 1e-10 and res.dof == 3
+
+
+@pytest.mark.parametrize("n,m", [(6, 1000), (130, 4001)])
+def test_single_trajectory_operator(n, m):
+    A, X, Y = systems.linear_snapshots(n, m, seed=n, restart=10**9)  # one trajectory: Y is X shifted by one
+    x = np.concatenate([X, Y[:, -1:]], axis=1)
+    res = ddb200.solve_dmd(ddb200.DiscreteDataDrivenProblem(x), ddb200.B200DMD(ddb200.DMDPINV()))
+    P0, Q0 = X @ X.T, Y @ X.T
+    sc = np.sqrt(np.outer(np.diag(P0), np.diag(P0)))
+    assert np.max(np.abs(res.P - P0) / sc) < 1e-13
+    assert np.max(np.abs(res.Q - Q0) / sc) < 1e-12
+    np.testing.assert_array_equal(res.P, res.P.T)
+    # K = Y / X  (pivoted QR in the reference) vs K = Q P^-1 (equilibrated Cholesky here)
+    Kref = np.linalg.lstsq(X.T, Y.T, rcond=None)[0].T
+    assert np.max(np.abs(np.real(res.K) - Kref)) <= 1e-8 * max(1.0, np.max(np.abs(Kref)))
+    np.testing.assert_allclose(np.real(res.K), A, atol=1e-6)
+
+
+@pytest.mark.parametrize("n,m", [(2, 16), (256, 3000), (300, 777), (514, 2049)])
+def test_gram_blocks_and_operator_general(n, m):
+    """Separate X and Y (restarted trajectories keep the snapshot matrix well conditioned): the C-ABI
+    entry points directly, including ragged block rows (n not a multiple of 128) and a ragged last stage."""
+    import torch
+
+    A, X, Y = systems.linear_snapshots(n, m, seed=n, restart=64)
+    dev = torch.device("cuda:0")
+    Xt = torch.from_numpy(np.ascontiguousarray(X.T)).to(dev)  # (m, n) row-major == n x m column-major
+    Yt = torch.from_numpy(np.ascontiguousarray(Y.T)).to(dev)
+    PQ = torch.zeros((2, n, n), dtype=torch.float64, device=dev)
+    K = torch.zeros((n, n), dtype=torch.float64, device=dev)
+    with ddb200.Context(0) as ctx:
+        ctx.dmd_gram(Xt.data_ptr(), Yt.data_ptr(), n, m, PQ[0].data_ptr(), PQ[1].data_ptr())
+        ctx.dmd_operator(PQ[0].data_ptr(), PQ[1].data_ptr(), n, K.data_ptr())
+    P, Q, Kh = PQ[0].T.cpu().numpy(), PQ[1].T.cpu().numpy(), K.T.cpu().numpy()
+    P0, Q0 = X @ X.T, Y @ X.T
+    sc = np.sqrt(np.outer(np.diag(P0), np.diag(P0)))
+    assert np.max(np.abs(P - P0) / sc) < 1e-13
+    assert np.max(np.abs(Q - Q0) / sc) < 1e-12
+    np.testing.assert_array_equal(P, P.T)
+    if m > 4 * n:  # K only when X X' is comfortably full rank
+        Kref = np.linalg.lstsq(X.T, Y.T, rcond=None)[0].T
+        assert np.max(np.abs(Kh - Kref)) <= 1e-9 * max(1.0, np.max(np.abs(Kref)))
+        np.testing.assert_allclose(Kh, A, atol=1e-8)
