@@ -73,6 +73,7 @@ void build_plan_from_pairs(GramPlan& plan, const std::vector<std::pair<int, int>
 
 struct SweepState;
 struct DmdState;
+struct RingState;
 
 }  // namespace ddb
 
@@ -107,6 +108,7 @@ struct ddb_ctx {
     // sweep / rss / select state lives in sweep.cu
     ddb::SweepState* sweep = nullptr;
     ddb::DmdState* dmd = nullptr;
+    ddb::RingState* ring = nullptr;
 
     ddb_timings timings = {};
 };

@@ -37,17 +37,6 @@
 
 namespace ddb {
 
-struct GramArgs {
-    const double* X;
-    const double* Y;
-    int n, n_t;
-    int64_t m;
-    int kaug;
-    const uint16_t* factors;  // kaug_pad x kMaxFactors
-    const GramSegment* segs;
-    const int32_t* cta_seg_begin;
-    double* partials;
-};
 
 constexpr int kNVS = 4;   // depth of the raw-sample (TMA) ring
 constexpr int kNTS = 4;   // depth of the Theta-tile ring (tiles are built kAhead stages before use)
@@ -570,7 +559,9 @@ static int launch_gram(ddb_ctx* ctx, const GramArgs& args, size_t smem) {
     return DDB_OK;
 }
 
-static int ensure_factor_table(ddb_ctx* ctx, int kaug_pad) {
+int gram_ensure_factors(ddb_ctx* ctx, int kaug_pad);
+static int ensure_factor_table(ddb_ctx* ctx, int kaug_pad) { return gram_ensure_factors(ctx, kaug_pad); }
+int gram_ensure_factors(ddb_ctx* ctx, int kaug_pad) {
     // (k + n_t) rows of kMaxFactors uint16: library terms then one single-factor row per target
     const int k = ctx->k, n = ctx->n, n_t = ctx->n_t;
     std::vector<uint16_t> tab((size_t)kaug_pad * kMaxFactors, kNoFactor);
@@ -587,6 +578,24 @@ static int ensure_factor_table(ddb_ctx* ctx, int kaug_pad) {
     ctx->factors_nt = n_t;
     return DDB_OK;
 }
+
+// Runs the self-building kernel (BT = 128) over an arbitrary segment list; used by gram_ring.cu for the
+// block pairs that do not get a whole CTA in the ring pass.
+int gram_launch_bt128(ddb_ctx* ctx, const GramArgs& args, int nctas, bool small_deg) {
+    const size_t smem = gram_smem_bytes<128>(args.n, args.n_t);
+    auto kern = small_deg ? gram_kernel<128, 2> : gram_kernel<128, 8>;
+    DDB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<nctas, GramCfg<128>::kThreads, smem, ctx->stream>>>(args);
+    DDB_CUDA_TRY(cudaGetLastError());
+    return DDB_OK;
+}
+void gram_reduce_launch(ddb_ctx* ctx, const double* partials, const int2* pairs, const int32_t* pair_slot_begin,
+                        int npairs, int bt, int k, int n_t, double* packed) {
+    dim3 rgrid(npairs, (bt * bt + 255) / 256);
+    gram_reduce_kernel<<<rgrid, 256, 0, ctx->stream>>>(partials, pairs, pair_slot_begin, bt, k, n_t, packed);
+}
+int gram_ensure_factors(ddb_ctx* ctx, int rows);
+int gram_ring_run(ddb_ctx* ctx, double* dPacked, bool* handled);
 
 int gram_run(ddb_ctx* ctx, double* dPacked) {
     if (ctx->k <= 0) {
@@ -614,6 +623,11 @@ int gram_run(ddb_ctx* ctx, double* dPacked) {
     if (((uintptr_t)ctx->dX & 15) || ((uintptr_t)ctx->dY & 15)) {
         set_error("ddb_gram: device data pointers must be 16-byte aligned");
         return DDB_INVALID_ARG;
+    }
+    if (bt == 128) {
+        bool handled = false;
+        DDB_TRY(gram_ring_run(ctx, dPacked, &handled));
+        if (handled) return DDB_OK;
     }
     // persistent grid: CTAs per SM from the occupancy calculator (1 for BT=128, up to 3 for BT=64)
     int occ = 1;

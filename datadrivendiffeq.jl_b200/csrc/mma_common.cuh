@@ -6,6 +6,19 @@ namespace ddb {
 
 constexpr int kKS = 16;  // samples per stage
 
+struct GramArgs {
+    const double* X;
+    const double* Y;
+    int n, n_t;
+    int64_t m;
+    int kaug;
+    const uint16_t* factors;  // kaug_pad x kMaxFactors
+    const GramSegment* segs;
+    const int32_t* cta_seg_begin;
+    double* partials;
+};
+
+
 // ---------------------------------------------------------------------------------------------
 // PTX helpers
 // ---------------------------------------------------------------------------------------------
