@@ -368,7 +368,8 @@ def main():
     F = gram_flops_per_sample(k, n_t)
     gram_ms = float(np.mean(stage["gram_ms"]))
     achieved = F * m_local / (gram_ms * 1e-3) * 1e-12
-    roofline = {"bound": "tensor", "kernel": "ddb::gram_kernel (FP64 DMMA.8x8x4)", "achieved": achieved, "peak": FP64_DMMA_PEAK_TFLOPS,
+    roofline = {"bound": "tensor", "kernel": "Gram stage = ddb::gram_ring_kernel (producer SMs + TMA-fed FP64 DMMA.8x8x4 consumers) + ddb::gram_kernel (diagonal pairs) + reduce",
+                "achieved": achieved, "peak": FP64_DMMA_PEAK_TFLOPS,
                 "unit": "TFLOP/s", "frac": achieved / FP64_DMMA_PEAK_TFLOPS, "traffic": None,
                 "peak_source": "measured on this pool with tools/fp64_peak.cu (DMMA issue-rate; profiles/fp64_peak_r1.json); "
                                "MEASURED_PEAKS.json has no FP64 figure",
@@ -377,7 +378,7 @@ def main():
 
     if rank == 0:
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:
             v, desc = cpu_reference_sample(wl)
             cpu = {"value": v, "unit": "samples/s", "cores": os.cpu_count() or 1, "kind": "port", "sample": desc}
         line = {

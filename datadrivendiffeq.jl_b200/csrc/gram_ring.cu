@@ -89,7 +89,7 @@ __device__ __forceinline__ void st_release(unsigned long long* p, unsigned long 
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// The TMA side of a consumer, run by warp 0 between its DMMAs: lane l < nops copies operand tile l of a
+// The TMA side of a consumer, run by one warp at a time between its DMMAs: lane l < nops copies operand tile l of a
 // stage (one contiguous chunk of the global ring) into the stage ring.
 struct RingFeed {
     const double* zring;
@@ -174,17 +174,19 @@ struct RingWarp {
                 if ((MASK >> (i * CJ + j)) & 1u) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
     // offA/offB: this lane's fragment offsets inside a stage; pitch4A/B = 4 sample rows of the operand tile.
-    // feeder is true on warp 0: it keeps DEPTH - 2 stages in flight (the slot it refills was released a
-    // whole stage ago by every warp, so the wait inside issue() does not stall the DMMA stream).
+    // The warps take turns driving the TMA unit (warp st % 8 requests stage st + DEPTH - 2 at the top of its
+    // stage st): a fixed feeder warp would always be the slowest one and, being alone in setting the pace,
+    // expose its bookkeeping on the tensor pipe.  The slot being refilled was released a whole stage ago by
+    // every warp, so the wait inside issue() does not normally stall.
     __device__ __forceinline__ void run(const double* ring, uint64_t* full, uint64_t* empty, int64_t nstages,
-                                        int offA, int offB, int pitch4A, int pitch4B, const bool feeder, RingFeed& fd,
+                                        int offA, int offB, int pitch4A, int pitch4B, const int warp, RingFeed& fd,
                                         unsigned long long* progress, int lane, long long& t_wait) {
         constexpr int kAhead = DEPTH - 2;
 #pragma unroll
         for (int i = 0; i < RI; ++i)
 #pragma unroll
             for (int j = 0; j < CJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-        if (feeder)
+        if (warp == 0)
             for (int q = 0; q < kAhead; ++q) fd.template issue<DEPTH, STAGE>(q);
         double a0[RI], b0[CJ], a1[RI], b1[CJ];
         mbar_wait(&full[0], 0u);
@@ -192,7 +194,7 @@ struct RingWarp {
         int slot = 0;
         uint32_t par = 0;
         for (int64_t st = 0; st < nstages; ++st) {
-            if (feeder) {
+            if (((uint32_t)st & (kRingWarps - 1)) == (uint32_t)warp) {  // this warp's turn to drive the TMA unit
                 // the last stage of a window has landed in shared memory: the global ring slot may be recycled
                 if (lane == 0 && ((uint32_t)st % kSPW) == kSPW - 1) st_release(progress, (unsigned long long)((uint32_t)st / kSPW + 1));
                 fd.template issue<DEPTH, STAGE>(st + kAhead);
@@ -377,7 +379,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) gram_ring_kernel(const RingAr
     const int64_t nstages = nwin * kSPW;  // producers zero-fill the tail, every stage is full
 
     RingFeed feed = {};
-    if (warp == 0) {
+    {
         // operand tiles of a stage: pair = {block a, block b}; strip = {short last block, nb block columns}
         const int chunk = kWin * kRingPitch;  // doubles per full block of a window
         const int nops = strip ? 1 + cd.nb : (same ? 1 : 2);
@@ -405,7 +407,6 @@ __global__ void __launch_bounds__(kRingThreads, 1) gram_ring_kernel(const RingAr
         feed.lane = lane;
         feed.t_ready = feed.t_empty = 0;
     }
-    const bool feeder = warp == 0;
 
     const int g = lane >> 2, t = lane & 3;
     long long t_wait = 0;
@@ -427,7 +428,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) gram_ring_kernel(const RingAr
         auto go = [&](auto tag) {
             constexpr uint32_t MASK = decltype(tag)::value;
             RingWarp<8, 4, MASK, kPairDepth, kPairStage, false> w;
-            w.run(ring, full, empty, nstages, offA, offB, 4 * kRingPitch, 4 * kRingPitch, feeder, feed, args.progress + c, lane,
+            w.run(ring, full, empty, nstages, offA, offB, 4 * kRingPitch, 4 * kRingPitch, warp, feed, args.progress + c, lane,
                   t_wait);
 #pragma unroll
             for (int i = 0; i < 8; ++i)
@@ -449,7 +450,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) gram_ring_kernel(const RingAr
         const int offA = t * kStripPitch + g;
         const int offB = kKS * kStripPitch + t * kRingPitch + warp * 16 + g;
         RingWarp<5, 6, 0x3FFFFFFFu, kStripDepth, kStripStage, true> w;
-        w.run(ring, full, empty, nstages, offA, offB, 4 * kStripPitch, 4 * kRingPitch, feeder, feed, args.progress + c, lane,
+        w.run(ring, full, empty, nstages, offA, offB, 4 * kStripPitch, 4 * kRingPitch, warp, feed, args.progress + c, lane,
               t_wait);
 #pragma unroll
         for (int j = 0; j < 6; ++j) {
@@ -466,7 +467,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) gram_ring_kernel(const RingAr
 #ifdef DDB_RING_TIMING
     if (lane == 0 && ((c % 37) == 0 || strip) && (warp == 0 || warp == 5))
         printf("consumer %d kind %d warp %d: all %lld full-wait %lld ready-wait %lld empty-wait %lld\n", c, cd.kind, warp,
-               clock64() - tm_all, t_wait, warp == 0 ? feed.t_ready : 0ll, warp == 0 ? feed.t_empty : 0ll);
+               clock64() - tm_all, t_wait, feed.t_ready, feed.t_empty);
 #endif
 }
 
