@@ -98,7 +98,8 @@ struct RingFeed {
     uint64_t* empty;
     double* ring;
     int64_t nstages;
-    unsigned long long known;  // lane p < nprod: windows producer p is known to have finished
+    uint32_t* s_ready;         // shared watermark: every window below it is complete in the global ring
+    uint32_t ready;            // this warp's copy of the watermark
     int nprod, lane, win_doubles;
     int src_off, src_stage, dst_off;  // this lane's operand: offset in a window, per-stage stride, offset in a stage
     uint32_t bytes, stage_bytes;
@@ -109,16 +110,27 @@ struct RingFeed {
         if (st >= nstages) return;
         const int slot = (int)((uint32_t)st % (uint32_t)DEPTH);  // st < 2^32 (checked on the host)
         const uint32_t w = (uint32_t)st / kSPW;
-        if (((uint32_t)st % kSPW) == 0) {  // first stage of a window: the producer must have published it
-            const int p = (int)(w % (uint32_t)nprod);
-            const unsigned long long need = (unsigned long long)(w / (uint32_t)nprod) + 1;
+        if (w >= ready) {
+            // Windows [0, ready) are known to be complete.  The watermark is shared through shared memory
+            // (any warp may have refreshed it); whoever finds it short polls the producers' counters:
+            // producer p has finished windows p, p + nprod, ... (done[p] of them), so every window below
+            // min_p (done[p] * nprod + p) is complete.
 #ifdef DDB_RING_TIMING
             const long long t0 = clock64();
 #endif
-            while (__shfl_sync(0xFFFFFFFFu, known, p) < need) {
-                known = lane < nprod ? ld_acquire(done + lane) : 0ull;
-                asm volatile("fence.proxy.async;" ::: "memory");
+            uint32_t r;
+            asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(r) : "r"(smem_u32(s_ready)) : "memory");
+            if (w >= r) {
+                do {
+                    r = lane < nprod ? (uint32_t)ld_acquire(done + lane) * (uint32_t)nprod + (uint32_t)lane : 0xFFFFFFFFu;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) r = min(r, __shfl_xor_sync(0xFFFFFFFFu, r, o));
+                } while (w >= r);
+                if (lane == 0) asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(s_ready)), "r"(r) : "memory");
             }
+            ready = r;
+            // the producers wrote through the generic proxy, the bulk copies below read through the async proxy
+            asm volatile("fence.proxy.async;" ::: "memory");
 #ifdef DDB_RING_TIMING
             t_ready += clock64() - t0;
 #endif
@@ -362,7 +374,8 @@ __global__ void __launch_bounds__(kRingThreads, 1) gram_ring_kernel(const RingAr
     const int c = blockIdx.x - args.nprod;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);  // [kMaxDepth] stage landed
     uint64_t* empty = full + kMaxDepth;                      // [kMaxDepth] every warp is done with the slot
-    double* ring = reinterpret_cast<double*>(smem_raw + 128);
+    uint32_t* s_ready = reinterpret_cast<uint32_t*>(smem_raw + 128);
+    double* ring = reinterpret_cast<double*>(smem_raw + 256);
     const RingCons cd = args.cons[c];
     const bool strip = cd.kind == 1;
     const bool same = !strip && cd.a == cd.b;
@@ -372,6 +385,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) gram_ring_kernel(const RingAr
             mbar_init(&empty[i], kRingWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        *s_ready = 0u;
     }
     if (strip)  // block columns past the strip's range are never copied: they must read as zero, not as garbage
         for (int e = tid; e < kStripDepth * kStripStage; e += kRingThreads) ring[e] = 0.0;
@@ -401,7 +415,8 @@ __global__ void __launch_bounds__(kRingThreads, 1) gram_ring_kernel(const RingAr
         feed.empty = empty;
         feed.ring = ring;
         feed.nstages = nstages;
-        feed.known = 0ull;
+        feed.s_ready = s_ready;
+        feed.ready = 0u;
         feed.win_doubles = args.win_doubles;
         feed.nprod = args.nprod;
         feed.lane = lane;
@@ -626,7 +641,7 @@ int gram_ring_run(ddb_ctx* ctx, double* dPacked, bool* handled) {
     a.done = R->flags.as<unsigned long long>();
     a.progress = a.done + kMaxProducers;
     a.partials = R->partials.as<double>();
-    const size_t smem_cons = 128 + (size_t)kRingSmemDoubles * sizeof(double);
+    const size_t smem_cons = 256 + (size_t)kRingSmemDoubles * sizeof(double);
     const size_t smem_prod = (size_t)(kWin + 2 + kWin * (n + n_t)) * sizeof(double);
     const size_t smem = std::max(smem_cons, smem_prod);
     const void* kern = small_deg ? (const void*)gram_ring_kernel<2> : (const void*)gram_ring_kernel<8>;

@@ -19,34 +19,41 @@
 
 namespace ddb {
 
+// One sparse term of a candidate, decoded once per pass: the coefficient and the shared-memory ROWS of its
+// factors (states 0..n-1; row n + n_t holds ones, so a missing factor multiplies by 1.0 and the product
+// needs no predicate).  o32 = first two factor rows pre-multiplied by the tile pitch (degree <= 2 path reads
+// only the first 16 bytes), o16 = all kMaxFactors rows.
 struct __align__(16) RssTerm {
-    int16_t off[kMaxFactors];  // offset inside one sample's x row, -1 = no factor
     double val;
-    double pad;
+    int32_t o32[2];
+    uint16_t o16[kMaxFactors];
 };
-
-__global__ void rss_expand_kernel(const int32_t* __restrict__ cand_idx, const double* __restrict__ cand_val,
-                                  int64_t nterms, const uint16_t* __restrict__ factors, RssTerm* __restrict__ out) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nterms) return;
-    RssTerm r;
-    r.val = cand_val[t];
-    r.pad = 0.0;
-    const uint16_t* f = factors + (size_t)cand_idx[t] * kMaxFactors;
-#pragma unroll
-    for (int d = 0; d < kMaxFactors; ++d) r.off[d] = (f[d] == kNoFactor) ? (int16_t)-1 : (int16_t)f[d];
-    out[t] = r;
-}
+static_assert(sizeof(RssTerm) == 32, "RssTerm layout");
 
 constexpr int kRssTile = 32;   // samples per shared-memory tile (one per lane)
 constexpr int kRssAcc = 32;    // candidates per warp per pass (register accumulators per lane)
 constexpr int kRssWarps = 8;
 constexpr int kRssPitch = kRssTile + 1;  // doubles; transposed tile [state][sample], odd pitch -> conflict-free
 
+__global__ void rss_expand_kernel(const int32_t* __restrict__ cand_idx, const double* __restrict__ cand_val,
+                                  int64_t nterms, const uint16_t* __restrict__ factors, int ones_row,
+                                  RssTerm* __restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nterms) return;
+    RssTerm r;
+    r.val = cand_val[t];
+    const uint16_t* f = factors + (size_t)cand_idx[t] * kMaxFactors;
+#pragma unroll
+    for (int d = 0; d < kMaxFactors; ++d) r.o16[d] = (f[d] == kNoFactor) ? (uint16_t)ones_row : f[d];
+    r.o32[0] = (int)r.o16[0] * kRssPitch;
+    r.o32[1] = (int)r.o16[1] * kRssPitch;
+    out[t] = r;
+}
+
 struct RssArgs {
     const double* X;
     const double* Y;
-    int n, n_t, nf;
+    int n, n_t;
     int64_t m;
     int ncand;
     const int64_t* cand_off;
@@ -62,31 +69,46 @@ __device__ __forceinline__ void cp_async8(void* dst, const void* src) {
 }
 
 // Stage one tile of kRssTile samples TRANSPOSED into shared memory ([row][sample], rows = n states then
-// n_t targets) with 8-byte asynchronous copies: global reads stay coalesced (a sample's values are
-// contiguous), the transposition makes "lane = sample" accesses conflict-free.
-__device__ __forceinline__ void rss_stage_tile(const RssArgs& a, double* buf, int64_t s0, int valid) {
-    const int rows = a.n + a.n_t;
-    for (int e = threadIdx.x; e < kRssTile * a.n; e += blockDim.x) {
-        const int s = e / a.n, i = e % a.n;
-        if (s < valid) cp_async8(buf + i * kRssPitch + s, a.X + (s0 + s) * a.n + i);
+// n_t targets) with 8-byte asynchronous copies: global reads stay coalesced (a tile of X is one contiguous
+// run of 32 n doubles), the transposition makes "lane = sample" accesses conflict-free.  Element e of the
+// run goes to row e % w, sample e / w; the (row, sample) pair is advanced incrementally (no division).
+struct RssWalk {
+    int i0, s0, di, ds;  // element threadIdx.x -> (row i0, sample s0); + blockDim.x elements -> (+di, +ds)
+    __device__ __forceinline__ void init(int w) {
+        i0 = threadIdx.x % w;
+        s0 = threadIdx.x / w;
+        di = blockDim.x % w;
+        ds = blockDim.x / w;
     }
-    for (int e = threadIdx.x; e < kRssTile * a.n_t; e += blockDim.x) {
-        const int s = e / a.n_t, i = e % a.n_t;
-        if (s < valid) cp_async8(buf + (a.n + i) * kRssPitch + s, a.Y + (s0 + s) * a.n_t + i);
+};
+__device__ __forceinline__ void rss_stage_rows(double* buf, const double* src, int w, int valid, const RssWalk& k) {
+    int i = k.i0, s = k.s0;
+    const int total = valid * w;
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+        cp_async8(buf + i * kRssPitch + s, src + e);
+        i += k.di;
+        s += k.ds;
+        if (i >= w) {
+            i -= w;
+            ++s;
+        }
     }
-    (void)rows;
-    asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
+template <int NF>
 __global__ void __launch_bounds__(kRssWarps * 32) rss_kernel(const RssArgs a) {
     extern __shared__ double sm[];
-    const int rows = a.n + a.n_t;
+    const int rows = a.n + a.n_t + 1;  // + the row of ones
     double* buf[2] = {sm, sm + (size_t)rows * kRssPitch};
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cbase = blockIdx.y * (kRssWarps * kRssAcc);
     // this CTA's sample range (whole tiles)
     const int64_t ntiles = (a.m + kRssTile - 1) / kRssTile;
     const int64_t t_lo = ntiles * blockIdx.x / gridDim.x, t_hi = ntiles * (blockIdx.x + 1) / gridDim.x;
+    RssWalk wx, wy;
+    wx.init(a.n);
+    wy.init(a.n_t);
+    if (threadIdx.x < 2 * kRssPitch) buf[threadIdx.x / kRssPitch][(rows - 1) * kRssPitch + threadIdx.x % kRssPitch] = 1.0;
 
     // candidates of this warp: cbase + warp + 8 * slot
     int nslots = 0;
@@ -96,12 +118,18 @@ __global__ void __launch_bounds__(kRssWarps * 32) rss_kernel(const RssArgs a) {
 #pragma unroll
     for (int q = 0; q < kRssAcc; ++q) acc[q] = 0.0;
 
-    if (t_lo < t_hi) rss_stage_tile(a, buf[0], t_lo * kRssTile, (int)min((int64_t)kRssTile, a.m - t_lo * kRssTile));
+    auto stage = [&](double* dst, int64_t tile) {
+        const int64_t s0 = tile * kRssTile;
+        const int valid = (int)min((int64_t)kRssTile, a.m - s0);
+        rss_stage_rows(dst, a.X + s0 * a.n, a.n, valid, wx);
+        rss_stage_rows(dst + a.n * kRssPitch, a.Y + s0 * a.n_t, a.n_t, valid, wy);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (t_lo < t_hi) stage(buf[0], t_lo);
     for (int64_t tile = t_lo; tile < t_hi; ++tile) {
         const int cur = (int)((tile - t_lo) & 1);
         if (tile + 1 < t_hi) {
-            const int64_t s1 = (tile + 1) * kRssTile;
-            rss_stage_tile(a, buf[cur ^ 1], s1, (int)min((int64_t)kRssTile, a.m - s1));
+            stage(buf[cur ^ 1], tile + 1);
             asm volatile("cp.async.wait_group 1;" ::: "memory");
         } else {
             asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -114,23 +142,27 @@ __global__ void __launch_bounds__(kRssWarps * 32) rss_kernel(const RssArgs a) {
         for (int q = 0; q < kRssAcc; ++q) {
             if (q < nslots) {
                 const int c = cbase + warp + kRssWarps * q;
-                const int64_t off = __ldg(a.cand_off + c);
+                const RssTerm* r = a.terms + __ldg(a.cand_off + c);
                 const int nnz = __ldg(a.cand_nnz + c);
                 const int eq = __ldg(a.cand_eq + c);
                 double fit = 0.0;
-                for (int t = 0; t < nnz; ++t) {
-                    const RssTerm* r = a.terms + off + t;
-                    double p = __ldg(&r->val);
-                    const int4 o4 = __ldg(reinterpret_cast<const int4*>(r->off));  // 8 x int16
-                    const int o[4] = {o4.x, o4.y, o4.z, o4.w};
-#pragma unroll
-                    for (int d = 0; d < kMaxFactors; ++d) {
-                        if (d < a.nf) {
-                            const int od = (int)(short)((o[d >> 1] >> (16 * (d & 1))) & 0xFFFF);
-                            if (od >= 0) p *= xs[od * kRssPitch];
-                        }
+                if (NF <= 2) {
+#pragma unroll 4
+                    for (int t = 0; t < nnz; ++t) {
+                        const int4 w = __ldg(reinterpret_cast<const int4*>(r + t));  // {val, o32[0], o32[1]}
+                        const double v = __hiloint2double(w.y, w.x);
+                        fit = fma(v, xs[w.z] * xs[w.w], fit);
                     }
-                    fit += p;
+                } else {
+                    for (int t = 0; t < nnz; ++t) {
+                        const int4 w = __ldg(reinterpret_cast<const int4*>(r + t));
+                        const int4 o = __ldg(reinterpret_cast<const int4*>(r + t) + 1);  // 8 x uint16 rows
+                        double p = xs[w.z] * xs[w.w];
+                        const uint32_t ow[4] = {(uint32_t)o.x, (uint32_t)o.y, (uint32_t)o.z, (uint32_t)o.w};
+#pragma unroll
+                        for (int d = 2; d < NF; ++d) p *= xs[((ow[d >> 1] >> (16 * (d & 1))) & 0xFFFFu) * kRssPitch];
+                        fit = fma(__hiloint2double(w.y, w.x), p, fit);
+                    }
                 }
                 const double res = live ? fit - xs[(a.n + eq) * kRssPitch] : 0.0;
                 acc[q] = fma(res, res, acc[q]);
@@ -177,7 +209,7 @@ int rss_run(ddb_ctx* ctx, SweepState* S, double* dRss) {
     DDB_CUDA_TRY(cudaEventRecord(ctx->ev[4], st));
     if (nterms > 0)
         rss_expand_kernel<<<(unsigned)((nterms + 255) / 256), 256, 0, st>>>(S->cand_idx.as<int32_t>(), S->cand_val.as<double>(),
-                                                                            nterms, ctx->d_factors.as<uint16_t>(),
+                                                                            nterms, ctx->d_factors.as<uint16_t>(), ctx->n + ctx->n_t,
                                                                             S->cand_terms.as<RssTerm>());
     const int passes = (ncand + kRssWarps * kRssAcc - 1) / (kRssWarps * kRssAcc);
     const int64_t ntiles = (ctx->m + kRssTile - 1) / kRssTile;
@@ -188,7 +220,6 @@ int rss_run(ddb_ctx* ctx, SweepState* S, double* dRss) {
     a.Y = ctx->dY;
     a.n = ctx->n;
     a.n_t = ctx->n_t;
-    a.nf = std::max(1, ctx->max_degree);
     a.m = ctx->m;
     a.ncand = ncand;
     a.cand_off = S->cand_off.as<int64_t>();
@@ -196,13 +227,14 @@ int rss_run(ddb_ctx* ctx, SweepState* S, double* dRss) {
     a.cand_eq = S->cand_eq.as<int32_t>();
     a.terms = S->cand_terms.as<RssTerm>();
     a.partials = S->rss_partials.as<double>();
-    const size_t smem = 2 * (size_t)kRssPitch * (ctx->n + ctx->n_t) * sizeof(double);
+    const size_t smem = 2 * (size_t)kRssPitch * (ctx->n + ctx->n_t + 1) * sizeof(double);
     if (smem > 200 * 1024) {
         set_error("ddb_rss: n + n_t too large for the shared-memory sample tile");
         return DDB_UNSUPPORTED;
     }
-    DDB_CUDA_TRY(cudaFuncSetAttribute(rss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rss_kernel<<<dim3(nparts, passes), kRssWarps * 32, smem, st>>>(a);
+    auto kern = ctx->max_degree <= 2 ? rss_kernel<2> : rss_kernel<kMaxFactors>;
+    DDB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3(nparts, passes), kRssWarps * 32, smem, st>>>(a);
     rss_reduce_kernel<<<(ncand + 255) / 256, 256, 0, st>>>(S->rss_partials.as<double>(), nparts, ncand, dRss);
     DDB_CUDA_TRY(cudaGetLastError());
     DDB_CUDA_TRY(cudaEventRecord(ctx->ev[5], st));

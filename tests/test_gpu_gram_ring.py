@@ -1,0 +1,73 @@
+"""GPU tests of the ring schedule of the Gram stage (producer SMs -> L2 ring -> TMA + DMMA consumer SMs,
+csrc/gram_ring.cu): it must agree with the oracle, with the self-building schedule (csrc/gram.cu) and with
+itself bit for bit -- a race between producers and consumers shows up as run-to-run differences."""
+import os
+
+import numpy as np
+import pytest
+
+import ddb200
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = ddb200.Context(0)
+    yield c
+    c.close()
+
+
+def _gram(ctx, ring):
+    old = os.environ.get("DDB_GRAM_RING")
+    os.environ["DDB_GRAM_RING"] = "1" if ring else "0"
+    try:
+        ctx.gram()
+        return ctx.gram_download(), ctx.timings()["gram_launches"]
+    finally:
+        if old is None:
+            del os.environ["DDB_GRAM_RING"]
+        else:
+            os.environ["DDB_GRAM_RING"] = old
+
+
+@pytest.mark.parametrize("m", [4096, 20_001, 65_536 + 17])
+def test_ring_matches_oracle_and_self_building_schedule(ctx, m):
+    n = 64
+    rng = np.random.default_rng(m)
+    X = rng.standard_normal((n, m))
+    Y = rng.standard_normal((n, m))
+    ex = oracle.polynomial_exponents(n, 2)
+    ctx.set_library(ex)
+    ctx.upload(X, Y)
+    (G1, R1, y1), l1 = _gram(ctx, True)
+    (G0, R0, y0), l0 = _gram(ctx, False)
+    assert l1 == 3 and l0 == 2  # ring + diagonal pairs + reduce versus self-building + reduce
+    Th = oracle.evaluate_library(ex, X)
+    Gr, Rr, yr = Th @ Th.T, Th @ Y.T, (Y * Y).sum(1)
+    sc = np.sqrt(np.outer(np.diag(Gr), np.diag(Gr)))
+    for G, R, yy in ((G1, R1, y1), (G0, R0, y0)):
+        assert np.max(np.abs(G - Gr) / sc) < 1e-13
+        assert np.max(np.abs(R - Rr)) < 1e-13 * np.sqrt(np.max(np.diag(Gr)) * np.max(yr))
+        np.testing.assert_allclose(yy, yr, rtol=1e-13)
+        np.testing.assert_array_equal(G, G.T)
+
+
+def test_ring_is_bit_reproducible_at_scale(ctx):
+    """2 x 10^6 samples (31 250 producer windows, ~2000 recyclings of every global ring slot), five runs."""
+    n, m = 64, 2_000_000
+    ctx.set_library(oracle.polynomial_exponents(n, 2))
+    ctx.generate(1, n, m, 0, 0, 0.0)
+    (Ga, Ra, ya), launches = _gram(ctx, True)
+    assert launches == 3
+    for _ in range(4):
+        (G, R, yy), _l = _gram(ctx, True)
+        np.testing.assert_array_equal(G, Ga)
+        np.testing.assert_array_equal(R, Ra)
+        np.testing.assert_array_equal(yy, ya)
+    (G0, R0, y0), _l = _gram(ctx, False)
+    sc = np.sqrt(np.outer(np.diag(G0), np.diag(G0)))
+    assert np.max(np.abs(Ga - G0) / sc) < 1e-12
+    assert np.max(np.abs(Ra - R0)) < 1e-12 * np.sqrt(np.max(np.diag(G0)) * np.max(y0))
+    assert Ga[0, 0] == m  # constant term: a sum of ones is exact
