@@ -550,11 +550,26 @@ void build_plan_from_pairs(GramPlan& plan, const std::vector<std::pair<int, int>
 // ---------------------------------------------------------------------------------------------
 // Host side: launch
 // ---------------------------------------------------------------------------------------------
-template <int BT, int NF>
-static int launch_gram(ddb_ctx* ctx, const GramArgs& args, size_t smem) {
-    auto kern = gram_kernel<BT, NF>;
+
+// Kernel for a block tile and the library's maximum total degree: a term is a product of NF staged values,
+// NF = smallest instantiated count >= the degree (every FP64 multiply costs a DMMA issue slot).
+using GramKernel = void (*)(const GramArgs);
+template <int BT>
+static GramKernel pick_gram_kernel(int max_degree) {
+    if (max_degree <= 2) return gram_kernel<BT, 2>;
+    if (max_degree <= 3) return gram_kernel<BT, 3>;
+    if (max_degree <= 4) return gram_kernel<BT, 4>;
+    if (max_degree <= 5) return gram_kernel<BT, 5>;
+    return gram_kernel<BT, kMaxFactors>;
+}
+static GramKernel pick_gram_kernel(int bt, int max_degree) {
+    return bt == 64 ? pick_gram_kernel<64>(max_degree) : pick_gram_kernel<128>(max_degree);
+}
+
+static int launch_gram(ddb_ctx* ctx, int bt, const GramArgs& args, size_t smem) {
+    GramKernel kern = pick_gram_kernel(bt, ctx->max_degree);
     DDB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<ctx->plan.nctas, GramCfg<BT>::kThreads, smem, ctx->stream>>>(args);
+    kern<<<ctx->plan.nctas, bt == 64 ? GramCfg<64>::kThreads : GramCfg<128>::kThreads, smem, ctx->stream>>>(args);
     DDB_CUDA_TRY(cudaGetLastError());
     return DDB_OK;
 }
@@ -581,9 +596,9 @@ int gram_ensure_factors(ddb_ctx* ctx, int kaug_pad) {
 
 // Runs the self-building kernel (BT = 128) over an arbitrary segment list; used by gram_ring.cu for the
 // block pairs that do not get a whole CTA in the ring pass.
-int gram_launch_bt128(ddb_ctx* ctx, const GramArgs& args, int nctas, bool small_deg) {
+int gram_launch_bt128(ddb_ctx* ctx, const GramArgs& args, int nctas) {
     const size_t smem = gram_smem_bytes<128>(args.n, args.n_t);
-    auto kern = small_deg ? gram_kernel<128, 2> : gram_kernel<128, 8>;
+    GramKernel kern = pick_gram_kernel<128>(ctx->max_degree);
     DDB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<nctas, GramCfg<128>::kThreads, smem, ctx->stream>>>(args);
     DDB_CUDA_TRY(cudaGetLastError());
@@ -632,17 +647,10 @@ int gram_run(ddb_ctx* ctx, double* dPacked) {
     // persistent grid: CTAs per SM from the occupancy calculator (1 for BT=128, up to 3 for BT=64)
     int occ = 1;
     {
-        const bool sd = ctx->max_degree <= 2;
-        cudaError_t oe;
-        if (bt == 64) {
-            auto kern = sd ? gram_kernel<64, 2> : gram_kernel<64, 8>;
-            DDB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, GramCfg<64>::kThreads, smem);
-        } else {
-            auto kern = sd ? gram_kernel<128, 2> : gram_kernel<128, 8>;
-            DDB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, GramCfg<128>::kThreads, smem);
-        }
+        GramKernel kern = pick_gram_kernel(bt, ctx->max_degree);
+        DDB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+            &occ, kern, bt == 64 ? GramCfg<64>::kThreads : GramCfg<128>::kThreads, smem);
         DDB_CUDA_TRY(oe);
         if (occ < 1) {
             set_error("ddb_gram: kernel does not fit on an SM (smem %zu bytes)", smem);
@@ -700,12 +708,7 @@ int gram_run(ddb_ctx* ctx, double* dPacked) {
     args.partials = ctx->d_partials.as<double>();
 
     DDB_CUDA_TRY(cudaEventRecord(ctx->ev[0], ctx->stream));
-    const bool small_deg = ctx->max_degree <= 2;
-    int st;
-    if (bt == 64)
-        st = small_deg ? launch_gram<64, 2>(ctx, args, smem) : launch_gram<64, 8>(ctx, args, smem);
-    else
-        st = small_deg ? launch_gram<128, 2>(ctx, args, smem) : launch_gram<128, 8>(ctx, args, smem);
+    const int st = launch_gram(ctx, bt, args, smem);
     DDB_TRY(st);
     dim3 rgrid(pl.npairs, (bt * bt + 255) / 256);
     gram_reduce_kernel<<<rgrid, 256, 0, ctx->stream>>>(ctx->d_partials.as<double>(),
