@@ -18,6 +18,9 @@ from .api import (  # noqa: F401
     DirectDataDrivenProblem,
     DiscreteDataDrivenProblem,
     HardThreshold,
+    ImplicitOptimizer,
+    implicit_candidate_matrix,
+    implicit_regression,
     SR3,
     STLSQ,
     SoftThreshold,

@@ -88,6 +88,7 @@ PROTOTYPES = {
     "ddb_gram_buffer": (C.c_int, [_P, C.POINTER(_P)]),
     "ddb_gram_download": (C.c_int, [_P, _P, _P, _P]),
     "ddb_gram_upload": (C.c_int, [_P, _P, _P, _P, C.c_int]),
+    "ddb_implicit_select": (C.c_int, [_P, _P, C.c_int]),
     "ddb_sweep": (C.c_int, [_P, C.POINTER(SweepParams), _P, C.c_int, C.c_int64]),
     "ddb_rss_count": (C.c_int64, [_P]),
     "ddb_rss": (C.c_int, [_P, _P]),

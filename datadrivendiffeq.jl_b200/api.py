@@ -64,6 +64,8 @@ class Basis:
 
     exponents: np.ndarray
     names: Optional[List[str]] = None
+    implicits: int = 0  # trailing rows of `exponents` that are implicit variables (``Basis(...; implicits = du)``,
+    #                     src/basis/type.jl:15-17); they are evaluated on the problem's DX
 
     def __post_init__(self):
         e = np.asarray(self.exponents)
@@ -82,7 +84,17 @@ class Basis:
 
     @property
     def n_states(self) -> int:
+        return self.exponents.shape[0] - int(self.implicits)
+
+    @property
+    def n_variables(self) -> int:
         return self.exponents.shape[0]
+
+    @property
+    def implicit_idx(self) -> np.ndarray:
+        """``implicit_idx[i, j]``: term i depends on implicit variable j (``is_dependent`` table the reference
+        builds for an implicit ``Basis``)."""
+        return (self.exponents[self.n_states:, :] > 0).T.copy()
 
     def __len__(self) -> int:
         return self.exponents.shape[1]
@@ -91,12 +103,13 @@ class Basis:
         out = []
         for j in range(len(self)):
             parts = []
-            for i in range(self.n_states):
+            for i in range(self.n_variables):
                 p = int(self.exponents[i, j])
+                nm = f"x{i + 1}" if i < self.n_states else f"dx{i - self.n_states + 1}"
                 if p == 1:
-                    parts.append(f"x{i + 1}")
+                    parts.append(nm)
                 elif p > 1:
-                    parts.append(f"x{i + 1}^{p}")
+                    parts.append(f"{nm}^{p}")
             out.append("*".join(parts) if parts else "1")
         return out
 
@@ -256,6 +269,24 @@ class SR3:
         self.proximal = proximal
 
 
+class ImplicitOptimizer:
+    """``ImplicitOptimizer(threshold = 1e-1, opt = STLSQ)`` / ``ImplicitOptimizer(opt)``
+    (``algorithms/Implicit.jl:37-51``): wraps an explicit optimizer."""
+
+    name = "ImplicitOptimizer"
+
+    def __init__(self, optimizer=None, opt=STLSQ):
+        if optimizer is None:
+            optimizer = opt(1e-1)
+        elif not isinstance(optimizer, (STLSQ, ADMM, SR3)):
+            optimizer = opt(optimizer)  # a threshold or threshold grid
+        self.optimizer = optimizer
+
+    @property
+    def thresholds(self):
+        return self.optimizer.thresholds
+
+
 class B200Sparse:
     """The drop-in algorithm type: wraps one of the reference's sparse regression algorithms and runs
     it on B200 GPUs.  ``group``: an initialised ``torch.distributed`` process group (one process per
@@ -263,8 +294,8 @@ class B200Sparse:
     """
 
     def __init__(self, inner, device: int = 0, group=None):
-        if not isinstance(inner, (STLSQ, ADMM, SR3)):
-            raise ValueError("B200Sparse wraps STLSQ, ADMM or SR3")
+        if not isinstance(inner, (STLSQ, ADMM, SR3, ImplicitOptimizer)):
+            raise ValueError("B200Sparse wraps STLSQ, ADMM, SR3 or an ImplicitOptimizer of one of them")
         self.inner = inner
         self.device = int(device)
         self.group = group
@@ -341,6 +372,11 @@ def get_fit_targets(alg: B200Sparse, prob: DataDrivenProblem, basis: Basis):
     X, Y = prob.fit_inputs()
     if X.shape[0] != basis.n_states:
         raise ValueError(f"basis has {basis.n_states} states but the problem has {X.shape[0]}")
+    if basis.implicits:
+        # the library is evaluated on (implicits = get_implicit_data(prob), states); type.jl:433-455
+        if Y.shape[0] != basis.implicits:
+            raise ValueError(f"basis has {basis.implicits} implicit variables but the problem has {Y.shape[0]} targets")
+        return np.vstack([X, Y]), Y
     return X, Y
 
 
@@ -371,6 +407,104 @@ def _params_for(ctx: Context, inner, options: DataDrivenCommonOptions):
     )
 
 
+def _aicc(rss: float, dof: int, nobs: int) -> float:
+    """StatsAPI ``aicc`` of a sparse-regression cache (``DataDrivenSparse.jl:171-201``):
+    ll = -n/2 log(rss/n), aic = -2 ll + 2 k, aicc = aic + 2 k (k + 1) / (n - k - 1)."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ll = -nobs / 2.0 * np.log(rss / nobs)
+        return float(-2.0 * ll + 2.0 * dof + 2.0 * dof * (dof + 1.0) / (nobs - dof - 1.0))
+
+
+def implicit_candidate_matrix(implicit_idx: np.ndarray) -> np.ndarray:
+    """``candidate_matrix`` (``lib/DataDrivenSparse/src/commonsolve.jl:65-74``): term i is a candidate for
+    implicit variable j when it depends on j or on no other implicit variable."""
+    implicit_idx = np.asarray(implicit_idx, dtype=bool)
+    others = implicit_idx.sum(axis=1, keepdims=True) - implicit_idx
+    return implicit_idx | (others == 0)
+
+
+def implicit_regression(ctx: Context, idx: np.ndarray, necessary: np.ndarray, prm, lambdas, m_total: int, group=None):
+    """``(x::ImplicitOptimizer)(X[idx, :], Y; necessary_idx)`` (``Implicit.jl:57-108``) on the Gram blocks
+    already in ``ctx``: every selected row is regressed on the others in ONE batched sweep
+    (``ddb_implicit_select``), then the best left-hand side is chosen on the host exactly as the reference
+    does (dof >= 2, touches a necessary term, smallest AICc, first wins ties).
+    Returns ``(x_opt over idx, optimal_threshold, optimal_iterations, rss of the chosen model, SweepOutput)``."""
+    idx = np.asarray(idx, dtype=np.int64)
+    necessary = np.asarray(necessary, dtype=bool)
+    ctx.implicit_select(idx)
+    ctx.sweep(prm, lambdas, m_total)
+    if group is None:
+        ctx.rss()
+    else:
+        import torch
+
+        from . import dist
+
+        rss = torch.empty(max(1, ctx.rss_count()), dtype=torch.float64, device=f"cuda:{ctx.device}")
+        ctx.rss(rss.data_ptr())
+        dist.allreduce_sum(rss, group)
+    out = ctx.select()
+    kk = idx.size
+    best = -1
+    best_score = 0.0
+    for e in range(kk):
+        inds = np.ones(kk, dtype=bool)
+        inds[e] = False
+        c = out.coefficients[e]
+        if out.dof[e] >= 2 and np.any(c[inds][necessary[inds]] != 0.0):
+            score = _aicc(float(out.rss[e]), int(out.dof[e]), m_total)
+            if best < 0 or score < best_score:
+                best, best_score = e, score
+    if best < 0:
+        raise IndexError("ImplicitOptimizer: no candidate with dof >= 2 touches a necessary term (Implicit.jl:100-102)")
+    x_opt = out.coefficients[best].copy()
+    x_opt[best] = -1.0
+    return x_opt, float(out.lambda_opt[best]), int(out.iterations[best]), float(out.rss[best]), out
+
+
+def _solve_implicit(prob, basis, alg, options, X, Y):
+    """``__sparse_regression(ps::InternalDataDrivenProblem{<:ImplicitOptimizer}, X, Y)``
+    (``lib/DataDrivenSparse/src/commonsolve.jl:58-114``)."""
+    if not basis.implicits:
+        raise AssertionError("The provided `Basis` does not have implicit variables!")
+    ctx = alg.context()
+    ctx.set_library(basis.exponents)
+    inner = alg.inner.optimizer
+    prm = _params_for(ctx, inner, options)
+    ctx.upload(X, Y)
+    m_total = X.shape[1]
+    if alg.group is None:
+        ctx.gram()
+    else:
+        import torch
+
+        from . import dist
+
+        m_total = dist.total_samples(X.shape[1], alg.group, device=f"cuda:{ctx.device}")
+        packed = torch.empty(ctx.gram_count(), dtype=torch.float64, device=f"cuda:{ctx.device}")
+        ctx.gram(packed.data_ptr())
+        dist.allreduce_sum(packed, alg.group)
+        k, n_t, base = ctx.k, ctx.n_t, packed.data_ptr()
+        ctx.gram_upload_ptr(base, base + 8 * k * k, base + 8 * (k * k + k * n_t), n_t)
+    implicit_idx = basis.implicit_idx
+    cm = implicit_candidate_matrix(implicit_idx)
+    C = np.zeros((cm.shape[1], cm.shape[0]))
+    lams, iters, rss_total = [], [], 0.0
+    for i in range(cm.shape[1]):
+        idx = np.nonzero(cm[:, i])[0]
+        x_opt, lam, it, rss_i, _ = implicit_regression(ctx, idx, implicit_idx[idx, i], prm, inner.thresholds, m_total, alg.group)
+        C[i, idx] = x_opt
+        lams.append(lam)
+        iters.append(it)
+        rss_total += rss_i  # sum(abs2, C[i, :] * Theta) of the chosen row: its exact streaming rss
+    ctx.implicit_select(None)
+    res = SparseRegressionResult(coefficients=C, dof=int(np.sum(np.abs(C) > 0.0)), lambda_=np.asarray(lams),
+                                 iterations=np.asarray(iters), testerror=None, trainerror=float(rss_total), retcode=1)
+    Cr = construct_coefficients(C, options.digits)
+    return DataDrivenSolution(basis=basis, coefficients=Cr, results=[res], rss=res.trainerror, dof=int(np.sum(Cr != 0.0)),
+                              nobs=int(Y.shape[0] * m_total), retcode=1, timings=ctx.timings())
+
+
 def solve(prob: DataDrivenProblem, basis: Basis, alg: B200Sparse, options: Optional[DataDrivenCommonOptions] = None,
           paths: bool = False) -> DataDrivenSolution:
     """``solve(prob, basis, alg; options)`` = ``solve!(init(...))`` for the B200 backend.
@@ -381,6 +515,10 @@ def solve(prob: DataDrivenProblem, basis: Basis, alg: B200Sparse, options: Optio
     options = options or DataDrivenCommonOptions()
     _check_options(options)
     X, Y = get_fit_targets(alg, prob, basis)
+    if isinstance(alg.inner, ImplicitOptimizer):
+        return _solve_implicit(prob, basis, alg, options, X, Y)
+    if basis.implicits:
+        raise ValueError("a Basis with implicit variables needs an ImplicitOptimizer (src/basis/type.jl:15)")
     ctx = alg.context()
     ctx.set_library(basis.exponents)
     prm = _params_for(ctx, alg.inner, options)

@@ -76,6 +76,7 @@ class Context:
         """``exponents``: integer array (n x k), entry [i, j] = power of state i in term j."""
         e = np.asfortranarray(exponents, dtype=np.uint8)
         self.n, self.k = e.shape
+        self._imp_k = 0
         _lib.check(self._lib.ddb_set_library_monomial(self._ctx, self.n, self.k, _lib.ptr(e)))
 
     # -- data -------------------------------------------------------------------------------
@@ -113,6 +114,7 @@ class Context:
         return int(self._lib.ddb_gram_count(self._ctx))
 
     def gram(self, d_packed: Optional[int] = None):
+        self._imp_k = 0
         _lib.check(self._lib.ddb_gram(self._ctx, C.c_void_p(d_packed) if d_packed else None))
 
     def gram_buffer(self) -> int:
@@ -130,11 +132,13 @@ class Context:
     def gram_upload(self, G: np.ndarray, R: np.ndarray, yy: np.ndarray):
         G, R, yy = _f(G), _f(R), np.ascontiguousarray(yy, dtype=np.float64)
         self.n_t = R.shape[1]
+        self._imp_k = 0
         _lib.check(self._lib.ddb_gram_upload(self._ctx, _lib.ptr(G), _lib.ptr(R), _lib.ptr(yy), self.n_t))
 
     def gram_upload_ptr(self, pG: int, pR: int, pyy: int, n_t: int):
         """Install blocks from raw (host or device) pointers, e.g. an all-reduced torch tensor."""
         self.n_t = int(n_t)
+        self._imp_k = 0
         _lib.check(self._lib.ddb_gram_upload(self._ctx, C.c_void_p(pG), C.c_void_p(pR), C.c_void_p(pyy), self.n_t))
 
     # -- sweep ------------------------------------------------------------------------------
@@ -169,8 +173,22 @@ class Context:
         _lib.check(self._lib.ddb_rss_buffer(self._ctx, C.byref(p)))
         return int(p.value)
 
+    def implicit_select(self, idx: Optional[Sequence[int]]):
+        """``ddb_implicit_select``: the following sweep / rss / select calls regress EACH of the library rows
+        ``idx`` on the other selected rows (ImplicitOptimizer).  ``None`` or empty returns to explicit mode.
+        A new Gram, data set or library resets the selection on the device side as well."""
+        if idx is None or len(idx) == 0:
+            _lib.check(self._lib.ddb_implicit_select(self._ctx, None, 0))
+            self._imp_k = 0
+            return
+        a = np.ascontiguousarray(idx, dtype=np.int32)
+        _lib.check(self._lib.ddb_implicit_select(self._ctx, _lib.ptr(a), a.size))
+        self._imp_k = int(a.size)
+
     def select(self, paths: bool = False) -> SweepOutput:
         n_t, k, L = self.n_t, self.k, self._L
+        if getattr(self, "_imp_k", 0):
+            n_t = k = self._imp_k
         W = (k + 31) // 32
         coef = np.zeros((n_t, k), order="F")
         lam = np.zeros(n_t)

@@ -109,6 +109,8 @@ int ddb_ctx_destroy(ddb_ctx* ctx) {
     ctx->own_X.release();
     ctx->own_Y.release();
     ctx->d_packed.release();
+    ctx->imp_packed.release();
+    ctx->imp_idx.release();
     ctx->d_partials.release();
     ctx->d_plan.release();
     for (auto& ev : ctx->ev)
@@ -141,6 +143,7 @@ int ddb_set_library_monomial(ddb_ctx* ctx, int n, int k, const uint8_t* exps) {
     ctx->factors_nt = -1;
     ctx->plan_m = -1;
     ctx->have_gram = false;
+    ctx->imp_k = 0;
     return DDB_OK;
 }
 
@@ -175,6 +178,7 @@ int ddb_upload(ddb_ctx* ctx, const double* X, const double* Y, int n_t, int64_t 
     ctx->n_t = n_t;
     ctx->m = m;
     ctx->have_gram = false;
+    ctx->imp_k = 0;
     return DDB_OK;
 }
 
@@ -186,6 +190,7 @@ int ddb_bind_device(ddb_ctx* ctx, const double* dX, const double* dY, int n_t, i
     ctx->n_t = n_t;
     ctx->m = m;
     ctx->have_gram = false;
+    ctx->imp_k = 0;
     return DDB_OK;
 }
 
@@ -272,6 +277,7 @@ int ddb_gram_upload(ddb_ctx* ctx, const double* G, const double* R, const double
     DDB_CUDA_TRY(cudaMemcpyAsync(p + k * k + k * nt, yy, nt * sizeof(double), cudaMemcpyDefault, ctx->stream));
     DDB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     ctx->have_gram = true;
+    ctx->imp_k = 0;
     return DDB_OK;
 }
 

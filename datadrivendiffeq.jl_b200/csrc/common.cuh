@@ -105,6 +105,12 @@ struct ddb_ctx {
     int plan_kaug = -1;
     bool have_gram = false;
 
+    // implicit view (ddb_implicit_select): the sweep runs on G[idx, idx] with EVERY selected library row as a
+    // target regressed on the other selected rows (ImplicitOptimizer, reference Implicit.jl:57-108)
+    ddb::DevBuf imp_packed;              // [G' (kk x kk) | R' = G' | yy' = diag G']
+    ddb::DevBuf imp_idx;                 // kk int32: selected rows of the installed library
+    int imp_k = 0;                       // 0 = explicit mode
+
     // sweep / rss / select state lives in sweep.cu
     ddb::SweepState* sweep = nullptr;
     ddb::DmdState* dmd = nullptr;

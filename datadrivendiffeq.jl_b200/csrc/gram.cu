@@ -723,6 +723,7 @@ int gram_run(ddb_ctx* ctx, double* dPacked) {
     ctx->timings.gram_ms = ms;
     ctx->timings.gram_launches = 2;
     ctx->have_gram = (dPacked == ctx->d_packed.as<double>());
+    ctx->imp_k = 0;
     return DDB_OK;
 }
 

@@ -679,6 +679,7 @@ int gram_ring_run(ddb_ctx* ctx, double* dPacked, bool* handled) {
     ctx->timings.gram_ms = ms;
     ctx->timings.gram_launches = launches;
     ctx->have_gram = (dPacked == ctx->d_packed.as<double>());
+    ctx->imp_k = 0;
     *handled = true;
     return DDB_OK;
 }

@@ -35,14 +35,17 @@ constexpr int kRssAcc = 32;    // candidates per warp per pass (register accumul
 constexpr int kRssWarps = 8;
 constexpr int kRssPitch = kRssTile + 1;  // doubles; transposed tile [state][sample], odd pitch -> conflict-free
 
+// `map` (implicit mode) translates indices of the selected sub-library into rows of the installed library;
+// cand_val == nullptr writes coefficient 1 (the records of the implicit targets).
 __global__ void rss_expand_kernel(const int32_t* __restrict__ cand_idx, const double* __restrict__ cand_val,
                                   int64_t nterms, const uint16_t* __restrict__ factors, int ones_row,
-                                  RssTerm* __restrict__ out) {
+                                  const int32_t* __restrict__ map, RssTerm* __restrict__ out) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nterms) return;
     RssTerm r;
-    r.val = cand_val[t];
-    const uint16_t* f = factors + (size_t)cand_idx[t] * kMaxFactors;
+    r.val = cand_val ? cand_val[t] : 1.0;
+    const int term = cand_idx ? cand_idx[t] : (int)t;
+    const uint16_t* f = factors + (size_t)(map ? map[term] : term) * kMaxFactors;
 #pragma unroll
     for (int d = 0; d < kMaxFactors; ++d) r.o16[d] = (f[d] == kNoFactor) ? (uint16_t)ones_row : f[d];
     r.o32[0] = (int)r.o16[0] * kRssPitch;
@@ -60,6 +63,7 @@ struct RssArgs {
     const int32_t* cand_nnz;
     const int32_t* cand_eq;
     const RssTerm* terms;
+    const RssTerm* targets;  // implicit mode: target e is a library term (one record each); null = row e of Y
     double* partials;  // gridDim.x x ncand
 };
 
@@ -164,7 +168,20 @@ __global__ void __launch_bounds__(kRssWarps * 32) rss_kernel(const RssArgs a) {
                         fit = fma(__hiloint2double(w.y, w.x), p, fit);
                     }
                 }
-                const double res = live ? fit - xs[(a.n + eq) * kRssPitch] : 0.0;
+                double yv;
+                if (a.targets) {
+                    const int4 w = __ldg(reinterpret_cast<const int4*>(a.targets + eq));
+                    yv = xs[w.z] * xs[w.w];
+                    if (NF > 2) {
+                        const int4 o = __ldg(reinterpret_cast<const int4*>(a.targets + eq) + 1);
+                        const uint32_t ow[4] = {(uint32_t)o.x, (uint32_t)o.y, (uint32_t)o.z, (uint32_t)o.w};
+#pragma unroll
+                        for (int d = 2; d < NF; ++d) yv *= xs[((ow[d >> 1] >> (16 * (d & 1))) & 0xFFFFu) * kRssPitch];
+                    }
+                } else {
+                    yv = xs[(a.n + eq) * kRssPitch];
+                }
+                const double res = live ? fit - yv : 0.0;
                 acc[q] = fma(res, res, acc[q]);
             }
         }
@@ -199,6 +216,7 @@ int rss_run(ddb_ctx* ctx, SweepState* S, double* dRss) {
         return DDB_BAD_STATE;
     }
     const int ncand = S->ncand;
+    const bool implicit = ctx->imp_k > 0;
     cudaStream_t st = ctx->stream;
     if (!dRss) {
         DDB_TRY(S->rss.reserve((size_t)std::max(1, ncand) * 8));
@@ -210,7 +228,14 @@ int rss_run(ddb_ctx* ctx, SweepState* S, double* dRss) {
     if (nterms > 0)
         rss_expand_kernel<<<(unsigned)((nterms + 255) / 256), 256, 0, st>>>(S->cand_idx.as<int32_t>(), S->cand_val.as<double>(),
                                                                             nterms, ctx->d_factors.as<uint16_t>(), ctx->n + ctx->n_t,
+                                                                            implicit ? ctx->imp_idx.as<int32_t>() : nullptr,
                                                                             S->cand_terms.as<RssTerm>());
+    if (implicit) {  // one record per target: the library term on the left-hand side
+        DDB_TRY(S->tgt_terms.reserve((size_t)ctx->imp_k * sizeof(RssTerm)));
+        rss_expand_kernel<<<(ctx->imp_k + 255) / 256, 256, 0, st>>>(nullptr, nullptr, ctx->imp_k, ctx->d_factors.as<uint16_t>(),
+                                                                   ctx->n + ctx->n_t, ctx->imp_idx.as<int32_t>(),
+                                                                   S->tgt_terms.as<RssTerm>());
+    }
     const int passes = (ncand + kRssWarps * kRssAcc - 1) / (kRssWarps * kRssAcc);
     const int64_t ntiles = (ctx->m + kRssTile - 1) / kRssTile;
     const int nparts = (int)std::min<int64_t>(ntiles, (int64_t)ctx->sm_count * 4);
@@ -226,6 +251,7 @@ int rss_run(ddb_ctx* ctx, SweepState* S, double* dRss) {
     a.cand_nnz = S->cand_nnz.as<int32_t>();
     a.cand_eq = S->cand_eq.as<int32_t>();
     a.terms = S->cand_terms.as<RssTerm>();
+    a.targets = implicit ? S->tgt_terms.as<RssTerm>() : nullptr;
     a.partials = S->rss_partials.as<double>();
     const size_t smem = 2 * (size_t)kRssPitch * (ctx->n + ctx->n_t + 1) * sizeof(double);
     if (smem > 200 * 1024) {

@@ -348,6 +348,11 @@ struct SweepDev {
     const double* dinv;     // k
     const double* rs;       // n_t x k scaled right-hand sides
     const double* rraw;     // n_t x k unscaled right-hand sides (R, column e = target e)
+    // implicit mode (n_t == k, target e is library row e regressed on the others): Ninv = inverse of the
+    // equilibrated system matrix; a solve with the full matrix and entry e of the right-hand side zeroed,
+    // followed by z -= Ninv[:, e] * z[e] / Ninv[e, e], is the solve with row and column e deleted.
+    int implicit;
+    const double* Ninv;     // k x k (symmetric) or null
     // per target
     double* x;              // n_t x k
     double* xprev;          // n_t x k
@@ -538,27 +543,72 @@ __device__ void finish_step(const SweepDev& S, int e, double* red, int* redi, in
     __syncthreads();
 }
 
+// implicit mode: Ninv <- identity (right-hand sides of the inverse), z[e][e] <- 0
+__global__ void implicit_prep_kernel(double* __restrict__ Ninv, double* __restrict__ z, int k) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)k * k) return;
+    const int e = (int)(t / k), i = (int)(t % k);
+    Ninv[t] = (e == i) ? 1.0 : 0.0;
+    if (e == i) z[t] = 0.0;
+}
+
+// implicit view: packed' = [G[idx, idx] | G[idx, idx] | diag] from the full packed blocks
+__global__ void implicit_gather_kernel(const double* __restrict__ G, int k, const int32_t* __restrict__ idx, int kk,
+                                       double* __restrict__ out) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)kk * kk) return;
+    const int j = (int)(t / kk), i = (int)(t % kk);
+    const double v = G[(size_t)idx[i] + (size_t)k * idx[j]];
+    out[t] = v;
+    out[(size_t)kk * kk + t] = v;
+    if (i == j) out[2 * (size_t)kk * kk + i] = v;
+}
+
+int implicit_select(ddb_ctx* ctx, const int32_t* idx, int kk) {
+    if (kk == 0) {
+        ctx->imp_k = 0;
+        return DDB_OK;
+    }
+    if (!ctx->d_packed.p || !ctx->have_gram || ctx->k <= 0) {
+        set_error("ddb_implicit_select: no normal-equation blocks in the context (run ddb_gram first)");
+        return DDB_BAD_STATE;
+    }
+    if (!idx || kk < 2 || kk > ctx->k) {
+        set_error("ddb_implicit_select: need 2 <= kk <= k selected library rows");
+        return DDB_INVALID_ARG;
+    }
+    std::vector<char> seen(ctx->k, 0);
+    for (int i = 0; i < kk; ++i) {
+        if (idx[i] < 0 || idx[i] >= ctx->k || seen[idx[i]]) {
+            set_error("ddb_implicit_select: idx[%d] = %d is out of range or repeated", i, idx[i]);
+            return DDB_INVALID_ARG;
+        }
+        seen[idx[i]] = 1;
+    }
+    cudaStream_t st = ctx->stream;
+    DDB_TRY(ctx->imp_idx.reserve((size_t)kk * 4));
+    DDB_TRY(ctx->imp_packed.reserve((2 * (size_t)kk * kk + kk) * 8));
+    DDB_CUDA_TRY(cudaMemcpyAsync(ctx->imp_idx.p, idx, (size_t)kk * 4, cudaMemcpyHostToDevice, st));
+    implicit_gather_kernel<<<(unsigned)(((size_t)kk * kk + 255) / 256), 256, 0, st>>>(
+        ctx->d_packed.as<double>(), ctx->k, ctx->imp_idx.as<int32_t>(), kk, ctx->imp_packed.as<double>());
+    DDB_CUDA_TRY(cudaGetLastError());
+    DDB_CUDA_TRY(cudaStreamSynchronize(st));  // idx is the caller's buffer
+    ctx->imp_k = kk;
+    if (ctx->sweep) ctx->sweep->valid = false;
+    return DDB_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // init: x0 from the shared full solve, initial mask, zero-model bookkeeping
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) sweep_init_kernel(SweepDev S) {
-    const int e = blockIdx.x;
+// Tail of init_cache for target e, given the initial full solution in x: initial mask (strict cut at the
+// smallest threshold), state machine, zero-model candidate.  Called by all threads of the CTA.
+__device__ void finish_init(const SweepDev& S, int e, int* redi) {
     const int k = S.k, W = S.W;
-    __shared__ double red[32];
-    __shared__ int redi[32];
     EqState& st = S.eq[e];
-    double* x = S.x + (size_t)e * k;
-    double* xp = S.xprev + (size_t)e * k;
-    const double* z = S.znew + (size_t)e * k;
+    const double* x = S.x + (size_t)e * k;
     uint32_t* act = S.active + (size_t)e * W;
     const double cut = threshold_cut(S, S.lambdas[0]);  // lambdas sorted: [0] is the minimum
-    for (int i = threadIdx.x; i < k; i += blockDim.x) {
-        const double v = z[i] * S.dinv[i];
-        x[i] = v;
-        xp[i] = (S.algorithm == DDB_ALG_SR3) ? v : 0.0;  // SR3.jl:122 copies, STLSQ/ADMM start from zero
-        if (S.aux1) S.aux1[(size_t)e * k + i] = 0.0;
-        if (S.aux2) S.aux2[(size_t)e * k + i] = 0.0;
-    }
     __syncthreads();
     int cnt = 0;
     for (int w = threadIdx.x; w < W; w += blockDim.x) {
@@ -579,14 +629,62 @@ __global__ void __launch_bounds__(256) sweep_init_kernel(SweepDev S) {
         st.nruns = 0;
         st.last_cand = -1;
         st.dof0 = na;  // dof of the zeroed best cache = mask of the initial solution (solver.jl:82-83)
-        st.flags = 0;
+        st.pad[0] = 0;  // initial solve done
         // candidate e is the zero model of target e
         S.cand_off[e] = 0;
         S.cand_nnz[e] = 0;
         S.cand_dof[e] = na;
         S.cand_eq[e] = e;
     }
-    (void)red;
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) sweep_init_kernel(SweepDev S) {
+    const int e = blockIdx.x;
+    const int k = S.k, W = S.W;
+    __shared__ int redi[32];
+    EqState& st = S.eq[e];
+    double* x = S.x + (size_t)e * k;
+    double* xp = S.xprev + (size_t)e * k;
+    const double* z = S.znew + (size_t)e * k;
+    if (S.implicit && S.algorithm == DDB_ALG_STLSQ) {
+        // Implicit STLSQ: the initial least squares of target e runs on the library WITHOUT row e.  With an
+        // exact implicit relation in the data the full Gram matrix is singular (that is the point of the
+        // method) while G without a row of the relation is not, so there is no shared factorisation here: the
+        // initial solve is a masked solve (mask = all but e) through the same kernels as every later step.
+        uint32_t* act = S.active + (size_t)e * W;
+        for (int i = threadIdx.x; i < k; i += blockDim.x) x[i] = xp[i] = 0.0;
+        for (int w = threadIdx.x; w < W; w += blockDim.x) {
+            uint32_t bits = (w * 32 + 32 <= k) ? 0xFFFFFFFFu : ((1u << (k - w * 32)) - 1u);
+            if (e / 32 == w) bits &= ~(1u << (e % 32));
+            act[w] = bits;
+        }
+        if (threadIdx.x == 0) {
+            st.j = 0;
+            st.iter = 0;
+            st.counter = 0;
+            st.na = k - 1;
+            st.status = kEqRunning;
+            st.nruns = 0;
+            st.last_cand = -1;
+            st.dof0 = 0;
+            st.flags = 0;
+            st.pad[0] = 1;  // initial solve pending
+        }
+        return;
+    }
+    // implicit ADMM / SR3: row/column e deleted through the rank-one correction (see SweepDev)
+    const double corr = S.implicit ? z[e] / S.Ninv[(size_t)e * k + e] : 0.0;
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        double v = z[i] * S.dinv[i];
+        if (S.implicit) v = (i == e) ? 0.0 : (z[i] - S.Ninv[(size_t)e * k + i] * corr) * S.dinv[i];
+        x[i] = v;
+        xp[i] = (S.algorithm == DDB_ALG_SR3) ? v : 0.0;  // SR3.jl:122 copies, STLSQ/ADMM start from zero
+        if (S.aux1) S.aux1[(size_t)e * k + i] = 0.0;
+        if (S.aux2) S.aux2[(size_t)e * k + i] = 0.0;
+    }
+    if (threadIdx.x == 0) st.flags = 0;
+    finish_init(S, e, redi);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -701,7 +799,10 @@ __global__ void __launch_bounds__(256) stlsq_small_kernel(SweepDev S, int small_
         // X[p] = solution (un-scaled)   (STLSQ.jl:128-140)
         for (int i = threadIdx.x; i < na; i += blockDim.x) x[idx[i]] = rhs[i] * S.dinv[idx[i]];
         __syncthreads();
-        finish_step(S, e, red, redi, s_tmp);
+        if (st.pad[0])
+            finish_init(S, e, redi);  // that was the initial solve of an implicit target, not a step
+        else
+            finish_step(S, e, red, redi, s_tmp);
     }
 }
 
@@ -765,7 +866,10 @@ __global__ void __launch_bounds__(256) stlsq_big_finish_kernel(SweepDev S, const
         S.eq[e].status = kEqRunning;
     }
     __syncthreads();
-    finish_step(S, e, red, redi, s_tmp);
+    if (S.eq[e].pad[0])
+        finish_init(S, e, redi);  // initial solve of an implicit target
+    else
+        finish_step(S, e, red, redi, s_tmp);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -790,7 +894,7 @@ __global__ void __launch_bounds__(256) relax_rhs_kernel(SweepDev S, int* active_
             b = r[i] + S.rho * (S.aux1[(size_t)e * k + i] - S.aux2[(size_t)e * k + i]);
         else
             b = r[i] + xi * S.rho;
-        z[i] = b * S.dinv[i];
+        z[i] = (S.implicit && i == e) ? 0.0 : b * S.dinv[i];
     }
 }
 
@@ -811,12 +915,18 @@ __global__ void __launch_bounds__(256) relax_finish_kernel(SweepDev S) {
     double* x = S.x + (size_t)e * k;
     const double* z = S.znew + (size_t)e * k;
     const double lam = S.lambdas[st.j];
+    // implicit mode: row/column e deleted from the system through the rank-one correction (see SweepDev)
+    const double corr = S.implicit ? z[e] / S.Ninv[(size_t)e * k + e] : 0.0;
+    auto solved = [&](int i) -> double {
+        if (!S.implicit) return z[i] * S.dinv[i];
+        return (i == e) ? 0.0 : (z[i] - S.Ninv[(size_t)e * k + i] * corr) * S.dinv[i];
+    };
     if (S.algorithm == DDB_ALG_ADMM) {
         double* alpha = S.aux1 + (size_t)e * k;
         double* w = S.aux2 + (size_t)e * k;
         const double t = lam / S.rho;
         for (int i = threadIdx.x; i < k; i += blockDim.x) {
-            const double xi = z[i] * S.dinv[i];       // X = (B + rho (alpha - w)) / A
+            const double xi = solved(i);              // X = (B + rho (alpha - w)) / A
             const double a = soft(xi + w[i], t);      // alpha = prox(X + w, lambda/rho)
             alpha[i] = a;
             w[i] += xi - a;                           // w += X - alpha
@@ -826,7 +936,7 @@ __global__ void __launch_bounds__(256) relax_finish_kernel(SweepDev S) {
         double* Wv = S.aux1 + (size_t)e * k;
         const double cadr = isnan(S.cad_rho) ? 5.0 * lam : S.cad_rho;
         for (int i = threadIdx.x; i < k; i += blockDim.x) {
-            const double wi = z[i] * S.dinv[i];       // W = (B + nu X) / A
+            const double wi = solved(i);              // W = (B + nu X) / A
             Wv[i] = wi;
             double xi;
             if (S.proximal == DDB_PROX_HARD) xi = (fabs(wi) > sqrt(2.0 * lam)) ? wi : 0.0;
@@ -934,7 +1044,8 @@ void SweepState::release_all() {
     DevBuf* all[] = {&As, &Lfac, &dinv, &rs, &x, &xprev, &aux1, &aux2, &znew, &active, &eq, &lambdas_d, &cand_idx,
                      &cand_val, &cand_off, &cand_nnz, &cand_dof, &cand_eq, &counters, &pool_used_d, &run_cand,
                      &run_jfirst, &run_j, &path_support, &path_coef, &path_iters, &big_ws, &big_idx, &big_na,
-                     &big_list, &big_fail, &active_matrix, &shared_fail, &rss, &rss_partials, &out_tmp, &cand_terms};
+                     &big_list, &big_fail, &active_matrix, &shared_fail, &rss, &rss_partials, &out_tmp, &cand_terms,
+                     &Ninv, &tgt_terms};
     for (DevBuf* b : all) b->release();
 }
 
@@ -964,7 +1075,9 @@ static SweepDev make_dev(ddb_ctx* ctx, SweepState* S) {
     D.As = S->As.as<double>();
     D.dinv = S->dinv.as<double>();
     D.rs = S->rs.as<double>();
-    D.rraw = ctx->d_packed.as<double>() + (size_t)S->k * S->k;
+    D.rraw = (ctx->imp_k > 0 ? ctx->imp_packed.as<double>() : ctx->d_packed.as<double>()) + (size_t)S->k * S->k;
+    D.implicit = ctx->imp_k > 0;
+    D.Ninv = D.implicit ? S->Ninv.as<double>() : nullptr;
     D.x = S->x.as<double>();
     D.xprev = S->xprev.as<double>();
     D.aux1 = S->prm.algorithm == DDB_ALG_STLSQ ? nullptr : S->aux1.as<double>();
@@ -999,7 +1112,7 @@ int sweep_run(ddb_ctx* ctx, const ddb_sweep_params* prm, const double* lambdas, 
         set_error("ddb_sweep: params, lambdas must be non-null and L, m_total positive");
         return DDB_INVALID_ARG;
     }
-    if (!ctx->d_packed.p || ctx->k <= 0 || ctx->n_t <= 0) {
+    if (!ctx->d_packed.p || ctx->k <= 0 || (ctx->n_t <= 0 && ctx->imp_k <= 0)) {
         set_error("ddb_sweep: no normal-equation blocks in the context (run ddb_gram or ddb_gram_upload first)");
         return DDB_BAD_STATE;
     }
@@ -1020,7 +1133,8 @@ int sweep_run(ddb_ctx* ctx, const ddb_sweep_params* prm, const double* lambdas, 
     SweepState* S = ctx->sweep;
     S->valid = false;
     S->have_rss = false;
-    const int k = ctx->k, n_t = ctx->n_t;
+    const bool implicit = ctx->imp_k > 0;
+    const int k = implicit ? ctx->imp_k : ctx->k, n_t = implicit ? ctx->imp_k : ctx->n_t;
     const int W = (k + 31) / 32;
     S->k = k;
     S->n_t = n_t;
@@ -1080,25 +1194,37 @@ int sweep_run(ddb_ctx* ctx, const ddb_sweep_params* prm, const double* lambdas, 
 
     DDB_CUDA_TRY(cudaEventRecord(ctx->ev[4], st));
     // ---- preparation + shared factorisation --------------------------------------------------
-    const double* G = ctx->d_packed.as<double>();
+    const double* G = implicit ? ctx->imp_packed.as<double>() : ctx->d_packed.as<double>();
     const double* R = G + kk;
     const double rho = prm->rho;  // 0 for plain STLSQ
     prep_diag_kernel<<<(k + 255) / 256, 256, 0, st>>>(G, k, rho, S->dinv.as<double>());
     prep_scale_kernel<<<(unsigned)((kk + 255) / 256), 256, 0, st>>>(G, k, rho, S->dinv.as<double>(), S->As.as<double>());
     prep_rhs_kernel<<<(unsigned)((nk + 255) / 256), 256, 0, st>>>(R, k, n_t, S->dinv.as<double>(), S->rs.as<double>());
     launches += 3;
-    DDB_CUDA_TRY(cudaMemcpyAsync(S->Lfac.p, S->As.p, kk * 8, cudaMemcpyDeviceToDevice, st));
-    DDB_TRY(chol_batched(ctx, S->Lfac.as<double>(), 0, k, nullptr, k, 1, S->shared_fail.as<int>(), &launches));
-    DDB_CUDA_TRY(cudaMemcpyAsync(S->znew.p, S->rs.p, nk * 8, cudaMemcpyDeviceToDevice, st));
     const size_t solve_smem = ((size_t)((k + 31) / 32) * 32 + 32 * 33) * sizeof(double);
     if (solve_smem > 200 * 1024) {
         set_error("ddb_sweep: library of %d terms exceeds the shared-memory triangular solver (max ~24000)", k);
         return DDB_UNSUPPORTED;
     }
     DDB_CUDA_TRY(cudaFuncSetAttribute(chol_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
-    chol_solve_kernel<<<dim3(n_t, 1), 256, solve_smem, st>>>(S->Lfac.as<double>(), 0, k, nullptr, k,
-                                                             S->znew.as<double>(), (size_t)k, n_t, nullptr, nullptr);
-    ++launches;
+    const bool shared_factor = !(implicit && prm->algorithm == DDB_ALG_STLSQ);  // see sweep_init_kernel
+    if (shared_factor) {
+        DDB_CUDA_TRY(cudaMemcpyAsync(S->Lfac.p, S->As.p, kk * 8, cudaMemcpyDeviceToDevice, st));
+        DDB_TRY(chol_batched(ctx, S->Lfac.as<double>(), 0, k, nullptr, k, 1, S->shared_fail.as<int>(), &launches));
+        DDB_CUDA_TRY(cudaMemcpyAsync(S->znew.p, S->rs.p, nk * 8, cudaMemcpyDeviceToDevice, st));
+        if (implicit) {
+            // inverse of the equilibrated matrix (identity right-hand sides) and the own entry of every
+            // target's right-hand side zeroed before the shared full solve
+            DDB_TRY(S->Ninv.reserve(kk * 8));
+            implicit_prep_kernel<<<(unsigned)((kk + 255) / 256), 256, 0, st>>>(S->Ninv.as<double>(), S->znew.as<double>(), k);
+            chol_solve_kernel<<<dim3(k, 1), 256, solve_smem, st>>>(S->Lfac.as<double>(), 0, k, nullptr, k,
+                                                                   S->Ninv.as<double>(), (size_t)k, k, nullptr, nullptr);
+            launches += 2;
+        }
+        chol_solve_kernel<<<dim3(n_t, 1), 256, solve_smem, st>>>(S->Lfac.as<double>(), 0, k, nullptr, k,
+                                                                 S->znew.as<double>(), (size_t)k, n_t, nullptr, nullptr);
+        ++launches;
+    }
     SweepDev D = make_dev(ctx, S);
     sweep_init_kernel<<<n_t, 256, 0, st>>>(D);
     ++launches;
@@ -1245,6 +1371,15 @@ int select_run(ddb_ctx* ctx, double* coef, double* lambda_opt, int32_t* iters, d
 using namespace ddb;
 
 extern "C" {
+
+int ddb_implicit_select(ddb_ctx* ctx, const int32_t* idx, int kk) {
+    if (!ctx) {
+        set_error("ddb_implicit_select: null context");
+        return DDB_INVALID_ARG;
+    }
+    DDB_CUDA_TRY(cudaSetDevice(ctx->device));
+    return implicit_select(ctx, idx, kk);
+}
 
 int ddb_sweep(ddb_ctx* ctx, const ddb_sweep_params* params, const double* lambdas, int L, int64_t m_total) {
     if (!ctx) {

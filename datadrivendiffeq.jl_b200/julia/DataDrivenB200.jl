@@ -27,7 +27,7 @@ struct SweepParams            # ddb_sweep_params
     abstol::Float64; reltol::Float64; rho::Float64; cad_rho::Float64
 end
 
-struct B200Sparse{A <: Union{STLSQ, ADMM, SR3}} <: DataDrivenSparse.AbstractSparseRegressionAlgorithm
+struct B200Sparse{A <: Union{STLSQ, ADMM, SR3, ImplicitOptimizer}} <: DataDrivenSparse.AbstractSparseRegressionAlgorithm
     inner::A
     device::Int
 end
@@ -50,8 +50,8 @@ function DataDrivenDiffEq.get_fit_targets(::B200Sparse, prob::DataDrivenDiffEq.A
 end
 
 # exponent table of a monomial basis, n x k, in the basis' own term order
-function exponent_table(basis)
-    xs = states(basis)
+function exponent_table(basis; implicits::Bool = false)
+    xs = implicits ? vcat(states(basis), DataDrivenDiffEq.implicit_variables(basis)) : states(basis)
     eqs = [eq.rhs for eq in equations(basis)]
     E = zeros(UInt8, length(xs), length(eqs))
     for (j, term) in enumerate(eqs), (i, x) in enumerate(xs)
@@ -75,6 +75,75 @@ relax(a::STLSQ) = Float64(a.rho); relax(a::ADMM) = Float64(a.rho); relax(a::SR3)
 selector_id(f) = f === DataDrivenDiffEq.bic ? Int32(0) : f === DataDrivenDiffEq.aic ? Int32(1) :
                  f === DataDrivenDiffEq.aicc ? Int32(2) : f === DataDrivenDiffEq.rss ? Int32(3) :
                  throw(ArgumentError("B200Sparse: selector must be bic, aic, aicc or rss"))
+
+# StatsAPI aicc of a sparse-regression cache (lib/DataDrivenSparse/src/DataDrivenSparse.jl:171-201)
+function aicc_of(rss, dof, nobs)
+    ll = -nobs / 2 * log(rss / nobs)
+    return -2ll + 2dof + 2dof * (dof + 1) / (nobs - dof - 1)
+end
+
+# HOOK 2b: ImplicitOptimizer (lib/DataDrivenSparse/src/commonsolve.jl:58-114 + algorithms/Implicit.jl:57-108).
+# The library is evaluated on (implicits = DX, states = X): the exponent table covers [states; implicits] and
+# the device "states" are vcat(X, DX).  One Gram pass; then, per implicit variable, ONE batched sweep regresses
+# every candidate row on the others (ddb_implicit_select) and the best left-hand side is chosen here exactly
+# as the reference does (dof >= 2, touches a necessary term, smallest AICc).
+function CommonSolve.solve!(ps::InternalDataDrivenProblem{<:B200Sparse{<:ImplicitOptimizer}})
+    (; alg, basis, traindata, problem, options, implicit_idx) = ps
+    @assert DataDrivenDiffEq.is_implicit(basis) "The provided `Basis` does not have implicit variables!"
+    X, Y = first(traindata)
+    XA = Matrix{Float64}(vcat(X, Y)); Y = Matrix{Float64}(Y)
+    n, m = size(XA); n_t = size(Y, 1)
+    E = exponent_table(basis; implicits = true); k = size(E, 2)
+    inner = alg.inner.optimizer
+    lambdas = collect(Float64, DataDrivenSparse.get_thresholds(inner))
+    prox = DataDrivenSparse.get_proximal(inner)
+    prm = Ref(SweepParams(alg_id(inner), prox_id(prox), selector_id(options.selector), options.maxiters,
+        options.abstol, options.reltol, relax(inner), prox isa ClippedAbsoluteDeviation ? Float64(prox.ρ) : NaN))
+    C = zeros(size(implicit_idx, 2), k); lams = Float64[]; its = Int[]; trainerror = 0.0
+    ctx = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:ddb_ctx_create, LIB), Cint, (Cint, Ptr{Ptr{Cvoid}}), alg.device, ctx))
+    try
+        GC.@preserve XA Y E lambdas begin
+            check(ccall((:ddb_set_library_monomial, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}), ctx[], n, k, E))
+            check(ccall((:ddb_upload, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cint, Int64), ctx[], XA, Y, n_t, m))
+            check(ccall((:ddb_gram, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), ctx[], C_NULL))
+            for i in axes(implicit_idx, 2)
+                others = [j for j in axes(implicit_idx, 2) if j != i]
+                idx = [r for r in axes(implicit_idx, 1) if implicit_idx[r, i] || !any(implicit_idx[r, others])]
+                kk = length(idx); idx0 = Int32.(idx .- 1)
+                coef = zeros(kk, kk); lam = zeros(kk); iters = zeros(Int32, kk); rss = zeros(kk); dof = zeros(Int32, kk)
+                GC.@preserve idx0 coef lam iters rss dof begin
+                    check(ccall((:ddb_implicit_select, LIB), Cint, (Ptr{Cvoid}, Ptr{Int32}, Cint), ctx[], idx0, kk))
+                    check(ccall((:ddb_sweep, LIB), Cint, (Ptr{Cvoid}, Ptr{SweepParams}, Ptr{Float64}, Cint, Int64),
+                        ctx[], prm, lambdas, length(lambdas), m))
+                    check(ccall((:ddb_rss, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), ctx[], C_NULL))
+                    check(ccall((:ddb_select, LIB), Cint,
+                        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Float64}, Ptr{Int32}, Ptr{UInt32},
+                         Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
+                        ctx[], coef, lam, iters, rss, dof, C_NULL, C_NULL, C_NULL, C_NULL))
+                end
+                necessary = implicit_idx[idx, i]
+                best = 0
+                for e in 1:kk
+                    inds = setdiff(1:kk, e)
+                    if dof[e] >= 2 && any(!iszero, coef[e, inds[necessary[inds]]])
+                        if best == 0 || aicc_of(rss[e], dof[e], m) < aicc_of(rss[best], dof[best], m)
+                            best = e
+                        end
+                    end
+                end
+                row = coef[best, :]; row[best] = -1.0          # BoundsError for best == 0, as in the reference
+                C[i, idx] .= row
+                push!(lams, lam[best]); push!(its, iters[best]); trainerror += rss[best]
+            end
+        end
+    finally
+        ccall((:ddb_ctx_destroy, LIB), Cint, (Ptr{Cvoid},), ctx[])
+    end
+    result = DataDrivenSparse.SparseRegressionResult(C, sum(abs.(C) .> 0.0), lams, its, nothing, trainerror, DDReturnCode(1))
+    new_basis = __construct_basis(copy(C), basis, problem, options)
+    return DataDrivenSolution(new_basis, problem, alg, [result], ps, result.retcode)
+end
 
 # HOOK 2
 function CommonSolve.solve!(ps::InternalDataDrivenProblem{<:B200Sparse})

@@ -153,6 +153,21 @@ int ddb_gram_upload(ddb_ctx* ctx, const double* G, const double* R, const double
 
 /* ---- stage 3: thresholded sweep ---------------------------------------------------------------- */
 
+/* ---- implicit sparse regression (ImplicitOptimizer) ----------------------------------------------
+ * Replaces the per-candidate loop of `(x::ImplicitOptimizer)(X, Y)` (lib/DataDrivenSparse/src/algorithms/
+ * Implicit.jl:57-108): `solver(X[inds, :], X[i, :])` for every library row i.  Every one of those regressions
+ * is a sub-block of the SAME Gram matrix, so no further pass over the data is needed.
+ *
+ * ddb_implicit_select restricts the following ddb_sweep / ddb_rss / ddb_select calls to the library rows
+ * idx[0..kk) (host array; indices into the installed library, distinct) and makes EACH of them a target that
+ * is regressed on the other kk - 1 selected rows: afterwards "k" = "n_t" = kk for the outputs of ddb_select
+ * (coef is kk x kk column-major, coef[e + kk*j] = coefficient of selected row j in the model of row e, zero on
+ * the diagonal; rss[e] = sum_s (theta_e(s) - sum_j coef[e,j] theta_j(s))^2 by the exact streaming pass).
+ * Needs the normal-equation blocks of the full library in the context (ddb_gram / ddb_gram_upload).
+ * kk = 0 returns to the explicit mode; a new Gram, data set or library does so as well.  The choice of the
+ * best left-hand side (dof >= 2, necessary terms, smallest AICc; Implicit.jl:87-98) is host logic. */
+int ddb_implicit_select(ddb_ctx* ctx, const int32_t* idx, int kk);
+
 /* Run the warm-started threshold sweep of SparseLinearSolver (solver.jl:72-118) for all n_t targets
  * on the normal-equation blocks currently in the context (after ddb_gram [+ all-reduce]).
  * lambdas: L thresholds exactly as the algorithm struct stores them (for SR3+HardThreshold the

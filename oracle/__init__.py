@@ -46,6 +46,9 @@ from .sparse import (  # noqa: F401
     apply_active_set,
     sparse_regression,
     construct_coefficients,
+    ImplicitOptimizer,
+    implicit_candidate_matrix,
+    implicit_sparse_regression,
     bic,
     aic,
     aicc,

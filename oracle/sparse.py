@@ -435,3 +435,87 @@ def construct_coefficients(C: np.ndarray, digits: int = 10) -> np.ndarray:
     out = np.trunc(np.asarray(C, dtype=np.float64) * og) / og
     out[np.abs(out) <= EPS] = 0.0
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# ImplicitOptimizer (lib/DataDrivenSparse/src/algorithms/Implicit.jl:37-108) and its driver
+# (lib/DataDrivenSparse/src/commonsolve.jl:58-114)
+# ----------------------------------------------------------------------------------------------
+class ImplicitOptimizer:
+    """``ImplicitOptimizer(opt)`` (``Implicit.jl:37-51``): wraps an explicit optimizer; every library row
+    in turn is the left-hand side, regressed on the remaining rows."""
+
+    name = "ImplicitOptimizer"
+
+    def __init__(self, optimizer=None, threshold=1e-1):
+        self.optimizer = optimizer if optimizer is not None else STLSQ(threshold)
+
+    @property
+    def thresholds(self):
+        return self.optimizer.thresholds
+
+    def __call__(self, X: np.ndarray, Y=None, options: Optional[CommonOptions] = None, necessary_idx=None, results_out=None):
+        """``(x::ImplicitOptimizer)(X, Y; options, necessary_idx)`` (``Implicit.jl:57-108``).  ``Y`` is not
+        used by the reference either.  Returns ``(x_opt 1 x n, optimal_threshold, optimal_iterations)``."""
+        X = np.asarray(X, dtype=np.float64)
+        n = X.shape[0]
+        necessary_idx = np.ones(n, dtype=bool) if necessary_idx is None else np.asarray(necessary_idx, dtype=bool)
+        solver = SparseLinearSolver(self.optimizer, options)
+        results = []
+        for i in range(n):  # :74-84
+            inds = np.ones(n, dtype=bool)
+            inds[i] = False
+            results.append(solver.solve_target(X[inds], X[i]))
+        best_id = -1
+        for i, res in enumerate(results):  # :87-98
+            inds = np.ones(n, dtype=bool)
+            inds[i] = False
+            c = res[0]
+            if dof(c) >= 2 and np.any(c.X[necessary_idx[inds]] != 0.0):
+                if best_id < 0 or aicc(c) < aicc(results[best_id][0]):
+                    best_id = i
+        if best_id < 0:
+            raise IndexError("ImplicitOptimizer: no candidate with dof >= 2 touches a necessary term (Implicit.jl:100-102)")
+        inds = np.ones(n, dtype=bool)
+        inds[best_id] = False
+        best_cache, lam, iters = results[best_id]
+        x_opt = np.zeros((1, n))
+        x_opt[0, best_id] = -1.0  # :105
+        x_opt[0, inds] = best_cache.X  # :106
+        if results_out is not None:
+            results_out.extend(results)
+        return x_opt, lam, iters
+
+
+def implicit_candidate_matrix(implicit_idx: np.ndarray) -> np.ndarray:
+    """``candidate_matrix`` of ``commonsolve.jl:65-74``: row i is a candidate for implicit variable j when it
+    depends on variable j or on no OTHER implicit variable."""
+    implicit_idx = np.asarray(implicit_idx, dtype=bool)
+    k, ni = implicit_idx.shape
+    cm = np.zeros((k, ni), dtype=bool)
+    for i in range(k):
+        for j in range(ni):
+            others = np.ones(ni, dtype=bool)
+            others[j] = False
+            cm[i, j] = implicit_idx[i, j] or implicit_idx[i, others].sum() == 0
+    return cm
+
+
+def implicit_sparse_regression(alg: ImplicitOptimizer, Theta: np.ndarray, implicit_idx: np.ndarray,
+                               options: Optional[CommonOptions] = None):
+    """``__sparse_regression(ps::InternalDataDrivenProblem{<:ImplicitOptimizer}, X, Y)``
+    (``commonsolve.jl:58-114``) for the default single batch without a test split."""
+    Theta = np.asarray(Theta, dtype=np.float64)
+    implicit_idx = np.asarray(implicit_idx, dtype=bool)
+    cm = implicit_candidate_matrix(implicit_idx)
+    C = np.zeros((cm.shape[1], cm.shape[0]))
+    lams, iters = [], []
+    for i in range(cm.shape[1]):  # :83-93
+        idx = cm[:, i]
+        coeff, lam, it = alg(Theta[idx], None, options=options, necessary_idx=implicit_idx[idx, i])
+        C[i, idx] = coeff[0]
+        lams.append(lam)
+        iters.append(it)
+    trainerror = float(np.sum((C @ Theta) ** 2))  # :95
+    d = int(np.sum(np.abs(C) > 0.0))  # :107
+    return SparseRegressionResult(C, d, lams, iters, None, trainerror, 1)

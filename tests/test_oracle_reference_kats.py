@@ -155,3 +155,23 @@ def test_golden_fixtures_are_current(golden_dir):
     res = oracle.sparse_regression(oracle.STLSQ(g["thresholds"]), Th, g["Y"])
     np.testing.assert_array_equal(res.coefficients, g["coefficients"])
     np.testing.assert_allclose(Th @ Th.T, g["G"], rtol=0, atol=0)
+
+
+def test_implicit_optimizer_reference_kat():
+    """``lib/DataDrivenSparse/test/Core/sparse_linear_solve.jl:98-116`` (deterministic data, no RNG):
+    ``vec(rescoeff) ~ [0.25, 0, -1, 0.11, 0, -0.5]`` atol 5e-2 for STLSQ(0.1, 1.0), ADMM(), SR3()."""
+    t = np.arange(0.0, 10.0 + 1e-12, 0.1)
+    X = np.vstack([np.sin(0.5 * t + 0.1), np.cos(0.5 * t), np.sin(2.0 * t**2), np.cos(0.5 * t**2 - 0.1), np.exp(-t)])
+    Y = 0.5 * X[0] + 0.22 * X[3] - 2.0 * X[2]
+    X = np.vstack([X, Y])
+    for alg in (oracle.STLSQ(0.1, 1.0), oracle.ADMM(), oracle.SR3()):
+        c, _lam, _it = oracle.ImplicitOptimizer(alg)(X, Y[None], options=oracle.CommonOptions(maxiters=2000))
+        np.testing.assert_allclose(c.ravel(), [0.25, 0.0, -1.0, 0.11, 0.0, -0.5], atol=5e-2)
+
+
+def test_implicit_candidate_matrix():
+    """``commonsolve.jl:65-74``: a term is a candidate for an implicit variable when it depends on it or on no
+    other implicit variable."""
+    ii = np.array([[1, 0], [0, 1], [0, 0], [1, 1]], dtype=bool)
+    cm = oracle.implicit_candidate_matrix(ii)
+    np.testing.assert_array_equal(cm, [[True, False], [False, True], [True, True], [True, True]])
