@@ -317,9 +317,13 @@ def main():
     packed = torch.empty(ctx.gram_count(), dtype=torch.float64, device=dev)
     stage_live = {"gram_ms": [], "factor_ms": [], "sweep_ms": [], "rss_ms": [], "select_ms": [], "launches": []}
 
-    def step():
-        """One pass of the hot path with device-resident inputs."""
-        ctx.gram(packed.data_ptr())
+    def step(host=None):
+        """One pass of the hot path; inputs device-resident, or (host = pinned X, Y) uploaded inside the step
+        with the copies overlapped by the Gram kernels (ddb_upload_gram, the call ddb_solve_sparse makes)."""
+        if host is None:
+            ctx.gram(packed.data_ptr())
+        else:
+            ctx.upload_gram_raw(host[0].data_ptr(), host[1].data_ptr(), n_t, m_local, packed.data_ptr())
         t = ctx.timings()
         if world > 1:
             ddb200.dist.allreduce_sum(packed, group)
@@ -384,8 +388,7 @@ def main():
         d2h = (n_t * k + 4 * n_t) * 8
 
         def e2e_step():
-            ctx.upload_raw(X_h.data_ptr(), Y_h.data_ptr(), n_t, m_local)
-            return step()
+            return step(host=(X_h, Y_h))
 
         with torch.cuda.stream(ext):
             e2e_step()

@@ -117,6 +117,22 @@ class Context:
         self._imp_k = 0
         _lib.check(self._lib.ddb_gram(self._ctx, C.c_void_p(d_packed) if d_packed else None))
 
+    def upload_gram(self, X: np.ndarray, Y: np.ndarray, d_packed: Optional[int] = None):
+        """``ddb_upload_gram``: upload + Gram with the copies overlapped by the kernels (chunked)."""
+        X, Y = _f(X), _f(Y)
+        assert X.shape[0] == self.n and X.shape[1] == Y.shape[1]
+        self.n_t, self.m = Y.shape
+        self._imp_k = 0
+        _lib.check(self._lib.ddb_upload_gram(self._ctx, _lib.ptr(X), _lib.ptr(Y), self.n_t, self.m,
+                                             C.c_void_p(d_packed) if d_packed else None))
+
+    def upload_gram_raw(self, x_ptr: int, y_ptr: int, n_t: int, m: int, d_packed: Optional[int] = None):
+        """Same from raw host pointers (e.g. pinned torch tensors)."""
+        self.n_t, self.m = int(n_t), int(m)
+        self._imp_k = 0
+        _lib.check(self._lib.ddb_upload_gram(self._ctx, C.c_void_p(x_ptr), C.c_void_p(y_ptr), self.n_t, self.m,
+                                             C.c_void_p(d_packed) if d_packed else None))
+
     def gram_buffer(self) -> int:
         p = C.c_void_p()
         _lib.check(self._lib.ddb_gram_buffer(self._ctx, C.byref(p)))

@@ -113,8 +113,12 @@ int ddb_ctx_destroy(ddb_ctx* ctx) {
     ctx->imp_idx.release();
     ctx->d_partials.release();
     ctx->d_plan.release();
+    ctx->d_chunk_packed.release();
     for (auto& ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->chunk_ev)
+        if (ev) cudaEventDestroy(ev);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return DDB_OK;
@@ -179,6 +183,94 @@ int ddb_upload(ddb_ctx* ctx, const double* X, const double* Y, int n_t, int64_t 
     ctx->m = m;
     ctx->have_gram = false;
     ctx->imp_k = 0;
+    return DDB_OK;
+}
+
+__global__ void packed_add_kernel(double* __restrict__ acc, const double* __restrict__ part, int64_t count, int first) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) acc[i] = first ? part[i] : acc[i] + part[i];
+}
+
+// Host buffers -> device (kept resident, as ddb_upload) with the copies overlapped by the Gram stage: the
+// samples are cut into chunks, chunk c + 1 travels on a copy stream while the Gram kernels run on chunk c;
+// the per-chunk blocks are added in chunk order (deterministic).  With pinned host memory the transfer
+// disappears behind the tensor work except for the first chunk.
+int ddb_upload_gram(ddb_ctx* ctx, const double* X, const double* Y, int n_t, int64_t m, double* dPacked) {
+    CHECK_CTX(ctx);
+    DDB_TRY(check_data_args(ctx, X, Y, n_t, m, "ddb_upload_gram"));
+    if (ctx->k <= 0) {
+        set_error("ddb_upload_gram: no library installed");
+        return DDB_BAD_STATE;
+    }
+    const int n = ctx->n;
+    const size_t row_bytes = (size_t)(n + n_t) * sizeof(double);
+    // ~512 MB per chunk, at most 16 chunks, chunk boundaries on multiples of 64 samples
+    int nchunks = (int)std::min<int64_t>(16, std::max<int64_t>(1, (int64_t)((double)m * row_bytes / (512.0 * 1024 * 1024))));
+    int64_t chunk = ((m + nchunks - 1) / nchunks + 63) / 64 * 64;
+    nchunks = (int)((m + chunk - 1) / chunk);
+    if (nchunks <= 1) {
+        DDB_TRY(ddb_upload(ctx, X, Y, n_t, m));
+        return gram_run(ctx, dPacked);
+    }
+    const size_t xb = (size_t)n * m * sizeof(double), yb = (size_t)n_t * m * sizeof(double);
+    DDB_TRY(ctx->own_X.reserve(xb));
+    DDB_TRY(ctx->own_Y.reserve(yb));
+    if (!ctx->copy_stream) DDB_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    while ((int)ctx->chunk_ev.size() < nchunks + 1) {
+        cudaEvent_t e;
+        DDB_CUDA_TRY(cudaEventCreate(&e));
+        ctx->chunk_ev.push_back(e);
+    }
+    ctx->n_t = n_t;
+    ctx->have_gram = false;
+    ctx->imp_k = 0;
+    const int64_t count = (int64_t)ctx->k * ctx->k + (int64_t)ctx->k * n_t + n_t;
+    if (!dPacked) {
+        DDB_TRY(ctx->d_packed.reserve((size_t)count * sizeof(double)));
+        dPacked = ctx->d_packed.as<double>();
+    }
+    DDB_TRY(ctx->d_chunk_packed.reserve((size_t)count * sizeof(double)));
+    double* dX = ctx->own_X.as<double>();
+    double* dY = ctx->own_Y.as<double>();
+    // all copies are queued up front; event c fires when chunk c is resident
+    DDB_CUDA_TRY(cudaEventRecord(ctx->chunk_ev[nchunks], ctx->copy_stream));
+    for (int c = 0; c < nchunks; ++c) {
+        const int64_t s0 = c * chunk, mc = std::min(chunk, m - s0);
+        DDB_CUDA_TRY(cudaMemcpyAsync(dX + s0 * n, X + s0 * n, (size_t)mc * n * sizeof(double), cudaMemcpyHostToDevice,
+                                     ctx->copy_stream));
+        DDB_CUDA_TRY(cudaMemcpyAsync(dY + s0 * n_t, Y + s0 * n_t, (size_t)mc * n_t * sizeof(double), cudaMemcpyHostToDevice,
+                                     ctx->copy_stream));
+        DDB_CUDA_TRY(cudaEventRecord(ctx->chunk_ev[c], ctx->copy_stream));
+    }
+    double gram_ms = 0.0;
+    int launches = 0, status = DDB_OK;
+    for (int c = 0; c < nchunks && status == DDB_OK; ++c) {
+        const int64_t s0 = c * chunk, mc = std::min(chunk, m - s0);
+        DDB_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[c], 0));
+        ctx->dX = dX + s0 * n;
+        ctx->dY = dY + s0 * n_t;
+        ctx->m = mc;
+        status = gram_run(ctx, ctx->d_chunk_packed.as<double>());
+        if (status != DDB_OK) break;
+        gram_ms += ctx->timings.gram_ms;
+        launches += ctx->timings.gram_launches + 1;
+        packed_add_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(dPacked, ctx->d_chunk_packed.as<double>(),
+                                                                                    count, c == 0);
+    }
+    ctx->dX = dX;
+    ctx->dY = dY;
+    ctx->m = m;
+    cudaError_t ce = cudaStreamSynchronize(ctx->copy_stream);
+    if (status != DDB_OK) return status;
+    DDB_CUDA_TRY(ce);
+    DDB_CUDA_TRY(cudaGetLastError());
+    DDB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    float h2d = 0.f;
+    DDB_CUDA_TRY(cudaEventElapsedTime(&h2d, ctx->chunk_ev[nchunks], ctx->chunk_ev[nchunks - 1]));
+    ctx->timings.h2d_ms = h2d;
+    ctx->timings.gram_ms = gram_ms;
+    ctx->timings.gram_launches = launches;
+    ctx->have_gram = (dPacked == ctx->d_packed.as<double>());
     return DDB_OK;
 }
 

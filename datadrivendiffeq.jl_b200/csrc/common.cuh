@@ -82,6 +82,9 @@ struct ddb_ctx {
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {};
+    cudaStream_t copy_stream = nullptr;  // host->device copies of ddb_upload_gram (overlap with the Gram kernels)
+    std::vector<cudaEvent_t> chunk_ev;   // chunk c has landed
+    ddb::DevBuf d_chunk_packed;          // blocks of one chunk before they are added to the total
 
     // library
     int n = 0, k = 0, max_degree = 0;

@@ -1436,8 +1436,7 @@ int ddb_select(ddb_ctx* ctx, double* coef, double* lambda_opt, int32_t* iters, d
 int ddb_solve_sparse(ddb_ctx* ctx, const double* X, const double* Y, int n_t, int64_t m,
                      const ddb_sweep_params* params, const double* lambdas, int L, double* coef, double* lambda_opt,
                      int32_t* iters, double* rss, int32_t* dof, uint32_t* support_path) {
-    DDB_TRY(ddb_upload(ctx, X, Y, n_t, m));
-    DDB_TRY(ddb_gram(ctx, nullptr));
+    DDB_TRY(ddb_upload_gram(ctx, X, Y, n_t, m, nullptr));  // copies overlapped by the Gram kernels
     DDB_TRY(ddb_sweep(ctx, params, lambdas, L, m));
     DDB_TRY(ddb_rss(ctx, nullptr));
     return ddb_select(ctx, coef, lambda_opt, iters, rss, dof, support_path, nullptr, nullptr, nullptr);

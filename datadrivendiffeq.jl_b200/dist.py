@@ -53,14 +53,20 @@ def total_samples(m_local: int, group=None, device="cpu") -> int:
 
 
 def reduce_blocks_and_sweep(ctx, prm, lambdas: Sequence[float], m_total: int, group=None, paths: bool = False,
-                            tensor_device=None):
+                            tensor_device=None, host_data=None):
     """Steps after the data of this rank is bound to ``ctx``: Gram -> all-reduce -> sweep -> rss ->
     all-reduce -> select.  ``ctx`` is a :class:`~.backend.Context` (or a test double with the same
     methods that works on CPU tensors)."""
     torch, dist = _torch()
     dev = tensor_device if tensor_device is not None else f"cuda:{ctx.device}"
-    packed = torch.empty(ctx.gram_count(), dtype=torch.float64, device=dev)
-    ctx.gram(packed.data_ptr())
+    if host_data is not None:  # (X_local, Y_local) host arrays: upload overlapped with the Gram kernels
+        Xl, Yl = host_data
+        ctx.n_t = Yl.shape[0]
+        packed = torch.empty(ctx.k * ctx.k + ctx.k * ctx.n_t + ctx.n_t, dtype=torch.float64, device=dev)
+        ctx.upload_gram(Xl, Yl, packed.data_ptr())
+    else:
+        packed = torch.empty(ctx.gram_count(), dtype=torch.float64, device=dev)
+        ctx.gram(packed.data_ptr())
     allreduce_sum(packed, group)
     k, n_t = ctx.k, ctx.n_t
     base = packed.data_ptr()
@@ -76,6 +82,5 @@ def reduce_blocks_and_sweep(ctx, prm, lambdas: Sequence[float], m_total: int, gr
 
 def solve_sharded(ctx, X_local: np.ndarray, Y_local: np.ndarray, prm, lambdas, group=None, paths: bool = False):
     """Every rank passes its own shard (n x m_local, n_t x m_local); returns ``(SweepOutput, m_total)``."""
-    ctx.upload(X_local, Y_local)
     m_total = total_samples(X_local.shape[1], group, device=f"cuda:{ctx.device}")
-    return reduce_blocks_and_sweep(ctx, prm, lambdas, m_total, group, paths), m_total
+    return reduce_blocks_and_sweep(ctx, prm, lambdas, m_total, group, paths, host_data=(X_local, Y_local)), m_total

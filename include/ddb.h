@@ -141,6 +141,13 @@ int64_t ddb_gram_count(const ddb_ctx* ctx);
  * dPacked: device buffer of ddb_gram_count() doubles, or NULL to use the context's own buffer. */
 int ddb_gram(ddb_ctx* ctx, double* dPacked);
 
+/* ddb_upload + ddb_gram in one call with the host->device copies OVERLAPPED by the Gram kernels: the samples
+ * are cut into chunks (<= 16, ~512 MB each), chunk c + 1 travels on a copy stream while the kernels run on
+ * chunk c, and the per-chunk blocks are added in chunk order (deterministic).  The data stay resident as
+ * after ddb_upload.  Pass page-locked host buffers for a real overlap (pageable memory still works, the
+ * copies then serialise).  This is what ddb_solve_sparse uses. */
+int ddb_upload_gram(ddb_ctx* ctx, const double* X, const double* Y, int n_t, int64_t m, double* dPacked);
+
 /* Device pointer of the context's own packed buffer (for an all-reduce by the caller:
  * torch.distributed / NCCL over NVLink; one sum all-reduce of ddb_gram_count() doubles). */
 int ddb_gram_buffer(ddb_ctx* ctx, double** dPacked);

@@ -71,3 +71,33 @@ def test_ring_is_bit_reproducible_at_scale(ctx):
     assert np.max(np.abs(Ga - G0) / sc) < 1e-12
     assert np.max(np.abs(Ra - R0)) < 1e-12 * np.sqrt(np.max(np.diag(G0)) * np.max(y0))
     assert Ga[0, 0] == m  # constant term: a sum of ones is exact
+
+
+@pytest.mark.parametrize("n,deg,m", [(64, 2, 700_001), (3, 5, 300_000)])
+def test_upload_gram_chunked_overlap_matches_plain(ctx, n, deg, m):
+    """ddb_upload_gram (chunked upload overlapped by the Gram kernels, per-chunk blocks added in order)
+    against ddb_upload + ddb_gram on the same host data."""
+    import torch
+
+    rng = np.random.default_rng(5)
+    X = np.asfortranarray(rng.standard_normal((n, m)))
+    Y = np.asfortranarray(rng.standard_normal((n, m)))
+    ctx.set_library(oracle.polynomial_exponents(n, deg))
+    ctx.upload(X, Y)
+    ctx.gram()
+    G0, R0, y0 = ctx.gram_download()
+    # pinned host memory -> real overlap
+    Xp = torch.from_numpy(np.ascontiguousarray(X.T)).pin_memory()  # (m, n) row-major == n x m column-major
+    Yp = torch.from_numpy(np.ascontiguousarray(Y.T)).pin_memory()
+    ctx.upload_gram_raw(Xp.data_ptr(), Yp.data_ptr(), n, m)
+    G1, R1, y1 = ctx.gram_download()
+    sc = np.sqrt(np.outer(np.diag(G0), np.diag(G0)))
+    assert np.max(np.abs(G1 - G0) / sc) < 1e-13
+    assert np.max(np.abs(R1 - R0)) < 1e-13 * np.sqrt(np.max(np.diag(G0)) * np.max(y0))
+    np.testing.assert_allclose(y1, y0, rtol=1e-13)
+    Xd, Yd = ctx.download_data()  # the data stay resident, whole
+    np.testing.assert_array_equal(Xd, X)
+    np.testing.assert_array_equal(Yd, Y)
+    ctx.upload_gram_raw(Xp.data_ptr(), Yp.data_ptr(), n, m)  # deterministic
+    G2, _, _ = ctx.gram_download()
+    np.testing.assert_array_equal(G1, G2)
