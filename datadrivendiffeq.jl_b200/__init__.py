@@ -28,6 +28,11 @@ from .api import (  # noqa: F401
     construct_coefficients,
     get_fit_targets,
     monomial_basis,
+    sin_basis,
+    cos_basis,
+    chebyshev_basis,
+    fourier_basis,
+    concat_bases,
     polynomial_basis,
     solve,
 )

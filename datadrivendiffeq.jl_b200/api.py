@@ -66,6 +66,11 @@ class Basis:
     names: Optional[List[str]] = None
     implicits: int = 0  # trailing rows of `exponents` that are implicit variables (``Basis(...; implicits = du)``,
     #                     src/basis/type.jl:15-17); they are evaluated on the problem's DX
+    # Feature map: when set, row i of `exponents` is the power of FEATURE i = g(coef * x[source]) of the raw
+    # states, a sequence of (kind, source, coef) with kind in FEAT_* (``ddb_set_features``); covers the
+    # generators sin_basis / cos_basis / fourier_basis / chebyshev_basis and their products with monomials
+    features: Optional[List[tuple]] = None
+    n_raw: int = 0  # number of raw states when `features` is set
 
     def __post_init__(self):
         e = np.asarray(self.exponents)
@@ -84,6 +89,9 @@ class Basis:
 
     @property
     def n_states(self) -> int:
+        """States the PROBLEM must provide."""
+        if self.features is not None:
+            return int(self.n_raw)
         return self.exponents.shape[0] - int(self.implicits)
 
     @property
@@ -105,13 +113,91 @@ class Basis:
             parts = []
             for i in range(self.n_variables):
                 p = int(self.exponents[i, j])
-                nm = f"x{i + 1}" if i < self.n_states else f"dx{i - self.n_states + 1}"
+                if self.features is not None:
+                    kind, src, coef = self.features[i]
+                    fn = {FEAT_IDENTITY: "", FEAT_SIN: "sin", FEAT_COS: "cos", FEAT_EXP: "exp", FEAT_CHEBYSHEV: "cheb"}[kind]
+                    arg = f"x{src + 1}" if coef == 1.0 else f"{coef:g}*x{src + 1}"
+                    nm = f"{fn}({arg})" if fn else arg
+                else:
+                    nm = f"x{i + 1}" if i < self.n_states else f"dx{i - self.n_states + 1}"
                 if p == 1:
                     parts.append(nm)
                 elif p > 1:
                     parts.append(f"{nm}^{p}")
             out.append("*".join(parts) if parts else "1")
         return out
+
+
+FEAT_IDENTITY, FEAT_SIN, FEAT_COS, FEAT_EXP, FEAT_CHEBYSHEV = 0, 1, 2, 3, 4
+
+
+def _generator_basis(kind: str, n_states: int, coefficients) -> Basis:
+    """One library term per (coefficient, state), coefficient-major with the state varying fastest
+    (``_generateBasis!``, ``src/utils/basis_generators.jl:15-22``)."""
+    cs = list(range(1, int(coefficients) + 1)) if np.isscalar(coefficients) else list(coefficients)
+    feats = []
+    for t in cs:
+        for i in range(int(n_states)):
+            if kind == "sin":
+                feats.append((FEAT_SIN, i, float(t)))
+            elif kind == "cos":
+                feats.append((FEAT_COS, i, float(t)))
+            elif kind == "chebyshev":
+                feats.append((FEAT_CHEBYSHEV, i, float(t)))
+            else:  # fourier: iseven(t) ? cos(t x / 2) : sin(t x / 2)
+                if int(t) != t:
+                    raise ValueError("fourier_basis takes integer coefficients")
+                feats.append((FEAT_COS if int(t) % 2 == 0 else FEAT_SIN, i, float(t) / 2.0))
+    return Basis(np.eye(len(feats), dtype=np.uint8), features=feats, n_raw=int(n_states))
+
+
+def sin_basis(n_states: int, coefficients=1) -> Basis:
+    """``sin_basis(x, c)`` = ``sin.(t .* x)`` (``src/utils/basis_generators.jl:46-55``)."""
+    return _generator_basis("sin", n_states, coefficients)
+
+
+def cos_basis(n_states: int, coefficients=1) -> Basis:
+    """``cos_basis(x, c)`` = ``cos.(t .* x)`` (``basis_generators.jl:61-70``)."""
+    return _generator_basis("cos", n_states, coefficients)
+
+
+def chebyshev_basis(n_states: int, coefficients=1) -> Basis:
+    """``chebyshev_basis(x, c)`` = ``cos.(t .* acos.(x))`` (``basis_generators.jl:30-40``)."""
+    return _generator_basis("chebyshev", n_states, coefficients)
+
+
+def fourier_basis(n_states: int, coefficients=1) -> Basis:
+    """``fourier_basis(x, c)`` (``basis_generators.jl:76-82``)."""
+    return _generator_basis("fourier", n_states, coefficients)
+
+
+def concat_bases(bases: Sequence[Basis]) -> Basis:
+    """``Basis([b1; b2; ...], u)``: the union of term lists over the same raw states, duplicates removed
+    without reordering (``src/basis/type.jl:91-135``).  Monomial parts are expressed over identity features."""
+    n_raw = bases[0].n_states
+    feats: List[tuple] = [(FEAT_IDENTITY, i, 1.0) for i in range(n_raw)]
+    index = {f: i for i, f in enumerate(feats)}
+    cols = []
+    for b in bases:
+        if b.implicits:
+            raise ValueError("concat_bases: bases with implicit variables are not supported")
+        if b.n_states != n_raw:
+            raise ValueError("concat_bases: all bases must be over the same states")
+        bf = b.features if b.features is not None else [(FEAT_IDENTITY, i, 1.0) for i in range(n_raw)]
+        loc = []
+        for f in bf:
+            f = (int(f[0]), int(f[1]), float(f[2]))
+            if f not in index:
+                index[f] = len(feats)
+                feats.append(f)
+            loc.append(index[f])
+        for j in range(len(b)):
+            cols.append({loc[i]: int(b.exponents[i, j]) for i in range(b.exponents.shape[0]) if b.exponents[i, j]})
+    E = np.zeros((len(feats), len(cols)), dtype=np.uint8)
+    for j, c in enumerate(cols):
+        for i, p in c.items():
+            E[i, j] = p
+    return Basis(E, features=feats, n_raw=n_raw)
 
 
 def polynomial_basis(n_states: int, degree: int = 1) -> Basis:
@@ -467,7 +553,10 @@ def _solve_implicit(prob, basis, alg, options, X, Y):
     (``lib/DataDrivenSparse/src/commonsolve.jl:58-114``)."""
     if not basis.implicits:
         raise AssertionError("The provided `Basis` does not have implicit variables!")
+    if basis.features is not None:
+        raise ValueError("implicit libraries over a feature map are not supported")
     ctx = alg.context()
+    ctx.set_features(0, None)
     ctx.set_library(basis.exponents)
     inner = alg.inner.optimizer
     prm = _params_for(ctx, inner, options)
@@ -520,6 +609,7 @@ def solve(prob: DataDrivenProblem, basis: Basis, alg: B200Sparse, options: Optio
     if basis.implicits:
         raise ValueError("a Basis with implicit variables needs an ImplicitOptimizer (src/basis/type.jl:15)")
     ctx = alg.context()
+    ctx.set_features(basis.n_raw, basis.features)
     ctx.set_library(basis.exponents)
     prm = _params_for(ctx, alg.inner, options)
     lambdas = alg.inner.thresholds

@@ -79,10 +79,25 @@ class Context:
         self._imp_k = 0
         _lib.check(self._lib.ddb_set_library_monomial(self._ctx, self.n, self.k, _lib.ptr(e)))
 
+    def set_features(self, n_raw: int, features: Optional[Sequence] = None):
+        """``ddb_set_features``: the library's states become features ``g(coef * x[src])`` of ``n_raw`` raw
+        states; ``features`` = sequence of ``(kind, source, coef)``; ``None`` / empty removes the map.
+        Uploads and binds then take RAW states."""
+        self._imp_k = 0
+        if not features:
+            _lib.check(self._lib.ddb_set_features(self._ctx, 0, 0, None, None, None))
+            self.n_raw = 0
+            return
+        kind = np.ascontiguousarray([f[0] for f in features], dtype=np.int32)
+        src = np.ascontiguousarray([f[1] for f in features], dtype=np.int32)
+        coef = np.ascontiguousarray([f[2] for f in features], dtype=np.float64)
+        _lib.check(self._lib.ddb_set_features(self._ctx, int(n_raw), kind.size, _lib.ptr(kind), _lib.ptr(src), _lib.ptr(coef)))
+        self.n_raw = int(n_raw)
+
     # -- data -------------------------------------------------------------------------------
     def upload(self, X: np.ndarray, Y: np.ndarray):
         X, Y = _f(X), _f(Y)
-        assert X.shape[0] == self.n and X.shape[1] == Y.shape[1]
+        assert X.shape[0] == (getattr(self, "n_raw", 0) or self.n) and X.shape[1] == Y.shape[1]
         self.n_t, self.m = Y.shape
         _lib.check(self._lib.ddb_upload(self._ctx, _lib.ptr(X), _lib.ptr(Y), self.n_t, self.m))
 
@@ -120,7 +135,7 @@ class Context:
     def upload_gram(self, X: np.ndarray, Y: np.ndarray, d_packed: Optional[int] = None):
         """``ddb_upload_gram``: upload + Gram with the copies overlapped by the kernels (chunked)."""
         X, Y = _f(X), _f(Y)
-        assert X.shape[0] == self.n and X.shape[1] == Y.shape[1]
+        assert X.shape[0] == (getattr(self, "n_raw", 0) or self.n) and X.shape[1] == Y.shape[1]
         self.n_t, self.m = Y.shape
         self._imp_k = 0
         _lib.check(self._lib.ddb_upload_gram(self._ctx, _lib.ptr(X), _lib.ptr(Y), self.n_t, self.m,

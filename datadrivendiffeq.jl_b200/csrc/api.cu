@@ -114,6 +114,8 @@ int ddb_ctx_destroy(ddb_ctx* ctx) {
     ctx->d_partials.release();
     ctx->d_plan.release();
     ctx->d_chunk_packed.release();
+    ctx->d_feat.release();
+    ctx->raw_X.release();
     for (auto& ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->chunk_ev)
@@ -151,6 +153,75 @@ int ddb_set_library_monomial(ddb_ctx* ctx, int n, int k, const uint8_t* exps) {
     return DDB_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// feature map: phi_f(x) = g_f(c_f * x[src_f])
+// ---------------------------------------------------------------------------------------------
+struct FeatDesc {
+    int32_t kind, src;
+    double coef;
+};
+
+__global__ void feature_kernel(const double* __restrict__ raw, int n_raw, const FeatDesc* __restrict__ feat, int n,
+                               int64_t m, double* __restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m * n) return;
+    const int64_t s = t / n;
+    const int f = (int)(t % n);
+    const FeatDesc d = feat[f];
+    const double x = raw[s * n_raw + d.src];
+    double v;
+    switch (d.kind) {
+        case DDB_FEAT_SIN: v = sin(d.coef * x); break;
+        case DDB_FEAT_COS: v = cos(d.coef * x); break;
+        case DDB_FEAT_EXP: v = exp(d.coef * x); break;
+        case DDB_FEAT_CHEBYSHEV: v = cos(d.coef * acos(x)); break;
+        default: v = d.coef * x; break;
+    }
+    out[t] = v;
+}
+
+// expands raw states [s0, s0 + mc) (device pointer to the first of them) into ctx->own_X rows [s0, ...)
+static int expand_features(ddb_ctx* ctx, const double* d_raw, int64_t s0, int64_t mc, cudaStream_t st) {
+    const int64_t tot = mc * ctx->n;
+    feature_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(d_raw, ctx->n_raw, ctx->d_feat.as<FeatDesc>(), ctx->n, mc,
+                                                                  ctx->own_X.as<double>() + s0 * ctx->n);
+    DDB_CUDA_TRY(cudaGetLastError());
+    return DDB_OK;
+}
+
+int ddb_set_features(ddb_ctx* ctx, int n_raw, int n_feat, const int32_t* kind, const int32_t* source, const double* coef) {
+    CHECK_CTX(ctx);
+    if (n_feat == 0) {
+        ctx->n_raw = 0;
+        ctx->have_gram = false;
+        ctx->imp_k = 0;
+        return DDB_OK;
+    }
+    if (n_raw <= 0 || n_feat < 0 || !kind || !source || !coef) {
+        set_error("ddb_set_features: n_raw must be positive and kind, source, coef non-null");
+        return DDB_INVALID_ARG;
+    }
+    std::vector<FeatDesc> tab(n_feat);
+    for (int f = 0; f < n_feat; ++f) {
+        if (kind[f] < DDB_FEAT_IDENTITY || kind[f] > DDB_FEAT_CHEBYSHEV || source[f] < 0 || source[f] >= n_raw ||
+            !std::isfinite(coef[f])) {
+            set_error("ddb_set_features: feature %d has an invalid kind / source / coefficient", f);
+            return DDB_INVALID_ARG;
+        }
+        tab[f] = {kind[f], source[f], coef[f]};
+    }
+    DDB_TRY(ctx->d_feat.reserve(tab.size() * sizeof(FeatDesc)));
+    DDB_CUDA_TRY(cudaMemcpyAsync(ctx->d_feat.p, tab.data(), tab.size() * sizeof(FeatDesc), cudaMemcpyHostToDevice, ctx->stream));
+    DDB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    ctx->n_raw = n_raw;
+    ctx->have_gram = false;
+    ctx->imp_k = 0;
+    // the library must be (re)installed over n_feat states; data must be (re)bound
+    ctx->dX = ctx->dY = nullptr;
+    ctx->m = 0;
+    return DDB_OK;
+}
+
 static int check_data_args(ddb_ctx* ctx, const void* X, const void* Y, int n_t, int64_t m, const char* who) {
     if (ctx->n <= 0) {
         set_error("%s: install the library first (the number of states comes from it)", who);
@@ -159,6 +230,10 @@ static int check_data_args(ddb_ctx* ctx, const void* X, const void* Y, int n_t, 
     if (!X || !Y || n_t <= 0 || m <= 0) {
         set_error("%s: X, Y must be non-null and n_t, m positive", who);
         return DDB_INVALID_ARG;
+    }
+    if (ctx->n_raw > 0 && ctx->d_feat.bytes < (size_t)ctx->n * sizeof(FeatDesc)) {
+        set_error("%s: the installed library has %d states but the feature map defines fewer features", who, ctx->n);
+        return DDB_BAD_STATE;
     }
     return DDB_OK;
 }
@@ -170,7 +245,14 @@ int ddb_upload(ddb_ctx* ctx, const double* X, const double* Y, int n_t, int64_t 
     DDB_TRY(ctx->own_X.reserve(xb));
     DDB_TRY(ctx->own_Y.reserve(yb));
     DDB_CUDA_TRY(cudaEventRecord(ctx->ev[2], ctx->stream));
-    DDB_CUDA_TRY(cudaMemcpyAsync(ctx->own_X.p, X, xb, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->n_raw > 0) {  // raw states -> staging -> features
+        const size_t rb = (size_t)ctx->n_raw * m * sizeof(double);
+        DDB_TRY(ctx->raw_X.reserve(rb));
+        DDB_CUDA_TRY(cudaMemcpyAsync(ctx->raw_X.p, X, rb, cudaMemcpyHostToDevice, ctx->stream));
+        DDB_TRY(expand_features(ctx, ctx->raw_X.as<double>(), 0, m, ctx->stream));
+    } else {
+        DDB_CUDA_TRY(cudaMemcpyAsync(ctx->own_X.p, X, xb, cudaMemcpyHostToDevice, ctx->stream));
+    }
     DDB_CUDA_TRY(cudaMemcpyAsync(ctx->own_Y.p, Y, yb, cudaMemcpyHostToDevice, ctx->stream));
     DDB_CUDA_TRY(cudaEventRecord(ctx->ev[3], ctx->stream));
     DDB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -203,7 +285,8 @@ int ddb_upload_gram(ddb_ctx* ctx, const double* X, const double* Y, int n_t, int
         return DDB_BAD_STATE;
     }
     const int n = ctx->n;
-    const size_t row_bytes = (size_t)(n + n_t) * sizeof(double);
+    const int n_in = ctx->n_raw > 0 ? ctx->n_raw : n;  // states per sample in the caller's buffer
+    const size_t row_bytes = (size_t)(n_in + n_t) * sizeof(double);
     // ~512 MB per chunk, at most 16 chunks, chunk boundaries on multiples of 64 samples
     int nchunks = (int)std::min<int64_t>(16, std::max<int64_t>(1, (int64_t)((double)m * row_bytes / (512.0 * 1024 * 1024))));
     int64_t chunk = ((m + nchunks - 1) / nchunks + 63) / 64 * 64;
@@ -232,12 +315,17 @@ int ddb_upload_gram(ddb_ctx* ctx, const double* X, const double* Y, int n_t, int
     DDB_TRY(ctx->d_chunk_packed.reserve((size_t)count * sizeof(double)));
     double* dX = ctx->own_X.as<double>();
     double* dY = ctx->own_Y.as<double>();
+    double* dIn = dX;  // where the copies land: the state buffer itself, or the raw staging of a feature map
+    if (ctx->n_raw > 0) {
+        DDB_TRY(ctx->raw_X.reserve((size_t)n_in * m * sizeof(double)));
+        dIn = ctx->raw_X.as<double>();
+    }
     // all copies are queued up front; event c fires when chunk c is resident
     DDB_CUDA_TRY(cudaEventRecord(ctx->chunk_ev[nchunks], ctx->copy_stream));
     for (int c = 0; c < nchunks; ++c) {
         const int64_t s0 = c * chunk, mc = std::min(chunk, m - s0);
-        DDB_CUDA_TRY(cudaMemcpyAsync(dX + s0 * n, X + s0 * n, (size_t)mc * n * sizeof(double), cudaMemcpyHostToDevice,
-                                     ctx->copy_stream));
+        DDB_CUDA_TRY(cudaMemcpyAsync(dIn + s0 * n_in, X + s0 * n_in, (size_t)mc * n_in * sizeof(double),
+                                     cudaMemcpyHostToDevice, ctx->copy_stream));
         DDB_CUDA_TRY(cudaMemcpyAsync(dY + s0 * n_t, Y + s0 * n_t, (size_t)mc * n_t * sizeof(double), cudaMemcpyHostToDevice,
                                      ctx->copy_stream));
         DDB_CUDA_TRY(cudaEventRecord(ctx->chunk_ev[c], ctx->copy_stream));
@@ -247,6 +335,8 @@ int ddb_upload_gram(ddb_ctx* ctx, const double* X, const double* Y, int n_t, int
     for (int c = 0; c < nchunks && status == DDB_OK; ++c) {
         const int64_t s0 = c * chunk, mc = std::min(chunk, m - s0);
         DDB_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[c], 0));
+        if (ctx->n_raw > 0) status = expand_features(ctx, dIn + s0 * n_in, s0, mc, ctx->stream);
+        if (status != DDB_OK) break;
         ctx->dX = dX + s0 * n;
         ctx->dY = dY + s0 * n_t;
         ctx->m = mc;
@@ -277,6 +367,12 @@ int ddb_upload_gram(ddb_ctx* ctx, const double* X, const double* Y, int n_t, int
 int ddb_bind_device(ddb_ctx* ctx, const double* dX, const double* dY, int n_t, int64_t m) {
     CHECK_CTX(ctx);
     DDB_TRY(check_data_args(ctx, dX, dY, n_t, m, "ddb_bind_device"));
+    if (ctx->n_raw > 0) {  // dX holds raw states: expand once into the context's own buffer
+        DDB_TRY(ctx->own_X.reserve((size_t)ctx->n * m * sizeof(double)));
+        DDB_TRY(expand_features(ctx, dX, 0, m, ctx->stream));
+        DDB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        dX = ctx->own_X.as<double>();
+    }
     ctx->dX = dX;
     ctx->dY = dY;
     ctx->n_t = n_t;

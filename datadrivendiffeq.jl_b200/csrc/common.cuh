@@ -92,6 +92,12 @@ struct ddb_ctx {
     ddb::DevBuf d_factors;               // (k + n_t) x kMaxFactors uint16, built when n_t is known
     int factors_nt = -1;
 
+    // feature map (ddb_set_features): the library's "states" are n features g_f(c_f * x[src_f]) of n_raw raw
+    // states; uploads / binds take RAW states and a small kernel expands them once (n x m doubles, resident)
+    int n_raw = 0;                       // 0 = no feature map (the states are used as they are)
+    ddb::DevBuf d_feat;                  // n x {int kind, int src, double coef}
+    ddb::DevBuf raw_X;                   // staging of the raw states for host uploads
+
     // data
     const double* dX = nullptr;
     const double* dY = nullptr;

@@ -104,6 +104,10 @@ int generate_run(ddb_ctx* ctx, int system_id, int n_states, int64_t m, int64_t f
         set_error("ddb_generate: need 3 <= n <= 1024, m > 0, first_sample >= 0");
         return DDB_INVALID_ARG;
     }
+    if (ctx->n_raw > 0) {
+        set_error("ddb_generate: the synthetic systems are generated as states; remove the feature map first");
+        return DDB_BAD_STATE;
+    }
     if (ctx->n != 0 && ctx->n != n) {
         set_error("ddb_generate: system has %d states but the installed library has %d", n, ctx->n);
         return DDB_INVALID_ARG;

@@ -126,6 +126,24 @@ int ddb_bind_device(ddb_ctx* ctx, const double* dX, const double* dY, int n_t, i
 int ddb_generate(ddb_ctx* ctx, int system_id, int n_states, int64_t m, int64_t first_sample,
                  uint64_t seed, double noise_std);
 
+/* ---- feature map: libraries of sin / cos / exp / Chebyshev terms and their products with monomials ----
+ * Replaces the non-polynomial generators `sin_basis`, `cos_basis`, `fourier_basis`, `chebyshev_basis`
+ * (src/utils/basis_generators.jl:30-82) and libraries mixing them with polynomials (e.g.
+ * `[polynomial_basis(u, 5); sin.(u); cos.(u)]`, lib/DataDrivenSparse/test/Core/pendulum.jl:13).
+ * Feature f is  g_f(coef[f] * x[source[f]])  of the n_raw raw states; the monomial library
+ * (ddb_set_library_monomial with n = n_feat) is then a table of exponents over the FEATURES.  After this call
+ * ddb_upload / ddb_upload_gram / ddb_bind_device take RAW states (n_raw x m) and expand them once on the
+ * device (n_feat x m doubles stay resident; Theta itself is still never built).  n_feat = 0 removes the map.
+ * Call before binding data. */
+typedef enum ddb_feature_kind {
+    DDB_FEAT_IDENTITY = 0,  /* coef * x            */
+    DDB_FEAT_SIN = 1,       /* sin(coef * x)       sin_basis, odd fourier_basis terms (coef = t/2) */
+    DDB_FEAT_COS = 2,       /* cos(coef * x)       cos_basis, even fourier_basis terms             */
+    DDB_FEAT_EXP = 3,       /* exp(coef * x)                                                        */
+    DDB_FEAT_CHEBYSHEV = 4  /* cos(coef * acos(x)) chebyshev_basis                                  */
+} ddb_feature_kind;
+int ddb_set_features(ddb_ctx* ctx, int n_raw, int n_feat, const int32_t* kind, const int32_t* source, const double* coef);
+
 /* Copy the bound device data back to the host (for tests and the end-to-end bench). */
 int ddb_download_data(ddb_ctx* ctx, double* X, double* Y);
 

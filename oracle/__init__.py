@@ -33,6 +33,8 @@ from .basis import (  # noqa: F401
     polynomial_exponents,
     monomial_exponents,
     evaluate_library,
+    generator_features,
+    evaluate_features,
 )
 from .sparse import (  # noqa: F401
     STLSQ,

@@ -78,3 +78,53 @@ def evaluate_library(exps: np.ndarray, X: np.ndarray) -> np.ndarray:
             elif e > 1:
                 row *= np.power(X[i], e)
     return theta
+
+
+# ----------------------------------------------------------------------------------------------
+# non-polynomial generators (src/utils/basis_generators.jl:30-82) as FEATURES of the states
+# ----------------------------------------------------------------------------------------------
+FEAT_IDENTITY, FEAT_SIN, FEAT_COS, FEAT_EXP, FEAT_CHEBYSHEV = 0, 1, 2, 3, 4
+
+
+def _coefficients(c):
+    """``f(x, terms::Int) = f(x, 1:terms)`` (``basis_generators.jl:40,55,70,82``)."""
+    return list(range(1, int(c) + 1)) if np.isscalar(c) else [v for v in c]
+
+
+def generator_features(kind: str, n_variables: int, coefficients) -> list:
+    """Feature list ``(kind, source, coef)`` of ``sin_basis`` / ``cos_basis`` / ``chebyshev_basis`` /
+    ``fourier_basis`` in the reference's order: coefficient-major, variable fastest
+    (``_generateBasis!``, ``basis_generators.jl:15-22``)."""
+    out = []
+    for t in _coefficients(coefficients):
+        for i in range(n_variables):
+            if kind == "sin":  # sin.(t .* x), :48
+                out.append((FEAT_SIN, i, float(t)))
+            elif kind == "cos":  # cos.(t .* x), :63
+                out.append((FEAT_COS, i, float(t)))
+            elif kind == "chebyshev":  # cos.(t .* acos.(x)), :33
+                out.append((FEAT_CHEBYSHEV, i, float(t)))
+            elif kind == "fourier":  # iseven(t) ? cos.(t .* x ./ 2) : sin.(t .* x ./ 2), :78
+                out.append((FEAT_COS if int(t) % 2 == 0 else FEAT_SIN, i, float(t) / 2.0))
+            else:
+                raise ValueError(kind)
+    return out
+
+
+def evaluate_features(features, X: np.ndarray) -> np.ndarray:
+    """Feature matrix (n_feat x m) of raw states X (n_raw x m)."""
+    X = np.asarray(X, dtype=np.float64)
+    out = np.empty((len(features), X.shape[1]))
+    for f, (kind, src, coef) in enumerate(features):
+        x = X[src]
+        if kind == FEAT_SIN:
+            out[f] = np.sin(coef * x)
+        elif kind == FEAT_COS:
+            out[f] = np.cos(coef * x)
+        elif kind == FEAT_EXP:
+            out[f] = np.exp(coef * x)
+        elif kind == FEAT_CHEBYSHEV:
+            out[f] = np.cos(coef * np.arccos(x))
+        else:
+            out[f] = coef * x
+    return out

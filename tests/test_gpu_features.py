@@ -1,0 +1,99 @@
+"""GPU parity of libraries with non-polynomial generators (``sin_basis``, ``cos_basis``,
+``fourier_basis``, ``chebyshev_basis`` of ``src/utils/basis_generators.jl:30-82`` and their mixtures with
+polynomials) through the feature map of the C ABI (``ddb_set_features``)."""
+import numpy as np
+import pytest
+
+import ddb200
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = ddb200.Context(0)
+    yield c
+    c.close()
+
+
+def _theta(basis, X):
+    F = oracle.evaluate_features(basis.features, X) if basis.features is not None else X
+    return oracle.evaluate_library(basis.exponents, F)
+
+
+def _pendulum_data(m=401, dt=0.05):
+    """The reference's pendulum test system (``lib/DataDrivenSparse/test/Core/pendulum.jl:15-25``), RK4."""
+
+    def f(u):
+        return np.array([u[1], -9.81 * np.sin(u[0]) - 0.1 * u[1] ** 3 - 0.2 * np.cos(u[0])])
+
+    u = np.array([0.99 * np.pi, -1.0])
+    X = np.empty((2, m))
+    h = dt / 20
+    for s in range(m):
+        X[:, s] = u
+        for _ in range(20):
+            k1 = f(u); k2 = f(u + 0.5 * h * k1); k3 = f(u + 0.5 * h * k2); k4 = f(u + h * k3)
+            u = u + h / 6 * (k1 + 2 * k2 + 2 * k3 + k4)
+    DX = np.stack([f(X[:, s]) for s in range(m)], axis=1)
+    return X, DX
+
+
+@pytest.mark.parametrize("make", [
+    lambda: ddb200.sin_basis(3, 2), lambda: ddb200.cos_basis(3, [1, 3]), lambda: ddb200.fourier_basis(2, 4),
+    lambda: ddb200.chebyshev_basis(2, 3),
+    lambda: ddb200.concat_bases([ddb200.polynomial_basis(2, 5), ddb200.sin_basis(2, 1), ddb200.cos_basis(2, 1)]),
+])
+def test_gram_of_generator_libraries(ctx, make):
+    basis = make()
+    n, m = basis.n_states, 3001
+    rng = np.random.default_rng(len(basis))
+    X = rng.uniform(-0.95, 0.95, size=(n, m))
+    Y = rng.standard_normal((n, m))
+    ctx.set_features(basis.n_raw, basis.features)
+    ctx.set_library(basis.exponents)
+    ctx.upload(X, Y)
+    ctx.gram()
+    G, R, yy = ctx.gram_download()
+    Th = _theta(basis, X)
+    G0, R0 = Th @ Th.T, Th @ Y.T
+    sc = np.sqrt(np.outer(np.diag(G0), np.diag(G0)))
+    assert np.max(np.abs(G - G0) / sc) < 1e-13
+    assert np.max(np.abs(R - R0)) < 1e-13 * np.sqrt(np.max(np.diag(G0)) * np.max((Y * Y).sum(1)))
+    ctx.set_features(0, None)
+
+
+@pytest.mark.parametrize("alg_name", ["STLSQ", "STLSQ-ridge", "ADMM", "SR3"])
+def test_pendulum_library_solve_matches_oracle(ctx, alg_name):
+    """``Basis([polynomial_basis(u, 5); sin.(u); cos.(u)], u)`` on the pendulum (pendulum.jl:13-46)."""
+    X, DX = _pendulum_data()
+    basis = ddb200.concat_bases([ddb200.polynomial_basis(2, 5), ddb200.sin_basis(2, 1), ddb200.cos_basis(2, 1)])
+    # the reference's grid 1e-2:1e-2:1e-1 scaled by 0.97: the true coefficient -0.1 of x2^3 must not sit exactly
+    # on a threshold (a 1-ulp knife edge decides the support there, in the reference as well)
+    lams = 0.97 * np.arange(1e-2, 1e-1 + 1e-9, 1e-2)
+    mk = {"STLSQ": lambda m: m.STLSQ(lams), "STLSQ-ridge": lambda m: m.STLSQ(lams, 1e-4),
+          "ADMM": lambda m: m.ADMM(lams), "SR3": lambda m: m.SR3(lams)}[alg_name]
+    alg = ddb200.B200Sparse(mk(ddb200))
+    alg._ctx = ctx
+    sol = ddb200.solve(ddb200.ContinuousDataDrivenProblem(X, DX=DX), basis, alg, paths=True)
+    Th = _theta(basis, X)
+    traces = []
+    ref = oracle.sparse_regression(mk(oracle), Th, DX, traces=traces)
+    C = sol.results[0].coefficients
+    np.testing.assert_array_equal(C != 0.0, ref.coefficients != 0.0)
+    tol = 1e-7 if alg_name in ("ADMM", "SR3") else 1e-8
+    np.testing.assert_allclose(C, ref.coefficients, rtol=tol, atol=1e-11)
+    for i, tr in enumerate(traces):  # identical support at every threshold
+        np.testing.assert_array_equal(sol.paths.support_path[i], np.asarray(tr.support_path))
+    if alg_name.startswith("STLSQ"):  # the reference's own assertions (pendulum.jl:36-44)
+        assert 2 <= sol.results[0].dof <= 6
+    ctx.set_features(0, None)
+
+
+def test_feature_map_errors(ctx):
+    with pytest.raises(ddb200._lib.DDBError):
+        ctx.set_features(2, [(9, 0, 1.0)])  # unknown kind
+    with pytest.raises(ddb200._lib.DDBError):
+        ctx.set_features(2, [(1, 2, 1.0)])  # source out of range
+    ctx.set_features(0, None)

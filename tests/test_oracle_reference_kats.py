@@ -175,3 +175,27 @@ def test_implicit_candidate_matrix():
     ii = np.array([[1, 0], [0, 1], [0, 0], [1, 1]], dtype=bool)
     cm = oracle.implicit_candidate_matrix(ii)
     np.testing.assert_array_equal(cm, [[True, False], [False, True], [True, True], [True, True]])
+
+
+def test_generator_forms_match_the_reference():
+    """``test/Core/generators.jl:7-11,20-23``: sin_basis(u,1) = sin.(1 .* u); cos_basis(u,2) = [cos.(u); cos.(2u)];
+    chebyshev_basis(u,1) = cos.(acos.(u)); fourier_basis(u,1:2) = [sin.(u ./ 2); cos.(2u ./ 2)]."""
+    rng = np.random.default_rng(0)
+    U = rng.uniform(-0.9, 0.9, size=(3, 17))
+    ev = lambda kind, c: oracle.evaluate_features(oracle.generator_features(kind, 3, c), U)
+    np.testing.assert_array_equal(ev("sin", 1), np.sin(1 * U))
+    np.testing.assert_array_equal(ev("cos", 2), np.vstack([np.cos(1 * U), np.cos(2 * U)]))
+    np.testing.assert_array_equal(ev("chebyshev", 1), np.cos(1 * np.arccos(U)))
+    np.testing.assert_array_equal(ev("fourier", 1), np.sin(1 * U / 2))
+    np.testing.assert_array_equal(ev("sin", [1, 2]), np.vstack([np.sin(i * U) for i in (1, 2)]))
+    np.testing.assert_array_equal(ev("cos", range(1, 6)), np.vstack([np.cos(i * U) for i in range(1, 6)]))
+    np.testing.assert_array_equal(ev("chebyshev", [1, 2]), np.vstack([np.cos(i * np.arccos(U)) for i in (1, 2)]))
+    np.testing.assert_array_equal(ev("fourier", [1, 2]), np.vstack([np.sin(1 * U / 2), np.cos(2 * U / 2)]))
+    # the host mirror builds the same feature lists
+    import ddb200
+
+    for kind, fn in (("sin", ddb200.sin_basis), ("cos", ddb200.cos_basis), ("chebyshev", ddb200.chebyshev_basis),
+                     ("fourier", ddb200.fourier_basis)):
+        assert fn(3, 2).features == oracle.generator_features(kind, 3, 2)
+    b = ddb200.concat_bases([ddb200.polynomial_basis(2, 5), ddb200.sin_basis(2, 1), ddb200.cos_basis(2, 1)])
+    assert len(b) == 25 and b.n_states == 2 and b.term_strings()[-4:] == ["sin(x1)", "sin(x2)", "cos(x1)", "cos(x2)"]
