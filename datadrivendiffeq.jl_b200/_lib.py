@@ -85,6 +85,10 @@ PROTOTYPES = {
     "ddb_download_data": (C.c_int, [_P, _P, _P]),
     "ddb_gram_count": (C.c_int64, [_P]),
     "ddb_gram": (C.c_int, [_P, _P]),
+    "ddb_set_sample_range": (C.c_int, [_P, C.c_int64, C.c_int64]),
+    "ddb_permute_samples": (C.c_int, [_P, _P]),
+    "ddb_gram_scale_terms": (C.c_int, [_P, _P]),
+    "ddb_residual": (C.c_int, [_P, _P, _P]),
     "ddb_set_features": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P]),
     "ddb_upload_gram": (C.c_int, [_P, _P, _P, C.c_int, C.c_int64, _P]),
     "ddb_gram_buffer": (C.c_int, [_P, C.POINTER(_P)]),

@@ -283,9 +283,12 @@ class DataDrivenCommonOptions:
     progress: bool = False
     verbose: bool = False
     denoise: bool = False
-    normalize: Optional[str] = None  # DataNormalization{Nothing}
-    split: float = 1.0  # DataProcessing.split
-    batchsize: int = 0  # DataProcessing.batchsize
+    normalize: Optional[str] = None  # None = DataNormalization{Nothing}; "ZScoreTransform" (data_processing.jl:75-80)
+    split: float = 1.0  # DataProcessing.split: (rough) fraction of training samples (data_processing.jl:17)
+    batchsize: int = 0  # DataProcessing.batchsize: 0 = one batch
+    partial: bool = True  # DataProcessing.partial: keep a last, smaller batch
+    shuffle_seed: Optional[int] = 0  # seed of the DataLoader's shuffle (its rng field); None = keep the order
+    perm: Optional[np.ndarray] = None  # explicit order of the training samples (overrides shuffle_seed)
     roundingmode: str = "RoundToZero"
     digits: int = 10
     selector: str = "bic"
@@ -469,10 +472,9 @@ def get_fit_targets(alg: B200Sparse, prob: DataDrivenProblem, basis: Basis):
 def _check_options(options: DataDrivenCommonOptions):
     if options.denoise:
         raise ValueError("B200Sparse: denoise=true (optimal shrinkage of Theta) is not supported: Theta is never materialised")
-    if options.normalize is not None:
-        raise ValueError("B200Sparse: only DataNormalization{Nothing} is supported (the Gram path equilibrates internally)")
-    if options.split != 1.0 or options.batchsize > 0:
-        raise ValueError("B200Sparse: train/test split and mini-batches are not supported")
+    if options.normalize not in (None, "ZScoreTransform"):
+        raise ValueError("B200Sparse: normalize must be None (DataNormalization{Nothing}) or 'ZScoreTransform'; the "
+                         "reference's UnitRangeTransform shifts Theta and is not supported")
     if options.roundingmode != "RoundToZero":
         raise ValueError("B200Sparse: only RoundToZero post-processing is supported")
     if options.selector not in ("bic", "aic", "aicc", "rss"):
@@ -594,6 +596,99 @@ def _solve_implicit(prob, basis, alg, options, X, Y):
                               nobs=int(Y.shape[0] * m_total), retcode=1, timings=ctx.timings())
 
 
+def _needs_processing(options: DataDrivenCommonOptions) -> bool:
+    return options.normalize is not None or options.split != 1.0 or options.batchsize > 0
+
+
+def zscore_scales(G: np.ndarray, sums: np.ndarray, m: int) -> np.ndarray:
+    """Scales of ``fit(ZScoreTransform, Theta, dims = 2, center = false)`` (``data_processing.jl:75-80``) from
+    the Gram blocks: sigma_j = sqrt((sum theta_j^2 - (sum theta_j)^2 / m) / (m - 1)), constants scaled with 1."""
+    var = (np.diag(G) - sums * sums / m) / (m - 1)
+    sig = np.sqrt(np.maximum(var, 0.0))
+    # a constant row has zero spread up to the rounding of the two sums
+    sig[var <= 1e-14 * np.maximum(np.diag(G) / m, 1e-300)] = 1.0
+    return sig
+
+
+def _solve_processed(prob, basis, alg, options, X, Y, paths=False):
+    """``init`` + ``solve!`` with the reference's pre-processing options (``src/commonsolve.jl:92-139``,
+    ``lib/DataDrivenSparse/src/commonsolve.jl:1-24``): ZScore normalisation fitted on ALL samples, train/test
+    split, shuffled mini-batches; every batch is regressed separately and the result with the smallest test
+    (or train) error wins.  Train part, test part and batches are views of the resident data."""
+    if alg.group is not None:
+        raise ValueError("B200Sparse: normalisation / split / batches are not supported on the sharded path yet")
+    ctx = alg.context()
+    ctx.set_features(basis.n_raw, basis.features)
+    ctx.set_library(basis.exponents)
+    prm = _params_for(ctx, alg.inner, options)
+    lambdas = alg.inner.thresholds
+    m = X.shape[1]
+    k, n_t = len(basis), Y.shape[0]
+    split = min(max(float(options.split), 0.0), 1.0)
+    m_train = int(round(split * m))  # MLUtils.splitobs(at = split)
+    if m_train <= 0:
+        raise ValueError("B200Sparse: the training split is empty")
+    ctx.upload(X, Y)
+    sigma = None
+    if options.normalize == "ZScoreTransform":
+        ctx.gram()  # over ALL samples: the transform is fitted before the split (commonsolve.jl:128-130)
+        G, _R, _yy = ctx.gram_download()
+        const = np.nonzero(basis.exponents.sum(axis=0) == 0)[0]
+        if const.size:
+            sums = G[const[0]].copy()  # row of the constant term = sum over samples of every term
+        else:  # one more pass with a row of ones as the target: R[:, 0] = sum theta
+            ctx.upload(X, np.ones((1, m)))
+            ctx.gram()
+            sums = ctx.gram_download()[1][:, 0].copy()
+            ctx.upload(X, Y)
+        sigma = zscore_scales(G, sums, m)
+    # order of the training samples: shuffled by the DataLoader (data_processing.jl:38)
+    batchsize = m_train if options.batchsize <= 0 else int(options.batchsize)
+    perm = None
+    if options.perm is not None:
+        perm = np.asarray(options.perm, dtype=np.int64)
+    elif options.shuffle_seed is not None and batchsize < m_train:
+        perm = np.random.default_rng(options.shuffle_seed).permutation(m_train)
+    if perm is not None:
+        if perm.size != m_train:
+            raise ValueError("perm must order the training samples")
+        ctx.permute_samples(np.concatenate([perm, np.arange(m_train, m)]))
+    starts = list(range(0, m_train, batchsize))
+    if not options.partial and m_train % batchsize:
+        starts = starts[:-1]
+    results, outs = [], []
+    for b0 in starts:
+        b1 = min(b0 + batchsize, m_train)
+        ctx.set_sample_range(b0, b1)
+        ctx.gram()
+        if sigma is not None:
+            ctx.gram_scale_terms(sigma)
+        ctx.sweep(prm, lambdas, b1 - b0)
+        ctx.rss()
+        out = ctx.select(paths=paths)
+        Cs = out.coefficients  # in the scaled space when sigma is set
+        Cu = Cs / sigma[None, :] if sigma is not None else Cs
+        testerror = None
+        if m_train < m:
+            ctx.set_sample_range(m_train, m)
+            testerror = float(np.sum(ctx.residual(Cu)))
+        results.append(SparseRegressionResult(coefficients=Cs, dof=int(np.sum(np.abs(Cs) > 0.0)), lambda_=out.lambda_opt,
+                                              iterations=out.iterations, testerror=testerror,
+                                              trainerror=float(np.sum(out.rss)), retcode=1 if not np.any(out.flags & 1) else 2))
+        outs.append(out)
+    ctx.set_sample_range(0, -1)
+    order = sorted(range(len(results)), key=lambda i: results[i].testerror if results[i].testerror is not None
+                   else results[i].trainerror)  # sort!(results, by = l2error), stable
+    results = [results[i] for i in order]
+    best = results[0]
+    C = best.coefficients / sigma[None, :] if sigma is not None else best.coefficients  # apply_transform (commonsolve.jl:19-21)
+    Cr = construct_coefficients(C, options.digits)
+    rss_all = float(np.sum(ctx.residual(Cr)))  # what DataDrivenSolution recomputes on all data (src/solution.jl:37-56)
+    return DataDrivenSolution(basis=basis, coefficients=Cr, results=results, rss=rss_all, dof=int(np.sum(Cr != 0.0)),
+                              nobs=int(Y.size), retcode=best.retcode, timings=ctx.timings(),
+                              paths=outs[order[0]] if paths else None)
+
+
 def solve(prob: DataDrivenProblem, basis: Basis, alg: B200Sparse, options: Optional[DataDrivenCommonOptions] = None,
           paths: bool = False) -> DataDrivenSolution:
     """``solve(prob, basis, alg; options)`` = ``solve!(init(...))`` for the B200 backend.
@@ -605,9 +700,13 @@ def solve(prob: DataDrivenProblem, basis: Basis, alg: B200Sparse, options: Optio
     _check_options(options)
     X, Y = get_fit_targets(alg, prob, basis)
     if isinstance(alg.inner, ImplicitOptimizer):
+        if _needs_processing(options):
+            raise ValueError("B200Sparse: normalisation / split / batches are not supported with an ImplicitOptimizer")
         return _solve_implicit(prob, basis, alg, options, X, Y)
     if basis.implicits:
         raise ValueError("a Basis with implicit variables needs an ImplicitOptimizer (src/basis/type.jl:15)")
+    if _needs_processing(options):
+        return _solve_processed(prob, basis, alg, options, X, Y, paths)
     ctx = alg.context()
     ctx.set_features(basis.n_raw, basis.features)
     ctx.set_library(basis.exponents)

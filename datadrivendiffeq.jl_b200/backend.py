@@ -124,6 +124,32 @@ class Context:
         _lib.check(self._lib.ddb_download_data(self._ctx, _lib.ptr(X), _lib.ptr(Y)))
         return X, Y
 
+    # -- sample views / permutation / residuals ---------------------------------------------
+    def set_sample_range(self, first: int = 0, last: int = -1):
+        """``ddb_set_sample_range``: Gram / rss / residual see samples [first, last) only (-1 = to the end)."""
+        self._imp_k = 0
+        _lib.check(self._lib.ddb_set_sample_range(self._ctx, int(first), int(last)))
+
+    def permute_samples(self, perm: Sequence[int]):
+        """``ddb_permute_samples``: new sample s = old sample perm[s]."""
+        p = np.ascontiguousarray(perm, dtype=np.int64)
+        self._imp_k = 0
+        _lib.check(self._lib.ddb_permute_samples(self._ctx, _lib.ptr(p)))
+
+    def gram_scale_terms(self, scale: np.ndarray):
+        """``ddb_gram_scale_terms``: the sweep then runs on Theta_j / scale_j (ZScore normalisation)."""
+        s = np.ascontiguousarray(scale, dtype=np.float64)
+        assert s.size == self.k
+        _lib.check(self._lib.ddb_gram_scale_terms(self._ctx, _lib.ptr(s)))
+
+    def residual(self, coef: np.ndarray) -> np.ndarray:
+        """``ddb_residual``: rss per target of an arbitrary coefficient matrix (n_t x k) over the current view."""
+        c = np.asfortranarray(coef, dtype=np.float64)
+        assert c.shape == (self.n_t, self.k)
+        out = np.zeros(self.n_t)
+        _lib.check(self._lib.ddb_residual(self._ctx, _lib.ptr(c), _lib.ptr(out)))
+        return out
+
     # -- normal-equation blocks -------------------------------------------------------------
     def gram_count(self) -> int:
         return int(self._lib.ddb_gram_count(self._ctx))

@@ -40,6 +40,7 @@ void DevBuf::release() {
 }
 
 int gram_run(ddb_ctx* ctx, double* dPacked);
+int residual_run(ddb_ctx* ctx, const double* coef, double* rss_out);
 int generate_run(ddb_ctx* ctx, int system_id, int n_states, int64_t m, int64_t first_sample, uint64_t seed,
                  double noise_std);
 void sweep_free(ddb_ctx* ctx);
@@ -114,6 +115,10 @@ int ddb_ctx_destroy(ddb_ctx* ctx) {
     ctx->d_partials.release();
     ctx->d_plan.release();
     ctx->d_chunk_packed.release();
+    ctx->d_term_scale.release();
+    ctx->d_resid.release();
+    ctx->d_resid_terms.release();
+    ctx->d_resid_partials.release();
     ctx->d_feat.release();
     ctx->raw_X.release();
     for (auto& ev : ctx->ev)
@@ -150,6 +155,7 @@ int ddb_set_library_monomial(ddb_ctx* ctx, int n, int k, const uint8_t* exps) {
     ctx->plan_m = -1;
     ctx->have_gram = false;
     ctx->imp_k = 0;
+    ctx->term_scale_on = false;
     return DDB_OK;
 }
 
@@ -216,8 +222,10 @@ int ddb_set_features(ddb_ctx* ctx, int n_raw, int n_feat, const int32_t* kind, c
     ctx->n_raw = n_raw;
     ctx->have_gram = false;
     ctx->imp_k = 0;
+    ctx->term_scale_on = false;
     // the library must be (re)installed over n_feat states; data must be (re)bound
     ctx->dX = ctx->dY = nullptr;
+    ctx->range_on = false;
     ctx->m = 0;
     return DDB_OK;
 }
@@ -261,10 +269,12 @@ int ddb_upload(ddb_ctx* ctx, const double* X, const double* Y, int n_t, int64_t 
     ctx->timings.h2d_ms = ms;
     ctx->dX = ctx->own_X.as<double>();
     ctx->dY = ctx->own_Y.as<double>();
+    ctx->range_on = false;
     ctx->n_t = n_t;
     ctx->m = m;
     ctx->have_gram = false;
     ctx->imp_k = 0;
+    ctx->term_scale_on = false;
     return DDB_OK;
 }
 
@@ -305,8 +315,10 @@ int ddb_upload_gram(ddb_ctx* ctx, const double* X, const double* Y, int n_t, int
         ctx->chunk_ev.push_back(e);
     }
     ctx->n_t = n_t;
+    ctx->range_on = false;
     ctx->have_gram = false;
     ctx->imp_k = 0;
+    ctx->term_scale_on = false;
     const int64_t count = (int64_t)ctx->k * ctx->k + (int64_t)ctx->k * n_t + n_t;
     if (!dPacked) {
         DDB_TRY(ctx->d_packed.reserve((size_t)count * sizeof(double)));
@@ -364,6 +376,139 @@ int ddb_upload_gram(ddb_ctx* ctx, const double* X, const double* Y, int n_t, int
     return DDB_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// sample views, permutation, term normalisation, residuals (pre-/post-processing options of the reference)
+// ---------------------------------------------------------------------------------------------
+int ddb_set_sample_range(ddb_ctx* ctx, int64_t first, int64_t last) {
+    CHECK_CTX(ctx);
+    if (!ctx->range_on) {
+        ctx->full_X = ctx->dX;
+        ctx->full_Y = ctx->dY;
+        ctx->full_m = ctx->m;
+    }
+    if (!ctx->full_X || ctx->full_m <= 0) {
+        set_error("ddb_set_sample_range: no data bound");
+        return DDB_BAD_STATE;
+    }
+    if (last < 0) last = ctx->full_m;
+    if (first < 0 || first >= last || last > ctx->full_m) {
+        set_error("ddb_set_sample_range: need 0 <= first < last <= m");
+        return DDB_INVALID_ARG;
+    }
+    ctx->range_on = !(first == 0 && last == ctx->full_m);
+    ctx->dX = ctx->full_X + first * ctx->n;
+    ctx->dY = ctx->full_Y + first * ctx->n_t;
+    ctx->m = last - first;
+    ctx->have_gram = false;
+    ctx->imp_k = 0;
+    ctx->term_scale_on = false;
+    return DDB_OK;
+}
+
+__global__ void permute_kernel(const double* __restrict__ in, int w, const int64_t* __restrict__ perm, int64_t m,
+                               double* __restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m * w) return;
+    const int64_t s = t / w;
+    out[t] = in[perm[s] * w + (t % w)];
+}
+
+int ddb_permute_samples(ddb_ctx* ctx, const int64_t* perm) {
+    CHECK_CTX(ctx);
+    if (ctx->range_on) {
+        set_error("ddb_permute_samples: reset the sample range first");
+        return DDB_BAD_STATE;
+    }
+    if (!ctx->dX || !ctx->dY || ctx->m <= 0 || !perm) {
+        set_error("ddb_permute_samples: no data bound or null permutation");
+        return DDB_BAD_STATE;
+    }
+    const int64_t m = ctx->m;
+    std::vector<char> seen((size_t)m, 0);
+    for (int64_t s = 0; s < m; ++s) {
+        if (perm[s] < 0 || perm[s] >= m || seen[(size_t)perm[s]]) {
+            set_error("ddb_permute_samples: perm is not a permutation of 0..m-1");
+            return DDB_INVALID_ARG;
+        }
+        seen[(size_t)perm[s]] = 1;
+    }
+    const int n = ctx->n, n_t = ctx->n_t;
+    ddb::DevBuf px, py, pp;
+    int st = px.reserve((size_t)n * m * 8);
+    if (st == DDB_OK) st = py.reserve((size_t)n_t * m * 8);
+    if (st == DDB_OK) st = pp.reserve((size_t)m * 8);
+    if (st != DDB_OK) {
+        px.release(), py.release(), pp.release();
+        return st;
+    }
+    cudaMemcpyAsync(pp.p, perm, (size_t)m * 8, cudaMemcpyHostToDevice, ctx->stream);
+    permute_kernel<<<(unsigned)((m * n + 255) / 256), 256, 0, ctx->stream>>>(ctx->dX, n, pp.as<int64_t>(), m, px.as<double>());
+    permute_kernel<<<(unsigned)((m * n_t + 255) / 256), 256, 0, ctx->stream>>>(ctx->dY, n_t, pp.as<int64_t>(), m, py.as<double>());
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    pp.release();
+    if (e != cudaSuccess || (e = cudaGetLastError()) != cudaSuccess) {
+        px.release(), py.release();
+        set_error("ddb_permute_samples: %s", cudaGetErrorString(e));
+        return DDB_CUDA_ERROR;
+    }
+    ctx->own_X.release();
+    ctx->own_Y.release();
+    ctx->own_X = px;
+    ctx->own_Y = py;
+    ctx->dX = ctx->own_X.as<double>();
+    ctx->dY = ctx->own_Y.as<double>();
+    ctx->have_gram = false;
+    ctx->imp_k = 0;
+    ctx->term_scale_on = false;
+    return DDB_OK;
+}
+
+__global__ void scale_terms_kernel(double* __restrict__ packed, int k, int n_t, const double* __restrict__ scale) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t kk = (size_t)k * k, kn = (size_t)k * n_t;
+    if (t < kk) {
+        packed[t] /= scale[t % k] * scale[t / k];
+    } else if (t < kk + kn) {
+        packed[t] /= scale[(t - kk) % k];
+    }
+}
+
+int ddb_gram_scale_terms(ddb_ctx* ctx, const double* scale) {
+    CHECK_CTX(ctx);
+    if (!ctx->have_gram || !ctx->d_packed.p) {
+        set_error("ddb_gram_scale_terms: no normal-equation blocks in the context");
+        return DDB_BAD_STATE;
+    }
+    if (ctx->term_scale_on) {
+        set_error("ddb_gram_scale_terms: the blocks are already scaled");
+        return DDB_BAD_STATE;
+    }
+    if (!scale) {
+        set_error("ddb_gram_scale_terms: null scale");
+        return DDB_INVALID_ARG;
+    }
+    for (int j = 0; j < ctx->k; ++j)
+        if (!(scale[j] > 0.0) || !std::isfinite(scale[j])) {
+            set_error("ddb_gram_scale_terms: scale[%d] must be positive and finite", j);
+            return DDB_INVALID_ARG;
+        }
+    DDB_TRY(ctx->d_term_scale.reserve((size_t)ctx->k * 8));
+    DDB_CUDA_TRY(cudaMemcpyAsync(ctx->d_term_scale.p, scale, (size_t)ctx->k * 8, cudaMemcpyHostToDevice, ctx->stream));
+    const size_t tot = (size_t)ctx->k * ctx->k + (size_t)ctx->k * ctx->n_t;
+    scale_terms_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_packed.as<double>(), ctx->k, ctx->n_t,
+                                                                             ctx->d_term_scale.as<double>());
+    DDB_CUDA_TRY(cudaGetLastError());
+    DDB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    ctx->term_scale_on = true;
+    ctx->imp_k = 0;
+    return DDB_OK;
+}
+
+int ddb_residual(ddb_ctx* ctx, const double* coef, double* rss) {
+    CHECK_CTX(ctx);
+    return residual_run(ctx, coef, rss);
+}
+
 int ddb_bind_device(ddb_ctx* ctx, const double* dX, const double* dY, int n_t, int64_t m) {
     CHECK_CTX(ctx);
     DDB_TRY(check_data_args(ctx, dX, dY, n_t, m, "ddb_bind_device"));
@@ -375,10 +520,12 @@ int ddb_bind_device(ddb_ctx* ctx, const double* dX, const double* dY, int n_t, i
     }
     ctx->dX = dX;
     ctx->dY = dY;
+    ctx->range_on = false;
     ctx->n_t = n_t;
     ctx->m = m;
     ctx->have_gram = false;
     ctx->imp_k = 0;
+    ctx->term_scale_on = false;
     return DDB_OK;
 }
 

@@ -114,6 +114,17 @@ struct ddb_ctx {
     int plan_kaug = -1;
     bool have_gram = false;
 
+    // term normalisation (ddb_gram_scale_terms): the blocks in d_packed are those of Theta_j / scale_j
+    ddb::DevBuf d_term_scale;
+    bool term_scale_on = false;
+    // ddb_residual scratch
+    ddb::DevBuf d_resid, d_resid_terms, d_resid_partials;
+    // sample view (ddb_set_sample_range): dX / dY / m above describe the view; the whole data set is kept here
+    bool range_on = false;
+    const double* full_X = nullptr;
+    const double* full_Y = nullptr;
+    int64_t full_m = 0;
+
     // implicit view (ddb_implicit_select): the sweep runs on G[idx, idx] with EVERY selected library row as a
     // target regressed on the other selected rows (ImplicitOptimizer, reference Implicit.jl:57-108)
     ddb::DevBuf imp_packed;              // [G' (kk x kk) | R' = G' | yy' = diag G']

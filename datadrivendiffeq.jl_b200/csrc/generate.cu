@@ -141,6 +141,7 @@ int generate_run(ddb_ctx* ctx, int system_id, int n_states, int64_t m, int64_t f
         generate_kernel<1><<<ntraj, threads, smem, ctx->stream>>>(a);
     DDB_CUDA_TRY(cudaGetLastError());
     DDB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    ctx->range_on = false;
     ctx->dX = a.X;
     ctx->dY = a.Y;
     ctx->n_t = n;

@@ -206,7 +206,28 @@ __global__ void rss_reduce_kernel(const double* __restrict__ partials, int npart
     rss[c] = s;
 }
 
-int rss_run(ddb_ctx* ctx, SweepState* S, double* dRss) {
+// The streaming pass proper: candidates given as device arrays (CSR of (term, value) + target per candidate).
+// `map` translates term indices into rows of the installed library (implicit view) or is null; `scale` (per
+// term of the CANDIDATE index space, or null) divides the values (term normalisation: the candidates live in
+// the scaled space, the data are unscaled).  Writes ncand sums to dRss (device).
+struct RssCand {
+    int ncand;
+    int64_t nterms;
+    const int64_t* off;
+    const int32_t* nnz;
+    const int32_t* eq;
+    const int32_t* idx;
+    const double* val;
+};
+
+__global__ void rss_scale_kernel(RssTerm* __restrict__ terms, const int32_t* __restrict__ cand_idx, int64_t nterms,
+                                 const double* __restrict__ scale) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nterms) terms[t].val /= scale[cand_idx[t]];
+}
+
+static int rss_core(ddb_ctx* ctx, const RssCand& c, const int32_t* map, const RssTerm* targets, const double* scale,
+                    DevBuf& terms, DevBuf& partials, double* dRss, int* launches) {
     if (!ctx->dX || !ctx->dY || ctx->m <= 0) {
         set_error("ddb_rss: no data bound");
         return DDB_BAD_STATE;
@@ -215,31 +236,22 @@ int rss_run(ddb_ctx* ctx, SweepState* S, double* dRss) {
         set_error("ddb_rss: the library factor table is missing (run ddb_gram on this context first)");
         return DDB_BAD_STATE;
     }
-    const int ncand = S->ncand;
-    const bool implicit = ctx->imp_k > 0;
     cudaStream_t st = ctx->stream;
-    if (!dRss) {
-        DDB_TRY(S->rss.reserve((size_t)std::max(1, ncand) * 8));
-        dRss = S->rss.as<double>();
-    }
-    const int64_t nterms = S->pool_used;
-    DDB_TRY(S->cand_terms.reserve((size_t)std::max<int64_t>(1, nterms) * sizeof(RssTerm)));
-    DDB_CUDA_TRY(cudaEventRecord(ctx->ev[4], st));
-    if (nterms > 0)
-        rss_expand_kernel<<<(unsigned)((nterms + 255) / 256), 256, 0, st>>>(S->cand_idx.as<int32_t>(), S->cand_val.as<double>(),
-                                                                            nterms, ctx->d_factors.as<uint16_t>(), ctx->n + ctx->n_t,
-                                                                            implicit ? ctx->imp_idx.as<int32_t>() : nullptr,
-                                                                            S->cand_terms.as<RssTerm>());
-    if (implicit) {  // one record per target: the library term on the left-hand side
-        DDB_TRY(S->tgt_terms.reserve((size_t)ctx->imp_k * sizeof(RssTerm)));
-        rss_expand_kernel<<<(ctx->imp_k + 255) / 256, 256, 0, st>>>(nullptr, nullptr, ctx->imp_k, ctx->d_factors.as<uint16_t>(),
-                                                                   ctx->n + ctx->n_t, ctx->imp_idx.as<int32_t>(),
-                                                                   S->tgt_terms.as<RssTerm>());
+    const int ncand = c.ncand;
+    DDB_TRY(terms.reserve((size_t)std::max<int64_t>(1, c.nterms) * sizeof(RssTerm)));
+    if (c.nterms > 0) {
+        rss_expand_kernel<<<(unsigned)((c.nterms + 255) / 256), 256, 0, st>>>(c.idx, c.val, c.nterms, ctx->d_factors.as<uint16_t>(),
+                                                                              ctx->n + ctx->n_t, map, terms.as<RssTerm>());
+        ++*launches;
+        if (scale) {
+            rss_scale_kernel<<<(unsigned)((c.nterms + 255) / 256), 256, 0, st>>>(terms.as<RssTerm>(), c.idx, c.nterms, scale);
+            ++*launches;
+        }
     }
     const int passes = (ncand + kRssWarps * kRssAcc - 1) / (kRssWarps * kRssAcc);
     const int64_t ntiles = (ctx->m + kRssTile - 1) / kRssTile;
     const int nparts = (int)std::min<int64_t>(ntiles, (int64_t)ctx->sm_count * 4);
-    DDB_TRY(S->rss_partials.reserve((size_t)nparts * ncand * 8));
+    DDB_TRY(partials.reserve((size_t)nparts * ncand * 8));
     RssArgs a;
     a.X = ctx->dX;
     a.Y = ctx->dY;
@@ -247,12 +259,12 @@ int rss_run(ddb_ctx* ctx, SweepState* S, double* dRss) {
     a.n_t = ctx->n_t;
     a.m = ctx->m;
     a.ncand = ncand;
-    a.cand_off = S->cand_off.as<int64_t>();
-    a.cand_nnz = S->cand_nnz.as<int32_t>();
-    a.cand_eq = S->cand_eq.as<int32_t>();
-    a.terms = S->cand_terms.as<RssTerm>();
-    a.targets = implicit ? S->tgt_terms.as<RssTerm>() : nullptr;
-    a.partials = S->rss_partials.as<double>();
+    a.cand_off = c.off;
+    a.cand_nnz = c.nnz;
+    a.cand_eq = c.eq;
+    a.terms = terms.as<RssTerm>();
+    a.targets = targets;
+    a.partials = partials.as<double>();
     const size_t smem = 2 * (size_t)kRssPitch * (ctx->n + ctx->n_t + 1) * sizeof(double);
     if (smem > 200 * 1024) {
         set_error("ddb_rss: n + n_t too large for the shared-memory sample tile");
@@ -261,16 +273,99 @@ int rss_run(ddb_ctx* ctx, SweepState* S, double* dRss) {
     auto kern = ctx->max_degree <= 2 ? rss_kernel<2> : rss_kernel<kMaxFactors>;
     DDB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<dim3(nparts, passes), kRssWarps * 32, smem, st>>>(a);
-    rss_reduce_kernel<<<(ncand + 255) / 256, 256, 0, st>>>(S->rss_partials.as<double>(), nparts, ncand, dRss);
+    rss_reduce_kernel<<<(ncand + 255) / 256, 256, 0, st>>>(partials.as<double>(), nparts, ncand, dRss);
+    *launches += 2;
     DDB_CUDA_TRY(cudaGetLastError());
+    return DDB_OK;
+}
+
+int rss_run(ddb_ctx* ctx, SweepState* S, double* dRss) {
+    const int ncand = S->ncand;
+    const bool implicit = ctx->imp_k > 0;
+    cudaStream_t st = ctx->stream;
+    if (!dRss) {
+        DDB_TRY(S->rss.reserve((size_t)std::max(1, ncand) * 8));
+        dRss = S->rss.as<double>();
+    }
+    DDB_CUDA_TRY(cudaEventRecord(ctx->ev[4], st));
+    int launches = 0;
+    if (implicit) {  // one record per target: the library term on the left-hand side
+        DDB_TRY(S->tgt_terms.reserve((size_t)ctx->imp_k * sizeof(RssTerm)));
+        rss_expand_kernel<<<(ctx->imp_k + 255) / 256, 256, 0, st>>>(nullptr, nullptr, ctx->imp_k, ctx->d_factors.as<uint16_t>(),
+                                                                   ctx->n + ctx->n_t, ctx->imp_idx.as<int32_t>(),
+                                                                   S->tgt_terms.as<RssTerm>());
+        ++launches;
+    }
+    RssCand c{ncand, S->pool_used, S->cand_off.as<int64_t>(), S->cand_nnz.as<int32_t>(), S->cand_eq.as<int32_t>(),
+              S->cand_idx.as<int32_t>(), S->cand_val.as<double>()};
+    const double* scale = (!implicit && ctx->term_scale_on) ? ctx->d_term_scale.as<double>() : nullptr;
+    DDB_TRY(rss_core(ctx, c, implicit ? ctx->imp_idx.as<int32_t>() : nullptr, implicit ? S->tgt_terms.as<RssTerm>() : nullptr,
+                     scale, S->cand_terms, S->rss_partials, dRss, &launches));
     DDB_CUDA_TRY(cudaEventRecord(ctx->ev[5], st));
     DDB_CUDA_TRY(cudaStreamSynchronize(st));
     float ms = 0.f;
     DDB_CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]));
     ctx->timings.rss_ms = ms;
-    ctx->timings.sweep_launches += 3;
+    ctx->timings.sweep_launches += launches;
     S->rss_ptr = dRss;
     S->have_rss = true;
+    return DDB_OK;
+}
+
+// ddb_residual: rss of an arbitrary coefficient matrix (n_t x k column-major, host) over the current samples
+int residual_run(ddb_ctx* ctx, const double* coef, double* rss_out) {
+    const int k = ctx->k, n_t = ctx->n_t;
+    if (k <= 0 || n_t <= 0 || !coef || !rss_out) {
+        set_error("ddb_residual: library and data must be set, coef and rss non-null");
+        return DDB_INVALID_ARG;
+    }
+    if (ctx->factors_nt != n_t || !ctx->d_factors.p) {
+        extern int gram_ensure_factors(ddb_ctx * ctx, int kaug_pad);
+        DDB_TRY(gram_ensure_factors(ctx, ((k + n_t + 127) / 128) * 128));
+    }
+    std::vector<int64_t> off(n_t);
+    std::vector<int32_t> nnz(n_t), eq(n_t), idx;
+    std::vector<double> val;
+    for (int e = 0; e < n_t; ++e) {
+        off[e] = (int64_t)idx.size();
+        eq[e] = e;
+        for (int j = 0; j < k; ++j) {
+            const double v = coef[(size_t)e + (size_t)n_t * j];
+            if (v != 0.0) {
+                idx.push_back(j);
+                val.push_back(v);
+            }
+        }
+        nnz[e] = (int32_t)((int64_t)idx.size() - off[e]);
+    }
+    const int64_t nterms = (int64_t)idx.size();
+    cudaStream_t st = ctx->stream;
+    DevBuf& B = ctx->d_resid;  // [off | nnz | eq | idx | val | rss]
+    const size_t o_nnz = (size_t)n_t * 8, o_eq = o_nnz + (size_t)n_t * 4, o_idx = (o_eq + (size_t)n_t * 4 + 7) & ~size_t(7);
+    const size_t o_val = (o_idx + (size_t)std::max<int64_t>(1, nterms) * 4 + 7) & ~size_t(7);
+    const size_t o_rss = o_val + (size_t)std::max<int64_t>(1, nterms) * 8;
+    DDB_TRY(B.reserve(o_rss + (size_t)n_t * 8));
+    unsigned char* base = static_cast<unsigned char*>(B.p);
+    DDB_CUDA_TRY(cudaMemcpyAsync(base, off.data(), (size_t)n_t * 8, cudaMemcpyHostToDevice, st));
+    DDB_CUDA_TRY(cudaMemcpyAsync(base + o_nnz, nnz.data(), (size_t)n_t * 4, cudaMemcpyHostToDevice, st));
+    DDB_CUDA_TRY(cudaMemcpyAsync(base + o_eq, eq.data(), (size_t)n_t * 4, cudaMemcpyHostToDevice, st));
+    if (nterms) {
+        DDB_CUDA_TRY(cudaMemcpyAsync(base + o_idx, idx.data(), (size_t)nterms * 4, cudaMemcpyHostToDevice, st));
+        DDB_CUDA_TRY(cudaMemcpyAsync(base + o_val, val.data(), (size_t)nterms * 8, cudaMemcpyHostToDevice, st));
+    }
+    RssCand c{n_t, nterms, reinterpret_cast<const int64_t*>(base), reinterpret_cast<const int32_t*>(base + o_nnz),
+              reinterpret_cast<const int32_t*>(base + o_eq), reinterpret_cast<const int32_t*>(base + o_idx),
+              reinterpret_cast<const double*>(base + o_val)};
+    int launches = 0;
+    DDB_CUDA_TRY(cudaEventRecord(ctx->ev[4], st));
+    DDB_TRY(rss_core(ctx, c, nullptr, nullptr, nullptr, ctx->d_resid_terms, ctx->d_resid_partials,
+                     reinterpret_cast<double*>(base + o_rss), &launches));
+    DDB_CUDA_TRY(cudaEventRecord(ctx->ev[5], st));
+    DDB_CUDA_TRY(cudaMemcpyAsync(rss_out, base + o_rss, (size_t)n_t * 8, cudaMemcpyDeviceToHost, st));
+    DDB_CUDA_TRY(cudaStreamSynchronize(st));  // off/nnz/... are stack-lifetime host buffers
+    float ms = 0.f;
+    DDB_CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]));
+    ctx->timings.rss_ms = ms;
     return DDB_OK;
 }
 

@@ -176,6 +176,27 @@ int ddb_gram_download(ddb_ctx* ctx, double* G, double* R, double* yy);
  * blocks).  G, R, yy may be host or device pointers. */
 int ddb_gram_upload(ddb_ctx* ctx, const double* G, const double* R, const double* yy, int n_t);
 
+/* ---- pre-/post-processing options of the reference on the device ---------------------------------
+ * ddb_set_sample_range: the following ddb_gram / ddb_rss / ddb_residual calls see samples [first, last) of the
+ *   bound data only (last < 0 = to the end; ddb_gram needs first * n and first * n_t even -- 16-byte alignment of
+ *   the bulk copies -- the rss / residual passes take any first).  Replaces `splitobs(data, at = split)` and the
+ *   batches of the `DataLoader` (src/utils/data_processing.jl:29-39): train part, test part and every batch are
+ *   views of the resident data.  A new upload / bind resets the view.
+ * ddb_permute_samples: reorders the resident samples, new sample s = old sample perm[s] (host array of m
+ *   indices); the `shuffle = true` of the DataLoader (data_processing.jl:38).
+ * ddb_gram_scale_terms: divides the blocks in the context by per-term scales (G_ij / (s_i s_j), R_ie / s_i):
+ *   the regression then runs on Theta_j / s_j as after `apply_transform!(ZScoreTransform(center = false))`
+ *   (data_processing.jl:64-80, src/commonsolve.jl:128-130) -- thresholds act on the scaled coefficients, the
+ *   exact-rss pass divides the candidates by the scales, ddb_select returns SCALED coefficients (the caller
+ *   maps them back, lib/DataDrivenSparse/src/commonsolve.jl:19-21).  Reset by a new Gram.
+ * ddb_residual: rss[e] = sum_s (Y[e,s] - sum_j coef[e,j] theta_j(x(s)))^2 over the current sample view for an
+ *   arbitrary coefficient matrix (n_t x k column-major, host): test error (commonsolve.jl:42) and the rss that
+ *   `DataDrivenSolution` recomputes on the CPU (src/solution.jl:37-56). */
+int ddb_set_sample_range(ddb_ctx* ctx, int64_t first, int64_t last);
+int ddb_permute_samples(ddb_ctx* ctx, const int64_t* perm);
+int ddb_gram_scale_terms(ddb_ctx* ctx, const double* scale);
+int ddb_residual(ddb_ctx* ctx, const double* coef, double* rss);
+
 /* ---- stage 3: thresholded sweep ---------------------------------------------------------------- */
 
 /* ---- implicit sparse regression (ImplicitOptimizer) ----------------------------------------------

@@ -51,6 +51,8 @@ from .sparse import (  # noqa: F401
     ImplicitOptimizer,
     implicit_candidate_matrix,
     implicit_sparse_regression,
+    solve_processed,
+    zscore_fit,
     bic,
     aic,
     aicc,

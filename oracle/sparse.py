@@ -519,3 +519,53 @@ def implicit_sparse_regression(alg: ImplicitOptimizer, Theta: np.ndarray, implic
     trainerror = float(np.sum((C @ Theta) ** 2))  # :95
     d = int(np.sum(np.abs(C) > 0.0))  # :107
     return SparseRegressionResult(C, d, lams, iters, None, trainerror, 1)
+
+
+# ----------------------------------------------------------------------------------------------
+# init + solve! with the pre-processing options (src/commonsolve.jl:92-139, src/utils/data_processing.jl:29-126,
+# lib/DataDrivenSparse/src/commonsolve.jl:1-24)
+# ----------------------------------------------------------------------------------------------
+def zscore_fit(Theta: np.ndarray) -> np.ndarray:
+    """``fit(DataNormalization{ZScoreTransform}, data)`` (``data_processing.jl:75-80``): per-row standard
+    deviation (``center = false`` only suppresses the subtraction of the mean when the transform is APPLIED),
+    zero scales replaced by one (constants)."""
+    s = np.std(Theta, axis=1, ddof=1)
+    s[s == 0.0] = 1.0
+    return s
+
+
+def solve_processed(alg, Theta: np.ndarray, Y: np.ndarray, options: Optional[CommonOptions] = None, normalize=None,
+                    split: float = 1.0, batchsize: int = 0, partial: bool = True, perm=None):
+    """Returns ``(coefficients after apply_transform, results sorted by l2error, sigma)``.  ``perm``: order of
+    the training samples (the DataLoader's shuffle; ``None`` keeps the order)."""
+    Theta = np.array(Theta, dtype=np.float64)
+    Y = np.atleast_2d(np.asarray(Y, dtype=np.float64))
+    m = Theta.shape[1]
+    sigma = None
+    if normalize == "ZScoreTransform":  # commonsolve.jl:128-130: fitted and applied on ALL samples before the split
+        sigma = zscore_fit(Theta)
+        Theta = Theta / sigma[:, None]
+    elif normalize is not None:
+        raise ValueError(normalize)
+    split = min(max(float(split), 0.0), 1.0)  # data_processing.jl:32
+    m_train = int(round(split * m))  # MLUtils.splitobs(at = split, shuffle = false)
+    Tt, Yt = Theta[:, m_train:], Y[:, m_train:]
+    order = np.arange(m_train) if perm is None else np.asarray(perm)
+    bs = m_train if batchsize <= 0 else batchsize  # :36
+    starts = list(range(0, m_train, bs))
+    if not partial and m_train % bs:
+        starts = starts[:-1]
+    results = []
+    for b0 in starts:
+        idx = order[b0:b0 + bs]
+        Tb, Yb = Theta[:, idx], Y[:, idx]
+        C, lams, iters = run_algorithm(alg, Tb, Yb, options)
+        trainerror = float(np.sum((Yb - C @ Tb) ** 2))  # lib commonsolve.jl:37
+        testerror = float(np.sum((Yt - C @ Tt) ** 2)) if Tt.shape[1] else None  # :41-45
+        results.append(SparseRegressionResult(C, int(np.sum(np.abs(C) > 0.0)), lams, iters, testerror, trainerror, 1))
+    results.sort(key=lambda r: r.testerror if r.testerror is not None else r.trainerror)  # :12 sort!(results, by = l2error)
+    best = results[0]
+    C = best.coefficients.copy()
+    if sigma is not None:
+        C = C / sigma[None, :]  # :19-21 apply_transform(transform, coefficients')' with an empty mean
+    return C, results, sigma

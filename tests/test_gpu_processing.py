@@ -1,0 +1,112 @@
+"""GPU parity of the reference's pre-processing options: ZScore normalisation of the
+library rows (``src/utils/data_processing.jl:64-126``), train/test split and shuffled mini-batches
+(``:29-39``), best batch by test error (``lib/DataDrivenSparse/src/commonsolve.jl:10-21``), and the device
+residual pass that replaces the CPU re-evaluation of the solution (``src/solution.jl:37-56``, row f2)."""
+import numpy as np
+import pytest
+
+import ddb200
+import oracle
+from ddb200 import systems
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = ddb200.Context(0)
+    yield c
+    c.close()
+
+
+def _lorenz(m=2000, noise=0.05, seed=1):
+    X, DX = systems.lorenz_ensemble(m, seed=seed, samples_per_traj=500)
+    rng = np.random.default_rng(seed)
+    return X, DX + noise * rng.standard_normal(DX.shape)
+
+
+def _solve(ctx, basis, X, DX, inner, **opts):
+    alg = ddb200.B200Sparse(inner)
+    alg._ctx = ctx
+    return ddb200.solve(ddb200.ContinuousDataDrivenProblem(X, DX=DX), basis, alg, ddb200.DataDrivenCommonOptions(**opts))
+
+
+# thresholds large enough that the selected models are sparse: with a dense active set the normal-equation
+# solve of this noisy degree-3 library is only good to ~1e-7 against the reference's QR
+LAMS = 10.0 ** np.arange(-1, 1.01, 0.25)
+ALGS = {"STLSQ": lambda m: m.STLSQ(LAMS), "STLSQ-ridge": lambda m: m.STLSQ(LAMS, 1e-3), "ADMM": lambda m: m.ADMM(LAMS[::2]),
+        "SR3": lambda m: m.SR3(LAMS)}
+
+
+@pytest.mark.parametrize("name", list(ALGS))
+@pytest.mark.parametrize("with_const", [True, False])
+def test_zscore_normalisation_matches_oracle(ctx, name, with_const):
+    X, DX = _lorenz()
+    basis = ddb200.polynomial_basis(3, 3)
+    if not with_const:  # library without the constant term: the column sums need their own pass
+        basis = ddb200.Basis(basis.exponents[:, 1:])
+    Th = oracle.evaluate_library(basis.exponents, X)
+    C_ref, res_ref, sigma = oracle.solve_processed(ALGS[name](oracle), Th, DX, normalize="ZScoreTransform")
+    sol = _solve(ctx, basis, X, DX, ALGS[name](ddb200), normalize="ZScoreTransform")
+    Cs = sol.results[0].coefficients  # scaled space: thresholds act here
+    np.testing.assert_array_equal(Cs != 0.0, res_ref[0].coefficients != 0.0)
+    # noisy data, cond(Theta) ~ 1e5: both sides solve normal equations here (ridge) or QR vs Gram (rho = 0) and
+    # agree to ~1e-8; the 1e-10 criterion of the north star is checked on the well-conditioned configurations
+    np.testing.assert_allclose(Cs, res_ref[0].coefficients, rtol=1e-7, atol=1e-11)
+    np.testing.assert_allclose(sol.coefficients, oracle.construct_coefficients(C_ref), rtol=1e-7, atol=2e-10)
+    np.testing.assert_allclose(sol.results[0].trainerror, res_ref[0].trainerror, rtol=1e-7)
+
+
+@pytest.mark.parametrize("normalize", [None, "ZScoreTransform"])
+def test_split_and_batches_match_oracle(ctx, normalize):
+    X, DX = _lorenz(m=2000)
+    X, DX = X[:, :1501], DX[:, :1501]
+    basis = ddb200.polynomial_basis(3, 2)
+    Th = oracle.evaluate_library(basis.exponents, X)
+    m = X.shape[1]
+    m_train = int(round(0.8 * m))
+    perm = np.random.default_rng(3).permutation(m_train)
+    kw = dict(split=0.8, batchsize=250, partial=True)
+    C_ref, res_ref, _ = oracle.solve_processed(oracle.STLSQ(LAMS), Th, DX, normalize=normalize, perm=perm, **kw)
+    sol = _solve(ctx, basis, X, DX, ddb200.STLSQ(LAMS), normalize=normalize, perm=perm, **kw)
+    assert len(sol.results) == len(res_ref) == 5  # 1201 training samples: 4 x 250 + 201; the test part starts at an odd sample
+    for got, ref in zip(sol.results, res_ref):  # same order after sort!(results, by = l2error)
+        np.testing.assert_array_equal(got.coefficients != 0.0, ref.coefficients != 0.0)
+        np.testing.assert_allclose(got.coefficients, ref.coefficients, rtol=1e-7, atol=1e-10)
+        np.testing.assert_allclose(got.testerror, ref.testerror, rtol=1e-7)
+        np.testing.assert_allclose(got.trainerror, ref.trainerror, rtol=1e-6, atol=1e-12)
+    np.testing.assert_allclose(sol.coefficients, oracle.construct_coefficients(C_ref), rtol=1e-7, atol=2e-10)
+    # rss of the final (rounded) model on ALL samples, as DataDrivenSolution recomputes it
+    assert sol.rss == pytest.approx(float(np.sum((DX - sol.coefficients @ Th) ** 2)), rel=1e-9)
+    # partial = false drops the one-sample batch
+    sol2 = _solve(ctx, basis, X, DX, ddb200.STLSQ(LAMS), normalize=normalize, perm=perm, split=0.8, batchsize=250, partial=False)
+    assert len(sol2.results) == 4
+
+
+def test_residual_permute_and_range(ctx):
+    X, DX = _lorenz(m=1000)
+    ex = oracle.polynomial_exponents(3, 2)
+    Th = oracle.evaluate_library(ex, X)
+    rng = np.random.default_rng(0)
+    C = rng.standard_normal((3, ex.shape[1])) * (rng.random((3, ex.shape[1])) < 0.4)
+    ctx.set_features(0, None)
+    ctx.set_library(ex)
+    ctx.upload(X, DX)
+    np.testing.assert_allclose(ctx.residual(C), ((DX - C @ Th) ** 2).sum(1), rtol=1e-12)
+    ctx.set_sample_range(200, 701)
+    np.testing.assert_allclose(ctx.residual(C), ((DX[:, 200:701] - C @ Th[:, 200:701]) ** 2).sum(1), rtol=1e-12)
+    ctx.gram()
+    G, R, yy = ctx.gram_download()
+    np.testing.assert_allclose(G, Th[:, 200:701] @ Th[:, 200:701].T, rtol=1e-12, atol=1e-9)
+    ctx.set_sample_range(0, -1)
+    perm = rng.permutation(1000)
+    ctx.permute_samples(perm)
+    Xd, Yd = ctx.download_data()
+    np.testing.assert_array_equal(Xd, X[:, perm])
+    np.testing.assert_array_equal(Yd, DX[:, perm])
+    with pytest.raises(ddb200._lib.DDBError):
+        ctx.permute_samples(np.zeros(1000, dtype=np.int64))
+    with pytest.raises(ddb200._lib.DDBError):
+        ctx.set_sample_range(10, 5)
+    ctx.set_sample_range(201, 500)  # odd first sample: fine for the residual pass
+    np.testing.assert_allclose(ctx.residual(C), ((DX[:, perm][:, 201:500] - C @ Th[:, perm][:, 201:500]) ** 2).sum(1), rtol=1e-12)
