@@ -58,8 +58,8 @@ def test_default_options_match_reference():
     assert o.abstol == o.reltol == math.sqrt(np.finfo(float).eps)
 
 
-@pytest.mark.parametrize("kw", [dict(denoise=True), dict(normalize="ZScoreTransform"), dict(split=0.8), dict(batchsize=32),
-                                dict(roundingmode="RoundNearest"), dict(selector="mdl")])
+@pytest.mark.parametrize("kw", [dict(denoise=True), dict(normalize="UnitRangeTransform"), dict(roundingmode="RoundNearest"),
+                                dict(selector="mdl")])
 def test_unsupported_options_raise(kw):
     from ddb200.api import _check_options
 
