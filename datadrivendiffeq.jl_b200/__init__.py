@@ -36,5 +36,5 @@ from .api import (  # noqa: F401
     polynomial_basis,
     solve,
 )
-from .dmd import B200DMD, DMDPINV, DMDSVD, KoopmanResult, solve_dmd  # noqa: F401
+from .dmd import B200DMD, DMDPINV, DMDSVD, FBDMD, TOTALDMD, KoopmanResult, solve_dmd  # noqa: F401
 from . import dist, systems  # noqa: F401

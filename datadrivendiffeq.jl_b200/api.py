@@ -232,6 +232,7 @@ class DataDrivenProblem:
     DX: Optional[np.ndarray] = None
     Y: Optional[np.ndarray] = None
     t: Optional[np.ndarray] = None
+    U: Optional[np.ndarray] = None  # control inputs (DataDrivenDMD only; the sparse path rejects controls)
 
     def __post_init__(self):
         self.X = np.asarray(self.X, dtype=np.float64)
@@ -261,8 +262,8 @@ def ContinuousDataDrivenProblem(X, t=None, DX=None) -> DataDrivenProblem:
     return DataDrivenProblem(X=X, kind="continuous", DX=DX, t=t)
 
 
-def DiscreteDataDrivenProblem(X, t=None) -> DataDrivenProblem:
-    return DataDrivenProblem(X=X, kind="discrete", t=t)
+def DiscreteDataDrivenProblem(X, t=None, U=None) -> DataDrivenProblem:
+    return DataDrivenProblem(X=X, kind="discrete", t=t, U=U)
 
 
 def DirectDataDrivenProblem(X, Y, t=None) -> DataDrivenProblem:

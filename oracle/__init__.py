@@ -60,4 +60,14 @@ from .sparse import (  # noqa: F401
     dof,
     r2,
 )
-from .dmd import DMDPINV, DMDSVD, truncated_svd, koopman_solve  # noqa: F401
+from .dmd import (  # noqa: F401
+    DMDPINV,
+    DMDSVD,
+    TOTALDMD,
+    FBDMD,
+    dmdpinv_controlled,
+    dmdsvd_controlled,
+    operator_matrix,
+    truncated_svd,
+    koopman_solve,
+)

@@ -98,3 +98,57 @@ def koopman_solve(alg, x: np.ndarray) -> KoopmanResult:
     with np.errstate(divide="ignore"):
         ll = float(-n / 2 * np.log(np.float64(rss) / n))
     return KoopmanResult(lam, phi, Kr, C, Q, P, rss, d, n, ll)
+
+
+# ----------------------------------------------------------------------------------------------
+# variants (lib/DataDrivenDMD/src/algorithms.jl:84-93, 160-176, 215-235, 276-292)
+# ----------------------------------------------------------------------------------------------
+def dmdpinv_controlled(X, Y, U):
+    """``(x::DMDPINV)(X, Y, U)`` (``algorithms.jl:84-93``): ``Ktilde = Y / [X; U]``; returns (lam, phi, B)."""
+    nx = X.shape[0]
+    XU = np.vstack([X, U])
+    Kt = _ldiv(np.ascontiguousarray(XU.T), np.ascontiguousarray(Y.T)).T
+    lam, phi = sla.eig(Kt[:, :nx])
+    return lam, phi, Kt[:, nx:]
+
+
+def dmdsvd_controlled(X, Y, U, truncation=0.0):
+    """``(x::DMDSVD)(X, Y, U)`` (``algorithms.jl:160-176``, DMDc)."""
+    nx = X.shape[0]
+    Ut, St, Vt = truncated_svd(np.vstack([X, U]), truncation)
+    Uh = sla.svd(Y, full_matrices=False, lapack_driver="gesdd")[0]
+    U1, U2 = Ut[:nx], Ut[nx:]
+    C = (Y @ Vt) * (1.0 / St)[None, :]
+    At = Uh.T @ C @ U1.T @ Uh
+    Bt = C @ U2.T
+    lam, om = sla.eig(At)
+    phi = C @ U1.T @ Uh @ om
+    return lam, phi, Bt
+
+
+class TOTALDMD:
+    """``TOTALDMD(truncation, alg)`` (``algorithms.jl:215-235``): project on the right singular subspace of
+    ``[X; Y]``, then run ``alg``."""
+
+    def __init__(self, truncation=0.0, alg=None):
+        self.truncation, self.alg = truncation, alg if alg is not None else DMDPINV()
+
+    def __call__(self, X, Y):
+        _, _, Q = truncated_svd(np.vstack([X, Y]), self.truncation)
+        return self.alg(X @ Q, Y @ Q)
+
+
+class FBDMD:
+    """``FBDMD(truncation)`` (``algorithms.jl:276-292``): ``sqrt(A1 * inv(A2))`` of the forward and backward
+    exact-DMD operators, signs taken from ``A1``."""
+
+    def __init__(self, truncation=0.0):
+        self.alg = DMDSVD(truncation)
+
+    def __call__(self, X, Y):
+        A1 = operator_matrix(*self.alg(X, Y))
+        A2 = operator_matrix(*self.alg(Y, X))
+        A1 = np.real_if_close(A1, tol=1e6)
+        At = sla.sqrtm(A1 @ np.linalg.inv(A2))
+        At = np.abs(At) * np.sign(np.real(A1))
+        return sla.eig(At)

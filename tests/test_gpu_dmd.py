@@ -72,3 +72,88 @@ def test_gram_blocks_and_operator_general(n, m):
         Kref = np.linalg.lstsq(X.T, Y.T, rcond=None)[0].T
         assert np.max(np.abs(Kh - Kref)) <= 1e-9 * max(1.0, np.max(np.abs(Kref)))
         np.testing.assert_allclose(Kh, A, atol=1e-8)
+
+
+# ------------------------------------------------------------------------------------------------
+# variants on the Gram blocks: TOTALDMD, FBDMD, controlled DMD
+# ------------------------------------------------------------------------------------------------
+def _variant(name):
+    return {
+        "TOTALDMD-PINV": (ddb200.TOTALDMD(0.0, ddb200.DMDPINV()), oracle.TOTALDMD(0.0, oracle.DMDPINV())),
+        "TOTALDMD-SVD": (ddb200.TOTALDMD(0.0, ddb200.DMDSVD()), oracle.TOTALDMD(0.0, oracle.DMDSVD())),
+        "FBDMD": (ddb200.FBDMD(), oracle.FBDMD()),
+    }[name]
+
+
+@pytest.mark.parametrize("name", ["TOTALDMD-PINV", "TOTALDMD-SVD", "FBDMD"])
+def test_variants_linear_discrete_groundtruth(name):
+    # lib/DataDrivenDMD/test/Core/linear_autonomous.jl:11-37 runs the same ground truth for every algorithm
+    A = np.array([[0.9, -0.2], [0.0, 0.2]])
+    x = _snapshots(A, [10.0, -10.0], 10)
+    mine, ref = _variant(name)
+    res = ddb200.solve_dmd(ddb200.DiscreteDataDrivenProblem(x), ddb200.B200DMD(mine))
+    Kref = np.real(oracle.operator_matrix(*ref(x[:, :-1], x[:, 1:])))
+    np.testing.assert_allclose(np.real(res.K), A, atol=1e-8)
+    np.testing.assert_allclose(np.real(res.K), Kref, atol=1e-8)
+    assert res.rss <= 1e-10 and res.dof == 3
+
+
+@pytest.mark.parametrize("name", ["TOTALDMD-PINV", "TOTALDMD-SVD", "FBDMD"])
+def test_variants_match_oracle_on_noisy_snapshots(name):
+    n, m = 12, 3000
+    A, X, Y = systems.linear_snapshots(n, m, seed=5, restart=10**9)
+    x = np.concatenate([X, Y[:, -1:]], axis=1)
+    x = x + 1e-3 * np.random.default_rng(0).standard_normal(x.shape)  # total-least-squares setting: noise in X and Y
+    mine, ref = _variant(name)
+    res = ddb200.solve_dmd(ddb200.DiscreteDataDrivenProblem(x), ddb200.B200DMD(mine))
+    lam, phi = ref(x[:, :-1], x[:, 1:])
+    Kref = np.real(oracle.operator_matrix(lam, phi))
+    assert np.max(np.abs(np.real(res.K) - Kref)) <= 1e-6 * max(1.0, np.max(np.abs(Kref)))
+    np.testing.assert_allclose(np.sort_complex(res.eigenvalues), np.sort_complex(lam), atol=1e-6)
+
+
+def test_totaldmd_integer_truncation():
+    n, m = 8, 2000
+    A, X, Y = systems.linear_snapshots(n, m, seed=2, restart=10**9)
+    x = np.concatenate([X, Y[:, -1:]], axis=1)
+    res = ddb200.solve_dmd(ddb200.DiscreteDataDrivenProblem(x), ddb200.B200DMD(ddb200.TOTALDMD(6, ddb200.DMDSVD())))
+    lam, phi = oracle.TOTALDMD(6, oracle.DMDSVD())(x[:, :-1], x[:, 1:])
+    np.testing.assert_allclose(np.sort_complex(res.eigenvalues), np.sort_complex(lam), atol=1e-7)
+
+
+@pytest.mark.parametrize("inner", ["DMDPINV", "DMDSVD", "TOTALDMD"])
+def test_forced_unstable_system_with_known_input_matrix(inner):
+    # lib/DataDrivenDMD/test/Core/linear_forced.jl:36-54
+    X = np.array([[4, 2, 1, 0.5, 0.25], [7, 0.7, 0.07, 0.007, 0.0007]])
+    U = np.array([[-4, -2, -1, -0.5, 0.0]])
+    B = np.array([[1.0], [0.0]])
+    alg = {"DMDPINV": ddb200.DMDPINV(), "DMDSVD": ddb200.DMDSVD(), "TOTALDMD": ddb200.TOTALDMD(2, ddb200.DMDPINV())}[inner]
+    res = ddb200.solve_dmd(ddb200.DiscreteDataDrivenProblem(X, U=U), ddb200.B200DMD(alg), control_input=B)
+    np.testing.assert_allclose(np.real(res.K), [[1.5, 0.0], [0.0, 0.1]], atol=1e-9)
+    np.testing.assert_array_equal(res.B, B)
+    assert res.dof == 3 and res.rss <= 1e-20
+
+
+@pytest.mark.parametrize("inner", ["DMDPINV", "DMDSVD"])
+def test_controlled_dmd_matches_oracle(inner):
+    rng = np.random.default_rng(11)
+    n, nu, m = 6, 2, 800
+    A = 0.9 * np.linalg.qr(rng.standard_normal((n, n)))[0]
+    Bt = rng.standard_normal((n, nu))
+    U = rng.standard_normal((nu, m + 1))
+    x = np.empty((n, m + 1))
+    x[:, 0] = rng.standard_normal(n)
+    for j in range(m):
+        x[:, j + 1] = A @ x[:, j] + Bt @ U[:, j]
+    alg = ddb200.DMDPINV() if inner == "DMDPINV" else ddb200.DMDSVD()
+    res = ddb200.solve_dmd(ddb200.DiscreteDataDrivenProblem(x, U=U), ddb200.B200DMD(alg))
+    if inner == "DMDPINV":
+        lam, phi, Bref = oracle.dmdpinv_controlled(x[:, :-1], x[:, 1:], U[:, :-1])
+    else:
+        lam, phi, Bref = oracle.dmdsvd_controlled(x[:, :-1], x[:, 1:], U[:, :-1])
+    Kref = np.real(oracle.operator_matrix(lam, phi))
+    np.testing.assert_allclose(np.real(res.K), Kref, atol=1e-8)
+    np.testing.assert_allclose(res.B, Bref, atol=1e-8)
+    np.testing.assert_allclose(np.real(res.K), A, atol=1e-8)
+    np.testing.assert_allclose(res.B, Bt, atol=1e-8)
+    assert res.rss <= 1e-16 * m

@@ -199,3 +199,21 @@ def test_generator_forms_match_the_reference():
         assert fn(3, 2).features == oracle.generator_features(kind, 3, 2)
     b = ddb200.concat_bases([ddb200.polynomial_basis(2, 5), ddb200.sin_basis(2, 1), ddb200.cos_basis(2, 1)])
     assert len(b) == 25 and b.n_states == 2 and b.term_strings()[-4:] == ["sin(x1)", "sin(x2)", "cos(x1)", "cos(x2)"]
+
+
+def test_dmd_variants_reference_ground_truths():
+    """``lib/DataDrivenDMD/test/Core/linear_autonomous.jl:11-37`` (every algorithm recovers
+    ``[0.9 -0.2; 0.0 0.2]``) and ``linear_forced.jl:36-54`` (``K ~ [1.5 0; 0 0.1]`` with the known input matrix)."""
+    A = np.array([[0.9, -0.2], [0.0, 0.2]])
+    x = np.empty((2, 11))
+    x[:, 0] = [10.0, -10.0]
+    for i in range(10):
+        x[:, i + 1] = A @ x[:, i]
+    for alg in (oracle.TOTALDMD(0.0, oracle.DMDPINV()), oracle.TOTALDMD(0.0, oracle.DMDSVD()), oracle.FBDMD()):
+        np.testing.assert_allclose(np.real(oracle.operator_matrix(*alg(x[:, :-1], x[:, 1:]))), A, atol=1e-8)
+    X = np.array([[4, 2, 1, 0.5, 0.25], [7, 0.7, 0.07, 0.007, 0.0007]])
+    U = np.array([[-4, -2, -1, -0.5, 0.0]])
+    B = np.array([[1.0], [0.0]])
+    Yeff = X[:, 1:] - B @ U[:, :-1]
+    for alg in (oracle.DMDPINV(), oracle.DMDSVD(), oracle.TOTALDMD(2, oracle.DMDPINV())):
+        np.testing.assert_allclose(np.real(oracle.operator_matrix(*alg(X[:, :-1], Yeff))), [[1.5, 0.0], [0.0, 0.1]], atol=1e-9)
