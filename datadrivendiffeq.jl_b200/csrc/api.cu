@@ -297,8 +297,9 @@ int ddb_upload_gram(ddb_ctx* ctx, const double* X, const double* Y, int n_t, int
     const int n = ctx->n;
     const int n_in = ctx->n_raw > 0 ? ctx->n_raw : n;  // states per sample in the caller's buffer
     const size_t row_bytes = (size_t)(n_in + n_t) * sizeof(double);
-    // ~512 MB per chunk, at most 16 chunks, chunk boundaries on multiples of 64 samples
-    int nchunks = (int)std::min<int64_t>(16, std::max<int64_t>(1, (int64_t)((double)m * row_bytes / (512.0 * 1024 * 1024))));
+    // at most 16 chunks of at least ~64 MB (the first chunk's copy is the only exposed one), chunk boundaries
+    // on multiples of 64 samples
+    int nchunks = (int)std::min<int64_t>(16, std::max<int64_t>(1, (int64_t)((double)m * row_bytes / (64.0 * 1024 * 1024))));
     int64_t chunk = ((m + nchunks - 1) / nchunks + 63) / 64 * 64;
     nchunks = (int)((m + chunk - 1) / chunk);
     if (nchunks <= 1) {

@@ -64,6 +64,7 @@ struct RssArgs {
     const int32_t* cand_eq;
     const RssTerm* terms;
     const RssTerm* targets;  // implicit mode: target e is a library term (one record each); null = row e of Y
+    int term_cap;            // term records of one CTA's candidates that fit in shared memory
     double* partials;  // gridDim.x x ncand
 };
 
@@ -99,68 +100,66 @@ __device__ __forceinline__ void rss_stage_rows(double* buf, const double* src, i
     }
 }
 
-template <int NF>
-__global__ void __launch_bounds__(kRssWarps * 32) rss_kernel(const RssArgs a) {
-    extern __shared__ double sm[];
-    const int rows = a.n + a.n_t + 1;  // + the row of ones
-    double* buf[2] = {sm, sm + (size_t)rows * kRssPitch};
+// The tile loop.  SMEM_TERMS: the candidates' term records live in shared memory (s_terms); otherwise they are
+// read from the global table.  Every shared-memory address is formed from `sm` directly so that the compiler
+// keeps the accesses in the shared address space (LDS with 32-bit addressing, no generic-pointer arithmetic).
+template <int NF, bool SMEM_TERMS>
+__device__ __forceinline__ void rss_tiles(const RssArgs& a, double* sm, const int4* s_meta, const RssTerm* s_terms,
+                                          int nslots, int cbase, int64_t t_lo, int64_t t_hi, int tp,
+                                          double (&acc)[kRssAcc]) {
+    const int rows = a.n + a.n_t + 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int cbase = blockIdx.y * (kRssWarps * kRssAcc);
-    // this CTA's sample range (whole tiles)
-    const int64_t ntiles = (a.m + kRssTile - 1) / kRssTile;
-    const int64_t t_lo = ntiles * blockIdx.x / gridDim.x, t_hi = ntiles * (blockIdx.x + 1) / gridDim.x;
+    const int tile_doubles = rows * kRssPitch;
     RssWalk wx, wy;
     wx.init(a.n);
     wy.init(a.n_t);
-    if (threadIdx.x < 2 * kRssPitch) buf[threadIdx.x / kRssPitch][(rows - 1) * kRssPitch + threadIdx.x % kRssPitch] = 1.0;
-
-    // candidates of this warp: cbase + warp + 8 * slot
-    int nslots = 0;
-    for (int q = 0; q < kRssAcc; ++q)
-        if (cbase + warp + kRssWarps * q < a.ncand) nslots = q + 1;
-    double acc[kRssAcc];
-#pragma unroll
-    for (int q = 0; q < kRssAcc; ++q) acc[q] = 0.0;
-
-    auto stage = [&](double* dst, int64_t tile) {
+    auto stage = [&](int which, int64_t tile) {
         const int64_t s0 = tile * kRssTile;
         const int valid = (int)min((int64_t)kRssTile, a.m - s0);
+        double* dst = sm + which * tile_doubles;
         rss_stage_rows(dst, a.X + s0 * a.n, a.n, valid, wx);
         rss_stage_rows(dst + a.n * kRssPitch, a.Y + s0 * a.n_t, a.n_t, valid, wy);
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    if (t_lo < t_hi) stage(buf[0], t_lo);
+    if (t_lo < t_hi) stage(0, t_lo);
     for (int64_t tile = t_lo; tile < t_hi; ++tile) {
         const int cur = (int)((tile - t_lo) & 1);
         if (tile + 1 < t_hi) {
-            stage(buf[cur ^ 1], tile + 1);
+            stage(cur ^ 1, tile + 1);
             asm volatile("cp.async.wait_group 1;" ::: "memory");
         } else {
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
         const int valid = (int)min((int64_t)kRssTile, a.m - tile * kRssTile);
-        const double* xs = buf[cur] + lane;
+        const double* xs = sm + cur * tile_doubles + lane;
         const bool live = lane < valid;
 #pragma unroll
         for (int q = 0; q < kRssAcc; ++q) {
             if (q < nslots) {
-                const int c = cbase + warp + kRssWarps * q;
-                const RssTerm* r = a.terms + __ldg(a.cand_off + c);
-                const int nnz = __ldg(a.cand_nnz + c);
-                const int eq = __ldg(a.cand_eq + c);
+                const int4 mt = s_meta[warp + kRssWarps * q];
+                const int nnz = SMEM_TERMS ? mt.w : mt.y, eq = mt.z;  // shared-memory records are padded to 4s
+                const RssTerm* r = SMEM_TERMS ? s_terms + mt.x : a.terms + __ldg(a.cand_off + cbase + warp + kRssWarps * q);
+                const int4* r16 = reinterpret_cast<const int4*>(s_terms) + mt.x;  // compact records (degree <= 2)
                 double fit = 0.0;
-                if (NF <= 2) {
-#pragma unroll 4
+                if (NF <= 2 && SMEM_TERMS) {
+                    for (int t = 0; t < nnz; t += 4) {  // the padded count is a multiple of 4
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int4 w = r16[t + u];  // {val, o32[0], o32[1]}
+                            fit = fma(__hiloint2double(w.y, w.x), xs[w.z] * xs[w.w], fit);
+                        }
+                    }
+                } else if (NF <= 2) {
                     for (int t = 0; t < nnz; ++t) {
-                        const int4 w = __ldg(reinterpret_cast<const int4*>(r + t));  // {val, o32[0], o32[1]}
-                        const double v = __hiloint2double(w.y, w.x);
-                        fit = fma(v, xs[w.z] * xs[w.w], fit);
+                        const int4 w = __ldg(reinterpret_cast<const int4*>(r + t));
+                        fit = fma(__hiloint2double(w.y, w.x), xs[w.z] * xs[w.w], fit);
                     }
                 } else {
                     for (int t = 0; t < nnz; ++t) {
-                        const int4 w = __ldg(reinterpret_cast<const int4*>(r + t));
-                        const int4 o = __ldg(reinterpret_cast<const int4*>(r + t) + 1);  // 8 x uint16 rows
+                        const int4 w = SMEM_TERMS ? *reinterpret_cast<const int4*>(r + t) : __ldg(reinterpret_cast<const int4*>(r + t));
+                        const int4 o = SMEM_TERMS ? *(reinterpret_cast<const int4*>(r + t) + 1)
+                                                  : __ldg(reinterpret_cast<const int4*>(r + t) + 1);  // 8 x uint16 rows
                         double p = xs[w.z] * xs[w.w];
                         const uint32_t ow[4] = {(uint32_t)o.x, (uint32_t)o.y, (uint32_t)o.z, (uint32_t)o.w};
 #pragma unroll
@@ -185,8 +184,82 @@ __global__ void __launch_bounds__(kRssWarps * 32) rss_kernel(const RssArgs a) {
                 acc[q] = fma(res, res, acc[q]);
             }
         }
-        __syncthreads();  // everyone is done with buf[cur] before it is refilled two iterations later
+        __syncthreads();  // everyone is done with this buffer before it is refilled two iterations later
     }
+}
+
+template <int NF>
+__global__ void __launch_bounds__(kRssWarps * 32) rss_kernel(const RssArgs a) {
+    extern __shared__ double sm[];
+    const int rows = a.n + a.n_t + 1;  // + the row of ones
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cbase = blockIdx.y * (kRssWarps * kRssAcc);
+    // this CTA's sample range (whole tiles)
+    const int64_t ntiles = (a.m + kRssTile - 1) / kRssTile;
+    const int64_t t_lo = ntiles * blockIdx.x / gridDim.x, t_hi = ntiles * (blockIdx.x + 1) / gridDim.x;
+    if (threadIdx.x < 2 * kRssPitch)
+        sm[(threadIdx.x / kRssPitch) * rows * kRssPitch + (rows - 1) * kRssPitch + threadIdx.x % kRssPitch] = 1.0;
+
+    // candidates of this warp: cbase + warp + 8 * slot
+    int nslots = 0;
+    for (int q = 0; q < kRssAcc; ++q)
+        if (cbase + warp + kRssWarps * q < a.ncand) nslots = q + 1;
+    // The candidates' metadata and term records are the same for every tile: they are copied into shared
+    // memory once (when they fit), so the inner loop's dependent loads are shared-memory latency, not L2.
+    int4* s_meta = reinterpret_cast<int4*>(sm + 2 * (size_t)rows * kRssPitch);  // [256] {local term offset, nnz, eq, -}
+    RssTerm* s_terms = reinterpret_cast<RssTerm*>(s_meta + kRssWarps * kRssAcc);
+    __shared__ int s_scan[kRssWarps];
+    __shared__ int s_total;
+    {
+        const int lc = threadIdx.x;  // local candidate id: warp w, slot q  <->  lc = w + 8 q
+        const int c = cbase + lc;
+        const int nnz = c < a.ncand ? a.cand_nnz[c] : 0;
+        // shared-memory mode: every candidate's record list is padded to a multiple of 4 (padding records have
+        // coefficient 0 and read the row of ones), so the term loop runs in branch-free groups of four
+        const int n4 = (nnz + 3) & ~3;
+        int v = n4;  // inclusive block scan of the padded counts -> offsets
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += t;
+        }
+        if (lane == 31) s_scan[warp] = v;
+        __syncthreads();
+        int base = 0, total = 0;
+        for (int w = 0; w < kRssWarps; ++w) {
+            if (w < warp) base += s_scan[w];
+            total += s_scan[w];
+        }
+        if (threadIdx.x == 0) s_total = total;
+        const int loff = base + v - n4;
+        // degree <= 2 keeps only the first 16 bytes of a record ({val, o32[0], o32[1]}): twice the capacity
+        constexpr int kRec = NF <= 2 ? 1 : 2;  // int4 per record
+        const bool fits = (int64_t)total * kRec <= (int64_t)a.term_cap * 2;
+        s_meta[lc] = make_int4(loff, nnz, c < a.ncand ? a.cand_eq[c] : 0, n4);
+        if (fits) {
+            RssTerm pad;
+            pad.val = 0.0;
+            pad.o32[0] = pad.o32[1] = (rows - 1) * kRssPitch;
+#pragma unroll
+            for (int d = 0; d < kMaxFactors; ++d) pad.o16[d] = (uint16_t)(rows - 1);
+            const RssTerm* src = c < a.ncand ? a.terms + a.cand_off[c] : nullptr;
+            int4* dst = reinterpret_cast<int4*>(s_terms) + (size_t)loff * kRec;
+            for (int t = 0; t < n4; ++t) {
+                const RssTerm rec = (t < nnz) ? src[t] : pad;
+                const int4* p = reinterpret_cast<const int4*>(&rec);
+                dst[t * kRec] = p[0];
+                if (kRec == 2) dst[t * kRec + 1] = p[1];
+            }
+        }
+        __syncthreads();
+    }
+    const int tp = s_total;
+    double acc[kRssAcc];
+#pragma unroll
+    for (int q = 0; q < kRssAcc; ++q) acc[q] = 0.0;
+    if ((int64_t)tp * (NF <= 2 ? 1 : 2) <= (int64_t)a.term_cap * 2)
+        rss_tiles<NF, true>(a, sm, s_meta, s_terms, nslots, cbase, t_lo, t_hi, tp, acc);
+    else
+        rss_tiles<NF, false>(a, sm, s_meta, s_terms, nslots, cbase, t_lo, t_hi, tp, acc);
     // lanes hold per-sample-slot partial sums: fixed shuffle tree, then one write per candidate
 #pragma unroll
     for (int q = 0; q < kRssAcc; ++q) {
@@ -265,11 +338,16 @@ static int rss_core(ddb_ctx* ctx, const RssCand& c, const int32_t* map, const Rs
     a.terms = terms.as<RssTerm>();
     a.targets = targets;
     a.partials = partials.as<double>();
-    const size_t smem = 2 * (size_t)kRssPitch * (ctx->n + ctx->n_t + 1) * sizeof(double);
-    if (smem > 200 * 1024) {
+    const size_t smem_tiles = 2 * (size_t)kRssPitch * (ctx->n + ctx->n_t + 1) * sizeof(double);
+    if (smem_tiles > 180 * 1024) {
         set_error("ddb_rss: n + n_t too large for the shared-memory sample tile");
         return DDB_UNSUPPORTED;
     }
+    // candidate metadata + as many term records as keep two CTAs per SM (about 112 KB each)
+    const size_t smem_meta = (size_t)kRssWarps * kRssAcc * sizeof(int4);
+    const size_t budget = smem_tiles + smem_meta < 112 * 1024 ? 112 * 1024 - smem_tiles - smem_meta : 0;
+    a.term_cap = (int)std::min<size_t>(budget / sizeof(RssTerm), 1u << 15);
+    const size_t smem = smem_tiles + smem_meta + (size_t)a.term_cap * sizeof(RssTerm);
     auto kern = ctx->max_degree <= 2 ? rss_kernel<2> : rss_kernel<kMaxFactors>;
     DDB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<dim3(nparts, passes), kRssWarps * 32, smem, st>>>(a);

@@ -160,7 +160,7 @@ int64_t ddb_gram_count(const ddb_ctx* ctx);
 int ddb_gram(ddb_ctx* ctx, double* dPacked);
 
 /* ddb_upload + ddb_gram in one call with the host->device copies OVERLAPPED by the Gram kernels: the samples
- * are cut into chunks (<= 16, ~512 MB each), chunk c + 1 travels on a copy stream while the kernels run on
+ * are cut into chunks (<= 16, >= ~64 MB each), chunk c + 1 travels on a copy stream while the kernels run on
  * chunk c, and the per-chunk blocks are added in chunk order (deterministic).  The data stay resident as
  * after ddb_upload.  Pass page-locked host buffers for a real overlap (pageable memory still works, the
  * copies then serialise).  This is what ddb_solve_sparse uses. */
