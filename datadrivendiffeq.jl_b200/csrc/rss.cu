@@ -16,6 +16,10 @@
 // HBM-bound when the candidates are sparse: algorithmic bytes = 8 (n + n_t) per sample.
 #include "common.cuh"
 #include "sweep.cuh"
+#include <cmath>
+#include <cstdlib>
+#include <string>
+#include <unordered_map>
 
 namespace ddb {
 
@@ -357,6 +361,39 @@ static int rss_core(ddb_ctx* ctx, const RssCand& c, const int32_t* map, const Rs
     return DDB_OK;
 }
 
+// Candidates of one target that share a support S (ADMM and SR3 record one per iteration: thousands on one
+// support) are not streamed one by one.  For a reference point c0 on S,
+//     rss(c) = rss(c0) - 2 d' g0 + d' G_SS d,      d = c - c0,   g0 = r_S - G_SS c0,
+// and with c0 = the least-squares solution on S the cross term vanishes up to rounding: rss(c) is a SUM of
+// two non-negative terms, so there is no cancellation (unlike y'y - 2 c'r + c'Gc).  Only c0 is streamed
+// (exactly, sample by sample); the small terms come from the Gram blocks in extended precision on the host.
+// This is also more accurate than streaming c itself when the fit is nearly exact (the per-sample residual
+// y - c'theta then loses its leading digits).  Supports of more than kGroupMax terms and singletons are
+// streamed directly.
+constexpr int kGroupMax = 16;
+
+__global__ void gather_gss_kernel(const double* __restrict__ packed, int k, int n_t, const int32_t* __restrict__ gidx,
+                                  const int32_t* __restrict__ gsize, const int32_t* __restrict__ geq,
+                                  double* __restrict__ out) {
+    // group g: out[g] = [G_SS (kGroupMax x kGroupMax, row-major) | r_S (kGroupMax)]
+    const int g = blockIdx.x;
+    const int s = gsize[g], e = geq[g];
+    const int32_t* idx = gidx + (size_t)g * kGroupMax;
+    double* o = out + (size_t)g * (kGroupMax * kGroupMax + kGroupMax);
+    const double* R = packed + (size_t)k * k;
+    for (int t = threadIdx.x; t < s * s; t += blockDim.x) {
+        const int i = t / s, j = t % s;
+        o[i * kGroupMax + j] = packed[(size_t)idx[i] + (size_t)k * idx[j]];
+    }
+    for (int i = threadIdx.x; i < s; i += blockDim.x) o[kGroupMax * kGroupMax + i] = R[(size_t)idx[i] + (size_t)k * e];
+}
+
+__global__ void scatter_group_rss_kernel(const double* __restrict__ rep, const int32_t* __restrict__ group, int ncand,
+                                         double* __restrict__ rss) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < ncand) rss[c] = rep[group[c]];
+}
+
 int rss_run(ddb_ctx* ctx, SweepState* S, double* dRss) {
     const int ncand = S->ncand;
     const bool implicit = ctx->imp_k > 0;
@@ -365,6 +402,7 @@ int rss_run(ddb_ctx* ctx, SweepState* S, double* dRss) {
         DDB_TRY(S->rss.reserve((size_t)std::max(1, ncand) * 8));
         dRss = S->rss.as<double>();
     }
+    DDB_TRY(S->rss_corr.reserve((size_t)std::max(1, ncand) * 8));
     DDB_CUDA_TRY(cudaEventRecord(ctx->ev[4], st));
     int launches = 0;
     if (implicit) {  // one record per target: the library term on the left-hand side
@@ -374,11 +412,209 @@ int rss_run(ddb_ctx* ctx, SweepState* S, double* dRss) {
                                                                    S->tgt_terms.as<RssTerm>());
         ++launches;
     }
-    RssCand c{ncand, S->pool_used, S->cand_off.as<int64_t>(), S->cand_nnz.as<int32_t>(), S->cand_eq.as<int32_t>(),
-              S->cand_idx.as<int32_t>(), S->cand_val.as<double>()};
+    const int32_t* map = implicit ? ctx->imp_idx.as<int32_t>() : nullptr;
+    const RssTerm* targets = implicit ? S->tgt_terms.as<RssTerm>() : nullptr;
     const double* scale = (!implicit && ctx->term_scale_on) ? ctx->d_term_scale.as<double>() : nullptr;
-    DDB_TRY(rss_core(ctx, c, implicit ? ctx->imp_idx.as<int32_t>() : nullptr, implicit ? S->tgt_terms.as<RssTerm>() : nullptr,
-                     scale, S->cand_terms, S->rss_partials, dRss, &launches));
+
+    // ---- group the candidates by (target, support) -----------------------------------------------
+    const int64_t nterms = S->pool_used;
+    const char* genv = getenv("DDB_RSS_GROUPING");
+    const bool grouping = !(genv && atoi(genv) == 0) && ncand > 2 * S->n_t && nterms > 0;
+    if (!grouping) {
+        DDB_CUDA_TRY(cudaMemsetAsync(S->rss_corr.p, 0, (size_t)std::max(1, ncand) * 8, st));
+        RssCand c{ncand, nterms, S->cand_off.as<int64_t>(), S->cand_nnz.as<int32_t>(), S->cand_eq.as<int32_t>(),
+                  S->cand_idx.as<int32_t>(), S->cand_val.as<double>()};
+        DDB_TRY(rss_core(ctx, c, map, targets, scale, S->cand_terms, S->rss_partials, dRss, &launches));
+    } else {
+        std::vector<int64_t> off(ncand);
+        std::vector<int32_t> nnz(ncand), eq(ncand), idx((size_t)nterms);
+        std::vector<double> val((size_t)nterms);
+        DDB_CUDA_TRY(cudaMemcpyAsync(off.data(), S->cand_off.p, (size_t)ncand * 8, cudaMemcpyDeviceToHost, st));
+        DDB_CUDA_TRY(cudaMemcpyAsync(nnz.data(), S->cand_nnz.p, (size_t)ncand * 4, cudaMemcpyDeviceToHost, st));
+        DDB_CUDA_TRY(cudaMemcpyAsync(eq.data(), S->cand_eq.p, (size_t)ncand * 4, cudaMemcpyDeviceToHost, st));
+        DDB_CUDA_TRY(cudaMemcpyAsync(idx.data(), S->cand_idx.p, (size_t)nterms * 4, cudaMemcpyDeviceToHost, st));
+        DDB_CUDA_TRY(cudaMemcpyAsync(val.data(), S->cand_val.p, (size_t)nterms * 8, cudaMemcpyDeviceToHost, st));
+        DDB_CUDA_TRY(cudaStreamSynchronize(st));
+        // groups: key = (target, support); a group is "shared" when it has >= 2 members and 1..kGroupMax terms
+        std::unordered_map<std::string, int> key2group;
+        std::vector<int32_t> group(ncand);
+        std::vector<int> first, members;  // first member and member count per group
+        std::string key;
+        for (int c = 0; c < ncand; ++c) {
+            key.assign(reinterpret_cast<const char*>(&eq[c]), 4);
+            key.append(reinterpret_cast<const char*>(idx.data() + off[c]), (size_t)nnz[c] * 4);
+            auto it = key2group.find(key);
+            if (it == key2group.end()) {
+                it = key2group.emplace(key, (int)first.size()).first;
+                first.push_back(c);
+                members.push_back(0);
+            }
+            group[c] = it->second;
+            ++members[it->second];
+        }
+        // split groups that cannot use the identity back into singletons
+        const int ng0 = (int)first.size();
+        std::vector<char> shared(ng0);
+        int nshared = 0;
+        for (int g = 0; g < ng0; ++g) {
+            shared[g] = members[g] >= 2 && nnz[first[g]] >= 1 && nnz[first[g]] <= kGroupMax;
+            nshared += shared[g];
+        }
+        // representative list: shared groups first (one each), then every other candidate on its own
+        std::vector<int> gslot(ng0, -1);
+        std::vector<int32_t> g_idx((size_t)std::max(1, nshared) * kGroupMax, 0), g_size(std::max(1, nshared)), g_eq(std::max(1, nshared));
+        int ns = 0;
+        for (int g = 0; g < ng0; ++g)
+            if (shared[g]) {
+                gslot[g] = ns;
+                const int c = first[g];
+                g_size[ns] = nnz[c];
+                g_eq[ns] = eq[c];
+                for (int t = 0; t < nnz[c]; ++t) g_idx[(size_t)ns * kGroupMax + t] = idx[off[c] + t];
+                ++ns;
+            }
+        // G_SS and r_S of the shared groups (in the space the sweep ran in: scaled blocks when a term
+        // normalisation is on, the gathered sub-blocks in implicit mode)
+        const int kk = implicit ? ctx->imp_k : ctx->k, ntt = implicit ? ctx->imp_k : ctx->n_t;
+        const double* packed = implicit ? ctx->imp_packed.as<double>() : ctx->d_packed.as<double>();
+        const size_t gstride = kGroupMax * kGroupMax + kGroupMax;
+        std::vector<double> gss((size_t)std::max(1, ns) * gstride);
+        if (ns > 0) {
+            const size_t b_idx = (size_t)ns * kGroupMax * 4, b_sz = (size_t)ns * 4;
+            const size_t o_sz = (b_idx + 7) & ~size_t(7), o_eq = (o_sz + b_sz + 7) & ~size_t(7), o_out = (o_eq + b_sz + 7) & ~size_t(7);
+            DDB_TRY(S->grp_buf.reserve(o_out + (size_t)ns * gstride * 8));
+            unsigned char* gb = static_cast<unsigned char*>(S->grp_buf.p);
+            DDB_CUDA_TRY(cudaMemcpyAsync(gb, g_idx.data(), b_idx, cudaMemcpyHostToDevice, st));
+            DDB_CUDA_TRY(cudaMemcpyAsync(gb + o_sz, g_size.data(), b_sz, cudaMemcpyHostToDevice, st));
+            DDB_CUDA_TRY(cudaMemcpyAsync(gb + o_eq, g_eq.data(), b_sz, cudaMemcpyHostToDevice, st));
+            gather_gss_kernel<<<ns, 256, 0, st>>>(packed, kk, ntt, reinterpret_cast<const int32_t*>(gb),
+                                                  reinterpret_cast<const int32_t*>(gb + o_sz),
+                                                  reinterpret_cast<const int32_t*>(gb + o_eq),
+                                                  reinterpret_cast<double*>(gb + o_out));
+            ++launches;
+            DDB_CUDA_TRY(cudaMemcpyAsync(gss.data(), gb + o_out, (size_t)ns * gstride * 8, cudaMemcpyDeviceToHost, st));
+            DDB_CUDA_TRY(cudaStreamSynchronize(st));
+        }
+        // least-squares reference point per shared group (Cholesky in extended precision), corrections
+        std::vector<double> corr(ncand, 0.0), c0((size_t)std::max(1, ns) * kGroupMax, 0.0);
+        std::vector<long double> g0((size_t)std::max(1, ns) * kGroupMax, 0.0L);
+        for (int g = 0; g < ng0; ++g) {
+            if (!shared[g]) continue;
+            const int q = gslot[g], s = g_size[q];
+            const double* Gs = gss.data() + (size_t)q * gstride;
+            const double* rS = Gs + kGroupMax * kGroupMax;
+            long double L[kGroupMax][kGroupMax], z[kGroupMax];
+            bool ok = true;
+            for (int i = 0; i < s && ok; ++i)
+                for (int j = 0; j <= i; ++j) {
+                    long double a = Gs[i * kGroupMax + j];
+                    for (int t = 0; t < j; ++t) a -= L[i][t] * L[j][t];
+                    if (i == j) {
+                        if (!(a > 0.0L)) {
+                            ok = false;
+                            break;
+                        }
+                        L[i][i] = sqrtl(a);
+                    } else {
+                        L[i][j] = a / L[j][j];
+                    }
+                }
+            if (!ok) {  // singular sub-block: stream every member directly
+                shared[g] = 0;
+                continue;
+            }
+            for (int i = 0; i < s; ++i) {
+                long double a = rS[i];
+                for (int t = 0; t < i; ++t) a -= L[i][t] * z[t];
+                z[i] = a / L[i][i];
+            }
+            for (int i = s - 1; i >= 0; --i) {
+                long double a = z[i];
+                for (int t = i + 1; t < s; ++t) a -= L[t][i] * z[t];
+                z[i] = a / L[i][i];
+            }
+            for (int i = 0; i < s; ++i) c0[(size_t)q * kGroupMax + i] = (double)z[i];
+            for (int i = 0; i < s; ++i) {  // g0 = r_S - G_SS c0 with the ROUNDED c0 that is streamed
+                long double a = rS[i];
+                for (int j = 0; j < s; ++j) a -= (long double)Gs[i * kGroupMax + j] * (long double)c0[(size_t)q * kGroupMax + j];
+                g0[(size_t)q * kGroupMax + i] = a;
+            }
+        }
+        // representatives: shared groups (their c0), then all remaining candidates
+        std::vector<int64_t> r_off;
+        std::vector<int32_t> r_nnz, r_eq, r_idx;
+        std::vector<double> r_val;
+        std::vector<int> rep_of_group(ng0, -1);
+        for (int g = 0; g < ng0; ++g) {
+            if (!shared[g]) continue;
+            const int q = gslot[g], s = g_size[q];
+            rep_of_group[g] = (int)r_off.size();
+            r_off.push_back((int64_t)r_idx.size());
+            r_nnz.push_back(s);
+            r_eq.push_back(g_eq[q]);
+            for (int t = 0; t < s; ++t) {
+                r_idx.push_back(g_idx[(size_t)q * kGroupMax + t]);
+                r_val.push_back(c0[(size_t)q * kGroupMax + t]);
+            }
+        }
+        std::vector<int32_t> rep(ncand);
+        for (int c = 0; c < ncand; ++c) {
+            const int g = group[c];
+            if (shared[g]) {
+                rep[c] = rep_of_group[g];
+                const int q = gslot[g], s = g_size[q];
+                const double* Gs = gss.data() + (size_t)q * gstride;
+                long double d[kGroupMax], acc = 0.0L;
+                for (int t = 0; t < s; ++t) d[t] = (long double)val[off[c] + t] - (long double)c0[(size_t)q * kGroupMax + t];
+                for (int i = 0; i < s; ++i) {
+                    long double gd = 0.0L;
+                    for (int j = 0; j < s; ++j) gd += (long double)Gs[i * kGroupMax + j] * d[j];
+                    acc += d[i] * (gd - 2.0L * g0[(size_t)q * kGroupMax + i]);
+                }
+                corr[c] = (double)acc;
+            } else {
+                rep[c] = (int)r_off.size();
+                r_off.push_back((int64_t)r_idx.size());
+                r_nnz.push_back(nnz[c]);
+                r_eq.push_back(eq[c]);
+                for (int t = 0; t < nnz[c]; ++t) {
+                    r_idx.push_back(idx[off[c] + t]);
+                    r_val.push_back(val[off[c] + t]);
+                }
+            }
+        }
+        const int nrep = (int)r_off.size();
+        const int64_t rterms = (int64_t)r_idx.size();
+        const size_t o_nnz = (size_t)nrep * 8, o_eq = o_nnz + (size_t)nrep * 4, o_idx = (o_eq + (size_t)nrep * 4 + 7) & ~size_t(7);
+        const size_t o_val = (o_idx + (size_t)std::max<int64_t>(1, rterms) * 4 + 7) & ~size_t(7);
+        const size_t o_rep = o_val + (size_t)std::max<int64_t>(1, rterms) * 8;
+        const size_t o_map = o_rep + (size_t)nrep * 8;
+        DDB_TRY(S->rep_buf.reserve(o_map + (size_t)ncand * 4));
+        unsigned char* rb = static_cast<unsigned char*>(S->rep_buf.p);
+        DDB_CUDA_TRY(cudaMemcpyAsync(rb, r_off.data(), (size_t)nrep * 8, cudaMemcpyHostToDevice, st));
+        DDB_CUDA_TRY(cudaMemcpyAsync(rb + o_nnz, r_nnz.data(), (size_t)nrep * 4, cudaMemcpyHostToDevice, st));
+        DDB_CUDA_TRY(cudaMemcpyAsync(rb + o_eq, r_eq.data(), (size_t)nrep * 4, cudaMemcpyHostToDevice, st));
+        if (rterms) {
+            DDB_CUDA_TRY(cudaMemcpyAsync(rb + o_idx, r_idx.data(), (size_t)rterms * 4, cudaMemcpyHostToDevice, st));
+            DDB_CUDA_TRY(cudaMemcpyAsync(rb + o_val, r_val.data(), (size_t)rterms * 8, cudaMemcpyHostToDevice, st));
+        }
+        DDB_CUDA_TRY(cudaMemcpyAsync(rb + o_map, rep.data(), (size_t)ncand * 4, cudaMemcpyHostToDevice, st));
+        DDB_CUDA_TRY(cudaMemcpyAsync(S->rss_corr.p, corr.data(), (size_t)ncand * 8, cudaMemcpyHostToDevice, st));
+        RssCand c{nrep, rterms, reinterpret_cast<const int64_t*>(rb), reinterpret_cast<const int32_t*>(rb + o_nnz),
+                  reinterpret_cast<const int32_t*>(rb + o_eq), reinterpret_cast<const int32_t*>(rb + o_idx),
+                  reinterpret_cast<const double*>(rb + o_val)};
+        DDB_TRY(rss_core(ctx, c, map, targets, scale, S->cand_terms, S->rss_partials, reinterpret_cast<double*>(rb + o_rep), &launches));
+        scatter_group_rss_kernel<<<(ncand + 255) / 256, 256, 0, st>>>(reinterpret_cast<const double*>(rb + o_rep),
+                                                                      reinterpret_cast<const int32_t*>(rb + o_map), ncand, dRss);
+        ++launches;
+        DDB_CUDA_TRY(cudaGetLastError());
+        DDB_CUDA_TRY(cudaStreamSynchronize(st));  // the host vectors above are stack-lifetime
+        ctx->timings.candidates = ncand;
+        S->nstreamed = nrep;
+        if (getenv("DDB_RSS_DEBUG"))
+            fprintf(stderr, "rss grouping: %d candidates (%lld terms) -> %d streamed (%lld terms), %d shared groups\n", ncand,
+                    (long long)nterms, nrep, (long long)rterms, ns);
+    }
     DDB_CUDA_TRY(cudaEventRecord(ctx->ev[5], st));
     DDB_CUDA_TRY(cudaStreamSynchronize(st));
     float ms = 0.f;

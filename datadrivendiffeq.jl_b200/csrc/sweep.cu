@@ -986,8 +986,10 @@ __device__ __forceinline__ double score_of(int selector, double rss, int dof, do
     return aic + (2.0 * dof * (dof + 1.0)) / (nobs - dof - 1.0);
 }
 
-__global__ void __launch_bounds__(256) select_kernel(SweepDev S, const double* __restrict__ rss, int selector,
-                                                     double nobs, double* coef /* n_t x k col-major */,
+// rss[c] = streamed value of candidate c's group representative (summed over ranks on the sharded path);
+// corr[c] = the exact quadratic correction of rss.cu (zero for candidates that were streamed themselves)
+__global__ void __launch_bounds__(256) select_kernel(SweepDev S, const double* __restrict__ rss_rep,
+                                                     const double* __restrict__ corr, int selector, double nobs, double* coef /* n_t x k col-major */,
                                                      double* lambda_opt, int32_t* iters, double* rss_out,
                                                      int32_t* dof_out, int32_t* flags) {
     const int e = blockIdx.x;
@@ -995,15 +997,19 @@ __global__ void __launch_bounds__(256) select_kernel(SweepDev S, const double* _
     __shared__ int s_best;
     __shared__ int s_bestj;
     const EqState& st = S.eq[e];
+    auto rss = [&](int c) -> double {
+        const double v = rss_rep[c] + corr[c];
+        return v > 0.0 ? v : 0.0;
+    };
     if (threadIdx.x == 0) {
         int best = e;  // zero model
         int bestj = 0;
-        double best_score = score_of(selector, rss[e], S.cand_dof[e], nobs);
+        double best_score = score_of(selector, rss(e), S.cand_dof[e], nobs);
         for (int r = 0; r < st.nruns; ++r) {
             const int c = S.run_cand[(size_t)e * S.run_cap + r];
             const int jfirst = S.run_jfirst[(size_t)e * S.run_cap + r];
             const int jlast = S.run_j[(size_t)e * S.run_cap + r];
-            const double sc = score_of(selector, rss[c], S.cand_dof[c], nobs);
+            const double sc = score_of(selector, rss(c), S.cand_dof[c], nobs);
             // A run is a maximal sequence of steps whose cache content did not change.  Its first step is
             // taken unconditionally when it belongs to the first threshold (`j == 1` in the reference),
             // otherwise iff score <= best; once taken, the remaining steps of the run tie with themselves
@@ -1018,7 +1024,7 @@ __global__ void __launch_bounds__(256) select_kernel(SweepDev S, const double* _
         s_bestj = bestj;
         if (lambda_opt) lambda_opt[e] = S.lambdas[bestj < S.L ? bestj : S.L - 1];
         if (iters) iters[e] = st.counter;
-        if (rss_out) rss_out[e] = rss[best];
+        if (rss_out) rss_out[e] = rss(best);
         if (dof_out) dof_out[e] = S.cand_dof[best];
         if (flags) flags[e] = st.flags;
     }
@@ -1045,7 +1051,7 @@ void SweepState::release_all() {
                      &cand_val, &cand_off, &cand_nnz, &cand_dof, &cand_eq, &counters, &pool_used_d, &run_cand,
                      &run_jfirst, &run_j, &path_support, &path_coef, &path_iters, &big_ws, &big_idx, &big_na,
                      &big_list, &big_fail, &active_matrix, &shared_fail, &rss, &rss_partials, &out_tmp, &cand_terms,
-                     &Ninv, &tgt_terms};
+                     &Ninv, &tgt_terms, &rss_corr, &grp_buf, &rep_buf};
     for (DevBuf* b : all) b->release();
 }
 
@@ -1339,7 +1345,7 @@ int select_run(ddb_ctx* ctx, double* coef, double* lambda_opt, int32_t* iters, d
     int32_t* d_fl = d_dof + n_t;
     DDB_CUDA_TRY(cudaEventRecord(ctx->ev[4], st));
     SweepDev D = make_dev(ctx, S);
-    select_kernel<<<n_t, 256, 0, st>>>(D, S->rss_ptr, S->prm.selector, (double)S->m_total, d_coef, d_lam, d_it, d_rss,
+    select_kernel<<<n_t, 256, 0, st>>>(D, S->rss_ptr, S->rss_corr.as<double>(), S->prm.selector, (double)S->m_total, d_coef, d_lam, d_it, d_rss,
                                        d_dof, d_fl);
     DDB_CUDA_TRY(cudaGetLastError());
     DDB_CUDA_TRY(cudaEventRecord(ctx->ev[5], st));
