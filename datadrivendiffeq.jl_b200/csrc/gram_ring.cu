@@ -511,7 +511,8 @@ int gram_ring_run(ddb_ctx* ctx, double* dPacked, bool* handled) {
     const int k = ctx->k, n = ctx->n, n_t = ctx->n_t, kaug = k + n_t;
     const int nblk = (kaug + kRingBT - 1) / kRingBT;
     const int krow = nblk * kRingBT;
-    const int nprod = 4;
+    int nprod = 4;
+    if (const char* e = getenv("DDB_RING_NPROD")) nprod = std::max(1, std::min(kMaxProducers, atoi(e)));  // tuning knob
     const int ncons = ctx->sm_count - nprod;
     const int npairs = nblk * (nblk + 1) / 2;
     // eligible when every consumer SM gets work for the whole stream, the producer can hold its terms in

@@ -359,6 +359,7 @@ struct SweepDev {
     double* aux1;           // n_t x k  (ADMM alpha / SR3 W)
     double* aux2;           // n_t x k  (ADMM w)
     double* znew;           // n_t x k  solve results (scaled unknowns) for the global-memory paths
+    const double* zsol;     // n_t x k  where relax_finish reads the solved systems (znew, or the product with Ninv)
     uint32_t* active;       // n_t x W
     EqState* eq;            // n_t
     // candidates
@@ -549,7 +550,7 @@ __global__ void implicit_prep_kernel(double* __restrict__ Ninv, double* __restri
     if (t >= (size_t)k * k) return;
     const int e = (int)(t / k), i = (int)(t % k);
     Ninv[t] = (e == i) ? 1.0 : 0.0;
-    if (e == i) z[t] = 0.0;
+    if (z && e == i) z[t] = 0.0;
 }
 
 // implicit view: packed' = [G[idx, idx] | G[idx, idx] | diag] from the full packed blocks
@@ -898,6 +899,45 @@ __global__ void __launch_bounds__(256) relax_rhs_kernel(SweepDev S, int* active_
     }
 }
 
+// ADMM / SR3 with a large library: every iteration solves the SAME matrix for all running targets.  One CTA
+// per right-hand side streaming the whole factor (chol_solve_kernel) is bound by the L2 rate of a single SM
+// (37 MB per solve at k = 2145); with the inverse of the equilibrated matrix formed once per sweep the
+// iteration is a product  Zsol (n_t x k) = Z * Ninv  that reads Ninv once for all targets.
+// CTA tile: 64 targets x 16 columns, K in chunks of 32 through shared memory; grid (ceil(k/16), ceil(n_t/64)).
+__global__ void __launch_bounds__(256) ninv_apply_kernel(const double* __restrict__ Ninv, int k, const double* __restrict__ Z,
+                                                         int n_t, const int* __restrict__ active, double* __restrict__ Zsol) {
+    __shared__ double zs[64][33];
+    __shared__ double ns[32][17];
+    const int tid = threadIdx.x;
+    const int c0 = blockIdx.x * 16, e0 = blockIdx.y * 64;
+    const int te = tid >> 2, tc = (tid & 3) * 4;  // this thread: target e0 + te, columns c0 + tc .. + 3
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int k0 = 0; k0 < k; k0 += 32) {
+        for (int q = tid; q < 64 * 32; q += 256) {
+            const int e = q >> 5, kk = q & 31;
+            zs[e][kk] = (e0 + e < n_t && k0 + kk < k) ? Z[(size_t)(e0 + e) * k + k0 + kk] : 0.0;
+        }
+        for (int q = tid; q < 32 * 16; q += 256) {
+            const int kk = q >> 4, c = q & 15;
+            ns[kk][c] = (k0 + kk < k && c0 + c < k) ? Ninv[(size_t)(k0 + kk) * k + c0 + c] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int kk = 0; kk < 32; ++kk) {
+            const double z = zs[te][kk];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j] = fma(z, ns[kk][tc + j], acc[j]);
+        }
+        __syncthreads();
+    }
+    const int e = e0 + te;
+    if (e < n_t && active[e]) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (c0 + tc + j < k) Zsol[(size_t)e * k + c0 + tc + j] = acc[j];
+    }
+}
+
 __device__ __forceinline__ double soft(double v, double lam) {
     const double a = fabs(v) - lam;
     const double sgn = (v > 0.0) ? 1.0 : ((v < 0.0) ? -1.0 : 0.0);
@@ -913,7 +953,7 @@ __global__ void __launch_bounds__(256) relax_finish_kernel(SweepDev S) {
     EqState& st = S.eq[e];
     if (st.status != kEqRunning) return;
     double* x = S.x + (size_t)e * k;
-    const double* z = S.znew + (size_t)e * k;
+    const double* z = S.zsol + (size_t)e * k;
     const double lam = S.lambdas[st.j];
     // implicit mode: row/column e deleted from the system through the rank-one correction (see SweepDev)
     const double corr = S.implicit ? z[e] / S.Ninv[(size_t)e * k + e] : 0.0;
@@ -1051,7 +1091,7 @@ void SweepState::release_all() {
                      &cand_val, &cand_off, &cand_nnz, &cand_dof, &cand_eq, &counters, &pool_used_d, &run_cand,
                      &run_jfirst, &run_j, &path_support, &path_coef, &path_iters, &big_ws, &big_idx, &big_na,
                      &big_list, &big_fail, &active_matrix, &shared_fail, &rss, &rss_partials, &out_tmp, &cand_terms,
-                     &Ninv, &tgt_terms, &rss_corr, &grp_buf, &rep_buf};
+                     &Ninv, &tgt_terms, &rss_corr, &grp_buf, &rep_buf, &zsol};
     for (DevBuf* b : all) b->release();
 }
 
@@ -1089,6 +1129,7 @@ static SweepDev make_dev(ddb_ctx* ctx, SweepState* S) {
     D.aux1 = S->prm.algorithm == DDB_ALG_STLSQ ? nullptr : S->aux1.as<double>();
     D.aux2 = S->prm.algorithm == DDB_ALG_ADMM ? S->aux2.as<double>() : nullptr;
     D.znew = S->znew.as<double>();
+    D.zsol = D.znew;
     D.active = S->active.as<uint32_t>();
     D.eq = S->eq.as<EqState>();
     D.cand_idx = S->cand_idx.as<int32_t>();
@@ -1214,15 +1255,20 @@ int sweep_run(ddb_ctx* ctx, const ddb_sweep_params* prm, const double* lambdas, 
     }
     DDB_CUDA_TRY(cudaFuncSetAttribute(chol_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
     const bool shared_factor = !(implicit && prm->algorithm == DDB_ALG_STLSQ);  // see sweep_init_kernel
+    // ADMM / SR3 iterations through the explicit inverse when the library is large (see ninv_apply_kernel)
+    const char* ienv = getenv("DDB_SWEEP_INVERSE");
+    const bool use_inverse = prm->algorithm != DDB_ALG_STLSQ && (ienv ? atoi(ienv) != 0 : k >= 256);
+    if (use_inverse) DDB_TRY(S->zsol.reserve(nk * 8));
     if (shared_factor) {
         DDB_CUDA_TRY(cudaMemcpyAsync(S->Lfac.p, S->As.p, kk * 8, cudaMemcpyDeviceToDevice, st));
         DDB_TRY(chol_batched(ctx, S->Lfac.as<double>(), 0, k, nullptr, k, 1, S->shared_fail.as<int>(), &launches));
         DDB_CUDA_TRY(cudaMemcpyAsync(S->znew.p, S->rs.p, nk * 8, cudaMemcpyDeviceToDevice, st));
-        if (implicit) {
-            // inverse of the equilibrated matrix (identity right-hand sides) and the own entry of every
-            // target's right-hand side zeroed before the shared full solve
+        if (implicit || use_inverse) {
+            // inverse of the equilibrated matrix (identity right-hand sides); implicit mode also zeroes the own
+            // entry of every target's right-hand side before the shared full solve
             DDB_TRY(S->Ninv.reserve(kk * 8));
-            implicit_prep_kernel<<<(unsigned)((kk + 255) / 256), 256, 0, st>>>(S->Ninv.as<double>(), S->znew.as<double>(), k);
+            implicit_prep_kernel<<<(unsigned)((kk + 255) / 256), 256, 0, st>>>(S->Ninv.as<double>(),
+                                                                               implicit ? S->znew.as<double>() : nullptr, k);
             chol_solve_kernel<<<dim3(k, 1), 256, solve_smem, st>>>(S->Lfac.as<double>(), 0, k, nullptr, k,
                                                                    S->Ninv.as<double>(), (size_t)k, k, nullptr, nullptr);
             launches += 2;
@@ -1232,6 +1278,7 @@ int sweep_run(ddb_ctx* ctx, const ddb_sweep_params* prm, const double* lambdas, 
         ++launches;
     }
     SweepDev D = make_dev(ctx, S);
+    if (use_inverse) D.zsol = S->zsol.as<double>();
     sweep_init_kernel<<<n_t, 256, 0, st>>>(D);
     ++launches;
     DDB_CUDA_TRY(cudaGetLastError());
@@ -1277,9 +1324,13 @@ int sweep_run(ddb_ctx* ctx, const ddb_sweep_params* prm, const double* lambdas, 
         const int64_t max_steps = steps_bound;
         for (int64_t it = 0; it < max_steps; ++it) {
             relax_rhs_kernel<<<n_t, 256, 0, st>>>(D, S->active_matrix.as<int>());
-            chol_solve_kernel<<<dim3(1, n_t), 256, solve_smem, st>>>(S->Lfac.as<double>(), 0, k, nullptr, k,
-                                                                     S->znew.as<double>(), (size_t)k, 1,
-                                                                     S->active_matrix.as<int>(), nullptr);
+            if (use_inverse)
+                ninv_apply_kernel<<<dim3((k + 15) / 16, (n_t + 63) / 64), 256, 0, st>>>(
+                    S->Ninv.as<double>(), k, S->znew.as<double>(), n_t, S->active_matrix.as<int>(), S->zsol.as<double>());
+            else
+                chol_solve_kernel<<<dim3(1, n_t), 256, solve_smem, st>>>(S->Lfac.as<double>(), 0, k, nullptr, k,
+                                                                         S->znew.as<double>(), (size_t)k, 1,
+                                                                         S->active_matrix.as<int>(), nullptr);
             relax_finish_kernel<<<n_t, 256, 0, st>>>(D);
             launches += 3;
             if ((it & 7) == 7 || it + 1 == max_steps) {

@@ -361,3 +361,35 @@ def test_c2_full_size_lorenz_recovers_the_model(ctx):
     terms = {tuple(ex[:, j]): j for j in range(ex.shape[1])}
     np.testing.assert_allclose(out.coefficients[0, [terms[(1, 0, 0)], terms[(0, 1, 0)]]], [-10.0, 10.0], rtol=1e-8)
     np.testing.assert_allclose(out.coefficients[2, [terms[(1, 1, 0)], terms[(0, 0, 1)]]], [1.0, -8.0 / 3.0], rtol=1e-8)
+
+
+@pytest.mark.parametrize("alg,rho,prox", [("ADMM", 1.0, "SoftThreshold"), ("SR3", 1.0, "HardThreshold"), ("SR3", 1.0, "SoftThreshold")])
+def test_relaxed_algorithms_large_library_inverse_path(ctx, alg, rho, prox):
+    """k = 325 >= 256: the ADMM / SR3 iterations go through the explicit inverse of the equilibrated matrix
+    (ninv_apply_kernel) instead of one triangular solve per target; compared with the oracle step by step."""
+    n, m = 24, 4000
+    X, DX = systems.lorenz96_ensemble(m, n=n, seed=3, samples_per_traj=500)
+    DX = DX + 1e-2 * np.random.default_rng(0).standard_normal(DX.shape)
+    ex = oracle.polynomial_exponents(n, 2)
+    assert ex.shape[1] == 325
+    lams = 10.0 ** np.arange(-3, -0.9, 0.5)
+    mk = {"ADMM": lambda: oracle.ADMM(lams, rho), "SR3": lambda: oracle.SR3(lams, rho, getattr(oracle, prox)())}[alg]
+    Th = oracle.evaluate_library(ex, X)
+    traces = []
+    ref = oracle.sparse_regression(mk(), Th, DX[:6], traces=traces)
+    thr = mk().thresholds  # SR3 with the hard threshold stores thr^2 / 2
+    ctx.set_library(ex)
+    ctx.upload(X, DX[:6])
+    ctx.gram()
+    ctx.sweep(ctx.make_params(alg, rho=rho, proximal=prox), thr)
+    ctx.rss()
+    out = ctx.select(paths=True)
+    for i, tr in enumerate(traces):
+        np.testing.assert_array_equal(out.support_path[i], np.asarray(tr.support_path))  # every threshold
+        cp = np.asarray(tr.coef_path)
+        nz = cp != 0
+        assert (np.abs(out.coef_path[i][nz] - cp[nz]) / np.abs(cp[nz])).max() <= 1e-9
+        assert list(out.iters_path[i]) == list(tr.iters_path)
+    np.testing.assert_array_equal(out.coefficients != 0, ref.coefficients != 0)
+    nz = ref.coefficients != 0
+    assert (np.abs(out.coefficients[nz] - ref.coefficients[nz]) / np.abs(ref.coefficients[nz])).max() <= 1e-7
