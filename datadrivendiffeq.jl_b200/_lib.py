@@ -106,6 +106,7 @@ PROTOTYPES = {
     ),
     "ddb_dmd_gram": (C.c_int, [_P, _P, _P, C.c_int, C.c_int64, _P, _P]),
     "ddb_dmd_operator": (C.c_int, [_P, _P, _P, C.c_int, _P]),
+    "ddb_dmd_solve": (C.c_int, [_P, _P, C.c_int, C.c_int64, _P, _P, _P]),
     "ddb_gram_plan_describe": (C.c_int64, [C.c_int, C.c_int64, C.c_int, _P, C.c_int64, _P]),
     "ddb_get_timings": (C.c_int, [_P, C.POINTER(Timings)]),
     "ddb_get_stream": (C.c_int, [_P, C.POINTER(_P)]),

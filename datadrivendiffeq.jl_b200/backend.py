@@ -296,6 +296,16 @@ class Context:
         """K = Q P^-1 (DMDPINV through the normal equations), all device n x n column-major buffers."""
         _lib.check(self._lib.ddb_dmd_operator(self._ctx, C.c_void_p(dP), C.c_void_p(dQ), int(n), C.c_void_p(dK)))
 
+    def dmd_solve(self, x: np.ndarray, want_K: bool = True):
+        """``ddb_dmd_solve``: host snapshots ``x`` (n x (m+1)) -> ``(P, Q, K)`` with K = Q P^-1 (DMDPINV)."""
+        x = _f(x)
+        n, mp1 = x.shape
+        P = np.empty((n, n), order="F")
+        Q = np.empty((n, n), order="F")
+        K = np.empty((n, n), order="F") if want_K else None
+        _lib.check(self._lib.ddb_dmd_solve(self._ctx, _lib.ptr(x), n, mp1, _lib.ptr(P), _lib.ptr(Q), _lib.ptr(K)))
+        return P, Q, K
+
     # -- introspection ----------------------------------------------------------------------
     def timings(self) -> dict:
         t = _lib.Timings()

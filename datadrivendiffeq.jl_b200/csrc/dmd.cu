@@ -236,7 +236,7 @@ __global__ void dmd_out_kernel(const double* __restrict__ W, int n, const double
 }
 
 struct DmdState {
-    DevBuf plan, partials, Ps, dinv, Z, fail;
+    DevBuf plan, partials, Ps, dinv, Z, fail, hX, hPQK;
     GramPlan gp;
     int plan_n = -1;
     int64_t plan_m = -1;
@@ -366,6 +366,41 @@ int ddb_dmd_operator(ddb_ctx* ctx, const double* dP, const double* dQ, int n, do
     return DDB_OK;
 }
 
+// Host-buffer form of the exact-DMD Gram path (what a `ccall` from Julia binds): snapshots x (n x (m + 1),
+// column-major, one snapshot per column) -> P = X X', Q = Y X' with X = x[:, 1:m], Y = x[:, 2:m+1]
+// (lib/DataDrivenDMD/src/solve.jl:36-65, 128-129) and, when K is requested, K = Q P^-1 (DMDPINV,
+// algorithms.jl:80-83).  P, Q, K: n x n column-major host buffers, each optional.
+int ddb_dmd_solve(ddb_ctx* ctx, const double* x, int n, int64_t m_plus_1, double* P, double* Q, double* K) {
+    if (!ctx || !x || n <= 0 || m_plus_1 < 2) {
+        set_error("ddb_dmd_solve: null pointer, non-positive size or fewer than two snapshots");
+        return DDB_INVALID_ARG;
+    }
+    DDB_CUDA_TRY(cudaSetDevice(ctx->device));
+    if (!ctx->dmd) ctx->dmd = new DmdState();
+    DmdState* D = ctx->dmd;
+    const int64_t m = m_plus_1 - 1;
+    const size_t nn = (size_t)n * n;
+    DDB_TRY(D->hX.reserve((size_t)n * m_plus_1 * 8));
+    DDB_TRY(D->hPQK.reserve(3 * nn * 8));
+    cudaStream_t st = ctx->stream;
+    DDB_CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
+    DDB_CUDA_TRY(cudaMemcpyAsync(D->hX.p, x, (size_t)n * m_plus_1 * 8, cudaMemcpyHostToDevice, st));
+    DDB_CUDA_TRY(cudaEventRecord(ctx->ev[3], st));
+    double* dP = D->hPQK.as<double>();
+    double* dQ = dP + nn;
+    double* dK = dQ + nn;
+    DDB_TRY(ddb_dmd_gram(ctx, D->hX.as<double>(), D->hX.as<double>() + n, n, m, dP, dQ));
+    if (K) DDB_TRY(ddb_dmd_operator(ctx, dP, dQ, n, dK));
+    if (P) DDB_CUDA_TRY(cudaMemcpyAsync(P, dP, nn * 8, cudaMemcpyDeviceToHost, st));
+    if (Q) DDB_CUDA_TRY(cudaMemcpyAsync(Q, dQ, nn * 8, cudaMemcpyDeviceToHost, st));
+    if (K) DDB_CUDA_TRY(cudaMemcpyAsync(K, dK, nn * 8, cudaMemcpyDeviceToHost, st));
+    DDB_CUDA_TRY(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    DDB_CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
+    ctx->timings.h2d_ms = ms;
+    return DDB_OK;
+}
+
 }  // extern "C"
 
 namespace ddb {
@@ -378,6 +413,8 @@ void dmd_free(ddb_ctx* ctx) {
         D->dinv.release();
         D->Z.release();
         D->fail.release();
+        D->hX.release();
+        D->hPQK.release();
         delete D;
         ctx->dmd = nullptr;
     }

@@ -19,6 +19,7 @@ using DataDrivenDiffEq, DataDrivenSparse, CommonSolve
 using DataDrivenDiffEq: InternalDataDrivenProblem, DataDrivenSolution, DDReturnCode, get_implicit_data,
                         get_oop_args, __construct_basis, states, equations
 import Symbolics
+import LinearAlgebra
 
 const LIB = get(ENV, "DDB200_LIB", joinpath(@__DIR__, "..", "libddb200.so"))
 
@@ -181,5 +182,53 @@ function CommonSolve.solve!(ps::InternalDataDrivenProblem{<:B200Sparse})
     return DataDrivenSolution(new_basis, problem, alg, [result], ps, result.retcode)
 end
 
-export B200Sparse
+# ------------------------------------------------------------------------------------------------------
+# DataDrivenDMD: `B200DMD <: AbstractKoopmanAlgorithm` implementing the `alg(X, Y) -> (K::Eigen, B)` contract of
+# lib/DataDrivenDMD/src/algorithms.jl:80-83,147-158.  The snapshot contractions P = X X', Q = Y X' and the
+# DMDPINV operator K = Q P^-1 come from one `ddb_dmd_solve` call (the caller passes the snapshot matrix whose
+# columns 1:m are X and 2:m+1 are Y, as `get_fit_targets` builds them for a discrete problem, solve.jl:36-65);
+# the exact-DMD factors follow from the Gram identities  P = U S^2 U',  B = Y V S^-1 = Q U S^-2,  Atilde = U'B.
+# (Requires `using DataDrivenDMD, LinearAlgebra` in the host session.)
+# ------------------------------------------------------------------------------------------------------
+struct B200DMD{T <: Real}
+    truncation::T      # 0 => DMDPINV through the normal equations, otherwise DMDSVD(truncation)
+    device::Int
+end
+B200DMD() = B200DMD(0.0, 0)
+
+function dmd_blocks(alg::B200DMD, x::Matrix{Float64}; want_K::Bool = true)
+    n, mp1 = size(x)
+    P = zeros(n, n); Q = zeros(n, n); K = want_K ? zeros(n, n) : zeros(0, 0)
+    ctx = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:ddb_ctx_create, LIB), Cint, (Cint, Ptr{Ptr{Cvoid}}), alg.device, ctx))
+    try
+        GC.@preserve x P Q K begin
+            check(ccall((:ddb_dmd_solve, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Float64}, Cint, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                ctx[], x, n, mp1, P, Q, want_K ? pointer(K) : Ptr{Float64}(C_NULL)))
+        end
+    finally
+        ccall((:ddb_ctx_destroy, LIB), Cint, (Ptr{Cvoid},), ctx[])
+    end
+    return P, Q, K
+end
+
+# (alg::B200DMD)(x): x = [X Y[:, end]] -- one resident copy serves X and Y
+function (alg::B200DMD)(x::AbstractMatrix)
+    xs = Matrix{Float64}(x)
+    if alg.truncation == 0
+        _, _, K = dmd_blocks(alg, xs)
+        return (LinearAlgebra.eigen(K), zeros(0, 0))
+    end
+    P, Q, _ = dmd_blocks(alg, xs; want_K = false)
+    F = LinearAlgebra.eigen(LinearAlgebra.Symmetric(P))
+    s2 = reverse(F.values); U = reverse(F.vectors, dims = 2)
+    keep = s2 .> (min(alg.truncation, 1.0)^2 * s2[1])
+    U = U[:, keep]; s2 = s2[keep]
+    B = (Q * U) ./ s2'
+    λ, ω = LinearAlgebra.eigen(U' * B)
+    return (LinearAlgebra.Eigen(λ, B * ω), zeros(0, 0))
+end
+
+export B200Sparse, B200DMD
 end # module

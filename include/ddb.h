@@ -267,6 +267,13 @@ int ddb_dmd_gram(ddb_ctx* ctx, const double* dX, const double* dY, int n, int64_
  * equations) from reduced device blocks dP, dQ; K n x n written to dK (device). */
 int ddb_dmd_operator(ddb_ctx* ctx, const double* dP, const double* dQ, int n, double* dK);
 
+/* Host-buffer form of the two calls above for a discrete problem with the identity lifting: snapshots
+ * x (n x (m + 1), column-major, one snapshot per column; X = x[:, 1:m], Y = x[:, 2:m+1] as in
+ * lib/DataDrivenDMD/src/solve.jl:36-65) -> P = X X', Q = Y X' and K = Q P^-1 (DMDPINV).  P, Q, K are n x n
+ * column-major host buffers, each may be NULL.  n must be even.  This is the entry point the Julia glue
+ * binds (`B200DMD`); DMDSVD / TOTALDMD / FBDMD follow from P, Q (and S = Y Y') on the host side. */
+int ddb_dmd_solve(ddb_ctx* ctx, const double* x, int n, int64_t m_plus_1, double* P, double* Q, double* K);
+
 /* ---- introspection ----------------------------------------------------------------------------- */
 
 /* Host-only: the work plan the Gram stage would use for an augmented library of kaug = k + n_t rows,

@@ -157,3 +157,21 @@ def test_controlled_dmd_matches_oracle(inner):
     np.testing.assert_allclose(np.real(res.K), A, atol=1e-8)
     np.testing.assert_allclose(res.B, Bt, atol=1e-8)
     assert res.rss <= 1e-16 * m
+
+
+def test_dmd_solve_host_entry_point():
+    """``ddb_dmd_solve``: the host-buffer entry point the Julia glue binds."""
+    A = np.array([[0.9, -0.2], [0.0, 0.2]])
+    x = _snapshots(A, [10.0, -10.0], 10)
+    ctx = ddb200.Context(0)
+    P, Q, K = ctx.dmd_solve(x)
+    np.testing.assert_allclose(P, x[:, :-1] @ x[:, :-1].T, rtol=1e-13)
+    np.testing.assert_allclose(Q, x[:, 1:] @ x[:, :-1].T, rtol=1e-13)
+    np.testing.assert_allclose(K, A, atol=1e-9)
+    n, m = 130, 2001
+    _, X, Y = systems.linear_snapshots(n, m, seed=1, restart=10**9)
+    xs = np.concatenate([X, Y[:, -1:]], axis=1)
+    P, Q, K = ctx.dmd_solve(xs)
+    Kref = np.linalg.lstsq(X.T, Y.T, rcond=None)[0].T
+    assert np.max(np.abs(K - Kref)) <= 1e-8 * max(1.0, np.max(np.abs(Kref)))
+    ctx.close()
