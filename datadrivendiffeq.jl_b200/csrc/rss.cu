@@ -391,7 +391,19 @@ __global__ void gather_gss_kernel(const double* __restrict__ packed, int k, int 
 __global__ void scatter_group_rss_kernel(const double* __restrict__ rep, const int32_t* __restrict__ group, int ncand,
                                          double* __restrict__ rss) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < ncand) rss[c] = rep[group[c]];
+    if (c < ncand) rss[c] = group[c] >= 0 ? rep[group[c]] : 0.0;
+}
+
+// Candidates 0 .. n_t-1 are the zero models: their rss is sum_s y_e(s)^2 = yy[e], which the Gram stage already
+// holds (a sum of squares: no cancellation), so they are never streamed.  The streamed part is 0 and yy goes
+// into the correction that select adds AFTER the all-reduce (yy is the reduced, global value on every rank).
+__global__ void zero_model_rss_kernel(const double* __restrict__ yy, int n_t, double* __restrict__ rss,
+                                      double* __restrict__ corr) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n_t) {
+        rss[e] = 0.0;
+        corr[e] = yy[e];
+    }
 }
 
 int rss_run(ddb_ctx* ctx, SweepState* S, double* dRss) {
@@ -420,11 +432,19 @@ int rss_run(ddb_ctx* ctx, SweepState* S, double* dRss) {
     const int64_t nterms = S->pool_used;
     const char* genv = getenv("DDB_RSS_GROUPING");
     const bool grouping = !(genv && atoi(genv) == 0) && ncand > 2 * S->n_t && nterms > 0;
+    // yy of the space the sweep ran in (explicit: [G | R | yy]; implicit view: [G' | R' | diag G'])
+    const int n_t = S->n_t;
+    const double* yy_dev = (implicit ? ctx->imp_packed.as<double>() : ctx->d_packed.as<double>()) + (size_t)S->k * S->k +
+                           (size_t)S->k * n_t;
     if (!grouping) {
         DDB_CUDA_TRY(cudaMemsetAsync(S->rss_corr.p, 0, (size_t)std::max(1, ncand) * 8, st));
-        RssCand c{ncand, nterms, S->cand_off.as<int64_t>(), S->cand_nnz.as<int32_t>(), S->cand_eq.as<int32_t>(),
-                  S->cand_idx.as<int32_t>(), S->cand_val.as<double>()};
-        DDB_TRY(rss_core(ctx, c, map, targets, scale, S->cand_terms, S->rss_partials, dRss, &launches));
+        zero_model_rss_kernel<<<(n_t + 255) / 256, 256, 0, st>>>(yy_dev, n_t, dRss, S->rss_corr.as<double>());
+        ++launches;
+        if (ncand > n_t) {  // candidates n_t .. ncand-1 are the recorded models
+            RssCand c{ncand - n_t, nterms, S->cand_off.as<int64_t>() + n_t, S->cand_nnz.as<int32_t>() + n_t,
+                      S->cand_eq.as<int32_t>() + n_t, S->cand_idx.as<int32_t>(), S->cand_val.as<double>()};
+            DDB_TRY(rss_core(ctx, c, map, targets, scale, S->cand_terms, S->rss_partials, dRss + n_t, &launches));
+        }
     } else {
         std::vector<int64_t> off(ncand);
         std::vector<int32_t> nnz(ncand), eq(ncand), idx((size_t)nterms);
@@ -557,10 +577,16 @@ int rss_run(ddb_ctx* ctx, SweepState* S, double* dRss) {
                 r_val.push_back(c0[(size_t)q * kGroupMax + t]);
             }
         }
+        std::vector<double> yy_h(n_t);
+        DDB_CUDA_TRY(cudaMemcpyAsync(yy_h.data(), yy_dev, (size_t)n_t * 8, cudaMemcpyDeviceToHost, st));
+        DDB_CUDA_TRY(cudaStreamSynchronize(st));
         std::vector<int32_t> rep(ncand);
         for (int c = 0; c < ncand; ++c) {
             const int g = group[c];
-            if (shared[g]) {
+            if (nnz[c] == 0) {  // a zero model: rss = yy[target], never streamed
+                rep[c] = -1;
+                corr[c] = yy_h[eq[c]];
+            } else if (shared[g]) {
                 rep[c] = rep_of_group[g];
                 const int q = gslot[g], s = g_size[q];
                 const double* Gs = gss.data() + (size_t)q * gstride;
@@ -589,7 +615,7 @@ int rss_run(ddb_ctx* ctx, SweepState* S, double* dRss) {
         const size_t o_val = (o_idx + (size_t)std::max<int64_t>(1, rterms) * 4 + 7) & ~size_t(7);
         const size_t o_rep = o_val + (size_t)std::max<int64_t>(1, rterms) * 8;
         const size_t o_map = o_rep + (size_t)nrep * 8;
-        DDB_TRY(S->rep_buf.reserve(o_map + (size_t)ncand * 4));
+        DDB_TRY(S->rep_buf.reserve(o_map + (size_t)ncand * 4 + 64));
         unsigned char* rb = static_cast<unsigned char*>(S->rep_buf.p);
         DDB_CUDA_TRY(cudaMemcpyAsync(rb, r_off.data(), (size_t)nrep * 8, cudaMemcpyHostToDevice, st));
         DDB_CUDA_TRY(cudaMemcpyAsync(rb + o_nnz, r_nnz.data(), (size_t)nrep * 4, cudaMemcpyHostToDevice, st));
@@ -603,7 +629,9 @@ int rss_run(ddb_ctx* ctx, SweepState* S, double* dRss) {
         RssCand c{nrep, rterms, reinterpret_cast<const int64_t*>(rb), reinterpret_cast<const int32_t*>(rb + o_nnz),
                   reinterpret_cast<const int32_t*>(rb + o_eq), reinterpret_cast<const int32_t*>(rb + o_idx),
                   reinterpret_cast<const double*>(rb + o_val)};
-        DDB_TRY(rss_core(ctx, c, map, targets, scale, S->cand_terms, S->rss_partials, reinterpret_cast<double*>(rb + o_rep), &launches));
+        if (nrep > 0)
+            DDB_TRY(rss_core(ctx, c, map, targets, scale, S->cand_terms, S->rss_partials, reinterpret_cast<double*>(rb + o_rep),
+                             &launches));
         scatter_group_rss_kernel<<<(ncand + 255) / 256, 256, 0, st>>>(reinterpret_cast<const double*>(rb + o_rep),
                                                                       reinterpret_cast<const int32_t*>(rb + o_map), ncand, dRss);
         ++launches;
