@@ -393,3 +393,33 @@ def test_relaxed_algorithms_large_library_inverse_path(ctx, alg, rho, prox):
     np.testing.assert_array_equal(out.coefficients != 0, ref.coefficients != 0)
     nz = ref.coefficients != 0
     assert (np.abs(out.coefficients[nz] - ref.coefficients[nz]) / np.abs(ref.coefficients[nz])).max() <= 1e-7
+
+
+def test_c3_library_size_noisy_matches_oracle(ctx):
+    """The full C3 library (n = 64, 2145 terms) with noisy derivatives at 6000 samples -- as large as the
+    oracle (pivoted QR on a 2145-column Theta per target) finishes in seconds.  Goes through the ring schedule
+    of the Gram stage and, at the small thresholds, through the blocked Cholesky of >1000-term active sets."""
+    n, m = 64, 6000
+    X, D = systems.lorenz96_ensemble(m, n=n, seed=4, samples_per_traj=500)
+    D = D + 1e-2 * np.random.default_rng(1).standard_normal(D.shape)
+    ex = oracle.polynomial_exponents(n, 2)
+    lams = 10.0 ** np.arange(-4.5, -0.9, 0.5)
+    traces = []
+    ref = oracle.sparse_regression(oracle.STLSQ(lams), oracle.evaluate_library(ex, X), D[:2], traces=traces)
+    ctx.set_library(ex)
+    ctx.upload(X, D[:2])
+    ctx.gram()
+    assert ctx.timings()["gram_launches"] == 3  # ring + diagonal pairs + reduce
+    ctx.sweep(ctx.make_params("STLSQ"), lams)
+    ctx.rss()
+    out = ctx.select(paths=True)
+    assert ctx.timings()["big_steps"] > 0
+    for i in range(2):
+        np.testing.assert_array_equal(out.support_path[i], np.stack(traces[i].support_path))  # every threshold
+        cp = np.stack(traces[i].coef_path)
+        nz = cp != 0
+        assert (np.abs(out.coef_path[i][nz] - cp[nz]) / np.abs(cp[nz])).max() <= 1e-8
+    nz = ref.coefficients != 0
+    np.testing.assert_array_equal(out.coefficients != 0, nz)
+    assert (np.abs(out.coefficients[nz] - ref.coefficients[nz]) / np.abs(ref.coefficients[nz])).max() <= COEF_RTOL
+    np.testing.assert_allclose(out.lambda_opt, ref.lambdas, rtol=1e-15)
