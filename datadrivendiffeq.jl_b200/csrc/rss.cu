@@ -37,12 +37,15 @@ static_assert(sizeof(RssTerm) == 32, "RssTerm layout");
 constexpr int kRssTile = 32;   // samples per shared-memory tile (one per lane)
 constexpr int kRssAcc = 32;    // candidates per warp per pass (register accumulators per lane)
 constexpr int kRssWarps = 8;
-constexpr int kRssPitch = kRssTile + 1;  // doubles; transposed tile [state][sample], odd pitch -> conflict-free
+// A staged tile holds `sub` groups of kRssTile samples (sub = 1 for wide problems, up to 8 when a sample is only
+// a few doubles, so that a tile is ~16 KB either way and the per-tile synchronisation is amortised); it is
+// stored TRANSPOSED [state][sample] with the odd pitch 32 sub + 1 -> "lane = sample" reads are conflict-free.
+constexpr int kRssMaxSub = 8;
 
 // `map` (implicit mode) translates indices of the selected sub-library into rows of the installed library;
 // cand_val == nullptr writes coefficient 1 (the records of the implicit targets).
 __global__ void rss_expand_kernel(const int32_t* __restrict__ cand_idx, const double* __restrict__ cand_val,
-                                  int64_t nterms, const uint16_t* __restrict__ factors, int ones_row,
+                                  int64_t nterms, const uint16_t* __restrict__ factors, int ones_row, int pitch,
                                   const int32_t* __restrict__ map, RssTerm* __restrict__ out) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nterms) return;
@@ -52,8 +55,8 @@ __global__ void rss_expand_kernel(const int32_t* __restrict__ cand_idx, const do
     const uint16_t* f = factors + (size_t)(map ? map[term] : term) * kMaxFactors;
 #pragma unroll
     for (int d = 0; d < kMaxFactors; ++d) r.o16[d] = (f[d] == kNoFactor) ? (uint16_t)ones_row : f[d];
-    r.o32[0] = (int)r.o16[0] * kRssPitch;
-    r.o32[1] = (int)r.o16[1] * kRssPitch;
+    r.o32[0] = (int)r.o16[0] * pitch;
+    r.o32[1] = (int)r.o16[1] * pitch;
     out[t] = r;
 }
 
@@ -69,6 +72,7 @@ struct RssArgs {
     const RssTerm* terms;
     const RssTerm* targets;  // implicit mode: target e is a library term (one record each); null = row e of Y
     int term_cap;            // term records of one CTA's candidates that fit in shared memory
+    int sub, pitch;          // groups of 32 samples per staged tile; row pitch of the tile = 32 sub + 1
     double* partials;  // gridDim.x x ncand
 };
 
@@ -90,11 +94,12 @@ struct RssWalk {
         ds = blockDim.x / w;
     }
 };
-__device__ __forceinline__ void rss_stage_rows(double* buf, const double* src, int w, int valid, const RssWalk& k) {
+__device__ __forceinline__ void rss_stage_rows(double* buf, const double* src, int w, int valid, int pitch,
+                                               const RssWalk& k) {
     int i = k.i0, s = k.s0;
     const int total = valid * w;
     for (int e = threadIdx.x; e < total; e += blockDim.x) {
-        cp_async8(buf + i * kRssPitch + s, src + e);
+        cp_async8(buf + i * pitch + s, src + e);
         i += k.di;
         s += k.ds;
         if (i >= w) {
@@ -113,16 +118,17 @@ __device__ __forceinline__ void rss_tiles(const RssArgs& a, double* sm, const in
                                           double (&acc)[kRssAcc]) {
     const int rows = a.n + a.n_t + 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int tile_doubles = rows * kRssPitch;
+    const int pitch = a.pitch, tile_samples = kRssTile * a.sub;
+    const int tile_doubles = rows * pitch;
     RssWalk wx, wy;
     wx.init(a.n);
     wy.init(a.n_t);
     auto stage = [&](int which, int64_t tile) {
-        const int64_t s0 = tile * kRssTile;
-        const int valid = (int)min((int64_t)kRssTile, a.m - s0);
+        const int64_t s0 = tile * tile_samples;
+        const int valid = (int)min((int64_t)tile_samples, a.m - s0);
         double* dst = sm + which * tile_doubles;
-        rss_stage_rows(dst, a.X + s0 * a.n, a.n, valid, wx);
-        rss_stage_rows(dst + a.n * kRssPitch, a.Y + s0 * a.n_t, a.n_t, valid, wy);
+        rss_stage_rows(dst, a.X + s0 * a.n, a.n, valid, pitch, wx);
+        rss_stage_rows(dst + a.n * pitch, a.Y + s0 * a.n_t, a.n_t, valid, pitch, wy);
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     if (t_lo < t_hi) stage(0, t_lo);
@@ -135,12 +141,16 @@ __device__ __forceinline__ void rss_tiles(const RssArgs& a, double* sm, const in
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
-        const int valid = (int)min((int64_t)kRssTile, a.m - tile * kRssTile);
-        const double* xs = sm + cur * tile_doubles + lane;
-        const bool live = lane < valid;
+        const int valid = (int)min((int64_t)tile_samples, a.m - tile * tile_samples);
+#pragma unroll 1
+        for (int ss = 0; ss < a.sub; ++ss) {
+        const double* xs = sm + cur * tile_doubles + ss * kRssTile + lane;
+        const bool live = ss * kRssTile + lane < valid;
+        if (ss * kRssTile >= valid) break;
 #pragma unroll
         for (int q = 0; q < kRssAcc; ++q) {
-            if (q < nslots) {
+            if (q >= nslots) break;  // slots are filled in order: one exit instead of 32 guarded bodies
+            {
                 const int4 mt = s_meta[warp + kRssWarps * q];
                 const int nnz = SMEM_TERMS ? mt.w : mt.y, eq = mt.z;  // shared-memory records are padded to 4s
                 const RssTerm* r = SMEM_TERMS ? s_terms + mt.x : a.terms + __ldg(a.cand_off + cbase + warp + kRssWarps * q);
@@ -167,7 +177,7 @@ __device__ __forceinline__ void rss_tiles(const RssArgs& a, double* sm, const in
                         double p = xs[w.z] * xs[w.w];
                         const uint32_t ow[4] = {(uint32_t)o.x, (uint32_t)o.y, (uint32_t)o.z, (uint32_t)o.w};
 #pragma unroll
-                        for (int d = 2; d < NF; ++d) p *= xs[((ow[d >> 1] >> (16 * (d & 1))) & 0xFFFFu) * kRssPitch];
+                        for (int d = 2; d < NF; ++d) p *= xs[((ow[d >> 1] >> (16 * (d & 1))) & 0xFFFFu) * pitch];
                         fit = fma(__hiloint2double(w.y, w.x), p, fit);
                     }
                 }
@@ -179,14 +189,15 @@ __device__ __forceinline__ void rss_tiles(const RssArgs& a, double* sm, const in
                         const int4 o = __ldg(reinterpret_cast<const int4*>(a.targets + eq) + 1);
                         const uint32_t ow[4] = {(uint32_t)o.x, (uint32_t)o.y, (uint32_t)o.z, (uint32_t)o.w};
 #pragma unroll
-                        for (int d = 2; d < NF; ++d) yv *= xs[((ow[d >> 1] >> (16 * (d & 1))) & 0xFFFFu) * kRssPitch];
+                        for (int d = 2; d < NF; ++d) yv *= xs[((ow[d >> 1] >> (16 * (d & 1))) & 0xFFFFu) * pitch];
                     }
                 } else {
-                    yv = xs[(a.n + eq) * kRssPitch];
+                    yv = xs[(a.n + eq) * pitch];
                 }
                 const double res = live ? fit - yv : 0.0;
                 acc[q] = fma(res, res, acc[q]);
             }
+        }
         }
         __syncthreads();  // everyone is done with this buffer before it is refilled two iterations later
     }
@@ -199,10 +210,11 @@ __global__ void __launch_bounds__(kRssWarps * 32) rss_kernel(const RssArgs a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cbase = blockIdx.y * (kRssWarps * kRssAcc);
     // this CTA's sample range (whole tiles)
-    const int64_t ntiles = (a.m + kRssTile - 1) / kRssTile;
+    const int pitch = a.pitch;
+    const int64_t ntiles = (a.m + kRssTile * a.sub - 1) / (kRssTile * a.sub);
     const int64_t t_lo = ntiles * blockIdx.x / gridDim.x, t_hi = ntiles * (blockIdx.x + 1) / gridDim.x;
-    if (threadIdx.x < 2 * kRssPitch)
-        sm[(threadIdx.x / kRssPitch) * rows * kRssPitch + (rows - 1) * kRssPitch + threadIdx.x % kRssPitch] = 1.0;
+    for (int e = threadIdx.x; e < 2 * pitch; e += blockDim.x)
+        sm[(e / pitch) * rows * pitch + (rows - 1) * pitch + e % pitch] = 1.0;
 
     // candidates of this warp: cbase + warp + 8 * slot
     int nslots = 0;
@@ -210,7 +222,7 @@ __global__ void __launch_bounds__(kRssWarps * 32) rss_kernel(const RssArgs a) {
         if (cbase + warp + kRssWarps * q < a.ncand) nslots = q + 1;
     // The candidates' metadata and term records are the same for every tile: they are copied into shared
     // memory once (when they fit), so the inner loop's dependent loads are shared-memory latency, not L2.
-    int4* s_meta = reinterpret_cast<int4*>(sm + 2 * (size_t)rows * kRssPitch);  // [256] {local term offset, nnz, eq, -}
+    int4* s_meta = reinterpret_cast<int4*>(sm + (((2 * (size_t)rows * pitch) + 1) & ~size_t(1)));  // [256] {term offset, nnz, eq, padded nnz}
     RssTerm* s_terms = reinterpret_cast<RssTerm*>(s_meta + kRssWarps * kRssAcc);
     __shared__ int s_scan[kRssWarps];
     __shared__ int s_total;
@@ -242,7 +254,7 @@ __global__ void __launch_bounds__(kRssWarps * 32) rss_kernel(const RssArgs a) {
         if (fits) {
             RssTerm pad;
             pad.val = 0.0;
-            pad.o32[0] = pad.o32[1] = (rows - 1) * kRssPitch;
+            pad.o32[0] = pad.o32[1] = (rows - 1) * pitch;
 #pragma unroll
             for (int d = 0; d < kMaxFactors; ++d) pad.o16[d] = (uint16_t)(rows - 1);
             const RssTerm* src = c < a.ncand ? a.terms + a.cand_off[c] : nullptr;
@@ -303,6 +315,15 @@ __global__ void rss_scale_kernel(RssTerm* __restrict__ terms, const int32_t* __r
     if (t < nterms) terms[t].val /= scale[cand_idx[t]];
 }
 
+// groups of 32 samples per staged tile (~16 KB per tile) and the resulting row pitch
+static void rss_tile_shape(const ddb_ctx* ctx, int* sub_out, int* pitch_out) {
+    const int rows_all = ctx->n + ctx->n_t + 1;
+    int sub = 1;
+    while (sub < kRssMaxSub && (size_t)rows_all * kRssTile * (2 * sub) * 8 <= 16 * 1024) sub *= 2;
+    *sub_out = sub;
+    *pitch_out = kRssTile * sub + 1;
+}
+
 static int rss_core(ddb_ctx* ctx, const RssCand& c, const int32_t* map, const RssTerm* targets, const double* scale,
                     DevBuf& terms, DevBuf& partials, double* dRss, int* launches) {
     if (!ctx->dX || !ctx->dY || ctx->m <= 0) {
@@ -315,10 +336,12 @@ static int rss_core(ddb_ctx* ctx, const RssCand& c, const int32_t* map, const Rs
     }
     cudaStream_t st = ctx->stream;
     const int ncand = c.ncand;
+    int sub, pitch;
+    rss_tile_shape(ctx, &sub, &pitch);
     DDB_TRY(terms.reserve((size_t)std::max<int64_t>(1, c.nterms) * sizeof(RssTerm)));
     if (c.nterms > 0) {
         rss_expand_kernel<<<(unsigned)((c.nterms + 255) / 256), 256, 0, st>>>(c.idx, c.val, c.nterms, ctx->d_factors.as<uint16_t>(),
-                                                                              ctx->n + ctx->n_t, map, terms.as<RssTerm>());
+                                                                              ctx->n + ctx->n_t, pitch, map, terms.as<RssTerm>());
         ++*launches;
         if (scale) {
             rss_scale_kernel<<<(unsigned)((c.nterms + 255) / 256), 256, 0, st>>>(terms.as<RssTerm>(), c.idx, c.nterms, scale);
@@ -326,7 +349,8 @@ static int rss_core(ddb_ctx* ctx, const RssCand& c, const int32_t* map, const Rs
         }
     }
     const int passes = (ncand + kRssWarps * kRssAcc - 1) / (kRssWarps * kRssAcc);
-    const int64_t ntiles = (ctx->m + kRssTile - 1) / kRssTile;
+    const int rows_all = ctx->n + ctx->n_t + 1;
+    const int64_t ntiles = (ctx->m + kRssTile * sub - 1) / (kRssTile * sub);
     const int nparts = (int)std::min<int64_t>(ntiles, (int64_t)ctx->sm_count * 4);
     DDB_TRY(partials.reserve((size_t)nparts * ncand * 8));
     RssArgs a;
@@ -342,7 +366,9 @@ static int rss_core(ddb_ctx* ctx, const RssCand& c, const int32_t* map, const Rs
     a.terms = terms.as<RssTerm>();
     a.targets = targets;
     a.partials = partials.as<double>();
-    const size_t smem_tiles = 2 * (size_t)kRssPitch * (ctx->n + ctx->n_t + 1) * sizeof(double);
+    const size_t smem_tiles = ((2 * (size_t)pitch * rows_all + 1) & ~size_t(1)) * sizeof(double);
+    a.sub = sub;
+    a.pitch = pitch;
     if (smem_tiles > 180 * 1024) {
         set_error("ddb_rss: n + n_t too large for the shared-memory sample tile");
         return DDB_UNSUPPORTED;
@@ -419,8 +445,10 @@ int rss_run(ddb_ctx* ctx, SweepState* S, double* dRss) {
     int launches = 0;
     if (implicit) {  // one record per target: the library term on the left-hand side
         DDB_TRY(S->tgt_terms.reserve((size_t)ctx->imp_k * sizeof(RssTerm)));
+        int tsub, tpitch;
+        rss_tile_shape(ctx, &tsub, &tpitch);
         rss_expand_kernel<<<(ctx->imp_k + 255) / 256, 256, 0, st>>>(nullptr, nullptr, ctx->imp_k, ctx->d_factors.as<uint16_t>(),
-                                                                   ctx->n + ctx->n_t, ctx->imp_idx.as<int32_t>(),
+                                                                   ctx->n + ctx->n_t, tpitch, ctx->imp_idx.as<int32_t>(),
                                                                    S->tgt_terms.as<RssTerm>());
         ++launches;
     }
