@@ -160,8 +160,10 @@ __device__ __forceinline__ void rss_tiles(const RssArgs& a, double* sm, const in
                     for (int t = 0; t < nnz; t += 4) {  // the padded count is a multiple of 4
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
-                            const int4 w = r16[t + u];  // {val, o32[0], o32[1]}
-                            fit = fma(__hiloint2double(w.y, w.x), xs[w.z] * xs[w.w], fit);
+                            // {val, (o32[0], o32[1])} as two doubles: the coefficient lands in a register pair and
+                            // the offsets are the halves of the second one -- no moves
+                            const double2 w = reinterpret_cast<const double2*>(r16)[t + u];
+                            fit = fma(w.x, xs[__double2loint(w.y)] * xs[__double2hiint(w.y)], fit);
                         }
                     }
                 } else if (NF <= 2) {
