@@ -49,8 +49,11 @@ struct GramCfg {
     static constexpr int kThreads = kWarps * 32;
     static constexpr int kJobs = 2 * BT / kThreads;       // Theta columns built per thread: 1 or 2
     static constexpr int kPitch = BT + 4;  // doubles; pitch % 16 == 4 -> fragment loads hit 16 distinct banks
-    static constexpr int kStageDoubles = 2 * kKS * kPitch;  // Theta_I' and Theta_J' tiles of one stage
-    static constexpr int kMinBlocks = (BT == 128) ? 1 : 3;
+    // Theta_I' and Theta_J' tiles of one stage; BT = 64 only ever runs the single diagonal pair of a library of
+    // at most 64 augmented rows (one tile), which lets four CTAs share an SM: their heavy (26 sub-tiles) and
+    // light (10 sub-tiles) warps then pair up on the four sub-partitions
+    static constexpr int kStageDoubles = (BT == 128 ? 2 : 1) * kKS * kPitch;
+    static constexpr int kMinBlocks = (BT == 128) ? 1 : 4;
 };
 
 // One raw-sample slot (doubles): [ones(16) | 0.0 | pad | X tile 16 x n | Y tile 16 x n_t].
