@@ -101,3 +101,25 @@ def test_upload_gram_chunked_overlap_matches_plain(ctx, n, deg, m):
     ctx.upload_gram_raw(Xp.data_ptr(), Yp.data_ptr(), n, m)  # deterministic
     G2, _, _ = ctx.gram_download()
     np.testing.assert_array_equal(G1, G2)
+
+
+@pytest.mark.parametrize("n,n_t", [(65, 65), (66, 66), (70, 3), (64, 1), (72, 72)])
+def test_ring_plan_variants(ctx, n, n_t):
+    """Library sizes around the ring schedule's planning cases: with and without a short last block row (strip
+    consumers), last block rows of 40 / 66 / 100 live rows, more block pairs than consumers."""
+    m = 4500
+    rng = np.random.default_rng(n * 100 + n_t)
+    X = rng.standard_normal((n, m))
+    Y = rng.standard_normal((n_t, m))
+    ex = oracle.polynomial_exponents(n, 2)
+    ctx.set_library(ex)
+    ctx.upload(X, Y)
+    (G1, R1, y1), l1 = _gram(ctx, True)
+    assert l1 == 3  # the ring schedule ran
+    Th = oracle.evaluate_library(ex, X)
+    Gr, Rr, yr = Th @ Th.T, Th @ Y.T, (Y * Y).sum(1)
+    sc = np.sqrt(np.outer(np.diag(Gr), np.diag(Gr)))
+    assert np.max(np.abs(G1 - Gr) / sc) < 1e-13
+    assert np.max(np.abs(R1 - Rr)) < 1e-13 * np.sqrt(np.max(np.diag(Gr)) * np.max(yr))
+    np.testing.assert_allclose(y1, yr, rtol=1e-13)
+    np.testing.assert_array_equal(G1, G1.T)
