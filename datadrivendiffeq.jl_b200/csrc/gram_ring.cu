@@ -37,8 +37,9 @@ namespace ddb {
 
 constexpr int kRingBT = 128;
 constexpr int kRingPitch = kRingBT + 4;              // pair tile: [16 samples][132]
-constexpr int kPairStage = 2 * kKS * kRingPitch;     // doubles per stage of a pair consumer
-constexpr int kPairDepth = 6;                        // its shared-memory stage ring
+constexpr int kPairSamples = 32;                     // samples per stage of a pair consumer (one barrier round trip)
+constexpr int kPairStage = 2 * kPairSamples * kRingPitch;  // doubles per stage of a pair consumer
+constexpr int kPairDepth = 3;                        // its shared-memory stage ring
 constexpr int kStripRows = 40;                       // live rows of a strip (5 row groups of 8)
 constexpr int kStripPitch = kStripRows + 12;         // 52 = 4 (mod 16): conflict-free fragment loads
 constexpr int kStripBlocks = 3;                      // block columns per strip consumer (8 warps x 48 columns)
@@ -101,6 +102,7 @@ struct RingFeed {
     uint32_t* s_ready;         // shared watermark: every window below it is complete in the global ring
     uint32_t ready;            // this warp's copy of the watermark
     int nprod, lane, win_doubles;
+    uint32_t spw;              // stages per producer window (4 for 16-sample stages, 2 for 32-sample stages)
     int src_off, src_stage, dst_off;  // this lane's operand: offset in a window, per-stage stride, offset in a stage
     uint32_t bytes, stage_bytes;
     long long t_ready, t_empty;
@@ -109,7 +111,7 @@ struct RingFeed {
     __device__ __forceinline__ void issue(int64_t st) {
         if (st >= nstages) return;
         const int slot = (int)((uint32_t)st % (uint32_t)DEPTH);  // st < 2^32 (checked on the host)
-        const uint32_t w = (uint32_t)st / kSPW;
+        const uint32_t w = (uint32_t)st / spw;
         if (w >= ready) {
             // Windows [0, ready) are known to be complete.  The watermark is shared through shared memory
             // (any warp may have refreshed it); whoever finds it short polls the producers' counters:
@@ -147,7 +149,7 @@ struct RingFeed {
         if (lane == 0) mbar_expect_tx(&full[slot], stage_bytes);
         __syncwarp();
         if (bytes) {
-            const double* src = zring + (size_t)(w % kRingWindows) * win_doubles + src_off + ((uint32_t)st % kSPW) * src_stage;
+            const double* src = zring + (size_t)(w % kRingWindows) * win_doubles + src_off + ((uint32_t)st % spw) * src_stage;
             bulk_g2s(ring + (size_t)slot * STAGE + dst_off, src, bytes, &full[slot]);
         }
     }
@@ -157,8 +159,9 @@ struct RingFeed {
 // double-buffered across k-steps AND across stages: the loads of the next stage's first k-step are issued
 // before the last DMMAs of the current stage whenever its tile has already landed.
 // BSPLIT: column sub-tile j lives in operand tile j / 2 (strip consumers: two 8-column groups per block)
-template <int RI, int CJ, uint32_t MASK, int DEPTH, int STAGE, bool BSPLIT>
+template <int RI, int CJ, uint32_t MASK, int DEPTH, int STAGE, bool BSPLIT, int KSTEPS>
 struct RingWarp {
+    static_assert(KSTEPS % 2 == 0, "fragments alternate between two buffers");
     double acc[RI][CJ][2];
     __device__ __forceinline__ static constexpr bool row_live(int i) {
         uint32_t m = 0;
@@ -208,7 +211,7 @@ struct RingWarp {
         for (int64_t st = 0; st < nstages; ++st) {
             if (((uint32_t)st & (kRingWarps - 1)) == (uint32_t)warp) {  // this warp's turn to drive the TMA unit
                 // the last stage of a window has landed in shared memory: the global ring slot may be recycled
-                if (lane == 0 && ((uint32_t)st % kSPW) == kSPW - 1) st_release(progress, (unsigned long long)((uint32_t)st / kSPW + 1));
+                if (lane == 0 && ((uint32_t)st % fd.spw) == fd.spw - 1) st_release(progress, (unsigned long long)((uint32_t)st / fd.spw + 1));
                 fd.template issue<DEPTH, STAGE>(st + kAhead);
             }
             const double* base = ring + (size_t)slot * STAGE;
@@ -220,12 +223,16 @@ struct RingWarp {
             }
             const double* nbase = ring + (size_t)nslot * STAGE;
             if (MASK != 0u) {
-                load(a1, b1, base + offA + pitch4A, base + offB + pitch4B);
-                mma(a0, b0);
-                load(a0, b0, base + offA + 2 * pitch4A, base + offB + 2 * pitch4B);
-                mma(a1, b1);
-                load(a1, b1, base + offA + 3 * pitch4A, base + offB + 3 * pitch4B);
-                mma(a0, b0);
+#pragma unroll
+                for (int kk = 0; kk < KSTEPS - 1; ++kk) {
+                    if (kk & 1) {
+                        load(a0, b0, base + offA + (kk + 1) * pitch4A, base + offB + (kk + 1) * pitch4B);
+                        mma(a1, b1);
+                    } else {
+                        load(a1, b1, base + offA + (kk + 1) * pitch4A, base + offB + (kk + 1) * pitch4B);
+                        mma(a0, b0);
+                    }
+                }
             }
             if (st + 1 < nstages) {
                 if (MASK != 0u && mbar_test(&full[nslot], npar)) {
@@ -390,21 +397,23 @@ __global__ void __launch_bounds__(kRingThreads, 1) gram_ring_kernel(const RingAr
     if (strip)  // block columns past the strip's range are never copied: they must read as zero, not as garbage
         for (int e = tid; e < kStripDepth * kStripStage; e += kRingThreads) ring[e] = 0.0;
     __syncthreads();
-    const int64_t nstages = nwin * kSPW;  // producers zero-fill the tail, every stage is full
+    const int64_t nstages = nwin * (kWin / (cd.kind == 1 ? kKS : kPairSamples));  // producers zero-fill the tail
 
     RingFeed feed = {};
     {
         // operand tiles of a stage: pair = {block a, block b}; strip = {short last block, nb block columns}
         const int chunk = kWin * kRingPitch;  // doubles per full block of a window
         const int nops = strip ? 1 + cd.nb : (same ? 1 : 2);
+        const int sps = strip ? kKS : kPairSamples;  // samples per stage
         if (lane < nops) {
             const int blk = strip ? (lane == 0 ? cd.a : cd.b + lane - 1) : (lane == 0 ? cd.a : cd.b);
             const int pitch = (blk == args.nblk - 1) ? args.last_pitch : kRingPitch;
             feed.src_off = blk * chunk;
-            feed.src_stage = kKS * pitch;
-            feed.bytes = (uint32_t)(kKS * pitch * sizeof(double));
-            feed.dst_off = strip ? (lane == 0 ? 0 : kKS * kStripPitch + (lane - 1) * kKS * kRingPitch) : lane * kKS * kRingPitch;
+            feed.src_stage = sps * pitch;
+            feed.bytes = (uint32_t)(sps * pitch * sizeof(double));
+            feed.dst_off = strip ? (lane == 0 ? 0 : kKS * kStripPitch + (lane - 1) * kKS * kRingPitch) : lane * kPairSamples * kRingPitch;
         }
+        feed.spw = (uint32_t)(kWin / sps);
         uint32_t tot = feed.bytes;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xFFFFFFFFu, tot, o);
@@ -438,11 +447,11 @@ __global__ void __launch_bounds__(kRingThreads, 1) gram_ring_kernel(const RingAr
             shape = (d >= 3) ? 0 : (d == 0 ? 1 : (d == -4 ? 2 : 3));
         }
         const int offA = t * kRingPitch + row0 + g;
-        const int offB = (same ? 0 : kKS * kRingPitch) + t * kRingPitch + col0 + g;
+        const int offB = (same ? 0 : kPairSamples * kRingPitch) + t * kRingPitch + col0 + g;
         double* out = args.partials + (size_t)c * kRingBT * kRingBT;
         auto go = [&](auto tag) {
             constexpr uint32_t MASK = decltype(tag)::value;
-            RingWarp<8, 4, MASK, kPairDepth, kPairStage, false> w;
+            RingWarp<8, 4, MASK, kPairDepth, kPairStage, false, kPairSamples / 4> w;
             w.run(ring, full, empty, nstages, offA, offB, 4 * kRingPitch, 4 * kRingPitch, warp, feed, args.progress + c, lane,
                   t_wait);
 #pragma unroll
@@ -464,7 +473,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) gram_ring_kernel(const RingAr
         // of the (up to) three block columns, so its B fragments are affine in the sub-tile index
         const int offA = t * kStripPitch + g;
         const int offB = kKS * kStripPitch + t * kRingPitch + warp * 16 + g;
-        RingWarp<5, 6, 0x3FFFFFFFu, kStripDepth, kStripStage, true> w;
+        RingWarp<5, 6, 0x3FFFFFFFu, kStripDepth, kStripStage, true, kKS / 4> w;
         w.run(ring, full, empty, nstages, offA, offB, 4 * kStripPitch, 4 * kRingPitch, warp, feed, args.progress + c, lane,
               t_wait);
 #pragma unroll
