@@ -251,6 +251,98 @@ static int chol_batched(ddb_ctx* ctx, double* base, size_t stride, int ld, const
 // triangular solves with a row-major lower factor: z <- L^-T L^-1 z, one CTA per (rhs, matrix)
 //   z vector b, r lives at zbase + (b * nrhs + r) * zstride
 // ---------------------------------------------------------------------------------------------
+// RPC right-hand sides per CTA (RPC = 1 for the per-target solves of the sweep; 4 when one matrix serves many
+// right-hand sides -- inverse, DMD operator -- so that every element of L read from L2 is used four times).
+template <int RPC>
+__global__ void __launch_bounds__(256) chol_solve_kernel_t(const double* Lbase, size_t lstride, int ld,
+                                                           const int* na_arr, int na_all, double* zbase, size_t zstride,
+                                                           int nrhs, const int* active_matrix, const int* zmap) {
+    const int b = blockIdx.y, r0 = blockIdx.x * RPC;
+    if (active_matrix && !active_matrix[b]) return;
+    const int na = na_arr ? na_arr[b] : na_all;
+    if (na <= 0) return;
+    const double* L = Lbase + (size_t)b * lstride;
+    double* zg = zbase + ((size_t)(zmap ? zmap[b] : b) * nrhs + r0) * zstride;
+    const int nr = min(RPC, nrhs - r0);
+    extern __shared__ double sm[];
+    const int zp = ((na + 31) / 32) * 32;
+    double* z = sm;                   // RPC x zp
+    double* blk = sm + RPC * zp;      // 32 x 33
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int q = 0; q < RPC; ++q)
+        for (int i = tid; i < na; i += blockDim.x) z[q * zp + i] = (q < nr) ? zg[(size_t)q * zstride + i] : 0.0;
+    __syncthreads();
+    // forward: L y = z
+    for (int j0 = 0; j0 < na; j0 += 32) {
+        const int nb = min(32, na - j0);
+        for (int e = tid; e < 32 * 32; e += blockDim.x) {
+            const int i = e / 32, j = e % 32;
+            blk[i * 33 + j] = (i < nb && j <= i) ? L[(size_t)(j0 + i) * ld + j0 + j] : (i == j ? 1.0 : 0.0);
+        }
+        __syncthreads();
+        if (warp < RPC) {  // warp q substitutes right-hand side q
+            double* zq = z + warp * zp;
+            double zi = (lane < nb) ? zq[j0 + lane] : 0.0;
+            for (int c = 0; c < nb; ++c) {
+                const double zc = __shfl_sync(0xffffffffu, zi, c) / blk[c * 33 + c];
+                if (lane == c) zi = zc;
+                if (lane > c) zi -= blk[lane * 33 + c] * zc;
+            }
+            if (lane < nb) zq[j0 + lane] = zi;
+        }
+        __syncthreads();
+        for (int i = j0 + nb + tid; i < na; i += blockDim.x) {
+            const double* row = L + (size_t)i * ld + j0;
+            double s[RPC];
+#pragma unroll
+            for (int q = 0; q < RPC; ++q) s[q] = 0.0;
+            for (int c = 0; c < nb; ++c) {
+                const double l = row[c];
+#pragma unroll
+                for (int q = 0; q < RPC; ++q) s[q] = fma(l, z[q * zp + j0 + c], s[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < RPC; ++q) z[q * zp + i] -= s[q];
+        }
+        __syncthreads();
+    }
+    // backward: L' x = y
+    for (int j0 = ((na - 1) / 32) * 32; j0 >= 0; j0 -= 32) {
+        const int nb = min(32, na - j0);
+        for (int e = tid; e < 32 * 32; e += blockDim.x) {
+            const int i = e / 32, j = e % 32;
+            blk[i * 33 + j] = (i < nb && j <= i) ? L[(size_t)(j0 + i) * ld + j0 + j] : (i == j ? 1.0 : 0.0);
+        }
+        __syncthreads();
+        if (warp < RPC) {
+            double* zq = z + warp * zp;
+            double zi = (lane < nb) ? zq[j0 + lane] : 0.0;
+            for (int c = nb - 1; c >= 0; --c) {
+                const double zc = __shfl_sync(0xffffffffu, zi, c) / blk[c * 33 + c];
+                if (lane == c) zi = zc;
+                if (lane < c) zi -= blk[c * 33 + lane] * zc;
+            }
+            if (lane < nb) zq[j0 + lane] = zi;
+        }
+        __syncthreads();
+        for (int j = tid; j < j0; j += blockDim.x) {
+            double s[RPC];
+#pragma unroll
+            for (int q = 0; q < RPC; ++q) s[q] = 0.0;
+            for (int c = 0; c < nb; ++c) {
+                const double l = L[(size_t)(j0 + c) * ld + j];
+#pragma unroll
+                for (int q = 0; q < RPC; ++q) s[q] = fma(l, z[q * zp + j0 + c], s[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < RPC; ++q) z[q * zp + j] -= s[q];
+        }
+        __syncthreads();
+    }
+    for (int q = 0; q < nr; ++q)
+        for (int i = tid; i < na; i += blockDim.x) zg[(size_t)q * zstride + i] = z[q * zp + i];
+}
+
 __global__ void __launch_bounds__(256) chol_solve_kernel(const double* Lbase, size_t lstride, int ld,
                                                          const int* na_arr, int na_all, double* zbase, size_t zstride,
                                                          int nrhs, const int* active_matrix, const int* zmap) {
@@ -330,8 +422,15 @@ int chol_solve_many(ddb_ctx* ctx, const double* L, int k, double* Z, int nrhs) {
         set_error("triangular solver: order %d exceeds the shared-memory right-hand-side buffer", k);
         return DDB_UNSUPPORTED;
     }
-    DDB_CUDA_TRY(cudaFuncSetAttribute(chol_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
-    chol_solve_kernel<<<dim3(nrhs, 1), 256, solve_smem, ctx->stream>>>(L, 0, k, nullptr, k, Z, (size_t)k, nrhs, nullptr, nullptr);
+    const size_t smem4 = ((size_t)4 * ((k + 31) / 32) * 32 + 32 * 33) * sizeof(double);
+    if (nrhs >= 4 * ctx->sm_count && smem4 <= 200 * 1024) {  // many right-hand sides: four per CTA share every load of L
+        DDB_CUDA_TRY(cudaFuncSetAttribute(chol_solve_kernel_t<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+        chol_solve_kernel_t<4><<<dim3((nrhs + 3) / 4, 1), 256, smem4, ctx->stream>>>(L, 0, k, nullptr, k, Z, (size_t)k, nrhs,
+                                                                                    nullptr, nullptr);
+    } else {
+        DDB_CUDA_TRY(cudaFuncSetAttribute(chol_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
+        chol_solve_kernel<<<dim3(nrhs, 1), 256, solve_smem, ctx->stream>>>(L, 0, k, nullptr, k, Z, (size_t)k, nrhs, nullptr, nullptr);
+    }
     DDB_CUDA_TRY(cudaGetLastError());
     return DDB_OK;
 }
@@ -1269,8 +1368,7 @@ int sweep_run(ddb_ctx* ctx, const ddb_sweep_params* prm, const double* lambdas, 
             DDB_TRY(S->Ninv.reserve(kk * 8));
             implicit_prep_kernel<<<(unsigned)((kk + 255) / 256), 256, 0, st>>>(S->Ninv.as<double>(),
                                                                                implicit ? S->znew.as<double>() : nullptr, k);
-            chol_solve_kernel<<<dim3(k, 1), 256, solve_smem, st>>>(S->Lfac.as<double>(), 0, k, nullptr, k,
-                                                                   S->Ninv.as<double>(), (size_t)k, k, nullptr, nullptr);
+            DDB_TRY(chol_solve_many(ctx, S->Lfac.as<double>(), k, S->Ninv.as<double>(), k));
             launches += 2;
         }
         chol_solve_kernel<<<dim3(n_t, 1), 256, solve_smem, st>>>(S->Lfac.as<double>(), 0, k, nullptr, k,
