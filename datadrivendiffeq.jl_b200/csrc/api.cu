@@ -46,6 +46,7 @@ int generate_run(ddb_ctx* ctx, int system_id, int n_states, int64_t m, int64_t f
 void sweep_free(ddb_ctx* ctx);
 void dmd_free(ddb_ctx* ctx);
 void ring_free(ddb_ctx* ctx);
+void trsm_free(ddb_ctx* ctx);
 
 }  // namespace ddb
 
@@ -106,6 +107,7 @@ int ddb_ctx_destroy(ddb_ctx* ctx) {
     sweep_free(ctx);
     dmd_free(ctx);
     ring_free(ctx);
+    trsm_free(ctx);
     ctx->d_factors.release();
     ctx->own_X.release();
     ctx->own_Y.release();

@@ -74,6 +74,7 @@ void build_plan_from_pairs(GramPlan& plan, const std::vector<std::pair<int, int>
 struct SweepState;
 struct DmdState;
 struct RingState;
+struct TrsmState;
 
 }  // namespace ddb
 
@@ -135,6 +136,7 @@ struct ddb_ctx {
     ddb::SweepState* sweep = nullptr;
     ddb::DmdState* dmd = nullptr;
     ddb::RingState* ring = nullptr;
+    ddb::TrsmState* trsm = nullptr;
 
     ddb_timings timings = {};
 };

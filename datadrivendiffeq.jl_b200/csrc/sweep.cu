@@ -416,7 +416,12 @@ __global__ void __launch_bounds__(256) chol_solve_kernel(const double* Lbase, si
 int chol_factor_shared(ddb_ctx* ctx, double* A, int k, int* d_fail, int* launches) {
     return chol_batched(ctx, A, 0, k, nullptr, k, 1, d_fail, launches);
 }
+int trsm_gemm_solve(ddb_ctx* ctx, const double* L, size_t ld, int k, double* Z, int nrhs, int* launches);
+
 int chol_solve_many(ddb_ctx* ctx, const double* L, int k, double* Z, int nrhs) {
+    // many right-hand sides: blocked substitution whose bulk is DMMA GEMM (trsm.cu)
+    const char* tenv = getenv("DDB_TRSM_GEMM");
+    if ((tenv ? atoi(tenv) != 0 : true) && nrhs >= 256 && k >= 256) return trsm_gemm_solve(ctx, L, (size_t)k, k, Z, nrhs, nullptr);
     const size_t solve_smem = ((size_t)((k + 31) / 32) * 32 + 32 * 33) * sizeof(double);
     if (solve_smem > 200 * 1024) {
         set_error("triangular solver: order %d exceeds the shared-memory right-hand-side buffer", k);
