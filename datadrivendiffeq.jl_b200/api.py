@@ -71,6 +71,10 @@ class Basis:
     # generators sin_basis / cos_basis / fourier_basis / chebyshev_basis and their products with monomials
     features: Optional[List[tuple]] = None
     n_raw: int = 0  # number of raw states when `features` is set
+    # Variable order of the rows of `exponents` (the argument order of the generated function,
+    # src/basis/build_function.jl:6-38): [states | controls | independent variable | implicits]
+    controls: int = 0  # rows that are control inputs (``Basis(...; controls = u)``), evaluated on the problem's U
+    use_time: bool = False  # one row for the independent variable (``iv = t``), evaluated on the problem's t
 
     def __post_init__(self):
         e = np.asarray(self.exponents)
@@ -92,7 +96,7 @@ class Basis:
         """States the PROBLEM must provide."""
         if self.features is not None:
             return int(self.n_raw)
-        return self.exponents.shape[0] - int(self.implicits)
+        return self.exponents.shape[0] - int(self.implicits) - int(self.controls) - int(bool(self.use_time))
 
     @property
     def n_variables(self) -> int:
@@ -102,7 +106,8 @@ class Basis:
     def implicit_idx(self) -> np.ndarray:
         """``implicit_idx[i, j]``: term i depends on implicit variable j (``is_dependent`` table the reference
         builds for an implicit ``Basis``)."""
-        return (self.exponents[self.n_states:, :] > 0).T.copy()
+        lo = self.exponents.shape[0] - int(self.implicits)
+        return (self.exponents[lo:, :] > 0).T.copy()
 
     def __len__(self) -> int:
         return self.exponents.shape[1]
@@ -119,7 +124,9 @@ class Basis:
                     arg = f"x{src + 1}" if coef == 1.0 else f"{coef:g}*x{src + 1}"
                     nm = f"{fn}({arg})" if fn else arg
                 else:
-                    nm = f"x{i + 1}" if i < self.n_states else f"dx{i - self.n_states + 1}"
+                    ns, nc, nt = self.n_states, int(self.controls), int(bool(self.use_time))
+                    nm = (f"x{i + 1}" if i < ns else f"u{i - ns + 1}" if i < ns + nc else "t" if i < ns + nc + nt
+                          else f"dx{i - ns - nc - nt + 1}")
                 if p == 1:
                     parts.append(nm)
                 elif p > 1:
@@ -179,8 +186,8 @@ def concat_bases(bases: Sequence[Basis]) -> Basis:
     index = {f: i for i, f in enumerate(feats)}
     cols = []
     for b in bases:
-        if b.implicits:
-            raise ValueError("concat_bases: bases with implicit variables are not supported")
+        if b.implicits or b.controls or b.use_time:
+            raise ValueError("concat_bases: bases with implicit variables, controls or time are not supported")
         if b.n_states != n_raw:
             raise ValueError("concat_bases: all bases must be over the same states")
         bf = b.features if b.features is not None else [(FEAT_IDENTITY, i, 1.0) for i in range(n_raw)]
@@ -232,7 +239,7 @@ class DataDrivenProblem:
     DX: Optional[np.ndarray] = None
     Y: Optional[np.ndarray] = None
     t: Optional[np.ndarray] = None
-    U: Optional[np.ndarray] = None  # control inputs (DataDrivenDMD only; the sparse path rejects controls)
+    U: Optional[np.ndarray] = None  # control inputs (n_u x m): DMDc, and libraries with `controls`
 
     def __post_init__(self):
         self.X = np.asarray(self.X, dtype=np.float64)
@@ -256,18 +263,18 @@ class DataDrivenProblem:
         return self.X[:, :-1], self.X[:, 1:]
 
 
-def ContinuousDataDrivenProblem(X, t=None, DX=None) -> DataDrivenProblem:
+def ContinuousDataDrivenProblem(X, t=None, DX=None, U=None) -> DataDrivenProblem:
     if DX is None:
         raise ValueError("the B200 backend needs DX (collocation is out of scope: SURVEY.md section 2)")
-    return DataDrivenProblem(X=X, kind="continuous", DX=DX, t=t)
+    return DataDrivenProblem(X=X, kind="continuous", DX=DX, t=t, U=U)
 
 
 def DiscreteDataDrivenProblem(X, t=None, U=None) -> DataDrivenProblem:
     return DataDrivenProblem(X=X, kind="discrete", t=t, U=U)
 
 
-def DirectDataDrivenProblem(X, Y, t=None) -> DataDrivenProblem:
-    return DataDrivenProblem(X=X, kind="direct", Y=Y, t=t)
+def DirectDataDrivenProblem(X, Y, t=None, U=None) -> DataDrivenProblem:
+    return DataDrivenProblem(X=X, kind="direct", Y=Y, t=t, U=U)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -462,6 +469,23 @@ def get_fit_targets(alg: B200Sparse, prob: DataDrivenProblem, basis: Basis):
     X, Y = prob.fit_inputs()
     if X.shape[0] != basis.n_states:
         raise ValueError(f"basis has {basis.n_states} states but the problem has {X.shape[0]}")
+    if basis.controls or basis.use_time:
+        # the library is a function of (states, controls, t): evaluated on the stacked rows (get_oop_args,
+        # src/problem/type.jl:444-455); to the kernels controls and time are just more "states"
+        if basis.features is not None:
+            raise ValueError("controls / time in a library over a feature map are not supported")
+        m = X.shape[1]
+        rows = [X]
+        if basis.controls:
+            if prob.U is None or np.atleast_2d(prob.U).shape[0] != basis.controls:
+                raise ValueError(f"basis has {basis.controls} control inputs but the problem provides "
+                                 f"{0 if prob.U is None else np.atleast_2d(prob.U).shape[0]}")
+            rows.append(np.atleast_2d(np.asarray(prob.U, dtype=np.float64))[:, :m])
+        if basis.use_time:
+            if prob.t is None:
+                raise ValueError("the basis depends on the independent variable but the problem has no time points")
+            rows.append(np.asarray(prob.t, dtype=np.float64).reshape(1, -1)[:, :m])
+        X = np.vstack(rows)
     if basis.implicits:
         # the library is evaluated on (implicits = get_implicit_data(prob), states); type.jl:433-455
         if Y.shape[0] != basis.implicits:

@@ -97,3 +97,34 @@ def test_feature_map_errors(ctx):
     with pytest.raises(ddb200._lib.DDBError):
         ctx.set_features(2, [(1, 2, 1.0)])  # source out of range
     ctx.set_features(0, None)
+
+
+def test_library_with_controls_and_time(ctx):
+    """``Basis(eqs, x; controls = u, iv = t)``: to the kernels control inputs and the independent variable are
+    more columns of the staged samples.  Forced linear system (the shape of
+    ``lib/DataDrivenDMD/test/Core/linear_forced.jl:12-20``) with an explicitly time-dependent drift."""
+    rng = np.random.default_rng(2)
+    m = 1500
+    t = np.linspace(0.0, 30.0, m)
+    X = rng.uniform(-2, 2, size=(2, m))
+    U = np.sin(t)[None, :]
+    DX = np.vstack([-0.9 * X[0] + 0.1 * X[1], -0.8 * X[1] + 3.0 * U[0] + 0.05 * t])
+    # variables: [x1, x2 | u1 | t]; library = all monomials of degree <= 2 in the four variables
+    ex = oracle.polynomial_exponents(4, 2)
+    basis = ddb200.Basis(ex, controls=1, use_time=True)
+    assert basis.n_states == 2 and "u1" in basis.term_strings() and "t" in basis.term_strings()
+    lams = 10.0 ** np.arange(-3, -0.9, 0.5)
+    alg = ddb200.B200Sparse(ddb200.STLSQ(lams))
+    alg._ctx = ctx
+    sol = ddb200.solve(ddb200.ContinuousDataDrivenProblem(X, t=t, DX=DX, U=U), basis, alg)
+    Th = oracle.evaluate_library(ex, np.vstack([X, U, t[None, :]]))
+    ref = oracle.sparse_regression(oracle.STLSQ(lams), Th, DX)
+    C = sol.results[0].coefficients
+    np.testing.assert_array_equal(C != 0.0, ref.coefficients != 0.0)
+    np.testing.assert_allclose(C, ref.coefficients, rtol=1e-9, atol=1e-12)
+    names = basis.term_strings()
+    got = {names[j]: C[1, j] for j in np.nonzero(C[1])[0]}
+    assert set(got) == {"x2", "u1", "t"}
+    assert got["u1"] == pytest.approx(3.0, rel=1e-9) and got["t"] == pytest.approx(0.05, rel=1e-9)
+    with pytest.raises(ValueError):
+        ddb200.solve(ddb200.ContinuousDataDrivenProblem(X, t=t, DX=DX), basis, alg)  # no control data
