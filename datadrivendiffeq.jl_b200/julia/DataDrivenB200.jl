@@ -150,6 +150,11 @@ end
 function CommonSolve.solve!(ps::InternalDataDrivenProblem{<:B200Sparse})
     (; alg, basis, traindata, testdata, problem, options) = ps
     options.denoise && throw(ArgumentError("B200Sparse: denoise=true is not supported"))
+    # `init` fitted the normalisation on what get_fit_targets returned -- the RAW states, not Theta -- so anything
+    # but the identity transform would silently change the problem (the Python host layer implements ZScore on the
+    # Gram blocks, `ddb_gram_scale_terms`; this glue does not yet)
+    options.normalize isa DataDrivenDiffEq.DataNormalization{Nothing} ||
+        throw(ArgumentError("B200Sparse: only DataNormalization() (no normalisation) is supported by the Julia glue"))
     options.data_processing.split == 1.0 && options.data_processing.batchsize <= 0 ||
         throw(ArgumentError("B200Sparse: train/test split and mini-batches are not supported"))
     X, Y = first(traindata)          # single batch; column order is irrelevant to the Gram sums
