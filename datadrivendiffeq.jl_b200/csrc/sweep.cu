@@ -52,6 +52,13 @@ __device__ __forceinline__ int block_sum_int(int v, int* red) {
 // ---------------------------------------------------------------------------------------------
 // preparation: A = G + rho I, equilibrate, scaled right-hand sides
 // ---------------------------------------------------------------------------------------------
+// check_domain of the reference (src/problem/type.jl:418-420) for data that never passed through the host
+// mirror: NaN / Inf samples end up in the normal-equation blocks, where one pass finds them
+__global__ void nonfinite_check_kernel(const double* __restrict__ packed, size_t count, int* __restrict__ flag) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count && !isfinite(packed[i])) atomicExch(flag, 1);
+}
+
 __global__ void prep_diag_kernel(const double* __restrict__ G, int k, double rho, double* __restrict__ dinv) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= k) return;
@@ -1348,6 +1355,11 @@ int sweep_run(ddb_ctx* ctx, const ddb_sweep_params* prm, const double* lambdas, 
     const double* G = implicit ? ctx->imp_packed.as<double>() : ctx->d_packed.as<double>();
     const double* R = G + kk;
     const double rho = prm->rho;  // 0 for plain STLSQ
+    {
+        const size_t count = kk + nk + (size_t)n_t;
+        nonfinite_check_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(G, count, S->shared_fail.as<int>() + 1);
+        ++launches;
+    }
     prep_diag_kernel<<<(k + 255) / 256, 256, 0, st>>>(G, k, rho, S->dinv.as<double>());
     prep_scale_kernel<<<(unsigned)((kk + 255) / 256), 256, 0, st>>>(G, k, rho, S->dinv.as<double>(), S->As.as<double>());
     prep_rhs_kernel<<<(unsigned)((nk + 255) / 256), 256, 0, st>>>(R, k, n_t, S->dinv.as<double>(), S->rs.as<double>());
@@ -1454,7 +1466,9 @@ int sweep_run(ddb_ctx* ctx, const ddb_sweep_params* prm, const double* lambdas, 
     unsigned long long h_pool = 0;
     DDB_CUDA_TRY(cudaMemcpyAsync(h_counters, S->counters.p, sizeof(h_counters), cudaMemcpyDeviceToHost, st));
     DDB_CUDA_TRY(cudaMemcpyAsync(&h_pool, S->pool_used_d.p, 8, cudaMemcpyDeviceToHost, st));
+    int h_nonfinite = 0;
     DDB_CUDA_TRY(cudaMemcpyAsync(&h_shared_fail, S->shared_fail.p, 4, cudaMemcpyDeviceToHost, st));
+    DDB_CUDA_TRY(cudaMemcpyAsync(&h_nonfinite, S->shared_fail.as<int>() + 1, 4, cudaMemcpyDeviceToHost, st));
     DDB_CUDA_TRY(cudaStreamSynchronize(st));
     if (h_counters[1]) {
         set_error("ddb_sweep: candidate storage overflow");
@@ -1471,6 +1485,11 @@ int sweep_run(ddb_ctx* ctx, const ddb_sweep_params* prm, const double* lambdas, 
     S->ncand = h_counters[0];
     S->pool_used = (int64_t)h_pool;
     S->valid = true;
+    if (h_nonfinite) {
+        S->valid = false;
+        set_error("ddb_sweep: the normal-equation blocks contain NaN or Inf (one or more measurements contain `NaN` or `Inf`)");
+        return DDB_NONFINITE_INPUT;
+    }
     if (h_shared_fail) {
         set_error("ddb_sweep: the equilibrated normal matrix is not positive definite (rank-deficient library "
                   "or fewer samples than terms); this backend solves through the Gram matrix and has no QR fallback");

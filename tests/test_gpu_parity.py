@@ -423,3 +423,20 @@ def test_c3_library_size_noisy_matches_oracle(ctx):
     np.testing.assert_array_equal(out.coefficients != 0, nz)
     assert (np.abs(out.coefficients[nz] - ref.coefficients[nz]) / np.abs(ref.coefficients[nz])).max() <= COEF_RTOL
     np.testing.assert_allclose(out.lambda_opt, ref.lambdas, rtol=1e-15)
+
+
+def test_nonfinite_samples_are_reported(ctx):
+    """``check_domain`` (src/problem/type.jl:418-420): NaN / Inf measurements are an error, also for data
+    that were bound on the device and never seen by the host mirror."""
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((3, 500))
+    Y = rng.standard_normal((3, 500))
+    X[1, 77] = np.nan
+    ctx.set_library(oracle.polynomial_exponents(3, 2))
+    ctx.upload(X, Y)
+    ctx.gram()
+    with pytest.raises(ddb200._lib.DDBError) as e:
+        ctx.sweep(ctx.make_params("STLSQ"), [0.1])
+    assert e.value.status == -6
+    with pytest.raises(ValueError):
+        ddb200.ContinuousDataDrivenProblem(X, DX=Y)  # the host mirror refuses them up front
