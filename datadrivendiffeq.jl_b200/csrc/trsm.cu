@@ -157,19 +157,14 @@ __global__ void __launch_bounds__(256) transpose_kernel(const double* __restrict
 struct TrsmState {
     DevBuf linv, linvT, lt;
 };
-static TrsmState* g_dummy = nullptr;  // (per-context state lives in ddb_ctx::trsm)
 
 template <bool ASSIGN>
 static int launch_gemm(ddb_ctx* ctx, double* D, size_t ldd, const double* A, size_t lda, const double* B, size_t ldb,
                        int rows, int cols, int K) {
     if (rows <= 0 || cols <= 0 || K <= 0) return DDB_OK;
     const size_t smem = 2 * (size_t)kGStage * sizeof(double);
-    static bool set_a = false, set_s = false;
-    bool& done = ASSIGN ? set_a : set_s;
-    if (!done) {
-        DDB_CUDA_TRY(cudaFuncSetAttribute(gemm_nt_kernel<ASSIGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        done = true;
-    }
+    // (per device and cheap: no caching, a process may drive several GPUs through several contexts)
+    DDB_CUDA_TRY(cudaFuncSetAttribute(gemm_nt_kernel<ASSIGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     gemm_nt_kernel<ASSIGN><<<dim3((cols + kGT - 1) / kGT, (rows + kGT - 1) / kGT), 256, smem, ctx->stream>>>(D, ldd, A, lda, B, ldb,
                                                                                                           rows, cols, K);
     return DDB_OK;
@@ -178,7 +173,6 @@ static int launch_gemm(ddb_ctx* ctx, double* D, size_t ldd, const double* A, siz
 // Z (nrhs x k, row-major, leading dimension k) <- Z (L L')^-1  i.e. every ROW of Z is solved against the factor
 // L (k x k lower, row-major, leading dimension ld).
 int trsm_gemm_solve(ddb_ctx* ctx, const double* L, size_t ld, int k, double* Z, int nrhs, int* launches) {
-    (void)g_dummy;
     if (!ctx->trsm) ctx->trsm = new TrsmState();
     TrsmState* T = ctx->trsm;
     const int nblk = (k + kGT - 1) / kGT;
