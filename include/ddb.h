@@ -227,7 +227,12 @@ int ddb_sweep(ddb_ctx* ctx, const ddb_sweep_params* params, const double* lambda
 int64_t ddb_rss_count(const ddb_ctx* ctx);
 /* Exact residual sums of squares of every candidate over this context's bound samples (second
  * streaming pass; replaces rss(cache), DataDrivenSparse.jl:173-176, called by the selector at
- * solver.jl:100).  dRss: device buffer of ddb_rss_count() doubles or NULL for the context's own. */
+ * solver.jl:100).  dRss: device buffer of ddb_rss_count() doubles or NULL for the context's own.
+ * The table holds the STREAMED part of every candidate's rss, a plain sum over samples (so the tables of the
+ * ranks of a sharded run are combined with one sum all-reduce before ddb_select): the value of the candidate's
+ * representative -- candidates that share a (target, support) are represented by the least-squares point c0 of
+ * that support, zero models by nothing (0).  The remainder, rss(c) - rss(c0) = (c - c0)' G_SS (c - c0) -
+ * 2 (c - c0)' (r_S - G_SS c0) resp. yy, is exact Gram arithmetic and is added by ddb_select. */
 int ddb_rss(ddb_ctx* ctx, double* dRss);
 int ddb_rss_buffer(ddb_ctx* ctx, double** dRss);
 
