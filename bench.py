@@ -27,7 +27,10 @@ METRIC = "samples/sec through fused Theta+Gram; STLSQ lambda-sweep wall-time; % 
 # tools/fp64_peak.cu (profiles/fp64_peak_r1.json): DMMA issue-rate peak 37.0 TF, cublasDgemm 8192^3 35.9 TF.
 FP64_DMMA_PEAK_TFLOPS = 37.0
 CUBLAS_DGEMM_TFLOPS = 35.9
-C3_RING_DRAM_BYTES_PER_SAMPLE = (10353717248 + 28262912) / 1e7  # ncu, profiles/dram_traffic_r1c_c3_1e7.csv
+# DRAM read traffic of the two Gram kernels per sample (ncu dram__bytes_read.sum at 1e6 samples,
+# profiles/gram_traffic_r1g_c3_1e6.csv): gram_ring_kernel 1041 B (the algorithmic 1024 B + ring spill) and the
+# diagonal-pair pass of gram_kernel 1886 B (its 9 sample ranges x 16 pairs share tiles through L2)
+C3_RING_DRAM_BYTES_PER_SAMPLE = (1041148928 + 1886253824) / 1e6
 
 WORKLOADS = {
     "c3": dict(system=1, n=64, degree=2, m=10_000_000, name="Lorenz-96 n=64, degree-2 library (2145 terms), 1e7 samples, 41-lambda STLSQ"),
@@ -418,8 +421,8 @@ def main():
                 "achieved": achieved, "peak": FP64_DMMA_PEAK_TFLOPS,
                 "unit": "TFLOP/s", "frac": achieved / FP64_DMMA_PEAK_TFLOPS,
                 "traffic": (C3_RING_DRAM_BYTES_PER_SAMPLE * m_local if args.workload == "c3" else None),
-                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of gram_ring_kernel, ncu capture of this command at 1e7 "
-                                  "samples (profiles/dram_traffic_r1c_c3_1e7.csv: 10.354 GB + 0.028 GB), scaled by samples per launch",
+                "traffic_source": "dram__bytes_read.sum of gram_ring_kernel (1.041 GB) + gram_kernel diagonal-pair pass (1.886 GB) per 1e6 "
+                                  "samples, ncu (profiles/gram_traffic_r1g_c3_1e6.csv), scaled by samples per launch",
                 "peak_source": "measured on this pool with tools/fp64_peak.cu (DMMA issue-rate; profiles/fp64_peak_r1.json); "
                                "MEASURED_PEAKS.json has no FP64 figure",
                 "frac_of_cublas_dgemm": achieved / CUBLAS_DGEMM_TFLOPS, "algorithmic_flops_per_sample": F,

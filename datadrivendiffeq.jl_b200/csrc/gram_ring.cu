@@ -588,7 +588,43 @@ int gram_ring_run(ddb_ctx* ctx, double* dPacked, bool* handled) {
         GramPlan pb;
         R->have_rest = !rest.empty();
         if (R->have_rest) {
-            build_plan_from_pairs(pb, rest, rest_cost, ctx->m, ctx->sm_count, kRingBT, kKS);
+            const int nrest = (int)rest.size();
+            const int nranges = ctx->sm_count / nrest;
+            const int64_t ns = (ctx->m + kKS - 1) / kKS;
+            if (nranges >= 2 && ns >= nranges) {
+                // Lock-step plan: the sample stream is cut into `nranges` ranges and CTA r * nrest + p runs pair p
+                // over range r, so the nrest CTAs of a range walk the same samples at the same time and every
+                // X / Y tile comes from HBM once and from L2 for the other pairs (the cost-balanced stream split
+                // of build_plan_from_pairs made each pair's CTAs read the whole input again: 16 x the traffic).
+                pb = GramPlan();
+                pb.bt = kRingBT;
+                pb.ks = kKS;
+                pb.npairs = nrest;
+                pb.nctas = ctx->sm_count;
+                pb.nstages = ns;
+                pb.pairs = rest;
+                pb.cta_seg_begin.assign(ctx->sm_count + 1, 0);
+                pb.pair_slot_begin.assign(nrest + 1, 0);
+                for (int p = 0; p <= nrest; ++p) pb.pair_slot_begin[p] = p * nranges;
+                for (int c = 0; c < ctx->sm_count; ++c) {
+                    pb.cta_seg_begin[c] = (int32_t)pb.segments.size();
+                    if (c < nranges * nrest) {
+                        const int r = c / nrest, p = c % nrest;
+                        GramSegment sg;
+                        sg.bi = rest[p].first;
+                        sg.bj = rest[p].second;
+                        sg.slot = p * nranges + r;
+                        sg.pad = 0;
+                        sg.stage_begin = ns * r / nranges;
+                        sg.stage_end = ns * (r + 1) / nranges;
+                        pb.segments.push_back(sg);
+                    }
+                }
+                pb.cta_seg_begin[ctx->sm_count] = (int32_t)pb.segments.size();
+                pb.nslots = nrest * nranges;
+            } else {
+                build_plan_from_pairs(pb, rest, rest_cost, ctx->m, ctx->sm_count, kRingBT, kKS);
+            }
             for (auto& sgm : pb.segments) sgm.slot += nslots;
             for (size_t j = 0; j < rest.size(); ++j) {
                 all_pairs.push_back(make_int2(rest[j].first, rest[j].second));
