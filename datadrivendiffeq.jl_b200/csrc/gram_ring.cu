@@ -71,6 +71,7 @@ struct RingArgs {
     int win_doubles;          // doubles per window of the global ring
     int64_t m;
     int nprod, ncons;
+    int prod_bufs, prod_stride;  // producer staging tiles (1 or 2) and their stride in doubles
     const uint16_t* factors;
     const RingCons* cons;
     // global ring, kRingWindows windows of [block][sample 0..63][pitch]: one (block, stage) operand tile is
@@ -88,6 +89,15 @@ __device__ __forceinline__ unsigned long long ld_acquire(const unsigned long lon
 }
 __device__ __forceinline__ void st_release(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src)
+                 : "memory");
 }
 
 // The TMA side of a consumer, run by one warp at a time between its DMMAs: lane l < nops copies operand tile l of a
@@ -316,11 +326,42 @@ __global__ void __launch_bounds__(kRingThreads, 1) gram_ring_kernel(const RingAr
                     }
                 }
             }
-        for (int e = tid; e < kWin + 2; e += kRingThreads) v[e] = (e < kWin) ? 1.0 : 0.0;
+        // two staging tiles: the X/Y rows of this producer's next window are fetched with cp.async while
+        // the current one is multiplied out (one tile when two do not fit in shared memory)
+        const int vstride = args.prod_stride;
+        for (int e = tid; e < kWin + 2; e += kRingThreads) {
+            v[e] = (e < kWin) ? 1.0 : 0.0;
+            if (args.prod_bufs == 2) v[vstride + e] = (e < kWin) ? 1.0 : 0.0;
+        }
+        auto stage_window = [&](int64_t w, double* vb) {
+            const int64_t s0 = w * kWin;
+            const int valid = (int)min((int64_t)kWin, args.m - s0);
+            const double* gx = args.X + s0 * n;
+            const double* gy = args.Y + s0 * n_t;
+            const int nx = valid * n, ny = valid * n_t;
+            if ((((uintptr_t)gx | (uintptr_t)gy) & 15) == 0 && ((nx | ny) & 1) == 0) {
+                for (int e = 2 * tid; e < nx; e += 2 * kRingThreads) cp_async16(vb + kX + e, gx + e);
+                for (int e = 2 * tid; e < ny; e += 2 * kRingThreads) cp_async16(vb + kX + kWin * n + e, gy + e);
+            } else {
+                for (int e = tid; e < nx; e += kRingThreads) cp_async8(vb + kX + e, gx + e);
+                for (int e = tid; e < ny; e += kRingThreads) cp_async8(vb + kX + kWin * n + e, gy + e);
+            }
+            if (valid < kWin) {  // ragged last window: zero rows, and a zero "ones" column for them
+                for (int e = nx + tid; e < kWin * n; e += kRingThreads) vb[kX + e] = 0.0;
+                for (int e = ny + tid; e < kWin * n_t; e += kRingThreads) vb[kX + kWin * n + e] = 0.0;
+                for (int e = tid; e < kWin; e += kRingThreads) vb[kOnes + e] = (e < valid) ? 1.0 : 0.0;
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
 #ifdef DDB_RING_TIMING
         long long tp_wait = 0, tp_all = clock64(), tp0;
 #endif
+        int cur = 0;
+        if ((int64_t)blockIdx.x < nwin) stage_window(blockIdx.x, v);
         for (int64_t w = blockIdx.x; w < nwin; w += args.nprod) {
+            const double* vb = v + cur * vstride;
+            const bool ahead = args.prod_bufs == 2 && w + args.nprod < nwin;
+            if (ahead) stage_window(w + args.nprod, v + (cur ^ 1) * vstride);
 #ifdef DDB_RING_TIMING
             tp0 = clock64();
 #endif
@@ -337,13 +378,10 @@ __global__ void __launch_bounds__(kRingThreads, 1) gram_ring_kernel(const RingAr
 #ifdef DDB_RING_TIMING
             tp_wait += clock64() - tp0;
 #endif
-            const int64_t s0 = w * kWin;
-            const int valid = (int)min((int64_t)kWin, args.m - s0);
-            for (int e = tid; e < kWin * n; e += kRingThreads) v[kX + e] = (e < valid * n) ? args.X[s0 * n + e] : 0.0;
-            for (int e = tid; e < kWin * n_t; e += kRingThreads)
-                v[kX + kWin * n + e] = (e < valid * n_t) ? args.Y[s0 * n_t + e] : 0.0;
-            if (valid < kWin)
-                for (int e = tid; e < kWin; e += kRingThreads) v[kOnes + e] = (e < valid) ? 1.0 : 0.0;
+            if (ahead)
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            else
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncthreads();
             double* zwin = args.zring + (size_t)(w % kRingWindows) * args.win_doubles;
 #pragma unroll
@@ -354,12 +392,12 @@ __global__ void __launch_bounds__(kRingThreads, 1) gram_ring_kernel(const RingAr
                     double* dst = zwin + dsto[q];
 #pragma unroll 4
                     for (int s = 0; s < kWin; ++s) {
-                        double p0 = v[off[q][0][0] + s * str[q][0][0]];
-                        double p1 = v[off[q][1][0] + s * str[q][1][0]];
+                        double p0 = vb[off[q][0][0] + s * str[q][0][0]];
+                        double p1 = vb[off[q][1][0] + s * str[q][1][0]];
 #pragma unroll
                         for (int d = 1; d < NF; ++d) {
-                            p0 *= v[off[q][0][d] + s * str[q][0][d]];
-                            p1 *= v[off[q][1][d] + s * str[q][1][d]];
+                            p0 *= vb[off[q][0][d] + s * str[q][0][d]];
+                            p1 *= vb[off[q][1][d] + s * str[q][1][d]];
                         }
                         if (keep) *reinterpret_cast<double2*>(dst + s * dstp[q]) = make_double2(p0, p1);
                     }
@@ -370,6 +408,10 @@ __global__ void __launch_bounds__(kRingThreads, 1) gram_ring_kernel(const RingAr
                 __threadfence();
                 st_release(args.done + blockIdx.x, (unsigned long long)(w / args.nprod + 1));
             }
+            if (args.prod_bufs == 2)
+                cur ^= 1;
+            else if (w + args.nprod < nwin)
+                stage_window(w + args.nprod, v);
         }
 #ifdef DDB_RING_TIMING
         if (tid == 0) printf("producer %d: all %lld wait %lld\n", blockIdx.x, clock64() - tp_all, tp_wait);
@@ -688,7 +730,10 @@ int gram_ring_run(ddb_ctx* ctx, double* dPacked, bool* handled) {
     a.progress = a.done + kMaxProducers;
     a.partials = R->partials.as<double>();
     const size_t smem_cons = 256 + (size_t)kRingSmemDoubles * sizeof(double);
-    const size_t smem_prod = (size_t)(kWin + 2 + kWin * (n + n_t)) * sizeof(double);
+    const int prod_stride = (kWin + 2 + kWin * (n + n_t) + 1) & ~1;
+    a.prod_stride = prod_stride;
+    a.prod_bufs = (size_t)2 * prod_stride * sizeof(double) <= smem_cons ? 2 : 1;
+    const size_t smem_prod = (size_t)a.prod_bufs * prod_stride * sizeof(double);
     const size_t smem = std::max(smem_cons, smem_prod);
     const void* kern = small_deg ? (const void*)gram_ring_kernel<2> : (const void*)gram_ring_kernel<8>;
     DDB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
