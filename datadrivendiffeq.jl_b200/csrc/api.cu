@@ -46,6 +46,7 @@ int generate_run(ddb_ctx* ctx, int system_id, int n_states, int64_t m, int64_t f
 void sweep_free(ddb_ctx* ctx);
 void dmd_free(ddb_ctx* ctx);
 void ring_free(ddb_ctx* ctx);
+void moment_free(ddb_ctx* ctx);
 void trsm_free(ddb_ctx* ctx);
 
 }  // namespace ddb
@@ -107,6 +108,7 @@ int ddb_ctx_destroy(ddb_ctx* ctx) {
     sweep_free(ctx);
     dmd_free(ctx);
     ring_free(ctx);
+    moment_free(ctx);
     trsm_free(ctx);
     ctx->d_factors.release();
     ctx->own_X.release();
@@ -153,6 +155,7 @@ int ddb_set_library_monomial(ddb_ctx* ctx, int n, int k, const uint8_t* exps) {
     ctx->k = k;
     ctx->max_degree = maxdeg;
     ctx->exps.assign(exps, exps + (size_t)n * k);
+    ctx->lib_version++;
     ctx->factors_nt = -1;
     ctx->plan_m = -1;
     ctx->have_gram = false;

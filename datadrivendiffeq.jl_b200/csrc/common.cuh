@@ -75,6 +75,7 @@ struct SweepState;
 struct DmdState;
 struct RingState;
 struct TrsmState;
+struct MomentState;
 
 }  // namespace ddb
 
@@ -89,6 +90,7 @@ struct ddb_ctx {
 
     // library
     int n = 0, k = 0, max_degree = 0;
+    uint64_t lib_version = 0;            // bumped by every ddb_set_library_monomial
     std::vector<uint8_t> exps;           // n x k
     ddb::DevBuf d_factors;               // (k + n_t) x kMaxFactors uint16, built when n_t is known
     int factors_nt = -1;
@@ -137,6 +139,7 @@ struct ddb_ctx {
     ddb::DmdState* dmd = nullptr;
     ddb::RingState* ring = nullptr;
     ddb::TrsmState* trsm = nullptr;
+    ddb::MomentState* moment = nullptr;
 
     ddb_timings timings = {};
 };

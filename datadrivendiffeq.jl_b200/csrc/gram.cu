@@ -614,6 +614,7 @@ void gram_reduce_launch(ddb_ctx* ctx, const double* partials, const int2* pairs,
 }
 int gram_ensure_factors(ddb_ctx* ctx, int rows);
 int gram_ring_run(ddb_ctx* ctx, double* dPacked, bool* handled);
+int gram_moment_run(ddb_ctx* ctx, double* dPacked, bool* handled);
 
 int gram_run(ddb_ctx* ctx, double* dPacked) {
     if (ctx->k <= 0) {
@@ -644,6 +645,8 @@ int gram_run(ddb_ctx* ctx, double* dPacked) {
     }
     if (bt == 128) {
         bool handled = false;
+        DDB_TRY(gram_moment_run(ctx, dPacked, &handled));
+        if (handled) return DDB_OK;
         DDB_TRY(gram_ring_run(ctx, dPacked, &handled));
         if (handled) return DDB_OK;
     }

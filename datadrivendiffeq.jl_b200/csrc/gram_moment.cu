@@ -1,0 +1,336 @@
+// Moment schedule of the fused library + Gram stage: the Gram matrix of a MONOMIAL library is a moment matrix.
+//
+// G[t, u] = sum_s theta_t(s) theta_u(s) only depends on the product monomial theta_t * theta_u, i.e. on the
+// multiset union of the two terms' factors.  A polynomial library of total degree D over n states (reference
+// src/utils/basis_generators.jl:84-126) has k(k+1)/2 Gram entries but only C(n + 2D, 2D) distinct moments: at
+// the Lorenz-96 configuration (n = 64, D = 2, k = 2145) that is 814 385 moments for 2 301 585 entries.  Every
+// moment is computed ONCE here, on the same FP64 DMMA kernel (gram.cu) as the plain schedule:
+//
+//   * a moment's 2D factors (padded with the constant 1 as variable 0), sorted, are cut in the middle:
+//     P = the D smallest, Q = the D largest, so that max(P) <= min(Q);
+//   * the distinct P's, sorted by max(P), are the ROWS of a virtual library, the distinct Q's, sorted by
+//     decreasing min(Q), its COLUMNS (the targets come first among the columns: R = Theta Y' needs every
+//     row; they are also appended to the rows for diag(Y Y'));
+//   * the needed (P, Q) entries then form a staircase in the rows x columns plane, and only the 128 x 128
+//     block pairs that the staircase touches are contracted: 78 at Lorenz-96 against 153 + 18 diagonal;
+//   * a gather kernel writes every entry of the packed [G | R | yy] from the tile entry of its moment
+//     (G comes out exactly symmetric, and bit-reproducible: fixed slot order, no atomics).
+//
+// Nothing about the data path changes: X / Y tiles arrive by TMA, the (virtual) terms are multiplied out in
+// shared memory, DMMA.8x8x4 accumulates in registers; Theta is never materialised.  The CTAs run the block
+// pairs in lock-step waves (pairs x sample ranges) so that concurrently running CTAs read the same X / Y
+// tiles and HBM sees every tile about once per wave.
+//
+// Libraries that are not closed under the split (a P or Q that is not itself cheap to add) still work: the
+// virtual rows / columns are whatever monomials the splits produce.  The schedule is used when it needs
+// fewer block pairs than the plain one (see `eligible` below); DDB_GRAM_MOMENT=0 disables it.
+#include "common.cuh"
+#include "mma_common.cuh"
+#include <algorithm>
+#include <array>
+#include <cstdlib>
+#include <cstring>
+#include <unordered_map>
+
+namespace ddb {
+
+int gram_launch_bt128(ddb_ctx* ctx, const GramArgs& args, int nctas);
+int gram_ensure_factors(ddb_ctx* ctx, int kaug_pad);
+
+namespace {
+
+constexpr int kBT = 128;
+using Key = std::array<uint16_t, kMaxFactors>;  // factor codes, ascending, leading zeros = the constant 1
+struct KeyHash {
+    size_t operator()(const Key& k) const {
+        uint64_t h = 0x9E3779B97F4A7C15ull;
+        for (int i = 0; i < kMaxFactors; ++i) h = (h ^ k[i]) * 0x100000001B3ull + (h >> 29);
+        return (size_t)h;
+    }
+};
+
+// sum over the slots of the entry's block pair, in slot order
+__global__ void __launch_bounds__(256) moment_gather_kernel(const double* __restrict__ partials,
+                                                            const int32_t* __restrict__ pair_slot_begin,
+                                                            const int32_t* __restrict__ src, int64_t count,
+                                                            double* __restrict__ packed) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= count) return;
+    const int32_t sv = src[e];
+    const int pair = sv >> 14, off = sv & (kBT * kBT - 1);
+    double s = 0.0;
+    for (int sl = pair_slot_begin[pair]; sl < pair_slot_begin[pair + 1]; ++sl)
+        s += partials[(size_t)sl * (kBT * kBT) + off];
+    packed[e] = s;
+}
+
+}  // namespace
+
+struct MomentState {
+    // library-dependent part
+    uint64_t lib_version = ~0ull;
+    int k = -1, n_t = -1;
+    bool eligible = false;
+    int nrb = 0, ncb = 0, nvirt = 0, npairs = 0;
+    std::vector<std::pair<int, int>> pairs;  // (row block, nrb + column block)
+    DevBuf factors, src;
+    // sample-count-dependent part
+    int64_t plan_m = -1;
+    int plan_nctas = -1;
+    int nslots = 0;
+    DevBuf plan, partials;
+    size_t off_cta = 0, off_psb = 0;
+};
+
+static int analyse_library(ddb_ctx* ctx, MomentState* M) {
+    const int k = ctx->k, n = ctx->n, n_t = ctx->n_t, D = ctx->max_degree;
+    M->eligible = false;
+    M->lib_version = ctx->lib_version;
+    M->k = k;
+    M->n_t = n_t;
+    if (D < 1 || 2 * D > 2 * kMaxFactors) return DDB_OK;
+    // sorted factor codes of every term, right-aligned in D entries (code = state index + 1, 0 = constant)
+    std::vector<Key> term(k);
+    for (int j = 0; j < k; ++j) {
+        Key key{};
+        int d = 0;
+        uint16_t f[kMaxFactors];
+        for (int i = 0; i < n; ++i)
+            for (int e = 0; e < ctx->exps[(size_t)i + (size_t)n * j]; ++e) f[d++] = (uint16_t)(i + 1);
+        for (int i = 0; i < d; ++i) key[D - d + i] = f[i];
+        term[j] = key;
+    }
+    std::unordered_map<Key, int, KeyHash> row_id, col_id;
+    std::vector<Key> rows, cols;
+    auto get = [](std::unordered_map<Key, int, KeyHash>& map, std::vector<Key>& list, const Key& key) {
+        auto it = map.find(key);
+        if (it != map.end()) return it->second;
+        const int id = (int)list.size();
+        map.emplace(key, id);
+        list.push_back(key);
+        return id;
+    };
+    // every library term is a row (R = Theta Y' pairs it with the target columns)
+    for (int j = 0; j < k; ++j) get(row_id, rows, term[j]);
+    // (row id, column id) of every lower-triangular Gram entry
+    const size_t ntri = (size_t)k * (k + 1) / 2;
+    std::vector<int32_t> er(ntri), ec(ntri);
+    const size_t limit = (size_t)(k + n_t) * 3 / 2 + 256;  // more virtual rows / columns than this: not worth it
+    size_t e = 0;
+    for (int t = 0; t < k; ++t) {
+        const Key& a = term[t];
+        for (int u = 0; u <= t; ++u, ++e) {
+            const Key& b = term[u];
+            uint16_t mg[2 * kMaxFactors];
+            std::merge(a.begin(), a.begin() + D, b.begin(), b.begin() + D, mg);
+            Key P{}, Q{};
+            for (int i = 0; i < D; ++i) {
+                P[i] = mg[i];
+                Q[i] = mg[D + i];
+            }
+            er[e] = get(row_id, rows, P);
+            ec[e] = get(col_id, cols, Q);
+        }
+        if (rows.size() > limit || cols.size() > limit) return DDB_OK;
+    }
+    // positions: rows by increasing max (then lexicographic), targets last; columns: targets first, then by
+    // decreasing min (then lexicographic)
+    const int nrows = (int)rows.size(), ncols = (int)cols.size();
+    std::vector<int> rorder(nrows), corder(ncols), rpos(nrows), cpos(ncols);
+    for (int i = 0; i < nrows; ++i) rorder[i] = i;
+    for (int i = 0; i < ncols; ++i) corder[i] = i;
+    std::sort(rorder.begin(), rorder.end(), [&](int x, int y) {
+        if (rows[x][D - 1] != rows[y][D - 1]) return rows[x][D - 1] < rows[y][D - 1];
+        return rows[x] < rows[y];
+    });
+    std::sort(corder.begin(), corder.end(), [&](int x, int y) {
+        if (cols[x][0] != cols[y][0]) return cols[x][0] > cols[y][0];
+        return cols[x] < cols[y];
+    });
+    for (int i = 0; i < nrows; ++i) rpos[rorder[i]] = i;
+    for (int i = 0; i < ncols; ++i) cpos[corder[i]] = n_t + i;
+    const int nr_total = nrows + n_t, nc_total = n_t + ncols;
+    const int nrb = (nr_total + kBT - 1) / kBT, ncb = (nc_total + kBT - 1) / kBT;
+    // needed block pairs
+    std::vector<int> pair_of((size_t)nrb * ncb, -1);
+    auto mark = [&](int r, int c) { pair_of[(size_t)(r / kBT) * ncb + c / kBT] = 0; };
+    for (size_t i = 0; i < ntri; ++i) mark(rpos[er[i]], cpos[ec[i]]);
+    for (int t = 0; t < k; ++t)
+        for (int j = 0; j < n_t; ++j) mark(rpos[row_id[term[t]]], j);
+    for (int j = 0; j < n_t; ++j) mark(nrows + j, j);
+    M->pairs.clear();
+    for (int I = 0; I < nrb; ++I)
+        for (int J = 0; J < ncb; ++J)
+            if (pair_of[(size_t)I * ncb + J] == 0) {
+                pair_of[(size_t)I * ncb + J] = (int)M->pairs.size();
+                M->pairs.push_back({I, nrb + J});
+            }
+    M->npairs = (int)M->pairs.size();
+    M->nrb = nrb;
+    M->ncb = ncb;
+    M->nvirt = nrb * kBT + nc_total;
+    // the plain schedule: nblk (nblk - 1) / 2 full pairs + nblk diagonal pairs at 0.6
+    const int nblk = (k + n_t + kBT - 1) / kBT;
+    const double plain = 0.5 * nblk * (nblk - 1) + 0.6 * nblk;
+    if (getenv("DDB_GRAM_DEBUG"))
+        fprintf(stderr, "[ddb] moment schedule: k=%d n_t=%d D=%d rows=%d cols=%d blocks %d x %d pairs=%d (plain %.1f)\n", k,
+                n_t, D, nrows, ncols, nrb, ncb, M->npairs, plain);
+    if (M->npairs >= (1 << 17) || (double)M->npairs > 0.8 * plain) return DDB_OK;
+
+    // gather map of the packed [G | R | yy]
+    const size_t count = (size_t)k * k + (size_t)k * n_t + n_t;
+    std::vector<int32_t> src(count);
+    auto src_of = [&](int r, int c) {
+        return (int32_t)((pair_of[(size_t)(r / kBT) * ncb + c / kBT] << 14) | ((r % kBT) * kBT + (c % kBT)));
+    };
+    e = 0;
+    for (int t = 0; t < k; ++t)
+        for (int u = 0; u <= t; ++u, ++e) {
+            const int32_t s = src_of(rpos[er[e]], cpos[ec[e]]);
+            src[(size_t)t + (size_t)k * u] = s;
+            src[(size_t)u + (size_t)k * t] = s;
+        }
+    for (int j = 0; j < n_t; ++j) {
+        for (int t = 0; t < k; ++t) src[(size_t)k * k + (size_t)t + (size_t)k * j] = src_of(rpos[row_id[term[t]]], j);
+        src[(size_t)k * k + (size_t)k * n_t + j] = src_of(nrows + j, j);
+    }
+    // virtual factor table: [rows | targets | padding to a block] [targets | columns]
+    const int tab_rows = (nrb + ncb) * kBT;
+    std::vector<uint16_t> tab((size_t)tab_rows * kMaxFactors, kNoFactor);
+    auto put = [&](int row, const Key& key) {
+        int d = 0;
+        for (int i = 0; i < D; ++i)
+            if (key[i]) tab[(size_t)row * kMaxFactors + d++] = (uint16_t)(key[i] - 1);
+    };
+    for (int i = 0; i < nrows; ++i) put(rpos[i], rows[i]);
+    for (int j = 0; j < n_t; ++j) {
+        tab[(size_t)(nrows + j) * kMaxFactors] = (uint16_t)(kFactorIsY | j);
+        tab[(size_t)(nrb * kBT + j) * kMaxFactors] = (uint16_t)(kFactorIsY | j);
+    }
+    for (int i = 0; i < ncols; ++i) put(nrb * kBT + cpos[i], cols[i]);
+    DDB_TRY(M->factors.reserve(tab.size() * sizeof(uint16_t)));
+    DDB_TRY(M->src.reserve(src.size() * sizeof(int32_t)));
+    DDB_CUDA_TRY(cudaMemcpyAsync(M->factors.p, tab.data(), tab.size() * sizeof(uint16_t), cudaMemcpyHostToDevice,
+                                 ctx->stream));
+    DDB_CUDA_TRY(cudaMemcpyAsync(M->src.p, src.data(), src.size() * sizeof(int32_t), cudaMemcpyHostToDevice,
+                                 ctx->stream));
+    DDB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    M->eligible = true;
+    M->plan_m = -1;
+    return DDB_OK;
+}
+
+// Lock-step waves: a wave runs `np` block pairs over `nr` sample ranges, CTA r * np + p taking pair p over
+// range r, so that the CTAs of a range walk the same samples at the same time.  Waves follow each other
+// inside one launch (a CTA's segment list is its share of every wave).
+static int build_wave_plan(ddb_ctx* ctx, MomentState* M) {
+    const int nctas = ctx->sm_count;
+    const int64_t ns = (ctx->m + kKS - 1) / kKS;
+    std::vector<std::vector<GramSegment>> per_cta(nctas);
+    std::vector<int32_t> psb(M->npairs + 1, 0);
+    int first = 0, nslots = 0;
+    while (first < M->npairs) {
+        const int remaining = M->npairs - first;
+        int nr = (nctas + remaining - 1) / remaining;
+        nr = (int)std::max<int64_t>(1, std::min<int64_t>(nr, ns));
+        const int np = std::min(remaining, nctas / nr);
+        for (int p = 0; p < np; ++p) {
+            psb[first + p] = nslots;
+            for (int r = 0; r < nr; ++r) {
+                GramSegment sg;
+                sg.bi = M->pairs[first + p].first;
+                sg.bj = M->pairs[first + p].second;
+                sg.slot = nslots++;
+                sg.pad = 0;
+                sg.stage_begin = ns * r / nr;
+                sg.stage_end = ns * (r + 1) / nr;
+                per_cta[r * np + p].push_back(sg);
+            }
+        }
+        first += np;
+    }
+    psb[M->npairs] = nslots;
+    std::vector<GramSegment> segs;
+    std::vector<int32_t> cta_seg_begin(nctas + 1, 0);
+    for (int c = 0; c < nctas; ++c) {
+        cta_seg_begin[c] = (int32_t)segs.size();
+        segs.insert(segs.end(), per_cta[c].begin(), per_cta[c].end());
+    }
+    cta_seg_begin[nctas] = (int32_t)segs.size();
+    M->off_cta = segs.size() * sizeof(GramSegment);
+    M->off_psb = M->off_cta + cta_seg_begin.size() * sizeof(int32_t);
+    const size_t total = M->off_psb + psb.size() * sizeof(int32_t);
+    std::vector<unsigned char> host(total);
+    memcpy(host.data(), segs.data(), segs.size() * sizeof(GramSegment));
+    memcpy(host.data() + M->off_cta, cta_seg_begin.data(), cta_seg_begin.size() * sizeof(int32_t));
+    memcpy(host.data() + M->off_psb, psb.data(), psb.size() * sizeof(int32_t));
+    DDB_TRY(M->plan.reserve(total));
+    DDB_CUDA_TRY(cudaMemcpyAsync(M->plan.p, host.data(), total, cudaMemcpyHostToDevice, ctx->stream));
+    DDB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    DDB_TRY(M->partials.reserve((size_t)nslots * kBT * kBT * sizeof(double)));
+    M->nslots = nslots;
+    M->plan_m = ctx->m;
+    M->plan_nctas = nctas;
+    return DDB_OK;
+}
+
+int gram_moment_run(ddb_ctx* ctx, double* dPacked, bool* handled) {
+    *handled = false;
+    const char* env = getenv("DDB_GRAM_MOMENT");
+    if (env && atoi(env) == 0) return DDB_OK;
+    const int k = ctx->k, n_t = ctx->n_t;
+    if (k + n_t <= 2 * kBT) return DDB_OK;  // one or two blocks: nothing to skip
+    if (!ctx->moment) ctx->moment = new MomentState();
+    MomentState* M = ctx->moment;
+    if (M->lib_version != ctx->lib_version || M->k != k || M->n_t != n_t) DDB_TRY(analyse_library(ctx, M));
+    if (!M->eligible) return DDB_OK;
+    if (M->plan_m != ctx->m || M->plan_nctas != ctx->sm_count) DDB_TRY(build_wave_plan(ctx, M));
+    // the library's own factor table (the rss / residual passes evaluate the real terms)
+    if (ctx->factors_nt != n_t) DDB_TRY(gram_ensure_factors(ctx, (k + n_t + kBT - 1) / kBT * kBT));
+    if (!dPacked) {
+        DDB_TRY(ctx->d_packed.reserve((size_t)ddb_gram_count(ctx) * sizeof(double)));
+        dPacked = ctx->d_packed.as<double>();
+    }
+    unsigned char* base = static_cast<unsigned char*>(M->plan.p);
+    GramArgs a;
+    a.X = ctx->dX;
+    a.Y = ctx->dY;
+    a.n = ctx->n;
+    a.n_t = n_t;
+    a.m = ctx->m;
+    a.kaug = M->nvirt;
+    a.factors = M->factors.as<uint16_t>();
+    a.segs = reinterpret_cast<const GramSegment*>(base);
+    a.cta_seg_begin = reinterpret_cast<const int32_t*>(base + M->off_cta);
+    a.partials = M->partials.as<double>();
+    DDB_CUDA_TRY(cudaEventRecord(ctx->ev[0], ctx->stream));
+    DDB_TRY(gram_launch_bt128(ctx, a, ctx->sm_count));
+    const int64_t count = ddb_gram_count(ctx);
+    moment_gather_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(
+        M->partials.as<double>(), reinterpret_cast<const int32_t*>(base + M->off_psb), M->src.as<int32_t>(), count,
+        dPacked);
+    DDB_CUDA_TRY(cudaGetLastError());
+    DDB_CUDA_TRY(cudaEventRecord(ctx->ev[1], ctx->stream));
+    DDB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    DDB_CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+    ctx->timings.gram_ms = ms;
+    ctx->timings.gram_launches = 2;
+    ctx->have_gram = (dPacked == ctx->d_packed.as<double>());
+    ctx->imp_k = 0;
+    *handled = true;
+    return DDB_OK;
+}
+
+void moment_free(ddb_ctx* ctx) {
+    if (ctx->moment) {
+        ctx->moment->factors.release();
+        ctx->moment->src.release();
+        ctx->moment->plan.release();
+        ctx->moment->partials.release();
+        delete ctx->moment;
+        ctx->moment = nullptr;
+    }
+}
+
+}  // namespace ddb

@@ -1,0 +1,127 @@
+"""GPU tests of the moment schedule of the Gram stage (csrc/gram_moment.cu): the Gram matrix of a monomial
+library is a moment matrix, every distinct moment is contracted once (virtual row / column libraries, only the
+block pairs the staircase of needed entries touches) and gathered into the packed [G | R | yy].  It must agree
+with the oracle (Theta Theta', Theta Y', diag Y Y' of reference STLSQ.jl:90-91 on the materialised library) and
+with the plain schedules, and with itself bit for bit."""
+import os
+
+import numpy as np
+import pytest
+
+import ddb200
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = ddb200.Context(0)
+    yield c
+    c.close()
+
+
+def _gram(ctx, moment):
+    old = os.environ.get("DDB_GRAM_MOMENT")
+    os.environ["DDB_GRAM_MOMENT"] = "1" if moment else "0"
+    try:
+        ctx.gram()
+        return ctx.gram_download(), ctx.timings()
+    finally:
+        if old is None:
+            del os.environ["DDB_GRAM_MOMENT"]
+        else:
+            os.environ["DDB_GRAM_MOMENT"] = old
+
+
+def _check(ctx, ex, X, Y, tol=1e-13):
+    ctx.set_library(ex)
+    ctx.upload(X, Y)
+    (G1, R1, y1), t1 = _gram(ctx, True)
+    (G0, R0, y0), t0 = _gram(ctx, False)
+    Th = oracle.evaluate_library(ex, X)
+    Gr, Rr, yr = Th @ Th.T, Th @ Y.T, (Y * Y).sum(1)
+    sc = np.sqrt(np.outer(np.diag(Gr), np.diag(Gr)))
+    for G, R, yy in ((G1, R1, y1), (G0, R0, y0)):
+        assert np.max(np.abs(G - Gr) / sc) < tol
+        assert np.max(np.abs(R - Rr)) < tol * np.sqrt(np.max(np.diag(Gr)) * np.max(yr))
+        np.testing.assert_allclose(yy, yr, rtol=tol)
+        np.testing.assert_array_equal(G, G.T)
+    return (G1, R1, y1), t1, t0
+
+
+@pytest.mark.parametrize("m", [4096, 20_001, 65_536 + 17])
+def test_moment_schedule_lorenz96_library(ctx, m):
+    """n = 64, degree 2 (k = 2145, config C3): ragged last stage, more / fewer stages than sample ranges."""
+    n = 64
+    rng = np.random.default_rng(m)
+    X = rng.standard_normal((n, m))
+    Y = rng.standard_normal((n, m))
+    (G, R, yy), t1, t0 = _check(ctx, oracle.polynomial_exponents(n, 2), X, Y)
+    assert t1["gram_launches"] == 2  # self-building kernel over the staircase + gather
+    assert G[0, 0] == m  # constant x constant: a sum of ones is exact
+
+
+@pytest.mark.parametrize("n,deg,n_t,m", [(12, 3, 12, 9000), (7, 4, 2, 5001), (30, 2, 3, 7000), (23, 2, 40, 4100)])
+def test_moment_schedule_other_libraries(ctx, n, deg, n_t, m):
+    """Higher degrees (P and Q are degree-3 / degree-4 monomials), n_t != n, a short target block."""
+    rng = np.random.default_rng(n * 10 + deg)
+    X = 0.7 * rng.standard_normal((n, m))
+    Y = rng.standard_normal((n_t, m))
+    _check(ctx, oracle.polynomial_exponents(n, deg), X, Y, tol=2e-13)
+
+
+def test_moment_schedule_incomplete_library(ctx):
+    """A library that is not closed under the factor split: no constant term, every third term removed and a few
+    degree-3 terms appended.  The virtual rows / columns are then monomials outside the library; the schedule
+    either handles it or steps aside for the plain one -- the blocks must be right in both cases."""
+    n, m = 40, 6000
+    rng = np.random.default_rng(3)
+    ex = oracle.polynomial_exponents(n, 2)
+    keep = [j for j in range(1, ex.shape[1]) if j % 3 != 0]
+    extra = np.zeros((n, 5), dtype=ex.dtype)
+    for c in range(5):
+        extra[c, c] = 2
+        extra[c + 7, c] = 1
+    ex2 = np.concatenate([ex[:, keep], extra], axis=1)
+    X = 0.8 * rng.standard_normal((n, m))
+    Y = rng.standard_normal((n, m))
+    _check(ctx, ex2, X, Y, tol=2e-13)
+
+
+def test_moment_schedule_is_bit_reproducible_and_sample_views_work(ctx):
+    n, m = 64, 300_000
+    ctx.set_library(oracle.polynomial_exponents(n, 2))
+    ctx.generate(1, n, m, 0, 0, 0.0)
+    (Ga, Ra, ya), t = _gram(ctx, True)
+    assert t["gram_launches"] == 2
+    for _ in range(3):
+        (G, R, yy), _t = _gram(ctx, True)
+        np.testing.assert_array_equal(G, Ga)
+        np.testing.assert_array_equal(R, Ra)
+        np.testing.assert_array_equal(yy, ya)
+    # a sample view (train / test split, reference data_processing.jl:29-39): blocks of the two parts add up
+    first = 100_003
+    ctx.set_sample_range(0, first)
+    (G1, R1, y1), _t = _gram(ctx, True)
+    ctx.set_sample_range(first, m)
+    (G2, R2, y2), _t = _gram(ctx, True)
+    ctx.set_sample_range(0, -1)
+    sc = np.sqrt(np.outer(np.diag(Ga), np.diag(Ga)))
+    assert np.max(np.abs(G1 + G2 - Ga) / sc) < 1e-13
+    assert np.max(np.abs(R1 + R2 - Ra)) < 1e-13 * np.sqrt(np.max(np.diag(Ga)) * np.max(ya))
+    np.testing.assert_allclose(y1 + y2, ya, rtol=1e-13)
+
+
+def test_library_change_with_same_size_rebuilds_the_moment_map(ctx):
+    """Two libraries with identical (n, k) but different terms: the gather map belongs to the library."""
+    n, m = 30, 5000
+    rng = np.random.default_rng(11)
+    X = 0.9 * rng.standard_normal((n, m))
+    Y = rng.standard_normal((n, m))
+    ex = oracle.polynomial_exponents(n, 2)
+    _check(ctx, ex, X, Y)
+    ex2 = ex.copy()
+    ex2[:, 5], ex2[:, 200] = ex[:, 200].copy(), ex[:, 5].copy()  # swap two terms
+    ex2[0, 17] += 1  # and raise one to degree <= 3
+    _check(ctx, ex2, X, Y, tol=2e-13)

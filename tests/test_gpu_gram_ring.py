@@ -20,16 +20,20 @@ def ctx():
 
 
 def _gram(ctx, ring):
-    old = os.environ.get("DDB_GRAM_RING")
+    """Plain (non-moment) schedules only: the moment schedule (tests/test_gpu_gram_moment.py) would take
+    these libraries first."""
+    old = {key: os.environ.get(key) for key in ("DDB_GRAM_RING", "DDB_GRAM_MOMENT")}
     os.environ["DDB_GRAM_RING"] = "1" if ring else "0"
+    os.environ["DDB_GRAM_MOMENT"] = "0"
     try:
         ctx.gram()
         return ctx.gram_download(), ctx.timings()["gram_launches"]
     finally:
-        if old is None:
-            del os.environ["DDB_GRAM_RING"]
-        else:
-            os.environ["DDB_GRAM_RING"] = old
+        for key, val in old.items():
+            if val is None:
+                del os.environ[key]
+            else:
+                os.environ[key] = val
 
 
 @pytest.mark.parametrize("m", [4096, 20_001, 65_536 + 17])
