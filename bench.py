@@ -31,6 +31,10 @@ CUBLAS_DGEMM_TFLOPS = 35.9
 # profiles/gram_traffic_r1g_c3_1e6.csv): gram_ring_kernel 1041 B (the algorithmic 1024 B + ring spill) and the
 # diagonal-pair pass of gram_kernel 1886 B (its 9 sample ranges x 16 pairs share tiles through L2)
 C3_RING_DRAM_BYTES_PER_SAMPLE = (1041148928 + 1886253824) / 1e6
+# moment schedule (default at C3): gram_kernel over 78 block pairs in lock-step waves (two sample ranges of 74 pairs, then
+# 37 ranges of 4 pairs): dram__bytes_read.sum 2.0918 GB + dram__bytes_write.sum 0.0305 GB at 1e6 samples
+# (profiles/gram_traffic_r1i_c3_1e6.csv)
+C3_MOMENT_DRAM_BYTES_PER_SAMPLE = (2091837000 + 30451968) / 1e6
 
 WORKLOADS = {
     "c3": dict(system=1, n=64, degree=2, m=10_000_000, name="Lorenz-96 n=64, degree-2 library (2145 terms), 1e7 samples, 41-lambda STLSQ"),
@@ -319,6 +323,7 @@ def main():
 
     packed = torch.empty(ctx.gram_count(), dtype=torch.float64, device=dev)
     stage_live = {"gram_ms": [], "factor_ms": [], "sweep_ms": [], "rss_ms": [], "select_ms": [], "launches": []}
+    gram_info = {"schedule": 0, "dmma_flops": 0.0}
 
     def step(host=None):
         """One pass of the hot path; inputs device-resident, or (host = pinned X, Y) uploaded inside the step
@@ -343,6 +348,7 @@ def main():
         for key in ("factor_ms", "sweep_ms", "rss_ms", "select_ms"):
             stage_live[key].append(t2[key])
         stage_live["launches"].append(t["gram_launches"] + t2["sweep_launches"])
+        gram_info["schedule"], gram_info["dmma_flops"] = t["gram_schedule"], t["gram_dmma_flops"]
         return out
 
     def barrier():
@@ -417,12 +423,33 @@ def main():
     F = gram_flops_per_sample(k, n_t)
     gram_ms = float(np.mean(stage["gram_ms"]))
     achieved = F * m_local / (gram_ms * 1e-3) * 1e-12
-    roofline = {"bound": "tensor", "kernel": "Gram stage = ddb::gram_ring_kernel (producer SMs + TMA-fed FP64 DMMA.8x8x4 consumers) + ddb::gram_kernel (diagonal pairs) + reduce",
+    executed = gram_info["dmma_flops"] * m_local / (gram_ms * 1e-3) * 1e-12
+    sched = gram_info["schedule"]
+    kernels = {
+        0: "Gram stage = ddb::gram_kernel (self-building: TMA-fed X/Y tiles, terms multiplied out in shared memory, FP64 DMMA.8x8x4) + reduce",
+        1: "Gram stage = ddb::gram_ring_kernel (producer SMs + TMA-fed FP64 DMMA.8x8x4 consumers) + ddb::gram_kernel (diagonal pairs) + reduce",
+        2: "Gram stage = ddb::gram_kernel over the moment staircase (every distinct moment of the monomial library contracted once; "
+           "TMA-fed X/Y tiles, virtual terms multiplied out in shared memory, FP64 DMMA.8x8x4) + ddb::moment_gather_kernel",
+    }
+    traffic, traffic_source = None, None
+    if args.workload == "c3" and sched == 2:
+        traffic = C3_MOMENT_DRAM_BYTES_PER_SAMPLE * m_local
+        traffic_source = ("dram__bytes_read.sum + dram__bytes_write.sum of gram_kernel at 1e6 samples, ncu "
+                          "(profiles/gram_traffic_r1i_c3_1e6.csv), scaled by samples per launch")
+    elif args.workload == "c3" and sched == 1:
+        traffic = C3_RING_DRAM_BYTES_PER_SAMPLE * m_local
+        traffic_source = ("dram__bytes_read.sum of gram_ring_kernel (1.041 GB) + gram_kernel diagonal-pair pass (1.886 GB) per 1e6 "
+                          "samples, ncu (profiles/gram_traffic_r1g_c3_1e6.csv), scaled by samples per launch")
+    roofline = {"bound": "tensor", "kernel": kernels.get(sched, kernels[0]),
+                "schedule": {0: "self-building", 1: "ring", 2: "moment"}.get(sched, "?"),
                 "achieved": achieved, "peak": FP64_DMMA_PEAK_TFLOPS,
                 "unit": "TFLOP/s", "frac": achieved / FP64_DMMA_PEAK_TFLOPS,
-                "traffic": (C3_RING_DRAM_BYTES_PER_SAMPLE * m_local if args.workload == "c3" else None),
-                "traffic_source": "dram__bytes_read.sum of gram_ring_kernel (1.041 GB) + gram_kernel diagonal-pair pass (1.886 GB) per 1e6 "
-                                  "samples, ncu (profiles/gram_traffic_r1g_c3_1e6.csv), scaled by samples per launch",
+                # `achieved` credits the ALGORITHMIC flops of SURVEY 8(d) (k(k+1) + 2 k n_t + 2 n_t per sample); the moment
+                # schedule issues fewer (it skips repeated moments), so `frac` can exceed 1 -- `executed` is what the
+                # tensor pipe really issued (512 flops per DMMA.8x8x4) and `executed_frac` its share of the DMMA peak
+                "executed": executed, "executed_frac": executed / FP64_DMMA_PEAK_TFLOPS,
+                "executed_flops_per_sample": gram_info["dmma_flops"],
+                "traffic": traffic, "traffic_source": traffic_source,
                 "peak_source": "measured on this pool with tools/fp64_peak.cu (DMMA issue-rate; profiles/fp64_peak_r1.json); "
                                "MEASURED_PEAKS.json has no FP64 figure",
                 "frac_of_cublas_dgemm": achieved / CUBLAS_DGEMM_TFLOPS, "algorithmic_flops_per_sample": F,

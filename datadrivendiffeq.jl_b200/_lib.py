@@ -63,6 +63,9 @@ class Timings(C.Structure):
         ("sweep_launches", C.c_int32),
         ("big_steps", C.c_int32),
         ("candidates", C.c_int32),
+        ("gram_dmma_flops", C.c_double),
+        ("gram_schedule", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
     def as_dict(self):
@@ -93,6 +96,7 @@ PROTOTYPES = {
     "ddb_upload_gram": (C.c_int, [_P, _P, _P, C.c_int, C.c_int64, _P]),
     "ddb_gram_buffer": (C.c_int, [_P, C.POINTER(_P)]),
     "ddb_gram_download": (C.c_int, [_P, _P, _P, _P]),
+    "ddb_moment_plan_describe": (C.c_int64, [C.c_int, C.c_int, _P, C.c_int, _P, C.c_int64, _P, C.c_int64, _P, C.c_int64, _P]),
     "ddb_gram_upload": (C.c_int, [_P, _P, _P, _P, C.c_int]),
     "ddb_implicit_select": (C.c_int, [_P, _P, C.c_int]),
     "ddb_sweep": (C.c_int, [_P, C.POINTER(SweepParams), _P, C.c_int, C.c_int64]),

@@ -577,6 +577,22 @@ static int launch_gram(ddb_ctx* ctx, int bt, const GramArgs& args, size_t smem) 
     return DDB_OK;
 }
 
+// DMMA flops per sample of the plain schedules: live 8 x 8 sub-tiles of every lower-triangular block pair
+// (diagonal pairs skip the sub-tiles above the diagonal, a last block row of at most 64 rows is a 64-row patch)
+double gram_plain_dmma_flops(int kaug, int bt) {
+    const int nblk = (kaug + bt - 1) / bt, sub = bt / 8;
+    double tiles = 0.0;
+    for (int bi = 0; bi < nblk; ++bi) {
+        const int rows_valid = std::min(bt, kaug - bi * bt);
+        for (int bj = 0; bj <= bi; ++bj) {
+            if (bt == 128 && rows_valid <= 64) tiles += 8.0 * sub;
+            else if (bi == bj) tiles += 0.5 * sub * (sub + 1);
+            else tiles += (double)sub * sub;
+        }
+    }
+    return tiles * 2.0 * 64.0;
+}
+
 int gram_ensure_factors(ddb_ctx* ctx, int kaug_pad);
 static int ensure_factor_table(ddb_ctx* ctx, int kaug_pad) { return gram_ensure_factors(ctx, kaug_pad); }
 int gram_ensure_factors(ddb_ctx* ctx, int kaug_pad) {
@@ -728,6 +744,8 @@ int gram_run(ddb_ctx* ctx, double* dPacked) {
     DDB_CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
     ctx->timings.gram_ms = ms;
     ctx->timings.gram_launches = 2;
+    ctx->timings.gram_schedule = 0;
+    ctx->timings.gram_dmma_flops = gram_plain_dmma_flops(kaug, bt);
     ctx->have_gram = (dPacked == ctx->d_packed.as<double>());
     ctx->imp_k = 0;
     return DDB_OK;

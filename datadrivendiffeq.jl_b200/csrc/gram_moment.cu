@@ -82,13 +82,20 @@ struct MomentState {
     size_t off_cta = 0, off_psb = 0;
 };
 
-static int analyse_library(ddb_ctx* ctx, MomentState* M) {
-    const int k = ctx->k, n = ctx->n, n_t = ctx->n_t, D = ctx->max_degree;
-    M->eligible = false;
-    M->lib_version = ctx->lib_version;
-    M->k = k;
-    M->n_t = n_t;
-    if (D < 1 || 2 * D > 2 * kMaxFactors) return DDB_OK;
+// Host-only analysis of a monomial library (n x k exponent table, n_t targets): virtual rows / columns, needed
+// block pairs, gather map and virtual factor table.  `worth` = the schedule needs clearly fewer block pairs
+// than the plain one.
+struct MomentMap {
+    bool worth = false;
+    int nrows = 0, ncols = 0, nrb = 0, ncb = 0, nvirt = 0;
+    std::vector<std::pair<int, int>> pairs;  // (row block, nrb + column block)
+    std::vector<int32_t> src;                // per packed entry: (pair << 14) | (row-in-tile * 128 + column-in-tile)
+    std::vector<uint16_t> tab;               // (nrb + ncb) * 128 virtual terms x kMaxFactors factor codes
+};
+
+static void analyse_library(const uint8_t* exps, int n, int k, int n_t, int D, MomentMap* M) {
+    M->worth = false;
+    if (D < 1 || D > kMaxFactors) return;
     // sorted factor codes of every term, right-aligned in D entries (code = state index + 1, 0 = constant)
     std::vector<Key> term(k);
     for (int j = 0; j < k; ++j) {
@@ -96,7 +103,7 @@ static int analyse_library(ddb_ctx* ctx, MomentState* M) {
         int d = 0;
         uint16_t f[kMaxFactors];
         for (int i = 0; i < n; ++i)
-            for (int e = 0; e < ctx->exps[(size_t)i + (size_t)n * j]; ++e) f[d++] = (uint16_t)(i + 1);
+            for (int e = 0; e < exps[(size_t)i + (size_t)n * j]; ++e) f[d++] = (uint16_t)(i + 1);
         for (int i = 0; i < d; ++i) key[D - d + i] = f[i];
         term[j] = key;
     }
@@ -131,7 +138,7 @@ static int analyse_library(ddb_ctx* ctx, MomentState* M) {
             er[e] = get(row_id, rows, P);
             ec[e] = get(col_id, cols, Q);
         }
-        if (rows.size() > limit || cols.size() > limit) return DDB_OK;
+        if (rows.size() > limit || cols.size() > limit) return;
     }
     // positions: rows by increasing max (then lexicographic), targets last; columns: targets first, then by
     // decreasing min (then lexicographic)
@@ -165,7 +172,9 @@ static int analyse_library(ddb_ctx* ctx, MomentState* M) {
                 pair_of[(size_t)I * ncb + J] = (int)M->pairs.size();
                 M->pairs.push_back({I, nrb + J});
             }
-    M->npairs = (int)M->pairs.size();
+    const int npairs = (int)M->pairs.size();
+    M->nrows = nrows;
+    M->ncols = ncols;
     M->nrb = nrb;
     M->ncb = ncb;
     M->nvirt = nrb * kBT + nc_total;
@@ -174,12 +183,13 @@ static int analyse_library(ddb_ctx* ctx, MomentState* M) {
     const double plain = 0.5 * nblk * (nblk - 1) + 0.6 * nblk;
     if (getenv("DDB_GRAM_DEBUG"))
         fprintf(stderr, "[ddb] moment schedule: k=%d n_t=%d D=%d rows=%d cols=%d blocks %d x %d pairs=%d (plain %.1f)\n", k,
-                n_t, D, nrows, ncols, nrb, ncb, M->npairs, plain);
-    if (M->npairs >= (1 << 17) || (double)M->npairs > 0.8 * plain) return DDB_OK;
+                n_t, D, nrows, ncols, nrb, ncb, npairs, plain);
+    if (npairs >= (1 << 17) || (double)npairs > 0.9 * plain) return;
 
     // gather map of the packed [G | R | yy]
     const size_t count = (size_t)k * k + (size_t)k * n_t + n_t;
-    std::vector<int32_t> src(count);
+    std::vector<int32_t>& src = M->src;
+    src.assign(count, 0);
     auto src_of = [&](int r, int c) {
         return (int32_t)((pair_of[(size_t)(r / kBT) * ncb + c / kBT] << 14) | ((r % kBT) * kBT + (c % kBT)));
     };
@@ -196,7 +206,8 @@ static int analyse_library(ddb_ctx* ctx, MomentState* M) {
     }
     // virtual factor table: [rows | targets | padding to a block] [targets | columns]
     const int tab_rows = (nrb + ncb) * kBT;
-    std::vector<uint16_t> tab((size_t)tab_rows * kMaxFactors, kNoFactor);
+    std::vector<uint16_t>& tab = M->tab;
+    tab.assign((size_t)tab_rows * kMaxFactors, kNoFactor);
     auto put = [&](int row, const Key& key) {
         int d = 0;
         for (int i = 0; i < D; ++i)
@@ -208,16 +219,60 @@ static int analyse_library(ddb_ctx* ctx, MomentState* M) {
         tab[(size_t)(nrb * kBT + j) * kMaxFactors] = (uint16_t)(kFactorIsY | j);
     }
     for (int i = 0; i < ncols; ++i) put(nrb * kBT + cpos[i], cols[i]);
-    DDB_TRY(M->factors.reserve(tab.size() * sizeof(uint16_t)));
-    DDB_TRY(M->src.reserve(src.size() * sizeof(int32_t)));
-    DDB_CUDA_TRY(cudaMemcpyAsync(M->factors.p, tab.data(), tab.size() * sizeof(uint16_t), cudaMemcpyHostToDevice,
+    M->worth = true;
+}
+
+static int install_library(ddb_ctx* ctx, MomentState* M) {
+    M->eligible = false;
+    M->lib_version = ctx->lib_version;
+    M->k = ctx->k;
+    M->n_t = ctx->n_t;
+    MomentMap map;
+    analyse_library(ctx->exps.data(), ctx->n, ctx->k, ctx->n_t, ctx->max_degree, &map);
+    if (!map.worth) return DDB_OK;
+    M->pairs = map.pairs;
+    M->npairs = (int)map.pairs.size();
+    M->nrb = map.nrb;
+    M->ncb = map.ncb;
+    M->nvirt = map.nvirt;
+    DDB_TRY(M->factors.reserve(map.tab.size() * sizeof(uint16_t)));
+    DDB_TRY(M->src.reserve(map.src.size() * sizeof(int32_t)));
+    DDB_CUDA_TRY(cudaMemcpyAsync(M->factors.p, map.tab.data(), map.tab.size() * sizeof(uint16_t), cudaMemcpyHostToDevice,
                                  ctx->stream));
-    DDB_CUDA_TRY(cudaMemcpyAsync(M->src.p, src.data(), src.size() * sizeof(int32_t), cudaMemcpyHostToDevice,
+    DDB_CUDA_TRY(cudaMemcpyAsync(M->src.p, map.src.data(), map.src.size() * sizeof(int32_t), cudaMemcpyHostToDevice,
                                  ctx->stream));
-    DDB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    DDB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // `map` is a stack-lifetime host buffer
     M->eligible = true;
     M->plan_m = -1;
     return DDB_OK;
+}
+
+// Host-only view of the analysis for ddb_moment_plan_describe (api.cu).
+int64_t moment_plan_describe(const uint8_t* exps, int n, int k, int n_t, int32_t* src, int64_t src_cap, uint16_t* tab,
+                             int64_t tab_cap, int32_t* pairs, int64_t pairs_cap, int64_t* info) {
+    int D = 0;
+    for (int j = 0; j < k; ++j) {
+        int d = 0;
+        for (int i = 0; i < n; ++i) d += exps[(size_t)i + (size_t)n * j];
+        D = std::max(D, d);
+    }
+    MomentMap map;
+    analyse_library(exps, n, k, n_t, D, &map);
+    if (info) {
+        info[0] = map.worth, info[1] = map.nrows, info[2] = map.ncols, info[3] = map.nrb, info[4] = map.ncb;
+        info[5] = (int64_t)map.pairs.size(), info[6] = map.nvirt, info[7] = D;
+    }
+    if (!map.worth) return 0;
+    if (src)
+        for (int64_t i = 0; i < std::min<int64_t>(src_cap, (int64_t)map.src.size()); ++i) src[i] = map.src[i];
+    if (tab)
+        for (int64_t i = 0; i < std::min<int64_t>(tab_cap, (int64_t)map.tab.size()); ++i) tab[i] = map.tab[i];
+    if (pairs)
+        for (int64_t i = 0; i < std::min<int64_t>(pairs_cap, (int64_t)map.pairs.size()); ++i) {
+            pairs[2 * i] = map.pairs[i].first;
+            pairs[2 * i + 1] = map.pairs[i].second;
+        }
+    return (int64_t)map.src.size();
 }
 
 // Lock-step waves: a wave runs `np` block pairs over `nr` sample ranges, CTA r * np + p taking pair p over
@@ -282,7 +337,7 @@ int gram_moment_run(ddb_ctx* ctx, double* dPacked, bool* handled) {
     if (k + n_t <= 2 * kBT) return DDB_OK;  // one or two blocks: nothing to skip
     if (!ctx->moment) ctx->moment = new MomentState();
     MomentState* M = ctx->moment;
-    if (M->lib_version != ctx->lib_version || M->k != k || M->n_t != n_t) DDB_TRY(analyse_library(ctx, M));
+    if (M->lib_version != ctx->lib_version || M->k != k || M->n_t != n_t) DDB_TRY(install_library(ctx, M));
     if (!M->eligible) return DDB_OK;
     if (M->plan_m != ctx->m || M->plan_nctas != ctx->sm_count) DDB_TRY(build_wave_plan(ctx, M));
     // the library's own factor table (the rss / residual passes evaluate the real terms)
@@ -316,6 +371,8 @@ int gram_moment_run(ddb_ctx* ctx, double* dPacked, bool* handled) {
     DDB_CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
     ctx->timings.gram_ms = ms;
     ctx->timings.gram_launches = 2;
+    ctx->timings.gram_schedule = 2;
+    ctx->timings.gram_dmma_flops = 2.0 * kBT * kBT * M->npairs;
     ctx->have_gram = (dPacked == ctx->d_packed.as<double>());
     ctx->imp_k = 0;
     *handled = true;

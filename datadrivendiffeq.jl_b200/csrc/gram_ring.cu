@@ -555,6 +555,8 @@ struct RingState {
     bool have_rest = false;
 };
 
+double gram_plain_dmma_flops(int kaug, int bt);
+
 int gram_ring_run(ddb_ctx* ctx, double* dPacked, bool* handled) {
     *handled = false;
     const char* env = getenv("DDB_GRAM_RING");
@@ -769,6 +771,8 @@ int gram_ring_run(ddb_ctx* ctx, double* dPacked, bool* handled) {
     DDB_CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
     ctx->timings.gram_ms = ms;
     ctx->timings.gram_launches = launches;
+    ctx->timings.gram_schedule = 1;
+    ctx->timings.gram_dmma_flops = gram_plain_dmma_flops(kaug, kRingBT);
     ctx->have_gram = (dPacked == ctx->d_packed.as<double>());
     ctx->imp_k = 0;
     *handled = true;

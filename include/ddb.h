@@ -90,6 +90,10 @@ typedef struct ddb_timings {
     int32_t sweep_launches; /* kernels launched by the sweep + rss + select stages */
     int32_t big_steps;      /* sweep steps that needed the blocked (global-memory) Cholesky */
     int32_t candidates;     /* unique (equation, support, coefficients) candidates scored */
+    double gram_dmma_flops; /* FP64 tensor-core flops the last Gram stage issued PER SAMPLE (512 per DMMA.8x8x4);
+                               below the algorithmic k(k+1) + 2 k n_t + 2 n_t when the moment schedule ran */
+    int32_t gram_schedule;  /* schedule of the last Gram stage: 0 self-building, 1 ring, 2 moment */
+    int32_t reserved;
 } ddb_timings;
 
 /* ---- context ---------------------------------------------------------------------------------- */
@@ -287,6 +291,22 @@ int ddb_dmd_solve(ddb_ctx* ctx, const double* x, int n, int64_t m_plus_1, double
  * the number of segments (or a negative status).  info (may be NULL) receives {block_tile,
  * samples_per_stage, blocks_per_dim, block_pairs, stages, slots}.  Needs no GPU. */
 int64_t ddb_gram_plan_describe(int kaug, int64_t m, int nctas, int64_t* segments, int64_t cap, int64_t* info);
+
+/* Host-only: the moment schedule of the Gram stage for a monomial library (exps as in ddb_set_library_monomial)
+ * with n_t targets.  The Gram matrix of monomials is a moment matrix: G[t,u] only depends on the product
+ * theta_t theta_u, so every distinct moment is contracted once, as (virtual row term) x (virtual column term),
+ * and gathered into the packed [G (k x k) | R (k x n_t) | yy (n_t)].  info (8 int64, may be NULL) receives
+ * {used, virtual_rows, virtual_columns, row_blocks, column_blocks, block_pairs, virtual_terms, degree}; `used`
+ * = 0 means the library keeps the plain schedule (nothing else is written, returns 0).  Otherwise returns the
+ * number of packed entries and writes, each up to its cap and each optional:
+ *   src     per packed entry (pair << 14) | (row_in_tile * 128 + column_in_tile);
+ *   factors (row_blocks + column_blocks) * 128 virtual terms x 8 factor codes: state index, 0x8000 | target
+ *           index, 0xFFFF = no factor; row block I holds virtual terms [128 I, 128 I + 128), column block J
+ *           the terms [128 (row_blocks + J), ...);
+ *   pairs   block_pairs x {row_block, row_blocks + column_block}.
+ * Needs no GPU. */
+int64_t ddb_moment_plan_describe(int n, int k, const uint8_t* exps, int n_t, int32_t* src, int64_t src_cap, uint16_t* factors,
+                                 int64_t factors_cap, int32_t* pairs, int64_t pairs_cap, int64_t* info);
 
 int ddb_get_timings(const ddb_ctx* ctx, ddb_timings* out);
 /* The context's CUDA stream (cudaStream_t) so a caller can order its own work after ours. */

@@ -50,7 +50,7 @@ def test_no_cpu_fallback():
 
 def test_struct_layouts():
     assert C.sizeof(_lib.SweepParams) == 48
-    assert C.sizeof(_lib.Timings) == 72
+    assert C.sizeof(_lib.Timings) == 88
 
 
 @pytest.mark.parametrize("kaug,m,nctas", [(59, 10_000_000, 444), (2209, 1_250_000, 148), (2209, 1001, 148), (128, 777, 148),
@@ -82,3 +82,4 @@ def test_gram_plan_covers_every_stage_exactly_once(kaug, m, nctas):
     load = np.bincount(seg[:, 0], weights=cost * (seg[:, 5] - seg[:, 4]), minlength=nctas)
     if nstages * npairs > 50 * nctas:
         assert load.max() <= 1.06 * load.sum() / nctas + 1
+

@@ -62,13 +62,21 @@ def test_moment_schedule_lorenz96_library(ctx, m):
     assert G[0, 0] == m  # constant x constant: a sum of ones is exact
 
 
-@pytest.mark.parametrize("n,deg,n_t,m", [(12, 3, 12, 9000), (7, 4, 2, 5001), (30, 2, 3, 7000), (23, 2, 40, 4100)])
-def test_moment_schedule_other_libraries(ctx, n, deg, n_t, m):
-    """Higher degrees (P and Q are degree-3 / degree-4 monomials), n_t != n, a short target block."""
+@pytest.mark.parametrize("n,deg,n_t,m,used", [(12, 3, 12, 9000, True), (20, 3, 20, 5000, True), (9, 4, 2, 5001, True),
+                                                (40, 2, 5, 7000, True), (7, 4, 2, 5001, False), (30, 2, 3, 7000, False),
+                                                (23, 2, 40, 4100, None)])
+def test_moment_schedule_other_libraries(ctx, n, deg, n_t, m, used):
+    """Higher degrees (P and Q are degree-3 / degree-4 monomials), n_t != n, a short target block; libraries of a
+    few blocks where the staircase saves nothing keep the plain schedule (`used` False)."""
     rng = np.random.default_rng(n * 10 + deg)
     X = 0.7 * rng.standard_normal((n, m))
     Y = rng.standard_normal((n_t, m))
-    _check(ctx, oracle.polynomial_exponents(n, deg), X, Y, tol=2e-13)
+    _res, t1, t0 = _check(ctx, oracle.polynomial_exponents(n, deg), X, Y, tol=2e-13)
+    assert t0["gram_schedule"] != 2
+    if used is not None:
+        assert (t1["gram_schedule"] == 2) == used
+        if used:
+            assert t1["gram_dmma_flops"] < t0["gram_dmma_flops"]
 
 
 def test_moment_schedule_incomplete_library(ctx):

@@ -1,0 +1,97 @@
+"""Host logic of the moment schedule of the Gram stage (csrc/gram_moment.cu) through the host-only entry point
+ddb_moment_plan_describe: no GPU, no compute calls.  The GPU parity of the schedule is tests/test_gpu_gram_moment.py."""
+import numpy as np
+import pytest
+
+import oracle
+from ddb200 import _lib
+
+
+def _moment_plan(ex, n_t):
+    lib = _lib.load()
+    n, k = ex.shape
+    exf = np.asfortranarray(ex.astype(np.uint8))
+    info = np.zeros(8, dtype=np.int64)
+    count = lib.ddb_moment_plan_describe(n, k, _lib.ptr(exf), n_t, None, 0, None, 0, None, 0, _lib.ptr(info))
+    used, nrows, ncols, nrb, ncb, npairs, nvirt, deg = info.tolist()
+    if not used:
+        assert count == 0
+        return None
+    assert count == k * k + k * n_t + n_t
+    src = np.zeros(count, dtype=np.int32)
+    tab = np.zeros(((nrb + ncb) * 128, 8), dtype=np.uint16)
+    pairs = np.zeros((npairs, 2), dtype=np.int32)
+    assert lib.ddb_moment_plan_describe(n, k, _lib.ptr(exf), n_t, _lib.ptr(src), src.size, _lib.ptr(tab), tab.size,
+                                        _lib.ptr(pairs), pairs.size // 2, None) == count
+    return dict(src=src, tab=tab, pairs=pairs, nrb=nrb, ncb=ncb, npairs=npairs, nrows=nrows, ncols=ncols, nvirt=nvirt)
+
+
+def _virtual_exponents(tab, n, n_t):
+    """Exponent vector over [states | targets] of every virtual term of the factor table."""
+    out = np.zeros((tab.shape[0], n + n_t), dtype=np.int64)
+    for r in range(tab.shape[0]):
+        for f in tab[r]:
+            if f == 0xFFFF:
+                continue
+            out[r, (n + (f & 0x7FFF)) if (f & 0x8000) else f] += 1
+    return out
+
+
+@pytest.mark.parametrize("n,deg,n_t", [(64, 2, 64), (20, 3, 20), (9, 4, 2), (40, 2, 5), (12, 3, 12)])
+def test_moment_plan_maps_every_packed_entry_to_its_moment(n, deg, n_t):
+    """For EVERY entry of the packed [G | R | yy] the product of the virtual row term and the virtual column term
+    it is gathered from is the product monomial of the entry.  Checked on exponent vectors: all entries through
+    a random linear form of the exponents (a 60-bit fingerprint), 200 000 random entries exactly.  Entries of
+    the same moment share one source, different moments have different sources, and the block pairs are
+    exactly the ones the entries touch."""
+    ex = oracle.polynomial_exponents(n, deg)
+    k = ex.shape[1]
+    plan = _moment_plan(ex, n_t)
+    assert plan is not None
+    src, pairs, nrb = plan["src"], plan["pairs"], plan["nrb"]
+    vex = _virtual_exponents(plan["tab"], n, n_t)
+    pair, off = src >> 14, src & 16383
+    row = pairs[pair, 0] * 128 + off // 128
+    col = pairs[pair, 1] * 128 + off % 128
+    assert (pairs[:, 0] < nrb).all() and (pairs[:, 1] >= nrb).all()
+    full = np.concatenate([ex.T.astype(np.int64), np.zeros((k, n_t), dtype=np.int64)], axis=1)  # library terms
+    tgt = np.concatenate([np.zeros((n_t, n), dtype=np.int64), np.eye(n_t, dtype=np.int64)], axis=1)  # targets
+    rng = np.random.default_rng(0)
+    w = rng.integers(1, 1 << 56, size=n + n_t, dtype=np.int64)
+    hv, hf, ht = vex @ w, full @ w, tgt @ w
+    got = hv[row] + hv[col]
+    want = np.concatenate([(hf[None, :] + hf[:, None]).ravel(), (ht[:, None] + hf[None, :]).ravel(), 2 * ht])
+    np.testing.assert_array_equal(got, want)
+    # exact check of a sample of entries (entry e of G is (t, u) = (e % k, e // k); of R (t, j))
+    e = rng.integers(0, k * k + k * n_t, size=200_000)
+    a = np.where(e < k * k, e % k, (e - k * k) % k)
+    b = np.where(e < k * k, e // k, (e - k * k) // k)
+    second = np.where((e < k * k)[:, None], full[np.minimum(b, k - 1)], tgt[np.minimum(b, n_t - 1)])
+    np.testing.assert_array_equal(vex[row[e]] + vex[col[e]], full[a] + second)
+    # one source per distinct moment
+    G_src = src[: k * k].reshape(k, k)
+    np.testing.assert_array_equal(G_src, G_src.T)
+    keys, inv = np.unique(want[: k * k], return_inverse=True)
+    rep = np.zeros(keys.size, dtype=np.int64)
+    rep[inv] = src[: k * k]
+    np.testing.assert_array_equal(rep[inv], src[: k * k])
+    assert np.unique(rep).size == keys.size
+    assert np.unique(pair).size == plan["npairs"]  # no block pair without a needed entry
+    nblk = -(-(k + n_t) // 128)
+    assert plan["npairs"] <= 0.9 * (0.5 * nblk * (nblk - 1) + 0.6 * nblk)
+
+
+def test_moment_plan_lorenz96_counts():
+    """Config C3: 2145 virtual rows and columns (the library is closed under the split), 78 block pairs instead
+    of 153 off-diagonal + 18 diagonal ones."""
+    plan = _moment_plan(oracle.polynomial_exponents(64, 2), 64)
+    assert (plan["nrows"], plan["ncols"], plan["nrb"], plan["ncb"], plan["npairs"]) == (2145, 2145, 18, 18, 78)
+
+
+def test_moment_plan_steps_aside():
+    """Small libraries (one or two blocks) and libraries whose splits produce too many foreign monomials keep the
+    plain schedule."""
+    assert _moment_plan(oracle.polynomial_exponents(30, 2), 3) is None  # 8 block pairs against 6 + 4 diagonal
+    ex = oracle.polynomial_exponents(30, 2).copy()
+    ex[0, 17] += 1  # one cubic term: degree-3 splits of a degree-2 library leave the library
+    assert _moment_plan(ex, 30) is None
