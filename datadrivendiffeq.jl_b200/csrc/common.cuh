@@ -48,7 +48,7 @@ constexpr uint16_t kFactorIsY = 0x8000;
 struct GramSegment {
     int32_t bi, bj;          // block-row / block-column of the augmented library
     int32_t slot;            // partial-tile slot the accumulators are flushed to
-    int32_t pad;
+    int32_t pad;             // bit 0: only rows 0..63 of the pair are needed (64 x 128 patch; moment schedule)
     int64_t stage_begin, stage_end;
 };
 

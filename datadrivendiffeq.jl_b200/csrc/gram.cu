@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(GramCfg<BT>::kThreads, GramCfg<BT>::kMinBlocks
         const bool same = (seg.bi == seg.bj);
         const int rows_valid = min(BT, args.kaug - seg.bi * BT);
         // block rows with at most 64 live rows: lay all warps side by side (64 x 16 patches)
-        const bool flat = (BT == 128) && (rows_valid <= 64);
+        const bool flat = (BT == 128) && (rows_valid <= 64 || (seg.pad & 1));  // pad bit 0: the plan only needs rows 0..63
         const int row0 = flat ? 0 : wm * 64;
         const int col0 = flat ? warp * 16 : wn * 32;
         // shape of this warp's patch: 0 full, 1 diagonal offset 0, 2 diagonal offset -4, 3 empty, 4 flat

@@ -40,6 +40,7 @@ int gram_ensure_factors(ddb_ctx* ctx, int kaug_pad);
 namespace {
 
 constexpr int kBT = 128;
+constexpr double kHalfCost = 0.53;  // measured cost of a 64 x 128 patch relative to a whole 128 x 128 pair
 using Key = std::array<uint16_t, kMaxFactors>;  // factor codes, ascending, leading zeros = the constant 1
 struct KeyHash {
     size_t operator()(const Key& k) const {
@@ -72,7 +73,8 @@ struct MomentState {
     int k = -1, n_t = -1;
     bool eligible = false;
     int nrb = 0, ncb = 0, nvirt = 0, npairs = 0;
-    std::vector<std::pair<int, int>> pairs;  // (row block, nrb + column block)
+    std::vector<std::pair<int, int>> pairs;  // (row block, nrb + column block), whole pairs first
+    int nfull = 0;                           // pairs [nfull, npairs) only need their rows 0..63
     DevBuf factors, src;
     // sample-count-dependent part
     int64_t plan_m = -1;
@@ -88,7 +90,8 @@ struct MomentState {
 struct MomentMap {
     bool worth = false;
     int nrows = 0, ncols = 0, nrb = 0, ncb = 0, nvirt = 0;
-    std::vector<std::pair<int, int>> pairs;  // (row block, nrb + column block)
+    std::vector<std::pair<int, int>> pairs;  // (row block, nrb + column block), whole pairs first
+    std::vector<uint8_t> half;               // 1 = only rows 0..63 of the pair are needed
     std::vector<int32_t> src;                // per packed entry: (pair << 14) | (row-in-tile * 128 + column-in-tile)
     std::vector<uint16_t> tab;               // (nrb + ncb) * 128 virtual terms x kMaxFactors factor codes
 };
@@ -159,19 +162,27 @@ static void analyse_library(const uint8_t* exps, int n, int k, int n_t, int D, M
     const int nr_total = nrows + n_t, nc_total = n_t + ncols;
     const int nrb = (nr_total + kBT - 1) / kBT, ncb = (nc_total + kBT - 1) / kBT;
     // needed block pairs
-    std::vector<int> pair_of((size_t)nrb * ncb, -1);
-    auto mark = [&](int r, int c) { pair_of[(size_t)(r / kBT) * ncb + c / kBT] = 0; };
+    // bit 0: an entry in rows 0..63 of the block pair, bit 1: one in rows 64..127
+    std::vector<int> pair_of((size_t)nrb * ncb, 0);
+    auto mark = [&](int r, int c) { pair_of[(size_t)(r / kBT) * ncb + c / kBT] |= (r % kBT) < 64 ? 1 : 2; };
     for (size_t i = 0; i < ntri; ++i) mark(rpos[er[i]], cpos[ec[i]]);
     for (int t = 0; t < k; ++t)
         for (int j = 0; j < n_t; ++j) mark(rpos[row_id[term[t]]], j);
     for (int j = 0; j < n_t; ++j) mark(nrows + j, j);
+    // whole pairs first, then the pairs at the edge of the staircase that only need their upper 64 rows (the
+    // kernel's 64 x 128 patch, about half the tensor work); pair_of becomes the pair index
     M->pairs.clear();
-    for (int I = 0; I < nrb; ++I)
-        for (int J = 0; J < ncb; ++J)
-            if (pair_of[(size_t)I * ncb + J] == 0) {
-                pair_of[(size_t)I * ncb + J] = (int)M->pairs.size();
+    M->half.clear();
+    for (int pass = 0; pass < 2; ++pass)
+        for (int I = 0; I < nrb; ++I)
+            for (int J = 0; J < ncb; ++J) {
+                int& cell = pair_of[(size_t)I * ncb + J];
+                if (cell <= 0 || (cell == 1) != (pass == 1)) continue;
+                cell = -(int)M->pairs.size() - 1;  // negative while the passes run: index = -cell - 1
                 M->pairs.push_back({I, nrb + J});
+                M->half.push_back(pass == 1);
             }
+    for (int& cell : pair_of) cell = cell < 0 ? -cell - 1 : -1;
     const int npairs = (int)M->pairs.size();
     M->nrows = nrows;
     M->ncols = ncols;
@@ -182,9 +193,11 @@ static void analyse_library(const uint8_t* exps, int n, int k, int n_t, int D, M
     const int nblk = (k + n_t + kBT - 1) / kBT;
     const double plain = 0.5 * nblk * (nblk - 1) + 0.6 * nblk;
     if (getenv("DDB_GRAM_DEBUG"))
-        fprintf(stderr, "[ddb] moment schedule: k=%d n_t=%d D=%d rows=%d cols=%d blocks %d x %d pairs=%d (plain %.1f)\n", k,
-                n_t, D, nrows, ncols, nrb, ncb, npairs, plain);
-    if (npairs >= (1 << 17) || (double)npairs > 0.9 * plain) return;
+        fprintf(stderr, "[ddb] moment schedule: k=%d n_t=%d D=%d rows=%d cols=%d blocks %d x %d pairs=%d of which %d half (plain %.1f)\n",
+                k, n_t, D, nrows, ncols, nrb, ncb, npairs, (int)std::count(M->half.begin(), M->half.end(), (uint8_t)1), plain);
+    double cost = 0.0;
+    for (uint8_t h : M->half) cost += h ? kHalfCost : 1.0;
+    if (npairs >= (1 << 17) || cost > 0.9 * plain) return;
 
     // gather map of the packed [G | R | yy]
     const size_t count = (size_t)k * k + (size_t)k * n_t + n_t;
@@ -232,6 +245,7 @@ static int install_library(ddb_ctx* ctx, MomentState* M) {
     if (!map.worth) return DDB_OK;
     M->pairs = map.pairs;
     M->npairs = (int)map.pairs.size();
+    M->nfull = (int)std::count(map.half.begin(), map.half.end(), (uint8_t)0);
     M->nrb = map.nrb;
     M->ncb = map.ncb;
     M->nvirt = map.nvirt;
@@ -269,8 +283,9 @@ int64_t moment_plan_describe(const uint8_t* exps, int n, int k, int n_t, int32_t
         for (int64_t i = 0; i < std::min<int64_t>(tab_cap, (int64_t)map.tab.size()); ++i) tab[i] = map.tab[i];
     if (pairs)
         for (int64_t i = 0; i < std::min<int64_t>(pairs_cap, (int64_t)map.pairs.size()); ++i) {
-            pairs[2 * i] = map.pairs[i].first;
-            pairs[2 * i + 1] = map.pairs[i].second;
+            pairs[3 * i] = map.pairs[i].first;
+            pairs[3 * i + 1] = map.pairs[i].second;
+            pairs[3 * i + 2] = map.half[i] ? 64 : 128;
         }
     return (int64_t)map.src.size();
 }
@@ -285,7 +300,9 @@ static int build_wave_plan(ddb_ctx* ctx, MomentState* M) {
     std::vector<int32_t> psb(M->npairs + 1, 0);
     int first = 0, nslots = 0;
     while (first < M->npairs) {
-        const int remaining = M->npairs - first;
+        // waves never mix whole and half pairs (the CTAs of a wave must take the same time)
+        const bool half = first >= M->nfull;
+        const int remaining = (half ? M->npairs : M->nfull) - first;
         int nr = (nctas + remaining - 1) / remaining;
         nr = (int)std::max<int64_t>(1, std::min<int64_t>(nr, ns));
         const int np = std::min(remaining, nctas / nr);
@@ -296,7 +313,7 @@ static int build_wave_plan(ddb_ctx* ctx, MomentState* M) {
                 sg.bi = M->pairs[first + p].first;
                 sg.bj = M->pairs[first + p].second;
                 sg.slot = nslots++;
-                sg.pad = 0;
+                sg.pad = half ? 1 : 0;  // bit 0: 64 x 128 patch
                 sg.stage_begin = ns * r / nr;
                 sg.stage_end = ns * (r + 1) / nr;
                 per_cta[r * np + p].push_back(sg);
@@ -372,7 +389,7 @@ int gram_moment_run(ddb_ctx* ctx, double* dPacked, bool* handled) {
     ctx->timings.gram_ms = ms;
     ctx->timings.gram_launches = 2;
     ctx->timings.gram_schedule = 2;
-    ctx->timings.gram_dmma_flops = 2.0 * kBT * kBT * M->npairs;
+    ctx->timings.gram_dmma_flops = 2.0 * kBT * kBT * (M->nfull + 0.5 * (M->npairs - M->nfull));
     ctx->have_gram = (dPacked == ctx->d_packed.as<double>());
     ctx->imp_k = 0;
     *handled = true;

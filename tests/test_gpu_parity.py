@@ -387,8 +387,9 @@ def test_relaxed_algorithms_large_library_inverse_path(ctx, alg, rho, prox):
     for i, tr in enumerate(traces):
         np.testing.assert_array_equal(out.support_path[i], np.asarray(tr.support_path))  # every threshold
         cp = np.asarray(tr.coef_path)
-        nz = cp != 0
-        assert (np.abs(out.coef_path[i][nz] - cp[nz]) / np.abs(cp[nz])).max() <= 1e-9
+        # 1e-9 relative per entry; a soft-thresholded entry w - lambda that almost cancels (4e-5 next to
+        # coefficients of 8) carries the absolute rounding of w, so allow 1e-13 of the largest coefficient
+        assert (np.abs(out.coef_path[i] - cp) <= 1e-9 * np.abs(cp) + 1e-13 * np.abs(cp).max()).all()
         assert list(out.iters_path[i]) == list(tr.iters_path)
     np.testing.assert_array_equal(out.coefficients != 0, ref.coefficients != 0)
     nz = ref.coefficients != 0

@@ -20,9 +20,9 @@ def _moment_plan(ex, n_t):
     assert count == k * k + k * n_t + n_t
     src = np.zeros(count, dtype=np.int32)
     tab = np.zeros(((nrb + ncb) * 128, 8), dtype=np.uint16)
-    pairs = np.zeros((npairs, 2), dtype=np.int32)
+    pairs = np.zeros((npairs, 3), dtype=np.int32)
     assert lib.ddb_moment_plan_describe(n, k, _lib.ptr(exf), n_t, _lib.ptr(src), src.size, _lib.ptr(tab), tab.size,
-                                        _lib.ptr(pairs), pairs.size // 2, None) == count
+                                        _lib.ptr(pairs), pairs.shape[0], None) == count
     return dict(src=src, tab=tab, pairs=pairs, nrb=nrb, ncb=ncb, npairs=npairs, nrows=nrows, ncols=ncols, nvirt=nvirt)
 
 
@@ -54,6 +54,12 @@ def test_moment_plan_maps_every_packed_entry_to_its_moment(n, deg, n_t):
     row = pairs[pair, 0] * 128 + off // 128
     col = pairs[pair, 1] * 128 + off % 128
     assert (pairs[:, 0] < nrb).all() and (pairs[:, 1] >= nrb).all()
+    # pairs at the edge of the staircase that only use their first 64 rows come last and are marked
+    assert set(pairs[:, 2].tolist()) <= {64, 128} and (np.diff(pairs[:, 2]) <= 0).all()
+    assert ((off // 128) < pairs[pair, 2]).all()
+    top = np.zeros(plan["npairs"], dtype=bool)
+    np.logical_or.at(top, pair, (off // 128) >= 64)
+    np.testing.assert_array_equal(top, pairs[:, 2] == 128)
     full = np.concatenate([ex.T.astype(np.int64), np.zeros((k, n_t), dtype=np.int64)], axis=1)  # library terms
     tgt = np.concatenate([np.zeros((n_t, n), dtype=np.int64), np.eye(n_t, dtype=np.int64)], axis=1)  # targets
     rng = np.random.default_rng(0)
@@ -78,7 +84,8 @@ def test_moment_plan_maps_every_packed_entry_to_its_moment(n, deg, n_t):
     assert np.unique(rep).size == keys.size
     assert np.unique(pair).size == plan["npairs"]  # no block pair without a needed entry
     nblk = -(-(k + n_t) // 128)
-    assert plan["npairs"] <= 0.9 * (0.5 * nblk * (nblk - 1) + 0.6 * nblk)
+    cost = (pairs[:, 2] == 128).sum() + 0.53 * (pairs[:, 2] == 64).sum()
+    assert cost <= 0.9 * (0.5 * nblk * (nblk - 1) + 0.6 * nblk)
 
 
 def test_moment_plan_lorenz96_counts():
@@ -86,12 +93,13 @@ def test_moment_plan_lorenz96_counts():
     of 153 off-diagonal + 18 diagonal ones."""
     plan = _moment_plan(oracle.polynomial_exponents(64, 2), 64)
     assert (plan["nrows"], plan["ncols"], plan["nrb"], plan["ncb"], plan["npairs"]) == (2145, 2145, 18, 18, 78)
+    assert (plan["pairs"][:, 2] == 64).sum() == 13  # 65 whole pairs + 13 half pairs: 71.9 pair units
 
 
 def test_moment_plan_steps_aside():
     """Small libraries (one or two blocks) and libraries whose splits produce too many foreign monomials keep the
     plain schedule."""
-    assert _moment_plan(oracle.polynomial_exponents(30, 2), 3) is None  # 8 block pairs against 6 + 4 diagonal
+    assert _moment_plan(oracle.polynomial_exponents(23, 2), 40) is None  # 5 block pairs against 3 + 3 diagonal
     ex = oracle.polynomial_exponents(30, 2).copy()
     ex[0, 17] += 1  # one cubic term: degree-3 splits of a degree-2 library leave the library
     assert _moment_plan(ex, 30) is None
