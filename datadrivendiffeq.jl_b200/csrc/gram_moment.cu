@@ -40,6 +40,7 @@ int gram_ensure_factors(ddb_ctx* ctx, int kaug_pad);
 namespace {
 
 constexpr int kBT = 128;
+constexpr int kMaxMomentTerms = 8192;  // the analysis walks k (k + 1) / 2 entries on the host (1.4 s at k = 5151)
 constexpr double kHalfCost = 0.53;  // measured cost of a 64 x 128 patch relative to a whole 128 x 128 pair
 using Key = std::array<uint16_t, kMaxFactors>;  // factor codes, ascending, leading zeros = the constant 1
 struct KeyHash {
@@ -98,7 +99,7 @@ struct MomentMap {
 
 static void analyse_library(const uint8_t* exps, int n, int k, int n_t, int D, MomentMap* M) {
     M->worth = false;
-    if (D < 1 || D > kMaxFactors) return;
+    if (D < 1 || D > kMaxFactors || k > kMaxMomentTerms) return;
     // sorted factor codes of every term, right-aligned in D entries (code = state index + 1, 0 = constant)
     std::vector<Key> term(k);
     for (int j = 0; j < k; ++j) {
