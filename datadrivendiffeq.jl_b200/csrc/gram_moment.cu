@@ -91,8 +91,9 @@ struct MomentState {
 struct MomentMap {
     bool worth = false;
     int nrows = 0, ncols = 0, nrb = 0, ncb = 0, nvirt = 0;
-    std::vector<std::pair<int, int>> pairs;  // (row block, nrb + column block), whole pairs first
-    std::vector<uint8_t> half;               // 1 = only rows 0..63 of the pair are needed
+    std::vector<std::pair<int, int>> pairs;  // (first, second operand block of the kernel): (row block, nrb + column
+                                             // block), or the other way round for a column-half pair; whole pairs first
+    std::vector<uint8_t> half;               // 1 = only rows 0..63 of the first operand block are needed
     std::vector<int32_t> src;                // per packed entry: (pair << 14) | (row-in-tile * 128 + column-in-tile)
     std::vector<uint16_t> tab;               // (nrb + ncb) * 128 virtual terms x kMaxFactors factor codes
 };
@@ -163,25 +164,33 @@ static void analyse_library(const uint8_t* exps, int n, int k, int n_t, int D, M
     const int nr_total = nrows + n_t, nc_total = n_t + ncols;
     const int nrb = (nr_total + kBT - 1) / kBT, ncb = (nc_total + kBT - 1) / kBT;
     // needed block pairs
-    // bit 0: an entry in rows 0..63 of the block pair, bit 1: one in rows 64..127
+    // bit 0: an entry in rows 0..63 of the block pair, bit 1: one in rows 64..127; bits 2, 3: the same for columns
     std::vector<int> pair_of((size_t)nrb * ncb, 0);
-    auto mark = [&](int r, int c) { pair_of[(size_t)(r / kBT) * ncb + c / kBT] |= (r % kBT) < 64 ? 1 : 2; };
+    auto mark = [&](int r, int c) {
+        pair_of[(size_t)(r / kBT) * ncb + c / kBT] |= ((r % kBT) < 64 ? 1 : 2) | ((c % kBT) < 64 ? 4 : 8);
+    };
     for (size_t i = 0; i < ntri; ++i) mark(rpos[er[i]], cpos[ec[i]]);
     for (int t = 0; t < k; ++t)
         for (int j = 0; j < n_t; ++j) mark(rpos[row_id[term[t]]], j);
     for (int j = 0; j < n_t; ++j) mark(nrows + j, j);
-    // whole pairs first, then the pairs at the edge of the staircase that only need their upper 64 rows (the
-    // kernel's 64 x 128 patch, about half the tensor work); pair_of becomes the pair index
+    // whole pairs first, then the pairs at the edge of the staircase that only need their first 64 rows -- or their
+    // first 64 columns: those run transposed (column block as the kernel's row operand) -- as the kernel's
+    // 64 x 128 patch, about half the tensor work; pair_of becomes the pair index
     M->pairs.clear();
     M->half.clear();
+    std::vector<uint8_t> transposed;
     for (int pass = 0; pass < 2; ++pass)
         for (int I = 0; I < nrb; ++I)
             for (int J = 0; J < ncb; ++J) {
                 int& cell = pair_of[(size_t)I * ncb + J];
-                if (cell <= 0 || (cell == 1) != (pass == 1)) continue;
+                if (cell <= 0) continue;
+                const bool row_half = (cell & 3) == 1, col_half = !row_half && (cell & 12) == 4;
+                if ((row_half || col_half) != (pass == 1)) continue;
                 cell = -(int)M->pairs.size() - 1;  // negative while the passes run: index = -cell - 1
-                M->pairs.push_back({I, nrb + J});
+                if (col_half) M->pairs.push_back({nrb + J, I});
+                else M->pairs.push_back({I, nrb + J});
                 M->half.push_back(pass == 1);
+                transposed.push_back(col_half);
             }
     for (int& cell : pair_of) cell = cell < 0 ? -cell - 1 : -1;
     const int npairs = (int)M->pairs.size();
@@ -205,7 +214,9 @@ static void analyse_library(const uint8_t* exps, int n, int k, int n_t, int D, M
     std::vector<int32_t>& src = M->src;
     src.assign(count, 0);
     auto src_of = [&](int r, int c) {
-        return (int32_t)((pair_of[(size_t)(r / kBT) * ncb + c / kBT] << 14) | ((r % kBT) * kBT + (c % kBT)));
+        const int p = pair_of[(size_t)(r / kBT) * ncb + c / kBT];
+        const int off = transposed[p] ? (c % kBT) * kBT + (r % kBT) : (r % kBT) * kBT + (c % kBT);
+        return (int32_t)((p << 14) | off);
     };
     e = 0;
     for (int t = 0; t < k; ++t)

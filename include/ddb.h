@@ -301,10 +301,12 @@ int64_t ddb_gram_plan_describe(int kaug, int64_t m, int nctas, int64_t* segments
  * number of packed entries and writes, each up to its cap and each optional:
  *   src     per packed entry (pair << 14) | (row_in_tile * 128 + column_in_tile);
  *   factors (row_blocks + column_blocks) * 128 virtual terms x 8 factor codes: state index, 0x8000 | target
- *           index, 0xFFFF = no factor; row block I holds virtual terms [128 I, 128 I + 128), column block J
- *           the terms [128 (row_blocks + J), ...);
- *   pairs   block_pairs x {row_block, row_blocks + column_block, rows}: rows = 128, or 64 for a pair at the edge of
- *           the staircase whose needed entries all lie in its first 64 rows (whole pairs come first).
+ *           index, 0xFFFF = no factor; block B holds the virtual terms [128 B, 128 B + 128); blocks
+ *           [0, row_blocks) are the virtual rows, the others the virtual columns;
+ *   pairs   block_pairs x {first_block, second_block, rows}: the pair's tile is (terms of first_block) x (terms
+ *           of second_block); rows = 128, or 64 for a pair at the edge of the staircase whose needed entries all
+ *           lie in the first 64 terms of first_block (such a pair may have a column block first).  Whole pairs
+ *           come first.
  * Needs no GPU. */
 int64_t ddb_moment_plan_describe(int n, int k, const uint8_t* exps, int n_t, int32_t* src, int64_t src_cap, uint16_t* factors,
                                  int64_t factors_cap, int32_t* pairs, int64_t pairs_cap, int64_t* info);

@@ -64,7 +64,7 @@ def test_moment_schedule_lorenz96_library(ctx, m):
 
 @pytest.mark.parametrize("n,deg,n_t,m,used", [(12, 3, 12, 9000, True), (20, 3, 20, 5000, True), (9, 4, 2, 5001, True),
                                                 (40, 2, 5, 7000, True), (7, 4, 2, 5001, True), (30, 2, 3, 7000, True),
-                                                (23, 2, 40, 4100, False)])
+                                                (23, 2, 40, 4100, True), (20, 2, 100, 4100, False)])
 def test_moment_schedule_other_libraries(ctx, n, deg, n_t, m, used):
     """Higher degrees (P and Q are degree-3 / degree-4 monomials), n_t != n, a short target block; libraries of a
     few blocks where the staircase saves nothing keep the plain schedule (`used` False)."""

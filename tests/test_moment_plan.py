@@ -53,7 +53,8 @@ def test_moment_plan_maps_every_packed_entry_to_its_moment(n, deg, n_t):
     pair, off = src >> 14, src & 16383
     row = pairs[pair, 0] * 128 + off // 128
     col = pairs[pair, 1] * 128 + off % 128
-    assert (pairs[:, 0] < nrb).all() and (pairs[:, 1] >= nrb).all()
+    assert ((pairs[:, 0] < nrb) != (pairs[:, 1] < nrb)).all()  # a row block and a column block, either order
+    assert (pairs[pairs[:, 2] == 128, 0] < nrb).all()
     # pairs at the edge of the staircase that only use their first 64 rows come last and are marked
     assert set(pairs[:, 2].tolist()) <= {64, 128} and (np.diff(pairs[:, 2]) <= 0).all()
     assert ((off // 128) < pairs[pair, 2]).all()
@@ -93,13 +94,13 @@ def test_moment_plan_lorenz96_counts():
     of 153 off-diagonal + 18 diagonal ones."""
     plan = _moment_plan(oracle.polynomial_exponents(64, 2), 64)
     assert (plan["nrows"], plan["ncols"], plan["nrb"], plan["ncb"], plan["npairs"]) == (2145, 2145, 18, 18, 78)
-    assert (plan["pairs"][:, 2] == 64).sum() == 13  # 65 whole pairs + 13 half pairs: 71.9 pair units
+    assert (plan["pairs"][:, 2] == 64).sum() == 16  # 62 whole pairs + 13 row-half + 3 column-half pairs: 70.5 pair units
 
 
 def test_moment_plan_steps_aside():
     """Small libraries (one or two blocks) and libraries whose splits produce too many foreign monomials keep the
     plain schedule."""
-    assert _moment_plan(oracle.polynomial_exponents(23, 2), 40) is None  # 5 block pairs against 3 + 3 diagonal
+    assert _moment_plan(oracle.polynomial_exponents(20, 2), 100) is None  # many targets: 5 block pairs against 3 + 3 diagonal
     ex = oracle.polynomial_exponents(30, 2).copy()
     ex[0, 17] += 1  # one cubic term: degree-3 splits of a degree-2 library leave the library
     assert _moment_plan(ex, 30) is None
