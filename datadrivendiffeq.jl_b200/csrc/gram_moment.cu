@@ -12,7 +12,9 @@
 //     decreasing min(Q), its COLUMNS (the targets come first among the columns: R = Theta Y' needs every
 //     row; they are also appended to the rows for diag(Y Y'));
 //   * the needed (P, Q) entries then form a staircase in the rows x columns plane, and only the 128 x 128
-//     block pairs that the staircase touches are contracted: 78 at Lorenz-96 against 153 + 18 diagonal;
+//     block pairs that the staircase touches are contracted: 78 at Lorenz-96 against 153 + 18 diagonal, and
+//     pairs at its edge that only need their first 64 rows (or columns: run transposed) use the kernel's
+//     64 x 128 patch;
 //   * a gather kernel writes every entry of the packed [G | R | yy] from the tile entry of its moment
 //     (G comes out exactly symmetric, and bit-reproducible: fixed slot order, no atomics).
 //
