@@ -79,12 +79,13 @@ struct BuildJobs {
     int str[NJ][NF];  // per-sample stride of factor d
     int dst[NJ];      // offset of the column inside a Theta stage
     int s0;           // first sample this thread builds
+    bool live;        // false: the plan does not need this thread's column (rows past 64 / 32 of a half / quarter pair)
 };
 
 // One stage (16 samples): 4 k-steps of {build SPK samples of a later stage, load fragments, DMMAs}.
 // Straight-line code (the live sub-tiles are a template parameter) so that ptxas can software-
 // pipeline the shared-memory loads under the DMMAs and no DMMA is predicated.
-template <int BT, int NF, uint32_t MASK, bool SAME>
+template <int BT, int NF, uint32_t MASK, bool SAME, bool BUILD = true>
 __device__ __forceinline__ void stage_body(double (&acc)[8][4][2], const double* __restrict__ pa,
                                            const double* __restrict__ pb, const double* __restrict__ v,
                                            double* __restrict__ tnext,
@@ -95,12 +96,14 @@ __device__ __forceinline__ void stage_body(double (&acc)[8][4][2], const double*
 #pragma unroll
     for (int kk = 0; kk < kKS / 4; ++kk) {
         double fv[NJ][SPK][NF];
+        if constexpr (BUILD) {
 #pragma unroll
-        for (int j = 0; j < NJ; ++j)
+            for (int j = 0; j < NJ; ++j)
 #pragma unroll
-            for (int q = 0; q < SPK; ++q)
+                for (int q = 0; q < SPK; ++q)
 #pragma unroll
-                for (int d = 0; d < NF; ++d) fv[j][q][d] = v[jb.off[j][d] + (jb.s0 + kk * SPK + q) * jb.str[j][d]];
+                    for (int d = 0; d < NF; ++d) fv[j][q][d] = v[jb.off[j][d] + (jb.s0 + kk * SPK + q) * jb.str[j][d]];
+        }
         double a[8], b[4];
 #pragma unroll
         for (int i = 0; i < 8; ++i)
@@ -108,15 +111,17 @@ __device__ __forceinline__ void stage_body(double (&acc)[8][4][2], const double*
 #pragma unroll
         for (int j = 0; j < 4; ++j)
             if ((MASK >> j) & 0x11111111u) b[j] = pb[kk * 4 * LDT + 8 * j];
+        if constexpr (BUILD) {
 #pragma unroll
-        for (int j = 0; j < NJ; ++j)
+            for (int j = 0; j < NJ; ++j)
 #pragma unroll
-            for (int q = 0; q < SPK; ++q) {
-                double p = fv[j][q][0];
+                for (int q = 0; q < SPK; ++q) {
+                    double p = fv[j][q][0];
 #pragma unroll
-                for (int d = 1; d < NF; ++d) p *= fv[j][q][d];
-                tnext[jb.dst[j] + (jb.s0 + kk * SPK + q) * LDT] = p;
-            }
+                    for (int d = 1; d < NF; ++d) p *= fv[j][q][d];
+                    tnext[jb.dst[j] + (jb.s0 + kk * SPK + q) * LDT] = p;
+                }
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
@@ -226,6 +231,7 @@ __global__ void __launch_bounds__(GramCfg<BT>::kThreads, GramCfg<BT>::kMinBlocks
         bstage = seg.stage_begin;
         bseg_end = seg.stage_end;
         bsame = (seg.bi == seg.bj);
+        jb.live = true;
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
             int tile, col;
@@ -239,6 +245,8 @@ __global__ void __launch_bounds__(GramCfg<BT>::kThreads, GramCfg<BT>::kMinBlocks
                 jb.s0 = 0;
             }
             jb.dst[j] = tile * KS * LDT + col;
+            // half / quarter pairs of the moment schedule: rows past 64 / 32 of the row tile are never read
+            if (BT == 128 && tile == 0 && (((seg.pad & 1) && col >= 64) || ((seg.pad & 2) && col >= 32))) jb.live = false;
             const int term = (tile == 0 ? seg.bi : seg.bj) * BT + col;
             const uint4 q = *reinterpret_cast<const uint4*>(args.factors + (size_t)term * kMaxFactors);
             const uint32_t w[4] = {q.x, q.y, q.z, q.w};
@@ -271,7 +279,7 @@ __global__ void __launch_bounds__(GramCfg<BT>::kThreads, GramCfg<BT>::kMinBlocks
         mbar_wait(&vfull[it], 0);
         const double* v = vring + it * vdoubles;
         double* dstt = tring + it * Cfg::kStageDoubles;
-        const int njobs = (BT == 128 || bsame) ? 1 : 2;
+        const int njobs = !jb.live ? 0 : (BT == 128 || bsame) ? 1 : 2;
         const int cnt = (BT == 128 && bsame) ? KS / 2 : KS;
         for (int j = 0; j < njobs; ++j)
             for (int s = jb.s0; s < jb.s0 + cnt; ++s) {
@@ -303,12 +311,13 @@ __global__ void __launch_bounds__(GramCfg<BT>::kThreads, GramCfg<BT>::kMinBlocks
         const bool same = (seg.bi == seg.bj);
         const int rows_valid = min(BT, args.kaug - seg.bi * BT);
         // block rows with at most 64 live rows: lay all warps side by side (64 x 16 patches)
-        const bool flat = (BT == 128) && (rows_valid <= 64 || (seg.pad & 1));  // pad bit 0: the plan only needs rows 0..63
+        // pad bit 0: the plan only needs rows 0..63 of this pair, bit 1: only rows 0..31 (moment schedule)
+        const bool flat = (BT == 128) && (rows_valid <= 64 || (seg.pad & 3));
         const int row0 = flat ? 0 : wm * 64;
         const int col0 = flat ? warp * 16 : wn * 32;
-        // shape of this warp's patch: 0 full, 1 diagonal offset 0, 2 diagonal offset -4, 3 empty, 4 flat
+        // shape of this warp's patch: 0 full, 1 diagonal offset 0, 2 diagonal offset -4, 3 empty, 4 flat, 5 quarter
         int shape = 0;
-        if (flat) shape = 4;
+        if (flat) shape = (seg.pad & 2) ? 5 : 4;
         else if (same) {
             const int d = (row0 - col0) / 8;
             shape = (d >= 3) ? 0 : (d == 0 ? 1 : (d == -4 ? 2 : 3));
@@ -317,7 +326,8 @@ __global__ void __launch_bounds__(GramCfg<BT>::kThreads, GramCfg<BT>::kMinBlocks
                               : shape == 1 ? kShapeDiag0
                               : shape == 2 ? kShapeDiagM4
                               : shape == 3 ? kShapeEmpty
-                                           : kShapeFlat;
+                              : shape == 4 ? kShapeFlat
+                                           : kShapeQuarter;
 
         double acc[8][4][2];
 #pragma unroll
@@ -350,14 +360,16 @@ __global__ void __launch_bounds__(GramCfg<BT>::kThreads, GramCfg<BT>::kMinBlocks
 #define DDB_STAGE(M)                                                                     \
     do {                                                                                 \
         if (bsame) stage_body<BT, NF, M, true>(acc, pa, pb, v, tnext, jb);               \
-        else stage_body<BT, NF, M, false>(acc, pa, pb, v, tnext, jb);                    \
+        else if (jb.live) stage_body<BT, NF, M, false>(acc, pa, pb, v, tnext, jb);       \
+        else stage_body<BT, NF, M, false, false>(acc, pa, pb, v, tnext, jb);             \
     } while (0)
             switch (shape) {
                 case 0: DDB_STAGE(kShapeFull); break;
                 case 1: DDB_STAGE(kShapeDiag0); break;
                 case 2: DDB_STAGE(kShapeDiagM4); break;
                 case 3: DDB_STAGE(kShapeEmpty); break;
-                default: DDB_STAGE(kShapeFlat); break;
+                case 4: DDB_STAGE(kShapeFlat); break;
+                default: DDB_STAGE(kShapeQuarter); break;
             }
 #undef DDB_STAGE
             if (have_next) {

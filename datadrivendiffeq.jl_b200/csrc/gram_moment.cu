@@ -43,7 +43,8 @@ namespace {
 
 constexpr int kBT = 128;
 constexpr int kMaxMomentTerms = 8192;  // the analysis walks k (k + 1) / 2 entries on the host (1.4 s at k = 5151)
-constexpr double kHalfCost = 0.53;  // measured cost of a 64 x 128 patch relative to a whole 128 x 128 pair
+constexpr double kHalfCost = 0.53;     // measured cost of a 64 x 128 patch relative to a whole 128 x 128 pair
+constexpr double kQuarterCost = 0.45;  // 32 x 128 patch (eight DMMAs per warp and k-step do not fill the pipe)
 using Key = std::array<uint16_t, kMaxFactors>;  // factor codes, ascending, leading zeros = the constant 1
 struct KeyHash {
     size_t operator()(const Key& k) const {
@@ -77,7 +78,7 @@ struct MomentState {
     bool eligible = false;
     int nrb = 0, ncb = 0, nvirt = 0, npairs = 0;
     std::vector<std::pair<int, int>> pairs;  // (row block, nrb + column block), whole pairs first
-    int nfull = 0;                           // pairs [nfull, npairs) only need their rows 0..63
+    int nfull = 0, nhalf = 0;                // pairs [nfull, nfull + nhalf) only need rows 0..63, the rest rows 0..31
     DevBuf factors, src;
     // sample-count-dependent part
     int64_t plan_m = -1;
@@ -95,7 +96,7 @@ struct MomentMap {
     int nrows = 0, ncols = 0, nrb = 0, ncb = 0, nvirt = 0;
     std::vector<std::pair<int, int>> pairs;  // (first, second operand block of the kernel): (row block, nrb + column
                                              // block), or the other way round for a column-half pair; whole pairs first
-    std::vector<uint8_t> half;               // 1 = only rows 0..63 of the first operand block are needed
+    std::vector<uint8_t> rows_used;          // 128, or 64 / 32: only that many leading rows of the first operand block are needed
     std::vector<int32_t> src;                // per packed entry: (pair << 14) | (row-in-tile * 128 + column-in-tile)
     std::vector<uint16_t> tab;               // (nrb + ncb) * 128 virtual terms x kMaxFactors factor codes
 };
@@ -129,26 +130,67 @@ static void analyse_library(const uint8_t* exps, int n, int k, int n_t, int D, M
     // (row id, column id) of every lower-triangular Gram entry
     const size_t ntri = (size_t)k * (k + 1) / 2;
     std::vector<int32_t> er(ntri), ec(ntri);
-    const size_t limit = (size_t)(k + n_t) * 3 / 2 + 256;  // more virtual rows / columns than this: not worth it
-    size_t e = 0;
-    for (int t = 0; t < k; ++t) {
-        const Key& a = term[t];
-        for (int u = 0; u <= t; ++u, ++e) {
-            const Key& b = term[u];
-            uint16_t mg[2 * kMaxFactors];
-            std::merge(a.begin(), a.begin() + D, b.begin(), b.begin() + D, mg);
-            Key P{}, Q{};
+    // A moment may be cut in several ways; any (P, Q) whose product is the moment will do.  In order:
+    //   1. the D smallest / D largest of the padded factor list (densest staircase).  If over the whole library
+    //      this cut needs only a few monomials that are not library terms (e.g. the constant of a library without
+    //      one), they become virtual terms and cut 1 is used throughout.  Otherwise, for an entry whose cut 1
+    //      leaves the library:
+    //   2. the lower / upper half of the actual factors if both are library terms (mixed-degree libraries);
+    //   3. the entry's own two terms.
+    const std::unordered_map<Key, int, KeyHash> lib = row_id;
+    auto in_lib = [&](const Key& key) { return lib.find(key) != lib.end(); };
+    // cut `which` (1 or 2) of entry (t, u); returns whether both parts are library terms
+    auto cut = [&](int t, int u, int which, Key& P, Key& Q) {
+        uint16_t mg[2 * kMaxFactors];
+        std::merge(term[t].begin(), term[t].begin() + D, term[u].begin(), term[u].begin() + D, mg);
+        P = Key{};
+        Q = Key{};
+        if (which == 1) {
             for (int i = 0; i < D; ++i) {
                 P[i] = mg[i];
                 Q[i] = mg[D + i];
             }
+        } else {
+            int z = 0;
+            while (z < 2 * D && mg[z] == 0) ++z;
+            const int L = 2 * D - z, lp = L / 2, lq = L - lp;
+            for (int i = 0; i < lp; ++i) P[D - lp + i] = mg[z + i];
+            for (int i = 0; i < lq; ++i) Q[D - lq + i] = mg[z + lp + i];
+        }
+        return in_lib(P) && in_lib(Q);
+    };
+    std::vector<uint8_t> choice(ntri, 0);  // 0 = neither cut stays inside the library
+    std::unordered_map<Key, int, KeyHash> foreign;
+    size_t e = 0;
+    for (int t = 0; t < k; ++t)
+        for (int u = 0; u <= t; ++u, ++e) {
+            Key P, Q;
+            if (cut(t, u, 1, P, Q)) {
+                choice[e] = 1;
+            } else {
+                if (!in_lib(P)) foreign.emplace(P, 0);
+                if (!in_lib(Q)) foreign.emplace(Q, 0);
+                if (cut(t, u, 2, P, Q)) choice[e] = 2;
+            }
+        }
+    const bool allow_foreign = foreign.size() <= (size_t)(32 + (k + n_t) / 16);
+    e = 0;
+    for (int t = 0; t < k; ++t)
+        for (int u = 0; u <= t; ++u, ++e) {
+            Key P, Q;
+            if (allow_foreign || choice[e] == 1) {
+                cut(t, u, 1, P, Q);
+            } else if (choice[e] == 2) {
+                cut(t, u, 2, P, Q);
+            } else {
+                P = term[t];
+                Q = term[u];
+            }
             er[e] = get(row_id, rows, P);
             ec[e] = get(col_id, cols, Q);
         }
-        if (rows.size() > limit || cols.size() > limit) return;
-    }
-    // positions: rows by increasing max (then lexicographic), targets last; columns: targets first, then by
-    // decreasing min (then lexicographic)
+    // positions: rows by increasing max (then lexicographic), targets last; columns: targets first, then the
+    // full-degree ones by decreasing min, then the lower-degree ones by decreasing min (then lexicographic)
     const int nrows = (int)rows.size(), ncols = (int)cols.size();
     std::vector<int> rorder(nrows), corder(ncols), rpos(nrows), cpos(ncols);
     for (int i = 0; i < nrows; ++i) rorder[i] = i;
@@ -157,8 +199,15 @@ static void analyse_library(const uint8_t* exps, int n, int k, int n_t, int D, M
         if (rows[x][D - 1] != rows[y][D - 1]) return rows[x][D - 1] < rows[y][D - 1];
         return rows[x] < rows[y];
     });
+    auto min_factor = [&](const Key& key) {  // smallest actual factor (0 for the constant)
+        for (int i = 0; i < D; ++i)
+            if (key[i]) return (int)key[i];
+        return 0;
+    };
     std::sort(corder.begin(), corder.end(), [&](int x, int y) {
-        if (cols[x][0] != cols[y][0]) return cols[x][0] > cols[y][0];
+        if (cols[x][0] != cols[y][0]) return cols[x][0] > cols[y][0];  // full-degree columns first
+        const int mx = min_factor(cols[x]), my = min_factor(cols[y]);
+        if (mx != my) return mx > my;
         return cols[x] < cols[y];
     });
     for (int i = 0; i < nrows; ++i) rpos[rorder[i]] = i;
@@ -166,33 +215,37 @@ static void analyse_library(const uint8_t* exps, int n, int k, int n_t, int D, M
     const int nr_total = nrows + n_t, nc_total = n_t + ncols;
     const int nrb = (nr_total + kBT - 1) / kBT, ncb = (nc_total + kBT - 1) / kBT;
     // needed block pairs
-    // bit 0: an entry in rows 0..63 of the block pair, bit 1: one in rows 64..127; bits 2, 3: the same for columns
+    // bits 0..3: a needed entry in rows [32 q, 32 q + 32) of the block pair, bits 4..7: the same for columns
     std::vector<int> pair_of((size_t)nrb * ncb, 0);
     auto mark = [&](int r, int c) {
-        pair_of[(size_t)(r / kBT) * ncb + c / kBT] |= ((r % kBT) < 64 ? 1 : 2) | ((c % kBT) < 64 ? 4 : 8);
+        pair_of[(size_t)(r / kBT) * ncb + c / kBT] |= (1 << ((r % kBT) / 32)) | (16 << ((c % kBT) / 32));
     };
     for (size_t i = 0; i < ntri; ++i) mark(rpos[er[i]], cpos[ec[i]]);
     for (int t = 0; t < k; ++t)
         for (int j = 0; j < n_t; ++j) mark(rpos[row_id[term[t]]], j);
     for (int j = 0; j < n_t; ++j) mark(nrows + j, j);
-    // whole pairs first, then the pairs at the edge of the staircase that only need their first 64 rows -- or their
-    // first 64 columns: those run transposed (column block as the kernel's row operand) -- as the kernel's
-    // 64 x 128 patch, about half the tensor work; pair_of becomes the pair index
+    // whole pairs first, then the pairs at the edge of the staircase that only need their first 64, then those
+    // that only need their first 32 rows -- or columns: those run transposed (column block as the kernel's row
+    // operand) -- as the kernel's 64 x 128 / 32 x 128 patches; pair_of becomes the pair index
     M->pairs.clear();
-    M->half.clear();
+    M->rows_used.clear();
     std::vector<uint8_t> transposed;
-    for (int pass = 0; pass < 2; ++pass)
+    auto extent = [](int bits) { return (bits & 8) ? 128 : (bits & 4) ? 96 : (bits & 2) ? 64 : 32; };
+    for (int pass = 0; pass < 3; ++pass)
         for (int I = 0; I < nrb; ++I)
             for (int J = 0; J < ncb; ++J) {
                 int& cell = pair_of[(size_t)I * ncb + J];
                 if (cell <= 0) continue;
-                const bool row_half = (cell & 3) == 1, col_half = !row_half && (cell & 12) == 4;
-                if ((row_half || col_half) != (pass == 1)) continue;
+                const int re = extent(cell & 15), ce = extent((cell >> 4) & 15);
+                const int rcls = re <= 32 ? 32 : re <= 64 ? 64 : 128, ccls = ce <= 32 ? 32 : ce <= 64 ? 64 : 128;
+                const int used = std::min(rcls, ccls);
+                if (used != (pass == 0 ? 128 : pass == 1 ? 64 : 32)) continue;
+                const bool tr = ccls < rcls;
                 cell = -(int)M->pairs.size() - 1;  // negative while the passes run: index = -cell - 1
-                if (col_half) M->pairs.push_back({nrb + J, I});
+                if (tr) M->pairs.push_back({nrb + J, I});
                 else M->pairs.push_back({I, nrb + J});
-                M->half.push_back(pass == 1);
-                transposed.push_back(col_half);
+                M->rows_used.push_back((uint8_t)used);
+                transposed.push_back(tr);
             }
     for (int& cell : pair_of) cell = cell < 0 ? -cell - 1 : -1;
     const int npairs = (int)M->pairs.size();
@@ -205,10 +258,12 @@ static void analyse_library(const uint8_t* exps, int n, int k, int n_t, int D, M
     const int nblk = (k + n_t + kBT - 1) / kBT;
     const double plain = 0.5 * nblk * (nblk - 1) + 0.6 * nblk;
     if (getenv("DDB_GRAM_DEBUG"))
-        fprintf(stderr, "[ddb] moment schedule: k=%d n_t=%d D=%d rows=%d cols=%d blocks %d x %d pairs=%d of which %d half (plain %.1f)\n",
-                k, n_t, D, nrows, ncols, nrb, ncb, npairs, (int)std::count(M->half.begin(), M->half.end(), (uint8_t)1), plain);
+        fprintf(stderr, "[ddb] moment schedule: k=%d n_t=%d D=%d rows=%d cols=%d blocks %d x %d pairs=%d: %d whole, %d half, %d quarter (plain %.1f)\n",
+                k, n_t, D, nrows, ncols, nrb, ncb, npairs, (int)std::count(M->rows_used.begin(), M->rows_used.end(), (uint8_t)128),
+                (int)std::count(M->rows_used.begin(), M->rows_used.end(), (uint8_t)64),
+                (int)std::count(M->rows_used.begin(), M->rows_used.end(), (uint8_t)32), plain);
     double cost = 0.0;
-    for (uint8_t h : M->half) cost += h ? kHalfCost : 1.0;
+    for (uint8_t h : M->rows_used) cost += h == 128 ? 1.0 : h == 64 ? kHalfCost : kQuarterCost;
     if (npairs >= (1 << 17) || cost > 0.9 * plain) return;
 
     // gather map of the packed [G | R | yy]
@@ -259,7 +314,8 @@ static int install_library(ddb_ctx* ctx, MomentState* M) {
     if (!map.worth) return DDB_OK;
     M->pairs = map.pairs;
     M->npairs = (int)map.pairs.size();
-    M->nfull = (int)std::count(map.half.begin(), map.half.end(), (uint8_t)0);
+    M->nfull = (int)std::count(map.rows_used.begin(), map.rows_used.end(), (uint8_t)128);
+    M->nhalf = (int)std::count(map.rows_used.begin(), map.rows_used.end(), (uint8_t)64);
     M->nrb = map.nrb;
     M->ncb = map.ncb;
     M->nvirt = map.nvirt;
@@ -299,7 +355,7 @@ int64_t moment_plan_describe(const uint8_t* exps, int n, int k, int n_t, int32_t
         for (int64_t i = 0; i < std::min<int64_t>(pairs_cap, (int64_t)map.pairs.size()); ++i) {
             pairs[3 * i] = map.pairs[i].first;
             pairs[3 * i + 1] = map.pairs[i].second;
-            pairs[3 * i + 2] = map.half[i] ? 64 : 128;
+            pairs[3 * i + 2] = map.rows_used[i];
         }
     return (int64_t)map.src.size();
 }
@@ -314,9 +370,9 @@ static int build_wave_plan(ddb_ctx* ctx, MomentState* M) {
     std::vector<int32_t> psb(M->npairs + 1, 0);
     int first = 0, nslots = 0;
     while (first < M->npairs) {
-        // waves never mix whole and half pairs (the CTAs of a wave must take the same time)
-        const bool half = first >= M->nfull;
-        const int remaining = (half ? M->npairs : M->nfull) - first;
+        // waves never mix whole, half and quarter pairs (the CTAs of a wave must take the same time)
+        const int cls = first < M->nfull ? 0 : first < M->nfull + M->nhalf ? 1 : 2;
+        const int remaining = (cls == 0 ? M->nfull : cls == 1 ? M->nfull + M->nhalf : M->npairs) - first;
         int nr = (nctas + remaining - 1) / remaining;
         nr = (int)std::max<int64_t>(1, std::min<int64_t>(nr, ns));
         const int np = std::min(remaining, nctas / nr);
@@ -327,7 +383,7 @@ static int build_wave_plan(ddb_ctx* ctx, MomentState* M) {
                 sg.bi = M->pairs[first + p].first;
                 sg.bj = M->pairs[first + p].second;
                 sg.slot = nslots++;
-                sg.pad = half ? 1 : 0;  // bit 0: 64 x 128 patch
+                sg.pad = cls;  // 1: 64 x 128 patch, 2: 32 x 128 patch
                 sg.stage_begin = ns * r / nr;
                 sg.stage_end = ns * (r + 1) / nr;
                 per_cta[r * np + p].push_back(sg);
@@ -403,7 +459,7 @@ int gram_moment_run(ddb_ctx* ctx, double* dPacked, bool* handled) {
     ctx->timings.gram_ms = ms;
     ctx->timings.gram_launches = 2;
     ctx->timings.gram_schedule = 2;
-    ctx->timings.gram_dmma_flops = 2.0 * kBT * kBT * (M->nfull + 0.5 * (M->npairs - M->nfull));
+    ctx->timings.gram_dmma_flops = 2.0 * kBT * kBT * (M->nfull + 0.5 * M->nhalf + 0.25 * (M->npairs - M->nfull - M->nhalf));
     ctx->have_gram = (dPacked == ctx->d_packed.as<double>());
     ctx->imp_k = 0;
     *handled = true;

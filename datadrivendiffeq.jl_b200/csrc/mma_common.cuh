@@ -94,6 +94,8 @@ constexpr uint32_t kShapeDiag0 = shape_mask(0, 4);
 constexpr uint32_t kShapeDiagM4 = shape_mask(-4, 4);
 constexpr uint32_t kShapeEmpty = 0u;
 constexpr uint32_t kShapeFlat = shape_mask(8, 2);
+// QUARTER: the first four sub-tile rows of a FLAT patch -> rows 0..31 of the block pair over all eight warps
+constexpr uint32_t kShapeQuarter = kShapeFlat & 0xFFFFu;
 
 
 }  // namespace ddb

@@ -304,9 +304,9 @@ int64_t ddb_gram_plan_describe(int kaug, int64_t m, int nctas, int64_t* segments
  *           index, 0xFFFF = no factor; block B holds the virtual terms [128 B, 128 B + 128); blocks
  *           [0, row_blocks) are the virtual rows, the others the virtual columns;
  *   pairs   block_pairs x {first_block, second_block, rows}: the pair's tile is (terms of first_block) x (terms
- *           of second_block); rows = 128, or 64 for a pair at the edge of the staircase whose needed entries all
- *           lie in the first 64 terms of first_block (such a pair may have a column block first).  Whole pairs
- *           come first.
+ *           of second_block); rows = 128, or 64 / 32 for a pair at the edge of the staircase whose needed entries
+ *           all lie in the first 64 / 32 terms of first_block (such a pair may have a column block first).  Whole
+ *           pairs come first, then the 64-row, then the 32-row ones.
  * Needs no GPU. */
 int64_t ddb_moment_plan_describe(int n, int k, const uint8_t* exps, int n_t, int32_t* src, int64_t src_cap, uint16_t* factors,
                                  int64_t factors_cap, int32_t* pairs, int64_t pairs_cap, int64_t* info);

@@ -64,7 +64,7 @@ def test_moment_schedule_lorenz96_library(ctx, m):
 
 @pytest.mark.parametrize("n,deg,n_t,m,used", [(12, 3, 12, 9000, True), (20, 3, 20, 5000, True), (9, 4, 2, 5001, True),
                                                 (40, 2, 5, 7000, True), (7, 4, 2, 5001, True), (30, 2, 3, 7000, True),
-                                                (23, 2, 40, 4100, True), (20, 2, 100, 4100, False)])
+                                                (23, 2, 40, 4100, True), (20, 2, 100, 4100, True), (12, 2, 150, 4100, False)])
 def test_moment_schedule_other_libraries(ctx, n, deg, n_t, m, used):
     """Higher degrees (P and Q are degree-3 / degree-4 monomials), n_t != n, a short target block; libraries of a
     few blocks where the staircase saves nothing keep the plain schedule (`used` False)."""
@@ -95,6 +95,24 @@ def test_moment_schedule_incomplete_library(ctx):
     X = 0.8 * rng.standard_normal((n, m))
     Y = rng.standard_normal((n, m))
     _check(ctx, ex2, X, Y, tol=2e-13)
+
+
+def test_moment_schedule_mixed_degree_and_no_constant_libraries(ctx):
+    """The C3 library plus three cubic terms (cuts by actual degree, entries with a cubic term keep their own two
+    terms) and the C3 library without the constant (the constant becomes a virtual term outside the library):
+    both run on the moment schedule."""
+    n, m = 64, 3000
+    rng = np.random.default_rng(8)
+    X = 0.8 * rng.standard_normal((n, m))
+    Y = rng.standard_normal((n, m))
+    ex = oracle.polynomial_exponents(n, 2)
+    extra = np.zeros((n, 3), dtype=ex.dtype)
+    extra[0, 0] = 3
+    extra[1, 1], extra[2, 1] = 2, 1
+    extra[5, 2] = extra[6, 2] = extra[7, 2] = 1
+    for lib in (np.concatenate([ex, extra], axis=1), ex[:, 1:]):
+        _res, t1, _t0 = _check(ctx, lib, X, Y, tol=2e-13)
+        assert t1["gram_schedule"] == 2
 
 
 def test_moment_schedule_is_bit_reproducible_and_sample_views_work(ctx):
