@@ -160,7 +160,11 @@ int64_t ddb_gram_count(const ddb_ctx* ctx);
  *   G = Theta Theta' (k x k), R = Theta Y' (k x n_t), yy[i] = sum_s Y[i,s]^2,
  * Theta never written to memory.  Replaces the per-target `A*A'`, `B*A'` of
  * STLSQ.jl:90-91 / ADMM.jl:77-79 / SR3.jl:108-109 and the library evaluation feeding them.
- * dPacked: device buffer of ddb_gram_count() doubles, or NULL to use the context's own buffer. */
+ * dPacked: device buffer of ddb_gram_count() doubles, or NULL to use the context's own buffer.
+ * G is exactly symmetric and the result is bit-reproducible from call to call.  For monomial libraries the
+ * entries are contracted moment by moment (see ddb_moment_plan_describe): G[t,u] is the sum over the samples of
+ * the product of two monomials whose product is theta_t theta_u, not necessarily theta_t and theta_u themselves,
+ * so it differs from the plain contraction in the last bits (ddb_timings.gram_schedule says which ran). */
 int ddb_gram(ddb_ctx* ctx, double* dPacked);
 
 /* ddb_upload + ddb_gram in one call with the host->device copies OVERLAPPED by the Gram kernels: the samples
