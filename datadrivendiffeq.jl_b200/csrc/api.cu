@@ -47,6 +47,8 @@ void sweep_free(ddb_ctx* ctx);
 void dmd_free(ddb_ctx* ctx);
 void ring_free(ddb_ctx* ctx);
 void moment_free(ddb_ctx* ctx);
+int64_t moment_wave_describe(const uint8_t* exps, int n, int k, int n_t, int64_t m, int nctas, int64_t* segments,
+                             int64_t cap, double* info);
 int64_t moment_plan_describe(const uint8_t* exps, int n, int k, int n_t, int32_t* src, int64_t src_cap, uint16_t* tab,
                              int64_t tab_cap, int32_t* pairs, int64_t pairs_cap, int64_t* info);
 void trsm_free(ddb_ctx* ctx);
@@ -655,6 +657,15 @@ int64_t ddb_moment_plan_describe(int n, int k, const uint8_t* exps, int n_t, int
         return DDB_INVALID_ARG;
     }
     return moment_plan_describe(exps, n, k, n_t, src, src_cap, factors, factors_cap, pairs, pairs_cap, info);
+}
+
+int64_t ddb_moment_wave_describe(int n, int k, const uint8_t* exps, int n_t, int64_t m, int nctas, int64_t* segments,
+                                 int64_t cap, double* info) {
+    if (n <= 0 || k <= 0 || n_t <= 0 || m <= 0 || nctas < 0 || !exps) {
+        set_error("ddb_moment_wave_describe: n, k, n_t, m must be positive and exps non-null");
+        return DDB_INVALID_ARG;
+    }
+    return moment_wave_describe(exps, n, k, n_t, m, nctas == 0 ? 148 : nctas, segments, cap, info);
 }
 
 int ddb_get_timings(const ddb_ctx* ctx, ddb_timings* out) {

@@ -30,6 +30,7 @@
 #include "mma_common.cuh"
 #include <algorithm>
 #include <array>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <unordered_map>
@@ -44,6 +45,9 @@ namespace {
 constexpr int kBT = 128;
 constexpr int kMaxMomentTerms = 8192;  // the analysis walks k (k + 1) / 2 entries on the host (1.4 s at k = 5151)
 constexpr double kHalfCost = 0.53;     // measured cost of a 64 x 128 patch relative to a whole 128 x 128 pair
+// every wave is one more pass over the X / Y stream and one more pipeline fill per CTA: a wave must save this
+// fraction of the perfectly split time to be worth it
+constexpr double kWavePenaltyFrac = 0.006;
 constexpr double kQuarterCost = 0.45;  // 32 x 128 patch (eight DMMAs per warp and k-step do not fill the pipe)
 using Key = std::array<uint16_t, kMaxFactors>;  // factor codes, ascending, leading zeros = the constant 1
 struct KeyHash {
@@ -360,38 +364,122 @@ int64_t moment_plan_describe(const uint8_t* exps, int n, int k, int n_t, int32_t
     return (int64_t)map.src.size();
 }
 
-// Lock-step waves: a wave runs `np` block pairs over `nr` sample ranges, CTA r * np + p taking pair p over
-// range r, so that the CTAs of a range walk the same samples at the same time.  Waves follow each other
-// inside one launch (a CTA's segment list is its share of every wave).
+// Lock-step waves.  A wave gives every one of its block pairs a number of equal sample ranges, one CTA per
+// (pair, range), at most `nctas` CTAs in all; the CTAs of a range walk the same samples at the same time, so a
+// wave reads the X / Y stream from HBM about once per cost class.  Waves follow each other inside one launch (a
+// CTA's segment list is its share of every wave).  Two kinds of wave, chosen by exhaustive recursion over "how
+// many of the most expensive pairs go first" (the pairs are sorted whole, half, quarter):
+//   * a homogeneous wave of np equal-cost pairs over nr = ceil(nctas / remaining) ranges each;
+//   * a FINAL wave of all remaining pairs, pair p over r_p = ceil(cost_p / T) ranges with the smallest T that
+//     fits -- CTAs of cheaper pairs get longer ranges so that all take about the time T.
+struct WavePlan {
+    std::vector<std::vector<GramSegment>> per_cta;
+    std::vector<int32_t> psb;  // pair -> first slot (slots of a pair are contiguous), npairs + 1
+    int nslots = 0, nwaves = 0;
+    double time = 0.0;  // pair streams per CTA (1.0 = one whole pair over all samples)
+};
+
+static void plan_waves(const std::vector<std::pair<int, int>>& pairs, int nfull, int nhalf, int64_t ns, int nctas,
+                       WavePlan* W) {
+    const int npairs = (int)pairs.size();
+    auto cls_of = [&](int p) { return p < nfull ? 0 : p < nfull + nhalf ? 1 : 2; };
+    auto cost_of = [&](int p) { return p < nfull ? 1.0 : p < nfull + nhalf ? kHalfCost : kQuarterCost; };
+    const int64_t max_r = std::max<int64_t>(1, ns);
+    double ideal = 0.0;
+    for (int p = 0; p < npairs; ++p) ideal += cost_of(p) / nctas;
+    const double kWavePenalty = kWavePenaltyFrac * ideal;
+    // final wave from `first`: ranges per pair and its time; false if even one range per pair does not fit
+    auto final_wave = [&](int first, std::vector<int>* ranges, double* T) {
+        if (npairs - first > nctas) return false;
+        auto count = [&](double t, std::vector<int>* out) {
+            int64_t total = 0;
+            for (int p = first; p < npairs; ++p) {
+                const int64_t r = std::min<int64_t>(max_r, std::max<int64_t>(1, (int64_t)std::ceil(cost_of(p) / t - 1e-12)));
+                if (out) (*out)[p - first] = (int)r;
+                total += r;
+            }
+            return total;
+        };
+        double lo = 0.0, hi = 1.0;  // count(hi = 1) = one range per pair: fits
+        for (int it = 0; it < 60; ++it) {
+            const double mid = 0.5 * (lo + hi);
+            if (count(mid, nullptr) <= nctas) hi = mid;
+            else lo = mid;
+        }
+        ranges->assign(npairs - first, 1);
+        count(hi, ranges);
+        *T = 0.0;
+        for (int p = first; p < npairs; ++p) *T = std::max(*T, cost_of(p) / (*ranges)[p - first]);
+        return true;
+    };
+    auto homogeneous = [&](int first, int* np, int* nr) {
+        const int c = cls_of(first);
+        const int end = c == 0 ? nfull : c == 1 ? nfull + nhalf : npairs;
+        const int remaining = end - first;
+        *nr = (int)std::max<int64_t>(1, std::min<int64_t>((nctas + remaining - 1) / remaining, max_r));
+        *np = std::min(remaining, nctas / *nr);
+    };
+    // best[first] = least time for the pairs [first, npairs); choice[first] = 1: final wave, 0: homogeneous step
+    std::vector<double> best(npairs + 1, 0.0);
+    std::vector<uint8_t> choice(npairs + 1, 0);
+    for (int first = npairs - 1; first >= 0; --first) {
+        int np, nr;
+        homogeneous(first, &np, &nr);
+        best[first] = cost_of(first) / nr + kWavePenalty + best[first + np];
+        choice[first] = 0;
+        std::vector<int> ranges;
+        double T;
+        if (final_wave(first, &ranges, &T) && T + kWavePenalty <= best[first] * (1.0 + 1e-9)) {  // ties: fewer waves
+            best[first] = T + kWavePenalty;
+            choice[first] = 1;
+        }
+    }
+    W->per_cta.assign(nctas, {});
+    W->psb.assign(npairs + 1, 0);
+    W->nslots = 0;
+    W->nwaves = 0;
+    auto emit = [&](int p, int nr, int* cta) {
+        W->psb[p] = W->nslots;
+        for (int r = 0; r < nr; ++r) {
+            GramSegment sg;
+            sg.bi = pairs[p].first;
+            sg.bj = pairs[p].second;
+            sg.slot = W->nslots++;
+            sg.pad = cls_of(p);  // 1: 64 x 128 patch, 2: 32 x 128 patch
+            sg.stage_begin = ns * r / nr;
+            sg.stage_end = ns * (r + 1) / nr;
+            W->per_cta[(*cta)++].push_back(sg);
+        }
+    };
+    int first = 0;
+    while (first < npairs) {
+        int cta = 0;
+        ++W->nwaves;
+        if (choice[first]) {
+            std::vector<int> ranges;
+            double T;
+            final_wave(first, &ranges, &T);
+            for (int p = first; p < npairs; ++p) emit(p, ranges[p - first], &cta);
+            first = npairs;
+        } else {
+            int np, nr;
+            homogeneous(first, &np, &nr);
+            for (int p = 0; p < np; ++p) emit(first + p, nr, &cta);
+            first += np;
+        }
+    }
+    W->psb[npairs] = W->nslots;
+    W->time = best[0] - kWavePenalty * W->nwaves;
+}
+
 static int build_wave_plan(ddb_ctx* ctx, MomentState* M) {
     const int nctas = ctx->sm_count;
     const int64_t ns = (ctx->m + kKS - 1) / kKS;
-    std::vector<std::vector<GramSegment>> per_cta(nctas);
-    std::vector<int32_t> psb(M->npairs + 1, 0);
-    int first = 0, nslots = 0;
-    while (first < M->npairs) {
-        // waves never mix whole, half and quarter pairs (the CTAs of a wave must take the same time)
-        const int cls = first < M->nfull ? 0 : first < M->nfull + M->nhalf ? 1 : 2;
-        const int remaining = (cls == 0 ? M->nfull : cls == 1 ? M->nfull + M->nhalf : M->npairs) - first;
-        int nr = (nctas + remaining - 1) / remaining;
-        nr = (int)std::max<int64_t>(1, std::min<int64_t>(nr, ns));
-        const int np = std::min(remaining, nctas / nr);
-        for (int p = 0; p < np; ++p) {
-            psb[first + p] = nslots;
-            for (int r = 0; r < nr; ++r) {
-                GramSegment sg;
-                sg.bi = M->pairs[first + p].first;
-                sg.bj = M->pairs[first + p].second;
-                sg.slot = nslots++;
-                sg.pad = cls;  // 1: 64 x 128 patch, 2: 32 x 128 patch
-                sg.stage_begin = ns * r / nr;
-                sg.stage_end = ns * (r + 1) / nr;
-                per_cta[r * np + p].push_back(sg);
-            }
-        }
-        first += np;
-    }
-    psb[M->npairs] = nslots;
+    WavePlan W;
+    plan_waves(M->pairs, M->nfull, M->nhalf, ns, nctas, &W);
+    const std::vector<std::vector<GramSegment>>& per_cta = W.per_cta;
+    const std::vector<int32_t>& psb = W.psb;
+    const int nslots = W.nslots;
     std::vector<GramSegment> segs;
     std::vector<int32_t> cta_seg_begin(nctas + 1, 0);
     for (int c = 0; c < nctas; ++c) {
@@ -464,6 +552,38 @@ int gram_moment_run(ddb_ctx* ctx, double* dPacked, bool* handled) {
     ctx->imp_k = 0;
     *handled = true;
     return DDB_OK;
+}
+
+// Host-only view of the wave plan for ddb_moment_wave_describe (api.cu): 7 int64 per segment.
+int64_t moment_wave_describe(const uint8_t* exps, int n, int k, int n_t, int64_t m, int nctas, int64_t* segments,
+                             int64_t cap, double* info) {
+    int D = 0;
+    for (int j = 0; j < k; ++j) {
+        int d = 0;
+        for (int i = 0; i < n; ++i) d += exps[(size_t)i + (size_t)n * j];
+        D = std::max(D, d);
+    }
+    MomentMap map;
+    analyse_library(exps, n, k, n_t, D, &map);
+    if (!map.worth) return 0;
+    const int nfull = (int)std::count(map.rows_used.begin(), map.rows_used.end(), (uint8_t)128);
+    const int nhalf = (int)std::count(map.rows_used.begin(), map.rows_used.end(), (uint8_t)64);
+    WavePlan W;
+    plan_waves(map.pairs, nfull, nhalf, (m + kKS - 1) / kKS, nctas, &W);
+    double cost = 0.0;
+    for (uint8_t h : map.rows_used) cost += h == 128 ? 1.0 : h == 64 ? kHalfCost : kQuarterCost;
+    if (info) info[0] = W.time, info[1] = cost / nctas, info[2] = W.nwaves, info[3] = W.nslots;
+    int64_t w = 0;
+    for (int c = 0; c < nctas; ++c)
+        for (const GramSegment& g : W.per_cta[c]) {
+            if (segments && w < cap) {
+                int64_t* o = segments + 7 * w;
+                o[0] = c, o[1] = g.bi, o[2] = g.bj, o[3] = g.slot, o[4] = g.stage_begin, o[5] = g.stage_end;
+                o[6] = g.pad == 0 ? 128 : g.pad == 1 ? 64 : 32;
+            }
+            ++w;
+        }
+    return w;
 }
 
 void moment_free(ddb_ctx* ctx) {

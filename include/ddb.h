@@ -315,6 +315,15 @@ int64_t ddb_gram_plan_describe(int kaug, int64_t m, int nctas, int64_t* segments
 int64_t ddb_moment_plan_describe(int n, int k, const uint8_t* exps, int n_t, int32_t* src, int64_t src_cap, uint16_t* factors,
                                  int64_t factors_cap, int32_t* pairs, int64_t pairs_cap, int64_t* info);
 
+/* Host-only: the work plan of the moment schedule for m local samples on nctas persistent CTAs (0 = 148): the block
+ * pairs of ddb_moment_plan_describe run in lock-step waves, every pair over a number of equal sample ranges.
+ * Writes up to cap segments as 7 int64 each {cta, first_block, second_block, slot, stage_begin, stage_end, rows}
+ * (a stage is 16 samples; segments are listed CTA by CTA in execution order) and returns their number, 0 if the
+ * library keeps the plain schedule.  info (4 doubles, may be NULL): {planned time in pair streams per CTA, the same
+ * for a perfect split = pair units / nctas, waves, slots}.  Needs no GPU. */
+int64_t ddb_moment_wave_describe(int n, int k, const uint8_t* exps, int n_t, int64_t m, int nctas, int64_t* segments,
+                                 int64_t cap, double* info);
+
 int ddb_get_timings(const ddb_ctx* ctx, ddb_timings* out);
 /* The context's CUDA stream (cudaStream_t) so a caller can order its own work after ours. */
 int ddb_get_stream(ddb_ctx* ctx, void** stream);

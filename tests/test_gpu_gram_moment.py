@@ -62,21 +62,33 @@ def test_moment_schedule_lorenz96_library(ctx, m):
     assert G[0, 0] == m  # constant x constant: a sum of ones is exact
 
 
-@pytest.mark.parametrize("n,deg,n_t,m,used", [(12, 3, 12, 9000, True), (20, 3, 20, 5000, True), (9, 4, 2, 5001, True),
-                                                (40, 2, 5, 7000, True), (7, 4, 2, 5001, True), (30, 2, 3, 7000, True),
-                                                (23, 2, 40, 4100, True), (20, 2, 100, 4100, True), (12, 2, 150, 4100, False)])
-def test_moment_schedule_other_libraries(ctx, n, deg, n_t, m, used):
+def _plan_says_used(ex, n_t):
+    """The host-only analysis (ddb_moment_plan_describe) plus the run-time size gate (more than two blocks)."""
+    from ddb200 import _lib
+
+    exf = np.asfortranarray(ex.astype(np.uint8))
+    info = np.zeros(8, dtype=np.int64)
+    _lib.load().ddb_moment_plan_describe(ex.shape[0], ex.shape[1], _lib.ptr(exf), n_t, None, 0, None, 0, None, 0, _lib.ptr(info))
+    return bool(info[0]) and ex.shape[1] + n_t > 256
+
+
+@pytest.mark.parametrize("n,deg,n_t,m", [(12, 3, 12, 9000), (20, 3, 20, 5000), (9, 4, 2, 5001), (40, 2, 5, 7000), (7, 4, 2, 5001),
+                                           (30, 2, 3, 7000), (23, 2, 40, 4100), (20, 2, 100, 4100), (12, 2, 150, 4100)])
+def test_moment_schedule_other_libraries(ctx, n, deg, n_t, m):
     """Higher degrees (P and Q are degree-3 / degree-4 monomials), n_t != n, a short target block; libraries of a
-    few blocks where the staircase saves nothing keep the plain schedule (`used` False)."""
+    few blocks where the staircase saves nothing keep the plain schedule, exactly when the host-only plan says so."""
     rng = np.random.default_rng(n * 10 + deg)
     X = 0.7 * rng.standard_normal((n, m))
     Y = rng.standard_normal((n_t, m))
-    _res, t1, t0 = _check(ctx, oracle.polynomial_exponents(n, deg), X, Y, tol=2e-13)
+    ex = oracle.polynomial_exponents(n, deg)
+    _res, t1, t0 = _check(ctx, ex, X, Y, tol=2e-13)
     assert t0["gram_schedule"] != 2
-    if used is not None:
-        assert (t1["gram_schedule"] == 2) == used
-        if used:
-            assert t1["gram_dmma_flops"] < t0["gram_dmma_flops"]
+    used = _plan_says_used(ex, n_t)
+    assert (t1["gram_schedule"] == 2) == used
+    if used:
+        assert t1["gram_dmma_flops"] < t0["gram_dmma_flops"]
+    if (n, deg) in ((20, 3), (40, 2)):
+        assert used  # these clearly pay off
 
 
 def test_moment_schedule_incomplete_library(ctx):

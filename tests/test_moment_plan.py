@@ -129,3 +129,54 @@ def test_moment_plan_of_mixed_degree_and_incomplete_libraries():
 def test_moment_plan_steps_aside():
     """Libraries where the staircase saves nothing keep the plain schedule."""
     assert _moment_plan(oracle.polynomial_exponents(12, 2), 150) is None  # many targets: 4 block pairs against 1 + 2 diagonal
+
+
+def _wave_plan(ex, n_t, m, nctas=148):
+    lib = _lib.load()
+    n, k = ex.shape
+    exf = np.asfortranarray(ex.astype(np.uint8))
+    info = np.zeros(4, dtype=np.float64)
+    cnt = lib.ddb_moment_wave_describe(n, k, _lib.ptr(exf), n_t, m, nctas, None, 0, _lib.ptr(info))
+    assert cnt > 0
+    seg = np.zeros((cnt, 7), dtype=np.int64)
+    assert lib.ddb_moment_wave_describe(n, k, _lib.ptr(exf), n_t, m, nctas, _lib.ptr(seg), cnt, None) == cnt
+    return seg, info
+
+
+@pytest.mark.parametrize("n,deg,n_t,m,nctas", [(64, 2, 64, 10_000_000, 148), (64, 2, 64, 1_250_000, 148), (64, 2, 64, 4097, 148),
+                                                (64, 2, 64, 33, 148), (20, 3, 20, 200_000, 148), (100, 2, 100, 1_000_000, 148),
+                                                (40, 2, 5, 70_001, 132), (12, 3, 12, 9000, 148)])
+def test_moment_wave_plan_covers_every_pair_and_stage_once(n, deg, n_t, m, nctas):
+    """Host logic of the lock-step waves: every block pair of the moment plan is covered over all stages exactly
+    once by contiguous ranges, one partial-tile slot per segment with the slots of a pair contiguous and in stage
+    order (fixed summation order), at most nctas CTAs per wave, and the planned time is within 6 % of a perfect
+    split when there is enough work per CTA."""
+    ex = oracle.polynomial_exponents(n, deg)
+    plan = _moment_plan(ex, n_t)
+    seg, info = _wave_plan(ex, n_t, m, nctas)
+    nstages = -(-m // 16)
+    rows_of = {(int(a), int(b)): int(r) for a, b, r in plan["pairs"]}
+    cover = {}
+    for cta, bi, bj, slot, b, e, rows in seg.tolist():
+        assert 0 <= cta < nctas and 0 <= b <= e <= nstages
+        assert rows_of[(bi, bj)] == rows
+        cover.setdefault((bi, bj), []).append((b, e, slot))
+    assert set(cover) == set(rows_of)
+    for ranges in cover.values():
+        ranges.sort()
+        assert ranges[0][0] == 0 and ranges[-1][1] == nstages
+        assert all(ranges[i][1] == ranges[i + 1][0] for i in range(len(ranges) - 1))
+        assert [r[2] for r in ranges] == list(range(ranges[0][2], ranges[0][2] + len(ranges)))
+    assert sorted(seg[:, 3].tolist()) == list(range(seg.shape[0])) and info[3] == seg.shape[0]
+    # every CTA takes part in a wave at most once: its k-th segment belongs to wave k or later
+    per_cta = np.bincount(seg[:, 0], minlength=nctas)
+    assert per_cta.max() <= info[2]
+    if nstages >= 64 * nctas:
+        assert info[1] <= info[0] <= 1.06 * info[1]
+
+
+def test_moment_wave_plan_lorenz96_has_few_waves():
+    """C3 at full size: two waves (49 whole pairs x 3 ranges, then everything else in one mixed wave), so the
+    X / Y stream is read from HBM a handful of times instead of once per cost class and leftover."""
+    seg, info = _wave_plan(oracle.polynomial_exponents(64, 2), 64, 10_000_000)
+    assert info[2] <= 3 and info[0] <= 0.49
