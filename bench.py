@@ -31,10 +31,11 @@ CUBLAS_DGEMM_TFLOPS = 35.9
 # profiles/gram_traffic_r1g_c3_1e6.csv): gram_ring_kernel 1041 B (the algorithmic 1024 B + ring spill) and the
 # diagonal-pair pass of gram_kernel 1886 B (its 9 sample ranges x 16 pairs share tiles through L2)
 C3_RING_DRAM_BYTES_PER_SAMPLE = (1041148928 + 1886253824) / 1e6
-# moment schedule (default at C3): gram_kernel over 78 block pairs in two lock-step waves (49 whole pairs x 3 sample
-# ranges, then 13 whole x 7, 6 half x 4 and 10 quarter x 3 ranges: about four passes over the X / Y stream):
-# dram__bytes_read.sum 4.4276 GB + dram__bytes_write.sum 0.0321 GB at 1e6 samples (profiles/gram_traffic_r1n_c3_1e6.csv)
-C3_MOMENT_DRAM_BYTES_PER_SAMPLE = (4427609856 + 32102912) / 1e6
+# moment schedule (default at C3): gram_kernel over 78 block pairs in four lock-step waves (37 whole pairs x 4 sample
+# ranges, 21 x 7, 2 x 74, then 2 whole x 15, 6 half x 8 and 10 quarter x 7 ranges: about six passes over the X / Y
+# stream): dram__bytes_read.sum 6.9288 GB + dram__bytes_write.sum 0.0696 GB at 1e6 samples
+# (profiles/gram_traffic_r1o_c3_1e6.csv; a two-wave plan reads 4.43 GB and is 2.2 % slower, profiles/gram_traffic_r1n_c3_1e6.csv)
+C3_MOMENT_DRAM_BYTES_PER_SAMPLE = (6928822016 + 69605632) / 1e6
 
 WORKLOADS = {
     "c3": dict(system=1, n=64, degree=2, m=10_000_000, name="Lorenz-96 n=64, degree-2 library (2145 terms), 1e7 samples, 41-lambda STLSQ"),
@@ -435,7 +436,7 @@ def main():
     if args.workload == "c3" and sched == 2:
         traffic = C3_MOMENT_DRAM_BYTES_PER_SAMPLE * m_local
         traffic_source = ("dram__bytes_read.sum + dram__bytes_write.sum of gram_kernel at 1e6 samples, ncu "
-                          "(profiles/gram_traffic_r1n_c3_1e6.csv), scaled by samples per launch")
+                          "(profiles/gram_traffic_r1o_c3_1e6.csv), scaled by samples per launch")
     elif args.workload == "c3" and sched == 1:
         traffic = C3_RING_DRAM_BYTES_PER_SAMPLE * m_local
         traffic_source = ("dram__bytes_read.sum of gram_ring_kernel (1.041 GB) + gram_kernel diagonal-pair pass (1.886 GB) per 1e6 "

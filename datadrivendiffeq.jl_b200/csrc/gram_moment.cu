@@ -367,9 +367,9 @@ int64_t moment_plan_describe(const uint8_t* exps, int n, int k, int n_t, int32_t
 // Lock-step waves.  A wave gives every one of its block pairs a number of equal sample ranges, one CTA per
 // (pair, range), at most `nctas` CTAs in all; the CTAs of a range walk the same samples at the same time, so a
 // wave reads the X / Y stream from HBM about once per cost class.  Waves follow each other inside one launch (a
-// CTA's segment list is its share of every wave).  Two kinds of wave, chosen by exhaustive recursion over "how
+// CTA's segment list is its share of every wave).  Two kinds of wave, chosen by dynamic programming over "how
 // many of the most expensive pairs go first" (the pairs are sorted whole, half, quarter):
-//   * a homogeneous wave of np equal-cost pairs over nr = ceil(nctas / remaining) ranges each;
+//   * a homogeneous wave of np = min(rest of the class, nctas / nr) equal-cost pairs over nr ranges each, any nr;
 //   * a FINAL wave of all remaining pairs, pair p over r_p = ceil(cost_p / T) ranges with the smallest T that
 //     fits -- CTAs of cheaper pairs get longer ranges so that all take about the time T.
 struct WavePlan {
@@ -412,26 +412,33 @@ static void plan_waves(const std::vector<std::pair<int, int>>& pairs, int nfull,
         for (int p = first; p < npairs; ++p) *T = std::max(*T, cost_of(p) / (*ranges)[p - first]);
         return true;
     };
-    auto homogeneous = [&](int first, int* np, int* nr) {
+    // homogeneous wave from `first` with nr ranges per pair: how many pairs it takes (0 = not possible)
+    auto class_end = [&](int first) {
         const int c = cls_of(first);
-        const int end = c == 0 ? nfull : c == 1 ? nfull + nhalf : npairs;
-        const int remaining = end - first;
-        *nr = (int)std::max<int64_t>(1, std::min<int64_t>((nctas + remaining - 1) / remaining, max_r));
-        *np = std::min(remaining, nctas / *nr);
+        return c == 0 ? nfull : c == 1 ? nfull + nhalf : npairs;
     };
-    // best[first] = least time for the pairs [first, npairs); choice[first] = 1: final wave, 0: homogeneous step
+    auto homogeneous = [&](int first, int nr) { return std::min(class_end(first) - first, nctas / nr); };
+    // best[first] = least time for the pairs [first, npairs) (every wave also pays kWavePenalty);
+    // choice[first] = 0: final mixed wave, nr > 0: homogeneous wave with nr ranges per pair
     std::vector<double> best(npairs + 1, 0.0);
-    std::vector<uint8_t> choice(npairs + 1, 0);
+    std::vector<int> choice(npairs + 1, 0);
+    const int nr_max = (int)std::min<int64_t>(nctas, max_r);
     for (int first = npairs - 1; first >= 0; --first) {
-        int np, nr;
-        homogeneous(first, &np, &nr);
-        best[first] = cost_of(first) / nr + kWavePenalty + best[first + np];
-        choice[first] = 0;
+        best[first] = 1e300;
+        for (int nr = 1; nr <= nr_max; ++nr) {
+            const int np = homogeneous(first, nr);
+            if (np < 1) break;
+            const double t = cost_of(first) / nr + kWavePenalty + best[first + np];
+            if (t < best[first] * (1.0 - 1e-12)) {
+                best[first] = t;
+                choice[first] = nr;
+            }
+        }
         std::vector<int> ranges;
         double T;
         if (final_wave(first, &ranges, &T) && T + kWavePenalty <= best[first] * (1.0 + 1e-9)) {  // ties: fewer waves
             best[first] = T + kWavePenalty;
-            choice[first] = 1;
+            choice[first] = 0;
         }
     }
     W->per_cta.assign(nctas, {});
@@ -455,15 +462,14 @@ static void plan_waves(const std::vector<std::pair<int, int>>& pairs, int nfull,
     while (first < npairs) {
         int cta = 0;
         ++W->nwaves;
-        if (choice[first]) {
+        if (choice[first] == 0) {
             std::vector<int> ranges;
             double T;
             final_wave(first, &ranges, &T);
             for (int p = first; p < npairs; ++p) emit(p, ranges[p - first], &cta);
             first = npairs;
         } else {
-            int np, nr;
-            homogeneous(first, &np, &nr);
+            const int nr = choice[first], np = homogeneous(first, nr);
             for (int p = 0; p < np; ++p) emit(first + p, nr, &cta);
             first += np;
         }

@@ -149,7 +149,7 @@ def _wave_plan(ex, n_t, m, nctas=148):
 def test_moment_wave_plan_covers_every_pair_and_stage_once(n, deg, n_t, m, nctas):
     """Host logic of the lock-step waves: every block pair of the moment plan is covered over all stages exactly
     once by contiguous ranges, one partial-tile slot per segment with the slots of a pair contiguous and in stage
-    order (fixed summation order), at most nctas CTAs per wave, and the planned time is within 6 % of a perfect
+    order (fixed summation order), at most nctas CTAs per wave, and the planned time is within 2 % of a perfect
     split when there is enough work per CTA."""
     ex = oracle.polynomial_exponents(n, deg)
     plan = _moment_plan(ex, n_t)
@@ -172,11 +172,11 @@ def test_moment_wave_plan_covers_every_pair_and_stage_once(n, deg, n_t, m, nctas
     per_cta = np.bincount(seg[:, 0], minlength=nctas)
     assert per_cta.max() <= info[2]
     if nstages >= 64 * nctas:
-        assert info[1] <= info[0] <= 1.06 * info[1]
+        assert info[1] <= info[0] <= 1.02 * info[1]
 
 
-def test_moment_wave_plan_lorenz96_has_few_waves():
-    """C3 at full size: two waves (49 whole pairs x 3 ranges, then everything else in one mixed wave), so the
-    X / Y stream is read from HBM a handful of times instead of once per cost class and leftover."""
+def test_moment_wave_plan_lorenz96_is_within_one_percent_of_a_perfect_split():
+    """C3 at full size: four waves (37 whole pairs x 4 ranges, 21 x 7, 2 x 74, then the last 2 whole, 6 half and
+    10 quarter pairs in one mixed wave): 0.473 pair streams per CTA against 69.7 / 148 = 0.471."""
     seg, info = _wave_plan(oracle.polynomial_exponents(64, 2), 64, 10_000_000)
-    assert info[2] <= 3 and info[0] <= 0.49
+    assert info[2] <= 4 and info[0] <= 1.01 * info[1]
