@@ -180,3 +180,38 @@ def test_moment_wave_plan_lorenz96_is_within_one_percent_of_a_perfect_split():
     10 quarter pairs in one mixed wave): 0.473 pair streams per CTA against 69.7 / 148 = 0.471."""
     seg, info = _wave_plan(oracle.polynomial_exponents(64, 2), 64, 10_000_000)
     assert info[2] <= 4 and info[0] <= 1.01 * info[1]
+
+
+def test_moment_plan_random_libraries():
+    """Random sparse libraries (duplicate terms, missing constants, mixed degrees, a single term, all-constant
+    columns): whenever the analysis accepts a library its gather map must be right for every packed entry."""
+    rng = np.random.default_rng(0)
+    libs = []
+    for _ in range(25):
+        n, k, n_t, maxdeg = int(rng.integers(1, 12)), int(rng.integers(1, 700)), int(rng.integers(1, 40)), int(rng.integers(1, 6))
+        ex = np.zeros((n, k), dtype=np.uint8)
+        for j in range(k):
+            for _f in range(int(rng.integers(0, maxdeg + 1))):
+                ex[rng.integers(0, n), j] += 1
+        libs.append((ex, n_t))
+    libs += [(np.zeros((3, 300), dtype=np.uint8), 5), (np.ones((2, 400), dtype=np.uint8), 2), (np.zeros((1, 1), dtype=np.uint8), 1)]
+    used = 0
+    for ex, n_t in libs:
+        n, k = ex.shape
+        plan = _moment_plan(ex, n_t)
+        if plan is None:
+            continue
+        used += 1
+        src, pairs = plan["src"], plan["pairs"]
+        vex = _virtual_exponents(plan["tab"], n, n_t)
+        pair, off = src >> 14, src & 16383
+        row = pairs[pair, 0] * 128 + off // 128
+        col = pairs[pair, 1] * 128 + off % 128
+        full = np.concatenate([ex.T.astype(np.int64), np.zeros((k, n_t), dtype=np.int64)], axis=1)
+        tgt = np.concatenate([np.zeros((n_t, n), dtype=np.int64), np.eye(n_t, dtype=np.int64)], axis=1)
+        w = rng.integers(1, 1 << 56, size=n + n_t, dtype=np.int64)
+        hv, hf, ht = vex @ w, full @ w, tgt @ w
+        want = np.concatenate([(hf[None, :] + hf[:, None]).ravel(), (ht[:, None] + hf[None, :]).ravel(), 2 * ht])
+        np.testing.assert_array_equal(hv[row] + hv[col], want)
+        assert ((off // 128) < pairs[pair, 2]).all()
+    assert used >= 15
