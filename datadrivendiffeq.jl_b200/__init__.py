@@ -5,7 +5,7 @@
 the host-side mirror of the reference's plug-in interface.  There is no CPU fallback.
 """
 from . import _lib  # noqa: F401
-from .backend import Context, SweepOutput  # noqa: F401
+from .backend import Context, Group, SweepOutput  # noqa: F401
 from .api import (  # noqa: F401
     ADMM,
     B200Sparse,

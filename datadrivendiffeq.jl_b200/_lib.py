@@ -65,7 +65,9 @@ class Timings(C.Structure):
         ("candidates", C.c_int32),
         ("gram_dmma_flops", C.c_double),
         ("gram_schedule", C.c_int32),
-        ("reserved", C.c_int32),
+        ("allreduce_calls", C.c_int32),
+        ("allreduce_ms", C.c_double),
+        ("allreduce_bytes", C.c_double),
     ]
 
     def as_dict(self):
@@ -107,8 +109,30 @@ PROTOTYPES = {
     "ddb_select": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "ddb_solve_sparse": (
         C.c_int,
-        [_P, _P, _P, C.c_int, C.c_int64, C.POINTER(SweepParams), _P, C.c_int, _P, _P, _P, _P, _P, _P],
+        [_P, _P, _P, C.c_int, C.c_int64, C.POINTER(SweepParams), _P, C.c_int, _P, _P, _P, _P, _P, _P, _P],
     ),
+    "ddb_comm_unique_id": (C.c_int, [_P]),
+    "ddb_comm_init_rank": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "ddb_comm_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "ddb_allreduce_gram": (C.c_int, [_P]),
+    "ddb_allreduce_rss": (C.c_int, [_P]),
+    "ddb_allreduce_sum": (C.c_int, [_P, _P, C.c_int64]),
+    "ddb_solve_sparse_sharded": (
+        C.c_int,
+        [_P, _P, _P, C.c_int, C.c_int64, C.c_int64, C.POINTER(SweepParams), _P, C.c_int, _P, _P, _P, _P, _P, _P, _P],
+    ),
+    "ddb_group_create": (C.c_int, [C.c_int, _P, C.POINTER(_P)]),
+    "ddb_group_destroy": (C.c_int, [_P]),
+    "ddb_group_size": (C.c_int, [_P]),
+    "ddb_group_ctx": (_P, [_P, C.c_int]),
+    "ddb_group_set_library_monomial": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "ddb_group_set_features": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P]),
+    "ddb_group_shard": (C.c_int, [_P, C.c_int64, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "ddb_group_solve_sparse": (
+        C.c_int,
+        [_P, _P, _P, C.c_int, C.c_int64, C.POINTER(SweepParams), _P, C.c_int, _P, _P, _P, _P, _P, _P, _P],
+    ),
+    "ddb_group_get_timings": (C.c_int, [_P, C.POINTER(Timings)]),
     "ddb_dmd_gram": (C.c_int, [_P, _P, _P, C.c_int, C.c_int64, _P, _P]),
     "ddb_dmd_operator": (C.c_int, [_P, _P, _P, C.c_int, _P]),
     "ddb_dmd_solve": (C.c_int, [_P, _P, C.c_int, C.c_int64, _P, _P, _P]),

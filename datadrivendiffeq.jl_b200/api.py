@@ -386,22 +386,37 @@ class ImplicitOptimizer:
 
 class B200Sparse:
     """The drop-in algorithm type: wraps one of the reference's sparse regression algorithms and runs
-    it on B200 GPUs.  ``group``: an initialised ``torch.distributed`` process group (one process per
-    GPU); every rank passes ITS row shard of the samples to ``solve`` and receives the full result.
+    it on B200 GPUs.  Three ways to use several GPUs, all ending in the same two NCCL all-reduces inside the
+    library: ``ngpus = N`` -- ONE process drives N GPUs of the node (``ddb_group``: the samples are cut into N
+    ranges inside the library; this is what the Julia glue's ``B200Sparse(inner; ngpus = N)`` does);
+    ``group`` -- an initialised ``torch.distributed`` process group with one process per GPU, every rank
+    passing ITS row shard of the samples to ``solve`` and receiving the full result.
     """
 
-    def __init__(self, inner, device: int = 0, group=None):
+    def __init__(self, inner, device: int = 0, group=None, ngpus: int = 1, devices=None):
         if not isinstance(inner, (STLSQ, ADMM, SR3, ImplicitOptimizer)):
             raise ValueError("B200Sparse wraps STLSQ, ADMM, SR3 or an ImplicitOptimizer of one of them")
+        if ngpus < 1 or (ngpus > 1 and group is not None):
+            raise ValueError("B200Sparse: ngpus >= 1, and either ngpus > 1 (one process) or group (one process per GPU)")
         self.inner = inner
         self.device = int(device)
         self.group = group
+        self.ngpus = int(ngpus)
+        self.devices = devices
         self._ctx: Optional[Context] = None
+        self._grp = None
 
     def context(self) -> Context:
         if self._ctx is None:
             self._ctx = Context(self.device)
         return self._ctx
+
+    def gpu_group(self):
+        if self._grp is None:
+            from .backend import Group
+
+            self._grp = Group(self.ngpus, self.devices)
+        return self._grp
 
 
 # ----------------------------------------------------------------------------------------------
@@ -732,6 +747,15 @@ def solve(prob: DataDrivenProblem, basis: Basis, alg: B200Sparse, options: Optio
         raise ValueError("a Basis with implicit variables needs an ImplicitOptimizer (src/basis/type.jl:15)")
     if _needs_processing(options):
         return _solve_processed(prob, basis, alg, options, X, Y, paths)
+    if alg.ngpus > 1:
+        # one process, N GPUs: ddb_group_solve_sparse shards the host buffers itself
+        if paths:
+            raise ValueError("B200Sparse: paths = True is not available with ngpus > 1")
+        grp = alg.gpu_group()
+        grp.set_features(basis.n_raw, basis.features)
+        grp.set_library(basis.exponents)
+        out = grp.solve_sparse(X, Y, _params_for(grp, alg.inner, options), alg.inner.thresholds)
+        return _finish_solution(basis, options, out, Y.shape[0], X.shape[1], Y.size, grp.timings(), None)
     ctx = alg.context()
     ctx.set_features(basis.n_raw, basis.features)
     ctx.set_library(basis.exponents)
@@ -751,6 +775,11 @@ def solve(prob: DataDrivenProblem, basis: Basis, alg: B200Sparse, options: Optio
         from . import dist
 
         out, m_total = dist.solve_sharded(ctx, X, Y, prm, lambdas, alg.group, paths=paths)
+    nobs = int(Y.size if alg.group is None else Y.shape[0] * m_total)
+    return _finish_solution(basis, options, out, Y.shape[0], m_total, nobs, ctx.timings(), out if paths else None)
+
+
+def _finish_solution(basis, options, out, n_t, m_total, nobs, timings, paths_out):
     C = out.coefficients
     # __sparse_regression (commonsolve.jl:37-55): trainerror = sum(abs2, Y - C*Theta) = sum of the selected rss
     res = SparseRegressionResult(
@@ -769,8 +798,8 @@ def solve(prob: DataDrivenProblem, basis: Basis, alg: B200Sparse, options: Optio
         results=[res],
         rss=res.trainerror,
         dof=int(np.sum(Cr != 0.0)),
-        nobs=int(Y.size if alg.group is None else Y.shape[0] * m_total),
+        nobs=nobs,
         retcode=res.retcode,
-        timings=ctx.timings(),
-        paths=out if paths else None,
+        timings=timings,
+        paths=paths_out,
     )

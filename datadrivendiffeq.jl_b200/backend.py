@@ -279,12 +279,69 @@ class Context:
         iters = np.zeros(n_t, dtype=np.int32)
         rss = np.zeros(n_t)
         dof = np.zeros(n_t, dtype=np.int32)
+        flags = np.zeros(n_t, dtype=np.int32)
         _lib.check(
             self._lib.ddb_solve_sparse(self._ctx, _lib.ptr(X), _lib.ptr(Y), n_t, m, C.byref(params), _lib.ptr(lam_in),
                                        lam_in.size, _lib.ptr(coef), _lib.ptr(lam), _lib.ptr(iters), _lib.ptr(rss),
-                                       _lib.ptr(dof), None)
+                                       _lib.ptr(dof), None, _lib.ptr(flags))
         )
-        return SweepOutput(np.ascontiguousarray(coef), lam, iters, rss, dof, np.zeros(n_t, dtype=np.int32))
+        return SweepOutput(np.ascontiguousarray(coef), lam, iters, rss, dof, flags)
+
+    # -- multi-GPU: communicator inside the library (comm.cu) -------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """``ddb_comm_unique_id``: 128 bytes created on ONE rank and carried to the others by the host program."""
+        buf = (C.c_char * 128)()
+        _lib.check(_lib.load().ddb_comm_unique_id(buf))
+        return bytes(buf.raw)
+
+    def comm_init_rank(self, nranks: int, rank: int, unique_id: bytes):
+        """``ddb_comm_init_rank``: attach an NCCL communicator (one process or thread per GPU)."""
+        assert len(unique_id) == 128
+        buf = (C.c_char * 128).from_buffer_copy(unique_id)
+        _lib.check(self._lib.ddb_comm_init_rank(self._ctx, int(nranks), int(rank), buf))
+
+    def comm_info(self):
+        """``(nranks, rank, nccl_version)`` of the context's communicator (``(1, 0, v)`` without one)."""
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        _lib.check(self._lib.ddb_comm_info(self._ctx, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def allreduce_gram(self):
+        _lib.check(self._lib.ddb_allreduce_gram(self._ctx))
+
+    def allreduce_rss(self):
+        _lib.check(self._lib.ddb_allreduce_rss(self._ctx))
+
+    def allreduce_sum(self, d_ptr: int, count: int):
+        _lib.check(self._lib.ddb_allreduce_sum(self._ctx, C.c_void_p(d_ptr), int(count)))
+
+    def solve_sparse_sharded(self, X, Y, params: _lib.SweepParams, lambdas: Sequence[float], m_total: int,
+                             x_ptr: Optional[int] = None, y_ptr: Optional[int] = None, n_t: Optional[int] = None,
+                             m_local: Optional[int] = None) -> SweepOutput:
+        """``ddb_solve_sparse_sharded``: this rank's host shard in, the full result out (collective).  Either
+        NumPy arrays ``X``, ``Y`` or raw host pointers (``x_ptr``, ``y_ptr``, ``n_t``, ``m_local``)."""
+        if x_ptr is None:
+            X, Y = _f(X), _f(Y)
+            n_t, m_local = Y.shape
+            xp, yp = _lib.ptr(X), _lib.ptr(Y)
+        else:
+            xp, yp = C.c_void_p(x_ptr), C.c_void_p(y_ptr)
+        lam_in = np.ascontiguousarray(lambdas, dtype=np.float64)
+        self.n_t, self.m, self._L = int(n_t), int(m_local), lam_in.size
+        self._imp_k = 0
+        coef = np.zeros((n_t, self.k), order="F")
+        lam = np.zeros(n_t)
+        iters = np.zeros(n_t, dtype=np.int32)
+        rss = np.zeros(n_t)
+        dof = np.zeros(n_t, dtype=np.int32)
+        flags = np.zeros(n_t, dtype=np.int32)
+        _lib.check(
+            self._lib.ddb_solve_sparse_sharded(self._ctx, xp, yp, int(n_t), int(m_local), int(m_total), C.byref(params),
+                                               _lib.ptr(lam_in), lam_in.size, _lib.ptr(coef), _lib.ptr(lam), _lib.ptr(iters),
+                                               _lib.ptr(rss), _lib.ptr(dof), None, _lib.ptr(flags))
+        )
+        return SweepOutput(np.ascontiguousarray(coef), lam, iters, rss, dof, flags)
 
     # -- DataDrivenDMD Gram path ------------------------------------------------------------
     def dmd_gram(self, dX: int, dY: int, n: int, m: int, dP: int, dQ: int):
@@ -319,3 +376,82 @@ class Context:
 
     def synchronize(self):
         _lib.check(self._lib.ddb_synchronize(self._ctx))
+
+
+class Group:
+    """One process driving N GPUs: ``ddb_group`` = N contexts + ``ncclCommInitAll``.  ``solve_sparse`` is the
+    N-GPU form of ``Context.solve_sparse`` (host buffers in, host buffers out; the samples are cut into N
+    contiguous ranges inside the library)."""
+
+    def __init__(self, ngpus: int, devices: Optional[Sequence[int]] = None):
+        self._lib = _lib.load()
+        self._g = C.c_void_p()
+        dev = None if devices is None else np.ascontiguousarray(devices, dtype=np.int32)
+        _lib.check(self._lib.ddb_group_create(int(ngpus), _lib.ptr(dev), C.byref(self._g)))
+        self.ngpus = int(ngpus)
+        self.n = self.k = 0
+
+    def close(self):
+        if getattr(self, "_g", None) and self._g.value:
+            self._lib.ddb_group_destroy(self._g)
+            self._g = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def set_library(self, exponents: np.ndarray):
+        e = np.asfortranarray(exponents, dtype=np.uint8)
+        self.n, self.k = e.shape
+        _lib.check(self._lib.ddb_group_set_library_monomial(self._g, self.n, self.k, _lib.ptr(e)))
+
+    def set_features(self, n_raw: int, features: Optional[Sequence] = None):
+        if not features:
+            _lib.check(self._lib.ddb_group_set_features(self._g, 0, 0, None, None, None))
+            return
+        kind = np.ascontiguousarray([f[0] for f in features], dtype=np.int32)
+        src = np.ascontiguousarray([f[1] for f in features], dtype=np.int32)
+        coef = np.ascontiguousarray([f[2] for f in features], dtype=np.float64)
+        _lib.check(self._lib.ddb_group_set_features(self._g, int(n_raw), kind.size, _lib.ptr(kind), _lib.ptr(src), _lib.ptr(coef)))
+
+    def shard(self, m: int, rank: int):
+        a, b = C.c_int64(), C.c_int64()
+        _lib.check(self._lib.ddb_group_shard(self._g, int(m), int(rank), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    make_params = staticmethod(Context.make_params)
+
+    def solve_sparse(self, X, Y, params: _lib.SweepParams, lambdas: Sequence[float], x_ptr: Optional[int] = None,
+                     y_ptr: Optional[int] = None, n_t: Optional[int] = None, m: Optional[int] = None) -> SweepOutput:
+        if x_ptr is None:
+            X, Y = _f(X), _f(Y)
+            n_t, m = Y.shape
+            xp, yp = _lib.ptr(X), _lib.ptr(Y)
+        else:
+            xp, yp = C.c_void_p(x_ptr), C.c_void_p(y_ptr)
+        lam_in = np.ascontiguousarray(lambdas, dtype=np.float64)
+        coef = np.zeros((n_t, self.k), order="F")
+        lam = np.zeros(n_t)
+        iters = np.zeros(n_t, dtype=np.int32)
+        rss = np.zeros(n_t)
+        dof = np.zeros(n_t, dtype=np.int32)
+        flags = np.zeros(n_t, dtype=np.int32)
+        _lib.check(
+            self._lib.ddb_group_solve_sparse(self._g, xp, yp, int(n_t), int(m), C.byref(params), _lib.ptr(lam_in), lam_in.size,
+                                             _lib.ptr(coef), _lib.ptr(lam), _lib.ptr(iters), _lib.ptr(rss), _lib.ptr(dof), None,
+                                             _lib.ptr(flags))
+        )
+        return SweepOutput(np.ascontiguousarray(coef), lam, iters, rss, dof, flags)
+
+    def timings(self) -> dict:
+        t = _lib.Timings()
+        _lib.check(self._lib.ddb_group_get_timings(self._g, C.byref(t)))
+        return t.as_dict()

@@ -52,6 +52,8 @@ int64_t moment_wave_describe(const uint8_t* exps, int n, int k, int n_t, int64_t
 int64_t moment_plan_describe(const uint8_t* exps, int n, int k, int n_t, int32_t* src, int64_t src_cap, uint16_t* tab,
                              int64_t tab_cap, int32_t* pairs, int64_t pairs_cap, int64_t* info);
 void trsm_free(ddb_ctx* ctx);
+void comm_free(ddb_ctx* ctx);
+const char* last_error_message() { return g_error; }
 
 }  // namespace ddb
 
@@ -69,7 +71,7 @@ using namespace ddb;
 extern "C" {
 
 const char* ddb_last_error(void) { return g_error; }
-const char* ddb_version(void) { return "ddb200 0.1 (sm_100a)"; }
+const char* ddb_version(void) { return "ddb200 0.2 (sm_100a)"; }
 
 int ddb_ctx_create(int device, ddb_ctx** out) {
     if (!out) {
@@ -101,6 +103,7 @@ int ddb_ctx_create(int device, ddb_ctx** out) {
     ctx->sm_count = prop.multiProcessorCount;
     DDB_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     for (auto& ev : ctx->ev) DDB_CUDA_TRY(cudaEventCreate(&ev));
+    for (auto& ev : ctx->ev_ar) DDB_CUDA_TRY(cudaEventCreate(&ev));
     *out = ctx;
     return DDB_OK;
 }
@@ -109,6 +112,7 @@ int ddb_ctx_destroy(ddb_ctx* ctx) {
     if (!ctx) return DDB_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    comm_free(ctx);
     sweep_free(ctx);
     dmd_free(ctx);
     ring_free(ctx);
@@ -129,7 +133,11 @@ int ddb_ctx_destroy(ddb_ctx* ctx) {
     ctx->d_resid_partials.release();
     ctx->d_feat.release();
     ctx->raw_X.release();
+    ctx->view_X.release();
+    ctx->view_Y.release();
     for (auto& ev : ctx->ev)
+        if (ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->ev_ar)
         if (ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->chunk_ev)
         if (ev) cudaEventDestroy(ev);
@@ -409,6 +417,18 @@ int ddb_set_sample_range(ddb_ctx* ctx, int64_t first, int64_t last) {
     ctx->dX = ctx->full_X + first * ctx->n;
     ctx->dY = ctx->full_Y + first * ctx->n_t;
     ctx->m = last - first;
+    // The Gram kernels fetch sample tiles with 16-byte bulk copies: a view that starts on an odd double (odd
+    // first with an odd number of states or targets, e.g. Lorenz with a batch size of 125) is staged once into an
+    // aligned buffer of its own -- the reference accepts any batch size and split.
+    if ((((uintptr_t)ctx->dX) & 15) || (((uintptr_t)ctx->dY) & 15)) {
+        const size_t xb = (size_t)ctx->n * ctx->m * sizeof(double), yb = (size_t)ctx->n_t * ctx->m * sizeof(double);
+        DDB_TRY(ctx->view_X.reserve(xb));
+        DDB_TRY(ctx->view_Y.reserve(yb));
+        DDB_CUDA_TRY(cudaMemcpyAsync(ctx->view_X.p, ctx->dX, xb, cudaMemcpyDeviceToDevice, ctx->stream));
+        DDB_CUDA_TRY(cudaMemcpyAsync(ctx->view_Y.p, ctx->dY, yb, cudaMemcpyDeviceToDevice, ctx->stream));
+        ctx->dX = ctx->view_X.as<double>();
+        ctx->dY = ctx->view_Y.as<double>();
+    }
     ctx->have_gram = false;
     ctx->imp_k = 0;
     ctx->term_scale_on = false;

@@ -127,6 +127,7 @@ struct ddb_ctx {
     const double* full_X = nullptr;
     const double* full_Y = nullptr;
     int64_t full_m = 0;
+    ddb::DevBuf view_X, view_Y;          // aligned staging of a view that starts on an odd double
 
     // implicit view (ddb_implicit_select): the sweep runs on G[idx, idx] with EVERY selected library row as a
     // target regressed on the other selected rows (ImplicitOptimizer, reference Implicit.jl:57-108)
@@ -140,6 +141,12 @@ struct ddb_ctx {
     ddb::RingState* ring = nullptr;
     ddb::TrsmState* trsm = nullptr;
     ddb::MomentState* moment = nullptr;
+
+    // multi-GPU (comm.cu): NCCL communicator of this context's rank, owned by the context
+    void* comm = nullptr;                // ncclComm_t
+    int nranks = 1, rank = 0;
+    cudaEvent_t ev_ar[2] = {};           // brackets of the last queued all-reduce
+    bool allreduce_pending = false;
 
     ddb_timings timings = {};
 };

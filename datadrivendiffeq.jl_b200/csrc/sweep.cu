@@ -1126,6 +1126,56 @@ __global__ void list_big_kernel(const EqState* eq, int n_t, int* big_list, int* 
 }
 
 // ---------------------------------------------------------------------------------------------
+// canonical candidate numbering
+// ---------------------------------------------------------------------------------------------
+// record_candidate hands out ids with a global atomicAdd from CTAs that run concurrently (one per target), so
+// how the ids of different targets interleave depends on timing -- and differs between the GPUs of a sharded
+// run, whose candidate-rss tables are summed entry by entry.  After the sweep the candidates are therefore
+// renumbered into an order that only depends on the sweep's (deterministic) content: the zero models 0..n_t-1,
+// then the candidates of target 0 in the order it recorded them (one per run), target 1, ...  The sparse
+// records stay where they are in the pool (offsets are private to a rank); only the tables indexed by id move.
+__global__ void __launch_bounds__(1024) canon_base_kernel(const EqState* __restrict__ eq, int n_t, int* __restrict__ base) {
+    __shared__ int s_part[1024];
+    __shared__ int s_carry;
+    if (threadIdx.x == 0) s_carry = n_t;
+    __syncthreads();
+    for (int e0 = 0; e0 < n_t; e0 += blockDim.x) {
+        const int e = e0 + threadIdx.x;
+        const int c = e < n_t ? eq[e].nruns : 0;
+        s_part[threadIdx.x] = c;
+        __syncthreads();
+        for (int o = 1; o < (int)blockDim.x; o <<= 1) {  // inclusive Hillis-Steele scan
+            const int t = threadIdx.x >= o ? s_part[threadIdx.x - o] : 0;
+            __syncthreads();
+            s_part[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (e < n_t) base[e] = s_carry + s_part[threadIdx.x] - c;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_carry += s_part[threadIdx.x];
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) canon_permute_kernel(SweepDev S, const int* __restrict__ base, int64_t* __restrict__ t_off,
+                                                            int32_t* __restrict__ t_nnz, int32_t* __restrict__ t_dof,
+                                                            int32_t* __restrict__ t_eq) {
+    const int e = blockIdx.x;
+    EqState& st = S.eq[e];
+    const int nruns = st.nruns, b = base[e];
+    for (int r = threadIdx.x; r < nruns; r += blockDim.x) {
+        const int old = S.run_cand[(size_t)e * S.run_cap + r], nw = b + r;
+        t_off[nw] = S.cand_off[old];
+        t_nnz[nw] = S.cand_nnz[old];
+        t_dof[nw] = S.cand_dof[old];
+        t_eq[nw] = e;
+        S.run_cand[(size_t)e * S.run_cap + r] = nw;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && nruns > 0) st.last_cand = b + nruns - 1;
+}
+
+// ---------------------------------------------------------------------------------------------
 // selection along the recorded step sequence (solver.jl:94-115)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double score_of(int selector, double rss, int dof, double nobs) {
@@ -1202,7 +1252,7 @@ void SweepState::release_all() {
                      &cand_val, &cand_off, &cand_nnz, &cand_dof, &cand_eq, &counters, &pool_used_d, &run_cand,
                      &run_jfirst, &run_j, &path_support, &path_coef, &path_iters, &big_ws, &big_idx, &big_na,
                      &big_list, &big_fail, &active_matrix, &shared_fail, &rss, &rss_partials, &out_tmp, &cand_terms,
-                     &Ninv, &tgt_terms, &rss_corr, &grp_buf, &rep_buf, &zsol};
+                     &Ninv, &tgt_terms, &rss_corr, &grp_buf, &rep_buf, &zsol, &canon_tmp};
     for (DevBuf* b : all) b->release();
 }
 
@@ -1474,6 +1524,29 @@ int sweep_run(ddb_ctx* ctx, const ddb_sweep_params* prm, const double* lambdas, 
         set_error("ddb_sweep: candidate storage overflow");
         return DDB_OUT_OF_MEMORY;
     }
+    {   // canonical (rank-independent) candidate numbering, see canon_base_kernel
+        const int ncand = h_counters[0], nrec = ncand - n_t;
+        if (nrec > 0) {
+            const size_t o_nnz = (size_t)ncand * 8, o_dof = o_nnz + (size_t)ncand * 4, o_eq = o_dof + (size_t)ncand * 4;
+            DDB_TRY(S->canon_tmp.reserve(o_eq + (size_t)ncand * 4 + (size_t)n_t * 4 + 64));
+            unsigned char* tb = static_cast<unsigned char*>(S->canon_tmp.p);
+            int64_t* t_off = reinterpret_cast<int64_t*>(tb);
+            int32_t* t_nnz = reinterpret_cast<int32_t*>(tb + o_nnz);
+            int32_t* t_dof = reinterpret_cast<int32_t*>(tb + o_dof);
+            int32_t* t_eq = reinterpret_cast<int32_t*>(tb + o_eq);
+            int* t_base = reinterpret_cast<int*>(tb + o_eq + (size_t)ncand * 4);
+            canon_base_kernel<<<1, 1024, 0, st>>>(D.eq, n_t, t_base);
+            canon_permute_kernel<<<n_t, 256, 0, st>>>(D, t_base, t_off, t_nnz, t_dof, t_eq);
+            DDB_CUDA_TRY(cudaMemcpyAsync(D.cand_off + n_t, t_off + n_t, (size_t)nrec * 8, cudaMemcpyDeviceToDevice, st));
+            DDB_CUDA_TRY(cudaMemcpyAsync(D.cand_nnz + n_t, t_nnz + n_t, (size_t)nrec * 4, cudaMemcpyDeviceToDevice, st));
+            DDB_CUDA_TRY(cudaMemcpyAsync(D.cand_dof + n_t, t_dof + n_t, (size_t)nrec * 4, cudaMemcpyDeviceToDevice, st));
+            DDB_CUDA_TRY(cudaMemcpyAsync(D.cand_eq + n_t, t_eq + n_t, (size_t)nrec * 4, cudaMemcpyDeviceToDevice, st));
+            launches += 2;
+            DDB_CUDA_TRY(cudaGetLastError());
+            DDB_CUDA_TRY(cudaEventRecord(ctx->ev[6], st));  // the renumbering is part of the sweep's wall time
+            DDB_CUDA_TRY(cudaStreamSynchronize(st));
+        }
+    }
     float ms_f = 0.f, ms_s = 0.f;
     DDB_CUDA_TRY(cudaEventElapsedTime(&ms_f, ctx->ev[4], ctx->ev[5]));
     DDB_CUDA_TRY(cudaEventElapsedTime(&ms_s, ctx->ev[5], ctx->ev[6]));
@@ -1614,11 +1687,11 @@ int ddb_select(ddb_ctx* ctx, double* coef, double* lambda_opt, int32_t* iters, d
 
 int ddb_solve_sparse(ddb_ctx* ctx, const double* X, const double* Y, int n_t, int64_t m,
                      const ddb_sweep_params* params, const double* lambdas, int L, double* coef, double* lambda_opt,
-                     int32_t* iters, double* rss, int32_t* dof, uint32_t* support_path) {
+                     int32_t* iters, double* rss, int32_t* dof, uint32_t* support_path, int32_t* flags) {
     DDB_TRY(ddb_upload_gram(ctx, X, Y, n_t, m, nullptr));  // copies overlapped by the Gram kernels
     DDB_TRY(ddb_sweep(ctx, params, lambdas, L, m));
     DDB_TRY(ddb_rss(ctx, nullptr));
-    return ddb_select(ctx, coef, lambda_opt, iters, rss, dof, support_path, nullptr, nullptr, nullptr);
+    return ddb_select(ctx, coef, lambda_opt, iters, rss, dof, support_path, nullptr, nullptr, flags);
 }
 
 }  // extern "C"

@@ -9,6 +9,12 @@ The path has exactly two exchange steps, both plain sum all-reduces of small buf
 
 The sweep itself runs replicated on every rank: it is deterministic and all ranks hold bit-identical
 blocks after the all-reduce, so no further communication is needed.
+
+Both collectives run INSIDE the library (``csrc/comm.cu``: ``ncclAllReduce`` on the context's compute stream, no
+host synchronisation) once the context has a communicator: :func:`init_comm` creates the NCCL unique id on rank
+0, carries its 128 bytes to the other ranks over ``torch.distributed`` (the only job left to torch) and calls
+``ddb_comm_init_rank``.  Contexts without a communicator (the CPU test double of ``tests/test_dist_gloo.py``)
+keep the ``torch.distributed`` all-reduces.
 """
 
 from __future__ import annotations
@@ -52,11 +58,43 @@ def total_samples(m_local: int, group=None, device="cpu") -> int:
     return int(t.item())
 
 
+def init_comm(ctx, group=None):
+    """Attach an NCCL communicator to ``ctx`` whose ranks are those of the ``torch.distributed`` ``group``."""
+    torch, dist = _torch()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if world == 1:
+        return
+    dev = f"cuda:{ctx.device}"
+    uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        uid.copy_(torch.frombuffer(bytearray(ctx.comm_unique_id()), dtype=torch.uint8))
+    src = dist.get_global_rank(group, 0) if group is not None else 0
+    dist.broadcast(uid, src=src, group=group)
+    ctx.comm_init_rank(world, rank, bytes(uid.cpu().numpy().tobytes()))
+
+
+def _has_comm(ctx) -> bool:
+    info = getattr(ctx, "comm_info", None)
+    return bool(info) and info()[0] > 1
+
+
 def reduce_blocks_and_sweep(ctx, prm, lambdas: Sequence[float], m_total: int, group=None, paths: bool = False,
                             tensor_device=None, host_data=None):
     """Steps after the data of this rank is bound to ``ctx``: Gram -> all-reduce -> sweep -> rss ->
     all-reduce -> select.  ``ctx`` is a :class:`~.backend.Context` (or a test double with the same
     methods that works on CPU tensors)."""
+    if _has_comm(ctx):  # collectives inside the library, on the compute stream
+        if host_data is not None and not paths:
+            return ctx.solve_sparse_sharded(host_data[0], host_data[1], prm, lambdas, m_total)
+        if host_data is not None:
+            ctx.upload_gram(host_data[0], host_data[1])
+        else:
+            ctx.gram()
+        ctx.allreduce_gram()
+        ctx.sweep(prm, lambdas, m_total)
+        ctx.rss()
+        ctx.allreduce_rss()
+        return ctx.select(paths=paths)
     torch, dist = _torch()
     dev = tensor_device if tensor_device is not None else f"cuda:{ctx.device}"
     if host_data is not None:  # (X_local, Y_local) host arrays: upload overlapped with the Gram kernels
@@ -83,4 +121,6 @@ def reduce_blocks_and_sweep(ctx, prm, lambdas: Sequence[float], m_total: int, gr
 def solve_sharded(ctx, X_local: np.ndarray, Y_local: np.ndarray, prm, lambdas, group=None, paths: bool = False):
     """Every rank passes its own shard (n x m_local, n_t x m_local); returns ``(SweepOutput, m_total)``."""
     m_total = total_samples(X_local.shape[1], group, device=f"cuda:{ctx.device}")
+    if not _has_comm(ctx) and hasattr(ctx, "comm_init_rank"):
+        init_comm(ctx, group)
     return reduce_blocks_and_sweep(ctx, prm, lambdas, m_total, group, paths, host_data=(X_local, Y_local)), m_total

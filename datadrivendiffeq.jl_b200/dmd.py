@@ -101,7 +101,11 @@ def _gram_pair(ctx, A, B, group=None):
     if group is not None:
         from . import dist
 
-        dist.allreduce_sum(PQ, group)
+        if dist._has_comm(ctx):  # NCCL inside the library, on the compute stream
+            ctx.allreduce_sum(PQ.data_ptr(), PQ.numel())
+            ctx.synchronize()
+        else:
+            dist.allreduce_sum(PQ, group)
     return PQ[0].T, PQ[1].T, PQ  # column-major buffers seen from row-major torch: transposes
 
 
@@ -281,6 +285,10 @@ def solve_dmd(prob: DataDrivenProblem, alg: B200DMD, control_input: Optional[np.
         if Bfin is not None and Ud is not None:
             pred = pred + Ud[s0:s1] @ Bfin.T
         rss += float(((Yd[s0:s1] - pred) ** 2).sum())
+    if grp is not None:  # every rank scored its own snapshots: the statistic is the sum over the ranks
+        from . import dist
+
+        rss = float(dist.allreduce_sum(torch.tensor([rss], dtype=torch.float64, device=dev), grp).item())
     return KoopmanResult(
         K=Kh, eigenvalues=lam.cpu().numpy(), modes=phi.cpu().numpy(), C=np.eye(n), Q=Q.cpu().numpy(), P=P.cpu().numpy(),
         rss=rss, nobs=n * m_total,

@@ -14,8 +14,9 @@
  *   - The caller owns every host buffer and every device buffer it passes in and keeps it alive for
  *     the duration of the call; the library neither frees nor retains them after returning, except
  *     ddb_bind_device (retains the two data pointers until the next bind/upload/destroy).
- *   - A ddb_ctx is bound to ONE GPU (one process per GPU) and is not thread-safe; distinct contexts
- *     are independent.  Calls are synchronous unless the name ends in _async.
+ *   - A ddb_ctx is bound to ONE GPU and is not thread-safe; distinct contexts are independent (one host thread
+ *     per context is fine).  Several GPUs: either one process per GPU with ddb_comm_init_rank, or one process
+ *     with a ddb_group (N contexts + NCCL communicators, driven by one call).  Calls are synchronous.
  *   - There is NO CPU fallback: without a CUDA device every entry point that computes fails with
  *     DDB_CUDA_ERROR.
  */
@@ -93,7 +94,9 @@ typedef struct ddb_timings {
     double gram_dmma_flops; /* FP64 tensor-core flops the last Gram stage issued PER SAMPLE (512 per DMMA.8x8x4);
                                below the algorithmic k(k+1) + 2 k n_t + 2 n_t when the moment schedule ran */
     int32_t gram_schedule;  /* schedule of the last Gram stage: 0 self-building, 1 ring, 2 moment */
-    int32_t reserved;
+    int32_t allreduce_calls; /* NCCL all-reduces queued by the last sharded solve / since the last reset */
+    double allreduce_ms;    /* their duration on the compute stream (includes waiting for the slowest rank) */
+    double allreduce_bytes; /* payload per rank */
 } ddb_timings;
 
 /* ---- context ---------------------------------------------------------------------------------- */
@@ -186,8 +189,9 @@ int ddb_gram_upload(ddb_ctx* ctx, const double* G, const double* R, const double
 
 /* ---- pre-/post-processing options of the reference on the device ---------------------------------
  * ddb_set_sample_range: the following ddb_gram / ddb_rss / ddb_residual calls see samples [first, last) of the
- *   bound data only (last < 0 = to the end; ddb_gram needs first * n and first * n_t even -- 16-byte alignment of
- *   the bulk copies -- the rss / residual passes take any first).  Replaces `splitobs(data, at = split)` and the
+ *   bound data only (last < 0 = to the end; any first / last: a view that does not start on a 16-byte boundary --
+ *   odd first with an odd n or n_t -- is staged once into an aligned buffer for the bulk copies of the Gram
+ *   kernels).  Replaces `splitobs(data, at = split)` and the
  *   batches of the `DataLoader` (src/utils/data_processing.jl:29-39): train part, test part and every batch are
  *   views of the resident data.  A new upload / bind resets the view.
  * ddb_permute_samples: reorders the resident samples, new sample s = old sample perm[s] (host array of m
@@ -262,11 +266,62 @@ int ddb_select(ddb_ctx* ctx, double* coef, double* lambda_opt, int32_t* iters, d
  * `alg(X, Y; options)` (DataDrivenSparse.jl:258-277) together with the library evaluation that
  * `init` performs before it (src/commonsolve.jl:92-139).  trainerror (n_t... summed to a scalar by
  * the caller) is rss of the selected model per target = sum(abs2, Y - C*Theta) rows
- * (lib/DataDrivenSparse/src/commonsolve.jl:37). */
+ * (lib/DataDrivenSparse/src/commonsolve.jl:37).  flags (n_t, may be NULL): bit 0 = a factorisation broke down for
+ * that target (the caller maps it to DDReturnCode(2), src/DataDrivenDiffEq.jl:60-67). */
 int ddb_solve_sparse(ddb_ctx* ctx, const double* X, const double* Y, int n_t, int64_t m,
                      const ddb_sweep_params* params, const double* lambdas, int L, double* coef,
                      double* lambda_opt, int32_t* iters, double* rss, int32_t* dof,
-                     uint32_t* support_path);
+                     uint32_t* support_path, int32_t* flags);
+
+/* ---- multi-GPU: the row-sharded path ------------------------------------------------
+ * Rows (samples) shard across the GPUs; the path has exactly two exchange steps, each ONE
+ * `ncclAllReduce(sum, ncclDouble)` in place on the context's compute stream (no host synchronisation between the
+ * producing kernel, the collective and its consumer): the packed [G | R | yy] after the Gram stage and the
+ * candidate-rss table after the streaming rss pass.  The sweep runs replicated (deterministic, identical blocks
+ * on every rank; candidates are numbered canonically so that entry c of the table is the same model everywhere).
+ * Replaces nothing in the reference (it is single-process CPU code); the hook a maintainer binds is the same
+ * `CommonSolve.solve!` method as on one GPU (lib/DataDrivenSparse/src/commonsolve.jl:1-24), with
+ * `B200Sparse(inner; ngpus = N)` holding a ddb_group.  NCCL is loaded at run time (libnccl.so.2) on first use. */
+#define DDB_UNIQUE_ID_BYTES 128
+/* One process (or thread) per GPU: rank 0 creates the id, the host program carries its 128 bytes to the other
+ * ranks (MPI, torch.distributed, a file ...), then every rank attaches a communicator to its context. */
+int ddb_comm_unique_id(void* id128);
+int ddb_comm_init_rank(ddb_ctx* ctx, int nranks, int rank, const void* id128);
+/* nranks / rank of the context's communicator (1 / 0 without one) and the version of the loaded NCCL (0 if none). */
+int ddb_comm_info(const ddb_ctx* ctx, int* nranks, int* rank, int* nccl_version);
+/* In-place sum over the ranks, queued on the compute stream; no-ops without a communicator.
+ * ddb_allreduce_gram: the context's own packed blocks (after ddb_gram / ddb_upload_gram with dPacked = NULL);
+ * ddb_allreduce_rss: the context's own candidate-rss table (after ddb_rss with dRss = NULL);
+ * ddb_allreduce_sum: any device buffer of `count` doubles (e.g. the [P | Q] blocks of the DMD path). */
+int ddb_allreduce_gram(ddb_ctx* ctx);
+int ddb_allreduce_rss(ddb_ctx* ctx);
+int ddb_allreduce_sum(ddb_ctx* ctx, double* dBuf, int64_t count);
+/* ddb_solve_sparse for ONE RANK of a sharded run (collective: every rank calls it with its own host shard
+ * X n x m_local, Y n_t x m_local and the same library / parameters / thresholds; m_total = samples of all ranks;
+ * every rank receives the full result).  flags (n_t, may be NULL) as in ddb_select. */
+int ddb_solve_sparse_sharded(ddb_ctx* ctx, const double* X, const double* Y, int n_t, int64_t m_local, int64_t m_total,
+                             const ddb_sweep_params* params, const double* lambdas, int L, double* coef,
+                             double* lambda_opt, int32_t* iters, double* rss, int32_t* dof, uint32_t* support_path,
+                             int32_t* flags);
+
+/* One process driving N GPUs of a node: N contexts + `ncclCommInitAll` (devices = NULL means 0 .. ngpus-1).
+ * ddb_group_solve_sparse is the N-GPU form of ddb_solve_sparse: it cuts the host X / Y into N contiguous sample
+ * ranges (interior boundaries on multiples of 16 samples, ddb_group_shard), runs one host thread per GPU through
+ * ddb_solve_sparse_sharded and returns rank 0's (= every rank's) result.  m >= 16 * ngpus. */
+typedef struct ddb_group ddb_group;
+int ddb_group_create(int ngpus, const int* devices, ddb_group** out);
+int ddb_group_destroy(ddb_group* g);
+int ddb_group_size(const ddb_group* g);
+ddb_ctx* ddb_group_ctx(ddb_group* g, int rank); /* borrowed; owned by the group */
+int ddb_group_set_library_monomial(ddb_group* g, int n, int k, const uint8_t* exps);
+int ddb_group_set_features(ddb_group* g, int n_raw, int n_feat, const int32_t* kind, const int32_t* source, const double* coef);
+int ddb_group_shard(const ddb_group* g, int64_t m, int rank, int64_t* first, int64_t* last);
+int ddb_group_solve_sparse(ddb_group* g, const double* X, const double* Y, int n_t, int64_t m,
+                           const ddb_sweep_params* params, const double* lambdas, int L, double* coef,
+                           double* lambda_opt, int32_t* iters, double* rss, int32_t* dof, uint32_t* support_path,
+                           int32_t* flags);
+/* Stage timings of the last group solve: rank 0's, with the per-rank stages replaced by the slowest rank's. */
+int ddb_group_get_timings(const ddb_group* g, ddb_timings* out);
 
 /* ---- DataDrivenDMD Gram path ------------------------------------------------------------------- */
 

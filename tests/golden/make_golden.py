@@ -83,5 +83,35 @@ def main():
              Y=np.array([[2.0, 4.0, 6.0]]), threshold=0.1)
 
 
+def c4_inputs():
+    """Inputs of the C4-size fixtures (regenerated from the seed by the tests, not stored): the full Lorenz-96
+    library of BASELINE config 4 (n = 64, degree 2, k = 2145 terms) on 6000 noisy samples, 4 of the 64 targets."""
+    X, D = systems.lorenz96_ensemble(6000, n=64, seed=7, samples_per_traj=500)
+    D = D + 1e-2 * np.random.default_rng(17).standard_normal(D.shape)
+    return X, D[[0, 21, 42, 63]], oracle.polynomial_exponents(64, 2), 10.0 ** np.arange(-3, -0.9, 0.5)
+
+
+def c4_size():
+    """ADMM(rho = 1) and SR3(nu = 1, HardThreshold) step traces at k = 2145: the path that iterates through the explicit
+    inverse of the equilibrated matrix (`ninv_apply_kernel`) at the size the bench runs it.  The oracle needs minutes
+    here (one 2145 x 2145 `cho_solve` per iteration and target), so its traces are committed."""
+    X, Y, ex, lams = c4_inputs()
+    Th = oracle.evaluate_library(ex, X)
+    for name, alg in (("c4_k2145_admm", oracle.ADMM(lams, 1.0)), ("c4_k2145_sr3_hard", oracle.SR3(lams, 1.0))):
+        traces = []
+        res = oracle.sparse_regression(alg, Th, Y, oracle.CommonOptions(), traces=traces)
+        sp = np.stack([np.stack(t.support_path) for t in traces])
+        cp = np.stack([np.stack(t.coef_path) for t in traces])
+        ip = np.stack([np.asarray(t.iters_path) for t in traces])
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), thresholds=alg.thresholds, coefficients=res.coefficients,
+                            lambda_opt=np.asarray(res.lambdas), iterations=np.asarray(res.iterations),
+                            support_path=np.packbits(sp, axis=-1), coef_path=cp, iters_path=ip, k=ex.shape[1],
+                            x_checksum=float(np.sum(X)), y_checksum=float(np.sum(Y)))
+        print(name, "dof", [int(s.sum()) for s in sp[:, -1]], "iters", ip.sum(1).tolist())
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "c4":
+        c4_size()
+    else:
+        main()

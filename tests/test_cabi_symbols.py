@@ -50,7 +50,7 @@ def test_no_cpu_fallback():
 
 def test_struct_layouts():
     assert C.sizeof(_lib.SweepParams) == 48
-    assert C.sizeof(_lib.Timings) == 88
+    assert C.sizeof(_lib.Timings) == 104
 
 
 @pytest.mark.parametrize("kaug,m,nctas", [(59, 10_000_000, 444), (2209, 1_250_000, 148), (2209, 1001, 148), (128, 777, 148),

@@ -175,3 +175,33 @@ def test_dmd_solve_host_entry_point():
     Kref = np.linalg.lstsq(X.T, Y.T, rcond=None)[0].T
     assert np.max(np.abs(K - Kref)) <= 1e-8 * max(1.0, np.max(np.abs(Kref)))
     ctx.close()
+
+
+def test_c5_state_count_blocks_and_operator():
+    """BASELINE config 5 at its own state count: n = 4096 states, 2 x 10^4 snapshots (the Gram kernel is
+    sample-count independent per stage; the 4096-wide `trsm.cu` substitution is what no smaller test reaches).
+    P, Q <= 1e-13 scaled against NumPy; K = Q P^-1 against the least-squares solution of the reference
+    (`K = Y / X`, algorithms.jl:80-83; LAPACK gelsy = pivoted QR, as Julia's `/`) <= 1e-8."""
+    import scipy.linalg as sla
+    import torch
+
+    n, m = 4096, 20_000
+    A, X, Y = systems.linear_snapshots_blocked(n, m, seed=5, restart=64)
+    dev = torch.device("cuda:0")
+    Xt = torch.from_numpy(np.ascontiguousarray(X.T)).to(dev)
+    Yt = torch.from_numpy(np.ascontiguousarray(Y.T)).to(dev)
+    PQ = torch.zeros((2, n, n), dtype=torch.float64, device=dev)
+    K = torch.zeros((n, n), dtype=torch.float64, device=dev)
+    with ddb200.Context(0) as ctx:
+        ctx.dmd_gram(Xt.data_ptr(), Yt.data_ptr(), n, m, PQ[0].data_ptr(), PQ[1].data_ptr())
+        ctx.dmd_operator(PQ[0].data_ptr(), PQ[1].data_ptr(), n, K.data_ptr())
+    P, Q, Kh = PQ[0].T.cpu().numpy(), PQ[1].T.cpu().numpy(), K.T.cpu().numpy()
+    P0, Q0 = X @ X.T, Y @ X.T
+    sc = np.sqrt(np.outer(np.diag(P0), np.diag(P0)))
+    assert np.max(np.abs(P - P0) / sc) < 1e-13
+    assert np.max(np.abs(Q - Q0) / sc) < 1e-13
+    np.testing.assert_array_equal(P, P.T)
+    Kref = sla.lstsq(X.T, Y.T, lapack_driver="gelsy", check_finite=False)[0].T
+    assert np.max(np.abs(Kh - Kref)) <= 1e-8 * max(1.0, np.max(np.abs(Kref)))
+    # size-independent property: K P = Q (the normal equations the operator solves)
+    assert np.max(np.abs(Kh @ P0 - Q0)) <= 1e-9 * np.max(np.abs(Q0))

@@ -445,3 +445,48 @@ def test_nonfinite_samples_are_reported(ctx):
     assert e.value.status == -6
     with pytest.raises(ValueError):
         ddb200.ContinuousDataDrivenProblem(X, DX=Y)  # the host mirror refuses them up front
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE config 4 at its own library size: ADMM / SR3 at k = 2145 against committed oracle step traces
+# ------------------------------------------------------------------------------------------------
+def _c4_inputs():
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(os.path.dirname(__file__), "golden", "make_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.c4_inputs()
+
+
+@pytest.mark.parametrize("name,alg,prox", [("c4_k2145_admm", "ADMM", "SoftThreshold"), ("c4_k2145_sr3_hard", "SR3", "HardThreshold")])
+def test_c4_library_size_relaxed_algorithms_match_oracle_traces(ctx, golden_dir, name, alg, prox):
+    """ADMM(rho = 1) (ADMM.jl:107-121) and SR3(nu = 1, HardThreshold) (SR3.jl:129-141) on the full Lorenz-96 library
+    (k = 2145, 6000 noisy samples, 4 targets): every iteration goes through the explicit inverse of the equilibrated
+    2145 x 2145 matrix (`ninv_apply_kernel`).  Supports at every threshold, iteration counts per threshold and
+    coefficients (<= 1e-9) against the oracle's step traces (tests/golden/make_golden.py c4)."""
+    g = np.load(f"{golden_dir}/{name}.npz")
+    X, Y, ex, lams = _c4_inputs()
+    assert float(np.sum(X)) == float(g["x_checksum"]) and float(np.sum(Y)) == float(g["y_checksum"])  # same inputs
+    k = int(g["k"])
+    assert ex.shape[1] == k == 2145
+    ctx.set_features(0, None)
+    ctx.set_library(ex)
+    ctx.upload(X, Y)
+    ctx.gram()
+    ctx.sweep(ctx.make_params(alg, rho=1.0, proximal=prox), g["thresholds"])
+    ctx.rss()
+    out = ctx.select(paths=True)
+    sp = np.unpackbits(g["support_path"], axis=-1)[:, :, :k].astype(bool)
+    np.testing.assert_array_equal(out.support_path, sp)  # every threshold, every target
+    np.testing.assert_array_equal(out.iters_path, g["iters_path"])
+    cp = g["coef_path"]
+    assert (np.abs(out.coef_path - cp) <= 1e-9 * np.abs(cp) + 1e-13 * np.abs(cp).max()).all()
+    ref = g["coefficients"]
+    np.testing.assert_array_equal(out.coefficients != 0, ref != 0)
+    nz = ref != 0
+    tol = 1e-9 if alg == "ADMM" else 1e-7  # SR3: numerically tied iterates of neighbouring thresholds (DESIGN.md section 2)
+    assert (np.abs(out.coefficients[nz] - ref[nz]) / np.abs(ref[nz])).max() <= tol
+    np.testing.assert_array_equal(out.iterations, g["iterations"])
+    if alg == "ADMM":
+        np.testing.assert_allclose(out.lambda_opt, g["lambda_opt"], rtol=1e-15)

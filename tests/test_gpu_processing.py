@@ -110,3 +110,27 @@ def test_residual_permute_and_range(ctx):
         ctx.set_sample_range(10, 5)
     ctx.set_sample_range(201, 500)  # odd first sample: fine for the residual pass
     np.testing.assert_allclose(ctx.residual(C), ((DX[:, perm][:, 201:500] - C @ Th[:, perm][:, 201:500]) ** 2).sum(1), rtol=1e-12)
+
+
+def test_odd_batch_size_on_a_three_state_problem(ctx):
+    """Batches of 125 samples of a 3-state problem start on odd doubles (``first * n`` odd): the views are staged
+    into aligned buffers for the Gram kernel's bulk copies; the reference accepts any batch size."""
+    X, DX = _lorenz(m=1000)
+    basis = ddb200.polynomial_basis(3, 2)
+    Th = oracle.evaluate_library(basis.exponents, X)
+    perm = np.random.default_rng(5).permutation(875)
+    kw = dict(split=0.875, batchsize=125, partial=True)
+    C_ref, res_ref, _ = oracle.solve_processed(oracle.STLSQ(LAMS), Th, DX, perm=perm, **kw)
+    sol = _solve(ctx, basis, X, DX, ddb200.STLSQ(LAMS), perm=perm, **kw)
+    assert len(sol.results) == len(res_ref) == 7
+    for got, ref in zip(sol.results, res_ref):
+        np.testing.assert_array_equal(got.coefficients != 0.0, ref.coefficients != 0.0)
+        np.testing.assert_allclose(got.coefficients, ref.coefficients, rtol=1e-7, atol=1e-10)
+        np.testing.assert_allclose(got.testerror, ref.testerror, rtol=1e-7)
+    ctx.set_features(0, None)
+    ctx.set_library(basis.exponents)
+    ctx.upload(X, DX)
+    ctx.set_sample_range(125, 250)  # 375 doubles into X: not 16-byte aligned
+    ctx.gram()
+    G = ctx.gram_download()[0]
+    np.testing.assert_allclose(G, Th[:, 125:250] @ Th[:, 125:250].T, rtol=1e-12, atol=1e-9)
