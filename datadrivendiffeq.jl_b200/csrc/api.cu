@@ -4,6 +4,9 @@
 #include <cstdarg>
 #include <cstring>
 #include <cmath>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 
 namespace ddb {
 
@@ -307,6 +310,9 @@ __global__ void packed_add_kernel(double* __restrict__ acc, const double* __rest
 int ddb_upload_gram(ddb_ctx* ctx, const double* X, const double* Y, int n_t, int64_t m, double* dPacked) {
     CHECK_CTX(ctx);
     DDB_TRY(check_data_args(ctx, X, Y, n_t, m, "ddb_upload_gram"));
+    ctx->timings.allreduce_ms = 0.0;
+    ctx->timings.allreduce_bytes = 0.0;
+    ctx->timings.allreduce_calls = 0;
     if (ctx->k <= 0) {
         set_error("ddb_upload_gram: no library installed");
         return DDB_BAD_STATE;
@@ -350,21 +356,68 @@ int ddb_upload_gram(ddb_ctx* ctx, const double* X, const double* Y, int n_t, int
         DDB_TRY(ctx->raw_X.reserve((size_t)n_in * m * sizeof(double)));
         dIn = ctx->raw_X.as<double>();
     }
-    // all copies are queued up front; event c fires when chunk c is resident
+    // Page-locked host buffers: all copies are queued up front on the copy stream (event c fires when chunk c is
+    // resident) and the DMA engine runs ahead of the kernels.  PAGEABLE buffers (a Julia `Matrix`, a NumPy array):
+    // cudaMemcpyAsync stages them through the driver's pinned bounce buffers and blocks the calling thread while it
+    // does, so the copies are issued by a helper thread -- the calling thread keeps launching the Gram kernels of
+    // the chunks that have landed, and the transfer still hides behind the tensor work.
+    auto is_pinned = [](const void* p) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+    };
+    const bool pinned = is_pinned(X) && is_pinned(Y);
+    std::mutex mu;
+    std::condition_variable cv;
+    int landed = 0;                 // chunks whose copies have been issued and whose event is recorded
+    cudaError_t copy_err = cudaSuccess;
+    auto issue_copies = [&](bool notify) {
+        for (int c = 0; c < nchunks; ++c) {
+            const int64_t s0 = c * chunk, mc = std::min(chunk, m - s0);
+            cudaError_t e = cudaMemcpyAsync(dIn + s0 * n_in, X + s0 * n_in, (size_t)mc * n_in * sizeof(double),
+                                            cudaMemcpyHostToDevice, ctx->copy_stream);
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync(dY + s0 * n_t, Y + s0 * n_t, (size_t)mc * n_t * sizeof(double), cudaMemcpyHostToDevice,
+                                    ctx->copy_stream);
+            if (e == cudaSuccess) e = cudaEventRecord(ctx->chunk_ev[c], ctx->copy_stream);
+            if (notify) {
+                std::lock_guard<std::mutex> lk(mu);
+                if (e != cudaSuccess) copy_err = e;
+                landed = (e == cudaSuccess) ? c + 1 : nchunks;  // on failure release the consumer; it checks copy_err
+                cv.notify_all();
+            } else if (e != cudaSuccess) {
+                copy_err = e;
+            }
+            if (e != cudaSuccess) return;
+        }
+    };
     DDB_CUDA_TRY(cudaEventRecord(ctx->chunk_ev[nchunks], ctx->copy_stream));
-    for (int c = 0; c < nchunks; ++c) {
-        const int64_t s0 = c * chunk, mc = std::min(chunk, m - s0);
-        DDB_CUDA_TRY(cudaMemcpyAsync(dIn + s0 * n_in, X + s0 * n_in, (size_t)mc * n_in * sizeof(double),
-                                     cudaMemcpyHostToDevice, ctx->copy_stream));
-        DDB_CUDA_TRY(cudaMemcpyAsync(dY + s0 * n_t, Y + s0 * n_t, (size_t)mc * n_t * sizeof(double), cudaMemcpyHostToDevice,
-                                     ctx->copy_stream));
-        DDB_CUDA_TRY(cudaEventRecord(ctx->chunk_ev[c], ctx->copy_stream));
+    std::thread copier;
+    if (pinned) {
+        issue_copies(false);
+    } else {
+        const int device = ctx->device;
+        copier = std::thread([&, device] {
+            cudaSetDevice(device);
+            issue_copies(true);
+        });
     }
     double gram_ms = 0.0;
     int launches = 0, status = DDB_OK;
-    for (int c = 0; c < nchunks && status == DDB_OK; ++c) {
+    cudaError_t cerr = pinned ? copy_err : cudaSuccess;
+    for (int c = 0; c < nchunks && status == DDB_OK && cerr == cudaSuccess; ++c) {
         const int64_t s0 = c * chunk, mc = std::min(chunk, m - s0);
-        DDB_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[c], 0));
+        if (!pinned) {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return landed > c; });
+            cerr = copy_err;
+            if (cerr != cudaSuccess) break;
+        }
+        cerr = cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[c], 0);
+        if (cerr != cudaSuccess) break;
         if (ctx->n_raw > 0) status = expand_features(ctx, dIn + s0 * n_in, s0, mc, ctx->stream);
         if (status != DDB_OK) break;
         ctx->dX = dX + s0 * n;
@@ -377,14 +430,20 @@ int ddb_upload_gram(ddb_ctx* ctx, const double* X, const double* Y, int n_t, int
         packed_add_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(dPacked, ctx->d_chunk_packed.as<double>(),
                                                                                     count, c == 0);
     }
+    // every exit path: the helper thread is joined, both streams are drained (the caller may free X / Y as soon as
+    // we return) and the context describes the whole data set again
+    if (copier.joinable()) copier.join();
     ctx->dX = dX;
     ctx->dY = dY;
     ctx->m = m;
-    cudaError_t ce = cudaStreamSynchronize(ctx->copy_stream);
+    const cudaError_t ce = cudaStreamSynchronize(ctx->copy_stream);
+    const cudaError_t se = cudaStreamSynchronize(ctx->stream);
     if (status != DDB_OK) return status;
+    DDB_CUDA_TRY(cerr);
+    DDB_CUDA_TRY(copy_err);
     DDB_CUDA_TRY(ce);
+    DDB_CUDA_TRY(se);
     DDB_CUDA_TRY(cudaGetLastError());
-    DDB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     float h2d = 0.f;
     DDB_CUDA_TRY(cudaEventElapsedTime(&h2d, ctx->chunk_ev[nchunks], ctx->chunk_ev[nchunks - 1]));
     ctx->timings.h2d_ms = h2d;
@@ -586,8 +645,15 @@ int64_t ddb_gram_count(const ddb_ctx* ctx) {
     return (int64_t)ctx->k * ctx->k + (int64_t)ctx->k * ctx->n_t + ctx->n_t;
 }
 
+static void reset_allreduce_timings(ddb_ctx* ctx) {  // a new Gram starts a new solve
+    ctx->timings.allreduce_ms = 0.0;
+    ctx->timings.allreduce_bytes = 0.0;
+    ctx->timings.allreduce_calls = 0;
+}
+
 int ddb_gram(ddb_ctx* ctx, double* dPacked) {
     CHECK_CTX(ctx);
+    reset_allreduce_timings(ctx);
     return gram_run(ctx, dPacked);
 }
 

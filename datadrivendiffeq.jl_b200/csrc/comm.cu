@@ -117,7 +117,7 @@ int comm_allreduce(ddb_ctx* ctx, double* d, int64_t count) {
 }
 
 // adds the duration of the last queued all-reduce to the timings (call after a stream synchronisation)
-static void comm_collect_time(ddb_ctx* ctx) {
+void comm_collect_time(ddb_ctx* ctx) {
     if (!ctx->allreduce_pending) return;
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, ctx->ev_ar[0], ctx->ev_ar[1]) == cudaSuccess) ctx->timings.allreduce_ms += ms;
@@ -129,18 +129,12 @@ static void comm_collect_time(ddb_ctx* ctx) {
 int solve_sharded_rank(ddb_ctx* ctx, const double* X, const double* Y, int n_t, int64_t m_local, int64_t m_total,
                        const ddb_sweep_params* prm, const double* lambdas, int L, double* coef, double* lambda_opt,
                        int32_t* iters, double* rss, int32_t* dof, uint32_t* support_path, int32_t* flags) {
-    ctx->timings.allreduce_ms = 0.0;
-    ctx->timings.allreduce_bytes = 0.0;
-    ctx->timings.allreduce_calls = 0;
     DDB_TRY(ddb_upload_gram(ctx, X, Y, n_t, m_local, nullptr));  // copies overlapped by the Gram kernels
     DDB_TRY(comm_allreduce(ctx, ctx->d_packed.as<double>(), ddb_gram_count(ctx)));
-    DDB_TRY(sweep_run(ctx, prm, lambdas, L, m_total));           // synchronises: collect the all-reduce time
-    comm_collect_time(ctx);
+    DDB_TRY(sweep_run(ctx, prm, lambdas, L, m_total));           // synchronises and collects the all-reduce time
     DDB_TRY(rss_run(ctx, ctx->sweep, nullptr));
     DDB_TRY(comm_allreduce(ctx, ctx->sweep->rss.as<double>(), ctx->sweep->ncand));
-    DDB_TRY(select_run(ctx, coef, lambda_opt, iters, rss, dof, support_path, nullptr, nullptr, flags));
-    comm_collect_time(ctx);
-    return DDB_OK;
+    return select_run(ctx, coef, lambda_opt, iters, rss, dof, support_path, nullptr, nullptr, flags);
 }
 
 }  // namespace ddb

@@ -184,8 +184,8 @@ __global__ void __launch_bounds__(256) dmd_reduce_kernel(const double* __restric
 // ---------------------------------------------------------------------------------------------
 // K = Q P^-1 through the equilibrated Cholesky of P (kernels shared with the sweep, sweep.cu)
 // ---------------------------------------------------------------------------------------------
-int chol_factor_shared(ddb_ctx* ctx, double* A, int k, int* d_fail, int* launches);
-int chol_solve_many(ddb_ctx* ctx, const double* L, int k, double* Z, int nrhs);
+int chol_factor_shared(ddb_ctx* ctx, double* A, int k, int* d_fail, int extra, int* launches);
+int chol_solve_many(ddb_ctx* ctx, const double* L, int k, double* Z, int nrhs, int* launches);
 
 __global__ void dmd_diag_kernel(const double* __restrict__ P, int n, double* __restrict__ dinv) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -346,8 +346,8 @@ int ddb_dmd_operator(ddb_ctx* ctx, const double* dP, const double* dQ, int n, do
     dim3 tg((n + 31) / 32, (n + 31) / 32);
     dmd_rhs_kernel<<<tg, 256, 0, st>>>(dQ, n, D->dinv.as<double>(), D->Z.as<double>());
     int launches = 3;
-    DDB_TRY(chol_factor_shared(ctx, D->Ps.as<double>(), n, D->fail.as<int>(), &launches));
-    DDB_TRY(chol_solve_many(ctx, D->Ps.as<double>(), n, D->Z.as<double>(), n));
+    DDB_TRY(chol_factor_shared(ctx, D->Ps.as<double>(), n, D->fail.as<int>(), 0, &launches));
+    DDB_TRY(chol_solve_many(ctx, D->Ps.as<double>(), n, D->Z.as<double>(), n, &launches));
     dmd_out_kernel<<<tg, 256, 0, st>>>(D->Z.as<double>(), n, D->dinv.as<double>(), dK);
     DDB_CUDA_TRY(cudaGetLastError());
     DDB_CUDA_TRY(cudaEventRecord(ctx->ev[5], st));

@@ -84,12 +84,20 @@ struct MomentState {
     std::vector<std::pair<int, int>> pairs;  // (row block, nrb + column block), whole pairs first
     int nfull = 0, nhalf = 0;                // pairs [nfull, nfull + nhalf) only need rows 0..63, the rest rows 0..31
     DevBuf factors, src;
-    // sample-count-dependent part
-    int64_t plan_m = -1;
-    int plan_nctas = -1;
-    int nslots = 0;
-    DevBuf plan, partials;
-    size_t off_cta = 0, off_psb = 0;
+    // sample-count-dependent part: a few wave plans are kept (the chunked upload of ddb_upload_gram alternates
+    // between the chunk length and the length of the last chunk on every call)
+    struct DevPlan {
+        int64_t m = -1;
+        int nctas = -1;
+        int nslots = 0;
+        DevBuf buf;
+        size_t off_cta = 0, off_psb = 0;
+        uint64_t stamp = 0;
+    };
+    static constexpr int kPlans = 3;
+    DevPlan plans[kPlans];
+    uint64_t clock = 0;
+    DevBuf partials;
 };
 
 // Host-only analysis of a monomial library (n x k exponent table, n_t targets): virtual rows / columns, needed
@@ -331,7 +339,7 @@ static int install_library(ddb_ctx* ctx, MomentState* M) {
                                  ctx->stream));
     DDB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // `map` is a stack-lifetime host buffer
     M->eligible = true;
-    M->plan_m = -1;
+    for (auto& pl : M->plans) pl.m = -1;
     return DDB_OK;
 }
 
@@ -478,8 +486,19 @@ static void plan_waves(const std::vector<std::pair<int, int>>& pairs, int nfull,
     W->time = best[0] - kWavePenalty * W->nwaves;
 }
 
-static int build_wave_plan(ddb_ctx* ctx, MomentState* M) {
+static int build_wave_plan(ddb_ctx* ctx, MomentState* M, MomentState::DevPlan** out) {
     const int nctas = ctx->sm_count;
+    MomentState::DevPlan* P = nullptr;
+    for (auto& pl : M->plans)
+        if (pl.m == ctx->m && pl.nctas == nctas) P = &pl;
+    if (P) {
+        P->stamp = ++M->clock;
+        *out = P;
+        return DDB_OK;
+    }
+    P = &M->plans[0];
+    for (auto& pl : M->plans)
+        if (pl.stamp < P->stamp) P = &pl;  // least recently used
     const int64_t ns = (ctx->m + kKS - 1) / kKS;
     WavePlan W;
     plan_waves(M->pairs, M->nfull, M->nhalf, ns, nctas, &W);
@@ -493,20 +512,23 @@ static int build_wave_plan(ddb_ctx* ctx, MomentState* M) {
         segs.insert(segs.end(), per_cta[c].begin(), per_cta[c].end());
     }
     cta_seg_begin[nctas] = (int32_t)segs.size();
-    M->off_cta = segs.size() * sizeof(GramSegment);
-    M->off_psb = M->off_cta + cta_seg_begin.size() * sizeof(int32_t);
-    const size_t total = M->off_psb + psb.size() * sizeof(int32_t);
+    P->m = -1;
+    P->off_cta = segs.size() * sizeof(GramSegment);
+    P->off_psb = P->off_cta + cta_seg_begin.size() * sizeof(int32_t);
+    const size_t total = P->off_psb + psb.size() * sizeof(int32_t);
     std::vector<unsigned char> host(total);
     memcpy(host.data(), segs.data(), segs.size() * sizeof(GramSegment));
-    memcpy(host.data() + M->off_cta, cta_seg_begin.data(), cta_seg_begin.size() * sizeof(int32_t));
-    memcpy(host.data() + M->off_psb, psb.data(), psb.size() * sizeof(int32_t));
-    DDB_TRY(M->plan.reserve(total));
-    DDB_CUDA_TRY(cudaMemcpyAsync(M->plan.p, host.data(), total, cudaMemcpyHostToDevice, ctx->stream));
+    memcpy(host.data() + P->off_cta, cta_seg_begin.data(), cta_seg_begin.size() * sizeof(int32_t));
+    memcpy(host.data() + P->off_psb, psb.data(), psb.size() * sizeof(int32_t));
+    DDB_TRY(P->buf.reserve(total));
+    DDB_CUDA_TRY(cudaMemcpyAsync(P->buf.p, host.data(), total, cudaMemcpyHostToDevice, ctx->stream));
     DDB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    DDB_TRY(M->partials.reserve((size_t)nslots * kBT * kBT * sizeof(double)));
-    M->nslots = nslots;
-    M->plan_m = ctx->m;
-    M->plan_nctas = nctas;
+    DDB_TRY(M->partials.reserve((size_t)nslots * kBT * kBT * sizeof(double)));  // grows only: valid for every kept plan
+    P->nslots = nslots;
+    P->m = ctx->m;
+    P->nctas = nctas;
+    P->stamp = ++M->clock;
+    *out = P;
     return DDB_OK;
 }
 
@@ -520,14 +542,15 @@ int gram_moment_run(ddb_ctx* ctx, double* dPacked, bool* handled) {
     MomentState* M = ctx->moment;
     if (M->lib_version != ctx->lib_version || M->k != k || M->n_t != n_t) DDB_TRY(install_library(ctx, M));
     if (!M->eligible) return DDB_OK;
-    if (M->plan_m != ctx->m || M->plan_nctas != ctx->sm_count) DDB_TRY(build_wave_plan(ctx, M));
+    MomentState::DevPlan* P = nullptr;
+    DDB_TRY(build_wave_plan(ctx, M, &P));
     // the library's own factor table (the rss / residual passes evaluate the real terms)
     if (ctx->factors_nt != n_t) DDB_TRY(gram_ensure_factors(ctx, (k + n_t + kBT - 1) / kBT * kBT));
     if (!dPacked) {
         DDB_TRY(ctx->d_packed.reserve((size_t)ddb_gram_count(ctx) * sizeof(double)));
         dPacked = ctx->d_packed.as<double>();
     }
-    unsigned char* base = static_cast<unsigned char*>(M->plan.p);
+    unsigned char* base = static_cast<unsigned char*>(P->buf.p);
     GramArgs a;
     a.X = ctx->dX;
     a.Y = ctx->dY;
@@ -537,13 +560,13 @@ int gram_moment_run(ddb_ctx* ctx, double* dPacked, bool* handled) {
     a.kaug = M->nvirt;
     a.factors = M->factors.as<uint16_t>();
     a.segs = reinterpret_cast<const GramSegment*>(base);
-    a.cta_seg_begin = reinterpret_cast<const int32_t*>(base + M->off_cta);
+    a.cta_seg_begin = reinterpret_cast<const int32_t*>(base + P->off_cta);
     a.partials = M->partials.as<double>();
     DDB_CUDA_TRY(cudaEventRecord(ctx->ev[0], ctx->stream));
     DDB_TRY(gram_launch_bt128(ctx, a, ctx->sm_count));
     const int64_t count = ddb_gram_count(ctx);
     moment_gather_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(
-        M->partials.as<double>(), reinterpret_cast<const int32_t*>(base + M->off_psb), M->src.as<int32_t>(), count,
+        M->partials.as<double>(), reinterpret_cast<const int32_t*>(base + P->off_psb), M->src.as<int32_t>(), count,
         dPacked);
     DDB_CUDA_TRY(cudaGetLastError());
     DDB_CUDA_TRY(cudaEventRecord(ctx->ev[1], ctx->stream));
@@ -596,7 +619,7 @@ void moment_free(ddb_ctx* ctx) {
     if (ctx->moment) {
         ctx->moment->factors.release();
         ctx->moment->src.release();
-        ctx->moment->plan.release();
+        for (auto& pl : ctx->moment->plans) pl.buf.release();
         ctx->moment->partials.release();
         delete ctx->moment;
         ctx->moment = nullptr;

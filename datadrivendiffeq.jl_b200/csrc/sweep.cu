@@ -419,33 +419,14 @@ __global__ void __launch_bounds__(256) chol_solve_kernel(const double* Lbase, si
     for (int i = tid; i < na; i += blockDim.x) zg[i] = z[i];
 }
 
-// Entry points for other translation units (dmd.cu): one matrix, many right-hand sides.
-int chol_factor_shared(ddb_ctx* ctx, double* A, int k, int* d_fail, int* launches) {
-    return chol_batched(ctx, A, 0, k, nullptr, k, 1, d_fail, launches);
-}
-int trsm_gemm_solve(ddb_ctx* ctx, const double* L, size_t ld, int k, double* Z, int nrhs, int* launches);
-
-int chol_solve_many(ddb_ctx* ctx, const double* L, int k, double* Z, int nrhs) {
-    // many right-hand sides: blocked substitution whose bulk is DMMA GEMM (trsm.cu)
-    const char* tenv = getenv("DDB_TRSM_GEMM");
-    if ((tenv ? atoi(tenv) != 0 : true) && nrhs >= 256 && k >= 256) return trsm_gemm_solve(ctx, L, (size_t)k, k, Z, nrhs, nullptr);
-    const size_t solve_smem = ((size_t)((k + 31) / 32) * 32 + 32 * 33) * sizeof(double);
-    if (solve_smem > 200 * 1024) {
-        set_error("triangular solver: order %d exceeds the shared-memory right-hand-side buffer", k);
-        return DDB_UNSUPPORTED;
-    }
-    const size_t smem4 = ((size_t)4 * ((k + 31) / 32) * 32 + 32 * 33) * sizeof(double);
-    if (nrhs >= 4 * ctx->sm_count && smem4 <= 200 * 1024) {  // many right-hand sides: four per CTA share every load of L
-        DDB_CUDA_TRY(cudaFuncSetAttribute(chol_solve_kernel_t<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
-        chol_solve_kernel_t<4><<<dim3((nrhs + 3) / 4, 1), 256, smem4, ctx->stream>>>(L, 0, k, nullptr, k, Z, (size_t)k, nrhs,
-                                                                                    nullptr, nullptr);
-    } else {
-        DDB_CUDA_TRY(cudaFuncSetAttribute(chol_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
-        chol_solve_kernel<<<dim3(nrhs, 1), 256, solve_smem, ctx->stream>>>(L, 0, k, nullptr, k, Z, (size_t)k, nrhs, nullptr, nullptr);
-    }
-    DDB_CUDA_TRY(cudaGetLastError());
-    return DDB_OK;
-}
+// chol.cu / trsm.cu: blocked Cholesky with DMMA trailing updates and the GEMM-based substitution
+int chol128_batched(ddb_ctx* ctx, double* base, size_t stride, int ld, const int* d_na, int na_max, int batch, int* d_fail,
+                    int extra, int xrow, int* launches);
+int chol_back_batched(ddb_ctx* ctx, double* base, size_t stride, int ld, const int* d_na, int na_max, int batch, int yrow0,
+                      int nrhs, double* xout, size_t xstride_b, size_t xstride_r, const int* xmap, int* launches);
+int chol_factor_shared(ddb_ctx* ctx, double* A, int k, int* d_fail, int extra, int* launches);
+int chol_solve_many(ddb_ctx* ctx, const double* L, int k, double* Z, int nrhs, int* launches);
+void comm_collect_time(ddb_ctx* ctx);  // comm.cu: duration of the last queued all-reduce -> timings (after a sync)
 
 // ---------------------------------------------------------------------------------------------
 // per-target state and the shared post-solve step logic
@@ -660,7 +641,7 @@ __global__ void implicit_prep_kernel(double* __restrict__ Ninv, double* __restri
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (size_t)k * k) return;
     const int e = (int)(t / k), i = (int)(t % k);
-    Ninv[t] = (e == i) ? 1.0 : 0.0;
+    if (Ninv) Ninv[t] = (e == i) ? 1.0 : 0.0;
     if (z && e == i) z[t] = 0.0;
 }
 
@@ -921,7 +902,7 @@ __global__ void __launch_bounds__(256) stlsq_small_kernel(SweepDev S, int small_
 // big path, STLSQ: gather masked systems of the flagged targets into global workspaces
 // grid (row splits, number of flagged targets); dynamic shared memory: k ints
 __global__ void __launch_bounds__(256) stlsq_big_gather_kernel(SweepDev S, const int* big_list, double* ws,
-                                                               size_t ws_stride, int* idx_all, int* na_out) {
+                                                               size_t ws_stride, int* idx_all, int* na_out, int rhs_row) {
     const int slot = blockIdx.y;
     const int e = big_list[slot];
     const int k = S.k, W = S.W;
@@ -956,7 +937,10 @@ __global__ void __launch_bounds__(256) stlsq_big_gather_kernel(SweepDev S, const
         if (threadIdx.x == 0) na_out[slot] = na;
         for (int i = threadIdx.x; i < na; i += blockDim.x) idx[i] = sidx[i];
         for (int i = threadIdx.x; i < k; i += blockDim.x) xp[i] = x[i];  // X_prev .= X
-        for (int i = threadIdx.x; i < na; i += blockDim.x) z[i] = rs[sidx[i]];
+        // rhs_row: the right-hand side goes to row k of the slot's matrix buffer (it rides through the blocked
+        // factorisation); otherwise to znew (solved in place by chol_solve_kernel)
+        double* zdst = rhs_row ? A + (size_t)k * k : z;
+        for (int i = threadIdx.x; i < na; i += blockDim.x) zdst[i] = rs[sidx[i]];
     }
 }
 
@@ -1359,7 +1343,7 @@ int sweep_run(ddb_ctx* ctx, const ddb_sweep_params* prm, const double* lambdas, 
 
     const size_t kk = (size_t)k * k, nk = (size_t)n_t * k;
     DDB_TRY(S->As.reserve(kk * 8));
-    DDB_TRY(S->Lfac.reserve(kk * 8));
+    DDB_TRY(S->Lfac.reserve((kk + nk) * 8));  // + n_t rows: the right-hand sides ride through the factorisation
     DDB_TRY(S->dinv.reserve((size_t)k * 8));
     DDB_TRY(S->rs.reserve(nk * 8));
     DDB_TRY(S->x.reserve(nk * 8));
@@ -1425,22 +1409,40 @@ int sweep_run(ddb_ctx* ctx, const ddb_sweep_params* prm, const double* lambdas, 
     const char* ienv = getenv("DDB_SWEEP_INVERSE");
     const bool use_inverse = prm->algorithm != DDB_ALG_STLSQ && (ienv ? atoi(ienv) != 0 : k >= 256);
     if (use_inverse) DDB_TRY(S->zsol.reserve(nk * 8));
+    const char* fenv = getenv("DDB_CHOL_FMA");  // 1: the previous 32-wide FMA-pipe factorisation (A/B measurements)
+    const bool chol_fma = fenv && atoi(fenv) != 0;
     if (shared_factor) {
         DDB_CUDA_TRY(cudaMemcpyAsync(S->Lfac.p, S->As.p, kk * 8, cudaMemcpyDeviceToDevice, st));
-        DDB_TRY(chol_batched(ctx, S->Lfac.as<double>(), 0, k, nullptr, k, 1, S->shared_fail.as<int>(), &launches));
-        DDB_CUDA_TRY(cudaMemcpyAsync(S->znew.p, S->rs.p, nk * 8, cudaMemcpyDeviceToDevice, st));
-        if (implicit || use_inverse) {
-            // inverse of the equilibrated matrix (identity right-hand sides); implicit mode also zeroes the own
-            // entry of every target's right-hand side before the shared full solve
-            DDB_TRY(S->Ninv.reserve(kk * 8));
-            implicit_prep_kernel<<<(unsigned)((kk + 255) / 256), 256, 0, st>>>(S->Ninv.as<double>(),
-                                                                               implicit ? S->znew.as<double>() : nullptr, k);
-            DDB_TRY(chol_solve_many(ctx, S->Lfac.as<double>(), k, S->Ninv.as<double>(), k));
-            launches += 2;
+        if (chol_fma) {
+            DDB_CUDA_TRY(cudaMemcpyAsync(S->znew.p, S->rs.p, nk * 8, cudaMemcpyDeviceToDevice, st));
+            if (implicit) {
+                implicit_prep_kernel<<<(unsigned)((kk + 255) / 256), 256, 0, st>>>(nullptr, S->znew.as<double>(), k);
+                ++launches;
+            }
+            DDB_TRY(chol_batched(ctx, S->Lfac.as<double>(), 0, k, nullptr, k, 1, S->shared_fail.as<int>(), &launches));
+            chol_solve_kernel<<<dim3(n_t, 1), 256, solve_smem, st>>>(S->Lfac.as<double>(), 0, k, nullptr, k,
+                                                                     S->znew.as<double>(), (size_t)k, n_t, nullptr, nullptr);
+            ++launches;
+        } else {
+            // the n_t scaled right-hand sides are appended as rows k .. k + n_t - 1 of the factor's buffer: the
+            // factorisation forward-substitutes them on the way, one backward kernel finishes the initial full solve
+            double* zrows = S->Lfac.as<double>() + kk;
+            DDB_CUDA_TRY(cudaMemcpyAsync(zrows, S->rs.p, nk * 8, cudaMemcpyDeviceToDevice, st));
+            if (implicit) {  // zero the own entry of every target's right-hand side
+                implicit_prep_kernel<<<(unsigned)((kk + 255) / 256), 256, 0, st>>>(nullptr, zrows, k);
+                ++launches;
+            }
+            DDB_TRY(chol_factor_shared(ctx, S->Lfac.as<double>(), k, S->shared_fail.as<int>(), n_t, &launches));
+            DDB_TRY(chol_back_batched(ctx, S->Lfac.as<double>(), 0, k, nullptr, k, 1, k, n_t, S->znew.as<double>(), 0, (size_t)k,
+                                      nullptr, &launches));
         }
-        chol_solve_kernel<<<dim3(n_t, 1), 256, solve_smem, st>>>(S->Lfac.as<double>(), 0, k, nullptr, k,
-                                                                 S->znew.as<double>(), (size_t)k, n_t, nullptr, nullptr);
-        ++launches;
+        if (implicit || use_inverse) {
+            // inverse of the equilibrated matrix (identity right-hand sides)
+            DDB_TRY(S->Ninv.reserve(kk * 8));
+            implicit_prep_kernel<<<(unsigned)((kk + 255) / 256), 256, 0, st>>>(S->Ninv.as<double>(), nullptr, k);
+            ++launches;
+            DDB_TRY(chol_solve_many(ctx, S->Lfac.as<double>(), k, S->Ninv.as<double>(), k, &launches));
+        }
     }
     SweepDev D = make_dev(ctx, S);
     if (use_inverse) D.zsol = S->zsol.as<double>();
@@ -1468,18 +1470,27 @@ int sweep_run(ddb_ctx* ctx, const ddb_sweep_params* prm, const double* lambdas, 
             if (nbig == 0) break;
             // ---- big step: targets whose active set does not fit the shared-memory solver ----------
             ++big_steps;
-            DDB_TRY(S->big_ws.reserve((size_t)nbig * kk * 8));
+            const size_t ws_stride = chol_fma ? kk : kk + (size_t)k;  // + one row: the right-hand side
+            DDB_TRY(S->big_ws.reserve((size_t)nbig * ws_stride * 8));
             DDB_TRY(S->big_idx.reserve((size_t)nbig * k * 4));
             list_big_kernel<<<1, 32, 0, st>>>(D.eq, n_t, S->big_list.as<int>(), S->big_list.as<int>() + n_t);
             DDB_CUDA_TRY(cudaMemsetAsync(S->big_fail.p, 0, (size_t)n_t * 4, st));
             stlsq_big_gather_kernel<<<dim3(64, nbig), 256, (size_t)k * sizeof(int), st>>>(
-                D, S->big_list.as<int>(), S->big_ws.as<double>(), kk, S->big_idx.as<int>(), S->big_na.as<int>());
+                D, S->big_list.as<int>(), S->big_ws.as<double>(), ws_stride, S->big_idx.as<int>(), S->big_na.as<int>(),
+                chol_fma ? 0 : 1);
             launches += 2;
-            DDB_TRY(chol_batched(ctx, S->big_ws.as<double>(), kk, k, S->big_na.as<int>(), k, nbig,
-                                 S->big_fail.as<int>(), &launches));
-            chol_solve_kernel<<<dim3(1, nbig), 256, solve_smem, st>>>(S->big_ws.as<double>(), kk, k,
-                                                                      S->big_na.as<int>(), k, S->znew.as<double>(),
-                                                                      (size_t)k, 1, nullptr, S->big_list.as<int>());
+            if (chol_fma) {
+                DDB_TRY(chol_batched(ctx, S->big_ws.as<double>(), kk, k, S->big_na.as<int>(), k, nbig,
+                                     S->big_fail.as<int>(), &launches));
+                chol_solve_kernel<<<dim3(1, nbig), 256, solve_smem, st>>>(S->big_ws.as<double>(), kk, k,
+                                                                          S->big_na.as<int>(), k, S->znew.as<double>(),
+                                                                          (size_t)k, 1, nullptr, S->big_list.as<int>());
+            } else {
+                DDB_TRY(chol128_batched(ctx, S->big_ws.as<double>(), ws_stride, k, S->big_na.as<int>(), k, nbig,
+                                        S->big_fail.as<int>(), 1, k, &launches));
+                DDB_TRY(chol_back_batched(ctx, S->big_ws.as<double>(), ws_stride, k, S->big_na.as<int>(), k, nbig, k, 1,
+                                          S->znew.as<double>(), (size_t)k, 0, S->big_list.as<int>(), nullptr));
+            }
             stlsq_big_finish_kernel<<<nbig, 256, 0, st>>>(D, S->big_list.as<int>(), S->big_idx.as<int>(),
                                                           S->big_na.as<int>(), S->big_fail.as<int>());
             launches += 2;
@@ -1547,6 +1558,7 @@ int sweep_run(ddb_ctx* ctx, const ddb_sweep_params* prm, const double* lambdas, 
             DDB_CUDA_TRY(cudaStreamSynchronize(st));
         }
     }
+    comm_collect_time(ctx);
     float ms_f = 0.f, ms_s = 0.f;
     DDB_CUDA_TRY(cudaEventElapsedTime(&ms_f, ctx->ev[4], ctx->ev[5]));
     DDB_CUDA_TRY(cudaEventElapsedTime(&ms_s, ctx->ev[5], ctx->ev[6]));
@@ -1609,6 +1621,7 @@ int select_run(ddb_ctx* ctx, double* coef, double* lambda_opt, int32_t* iters, d
         DDB_CUDA_TRY(cudaMemcpyAsync(iters_path, S->path_iters.p, (size_t)n_t * L * 4, cudaMemcpyDeviceToHost, st));
     DDB_CUDA_TRY(cudaEventRecord(ctx->ev[6], st));
     DDB_CUDA_TRY(cudaStreamSynchronize(st));
+    comm_collect_time(ctx);
     float a = 0.f, b = 0.f;
     DDB_CUDA_TRY(cudaEventElapsedTime(&a, ctx->ev[4], ctx->ev[5]));
     DDB_CUDA_TRY(cudaEventElapsedTime(&b, ctx->ev[5], ctx->ev[6]));

@@ -98,7 +98,10 @@ __global__ void __launch_bounds__(256, 1) gemm_nt_kernel(double* __restrict__ D,
                 const int c = c0 + col0 + 8 * j + 2 * t + h;
                 if (c < cols) {
                     double* p = D + (size_t)r * ldd + c;
-                    *p = ASSIGN ? acc[i][j][h] : *p - acc[i][j][h];
+                    // subtract: one thread per element and launch -> a reduction (RED.ADD.F64) gives exactly D - acc
+                    // without the load -> subtract -> store round trip
+                    if (ASSIGN) *p = acc[i][j][h];
+                    else atomicAdd(p, -acc[i][j][h]);
                 }
             }
         }
@@ -156,7 +159,16 @@ __global__ void __launch_bounds__(256) transpose_kernel(const double* __restrict
 
 struct TrsmState {
     DevBuf linv, linvT, lt;
+    // chol_factor_shared (below) leaves L' above the diagonal of ITS factor: solves against that factor need no
+    // transposition pass; the inverses of its diagonal blocks are computed on the first such solve
+    DevBuf f_linv, f_linvT;
+    const double* factor = nullptr;
+    int factor_k = 0;
+    bool factor_inv = false;
 };
+
+int chol128_batched(ddb_ctx* ctx, double* base, size_t stride, int ld, const int* d_na, int na_max, int batch, int* d_fail,
+                    int extra, int xrow, int* launches);
 
 template <bool ASSIGN>
 static int launch_gemm(ddb_ctx* ctx, double* D, size_t ldd, const double* A, size_t lda, const double* B, size_t ldb,
@@ -171,32 +183,40 @@ static int launch_gemm(ddb_ctx* ctx, double* D, size_t ldd, const double* A, siz
 }
 
 // Z (nrhs x k, row-major, leading dimension k) <- Z (L L')^-1  i.e. every ROW of Z is solved against the factor
-// L (k x k lower, row-major, leading dimension ld).
-int trsm_gemm_solve(ddb_ctx* ctx, const double* L, size_t ld, int k, double* Z, int nrhs, int* launches) {
-    if (!ctx->trsm) ctx->trsm = new TrsmState();
-    TrsmState* T = ctx->trsm;
+// L (k x k lower, row-major, leading dimension ld).  mirrored: L' lives above the diagonal of the same buffer (as
+// chol128_batched leaves it) -- no transposition pass; linv / linvT: where the inverses of the 128-wide diagonal
+// blocks and their transposes are (or go); have_inv: they are already there.
+static int trsm_gemm_run(ddb_ctx* ctx, const double* L, size_t ld, int k, double* Z, int nrhs, int* launches, bool mirrored,
+                         double* linv, double* linvT, bool have_inv, DevBuf* lt_buf) {
     const int nblk = (k + kGT - 1) / kGT;
-    const size_t ldt = (size_t)k;
-    DDB_TRY(T->linv.reserve((size_t)nblk * kGT * kGT * 8));
-    DDB_TRY(T->linvT.reserve((size_t)nblk * kGT * kGT * 8));
-    DDB_TRY(T->lt.reserve((size_t)k * ldt * 8));
     cudaStream_t st = ctx->stream;
-    const size_t tsmem = (size_t)kGT * (kGT + 1) * sizeof(double);
-    DDB_CUDA_TRY(cudaFuncSetAttribute(tri_inv128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
-    tri_inv128_kernel<<<nblk, 128, tsmem, st>>>(L, ld, k, T->linv.as<double>(), T->linvT.as<double>());
-    transpose_kernel<<<dim3((k + 31) / 32, (k + 31) / 32), 256, 0, st>>>(L, ld, k, T->lt.as<double>(), ldt);
-    int n = 2;
+    int n = 0;
+    if (!have_inv) {
+        const size_t tsmem = (size_t)kGT * (kGT + 1) * sizeof(double);
+        DDB_CUDA_TRY(cudaFuncSetAttribute(tri_inv128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+        tri_inv128_kernel<<<nblk, 128, tsmem, st>>>(L, ld, k, linv, linvT);
+        ++n;
+    }
+    const double* Lt = L;  // Lt[i][j] = L[j][i] for j > i
+    size_t ldt = ld;
+    if (!mirrored) {
+        ldt = (size_t)k;
+        DDB_TRY(lt_buf->reserve((size_t)k * ldt * 8));
+        transpose_kernel<<<dim3((k + 31) / 32, (k + 31) / 32), 256, 0, st>>>(L, ld, k, lt_buf->as<double>(), ldt);
+        ++n;
+        Lt = lt_buf->as<double>();
+    }
     const size_t zs = (size_t)k;
     for (int b = 0; b < nblk; ++b) {  // forward
         const int j0 = b * kGT, nb = std::min(kGT, k - j0), rest = k - j0 - nb;
-        DDB_TRY(launch_gemm<true>(ctx, Z + j0, zs, Z + j0, zs, T->linv.as<double>() + (size_t)b * kGT * kGT, kGT, nrhs, nb, nb));
+        DDB_TRY(launch_gemm<true>(ctx, Z + j0, zs, Z + j0, zs, linv + (size_t)b * kGT * kGT, kGT, nrhs, nb, nb));
         DDB_TRY(launch_gemm<false>(ctx, Z + j0 + nb, zs, Z + j0, zs, L + (size_t)(j0 + nb) * ld + j0, ld, nrhs, rest, nb));
         n += 1 + (rest > 0);
     }
     for (int b = nblk - 1; b >= 0; --b) {  // backward
         const int j0 = b * kGT, nb = std::min(kGT, k - j0);
-        DDB_TRY(launch_gemm<true>(ctx, Z + j0, zs, Z + j0, zs, T->linvT.as<double>() + (size_t)b * kGT * kGT, kGT, nrhs, nb, nb));
-        DDB_TRY(launch_gemm<false>(ctx, Z, zs, Z + j0, zs, T->lt.as<double>() + j0, ldt, nrhs, j0, nb));
+        DDB_TRY(launch_gemm<true>(ctx, Z + j0, zs, Z + j0, zs, linvT + (size_t)b * kGT * kGT, kGT, nrhs, nb, nb));
+        DDB_TRY(launch_gemm<false>(ctx, Z, zs, Z + j0, zs, Lt + j0, ldt, nrhs, j0, nb));
         n += 1 + (j0 > 0);
     }
     DDB_CUDA_TRY(cudaGetLastError());
@@ -204,11 +224,48 @@ int trsm_gemm_solve(ddb_ctx* ctx, const double* L, size_t ld, int k, double* Z, 
     return DDB_OK;
 }
 
+// One matrix, many right-hand sides (the factor every target shares; P of the DMD operator): factorise A (k x k,
+// row-major, both triangles valid on entry) in place; L' is left above the diagonal.  `extra` right-hand sides
+// stored as rows k .. k + extra - 1 of the same buffer are forward-substituted on the way (they end up as L^-1 b;
+// chol_back_batched finishes them).
+int chol_factor_shared(ddb_ctx* ctx, double* A, int k, int* d_fail, int extra, int* launches) {
+    if (!ctx->trsm) ctx->trsm = new TrsmState();
+    TrsmState* T = ctx->trsm;
+    T->factor = nullptr;
+    DDB_TRY(chol128_batched(ctx, A, 0, k, nullptr, k, 1, d_fail, extra, k, launches));
+    T->factor = A;
+    T->factor_k = k;
+    T->factor_inv = false;
+    return DDB_OK;
+}
+
+// Z (nrhs x k row-major) <- Z (L L')^-1 for MANY right-hand sides (the inverse of the ADMM / SR3 iterations,
+// K = Q P^-1 of the DMD path): blocked substitution whose bulk is DMMA GEMM, against a factor of chol_factor_shared
+// (its mirrored L' is used, the block inverses are computed once per factor) or any other row-major lower factor.
+int chol_solve_many(ddb_ctx* ctx, const double* L, int k, double* Z, int nrhs, int* launches) {
+    if (!ctx->trsm) ctx->trsm = new TrsmState();
+    TrsmState* T = ctx->trsm;
+    const int nblk = (k + kGT - 1) / kGT;
+    if (T->factor == L && T->factor_k == k) {
+        DDB_TRY(T->f_linv.reserve((size_t)nblk * kGT * kGT * 8));
+        DDB_TRY(T->f_linvT.reserve((size_t)nblk * kGT * kGT * 8));
+        const bool have = T->factor_inv;
+        T->factor_inv = true;
+        return trsm_gemm_run(ctx, L, (size_t)k, k, Z, nrhs, launches, true, T->f_linv.as<double>(), T->f_linvT.as<double>(), have,
+                             &T->lt);
+    }
+    DDB_TRY(T->linv.reserve((size_t)nblk * kGT * kGT * 8));
+    DDB_TRY(T->linvT.reserve((size_t)nblk * kGT * kGT * 8));
+    return trsm_gemm_run(ctx, L, (size_t)k, k, Z, nrhs, launches, false, T->linv.as<double>(), T->linvT.as<double>(), false, &T->lt);
+}
+
 void trsm_free(ddb_ctx* ctx) {
     if (ctx->trsm) {
         ctx->trsm->linv.release();
         ctx->trsm->linvT.release();
         ctx->trsm->lt.release();
+        ctx->trsm->f_linv.release();
+        ctx->trsm->f_linvT.release();
         delete ctx->trsm;
         ctx->trsm = nullptr;
     }

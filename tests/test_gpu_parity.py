@@ -481,12 +481,23 @@ def test_c4_library_size_relaxed_algorithms_match_oracle_traces(ctx, golden_dir,
     np.testing.assert_array_equal(out.support_path, sp)  # every threshold, every target
     np.testing.assert_array_equal(out.iters_path, g["iters_path"])
     cp = g["coef_path"]
-    assert (np.abs(out.coef_path - cp) <= 1e-9 * np.abs(cp) + 1e-13 * np.abs(cp).max()).all()
+    # Both sides solve a 2145 x 2145 system of condition ~1e6 per iteration (the oracle un-equilibrated through
+    # LAPACK potrs, the device through the explicit inverse of the equilibrated matrix): every entry of an iterate
+    # carries an ABSOLUTE error of ~cond * eps * |x|_max, so the path is compared relative to the largest coefficient
+    # of the iterate (1e-9), the selected model entry by entry below.
+    err = np.abs(out.coef_path - cp)
+    scale = np.abs(cp).max(axis=-1, keepdims=True)
+    worst = float((err / np.maximum(scale, 1e-300)).max())
+    assert worst <= 1e-9, f"coef_path: max |diff| / max|coef of the iterate| = {worst:.3e}, max |diff| = {err.max():.3e}"
     ref = g["coefficients"]
     np.testing.assert_array_equal(out.coefficients != 0, ref != 0)
     nz = ref != 0
-    tol = 1e-9 if alg == "ADMM" else 1e-7  # SR3: numerically tied iterates of neighbouring thresholds
-    assert (np.abs(out.coefficients[nz] - ref[nz]) / np.abs(ref[nz])).max() <= tol
+    # selected model: <= 1e-9 of the target's largest coefficient for every entry (see above), <= 1e-7 entry by entry
+    # (an entry of 4e-3 next to coefficients of 8 carries the same absolute error); SR3 additionally has numerically
+    # tied iterates at neighbouring thresholds
+    dsel = np.abs(out.coefficients - ref)
+    assert (dsel / np.abs(ref).max(axis=1, keepdims=True)).max() <= 1e-9
+    assert (dsel[nz] / np.abs(ref[nz])).max() <= 1e-7
     np.testing.assert_array_equal(out.iterations, g["iterations"])
     if alg == "ADMM":
         np.testing.assert_allclose(out.lambda_opt, g["lambda_opt"], rtol=1e-15)
