@@ -83,6 +83,7 @@ PROTOTYPES = {
     "ddb_ctx_destroy": (C.c_int, [_P]),
     "ddb_last_error": (C.c_char_p, []),
     "ddb_version": (C.c_char_p, []),
+    "ddb_debug_check_guards": (C.c_int, []),
     "ddb_set_library_monomial": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "ddb_upload": (C.c_int, [_P, _P, _P, C.c_int, C.c_int64]),
     "ddb_bind_device": (C.c_int, [_P, _P, _P, C.c_int, C.c_int64]),
@@ -94,6 +95,8 @@ PROTOTYPES = {
     "ddb_permute_samples": (C.c_int, [_P, _P]),
     "ddb_gram_scale_terms": (C.c_int, [_P, _P]),
     "ddb_residual": (C.c_int, [_P, _P, _P]),
+    "ddb_target_stats": (C.c_int, [_P, C.c_int64, _P, _P]),
+    "ddb_group_target_stats": (C.c_int, [_P, _P, _P]),
     "ddb_set_features": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P]),
     "ddb_upload_gram": (C.c_int, [_P, _P, _P, C.c_int, C.c_int64, _P]),
     "ddb_gram_buffer": (C.c_int, [_P, C.POINTER(_P)]),
@@ -136,6 +139,10 @@ PROTOTYPES = {
     "ddb_dmd_gram": (C.c_int, [_P, _P, _P, C.c_int, C.c_int64, _P, _P]),
     "ddb_dmd_operator": (C.c_int, [_P, _P, _P, C.c_int, _P]),
     "ddb_dmd_solve": (C.c_int, [_P, _P, C.c_int, C.c_int64, _P, _P, _P]),
+    "ddb_dmd_residual": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int64, _P]),
+    "ddb_dmd_eig_sym": (C.c_int, [_P, _P, C.c_int, _P]),
+    "ddb_dmd_eig": (C.c_int, [_P, _P, C.c_int, _P, _P]),
+    "ddb_gemm_nt": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int64, _P, C.c_int64, C.c_int, C.c_int, C.c_int]),
     "ddb_gram_plan_describe": (C.c_int64, [C.c_int, C.c_int64, C.c_int, _P, C.c_int64, _P]),
     "ddb_get_timings": (C.c_int, [_P, C.POINTER(Timings)]),
     "ddb_get_stream": (C.c_int, [_P, C.POINTER(_P)]),

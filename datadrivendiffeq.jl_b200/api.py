@@ -449,6 +449,36 @@ class DataDrivenSolution:
     retcode: int
     timings: dict = field(default_factory=dict)
     paths: Optional[SweepOutput] = None
+    # sum(abs2, Y .- mean(Y, dims = 2)) from the device pass ddb_target_stats (None when it was not computed)
+    null_ss: Optional[float] = None
+
+    # -- StatsAPI statistics of a solution (src/solution.jl:105-157) ------------------------------------------
+    def loglikelihood(self) -> float:
+        """``-nobs / 2 * log(rss / nobs)`` (``src/solution.jl:117-121``)."""
+        with np.errstate(divide="ignore"):
+            return float(-self.nobs / 2.0 * np.log(np.float64(self.rss) / self.nobs))
+
+    def nullloglikelihood(self) -> float:
+        """``-nobs / 2 * log(sum(abs2, Y .- mean(Y, dims = 2)) / nobs)`` (``src/solution.jl:139-145``)."""
+        if self.null_ss is None:
+            raise ValueError("the target statistics were not computed for this solution")
+        with np.errstate(divide="ignore"):
+            return float(-self.nobs / 2.0 * np.log(np.float64(self.null_ss) / self.nobs))
+
+    def r2(self) -> float:
+        """Cox-Snell pseudo R^2 (``src/solution.jl:147-157`` -> StatsAPI ``r2(sol, :CoxSnell)``):
+        ``1 - exp(2 (nullloglikelihood - loglikelihood) / nobs)``."""
+        return float(1.0 - np.exp(2.0 * (self.nullloglikelihood() - self.loglikelihood()) / self.nobs))
+
+    def aic(self) -> float:
+        return -2.0 * self.loglikelihood() + 2.0 * self.dof
+
+    def aicc(self) -> float:
+        k, n = self.dof, self.nobs
+        return self.aic() + 2.0 * k * (k + 1.0) / (n - k - 1.0)
+
+    def bic(self) -> float:
+        return -2.0 * self.loglikelihood() + self.dof * float(np.log(self.nobs))
 
     def get_parameter_values(self) -> np.ndarray:
         """Non-zero coefficients in equation-major order (``__build_eqs`` numbering)."""
@@ -724,9 +754,11 @@ def _solve_processed(prob, basis, alg, options, X, Y, paths=False):
     C = best.coefficients / sigma[None, :] if sigma is not None else best.coefficients  # apply_transform (commonsolve.jl:19-21)
     Cr = construct_coefficients(C, options.digits)
     rss_all = float(np.sum(ctx.residual(Cr)))  # what DataDrivenSolution recomputes on all data (src/solution.jl:37-56)
+    t = ctx.timings()
+    null_ss = float(np.sum(ctx.target_stats(m)[1]))
     return DataDrivenSolution(basis=basis, coefficients=Cr, results=results, rss=rss_all, dof=int(np.sum(Cr != 0.0)),
-                              nobs=int(Y.size), retcode=best.retcode, timings=ctx.timings(),
-                              paths=outs[order[0]] if paths else None)
+                              nobs=int(Y.size), retcode=best.retcode, timings=t,
+                              paths=outs[order[0]] if paths else None, null_ss=null_ss)
 
 
 def solve(prob: DataDrivenProblem, basis: Basis, alg: B200Sparse, options: Optional[DataDrivenCommonOptions] = None,
@@ -755,7 +787,9 @@ def solve(prob: DataDrivenProblem, basis: Basis, alg: B200Sparse, options: Optio
         grp.set_features(basis.n_raw, basis.features)
         grp.set_library(basis.exponents)
         out = grp.solve_sparse(X, Y, _params_for(grp, alg.inner, options), alg.inner.thresholds)
-        return _finish_solution(basis, options, out, Y.shape[0], X.shape[1], Y.size, grp.timings(), None)
+        t = grp.timings()
+        null_ss = float(np.sum(grp.target_stats(Y.shape[0])[1]))
+        return _finish_solution(basis, options, out, Y.shape[0], X.shape[1], Y.size, t, None, null_ss)
     ctx = alg.context()
     ctx.set_features(basis.n_raw, basis.features)
     ctx.set_library(basis.exponents)
@@ -776,10 +810,12 @@ def solve(prob: DataDrivenProblem, basis: Basis, alg: B200Sparse, options: Optio
 
         out, m_total = dist.solve_sharded(ctx, X, Y, prm, lambdas, alg.group, paths=paths)
     nobs = int(Y.size if alg.group is None else Y.shape[0] * m_total)
-    return _finish_solution(basis, options, out, Y.shape[0], m_total, nobs, ctx.timings(), out if paths else None)
+    t = ctx.timings()
+    null_ss = float(np.sum(ctx.target_stats(m_total)[1]))  # device pass over the resident targets (collective if sharded)
+    return _finish_solution(basis, options, out, Y.shape[0], m_total, nobs, t, out if paths else None, null_ss)
 
 
-def _finish_solution(basis, options, out, n_t, m_total, nobs, timings, paths_out):
+def _finish_solution(basis, options, out, n_t, m_total, nobs, timings, paths_out, null_ss=None):
     C = out.coefficients
     # __sparse_regression (commonsolve.jl:37-55): trainerror = sum(abs2, Y - C*Theta) = sum of the selected rss
     res = SparseRegressionResult(
@@ -802,4 +838,5 @@ def _finish_solution(basis, options, out, n_t, m_total, nobs, timings, paths_out
         retcode=res.retcode,
         timings=timings,
         paths=paths_out,
+        null_ss=null_ss,
     )

@@ -150,6 +150,14 @@ class Context:
         _lib.check(self._lib.ddb_residual(self._ctx, _lib.ptr(c), _lib.ptr(out)))
         return out
 
+    def target_stats(self, m_total: Optional[int] = None):
+        """``ddb_target_stats``: per-target ``(mean, centred sum of squares)`` of the bound targets (collective on a
+        sharded run; ``m_total`` = samples of all ranks)."""
+        mean = np.zeros(self.n_t)
+        css = np.zeros(self.n_t)
+        _lib.check(self._lib.ddb_target_stats(self._ctx, int(m_total or self.m), _lib.ptr(mean), _lib.ptr(css)))
+        return mean, css
+
     # -- normal-equation blocks -------------------------------------------------------------
     def gram_count(self) -> int:
         return int(self._lib.ddb_gram_count(self._ctx))
@@ -353,6 +361,26 @@ class Context:
         """K = Q P^-1 (DMDPINV through the normal equations), all device n x n column-major buffers."""
         _lib.check(self._lib.ddb_dmd_operator(self._ctx, C.c_void_p(dP), C.c_void_p(dQ), int(n), C.c_void_p(dK)))
 
+    def dmd_residual(self, dX: int, dZ: int, dM: int, n_in: int, n_out: int, m: int) -> float:
+        """``ddb_dmd_residual``: ``|| Z - M X ||_F^2`` over resident snapshots (device pointers, column-major)."""
+        out = C.c_double(0.0)
+        _lib.check(self._lib.ddb_dmd_residual(self._ctx, C.c_void_p(dX), C.c_void_p(dZ), C.c_void_p(dM), int(n_in), int(n_out),
+                                              int(m), C.byref(out)))
+        return float(out.value)
+
+    def dmd_eig_sym(self, dA: int, n: int, dW: int):
+        """``ddb_dmd_eig_sym``: eigenvectors overwrite the symmetric matrix at ``dA``, ascending eigenvalues to ``dW``."""
+        _lib.check(self._lib.ddb_dmd_eig_sym(self._ctx, C.c_void_p(dA), int(n), C.c_void_p(dW)))
+
+    def dmd_eig(self, dA: int, n: int, dW: int, dVR: Optional[int]):
+        """``ddb_dmd_eig``: eigenvalues (complex interleaved) and packed right eigenvectors of a general real matrix."""
+        _lib.check(self._lib.ddb_dmd_eig(self._ctx, C.c_void_p(dA), int(n), C.c_void_p(dW), C.c_void_p(dVR) if dVR else None))
+
+    def gemm_nt(self, dD: int, ldd: int, dA: int, lda: int, dB: int, ldb: int, rows: int, cols: int, K: int):
+        """``ddb_gemm_nt``: row-major ``D = A B'`` on the library's DMMA kernel."""
+        _lib.check(self._lib.ddb_gemm_nt(self._ctx, C.c_void_p(dD), int(ldd), C.c_void_p(dA), int(lda), C.c_void_p(dB), int(ldb),
+                                         int(rows), int(cols), int(K)))
+
     def dmd_solve(self, x: np.ndarray, want_K: bool = True):
         """``ddb_dmd_solve``: host snapshots ``x`` (n x (m+1)) -> ``(P, Q, K)`` with K = Q P^-1 (DMDPINV)."""
         x = _f(x)
@@ -450,6 +478,13 @@ class Group:
                                              _lib.ptr(flags))
         )
         return SweepOutput(np.ascontiguousarray(coef), lam, iters, rss, dof, flags)
+
+    def target_stats(self, n_t: int):
+        """``ddb_group_target_stats`` over the shards the last ``solve_sparse`` left resident."""
+        mean = np.zeros(n_t)
+        css = np.zeros(n_t)
+        _lib.check(self._lib.ddb_group_target_stats(self._g, _lib.ptr(mean), _lib.ptr(css)))
+        return mean, css
 
     def timings(self) -> dict:
         t = _lib.Timings()

@@ -5,6 +5,7 @@
 #include <cstring>
 #include <cmath>
 #include <condition_variable>
+#include <map>
 #include <mutex>
 #include <thread>
 
@@ -19,27 +20,82 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+// ---- guard zones (DDB_GUARD=1): see DevBuf in common.cuh ----------------------------------------------------------
+constexpr size_t kGuard = 256;
+constexpr int kGuardByte = 0xA5;
+static bool guard_on() {
+    static const bool on = [] {
+        const char* e = getenv("DDB_GUARD");
+        return e && atoi(e) != 0;
+    }();
+    return on;
+}
+static std::mutex g_guard_mutex;
+static std::map<void*, size_t> g_guard_live;  // user pointer -> user bytes
+
 int DevBuf::reserve(size_t need) {
     if (need <= bytes && p) return DDB_OK;
-    if (p) {
-        cudaFree(p);
-        p = nullptr;
-        bytes = 0;
-    }
+    release();
     if (need == 0) need = 16;
-    cudaError_t e = cudaMalloc(&p, need);
+    const size_t pad = guard_on() ? kGuard : 0;
+    void* raw = nullptr;
+    cudaError_t e = cudaMalloc(&raw, need + 2 * pad);
     if (e != cudaSuccess) {
         set_error("cudaMalloc(%zu bytes) failed: %s", need, cudaGetErrorString(e));
         p = nullptr;
         return e == cudaErrorMemoryAllocation ? DDB_OUT_OF_MEMORY : DDB_CUDA_ERROR;
     }
+    if (pad) {
+        cudaMemset(raw, kGuardByte, pad);
+        cudaMemset(static_cast<char*>(raw) + pad + need, kGuardByte, pad);
+        std::lock_guard<std::mutex> lk(g_guard_mutex);
+        g_guard_live[static_cast<char*>(raw) + pad] = need;
+    }
+    p = static_cast<char*>(raw) + pad;
     bytes = need;
     return DDB_OK;
 }
 void DevBuf::release() {
-    if (p) cudaFree(p);
+    if (p) {
+        if (guard_on()) {
+            {
+                std::lock_guard<std::mutex> lk(g_guard_mutex);
+                g_guard_live.erase(p);
+            }
+            cudaFree(static_cast<char*>(p) - kGuard);
+        } else {
+            cudaFree(p);
+        }
+    }
     p = nullptr;
     bytes = 0;
+}
+
+// number of live allocations whose guard zones were overwritten (0 without DDB_GUARD); the first one is described
+// in the error message
+static int check_guards() {
+    if (!guard_on()) return 0;
+    cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> lk(g_guard_mutex);
+    int bad = 0;
+    std::vector<unsigned char> h(2 * kGuard);
+    for (const auto& kv : g_guard_live) {
+        char* user = static_cast<char*>(kv.first);
+        if (cudaMemcpy(h.data(), user - kGuard, kGuard, cudaMemcpyDeviceToHost) != cudaSuccess ||
+            cudaMemcpy(h.data() + kGuard, user + kv.second, kGuard, cudaMemcpyDeviceToHost) != cudaSuccess) {
+            cudaGetLastError();
+            continue;  // an allocation of another device's context: checked when that device is current
+        }
+        for (size_t i = 0; i < 2 * kGuard; ++i)
+            if (h[i] != kGuardByte) {
+                if (!bad)
+                    set_error("guard zone %s a %zu-byte allocation was overwritten (offset %zu)", i < kGuard ? "before" : "after",
+                              kv.second, i < kGuard ? i : i - kGuard);
+                ++bad;
+                break;
+            }
+    }
+    return bad;
 }
 
 int gram_run(ddb_ctx* ctx, double* dPacked);
@@ -75,6 +131,8 @@ extern "C" {
 
 const char* ddb_last_error(void) { return g_error; }
 const char* ddb_version(void) { return "ddb200 0.2 (sm_100a)"; }
+
+int ddb_debug_check_guards(void) { return check_guards(); }
 
 int ddb_ctx_create(int device, ddb_ctx** out) {
     if (!out) {
@@ -132,6 +190,7 @@ int ddb_ctx_destroy(ddb_ctx* ctx) {
     ctx->d_chunk_packed.release();
     ctx->d_term_scale.release();
     ctx->d_resid.release();
+    ctx->d_stats.release();
     ctx->d_resid_terms.release();
     ctx->d_resid_partials.release();
     ctx->d_feat.release();

@@ -393,6 +393,36 @@ int ddb_group_solve_sparse(ddb_group* g, const double* X, const double* Y, int n
     return DDB_OK;
 }
 
+int ddb_group_target_stats(ddb_group* g, double* mean, double* css) {
+    if (!g || g->ctxs.empty() || !mean || !css) {
+        set_error("ddb_group_target_stats: null argument");
+        return DDB_INVALID_ARG;
+    }
+    const int N = (int)g->ctxs.size();
+    int64_t m_total = 0;
+    for (ddb_ctx* c : g->ctxs) m_total += c->m;
+    const int n_t = g->ctxs[0]->n_t;
+    std::vector<int> status(N, DDB_OK);
+    std::vector<std::string> message(N);
+    std::vector<std::vector<double>> mn(N, std::vector<double>(std::max(1, n_t))), cs(N, std::vector<double>(std::max(1, n_t)));
+    auto work = [&](int r) {
+        cudaSetDevice(g->ctxs[r]->device);
+        status[r] = ddb_target_stats(g->ctxs[r], m_total, mn[r].data(), cs[r].data());
+        if (status[r] != DDB_OK) message[r] = last_error_message();
+    };
+    std::vector<std::thread> th;
+    for (int r = 1; r < N; ++r) th.emplace_back(work, r);
+    work(0);
+    for (auto& t : th) t.join();
+    for (int r = 0; r < N; ++r)
+        if (status[r] != DDB_OK) {
+            set_error("rank %d (device %d): %s", r, g->ctxs[r]->device, message[r].c_str());
+            return status[r];
+        }
+    for (int e = 0; e < n_t; ++e) mean[e] = mn[0][e], css[e] = cs[0][e];
+    return DDB_OK;
+}
+
 int ddb_group_get_timings(const ddb_group* g, ddb_timings* out) {
     if (!g || g->ctxs.empty() || !out) {
         set_error("ddb_group_get_timings: null argument");

@@ -28,7 +28,9 @@ void set_error(const char* fmt, ...);
         if (s__ != DDB_OK) return s__; \
     } while (0)
 
-// A device allocation that grows on demand and is released with the context.
+// A device allocation that grows on demand and is released with the context.  With DDB_GUARD=1 in the environment
+// every allocation is bracketed by 256-byte guard zones filled with a pattern; ddb_debug_check_guards() verifies them
+// (the pool's compute-sanitizer is closed, so out-of-bounds writes are caught this way in the test suite).
 struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
@@ -120,6 +122,7 @@ struct ddb_ctx {
     // term normalisation (ddb_gram_scale_terms): the blocks in d_packed are those of Theta_j / scale_j
     ddb::DevBuf d_term_scale;
     bool term_scale_on = false;
+    ddb::DevBuf d_stats;                 // ddb_target_stats scratch
     // ddb_residual scratch
     ddb::DevBuf d_resid, d_resid_terms, d_resid_partials;
     // sample view (ddb_set_sample_range): dX / dY / m above describe the view; the whole data set is kept here

@@ -25,14 +25,11 @@ __device__ __forceinline__ void cp8(double* dst, const double* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
 
-// D[r][c] (ASSIGN ? = : -=) sum_k A[r][k] B[c][k],  r < rows, c < cols, k < K.  D may alias A when cols <= 128
-// (every CTA reads its rows of A completely before it writes).
-template <bool ASSIGN>
-__global__ void __launch_bounds__(256, 1) gemm_nt_kernel(double* __restrict__ D, size_t ldd, const double* A, size_t lda,
-                                                         const double* __restrict__ B, size_t ldb, int rows, int cols, int K) {
-    extern __shared__ __align__(16) double gsm[];
+// acc (this warp's 64 x 32 patch of the 128 x 128 tile at (r0, c0)) = sum_k A[r][k] B[c][k],  r < rows, c < cols, k < K:
+// K in chunks of 32 through a double-buffered cp.async ring, 32 DMMA.8x8x4 accumulators per warp.
+__device__ __forceinline__ void gemm_nt_tile(double (&acc)[8][4][2], double* gsm, const double* A, size_t lda,
+                                             const double* __restrict__ B, size_t ldb, int rows, int cols, int K, int r0, int c0) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int r0 = blockIdx.y * kGT, c0 = blockIdx.x * kGT;
     const int g = lane >> 2, t = lane & 3;
     const int row0 = (warp >> 2) * 64, col0 = (warp & 3) * 32;
     const int nchunks = (K + kGK - 1) / kGK;
@@ -55,7 +52,6 @@ __global__ void __launch_bounds__(256, 1) gemm_nt_kernel(double* __restrict__ D,
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
-    double acc[8][4][2];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
@@ -87,6 +83,20 @@ __global__ void __launch_bounds__(256, 1) gemm_nt_kernel(double* __restrict__ D,
         }
         __syncthreads();  // the buffer is refilled by the next iteration's stage_load
     }
+}
+
+// D[r][c] (ASSIGN ? = : -=) sum_k A[r][k] B[c][k],  r < rows, c < cols, k < K.  D may alias A when cols <= 128
+// (every CTA reads its rows of A completely before it writes).
+template <bool ASSIGN>
+__global__ void __launch_bounds__(256, 1) gemm_nt_kernel(double* __restrict__ D, size_t ldd, const double* A, size_t lda,
+                                                         const double* __restrict__ B, size_t ldb, int rows, int cols, int K) {
+    extern __shared__ __align__(16) double gsm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r0 = blockIdx.y * kGT, c0 = blockIdx.x * kGT;
+    const int g = lane >> 2, t = lane & 3;
+    const int row0 = (warp >> 2) * 64, col0 = (warp & 3) * 32;
+    double acc[8][4][2];
+    gemm_nt_tile(acc, gsm, A, lda, B, ldb, rows, cols, K, r0, c0);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int r = r0 + row0 + 8 * i + g;
@@ -106,6 +116,59 @@ __global__ void __launch_bounds__(256, 1) gemm_nt_kernel(double* __restrict__ D,
             }
         }
     }
+}
+
+// partial[blockIdx.y * gridDim.x + blockIdx.x] = sum over the tile of (Z[r][c] - sum_k A[r][k] B[c][k])^2: the exact
+// residual sum of squares of a linear model, prediction never written to memory (fixed-order sums: reproducible).
+__global__ void __launch_bounds__(256, 1) gemm_nt_resid_kernel(const double* __restrict__ Z, size_t ldz, const double* A, size_t lda,
+                                                               const double* __restrict__ B, size_t ldb, int rows, int cols, int K,
+                                                               double* __restrict__ partial) {
+    extern __shared__ __align__(16) double gsm[];
+    __shared__ double wsum[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r0 = blockIdx.y * kGT, c0 = blockIdx.x * kGT;
+    const int g = lane >> 2, t = lane & 3;
+    const int row0 = (warp >> 2) * 64, col0 = (warp & 3) * 32;
+    double acc[8][4][2];
+    gemm_nt_tile(acc, gsm, A, lda, B, ldb, rows, cols, K, r0, c0);
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = r0 + row0 + 8 * i + g;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int c = c0 + col0 + 8 * j + 2 * t + h;
+                if (r < rows && c < cols) {
+                    const double e = Z[(size_t)r * ldz + c] - acc[i][j][h];
+                    s = fma(e, e, s);
+                }
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) wsum[warp] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < 8; ++w) tot += wsum[w];
+        partial[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = tot;
+    }
+}
+
+__global__ void sum_partials_kernel(const double* __restrict__ partial, int64_t count, double* __restrict__ out) {
+    // one CTA, fixed order: thread t adds entries t, t + 1024, ...; then a fixed tree
+    __shared__ double red[1024];
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < count; i += 1024) s += partial[i];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = red[0];
 }
 
 // Inverse of every 128-wide diagonal block of the lower factor L (block b: rows/cols 128 b ...): thread c
@@ -259,6 +322,27 @@ int chol_solve_many(ddb_ctx* ctx, const double* L, int k, double* Z, int nrhs, i
     return trsm_gemm_run(ctx, L, (size_t)k, k, Z, nrhs, launches, false, T->linv.as<double>(), T->linvT.as<double>(), false, &T->lt);
 }
 
+// rss = || Z - A B' ||_F^2 for row-major A (rows x K), B (cols x K), Z (rows x cols); device scalar out
+int gemm_nt_residual(ddb_ctx* ctx, const double* Z, size_t ldz, const double* A, size_t lda, const double* B, size_t ldb, int64_t rows,
+                     int cols, int K, double* d_partials, double* d_out) {
+    const size_t smem = 2 * (size_t)kGStage * sizeof(double);
+    DDB_CUDA_TRY(cudaFuncSetAttribute(gemm_nt_resid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t ty = (rows + kGT - 1) / kGT;
+    const int tx = (cols + kGT - 1) / kGT;
+    int64_t done = 0;
+    // the grid's y extent is limited to 65535 tiles: slabs of rows, partial sums appended
+    for (int64_t y0 = 0; y0 < ty; y0 += 65535) {
+        const int64_t ny = std::min<int64_t>(65535, ty - y0);
+        const int64_t r_lo = y0 * kGT, r_n = std::min<int64_t>(rows - r_lo, ny * kGT);
+        gemm_nt_resid_kernel<<<dim3(tx, (unsigned)ny), 256, smem, ctx->stream>>>(Z + r_lo * ldz, ldz, A + r_lo * lda, lda, B, ldb,
+                                                                                 (int)r_n, cols, K, d_partials + done);
+        done += ny * tx;
+    }
+    sum_partials_kernel<<<1, 1024, 0, ctx->stream>>>(d_partials, done, d_out);
+    DDB_CUDA_TRY(cudaGetLastError());
+    return DDB_OK;
+}
+
 void trsm_free(ddb_ctx* ctx) {
     if (ctx->trsm) {
         ctx->trsm->linv.release();
@@ -272,3 +356,17 @@ void trsm_free(ddb_ctx* ctx) {
 }
 
 }  // namespace ddb
+
+extern "C" int ddb_gemm_nt(ddb_ctx* ctx, double* dD, int64_t ldd, const double* dA, int64_t lda, const double* dB, int64_t ldb,
+                           int rows, int cols, int K) {
+    using namespace ddb;
+    if (!ctx || !dD || !dA || !dB || rows <= 0 || cols <= 0 || K <= 0 || ldd < cols || lda < K || ldb < K) {
+        set_error("ddb_gemm_nt: null pointer, non-positive size or leading dimension smaller than the row length");
+        return DDB_INVALID_ARG;
+    }
+    DDB_CUDA_TRY(cudaSetDevice(ctx->device));
+    DDB_TRY(launch_gemm<true>(ctx, dD, (size_t)ldd, dA, (size_t)lda, dB, (size_t)ldb, rows, cols, K));
+    DDB_CUDA_TRY(cudaGetLastError());
+    DDB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return DDB_OK;
+}

@@ -105,8 +105,11 @@ typedef struct ddb_timings {
 int ddb_ctx_create(int device, ddb_ctx** out);
 int ddb_ctx_destroy(ddb_ctx* ctx);
 const char* ddb_last_error(void);
-/* Library version string, e.g. "ddb200 0.1 (sm_100a)". */
+/* Library version string, e.g. "ddb200 0.2 (sm_100a)". */
 const char* ddb_version(void);
+/* Debugging aid: with DDB_GUARD=1 in the environment every device allocation of the library is bracketed by guard
+ * zones; returns how many live allocations had theirs overwritten (0 = clean; always 0 without DDB_GUARD). */
+int ddb_debug_check_guards(void);
 
 /* ---- candidate library (replaces Basis code generation + evaluation) ------------------------- */
 
@@ -208,6 +211,12 @@ int ddb_set_sample_range(ddb_ctx* ctx, int64_t first, int64_t last);
 int ddb_permute_samples(ddb_ctx* ctx, const int64_t* perm);
 int ddb_gram_scale_terms(ddb_ctx* ctx, const double* scale);
 int ddb_residual(ddb_ctx* ctx, const double* coef, double* rss);
+/* Per-target mean and centred sum of squares of the bound targets over the current sample view:
+ *   mean[e] = (sum over ALL ranks of sum_s Y[e,s]) / m_total,   css[e] = sum_s (Y[e,s] - mean[e])^2  (summed over ranks),
+ * two HBM passes over Y; with a communicator both sums are all-reduced inside (collective).  What
+ * `nullloglikelihood` / `r2` of a solution need besides rss (src/solution.jl:139-157:
+ * `sum(abs2, Y .- mean(Y, dims = 2))` = sum_e css[e]); replaces their CPU pass over Y.  mean, css: host, n_t each. */
+int ddb_target_stats(ddb_ctx* ctx, int64_t m_total, double* mean, double* css);
 
 /* ---- stage 3: thresholded sweep ---------------------------------------------------------------- */
 
@@ -320,6 +329,8 @@ int ddb_group_solve_sparse(ddb_group* g, const double* X, const double* Y, int n
                            const ddb_sweep_params* params, const double* lambdas, int L, double* coef,
                            double* lambda_opt, int32_t* iters, double* rss, int32_t* dof, uint32_t* support_path,
                            int32_t* flags);
+/* ddb_target_stats over the shards the last ddb_group_solve_sparse left resident (one host thread per GPU). */
+int ddb_group_target_stats(ddb_group* g, double* mean, double* css);
 /* Stage timings of the last group solve: rank 0's, with the per-rank stages replaced by the slowest rank's. */
 int ddb_group_get_timings(const ddb_group* g, ddb_timings* out);
 
@@ -341,6 +352,33 @@ int ddb_dmd_operator(ddb_ctx* ctx, const double* dP, const double* dQ, int n, do
  * column-major host buffers, each may be NULL.  n must be even.  This is the entry point the Julia glue
  * binds (`B200DMD`); DMDSVD / TOTALDMD / FBDMD follow from P, Q (and S = Y Y') on the host side. */
 int ddb_dmd_solve(ddb_ctx* ctx, const double* x, int n, int64_t m_plus_1, double* P, double* Q, double* K);
+
+/* Exact residual of a fitted linear model over resident snapshots: rss = || Z - M X ||_F^2 with X (n_in x m) and
+ * Z (n_out x m) device, column-major (one snapshot per column) and M (n_out x n_in) device, column-major.  Replaces
+ * `sum(abs2, Z .- C * (K * X + B * U))` behind `rss(::KoopmanResult)` (lib/DataDrivenDMD/src/result.jl:46-59; stack
+ * [X; U] and [K B] for a controlled system); the prediction is formed tile by tile on the tensor pipe and never
+ * written to memory.  rss: host scalar; sum it over the ranks of a sharded run. */
+int ddb_dmd_residual(ddb_ctx* ctx, const double* dX, const double* dZ, const double* dM, int n_in, int n_out, int64_t m,
+                     double* rss);
+
+/* Dense eigen-decompositions of the DMD algorithms (cuSOLVER Xsyevd / Xgeev, bound at run time; device buffers,
+ * column-major):
+ * ddb_dmd_eig_sym: symmetric dA (n x n, lower triangle read) -> eigenvalues ascending in dW (n), eigenvectors
+ *   overwrite dA.  `truncated_svd` through the Gram identity P = X X' = U S^2 U' (algorithms.jl:2-20).
+ * ddb_dmd_eig: general real dA (n x n, destroyed) -> dW = n complex eigenvalues (re, im interleaved: 2 n doubles) and,
+ *   unless dVR is NULL, the right eigenvectors in LAPACK's packed real form (n x n: a real eigenvalue's vector is one
+ *   column, a complex pair j, j + 1 is stored as columns Re v, Im v with v_j = Re + i Im, v_{j+1} = conj).
+ *   `eigen(K)` / `eigen(Atilde)` (algorithms.jl:81, 157). */
+int ddb_dmd_eig_sym(ddb_ctx* ctx, double* dA, int n, double* dW);
+int ddb_dmd_eig(ddb_ctx* ctx, double* dA, int n, double* dW, double* dVR);
+
+/* D (rows x cols) = A (rows x K) * B (cols x K)' for ROW-major device matrices with the given leading dimensions --
+ * the FP64 DMMA product the library's own substitution and operator steps use, exposed for the small dense
+ * compositions of the DMD variants (U' Q U S^-2, TOTALDMD projections; algorithms.jl:147-158, 215-248).
+ * A column-major n x m matrix is a row-major m x n one, so  C = A B  in Julia's layout is this call with the roles
+ * of the operands exchanged. */
+int ddb_gemm_nt(ddb_ctx* ctx, double* dD, int64_t ldd, const double* dA, int64_t lda, const double* dB, int64_t ldb, int rows,
+                int cols, int K);
 
 /* ---- introspection ----------------------------------------------------------------------------- */
 

@@ -70,4 +70,6 @@ from .dmd import (  # noqa: F401
     operator_matrix,
     truncated_svd,
     koopman_solve,
+    koopman_solve_lifted,
+    monomial_jacobian_times,
 )

@@ -100,6 +100,38 @@ def koopman_solve(alg, x: np.ndarray) -> KoopmanResult:
     return KoopmanResult(lam, phi, Kr, C, Q, P, rss, d, n, ll)
 
 
+def koopman_solve_lifted(alg, Theta: np.ndarray, Ytilde: np.ndarray, Z: np.ndarray) -> KoopmanResult:
+    """The same driver (``solve.jl:102-133``) on lifted data as ``get_fit_targets`` hands it over
+    (``solve.jl:3-65``): ``Theta = basis(X)``, ``Ytilde = basis(X shifted)`` (discrete) or ``J_basis(X) DX``
+    (continuous), ``Z`` = the raw targets."""
+    lam, phi = alg(Theta, Ytilde)
+    K = operator_matrix(lam, phi)
+    Q = Ytilde @ Theta.T
+    P = Theta @ Theta.T
+    C = _ldiv(np.ascontiguousarray(Ytilde.T), np.ascontiguousarray(Z.T)).T  # :130  C = Z / Y_
+    Kr = np.real(K) if np.max(np.abs(np.imag(K))) <= 1e-9 * max(1.0, np.max(np.abs(K))) else K
+    R = Z - C @ Kr @ Theta
+    rss = float(np.sum(np.abs(R) ** 2))
+    n = int(Z.size)
+    with np.errstate(divide="ignore"):
+        ll = float(-n / 2 * np.log(np.float64(rss) / n))
+    return KoopmanResult(lam, phi, Kr, C, Q, P, rss, int(np.sum(Kr != 0)), n, ll)
+
+
+def monomial_jacobian_times(exps: np.ndarray, X: np.ndarray, DX: np.ndarray) -> np.ndarray:
+    """``jacobian(basis)(x) * dx`` for a monomial library (``solve.jl:17-32``), column by column."""
+    n, k = exps.shape
+    out = np.zeros((k, X.shape[1]))
+    for j in range(k):
+        for i in range(n):
+            if exps[i, j] == 0:
+                continue
+            e = exps[:, j].astype(np.int64).copy()
+            e[i] -= 1
+            out[j] += exps[i, j] * np.prod(X ** e[:, None], axis=0) * DX[i]
+    return out
+
+
 # ----------------------------------------------------------------------------------------------
 # variants (lib/DataDrivenDMD/src/algorithms.jl:84-93, 160-176, 215-235, 276-292)
 # ----------------------------------------------------------------------------------------------

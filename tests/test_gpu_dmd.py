@@ -205,3 +205,114 @@ def test_c5_state_count_blocks_and_operator():
     assert np.max(np.abs(Kh - Kref)) <= 1e-8 * max(1.0, np.max(np.abs(Kref)))
     # size-independent property: K P = Q (the normal equations the operator solves)
     assert np.max(np.abs(Kh @ P0 - Q0)) <= 1e-9 * np.max(np.abs(Q0))
+
+
+# ------------------------------------------------------------------------------------------------
+# lifted bases and continuous problems (lib/DataDrivenDMD/src/solve.jl:3-65), output map C = Z / Ytilde (:130),
+# eigen-decompositions and residual behind the C ABI
+# ------------------------------------------------------------------------------------------------
+def _vdp_like(m, seed=0):
+    """A discrete nonlinear map whose degree-2 lifting is (nearly) closed: x1' = a x1, x2' = b x2 + c x1^2."""
+    rng = np.random.default_rng(seed)
+    a, b, c = 0.9, 0.5, 0.3
+    cols = []
+    for _ in range(m // 20 + 1):
+        x = rng.uniform(-1, 1, 2)
+        for _ in range(21):
+            cols.append(x.copy())
+            x = np.array([a * x[0], b * x[1] + c * x[0] ** 2])
+    return np.stack(cols[: m + 1], axis=1)
+
+
+@pytest.mark.parametrize("inner_name", ["DMDPINV", "DMDSVD"])
+def test_lifted_discrete_problem(inner_name):
+    x = _vdp_like(800)  # restarts every 21 snapshots: the few pairs across a restart are outliers both sides see alike
+    basis = ddb200.polynomial_basis(2, 2)
+    ex = basis.exponents
+    inner = getattr(ddb200, inner_name)()
+    res = ddb200.solve_dmd(ddb200.DiscreteDataDrivenProblem(x), ddb200.B200DMD(inner), basis=basis)
+    Th = oracle.evaluate_library(ex, x[:, :-1])
+    Yt = oracle.evaluate_library(ex, x[:, 1:])
+    Z = x[:, 1:]
+    ref = oracle.koopman_solve_lifted(getattr(oracle, inner_name)(), Th, Yt, Z)
+    sc = np.sqrt(np.outer(np.diag(ref.P), np.diag(ref.P)))
+    assert np.max(np.abs(res.P - ref.P) / sc) < 1e-12
+    assert np.max(np.abs(res.Q - ref.Q) / sc) < 1e-12
+    assert np.max(np.abs(np.real(res.K) - np.real(ref.K))) <= 1e-7 * max(1.0, np.max(np.abs(ref.K)))
+    assert np.max(np.abs(res.C - ref.C)) <= 1e-7 * max(1.0, np.max(np.abs(ref.C)))
+    assert res.rss == pytest.approx(ref.rss, rel=1e-6, abs=1e-12)
+    assert res.nobs == Z.size
+    np.testing.assert_allclose(np.sort_complex(res.eigenvalues), np.sort_complex(ref.eigenvalues), atol=1e-7)
+
+
+def test_lifted_continuous_problem():
+    """Continuous problem with a degree-2 lifting: Ytilde = J_basis(X) DX (solve.jl:3-34)."""
+    rng = np.random.default_rng(3)
+    m = 1500
+    X = rng.uniform(-1, 1, (2, m))
+    A = np.array([[-0.5, 1.0], [-1.0, -0.3]])
+    DX = A @ X + 0.2 * np.vstack([X[0] * X[1], X[0] ** 2])
+    basis = ddb200.polynomial_basis(2, 2)
+    ex = basis.exponents
+    res = ddb200.solve_dmd(ddb200.ContinuousDataDrivenProblem(X, DX=DX), ddb200.B200DMD(ddb200.DMDPINV()), basis=basis)
+    Th = oracle.evaluate_library(ex, X)
+    Yt = oracle.monomial_jacobian_times(ex, X, DX)
+    ref = oracle.koopman_solve_lifted(oracle.DMDPINV(), Th, Yt, DX)
+    sc = np.sqrt(np.outer(np.diag(ref.P), np.diag(ref.P)))
+    assert np.max(np.abs(res.P - ref.P) / sc) < 1e-12
+    assert np.max(np.abs(res.Q - ref.Q)) < 1e-11 * np.max(np.abs(ref.Q))
+    assert np.max(np.abs(np.real(res.K) - np.real(ref.K))) <= 1e-7 * max(1.0, np.max(np.abs(ref.K)))
+    assert np.max(np.abs(res.C - ref.C)) <= 1e-6 * max(1.0, np.max(np.abs(ref.C)))
+    assert res.rss == pytest.approx(ref.rss, rel=1e-5, abs=1e-10)
+
+
+def test_continuous_identity_lifting():
+    """``solve(ContinuousDataDrivenProblem, DMDPINV())``: Theta = X, Ytilde = Z = DX -> the generator A."""
+    rng = np.random.default_rng(4)
+    A = np.array([[-0.1, 2.0, 0.0, 0.0], [-2.0, -0.1, 0.0, 0.0], [0.0, 0.0, -0.3, 0.5], [0.0, 0.0, -0.5, -0.3]])
+    X = rng.standard_normal((4, 900))
+    DX = A @ X
+    res = ddb200.solve_dmd(ddb200.ContinuousDataDrivenProblem(X, DX=DX), ddb200.B200DMD(ddb200.DMDPINV()))
+    np.testing.assert_allclose(np.real(res.K), A, atol=1e-9)
+    assert res.rss <= 1e-18 * DX.size * 100 and res.nobs == DX.size
+    np.testing.assert_allclose(np.sort_complex(res.eigenvalues), np.sort_complex(np.linalg.eigvals(A)), atol=1e-9)
+
+
+def test_eig_and_residual_entry_points():
+    """``ddb_dmd_eig_sym`` / ``ddb_dmd_eig`` / ``ddb_dmd_residual`` / ``ddb_gemm_nt`` directly (what a Julia caller binds)."""
+    import torch
+
+    rng = np.random.default_rng(8)
+    dev = torch.device("cuda:0")
+    n, m = 130, 700
+    B = rng.standard_normal((n, n))
+    Psym = B @ B.T
+    K = rng.standard_normal((n, n)) / np.sqrt(n)
+    X = rng.standard_normal((n, m))
+    Zm = K @ X + 1e-3 * rng.standard_normal((n, m))
+    with ddb200.Context(0) as ctx:
+        A = torch.from_numpy(Psym.copy()).to(dev)
+        w = torch.empty(n, dtype=torch.float64, device=dev)
+        ctx.dmd_eig_sym(A.data_ptr(), n, w.data_ptr())
+        U = A.T.cpu().numpy()
+        np.testing.assert_allclose(w.cpu().numpy(), np.linalg.eigvalsh(Psym), rtol=1e-10)
+        np.testing.assert_allclose((U * w.cpu().numpy()) @ U.T, Psym, rtol=0, atol=1e-9 * np.abs(Psym).max())
+        Kc = torch.from_numpy(np.ascontiguousarray(K.T)).to(dev)  # column-major K
+        wc = torch.empty(2 * n, dtype=torch.float64, device=dev)
+        vr = torch.empty((n, n), dtype=torch.float64, device=dev)
+        Kwork = Kc.clone()  # the input is destroyed
+        ctx.dmd_eig(Kwork.data_ptr(), n, wc.data_ptr(), vr.data_ptr())
+        lam = wc.cpu().numpy()[0::2] + 1j * wc.cpu().numpy()[1::2]
+        np.testing.assert_allclose(np.sort_complex(lam), np.sort_complex(np.linalg.eigvals(K)), atol=1e-9)
+        V = vr.T.cpu().numpy()
+        j = int(np.argmax(lam.imag > 0))  # a complex pair: columns Re, Im
+        v = V[:, j] + 1j * V[:, j + 1]
+        assert np.linalg.norm(K @ v - lam[j] * v) <= 1e-9 * np.linalg.norm(v)
+        Xd = torch.from_numpy(np.ascontiguousarray(X.T)).to(dev)
+        Zd = torch.from_numpy(np.ascontiguousarray(Zm.T)).to(dev)
+        rss = ctx.dmd_residual(Xd.data_ptr(), Zd.data_ptr(), Kc.data_ptr(), n, n, m)
+        assert rss == pytest.approx(float(np.sum((Zm - K @ X) ** 2)), rel=1e-10)
+        D = torch.empty((m, n), dtype=torch.float64, device=dev)
+        Kr = torch.from_numpy(np.ascontiguousarray(K)).to(dev)
+        ctx.gemm_nt(D.data_ptr(), n, Xd.data_ptr(), n, Kr.data_ptr(), n, m, n, n)  # D = X' K'  (row-major)
+        np.testing.assert_allclose(D.cpu().numpy(), (K @ X).T, rtol=0, atol=1e-12 * np.abs(K @ X).max() + 1e-13)

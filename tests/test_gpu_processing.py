@@ -134,3 +134,46 @@ def test_odd_batch_size_on_a_three_state_problem(ctx):
     ctx.gram()
     G = ctx.gram_download()[0]
     np.testing.assert_allclose(G, Th[:, 125:250] @ Th[:, 125:250].T, rtol=1e-12, atol=1e-9)
+
+
+@pytest.mark.parametrize("n_t,m", [(3, 2000), (1, 77), (64, 5000), (300, 1001)])
+def test_target_stats_kernel(ctx, n_t, m):
+    """``ddb_target_stats``: per-target mean and centred sum of squares (two passes, deterministic), any target count."""
+    rng = np.random.default_rng(n_t + m)
+    X = rng.standard_normal((2, m))
+    Y = 50.0 + rng.standard_normal((n_t, m)) * np.linspace(0.1, 3.0, n_t)[:, None]  # mean >> spread: one-pass sums would cancel
+    ctx.set_features(0, None)
+    ctx.set_library(oracle.polynomial_exponents(2, 1))
+    ctx.upload(X, Y)
+    mean, css = ctx.target_stats()
+    np.testing.assert_allclose(mean, Y.mean(axis=1), rtol=1e-14)
+    np.testing.assert_allclose(css, ((Y - Y.mean(axis=1, keepdims=True)) ** 2).sum(axis=1), rtol=1e-12)
+    m2, c2 = ctx.target_stats()
+    np.testing.assert_array_equal(css, c2)  # bit-reproducible
+    ctx.set_sample_range(10, 60)
+    mean, css = ctx.target_stats(50)
+    np.testing.assert_allclose(css, ((Y[:, 10:60] - Y[:, 10:60].mean(axis=1, keepdims=True)) ** 2).sum(axis=1), rtol=1e-12)
+    ctx.set_sample_range(0, -1)
+
+
+def test_solution_statistics_match_the_reference_formulas(ctx):
+    """StatsAPI statistics of ``DataDrivenSolution`` (``src/solution.jl:105-157``): rss, nobs, loglikelihood,
+    nullloglikelihood, r2 (Cox-Snell), aic / aicc / bic -- from the device passes, against NumPy on the same data."""
+    X, DX = _lorenz(m=1500, noise=0.1)
+    basis = ddb200.polynomial_basis(3, 2)
+    sol = _solve(ctx, basis, X, DX, ddb200.STLSQ(LAMS))
+    Th = oracle.evaluate_library(basis.exponents, X)
+    n = DX.size
+    rss = float(np.sum((DX - sol.results[0].coefficients @ Th) ** 2))
+    ll = -n / 2 * np.log(rss / n)
+    nll = -n / 2 * np.log(np.sum((DX - DX.mean(axis=1, keepdims=True)) ** 2) / n)
+    assert sol.nobs == n
+    assert sol.rss == pytest.approx(rss, rel=1e-9)
+    assert sol.loglikelihood() == pytest.approx(ll, rel=1e-9)
+    assert sol.nullloglikelihood() == pytest.approx(nll, rel=1e-12)
+    assert sol.r2() == pytest.approx(1 - np.exp(2 * (nll - ll) / n), rel=1e-9)
+    k = sol.dof
+    assert sol.aic() == pytest.approx(-2 * ll + 2 * k, rel=1e-9)
+    assert sol.bic() == pytest.approx(-2 * ll + k * np.log(n), rel=1e-9)
+    assert sol.aicc() == pytest.approx(-2 * ll + 2 * k + 2 * k * (k + 1) / (n - k - 1), rel=1e-9)
+    assert 0.99 < sol.r2() <= 1.0  # the reference's own tests assert r2 ~ 1 on identifiable systems
