@@ -33,6 +33,8 @@ from .api import (  # noqa: F401
     chebyshev_basis,
     fourier_basis,
     concat_bases,
+    expression_basis,
+    FeatureSource,
     polynomial_basis,
     solve,
 )

@@ -95,9 +95,14 @@ PROTOTYPES = {
     "ddb_permute_samples": (C.c_int, [_P, _P]),
     "ddb_gram_scale_terms": (C.c_int, [_P, _P]),
     "ddb_residual": (C.c_int, [_P, _P, _P]),
+    "ddb_residual_affine": (C.c_int, [_P, _P, _P, _P]),
+    "ddb_term_minmax": (C.c_int, [_P, _P, _P]),
+    "ddb_gram_affine_terms": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64]),
     "ddb_target_stats": (C.c_int, [_P, C.c_int64, _P, _P]),
     "ddb_group_target_stats": (C.c_int, [_P, _P, _P]),
     "ddb_set_features": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P]),
+    "ddb_set_features_source": (C.c_int, [_P, C.c_int, C.c_int, C.c_char_p, _P, C.c_int]),
+    "ddb_features_source_check": (C.c_int, [C.c_char_p, _P, C.c_int]),
     "ddb_upload_gram": (C.c_int, [_P, _P, _P, C.c_int, C.c_int64, _P]),
     "ddb_gram_buffer": (C.c_int, [_P, C.POINTER(_P)]),
     "ddb_gram_download": (C.c_int, [_P, _P, _P, _P]),

@@ -56,6 +56,24 @@ def _exponent_table(n: int, degree: int) -> np.ndarray:
     return np.ascontiguousarray(np.asarray(vecs, dtype=np.uint8).T)
 
 
+class FeatureSource:
+    """Features written as CUDA C expressions of the raw variables ``x[i]`` (``[states | controls | t]``) and the
+    parameter values ``p[j]`` -- compiled by NVRTC into one feature kernel (``ddb_set_features_source``).  Replaces the
+    per-term code generation of ``DataDrivenFunction`` (``src/basis/build_function.jl:6-38``) for arbitrary symbolic
+    terms and symbolic parameters."""
+
+    def __init__(self, expressions: Sequence[str], params: Optional[Sequence[float]] = None):
+        self.expressions = [str(e) for e in expressions]
+        self.params = np.ascontiguousarray([] if params is None else params, dtype=np.float64)
+
+    def __len__(self):
+        return len(self.expressions)
+
+    @property
+    def body(self) -> str:
+        return "\n".join(f"f[{i}] = ({e});" for i, e in enumerate(self.expressions))
+
+
 @dataclass
 class Basis:
     """A monomial candidate library over ``n`` states: ``exponents[i, j]`` = power of state i in
@@ -118,7 +136,9 @@ class Basis:
             parts = []
             for i in range(self.n_variables):
                 p = int(self.exponents[i, j])
-                if self.features is not None:
+                if isinstance(self.features, FeatureSource):
+                    nm = f"({self.features.expressions[i]})"
+                elif self.features is not None:
                     kind, src, coef = self.features[i]
                     fn = {FEAT_IDENTITY: "", FEAT_SIN: "sin", FEAT_COS: "cos", FEAT_EXP: "exp", FEAT_CHEBYSHEV: "cheb"}[kind]
                     arg = f"x{src + 1}" if coef == 1.0 else f"{coef:g}*x{src + 1}"
@@ -178,6 +198,20 @@ def fourier_basis(n_states: int, coefficients=1) -> Basis:
     return _generator_basis("fourier", n_states, coefficients)
 
 
+def expression_basis(n_raw: int, expressions: Sequence[str], params: Optional[Sequence[float]] = None,
+                     exponents: Optional[np.ndarray] = None) -> Basis:
+    """A library of ARBITRARY terms: every expression is CUDA C in the raw variables ``x[0] .. x[n_raw - 1]`` (states,
+    then controls, then the independent variable, as ``get_fit_targets`` stacks them) and the parameters ``p[j]``
+    -- what ``Basis(eqs, u; parameters = p, iv = t, controls = c)`` is in the reference once Symbolics has generated
+    code for it (``src/basis/build_function.jl:6-38``).  ``exponents`` (n_feat x k) makes the terms monomials OVER the
+    expressions (default: identity, one term per expression)."""
+    fs = FeatureSource(expressions, params)
+    e = np.eye(len(fs), dtype=np.uint8) if exponents is None else np.asarray(exponents)
+    if e.shape[0] != len(fs):
+        raise ValueError("exponents must have one row per expression")
+    return Basis(e, features=fs, n_raw=int(n_raw))
+
+
 def concat_bases(bases: Sequence[Basis]) -> Basis:
     """``Basis([b1; b2; ...], u)``: the union of term lists over the same raw states, duplicates removed
     without reordering (``src/basis/type.jl:91-135``).  Monomial parts are expressed over identity features."""
@@ -190,6 +224,8 @@ def concat_bases(bases: Sequence[Basis]) -> Basis:
             raise ValueError("concat_bases: bases with implicit variables, controls or time are not supported")
         if b.n_states != n_raw:
             raise ValueError("concat_bases: all bases must be over the same states")
+        if isinstance(b.features, FeatureSource):
+            raise ValueError("concat_bases: expression libraries cannot be merged (write one expression list)")
         bf = b.features if b.features is not None else [(FEAT_IDENTITY, i, 1.0) for i in range(n_raw)]
         loc = []
         for f in bf:
@@ -542,9 +578,9 @@ def get_fit_targets(alg: B200Sparse, prob: DataDrivenProblem, basis: Basis):
 def _check_options(options: DataDrivenCommonOptions):
     if options.denoise:
         raise ValueError("B200Sparse: denoise=true (optimal shrinkage of Theta) is not supported: Theta is never materialised")
-    if options.normalize not in (None, "ZScoreTransform"):
-        raise ValueError("B200Sparse: normalize must be None (DataNormalization{Nothing}) or 'ZScoreTransform'; the "
-                         "reference's UnitRangeTransform shifts Theta and is not supported")
+    if options.normalize not in (None, "ZScoreTransform", "UnitRangeTransform"):
+        raise ValueError("B200Sparse: normalize must be None (DataNormalization{Nothing}), 'ZScoreTransform' or "
+                         "'UnitRangeTransform'")
     if options.roundingmode != "RoundToZero":
         raise ValueError("B200Sparse: only RoundToZero post-processing is supported")
     if options.selector not in ("bic", "aic", "aicc", "rss"):
@@ -698,8 +734,19 @@ def _solve_processed(prob, basis, alg, options, X, Y, paths=False):
     m_train = int(round(split * m))  # MLUtils.splitobs(at = split)
     if m_train <= 0:
         raise ValueError("B200Sparse: the training split is empty")
+    unit = options.normalize == "UnitRangeTransform"
+    if unit:
+        # a row of ones rides along as one more target: R[:, n_t] = Theta 1 of every batch view, which the affine
+        # transform of the blocks needs; its own regression is dropped from the results
+        Y = np.vstack([Y, np.ones((1, m))])
     ctx.upload(X, Y)
     sigma = None
+    umin = udiv = None
+    if unit:
+        # fit(UnitRangeTransform, Theta, dims = 2) on ALL samples (data_processing.jl:68-73; commonsolve.jl:128-130)
+        umin, umax = ctx.term_minmax()
+        rng = umax - umin
+        udiv = np.where(rng > 0.0, rng, 1.0)  # divisor = 1 / scale; an infinite scale (constant row) becomes 1
     if options.normalize == "ZScoreTransform":
         ctx.gram()  # over ALL samples: the transform is fitted before the split (commonsolve.jl:128-130)
         G, _R, _yy = ctx.gram_download()
@@ -733,15 +780,26 @@ def _solve_processed(prob, basis, alg, options, X, Y, paths=False):
         ctx.gram()
         if sigma is not None:
             ctx.gram_scale_terms(sigma)
+        if unit:
+            tsum = ctx.gram_download()[1][:, n_t].copy()       # Theta 1 over this view (the ones target)
+            ysum = ctx.target_stats(b1 - b0)[0] * (b1 - b0)     # Y 1
+            ctx.gram_affine_terms(umin, udiv, tsum, ysum, b1 - b0)
         ctx.sweep(prm, lambdas, b1 - b0)
         ctx.rss()
         out = ctx.select(paths=paths)
-        Cs = out.coefficients  # in the scaled space when sigma is set
-        Cu = Cs / sigma[None, :] if sigma is not None else Cs
+        if unit:  # drop the auxiliary ones target
+            out.coefficients, out.lambda_opt, out.iterations = out.coefficients[:n_t], out.lambda_opt[:n_t], out.iterations[:n_t]
+            out.rss, out.dof, out.flags = out.rss[:n_t], out.dof[:n_t], out.flags[:n_t]
+        Cs = out.coefficients  # in the transformed space when a normalisation is set
+        Cu = Cs / sigma[None, :] if sigma is not None else (Cs / udiv[None, :] if unit else Cs)
         testerror = None
         if m_train < m:
             ctx.set_sample_range(m_train, m)
-            testerror = float(np.sum(ctx.residual(Cu)))
+            if unit:  # residual of the transformed-space model on the transformed test rows, evaluated on the raw data
+                off = np.concatenate([-(Cu @ umin), [0.0]])
+                testerror = float(np.sum(ctx.residual_affine(np.vstack([Cu, np.zeros((1, k))]), off)[:n_t]))
+            else:
+                testerror = float(np.sum(ctx.residual(Cu)))
         results.append(SparseRegressionResult(coefficients=Cs, dof=int(np.sum(np.abs(Cs) > 0.0)), lambda_=out.lambda_opt,
                                               iterations=out.iterations, testerror=testerror,
                                               trainerror=float(np.sum(out.rss)), retcode=1 if not np.any(out.flags & 1) else 2))
@@ -751,13 +809,18 @@ def _solve_processed(prob, basis, alg, options, X, Y, paths=False):
                    else results[i].trainerror)  # sort!(results, by = l2error), stable
     results = [results[i] for i in order]
     best = results[0]
-    C = best.coefficients / sigma[None, :] if sigma is not None else best.coefficients  # apply_transform (commonsolve.jl:19-21)
+    if unit:
+        # lib commonsolve.jl:19-21 runs the data transform on the transposed coefficients: (C - min) .* scale, as written
+        C = (best.coefficients - umin[None, :]) / udiv[None, :]
+    else:
+        C = best.coefficients / sigma[None, :] if sigma is not None else best.coefficients  # apply_transform (commonsolve.jl:19-21)
     Cr = construct_coefficients(C, options.digits)
-    rss_all = float(np.sum(ctx.residual(Cr)))  # what DataDrivenSolution recomputes on all data (src/solution.jl:37-56)
+    # what DataDrivenSolution recomputes on all data (src/solution.jl:37-56)
+    rss_all = float(np.sum(ctx.residual(np.vstack([Cr, np.zeros((1, k))]))[:n_t])) if unit else float(np.sum(ctx.residual(Cr)))
     t = ctx.timings()
-    null_ss = float(np.sum(ctx.target_stats(m)[1]))
+    null_ss = float(np.sum(ctx.target_stats(m)[1][:n_t]))
     return DataDrivenSolution(basis=basis, coefficients=Cr, results=results, rss=rss_all, dof=int(np.sum(Cr != 0.0)),
-                              nobs=int(Y.size), retcode=best.retcode, timings=t,
+                              nobs=int(n_t * m), retcode=best.retcode, timings=t,
                               paths=outs[order[0]] if paths else None, null_ss=null_ss)
 
 

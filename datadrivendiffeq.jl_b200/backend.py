@@ -84,6 +84,12 @@ class Context:
         states; ``features`` = sequence of ``(kind, source, coef)``; ``None`` / empty removes the map.
         Uploads and binds then take RAW states."""
         self._imp_k = 0
+        if features is not None and hasattr(features, "body"):  # api.FeatureSource: NVRTC-compiled expressions
+            prm = np.ascontiguousarray(features.params, dtype=np.float64)
+            _lib.check(self._lib.ddb_set_features_source(self._ctx, int(n_raw), len(features), features.body.encode(),
+                                                          _lib.ptr(prm) if prm.size else None, int(prm.size)))
+            self.n_raw = int(n_raw)
+            return
         if not features:
             _lib.check(self._lib.ddb_set_features(self._ctx, 0, 0, None, None, None))
             self.n_raw = 0
@@ -148,6 +154,27 @@ class Context:
         assert c.shape == (self.n_t, self.k)
         out = np.zeros(self.n_t)
         _lib.check(self._lib.ddb_residual(self._ctx, _lib.ptr(c), _lib.ptr(out)))
+        return out
+
+    def term_minmax(self):
+        """``ddb_term_minmax``: ``(min, max)`` of every library term over the current sample view."""
+        mn, mx = np.zeros(self.k), np.zeros(self.k)
+        _lib.check(self._lib.ddb_term_minmax(self._ctx, _lib.ptr(mn), _lib.ptr(mx)))
+        return mn, mx
+
+    def gram_affine_terms(self, shift, scale, tsum, ysum, m_total: int):
+        """``ddb_gram_affine_terms``: the sweep then runs on ``(Theta_j - shift_j) / scale_j`` (UnitRangeTransform)."""
+        a = [np.ascontiguousarray(v, dtype=np.float64) for v in (shift, scale, tsum, ysum)]
+        assert a[0].size == a[1].size == a[2].size == self.k and a[3].size == self.n_t
+        _lib.check(self._lib.ddb_gram_affine_terms(self._ctx, _lib.ptr(a[0]), _lib.ptr(a[1]), _lib.ptr(a[2]), _lib.ptr(a[3]), int(m_total)))
+
+    def residual_affine(self, coef: np.ndarray, offset: np.ndarray) -> np.ndarray:
+        """``ddb_residual_affine``: rss per target of ``Y - (coef Theta + offset)``."""
+        c = np.asfortranarray(coef, dtype=np.float64)
+        o = np.ascontiguousarray(offset, dtype=np.float64)
+        assert c.shape == (self.n_t, self.k) and o.size == self.n_t
+        out = np.zeros(self.n_t)
+        _lib.check(self._lib.ddb_residual_affine(self._ctx, _lib.ptr(c), _lib.ptr(o), _lib.ptr(out)))
         return out
 
     def target_stats(self, m_total: Optional[int] = None):
@@ -442,6 +469,13 @@ class Group:
         _lib.check(self._lib.ddb_group_set_library_monomial(self._g, self.n, self.k, _lib.ptr(e)))
 
     def set_features(self, n_raw: int, features: Optional[Sequence] = None):
+        if features is not None and hasattr(features, "body"):
+            prm = np.ascontiguousarray(features.params, dtype=np.float64)
+            for r in range(self.ngpus):  # one compiled module per context
+                ctx = self._lib.ddb_group_ctx(self._g, r)
+                _lib.check(self._lib.ddb_set_features_source(ctx, int(n_raw), len(features), features.body.encode(),
+                                                              _lib.ptr(prm) if prm.size else None, int(prm.size)))
+            return
         if not features:
             _lib.check(self._lib.ddb_group_set_features(self._g, 0, 0, None, None, None))
             return

@@ -99,7 +99,8 @@ static int check_guards() {
 }
 
 int gram_run(ddb_ctx* ctx, double* dPacked);
-int residual_run(ddb_ctx* ctx, const double* coef, double* rss_out);
+int residual_run(ddb_ctx* ctx, const double* coef, const double* offset, double* rss_out);
+int gram_ensure_factors(ddb_ctx* ctx, int kaug_pad);
 int generate_run(ddb_ctx* ctx, int system_id, int n_states, int64_t m, int64_t first_sample, uint64_t seed,
                  double noise_std);
 void sweep_free(ddb_ctx* ctx);
@@ -112,6 +113,9 @@ int64_t moment_plan_describe(const uint8_t* exps, int n, int k, int n_t, int32_t
                              int64_t tab_cap, int32_t* pairs, int64_t pairs_cap, int64_t* info);
 void trsm_free(ddb_ctx* ctx);
 void comm_free(ddb_ctx* ctx);
+void userfeat_free(ddb_ctx* ctx);
+int userfeat_nfeat(const ddb_ctx* ctx);
+int userfeat_expand(ddb_ctx* ctx, const double* d_raw, int64_t mc, double* out, cudaStream_t st);
 const char* last_error_message() { return g_error; }
 
 }  // namespace ddb
@@ -174,6 +178,7 @@ int ddb_ctx_destroy(ddb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     comm_free(ctx);
+    userfeat_free(ctx);
     sweep_free(ctx);
     dmd_free(ctx);
     ring_free(ctx);
@@ -189,6 +194,8 @@ int ddb_ctx_destroy(ddb_ctx* ctx) {
     ctx->d_plan.release();
     ctx->d_chunk_packed.release();
     ctx->d_term_scale.release();
+    ctx->d_term_shift.release();
+    ctx->d_cand_shift.release();
     ctx->d_resid.release();
     ctx->d_stats.release();
     ctx->d_resid_terms.release();
@@ -267,6 +274,7 @@ __global__ void feature_kernel(const double* __restrict__ raw, int n_raw, const 
 
 // expands raw states [s0, s0 + mc) (device pointer to the first of them) into ctx->own_X rows [s0, ...)
 static int expand_features(ddb_ctx* ctx, const double* d_raw, int64_t s0, int64_t mc, cudaStream_t st) {
+    if (ctx->userfeat) return userfeat_expand(ctx, d_raw, mc, ctx->own_X.as<double>() + s0 * ctx->n, st);
     const int64_t tot = mc * ctx->n;
     feature_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(d_raw, ctx->n_raw, ctx->d_feat.as<FeatDesc>(), ctx->n, mc,
                                                                   ctx->own_X.as<double>() + s0 * ctx->n);
@@ -276,6 +284,7 @@ static int expand_features(ddb_ctx* ctx, const double* d_raw, int64_t s0, int64_
 
 int ddb_set_features(ddb_ctx* ctx, int n_raw, int n_feat, const int32_t* kind, const int32_t* source, const double* coef) {
     CHECK_CTX(ctx);
+    userfeat_free(ctx);  // the fixed feature kinds replace a compiled feature kernel
     if (n_feat == 0) {
         ctx->n_raw = 0;
         ctx->have_gram = false;
@@ -318,7 +327,12 @@ static int check_data_args(ddb_ctx* ctx, const void* X, const void* Y, int n_t, 
         set_error("%s: X, Y must be non-null and n_t, m positive", who);
         return DDB_INVALID_ARG;
     }
-    if (ctx->n_raw > 0 && ctx->d_feat.bytes < (size_t)ctx->n * sizeof(FeatDesc)) {
+    if (ctx->n_raw > 0 && ctx->userfeat && userfeat_nfeat(ctx) != ctx->n) {
+        set_error("%s: the installed library has %d states but the compiled feature kernel writes %d features", who, ctx->n,
+                  userfeat_nfeat(ctx));
+        return DDB_BAD_STATE;
+    }
+    if (ctx->n_raw > 0 && !ctx->userfeat && ctx->d_feat.bytes < (size_t)ctx->n * sizeof(FeatDesc)) {
         set_error("%s: the installed library has %d states but the feature map defines fewer features", who, ctx->n);
         return DDB_BAD_STATE;
     }
@@ -648,13 +662,177 @@ int ddb_gram_scale_terms(ddb_ctx* ctx, const double* scale) {
     DDB_CUDA_TRY(cudaGetLastError());
     DDB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     ctx->term_scale_on = true;
+    ctx->term_shift_on = false;
     ctx->imp_k = 0;
     return DDB_OK;
 }
 
 int ddb_residual(ddb_ctx* ctx, const double* coef, double* rss) {
     CHECK_CTX(ctx);
-    return residual_run(ctx, coef, rss);
+    return residual_run(ctx, coef, nullptr, rss);
+}
+
+int ddb_residual_affine(ddb_ctx* ctx, const double* coef, const double* offset, double* rss) {
+    CHECK_CTX(ctx);
+    return residual_run(ctx, coef, offset, rss);
+}
+
+// ---- min / max of every library term over the current sample view (UnitRangeTransform) ----------------------
+// monotone map double -> signed 64-bit key, so that integer atomicMin / atomicMax order doubles (no NaN in the data:
+// check_domain rejects them)
+__device__ __forceinline__ long long dkey(double v) {
+    const long long b = __double_as_longlong(v);
+    return b >= 0 ? b : (b ^ 0x7FFFFFFFFFFFFFFFLL);
+}
+static double dkey_inv(long long k) {
+    const long long b = k >= 0 ? k : (k ^ 0x7FFFFFFFFFFFFFFFLL);
+    double v;
+    memcpy(&v, &b, 8);
+    return v;
+}
+constexpr int kMMSamples = 32;   // samples per tile
+constexpr int kMMTerms = 16;     // terms per thread (k <= 256 * 16)
+__global__ void __launch_bounds__(256) term_minmax_kernel(const double* __restrict__ X, int n, int64_t m, const uint16_t* __restrict__ factors,
+                                                          int k, long long* __restrict__ kmin, long long* __restrict__ kmax) {
+    extern __shared__ double xs[];  // kMMSamples x (n + 1): the states of the tile, then 1.0 (missing factors)
+    const int tid = threadIdx.x;
+    const int pitch = n + 1;
+    double mn[kMMTerms], mx[kMMTerms];
+#pragma unroll
+    for (int q = 0; q < kMMTerms; ++q) mn[q] = INFINITY, mx[q] = -INFINITY;
+    const int64_t ntiles = (m + kMMSamples - 1) / kMMSamples;
+    for (int64_t tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
+        const int64_t s0 = tl * kMMSamples;
+        const int valid = (int)min((int64_t)kMMSamples, m - s0);
+        __syncthreads();
+        for (int e = tid; e < valid * n; e += 256) xs[(e / n) * pitch + e % n] = X[s0 * n + e];
+        for (int s = tid; s < valid; s += 256) xs[s * pitch + n] = 1.0;
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < kMMTerms; ++q) {
+            const int j = tid + 256 * q;
+            if (j >= k) break;
+            const uint4 w4 = *reinterpret_cast<const uint4*>(factors + (size_t)j * kMaxFactors);
+            const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+            int f[kMaxFactors];
+#pragma unroll
+            for (int d = 0; d < kMaxFactors; ++d) {
+                const uint32_t c = (w[d >> 1] >> (16 * (d & 1))) & 0xFFFFu;
+                f[d] = (c == kNoFactor) ? n : (int)c;
+            }
+            for (int s = 0; s < valid; ++s) {
+                const double* xr = xs + s * pitch;
+                double p = xr[f[0]];
+#pragma unroll
+                for (int d = 1; d < kMaxFactors; ++d) p *= xr[f[d]];
+                mn[q] = fmin(mn[q], p);
+                mx[q] = fmax(mx[q], p);
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < kMMTerms; ++q) {
+        const int j = tid + 256 * q;
+        if (j < k && mn[q] <= mx[q]) {
+            atomicMin(kmin + j, dkey(mn[q]));
+            atomicMax(kmax + j, dkey(mx[q]));
+        }
+    }
+}
+
+int ddb_term_minmax(ddb_ctx* ctx, double* mn, double* mx) {
+    CHECK_CTX(ctx);
+    if (!mn || !mx || ctx->k <= 0 || !ctx->dX || ctx->m <= 0) {
+        set_error("ddb_term_minmax: library and data must be set, outputs non-null");
+        return DDB_INVALID_ARG;
+    }
+    const int k = ctx->k, n = ctx->n;
+    if (k > 256 * kMMTerms) {
+        set_error("ddb_term_minmax: libraries of more than %d terms are not supported", 256 * kMMTerms);
+        return DDB_UNSUPPORTED;
+    }
+    if (ctx->factors_nt != ctx->n_t || !ctx->d_factors.p) DDB_TRY(gram_ensure_factors(ctx, ((k + ctx->n_t + 127) / 128) * 128));
+    DDB_TRY(ctx->d_stats.reserve((size_t)2 * k * 8));
+    long long* kmin = ctx->d_stats.as<long long>();
+    long long* kmax = kmin + k;
+    std::vector<long long> init(2 * (size_t)k);
+    for (int j = 0; j < k; ++j) init[j] = 0x7FFFFFFFFFFFFFFFLL, init[k + j] = (long long)0x8000000000000000ULL;
+    cudaStream_t st = ctx->stream;
+    DDB_CUDA_TRY(cudaMemcpyAsync(kmin, init.data(), init.size() * 8, cudaMemcpyHostToDevice, st));
+    const size_t smem = (size_t)kMMSamples * (n + 1) * sizeof(double);
+    if (smem > 200 * 1024) {
+        set_error("ddb_term_minmax: too many states for the shared-memory tile");
+        return DDB_UNSUPPORTED;
+    }
+    DDB_CUDA_TRY(cudaFuncSetAttribute(term_minmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t ntiles = (ctx->m + kMMSamples - 1) / kMMSamples;
+    const int nblk = (int)std::min<int64_t>(ntiles, (int64_t)ctx->sm_count * 4);
+    term_minmax_kernel<<<nblk, 256, smem, st>>>(ctx->dX, n, ctx->m, ctx->d_factors.as<uint16_t>(), k, kmin, kmax);
+    DDB_CUDA_TRY(cudaGetLastError());
+    DDB_CUDA_TRY(cudaMemcpyAsync(init.data(), kmin, init.size() * 8, cudaMemcpyDeviceToHost, st));
+    DDB_CUDA_TRY(cudaStreamSynchronize(st));
+    for (int j = 0; j < k; ++j) mn[j] = dkey_inv(init[j]), mx[j] = dkey_inv(init[k + j]);
+    return DDB_OK;
+}
+
+// G~ = S (G - mu t' - t mu' + m mu mu') S,  R~ = S (R - mu ysum'),  S = diag(1 / scale): the blocks of
+// theta~_j = (theta_j - mu_j) / scale_j from those of theta  (t = Theta 1, ysum = Y 1)
+__global__ void affine_terms_kernel(double* __restrict__ packed, int k, int n_t, const double* __restrict__ mu,
+                                    const double* __restrict__ scale, const double* __restrict__ tsum,
+                                    const double* __restrict__ ysum, double m) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t kk = (size_t)k * k, kn = (size_t)k * n_t;
+    if (t < kk) {
+        const int i = (int)(t % k), j = (int)(t / k);
+        // symmetric in (i, j) term by term: the result stays exactly symmetric
+        const double v = packed[t] - (mu[i] * tsum[j] + mu[j] * tsum[i]) + m * (mu[i] * mu[j]);
+        packed[t] = v / (scale[i] * scale[j]);
+    } else if (t < kk + kn) {
+        const int i = (int)((t - kk) % k), e = (int)((t - kk) / k);
+        packed[t] = (packed[t] - mu[i] * ysum[e]) / scale[i];
+    }
+}
+
+int ddb_gram_affine_terms(ddb_ctx* ctx, const double* shift, const double* scale, const double* tsum, const double* ysum,
+                          int64_t m_total) {
+    CHECK_CTX(ctx);
+    if (!ctx->have_gram || !ctx->d_packed.p) {
+        set_error("ddb_gram_affine_terms: no normal-equation blocks in the context");
+        return DDB_BAD_STATE;
+    }
+    if (ctx->term_scale_on) {
+        set_error("ddb_gram_affine_terms: the blocks are already transformed");
+        return DDB_BAD_STATE;
+    }
+    if (!shift || !scale || !tsum || !ysum || m_total <= 0) {
+        set_error("ddb_gram_affine_terms: null argument");
+        return DDB_INVALID_ARG;
+    }
+    const int k = ctx->k, n_t = ctx->n_t;
+    for (int j = 0; j < k; ++j)
+        if (!(scale[j] > 0.0) || !std::isfinite(scale[j]) || !std::isfinite(shift[j])) {
+            set_error("ddb_gram_affine_terms: scale[%d] must be positive and finite, shift finite", j);
+            return DDB_INVALID_ARG;
+        }
+    DDB_TRY(ctx->d_term_scale.reserve((size_t)k * 8));
+    DDB_TRY(ctx->d_term_shift.reserve((size_t)k * 8));
+    DDB_TRY(ctx->d_stats.reserve(((size_t)k + n_t) * 8));
+    cudaStream_t st = ctx->stream;
+    DDB_CUDA_TRY(cudaMemcpyAsync(ctx->d_term_scale.p, scale, (size_t)k * 8, cudaMemcpyHostToDevice, st));
+    DDB_CUDA_TRY(cudaMemcpyAsync(ctx->d_term_shift.p, shift, (size_t)k * 8, cudaMemcpyHostToDevice, st));
+    DDB_CUDA_TRY(cudaMemcpyAsync(ctx->d_stats.p, tsum, (size_t)k * 8, cudaMemcpyHostToDevice, st));
+    DDB_CUDA_TRY(cudaMemcpyAsync(ctx->d_stats.as<double>() + k, ysum, (size_t)n_t * 8, cudaMemcpyHostToDevice, st));
+    const size_t tot = (size_t)k * k + (size_t)k * n_t;
+    affine_terms_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(ctx->d_packed.as<double>(), k, n_t,
+                                                                       ctx->d_term_shift.as<double>(), ctx->d_term_scale.as<double>(),
+                                                                       ctx->d_stats.as<double>(), ctx->d_stats.as<double>() + k,
+                                                                       (double)m_total);
+    DDB_CUDA_TRY(cudaGetLastError());
+    DDB_CUDA_TRY(cudaStreamSynchronize(st));
+    ctx->term_scale_on = true;
+    ctx->term_shift_on = true;
+    ctx->imp_k = 0;
+    return DDB_OK;
 }
 
 int ddb_bind_device(ddb_ctx* ctx, const double* dX, const double* dY, int n_t, int64_t m) {

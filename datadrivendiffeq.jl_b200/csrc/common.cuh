@@ -78,6 +78,7 @@ struct DmdState;
 struct RingState;
 struct TrsmState;
 struct MomentState;
+struct UserFeat;
 
 }  // namespace ddb
 
@@ -102,6 +103,7 @@ struct ddb_ctx {
     int n_raw = 0;                       // 0 = no feature map (the states are used as they are)
     ddb::DevBuf d_feat;                  // n x {int kind, int src, double coef}
     ddb::DevBuf raw_X;                   // staging of the raw states for host uploads
+    ddb::UserFeat* userfeat = nullptr;   // NVRTC-compiled feature kernel (ddb_set_features_source); overrides d_feat
 
     // data
     const double* dX = nullptr;
@@ -120,8 +122,11 @@ struct ddb_ctx {
     bool have_gram = false;
 
     // term normalisation (ddb_gram_scale_terms): the blocks in d_packed are those of Theta_j / scale_j
-    ddb::DevBuf d_term_scale;
+    ddb::DevBuf d_term_scale;            // divisor per term
     bool term_scale_on = false;
+    ddb::DevBuf d_term_shift;            // affine normalisation (ddb_gram_affine_terms): theta~_j = (theta_j - shift_j) / scale_j
+    bool term_shift_on = false;
+    ddb::DevBuf d_cand_shift;            // per-candidate constants of the exact-rss pass under an affine normalisation
     ddb::DevBuf d_stats;                 // ddb_target_stats scratch
     // ddb_residual scratch
     ddb::DevBuf d_resid, d_resid_terms, d_resid_partials;

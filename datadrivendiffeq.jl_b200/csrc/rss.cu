@@ -71,6 +71,7 @@ struct RssArgs {
     const int32_t* cand_eq;
     const RssTerm* terms;
     const RssTerm* targets;  // implicit mode: target e is a library term (one record each); null = row e of Y
+    const double* cand_shift;  // per candidate: constant added to its fit (affine term normalisation) or null
     int term_cap;            // term records of one CTA's candidates that fit in shared memory
     int sub, pitch;          // groups of 32 samples per staged tile; row pitch of the tile = 32 sub + 1
     double* partials;  // gridDim.x x ncand
@@ -114,7 +115,7 @@ __device__ __forceinline__ void rss_stage_rows(double* buf, const double* src, i
 // keeps the accesses in the shared address space (LDS with 32-bit addressing, no generic-pointer arithmetic).
 template <int NF, bool SMEM_TERMS>
 __device__ __forceinline__ void rss_tiles(const RssArgs& a, double* sm, const int4* s_meta, const RssTerm* s_terms,
-                                          int nslots, int cbase, int64_t t_lo, int64_t t_hi, int tp,
+                                          const double* s_shift, int nslots, int cbase, int64_t t_lo, int64_t t_hi, int tp,
                                           double (&acc)[kRssAcc]) {
     const int rows = a.n + a.n_t + 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -155,7 +156,7 @@ __device__ __forceinline__ void rss_tiles(const RssArgs& a, double* sm, const in
                 const int nnz = SMEM_TERMS ? mt.w : mt.y, eq = mt.z;  // shared-memory records are padded to 4s
                 const RssTerm* r = SMEM_TERMS ? s_terms + mt.x : a.terms + __ldg(a.cand_off + cbase + warp + kRssWarps * q);
                 const int4* r16 = reinterpret_cast<const int4*>(s_terms) + mt.x;  // compact records (degree <= 2)
-                double fit = 0.0;
+                double fit = s_shift[warp + kRssWarps * q];
                 if (NF <= 2 && SMEM_TERMS) {
                     for (int t = 0; t < nnz; t += 4) {  // the padded count is a multiple of 4
 #pragma unroll
@@ -228,9 +229,11 @@ __global__ void __launch_bounds__(kRssWarps * 32) rss_kernel(const RssArgs a) {
     RssTerm* s_terms = reinterpret_cast<RssTerm*>(s_meta + kRssWarps * kRssAcc);
     __shared__ int s_scan[kRssWarps];
     __shared__ int s_total;
+    __shared__ double s_shift[kRssWarps * kRssAcc];
     {
         const int lc = threadIdx.x;  // local candidate id: warp w, slot q  <->  lc = w + 8 q
         const int c = cbase + lc;
+        s_shift[lc] = (a.cand_shift && c < a.ncand) ? a.cand_shift[c] : 0.0;
         const int nnz = c < a.ncand ? a.cand_nnz[c] : 0;
         // shared-memory mode: every candidate's record list is padded to a multiple of 4 (padding records have
         // coefficient 0 and read the row of ones), so the term loop runs in branch-free groups of four
@@ -275,9 +278,9 @@ __global__ void __launch_bounds__(kRssWarps * 32) rss_kernel(const RssArgs a) {
 #pragma unroll
     for (int q = 0; q < kRssAcc; ++q) acc[q] = 0.0;
     if ((int64_t)tp * (NF <= 2 ? 1 : 2) <= (int64_t)a.term_cap * 2)
-        rss_tiles<NF, true>(a, sm, s_meta, s_terms, nslots, cbase, t_lo, t_hi, tp, acc);
+        rss_tiles<NF, true>(a, sm, s_meta, s_terms, s_shift, nslots, cbase, t_lo, t_hi, tp, acc);
     else
-        rss_tiles<NF, false>(a, sm, s_meta, s_terms, nslots, cbase, t_lo, t_hi, tp, acc);
+        rss_tiles<NF, false>(a, sm, s_meta, s_terms, s_shift, nslots, cbase, t_lo, t_hi, tp, acc);
     // lanes hold per-sample-slot partial sums: fixed shuffle tree, then one write per candidate
 #pragma unroll
     for (int q = 0; q < kRssAcc; ++q) {
@@ -316,6 +319,17 @@ __global__ void rss_scale_kernel(RssTerm* __restrict__ terms, const int32_t* __r
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < nterms) terms[t].val /= scale[cand_idx[t]];
 }
+// affine term normalisation (theta~_j = (theta_j - mu_j) / scale_j): the candidate c~ evaluates on the raw terms as
+// sum_j (c~_j / scale_j) theta_j + shift with shift = -sum_j (c~_j / scale_j) mu_j; terms[].val is already divided
+__global__ void rss_shift_kernel(const RssTerm* __restrict__ terms, const int32_t* __restrict__ cand_idx,
+                                 const int64_t* __restrict__ off, const int32_t* __restrict__ nnz, int ncand,
+                                 const double* __restrict__ mu, double* __restrict__ shift) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncand) return;
+    double s = 0.0;
+    for (int t = 0; t < nnz[c]; ++t) s -= terms[off[c] + t].val * mu[cand_idx[off[c] + t]];
+    shift[c] = s;
+}
 
 // groups of 32 samples per staged tile (~16 KB per tile) and the resulting row pitch
 static void rss_tile_shape(const ddb_ctx* ctx, int* sub_out, int* pitch_out) {
@@ -327,7 +341,8 @@ static void rss_tile_shape(const ddb_ctx* ctx, int* sub_out, int* pitch_out) {
 }
 
 static int rss_core(ddb_ctx* ctx, const RssCand& c, const int32_t* map, const RssTerm* targets, const double* scale,
-                    DevBuf& terms, DevBuf& partials, double* dRss, int* launches) {
+                    DevBuf& terms, DevBuf& partials, double* dRss, int* launches, const double* mu = nullptr,
+                    const double* extra_shift = nullptr) {
     if (!ctx->dX || !ctx->dY || ctx->m <= 0) {
         set_error("ddb_rss: no data bound");
         return DDB_BAD_STATE;
@@ -350,6 +365,14 @@ static int rss_core(ddb_ctx* ctx, const RssCand& c, const int32_t* map, const Rs
             ++*launches;
         }
     }
+    const double* cand_shift = extra_shift;
+    if (mu) {  // affine normalisation: per-candidate constant (see rss_shift_kernel)
+        DDB_TRY(ctx->d_cand_shift.reserve((size_t)std::max(1, ncand) * 8));
+        rss_shift_kernel<<<(ncand + 255) / 256, 256, 0, st>>>(terms.as<RssTerm>(), c.idx, c.off, c.nnz, ncand, mu,
+                                                              ctx->d_cand_shift.as<double>());
+        ++*launches;
+        cand_shift = ctx->d_cand_shift.as<double>();
+    }
     const int passes = (ncand + kRssWarps * kRssAcc - 1) / (kRssWarps * kRssAcc);
     const int rows_all = ctx->n + ctx->n_t + 1;
     const int64_t ntiles = (ctx->m + kRssTile * sub - 1) / (kRssTile * sub);
@@ -367,6 +390,7 @@ static int rss_core(ddb_ctx* ctx, const RssCand& c, const int32_t* map, const Rs
     a.cand_eq = c.eq;
     a.terms = terms.as<RssTerm>();
     a.targets = targets;
+    a.cand_shift = cand_shift;
     a.partials = partials.as<double>();
     const size_t smem_tiles = ((2 * (size_t)pitch * rows_all + 1) & ~size_t(1)) * sizeof(double);
     a.sub = sub;
@@ -457,6 +481,7 @@ int rss_run(ddb_ctx* ctx, SweepState* S, double* dRss) {
     const int32_t* map = implicit ? ctx->imp_idx.as<int32_t>() : nullptr;
     const RssTerm* targets = implicit ? S->tgt_terms.as<RssTerm>() : nullptr;
     const double* scale = (!implicit && ctx->term_scale_on) ? ctx->d_term_scale.as<double>() : nullptr;
+    const double* mu = (!implicit && ctx->term_scale_on && ctx->term_shift_on) ? ctx->d_term_shift.as<double>() : nullptr;
 
     // ---- group the candidates by (target, support) -----------------------------------------------
     const int64_t nterms = S->pool_used;
@@ -473,7 +498,7 @@ int rss_run(ddb_ctx* ctx, SweepState* S, double* dRss) {
         if (ncand > n_t) {  // candidates n_t .. ncand-1 are the recorded models
             RssCand c{ncand - n_t, nterms, S->cand_off.as<int64_t>() + n_t, S->cand_nnz.as<int32_t>() + n_t,
                       S->cand_eq.as<int32_t>() + n_t, S->cand_idx.as<int32_t>(), S->cand_val.as<double>()};
-            DDB_TRY(rss_core(ctx, c, map, targets, scale, S->cand_terms, S->rss_partials, dRss + n_t, &launches));
+            DDB_TRY(rss_core(ctx, c, map, targets, scale, S->cand_terms, S->rss_partials, dRss + n_t, &launches, mu));
         }
     } else {
         std::vector<int64_t> off(ncand);
@@ -661,7 +686,7 @@ int rss_run(ddb_ctx* ctx, SweepState* S, double* dRss) {
                   reinterpret_cast<const double*>(rb + o_val)};
         if (nrep > 0)
             DDB_TRY(rss_core(ctx, c, map, targets, scale, S->cand_terms, S->rss_partials, reinterpret_cast<double*>(rb + o_rep),
-                             &launches));
+                             &launches, mu));
         scatter_group_rss_kernel<<<(ncand + 255) / 256, 256, 0, st>>>(reinterpret_cast<const double*>(rb + o_rep),
                                                                       reinterpret_cast<const int32_t*>(rb + o_map), ncand, dRss);
         ++launches;
@@ -685,7 +710,7 @@ int rss_run(ddb_ctx* ctx, SweepState* S, double* dRss) {
 }
 
 // ddb_residual: rss of an arbitrary coefficient matrix (n_t x k column-major, host) over the current samples
-int residual_run(ddb_ctx* ctx, const double* coef, double* rss_out) {
+int residual_run(ddb_ctx* ctx, const double* coef, const double* offset, double* rss_out) {
     const int k = ctx->k, n_t = ctx->n_t;
     if (k <= 0 || n_t <= 0 || !coef || !rss_out) {
         set_error("ddb_residual: library and data must be set, coef and rss non-null");
@@ -712,11 +737,11 @@ int residual_run(ddb_ctx* ctx, const double* coef, double* rss_out) {
     }
     const int64_t nterms = (int64_t)idx.size();
     cudaStream_t st = ctx->stream;
-    DevBuf& B = ctx->d_resid;  // [off | nnz | eq | idx | val | rss]
+    DevBuf& B = ctx->d_resid;  // [off | nnz | eq | idx | val | rss | offset]
     const size_t o_nnz = (size_t)n_t * 8, o_eq = o_nnz + (size_t)n_t * 4, o_idx = (o_eq + (size_t)n_t * 4 + 7) & ~size_t(7);
     const size_t o_val = (o_idx + (size_t)std::max<int64_t>(1, nterms) * 4 + 7) & ~size_t(7);
     const size_t o_rss = o_val + (size_t)std::max<int64_t>(1, nterms) * 8;
-    DDB_TRY(B.reserve(o_rss + (size_t)n_t * 8));
+    DDB_TRY(B.reserve(o_rss + 2 * (size_t)n_t * 8));
     unsigned char* base = static_cast<unsigned char*>(B.p);
     DDB_CUDA_TRY(cudaMemcpyAsync(base, off.data(), (size_t)n_t * 8, cudaMemcpyHostToDevice, st));
     DDB_CUDA_TRY(cudaMemcpyAsync(base + o_nnz, nnz.data(), (size_t)n_t * 4, cudaMemcpyHostToDevice, st));
@@ -728,10 +753,15 @@ int residual_run(ddb_ctx* ctx, const double* coef, double* rss_out) {
     RssCand c{n_t, nterms, reinterpret_cast<const int64_t*>(base), reinterpret_cast<const int32_t*>(base + o_nnz),
               reinterpret_cast<const int32_t*>(base + o_eq), reinterpret_cast<const int32_t*>(base + o_idx),
               reinterpret_cast<const double*>(base + o_val)};
+    const double* d_offset = nullptr;
+    if (offset) {
+        DDB_CUDA_TRY(cudaMemcpyAsync(base + o_rss + (size_t)n_t * 8, offset, (size_t)n_t * 8, cudaMemcpyHostToDevice, st));
+        d_offset = reinterpret_cast<const double*>(base + o_rss + (size_t)n_t * 8);
+    }
     int launches = 0;
     DDB_CUDA_TRY(cudaEventRecord(ctx->ev[4], st));
     DDB_TRY(rss_core(ctx, c, nullptr, nullptr, nullptr, ctx->d_resid_terms, ctx->d_resid_partials,
-                     reinterpret_cast<double*>(base + o_rss), &launches));
+                     reinterpret_cast<double*>(base + o_rss), &launches, nullptr, d_offset));
     DDB_CUDA_TRY(cudaEventRecord(ctx->ev[5], st));
     DDB_CUDA_TRY(cudaMemcpyAsync(rss_out, base + o_rss, (size_t)n_t * 8, cudaMemcpyDeviceToHost, st));
     DDB_CUDA_TRY(cudaStreamSynchronize(st));  // off/nnz/... are stack-lifetime host buffers

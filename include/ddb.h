@@ -154,6 +154,18 @@ typedef enum ddb_feature_kind {
 } ddb_feature_kind;
 int ddb_set_features(ddb_ctx* ctx, int n_raw, int n_feat, const int32_t* kind, const int32_t* source, const double* coef);
 
+/* Arbitrary features through NVRTC: `body` is CUDA C that assigns f[0] .. f[n_feat - 1] from the raw variables
+ * x[0] .. x[n_raw - 1] of one sample ([states | controls | independent variable], as the caller stacks them) and the
+ * parameter values p[0] .. p[n_params - 1], e.g. "f[0] = x[0]; f[1] = sin(x[0]) * x[1]; f[2] = exp(-p[0] * x[1] * x[1]);".
+ * One kernel is compiled for sm_100a and evaluated once per upload / bind; the installed monomial library is a table
+ * of exponents over these features (identity table = one term per expression).  Replaces the per-term code generation
+ * of `DataDrivenFunction` (src/basis/build_function.jl:6-38, argument order implicits, states, parameters,
+ * independent variable, controls) for terms the fixed kinds above do not cover; the Julia side can emit `body` with
+ * `Symbolics.build_function(...; target = Symbolics.CTarget())`.  Call before binding data; ddb_set_features replaces it.
+ * ddb_features_source_check only compiles (no GPU needed) and returns the compiler log. */
+int ddb_set_features_source(ddb_ctx* ctx, int n_raw, int n_feat, const char* body, const double* params, int n_params);
+int ddb_features_source_check(const char* body, char* log, int log_cap);
+
 /* Copy the bound device data back to the host (for tests and the end-to-end bench). */
 int ddb_download_data(ddb_ctx* ctx, double* X, double* Y);
 
@@ -211,6 +223,19 @@ int ddb_set_sample_range(ddb_ctx* ctx, int64_t first, int64_t last);
 int ddb_permute_samples(ddb_ctx* ctx, const int64_t* perm);
 int ddb_gram_scale_terms(ddb_ctx* ctx, const double* scale);
 int ddb_residual(ddb_ctx* ctx, const double* coef, double* rss);
+/* `UnitRangeTransform` normalisation of the library rows (src/utils/data_processing.jl:68-73, 119-126):
+ * ddb_term_minmax: minimum and maximum of every library term over the current sample view (host outputs, k each) --
+ *   what `fit(UnitRangeTransform, Theta, dims = 2)` needs; one pass over the states, Theta is not built.
+ * ddb_gram_affine_terms: turns the blocks in the context into those of theta~_j = (theta_j - shift_j) / scale_j
+ *   (G~ = S (G - mu t' - t mu' + m mu mu') S, R~ = S (R - mu ysum'); tsum = Theta 1 (k), ysum = Y 1 (n_t), m_total
+ *   samples behind the blocks).  The sweep then runs in the transformed space, the exact-rss pass evaluates every
+ *   candidate on the raw data with the equivalent coefficients and constant.  Reset by a new Gram.
+ * ddb_residual_affine: ddb_residual with a constant per target added to the fit (offset, n_t): residuals of a model
+ *   given in the transformed space. */
+int ddb_term_minmax(ddb_ctx* ctx, double* mn, double* mx);
+int ddb_gram_affine_terms(ddb_ctx* ctx, const double* shift, const double* scale, const double* tsum, const double* ysum,
+                          int64_t m_total);
+int ddb_residual_affine(ddb_ctx* ctx, const double* coef, const double* offset, double* rss);
 /* Per-target mean and centred sum of squares of the bound targets over the current sample view:
  *   mean[e] = (sum over ALL ranks of sum_s Y[e,s]) / m_total,   css[e] = sum_s (Y[e,s] - mean[e])^2  (summed over ranks),
  * two HBM passes over Y; with a communicator both sums are all-reduced inside (collective).  What

@@ -545,6 +545,16 @@ def solve_processed(alg, Theta: np.ndarray, Y: np.ndarray, options: Optional[Com
     if normalize == "ZScoreTransform":  # commonsolve.jl:128-130: fitted and applied on ALL samples before the split
         sigma = zscore_fit(Theta)
         Theta = Theta / sigma[:, None]
+    elif normalize == "UnitRangeTransform":
+        # fit(UnitRangeTransform, Theta, dims = 2) (data_processing.jl:68-73): per-row minimum and 1 / (max - min), an
+        # infinite scale (constant row) replaced by 1; apply_transform! (:119-126): (Theta - min) .* scale
+        tmin = Theta.min(axis=1)
+        rng = Theta.max(axis=1) - tmin
+        with np.errstate(divide="ignore"):
+            tscale = 1.0 / rng
+        tscale[np.isinf(tscale)] = 1.0
+        Theta = (Theta - tmin[:, None]) * tscale[:, None]
+        sigma = (tmin, tscale)
     elif normalize is not None:
         raise ValueError(normalize)
     split = min(max(float(split), 0.0), 1.0)  # data_processing.jl:32
@@ -566,6 +576,10 @@ def solve_processed(alg, Theta: np.ndarray, Y: np.ndarray, options: Optional[Com
     results.sort(key=lambda r: r.testerror if r.testerror is not None else r.trainerror)  # :12 sort!(results, by = l2error)
     best = results[0]
     C = best.coefficients.copy()
-    if sigma is not None:
+    if isinstance(sigma, tuple):
+        # lib commonsolve.jl:19-21: the SAME apply_transform! is run on the transposed coefficient matrix -- the rows
+        # of the coefficients are shifted by the library minima and multiplied by the scales (the reference as written)
+        C = (C - sigma[0][None, :]) * sigma[1][None, :]
+    elif sigma is not None:
         C = C / sigma[None, :]  # :19-21 apply_transform(transform, coefficients')' with an empty mean
     return C, results, sigma

@@ -128,3 +128,44 @@ def test_library_with_controls_and_time(ctx):
     assert got["u1"] == pytest.approx(3.0, rel=1e-9) and got["t"] == pytest.approx(0.05, rel=1e-9)
     with pytest.raises(ValueError):
         ddb200.solve(ddb200.ContinuousDataDrivenProblem(X, t=t, DX=DX), basis, alg)  # no control data
+
+
+def test_expression_library_through_nvrtc():
+    """Arbitrary terms and symbolic parameters (``src/basis/build_function.jl:6-38``): expressions in the raw variables
+    and parameter values, compiled by NVRTC into one feature kernel; the Gram blocks and a full ``solve`` against the
+    oracle on the same (host-evaluated) library."""
+    rng = np.random.default_rng(21)
+    m = 3000
+    X = rng.uniform(0.2, 2.0, (2, m))
+    p = np.array([0.7, 1.3])
+    exprs = ["1.0", "x[0]", "x[1]", "x[0] * x[1]", "sin(p[0] * x[0]) * x[1]", "x[0] / (p[1] + x[1])", "exp(-x[0] * x[0])"]
+    Theta = np.vstack([np.ones(m), X[0], X[1], X[0] * X[1], np.sin(p[0] * X[0]) * X[1], X[0] / (p[1] + X[1]), np.exp(-X[0] ** 2)])
+    Ctrue = np.zeros((2, 7))
+    Ctrue[0, [1, 4]] = [-0.8, 1.5]
+    Ctrue[1, [0, 5, 3]] = [0.4, 2.0, -0.6]
+    Y = Ctrue @ Theta + 1e-3 * rng.standard_normal((2, m))
+    basis = ddb200.expression_basis(2, exprs, params=p)
+    assert len(basis) == 7 and basis.n_states == 2
+    with ddb200.Context(0) as ctx:
+        ctx.set_features(2, basis.features)
+        ctx.set_library(basis.exponents)
+        ctx.upload(X, Y)
+        ctx.gram()
+        G, R, yy = ctx.gram_download()
+    G0, R0 = Theta @ Theta.T, Theta @ Y.T
+    sc = np.sqrt(np.outer(np.diag(G0), np.diag(G0)))
+    assert np.max(np.abs(G - G0) / sc) < 1e-12  # device sin / exp / division against NumPy's: a few ulp per feature
+    assert np.max(np.abs(R - R0)) < 1e-12 * np.sqrt(np.max(np.diag(G0)) * np.max((Y * Y).sum(1)))
+    lams = 10.0 ** np.arange(-2, -0.2, 0.25)
+    sol = ddb200.solve(ddb200.DirectDataDrivenProblem(X, Y), basis, ddb200.B200Sparse(ddb200.STLSQ(lams)))
+    ref = oracle.sparse_regression(oracle.STLSQ(lams), Theta, Y)
+    np.testing.assert_array_equal(sol.results[0].coefficients != 0, ref.coefficients != 0)
+    np.testing.assert_array_equal(ref.coefficients != 0, Ctrue != 0)
+    nz = ref.coefficients != 0
+    assert (np.abs(sol.results[0].coefficients[nz] - ref.coefficients[nz]) / np.abs(ref.coefficients[nz])).max() <= 1e-9
+    # a source that does not compile is an error with the compiler's message, never a silent fallback
+    bad = ddb200.expression_basis(2, ["x[0] +* 2"])
+    with ddb200.Context(0) as ctx:
+        with pytest.raises(ddb200._lib.DDBError) as e:
+            ctx.set_features(2, bad.features)
+        assert e.value.status == -1 and "error" in str(e.value)

@@ -177,3 +177,46 @@ def test_solution_statistics_match_the_reference_formulas(ctx):
     assert sol.bic() == pytest.approx(-2 * ll + k * np.log(n), rel=1e-9)
     assert sol.aicc() == pytest.approx(-2 * ll + 2 * k + 2 * k * (k + 1) / (n - k - 1), rel=1e-9)
     assert 0.99 < sol.r2() <= 1.0  # the reference's own tests assert r2 ~ 1 on identifiable systems
+
+
+@pytest.mark.parametrize("name", ["STLSQ", "STLSQ-ridge", "SR3"])
+@pytest.mark.parametrize("with_const", [True, False])
+def test_unit_range_normalisation_matches_oracle(ctx, name, with_const):
+    """``DataNormalization(UnitRangeTransform)`` (``src/utils/data_processing.jl:68-73, 119-126``): every library row is
+    shifted by its minimum and divided by its range (fitted on all samples), the regression runs on the transformed
+    rows and -- as the reference is written -- the same transform is applied to the coefficient matrix afterwards
+    (``lib/DataDrivenSparse/src/commonsolve.jl:19-21``).  On the device: term minima / maxima in one pass
+    (``ddb_term_minmax``), the blocks of the transformed rows from the blocks of the raw ones
+    (``ddb_gram_affine_terms``), candidates scored on the raw data with the equivalent constant."""
+    X, DX = _lorenz(m=1500)
+    basis = ddb200.polynomial_basis(3, 2)
+    if not with_const:
+        basis = ddb200.Basis(basis.exponents[:, 1:])
+    lams = 10.0 ** np.arange(-0.5, 1.6, 0.25)  # coefficients of the unit-range rows are ~range x the raw ones
+    algs = {"STLSQ": lambda mm: mm.STLSQ(lams), "STLSQ-ridge": lambda mm: mm.STLSQ(lams, 1e-3), "SR3": lambda mm: mm.SR3(lams)}
+    Th = oracle.evaluate_library(basis.exponents, X)
+    C_ref, res_ref, _ = oracle.solve_processed(algs[name](oracle), Th, DX, normalize="UnitRangeTransform", split=0.8)
+    sol = _solve(ctx, basis, X, DX, algs[name](ddb200), normalize="UnitRangeTransform", split=0.8)
+    Cs = sol.results[0].coefficients
+    np.testing.assert_array_equal(Cs != 0.0, res_ref[0].coefficients != 0.0)
+    np.testing.assert_allclose(Cs, res_ref[0].coefficients, rtol=2e-6, atol=1e-9)
+    np.testing.assert_allclose(sol.results[0].trainerror, res_ref[0].trainerror, rtol=1e-6)
+    np.testing.assert_allclose(sol.results[0].testerror, res_ref[0].testerror, rtol=1e-6)
+    np.testing.assert_allclose(sol.coefficients, oracle.construct_coefficients(C_ref), rtol=2e-6, atol=2e-9)
+
+
+def test_term_minmax(ctx):
+    rng = np.random.default_rng(3)
+    X = rng.standard_normal((5, 4001))
+    ex = oracle.polynomial_exponents(5, 3)
+    Th = oracle.evaluate_library(ex, X)
+    ctx.set_features(0, None)
+    ctx.set_library(ex)
+    ctx.upload(X, X[:2])
+    mn, mx = ctx.term_minmax()
+    np.testing.assert_allclose(mn, Th.min(axis=1), rtol=1e-14)
+    np.testing.assert_allclose(mx, Th.max(axis=1), rtol=1e-14)
+    ctx.set_sample_range(100, 777)
+    mn, mx = ctx.term_minmax()
+    np.testing.assert_allclose(mn, Th[:, 100:777].min(axis=1), rtol=1e-14)
+    ctx.set_sample_range(0, -1)

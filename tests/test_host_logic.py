@@ -104,3 +104,20 @@ def test_shard_ranges_tile_the_samples(m, world):
             assert hi % 16 == 0 or hi == m
         lo_prev = hi
     assert lo_prev == m
+
+
+def test_expression_source_compiles_without_a_gpu():
+    """``ddb_features_source_check``: NVRTC runs on the host, so the expressions of an ``expression_basis`` are
+    validated (and the compiler's diagnostics returned) before any GPU is involved."""
+    import ctypes as C
+
+    from ddb200 import _lib
+
+    lib = _lib.load()
+    fs = ddb200.FeatureSource(["x[0]", "sin(p[0] * x[0]) * x[1]", "exp(-x[0] * x[0])"], params=[0.7])
+    log = C.create_string_buffer(4096)
+    assert lib.ddb_features_source_check(fs.body.encode(), log, 4096) == 0
+    assert lib.ddb_features_source_check(b"f[0] = undefined_symbol;", log, 4096) == -1
+    assert b"undefined" in log.value
+    b = ddb200.expression_basis(2, fs.expressions, params=[0.7])
+    assert len(b) == 3 and b.n_states == 2 and b.term_strings()[1] == "(sin(p[0] * x[0]) * x[1])"
