@@ -722,7 +722,7 @@ def _solve_processed(prob, basis, alg, options, X, Y, paths=False):
     split, shuffled mini-batches; every batch is regressed separately and the result with the smallest test
     (or train) error wins.  Train part, test part and batches are views of the resident data."""
     if alg.group is not None:
-        raise ValueError("B200Sparse: normalisation / split / batches are not supported on the sharded path yet")
+        return _solve_processed_sharded(prob, basis, alg, options, X, Y)
     ctx = alg.context()
     ctx.set_features(basis.n_raw, basis.features)
     ctx.set_library(basis.exponents)
@@ -822,6 +822,104 @@ def _solve_processed(prob, basis, alg, options, X, Y, paths=False):
     return DataDrivenSolution(basis=basis, coefficients=Cr, results=results, rss=rss_all, dof=int(np.sum(Cr != 0.0)),
                               nobs=int(n_t * m), retcode=best.retcode, timings=t,
                               paths=outs[order[0]] if paths else None, null_ss=null_ss)
+
+
+def _solve_processed_sharded(prob, basis, alg, options, X, Y):
+    """:func:`_solve_processed` on the row-sharded path (one process per GPU; ``X``, ``Y`` are THIS rank's contiguous
+    shard in rank order).  The global sample order, split point and batches are those of the single-process run: the
+    split is contiguous (``splitobs(shuffle = false)``), the batches are cut from a global shuffle every rank derives
+    from the same seed / ``perm``; a rank's part of a batch or of the test set is a contiguous view of its resident
+    samples after one local gather (possibly EMPTY), and every statistic is a sum over the ranks (NCCL all-reduce inside
+    the library).  ZScore scales come from the all-reduced blocks of all samples."""
+    from . import dist
+
+    if options.normalize == "UnitRangeTransform":
+        raise ValueError("B200Sparse: UnitRangeTransform is not available on the sharded path (it needs a min / max exchange)")
+    ctx = alg.context()
+    grp = alg.group
+    if not dist._has_comm(ctx):
+        dist.init_comm(ctx, grp)
+    ctx.set_features(basis.n_raw, basis.features)
+    ctx.set_library(basis.exponents)
+    prm = _params_for(ctx, alg.inner, options)
+    lambdas = alg.inner.thresholds
+    m_local = X.shape[1]
+    lo, m = dist.shard_offsets(m_local, grp, device=f"cuda:{ctx.device}")
+    k, n_t = len(basis), Y.shape[0]
+    split = min(max(float(options.split), 0.0), 1.0)
+    m_train = int(round(split * m))
+    if m_train <= 0:
+        raise ValueError("B200Sparse: the training split is empty")
+    lt = min(max(m_train - lo, 0), m_local)  # this rank's training samples: local [0, lt); test part: [lt, m_local)
+    ctx.upload(X, Y)
+    sigma = None
+    if options.normalize == "ZScoreTransform":
+        ctx.gram()
+        ctx.allreduce_gram()
+        G, R, _yy = ctx.gram_download()
+        const = np.nonzero(basis.exponents.sum(axis=0) == 0)[0]
+        if const.size:
+            sums = G[const[0]].copy()
+        else:
+            ctx.upload(X, np.ones((1, m_local)))
+            ctx.gram()
+            ctx.allreduce_gram()
+            sums = ctx.gram_download()[1][:, 0].copy()
+            ctx.upload(X, Y)
+        sigma = zscore_scales(G, sums, m)
+    batchsize = m_train if options.batchsize <= 0 else int(options.batchsize)
+    perm = None
+    if options.perm is not None:
+        perm = np.asarray(options.perm, dtype=np.int64)
+    elif options.shuffle_seed is not None and batchsize < m_train:
+        perm = np.random.default_rng(options.shuffle_seed).permutation(m_train)
+    pos_local = np.arange(lo, lo + lt)  # position of my training samples in the (shuffled) global training order
+    if perm is not None:
+        if perm.size != m_train:
+            raise ValueError("perm must order the training samples")
+        inv = np.empty(m_train, dtype=np.int64)
+        inv[perm] = np.arange(m_train)
+        pos = inv[lo:lo + lt]
+        order = np.argsort(pos, kind="stable")
+        pos_local = pos[order]
+        ctx.permute_samples(np.concatenate([order, np.arange(lt, m_local)]))
+    starts = list(range(0, m_train, batchsize))
+    if not options.partial and m_train % batchsize:
+        starts = starts[:-1]
+    results = []
+    for b0 in starts:
+        b1 = min(b0 + batchsize, m_train)
+        l0, l1 = int(np.searchsorted(pos_local, b0)), int(np.searchsorted(pos_local, b1))
+        ctx.set_sample_range(l0, l1)  # possibly empty
+        ctx.gram()
+        ctx.allreduce_gram()
+        if sigma is not None:
+            ctx.gram_scale_terms(sigma)
+        ctx.sweep(prm, lambdas, b1 - b0)
+        ctx.rss()
+        ctx.allreduce_rss()
+        out = ctx.select()
+        Cs = out.coefficients
+        Cu = Cs / sigma[None, :] if sigma is not None else Cs
+        testerror = None
+        if m_train < m:
+            ctx.set_sample_range(lt, m_local)
+            testerror = float(np.sum(dist.allreduce_host_sum(ctx, ctx.residual(Cu), grp)))
+        results.append(SparseRegressionResult(coefficients=Cs, dof=int(np.sum(np.abs(Cs) > 0.0)), lambda_=out.lambda_opt,
+                                              iterations=out.iterations, testerror=testerror,
+                                              trainerror=float(np.sum(out.rss)), retcode=1 if not np.any(out.flags & 1) else 2))
+    ctx.set_sample_range(0, -1)
+    order = sorted(range(len(results)), key=lambda i: results[i].testerror if results[i].testerror is not None
+                   else results[i].trainerror)
+    results = [results[i] for i in order]
+    best = results[0]
+    C = best.coefficients / sigma[None, :] if sigma is not None else best.coefficients
+    Cr = construct_coefficients(C, options.digits)
+    rss_all = float(np.sum(dist.allreduce_host_sum(ctx, ctx.residual(Cr), grp)))
+    t = ctx.timings()
+    null_ss = float(np.sum(ctx.target_stats(m)[1]))
+    return DataDrivenSolution(basis=basis, coefficients=Cr, results=results, rss=rss_all, dof=int(np.sum(Cr != 0.0)),
+                              nobs=int(n_t * m), retcode=best.retcode, timings=t, null_ss=null_ss)
 
 
 def solve(prob: DataDrivenProblem, basis: Basis, alg: B200Sparse, options: Optional[DataDrivenCommonOptions] = None,

@@ -314,6 +314,7 @@ int ddb_set_features(ddb_ctx* ctx, int n_raw, int n_feat, const int32_t* kind, c
     // the library must be (re)installed over n_feat states; data must be (re)bound
     ctx->dX = ctx->dY = nullptr;
     ctx->range_on = false;
+    ctx->view_empty = false;
     ctx->m = 0;
     return DDB_OK;
 }
@@ -363,6 +364,7 @@ int ddb_upload(ddb_ctx* ctx, const double* X, const double* Y, int n_t, int64_t 
     ctx->dX = ctx->own_X.as<double>();
     ctx->dY = ctx->own_Y.as<double>();
     ctx->range_on = false;
+    ctx->view_empty = false;
     ctx->n_t = n_t;
     ctx->m = m;
     ctx->have_gram = false;
@@ -413,6 +415,7 @@ int ddb_upload_gram(ddb_ctx* ctx, const double* X, const double* Y, int n_t, int
     }
     ctx->n_t = n_t;
     ctx->range_on = false;
+    ctx->view_empty = false;
     ctx->have_gram = false;
     ctx->imp_k = 0;
     ctx->term_scale_on = false;
@@ -541,18 +544,21 @@ int ddb_set_sample_range(ddb_ctx* ctx, int64_t first, int64_t last) {
         return DDB_BAD_STATE;
     }
     if (last < 0) last = ctx->full_m;
-    if (first < 0 || first >= last || last > ctx->full_m) {
-        set_error("ddb_set_sample_range: need 0 <= first < last <= m");
+    // first == last: an EMPTY view (a rank of a sharded run that holds no sample of a batch or of the test part): the
+    // Gram / rss / residual / statistics passes then contribute zeros to the sums over the ranks
+    if (first < 0 || first > last || last > ctx->full_m) {
+        set_error("ddb_set_sample_range: need 0 <= first <= last <= m");
         return DDB_INVALID_ARG;
     }
     ctx->range_on = !(first == 0 && last == ctx->full_m);
+    ctx->view_empty = (first == last);
     ctx->dX = ctx->full_X + first * ctx->n;
     ctx->dY = ctx->full_Y + first * ctx->n_t;
     ctx->m = last - first;
     // The Gram kernels fetch sample tiles with 16-byte bulk copies: a view that starts on an odd double (odd
     // first with an odd number of states or targets, e.g. Lorenz with a batch size of 125) is staged once into an
     // aligned buffer of its own -- the reference accepts any batch size and split.
-    if ((((uintptr_t)ctx->dX) & 15) || (((uintptr_t)ctx->dY) & 15)) {
+    if (!ctx->view_empty && ((((uintptr_t)ctx->dX) & 15) || (((uintptr_t)ctx->dY) & 15))) {
         const size_t xb = (size_t)ctx->n * ctx->m * sizeof(double), yb = (size_t)ctx->n_t * ctx->m * sizeof(double);
         DDB_TRY(ctx->view_X.reserve(xb));
         DDB_TRY(ctx->view_Y.reserve(yb));
@@ -847,6 +853,7 @@ int ddb_bind_device(ddb_ctx* ctx, const double* dX, const double* dY, int n_t, i
     ctx->dX = dX;
     ctx->dY = dY;
     ctx->range_on = false;
+    ctx->view_empty = false;
     ctx->n_t = n_t;
     ctx->m = m;
     ctx->have_gram = false;

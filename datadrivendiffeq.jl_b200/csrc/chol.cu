@@ -34,6 +34,7 @@ constexpr int kCP = kCB + 4;       // shared-memory pitch: 132 = 4 (mod 16), con
 constexpr int kCK = 32;            // contraction chunk of the GEMMs
 constexpr int kCKP = kCK + 4;      // 36 = 4 (mod 16)
 constexpr int kCStage = 2 * kCB * kCKP;
+constexpr double kPivotTol = 64.0 * 2.220446049250313e-16;  // pivots of the equilibrated (unit-diagonal) matrices below this: breakdown
 
 struct CholBatch {
     double* base;        // matrix b at base + b * stride, row-major, leading dimension ld
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(256, 1) chol_diag128_kernel(CholBatch cb, int 
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
                 double d = __shfl_sync(0xffffffffu, a[c], c);
-                if (!(d > 0.0)) {
+                if (!(d > kPivotTol)) {  // unit-diagonal (equilibrated) matrices: numerically rank deficient
                     bad = 1;
                     d = 1.0;  // keep going with a harmless pivot; the flag invalidates the result
                 }

@@ -132,6 +132,7 @@ struct ddb_ctx {
     ddb::DevBuf d_resid, d_resid_terms, d_resid_partials;
     // sample view (ddb_set_sample_range): dX / dY / m above describe the view; the whole data set is kept here
     bool range_on = false;
+    bool view_empty = false;             // the current view holds no sample (ddb_set_sample_range(first, first))
     const double* full_X = nullptr;
     const double* full_Y = nullptr;
     int64_t full_m = 0;

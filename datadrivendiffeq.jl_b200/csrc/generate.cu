@@ -142,6 +142,7 @@ int generate_run(ddb_ctx* ctx, int system_id, int n_states, int64_t m, int64_t f
     DDB_CUDA_TRY(cudaGetLastError());
     DDB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     ctx->range_on = false;
+    ctx->view_empty = false;
     ctx->dX = a.X;
     ctx->dY = a.Y;
     ctx->n_t = n;

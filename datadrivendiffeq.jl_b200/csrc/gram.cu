@@ -649,6 +649,21 @@ int gram_run(ddb_ctx* ctx, double* dPacked) {
         set_error("ddb_gram: no library installed (call ddb_set_library_monomial first)");
         return DDB_BAD_STATE;
     }
+    if (ctx->view_empty && ctx->n_t > 0) {  // no sample in this rank's view: zero blocks (the other ranks hold the data)
+        const int64_t count = ddb_gram_count(ctx);
+        if (!dPacked) {
+            DDB_TRY(ctx->d_packed.reserve((size_t)count * sizeof(double)));
+            dPacked = ctx->d_packed.as<double>();
+        }
+        DDB_CUDA_TRY(cudaMemsetAsync(dPacked, 0, (size_t)count * sizeof(double), ctx->stream));
+        if (ctx->factors_nt != ctx->n_t) DDB_TRY(gram_ensure_factors(ctx, ((ctx->k + ctx->n_t + 127) / 128) * 128));
+        DDB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        ctx->timings.gram_ms = 0.0;
+        ctx->timings.gram_launches = 0;
+        ctx->have_gram = (dPacked == ctx->d_packed.as<double>());
+        ctx->imp_k = 0;
+        return DDB_OK;
+    }
     if (!ctx->dX || !ctx->dY || ctx->m <= 0) {
         set_error("ddb_gram: no data bound (call ddb_upload / ddb_bind_device / ddb_generate first)");
         return DDB_BAD_STATE;

@@ -343,6 +343,10 @@ static void rss_tile_shape(const ddb_ctx* ctx, int* sub_out, int* pitch_out) {
 static int rss_core(ddb_ctx* ctx, const RssCand& c, const int32_t* map, const RssTerm* targets, const double* scale,
                     DevBuf& terms, DevBuf& partials, double* dRss, int* launches, const double* mu = nullptr,
                     const double* extra_shift = nullptr) {
+    if (ctx->view_empty) {  // no sample in this rank's view: every streamed sum is zero
+        DDB_CUDA_TRY(cudaMemsetAsync(dRss, 0, (size_t)std::max(1, c.ncand) * 8, ctx->stream));
+        return DDB_OK;
+    }
     if (!ctx->dX || !ctx->dY || ctx->m <= 0) {
         set_error("ddb_rss: no data bound");
         return DDB_BAD_STATE;

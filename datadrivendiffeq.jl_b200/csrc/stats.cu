@@ -63,6 +63,21 @@ __global__ void target_reduce_kernel(const double* __restrict__ partials, int np
 }
 
 int target_stats_run(ddb_ctx* ctx, int64_t m_total, double* mean, double* css) {
+    if (ctx->view_empty && ctx->n_t > 0 && mean && css) {  // this rank contributes zeros to both sums
+        const int n_t = ctx->n_t;
+        cudaStream_t st = ctx->stream;
+        DDB_TRY(ctx->d_stats.reserve(2 * (size_t)n_t * 8));
+        double* d_sum = ctx->d_stats.as<double>();
+        std::vector<double> h(n_t);
+        for (int pass = 0; pass < 2; ++pass) {
+            DDB_CUDA_TRY(cudaMemsetAsync(d_sum, 0, (size_t)n_t * 8, st));
+            DDB_TRY(comm_allreduce(ctx, d_sum, n_t));
+            DDB_CUDA_TRY(cudaMemcpyAsync(h.data(), d_sum, (size_t)n_t * 8, cudaMemcpyDeviceToHost, st));
+            DDB_CUDA_TRY(cudaStreamSynchronize(st));
+            for (int e = 0; e < n_t; ++e) (pass == 0 ? mean : css)[e] = pass == 0 ? h[e] / (double)m_total : h[e];
+        }
+        return DDB_OK;
+    }
     if (!ctx->dY || ctx->m <= 0 || ctx->n_t <= 0) {
         set_error("ddb_target_stats: no data bound");
         return DDB_BAD_STATE;

@@ -444,6 +444,8 @@ struct SweepDev {
     // equilibrated system matrix; a solve with the full matrix and entry e of the right-hand side zeroed,
     // followed by z -= Ninv[:, e] * z[e] / Ninv[e, e], is the solve with row and column e deleted.
     int implicit;
+    int init_masked;        // the initial full least squares runs as a masked solve in the persistent kernel (the
+                            // shared factorisation broke down: rank-deficient library / fewer samples than terms)
     const double* Ninv;     // k x k (symmetric) or null
     // per target
     double* x;              // n_t x k
@@ -740,7 +742,7 @@ __global__ void __launch_bounds__(256) sweep_init_kernel(SweepDev S) {
     double* x = S.x + (size_t)e * k;
     double* xp = S.xprev + (size_t)e * k;
     const double* z = S.znew + (size_t)e * k;
-    if (S.implicit && S.algorithm == DDB_ALG_STLSQ) {
+    if ((S.implicit || S.init_masked) && S.algorithm == DDB_ALG_STLSQ) {
         // Implicit STLSQ: the initial least squares of target e runs on the library WITHOUT row e.  With an
         // exact implicit relation in the data the full Gram matrix is singular (that is the point of the
         // method) while G without a row of the relation is not, so there is no shared factorisation here: the
@@ -749,14 +751,14 @@ __global__ void __launch_bounds__(256) sweep_init_kernel(SweepDev S) {
         for (int i = threadIdx.x; i < k; i += blockDim.x) x[i] = xp[i] = 0.0;
         for (int w = threadIdx.x; w < W; w += blockDim.x) {
             uint32_t bits = (w * 32 + 32 <= k) ? 0xFFFFFFFFu : ((1u << (k - w * 32)) - 1u);
-            if (e / 32 == w) bits &= ~(1u << (e % 32));
+            if (S.implicit && e / 32 == w) bits &= ~(1u << (e % 32));
             act[w] = bits;
         }
         if (threadIdx.x == 0) {
             st.j = 0;
             st.iter = 0;
             st.counter = 0;
-            st.na = k - 1;
+            st.na = S.implicit ? k - 1 : k;
             st.status = kEqRunning;
             st.nruns = 0;
             st.last_cand = -1;
@@ -778,6 +780,83 @@ __global__ void __launch_bounds__(256) sweep_init_kernel(SweepDev S) {
     }
     if (threadIdx.x == 0) st.flags = 0;
     finish_init(S, e, redi);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Rank-deficient masked systems (fewer samples than active terms, collinear terms): minimum-norm least squares
+// ---------------------------------------------------------------------------------------------
+// The reference solves every STLSQ step with `A[p, :]' \ b` (STLSQ.jl:93-99, 135-140): pivoted QR, which returns the
+// MINIMUM-NORM least-squares solution when the system is rank deficient (its own "Skinny" test: 6 terms, 5 samples,
+// lib/DataDrivenSparse/test/Core/sparse_linear_solve.jl:63-96).  Through the normal equations that solution is
+// x = G_pp^+ r_p with the UN-scaled Gram block (the minimum norm is not invariant under column scaling).  When the
+// Cholesky factorisation of a small masked system breaks down, warp 0 diagonalises the block by cyclic Jacobi
+// rotations in shared memory (na <= kPinvMax) and applies the pseudo-inverse; eigenvalues below na * 16 eps * max
+// count as zero (singular values below ~1e-7 of the largest: what the squared condition number leaves of them).
+constexpr int kPinvMax = 64;
+
+// M: na x na symmetric (both triangles), V: na x na scratch, b: right-hand side -> solution.  Called by warp 0 only.
+__device__ void pinv_solve_warp(double* M, int ldm, double* V, int ldv, int na, double* b) {
+    const int lane = threadIdx.x & 31;
+    for (int e = lane; e < na * na; e += 32) V[(e / na) * ldv + e % na] = (e / na == e % na) ? 1.0 : 0.0;
+    __syncwarp();
+    for (int sweep = 0; sweep < 40; ++sweep) {
+        double off = 0.0, dg = 0.0;
+        for (int e = lane; e < na * na; e += 32) {
+            const int i = e / na, j = e % na;
+            const double v = M[i * ldm + j];
+            if (i == j) dg += v * v;
+            else off += v * v;
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            off += __shfl_xor_sync(0xffffffffu, off, o);
+            dg += __shfl_xor_sync(0xffffffffu, dg, o);
+        }
+        if (off <= 1e-30 * dg) break;
+        for (int p = 0; p < na - 1; ++p)
+            for (int q = p + 1; q < na; ++q) {
+                const double apq = M[p * ldm + q];
+                const double app = M[p * ldm + p], aqq = M[q * ldm + q];
+                if (fabs(apq) <= 1e-300 || fabs(apq) <= 1e-18 * sqrt(fabs(app * aqq))) continue;  // uniform over the warp
+                const double theta = (aqq - app) / (2.0 * apq);
+                const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+                __syncwarp();
+                for (int i = lane; i < na; i += 32) {  // columns p, q
+                    const double mip = M[i * ldm + p], miq = M[i * ldm + q];
+                    M[i * ldm + p] = c * mip - sn * miq;
+                    M[i * ldm + q] = sn * mip + c * miq;
+                    const double vip = V[i * ldv + p], viq = V[i * ldv + q];
+                    V[i * ldv + p] = c * vip - sn * viq;
+                    V[i * ldv + q] = sn * vip + c * viq;
+                }
+                __syncwarp();
+                for (int j = lane; j < na; j += 32) {  // rows p, q
+                    const double mpj = M[p * ldm + j], mqj = M[q * ldm + j];
+                    M[p * ldm + j] = c * mpj - sn * mqj;
+                    M[q * ldm + j] = sn * mpj + c * mqj;
+                }
+                __syncwarp();
+            }
+    }
+    double lmax = 0.0;
+    for (int i = 0; i < na; ++i) lmax = fmax(lmax, M[i * ldm + i]);
+    const double tol = (double)na * 16.0 * 2.220446049250313e-16 * lmax;
+    // x = sum_i [lambda_i > tol] (v_i' b / lambda_i) v_i ; lane = component
+    double x0 = 0.0, x1 = 0.0;
+    for (int i = 0; i < na; ++i) {
+        const double lam = M[i * ldm + i];
+        if (!(lam > tol)) continue;
+        double d = 0.0;
+        for (int j = lane; j < na; j += 32) d += V[j * ldv + i] * b[j];
+        for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+        d /= lam;
+        if (lane < na) x0 += d * V[lane * ldv + i];
+        if (lane + 32 < na) x1 += d * V[(lane + 32) * ldv + i];
+    }
+    __syncwarp();
+    if (lane < na) b[lane] = x0;
+    if (lane + 32 < na) b[lane + 32] = x1;
+    __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -853,10 +932,17 @@ __global__ void __launch_bounds__(256) stlsq_small_kernel(SweepDev S, int small_
         for (int i = threadIdx.x; i < na; i += blockDim.x) rhs[i] = rs[idx[i]];
         __syncthreads();
         // Cholesky in shared memory (right-looking, column at a time)
-        int bad = 0;
+        // The gathered block has a unit diagonal (equilibrated).  A pivot <= 0 is a breakdown; a pivot that is not
+        // clearly positive is SUSPICIOUS: the block is either numerically rank deficient (fewer samples than terms,
+        // collinear terms: the reference's pivoted QR then returns the minimum-norm solution) or merely very ill
+        // conditioned (exact implicit relations: condition 1e13, yet full rank).  The two are told apart below by the
+        // residual of the minimum-norm candidate.
+        const double piv_tol = (double)na * 16.0 * 2.220446049250313e-16;
+        int bad = 0, suspicious = 0;
         for (int c = 0; c < na; ++c) {
             const double d = M[c * ldm + c];
             if (!(d > 0.0)) bad = 1;
+            if (!(d > piv_tol)) suspicious = 1;
             const double piv = (d > 0.0) ? sqrt(d) : 1.0;
             __syncthreads();
             if (threadIdx.x == 0) M[c * ldm + c] = piv;
@@ -869,7 +955,8 @@ __global__ void __launch_bounds__(256) stlsq_small_kernel(SweepDev S, int small_
             }
             __syncthreads();
         }
-        if (bad && threadIdx.x == 0) st.flags |= 1;
+        const bool try_pinv = suspicious && na <= kPinvMax && S.algorithm == DDB_ALG_STLSQ;
+        if (bad && !try_pinv && threadIdx.x == 0) st.flags |= 1;
         // forward / backward substitution by warp 0 (na <= small_max: serial over columns, lanes over rows)
         if (threadIdx.x < 32) {
             const int lane = threadIdx.x;
@@ -889,9 +976,47 @@ __global__ void __launch_bounds__(256) stlsq_small_kernel(SweepDev S, int small_
             }
         }
         __syncthreads();
-        // X[p] = solution (un-scaled)   (STLSQ.jl:128-140)
-        for (int i = threadIdx.x; i < na; i += blockDim.x) x[idx[i]] = rhs[i] * S.dinv[idx[i]];
-        __syncthreads();
+        if (try_pinv) {
+            // minimum-norm candidate x_p = G_pp^+ r_p on the UN-scaled block; it replaces the Cholesky solution when
+            // the factorisation broke down or when x_p solves the normal equations (residual ~ rounding): the block
+            // is then rank deficient and x_p is what `A[p, :]' \ b` returns in the reference
+            const double xc = (threadIdx.x < na) ? rhs[threadIdx.x] * S.dinv[idx[threadIdx.x]] : 0.0;
+            __syncthreads();
+            for (int t = threadIdx.x; t < na * na; t += blockDim.x) {
+                const int i = t / na, j = t % na;
+                const double di = S.dinv[idx[i]], dj = S.dinv[idx[j]];
+                M[i * ldm + j] = (di > 0.0 && dj > 0.0) ? S.As[(size_t)idx[i] * k + idx[j]] / (di * dj) : 0.0;
+            }
+            for (int i = threadIdx.x; i < na; i += blockDim.x) {
+                const double di = S.dinv[idx[i]];
+                rhs[i] = di > 0.0 ? rs[idx[i]] / di : 0.0;
+            }
+            __syncthreads();
+            if (threadIdx.x < 32) pinv_solve_warp(M, ldm, M + (size_t)kPinvMax * ldm, ldm, na, rhs);
+            __syncthreads();
+            double ri = 0.0, bi = 0.0;
+            if (threadIdx.x < na) {
+                const int i = threadIdx.x;
+                const double di = S.dinv[idx[i]];
+                bi = di > 0.0 ? rs[idx[i]] / di : 0.0;
+                double acc = -bi;
+                for (int j = 0; j < na; ++j) {
+                    const double dj = S.dinv[idx[j]];
+                    if (di > 0.0 && dj > 0.0) acc = fma(S.As[(size_t)idx[i] * k + idx[j]] / (di * dj), rhs[j], acc);
+                }
+                ri = acc;
+            }
+            const double res2 = block_sum(ri * ri, red);
+            const double b2 = block_sum(bi * bi, red);
+            const bool use_p = bad || res2 <= 1e-14 * b2;
+            if (threadIdx.x < na) x[idx[threadIdx.x]] = use_p ? rhs[threadIdx.x] : xc;
+            if (use_p && threadIdx.x == 0) st.flags |= 2;  // bit 1: a minimum-norm solution was used
+            __syncthreads();
+        } else {
+            // X[p] = solution (un-scaled)   (STLSQ.jl:128-140)
+            for (int i = threadIdx.x; i < na; i += blockDim.x) x[idx[i]] = rhs[i] * S.dinv[idx[i]];
+            __syncthreads();
+        }
         if (st.pad[0])
             finish_init(S, e, redi);  // that was the initial solve of an implicit target, not a step
         else
@@ -1446,6 +1571,17 @@ int sweep_run(ddb_ctx* ctx, const ddb_sweep_params* prm, const double* lambdas, 
     }
     SweepDev D = make_dev(ctx, S);
     if (use_inverse) D.zsol = S->zsol.as<double>();
+    if (shared_factor && prm->algorithm == DDB_ALG_STLSQ && k <= kPinvMax) {
+        // small libraries: a factorisation that broke down (fewer samples than terms, collinear terms) is not an error --
+        // the initial least squares then runs as a masked solve with the minimum-norm fallback (pinv_solve_warp)
+        int h_fail = 0;
+        DDB_CUDA_TRY(cudaMemcpyAsync(&h_fail, S->shared_fail.p, 4, cudaMemcpyDeviceToHost, st));
+        DDB_CUDA_TRY(cudaStreamSynchronize(st));
+        if (h_fail) {
+            D.init_masked = 1;
+            DDB_CUDA_TRY(cudaMemsetAsync(S->shared_fail.p, 0, 4, st));
+        }
+    }
     sweep_init_kernel<<<n_t, 256, 0, st>>>(D);
     ++launches;
     DDB_CUDA_TRY(cudaGetLastError());

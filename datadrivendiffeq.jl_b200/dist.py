@@ -124,3 +124,30 @@ def solve_sharded(ctx, X_local: np.ndarray, Y_local: np.ndarray, prm, lambdas, g
     if not _has_comm(ctx) and hasattr(ctx, "comm_init_rank"):
         init_comm(ctx, group)
     return reduce_blocks_and_sweep(ctx, prm, lambdas, m_total, group, paths, host_data=(X_local, Y_local)), m_total
+
+
+def allreduce_host_sum(ctx, values, group=None):
+    """Sum over the ranks of a small host array (statistics, counts): through the library's communicator when the
+    context has one, else ``torch.distributed``."""
+    torch, dist = _torch()
+    a = np.ascontiguousarray(values, dtype=np.float64).ravel()
+    dev = f"cuda:{ctx.device}" if hasattr(ctx, "comm_info") else "cpu"
+    t = torch.from_numpy(a.copy()).to(dev)
+    if _has_comm(ctx):
+        ctx.allreduce_sum(t.data_ptr(), t.numel())
+        ctx.synchronize()
+    else:
+        allreduce_sum(t, group)
+    return t.cpu().numpy().reshape(np.shape(values))
+
+
+def shard_offsets(m_local: int, group=None, device="cpu"):
+    """``(first global sample of this rank, total samples)`` for contiguous row shards in rank order."""
+    torch, dist = _torch()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    t = torch.zeros(world, dtype=torch.int64, device=device)
+    t[rank] = int(m_local)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    counts = t.cpu().numpy()
+    return int(counts[:rank].sum()), int(counts.sum())
+

@@ -204,7 +204,9 @@ int ddb_gram_upload(ddb_ctx* ctx, const double* G, const double* R, const double
 
 /* ---- pre-/post-processing options of the reference on the device ---------------------------------
  * ddb_set_sample_range: the following ddb_gram / ddb_rss / ddb_residual calls see samples [first, last) of the
- *   bound data only (last < 0 = to the end; any first / last: a view that does not start on a 16-byte boundary --
+ *   bound data only (last < 0 = to the end; first == last is an EMPTY view -- a rank of a sharded run that holds no
+ *   sample of a batch or of the test part: every pass then contributes zeros to the sums over the ranks; any first /
+ *   last otherwise: a view that does not start on a 16-byte boundary --
  *   odd first with an odd n or n_t -- is staged once into an aligned buffer for the bulk copies of the Gram
  *   kernels).  Replaces `splitobs(data, at = split)` and the
  *   batches of the `DataLoader` (src/utils/data_processing.jl:29-39): train part, test part and every batch are

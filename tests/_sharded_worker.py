@@ -37,6 +37,29 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
         return
+    if alg == "PROCESSED":  # ZScore + split + shuffled batches on shards against the single-GPU run
+        Xs, Ds = systems.lorenz_ensemble(2001, seed=1, samples_per_traj=500)
+        Xs, Ds = Xs[:, :1901], Ds[:, :1901] + 0.05 * np.random.default_rng(1).standard_normal((3, 1901))
+        mm = Xs.shape[1]
+        basis = ddb200.polynomial_basis(3, 3)
+        lam = 10.0 ** np.arange(-1, 1.01, 0.25)
+        m_train = int(round(0.8 * mm))
+        opts = ddb200.DataDrivenCommonOptions(normalize="ZScoreTransform", split=0.8, batchsize=400, partial=True,
+                                              perm=np.random.default_rng(3).permutation(m_train))
+        lo, hi = ddb200.dist.shard_range(mm, rank, world)
+        sol = ddb200.solve(ddb200.ContinuousDataDrivenProblem(Xs[:, lo:hi], DX=Ds[:, lo:hi]), basis,
+                           ddb200.B200Sparse(ddb200.STLSQ(lam), device=local, group=dist.group.WORLD), opts)
+        if rank == 0:
+            one = ddb200.solve(ddb200.ContinuousDataDrivenProblem(Xs, DX=Ds), basis, ddb200.B200Sparse(ddb200.STLSQ(lam), device=local), opts)
+            np.savez(out_path, nres=len(sol.results), nres1=len(one.results),
+                     coef=np.stack([r.coefficients for r in sol.results]), coef1=np.stack([r.coefficients for r in one.results]),
+                     test=np.array([r.testerror for r in sol.results]), test1=np.array([r.testerror for r in one.results]),
+                     train=np.array([r.trainerror for r in sol.results]), train1=np.array([r.trainerror for r in one.results]),
+                     final=sol.coefficients, final1=one.coefficients, rss=sol.rss, rss1=one.rss, r2=sol.r2(), r21=one.r2(),
+                     nobs=sol.nobs, nobs1=one.nobs)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     n, m = 12, 6000
     X, D = systems.lorenz96_ensemble(m, n=n, seed=11, samples_per_traj=500)
     D = D + 1e-2 * np.random.default_rng(2).standard_normal(D.shape)

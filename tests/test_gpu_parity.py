@@ -262,15 +262,35 @@ def test_zero_target_and_zero_library_term(ctx):
     assert np.count_nonzero(out.coefficients[1]) == 1 and abs(out.coefficients[1, 1] - 2.0) < 1e-12
 
 
-def test_rank_deficient_library_is_reported(ctx):
+def test_rank_deficient_library(ctx):
+    """15 terms, 10 samples: the Gram matrix is singular.  Small libraries (<= 64 terms) follow the reference through
+    its minimum-norm steps (see test_skinny_fewer_samples_than_terms); larger ones are reported as
+    DDB_NOT_POSITIVE_DEFINITE -- never a silent fallback, never a garbage solution from a tiny pivot."""
     rng = np.random.default_rng(4)
-    X = rng.standard_normal((2, 10))  # 15 terms, 10 samples: Gram matrix singular
-    ctx.set_library(oracle.polynomial_exponents(2, 4))
+    X = rng.standard_normal((2, 10))
+    ex = oracle.polynomial_exponents(2, 4)
+    ctx.set_features(0, None)
+    ctx.set_library(ex)
     ctx.upload(X, X.copy())
+    ctx.gram()
+    lams = np.array([0.1, 0.3])
+    ctx.sweep(ctx.make_params("STLSQ"), lams)
+    ctx.rss()
+    out = ctx.select(paths=True)
+    traces = []
+    ref = oracle.sparse_regression(oracle.STLSQ(lams), oracle.evaluate_library(ex, X), X, traces=traces)
+    for i in range(2):
+        np.testing.assert_array_equal(out.support_path[i], np.stack(traces[i].support_path))
+    np.testing.assert_allclose(out.coefficients, ref.coefficients, rtol=1e-6, atol=1e-9)
+    assert not (out.flags & 1).any() and (out.flags & 2).all()  # bit 1: minimum-norm steps were taken
+    # 91 terms, 50 samples: beyond the shared-memory pseudo-inverse
+    X = rng.standard_normal((12, 50))
+    ctx.set_library(oracle.polynomial_exponents(12, 2))
+    ctx.upload(X, X[:2].copy())
     ctx.gram()
     with pytest.raises(ddb200._lib.DDBError) as ei:
         ctx.sweep(ctx.make_params("STLSQ"), np.array([0.1]))
-    assert ei.value.status == -5  # DDB_NOT_POSITIVE_DEFINITE, never a silent fallback
+    assert ei.value.status == -5  # DDB_NOT_POSITIVE_DEFINITE
 
 
 # ------------------------------------------------------------------------------------------------
@@ -501,3 +521,72 @@ def test_c4_library_size_relaxed_algorithms_match_oracle_traces(ctx, golden_dir,
     np.testing.assert_array_equal(out.iterations, g["iterations"])
     if alg == "ADMM":
         np.testing.assert_allclose(out.lambda_opt, g["lambda_opt"], rtol=1e-15)
+
+
+# ------------------------------------------------------------------------------------------------
+# fewer samples than terms / rank-deficient libraries: the reference's "Skinny" test
+# ------------------------------------------------------------------------------------------------
+def _skinny():
+    # lib/DataDrivenSparse/test/Core/sparse_linear_solve.jl:63-96: 6 terms x 5 samples, noise-free
+    rng = np.random.default_rng(52)
+    t = np.arange(0.0, 2.0 + 1e-9, 0.5)
+    Th = np.stack([np.sin(0.5 * t), np.cos(0.5 * t), np.sin(2.0 * t**2), np.cos(0.5 * t**2), np.exp(-t), rng.standard_normal(t.size)])
+    A = np.array([[0.68, 0.0, 0.0, 0.0, -1.2, 0.0]])
+    return Th, A @ Th
+
+
+@pytest.mark.parametrize("alg", ["STLSQ", "ADMM", "SR3"])
+def test_skinny_fewer_samples_than_terms(ctx, alg):
+    """The reference's "Skinny" test: the Gram matrix of 6 terms over 5 samples is singular.  STLSQ's steps are
+    minimum-norm least squares there (pivoted QR in the reference, the Jacobi pseudo-inverse of the un-scaled Gram block
+    here); ADMM's "fat" branch (ADMM.jl:82-86, 123-139) is the Woodbury form of the same solve with G + rho I, which is
+    positive definite and needs no special case.  Assertions of the reference (rss <= 0.15, aicc <= -5, dof == 2,
+    r2 ~ 1) and parity with the oracle."""
+    Th, Y = _skinny()
+    lams = np.linspace(0.1, 1.6, 15)
+    mk = {"STLSQ": oracle.STLSQ(lams), "ADMM": oracle.ADMM(lams), "SR3": oracle.SR3(lams)}[alg]
+    traces = []
+    ref = oracle.sparse_regression(mk, Th, Y, oracle.CommonOptions(maxiters=10_000), traces=traces)
+    # the library rows are the "states": an identity library of 6 states over 5 samples
+    ctx.set_features(0, None)
+    ctx.set_library(np.eye(6, dtype=np.uint8))
+    ctx.upload(Th, Y)
+    ctx.gram()
+    prm = ctx.make_params(alg, rho=0.0 if alg == "STLSQ" else 1.0, proximal="HardThreshold" if alg == "SR3" else "SoftThreshold",
+                          maxiters=10_000)
+    ctx.sweep(prm, mk.thresholds)
+    ctx.rss()
+    out = ctx.select(paths=True)
+    np.testing.assert_array_equal(out.support_path[0], np.stack(traces[0].support_path))
+    np.testing.assert_array_equal(out.coefficients != 0, ref.coefficients != 0)
+    nz = ref.coefficients != 0
+    assert (np.abs(out.coefficients[nz] - ref.coefficients[nz]) / np.abs(ref.coefficients[nz])).max() <= 1e-7
+    # the reference's own assertions
+    n = Y.size
+    rss, dof = float(out.rss[0]), int(out.dof[0])
+    assert rss <= 1.5e-1 and dof == 2
+    ll = -n / 2 * np.log(max(rss, 1e-300) / n)
+    assert -2 * ll + 2 * dof + 2 * dof * (dof + 1) / (n - dof - 1) <= -5.0
+    assert not (out.flags & 1).any()
+
+
+def test_collinear_library_minimum_norm(ctx):
+    """A library with an exactly repeated direction (x, y, x + y as three 'states'): rank-deficient Gram matrix with
+    MORE samples than terms.  Every STLSQ step is the minimum-norm solution, as `A' \\ b` gives in the reference."""
+    rng = np.random.default_rng(2)
+    m = 200
+    a, b = rng.standard_normal(m), rng.standard_normal(m)
+    Th = np.stack([a, b, a + b, rng.standard_normal(m)])
+    Y = (1.0 * a + 2.0 * b + 0.5 * Th[3])[None, :] + 1e-3 * rng.standard_normal((1, m))
+    lams = np.array([0.05, 0.2, 0.7])
+    traces = []
+    ref = oracle.sparse_regression(oracle.STLSQ(lams), Th, Y, traces=traces)
+    ctx.set_library(np.eye(4, dtype=np.uint8))
+    ctx.upload(Th, Y)
+    ctx.gram()
+    ctx.sweep(ctx.make_params("STLSQ"), lams)
+    ctx.rss()
+    out = ctx.select(paths=True)
+    np.testing.assert_array_equal(out.support_path[0], np.stack(traces[0].support_path))
+    np.testing.assert_allclose(out.coef_path[0], np.stack(traces[0].coef_path), rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(out.coefficients, ref.coefficients, rtol=1e-7, atol=1e-9)

@@ -58,7 +58,7 @@ def test_default_options_match_reference():
     assert o.abstol == o.reltol == math.sqrt(np.finfo(float).eps)
 
 
-@pytest.mark.parametrize("kw", [dict(denoise=True), dict(normalize="UnitRangeTransform"), dict(roundingmode="RoundNearest"),
+@pytest.mark.parametrize("kw", [dict(denoise=True), dict(normalize="MinMaxSomething"), dict(roundingmode="RoundNearest"),
                                 dict(selector="mdl")])
 def test_unsupported_options_raise(kw):
     from ddb200.api import _check_options
