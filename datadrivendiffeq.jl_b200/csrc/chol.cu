@@ -141,7 +141,9 @@ __global__ void __launch_bounds__(256, 1) chol_diag128_kernel(CholBatch cb, int 
 #pragma unroll
                 for (int j = c + 1; j < 32; ++j) {
                     // unconditional: entries above the diagonal (j > lane) hold garbage that is never read by a
-                    // valid lane (d comes from lane c, lj from lane j) and never stored
+                    // valid lane (d comes from lane c, lj from lane j) and never stored.  (Broadcasting the column
+                    // through shared memory instead of these shuffles was measured: not faster -- the block's time is
+                    // the chain of ~11 dependent FP64 operations per column, not the shuffle unit.)
                     const double lj = __shfl_sync(0xffffffffu, l, j);
                     a[j] = fma(-l, lj, a[j]);
                 }
@@ -343,6 +345,98 @@ __global__ void __launch_bounds__(256, 1) chol_syrk128_kernel(CholBatch cb, int 
     }
 }
 
+// The same trailing update with 64 x 64 tiles, four warps (32 x 32 patches) and three CTAs per SM: a single matrix of
+// order 2145 gives at most 136 tiles of 128 x 128 -- one wave whose length is the latency of ONE tile (17 us of DMMA
+// on one SM) whatever the tile count; quarter-size tiles cut that latency by four and still fill the machine
+// (544 tiles on 444 slots).  Batches that fill the machine with 128 x 128 tiles keep those (fewer fragment loads per
+// DMMA).  grid (column tiles, row tiles, batch)
+constexpr int kSB = 64;
+constexpr int kSStage = 2 * kSB * kCKP;
+__global__ void __launch_bounds__(128, 3) chol_syrk64_kernel(CholBatch cb, int j0) {
+    const int b = blockIdx.z;
+    const int na = cb.na_arr ? cb.na_arr[b] : cb.na_all;
+    if (j0 >= na) return;
+    const int nb = min(kCB, na - j0);
+    const int t0 = j0 + nb, rows = na - t0, rows_all = rows + cb.extra;
+    const int r0 = blockIdx.y * kSB, c0 = blockIdx.x * kSB;
+    if (r0 >= rows_all || c0 > r0 || c0 >= rows) return;
+    extern __shared__ __align__(16) double gsm[];
+    double* A = cb.base + (size_t)b * cb.stride;
+    const int ld = cb.ld;
+    const double* Bop = A + (size_t)(t0 + c0) * ld + j0;
+    const int bcols = rows - c0;
+    const int xoff = cb.xrow - t0 - rows;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int row0 = (warp >> 1) * 32, col0 = (warp & 1) * 32;
+    const int nchunks = (nb + kCK - 1) / kCK;
+
+    auto stage_load = [&](int chunk, int buf) {
+        double* sa = gsm + (size_t)buf * kSStage;
+        double* sb = sa + kSB * kCKP;
+        const int k0 = chunk * kCK;
+#pragma unroll 4
+        for (int e = tid; e < kSB * kCK; e += 128) {
+            const int r = e >> 5, kk = e & 31;
+            double* da = sa + r * kCKP + kk;
+            const int rr = r0 + r;
+            if (rr < rows_all && k0 + kk < nb) cp8c(da, A + (size_t)(t0 + rr + (rr >= rows ? xoff : 0)) * ld + j0 + k0 + kk);
+            else *da = 0.0;
+            double* db = sb + r * kCKP + kk;
+            if (r < bcols && k0 + kk < nb) cp8c(db, Bop + (size_t)r * ld + k0 + kk);
+            else *db = 0.0;
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    stage_load(0, 0);
+    for (int ch = 0; ch < nchunks; ++ch) {
+        const int buf = ch & 1;
+        if (ch + 1 < nchunks) {
+            stage_load(ch + 1, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const double* sa = gsm + (size_t)buf * kSStage + (row0 + g) * kCKP + t;
+        const double* sb = gsm + (size_t)buf * kSStage + kSB * kCKP + (col0 + g) * kCKP + t;
+#pragma unroll
+        for (int kk = 0; kk < kCK / 4; ++kk) {
+            double a[4], bq[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = sa[8 * i * kCKP + 4 * kk];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bq[j] = sb[8 * j * kCKP + 4 * kk];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], bq[j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = r0 + row0 + 8 * i + g;
+        if (r >= rows_all) continue;
+        double* arow = A + (size_t)(t0 + r + (r >= rows ? xoff : 0)) * ld;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int c = c0 + col0 + 8 * j + 2 * t + h;
+                if (c < rows && c <= r) atomicAdd(arow + t0 + c, -acc[i][j][h]);  // RED: see chol_syrk128_kernel
+            }
+        }
+    }
+}
+
 // Backward substitution x = L^-T y, one CTA per (right-hand side, matrix), left-looking over 32-row blocks from the
 // bottom: the contributions of the entries already solved are dot products along the ROWS of L' (stored above the
 // diagonal by the PANEL step: coalesced), the 32 x 32 diagonal block is substituted by one warp.
@@ -375,11 +469,17 @@ __global__ void __launch_bounds__(1024) chol_back_kernel(CholBatch cb, int yrow0
             const double* row = A + (size_t)(j0 + warp) * ld;
             double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
             int j = end + lane;
-            for (; j + 96 < na; j += 128) {
-                s0 = fma(__ldg(row + j), x[j], s0);
-                s1 = fma(__ldg(row + j + 32), x[j + 32], s1);
-                s2 = fma(__ldg(row + j + 64), x[j + 64], s2);
-                s3 = fma(__ldg(row + j + 96), x[j + 96], s3);
+            for (; j + 224 < na; j += 256) {
+                const double v0 = __ldg(row + j), v1 = __ldg(row + j + 32), v2 = __ldg(row + j + 64), v3 = __ldg(row + j + 96);
+                const double v4 = __ldg(row + j + 128), v5 = __ldg(row + j + 160), v6 = __ldg(row + j + 192), v7 = __ldg(row + j + 224);
+                s0 = fma(v0, x[j], s0);
+                s1 = fma(v1, x[j + 32], s1);
+                s2 = fma(v2, x[j + 64], s2);
+                s3 = fma(v3, x[j + 96], s3);
+                s0 = fma(v4, x[j + 128], s0);
+                s1 = fma(v5, x[j + 160], s1);
+                s2 = fma(v6, x[j + 192], s2);
+                s3 = fma(v7, x[j + 224], s3);
             }
             for (; j < na; j += 32) s0 = fma(__ldg(row + j), x[j], s0);
             double sv = (s0 + s1) + (s2 + s3);
@@ -418,6 +518,8 @@ int chol128_batched(ddb_ctx* ctx, double* base, size_t stride, int ld, const int
     DDB_CUDA_TRY(cudaFuncSetAttribute(chol_diag128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem));
     DDB_CUDA_TRY(cudaFuncSetAttribute(chol_panel128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
     DDB_CUDA_TRY(cudaFuncSetAttribute(chol_syrk128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+    const size_t g64smem = 2 * (size_t)kSStage * sizeof(double);
+    DDB_CUDA_TRY(cudaFuncSetAttribute(chol_syrk64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g64smem));
     cudaStream_t st = ctx->stream;
     int n = 0;
     for (int j0 = 0; j0 < na_max; j0 += kCB) {
@@ -429,7 +531,14 @@ int chol128_batched(ddb_ctx* ctx, double* base, size_t stride, int ld, const int
         chol_panel128_kernel<<<dim3(Tr, batch), 256, psmem, st>>>(cb, j0);
         ++n;
         if (Tc > 0) {
-            chol_syrk128_kernel<<<dim3(Tc, Tr, batch), 256, gsmem, st>>>(cb, j0);
+            // lower tiles of 128 x 128 in this launch; fewer than two per SM: quarter-size tiles (see chol_syrk64_kernel)
+            const long long tiles128 = (long long)batch * (Tc * (Tc + 1) / 2 + (Tr - Tc) * Tc);
+            if (tiles128 < 2LL * ctx->sm_count) {
+                const int Tr64 = (rem + extra + kSB - 1) / kSB, Tc64 = (rem + kSB - 1) / kSB;
+                chol_syrk64_kernel<<<dim3(Tc64, Tr64, batch), 128, g64smem, st>>>(cb, j0);
+            } else {
+                chol_syrk128_kernel<<<dim3(Tc, Tr, batch), 256, gsmem, st>>>(cb, j0);
+            }
             ++n;
         }
     }

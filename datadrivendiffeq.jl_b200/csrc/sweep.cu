@@ -490,9 +490,9 @@ __device__ __forceinline__ double threshold_cut(const SweepDev& S, double lam) {
 // Append / merge the candidate described by the CURRENT x of target e (sparse: entries != 0) with
 // dof = number of active entries.  Consecutive identical candidates extend the current run.
 // Called by all threads of the CTA; `red`/`redi` are shared scratch of >= 32 entries.
-__device__ void record_candidate(const SweepDev& S, int e, int j, int dof, double* red, int* redi, int* s_tmp) {
+__device__ void record_candidate(const SweepDev& S, int e, int j, int dof, double* red, int* redi, int* s_tmp,
+                                 const double* x) {
     const int k = S.k;
-    const double* x = S.x + (size_t)e * k;
     EqState& st = S.eq[e];
     // number of nonzeros
     int cnt = 0;
@@ -573,11 +573,11 @@ __device__ void record_candidate(const SweepDev& S, int e, int j, int dof, doubl
 // After the solve of one step wrote the new coefficients into x (entries of the old active set),
 // finish the step exactly as `step!` + the body of the solver loop do.  xprev must already hold the
 // pre-step x.  Returns nothing; updates the target's state machine.
-__device__ void finish_step(const SweepDev& S, int e, double* red, int* redi, int* s_tmp) {
+// x / xp: the target's coefficient vectors -- in global memory (S.x + e k, S.xprev + e k) or the persistent kernel's
+// shared-memory copies
+__device__ void finish_step(const SweepDev& S, int e, double* red, int* redi, int* s_tmp, double* x, const double* xp) {
     const int k = S.k, W = S.W;
     EqState& st = S.eq[e];
-    double* x = S.x + (size_t)e * k;
-    const double* xp = S.xprev + (size_t)e * k;
     uint32_t* act = S.active + (size_t)e * W;
     const int j = st.j;
     const double lam = S.lambdas[j];
@@ -610,7 +610,7 @@ __device__ void finish_step(const SweepDev& S, int e, double* red, int* redi, in
     const double delta = sqrt(block_sum(d2, red));
     const double nx = sqrt(block_sum(n2, red));
     __syncthreads();
-    record_candidate(S, e, j, na, red, redi, s_tmp);
+    record_candidate(S, e, j, na, red, redi, s_tmp, x);
     // convergence (_is_converged, DataDrivenSparse.jl:160-168)
     bool conv = (na == 0) || (delta < S.abstol) || (delta / nx < S.reltol);
     if (threadIdx.x == 0) {
@@ -698,10 +698,9 @@ int implicit_select(ddb_ctx* ctx, const int32_t* idx, int kk) {
 // ---------------------------------------------------------------------------------------------
 // Tail of init_cache for target e, given the initial full solution in x: initial mask (strict cut at the
 // smallest threshold), state machine, zero-model candidate.  Called by all threads of the CTA.
-__device__ void finish_init(const SweepDev& S, int e, int* redi) {
+__device__ void finish_init(const SweepDev& S, int e, int* redi, const double* x) {
     const int k = S.k, W = S.W;
     EqState& st = S.eq[e];
-    const double* x = S.x + (size_t)e * k;
     uint32_t* act = S.active + (size_t)e * W;
     const double cut = threshold_cut(S, S.lambdas[0]);  // lambdas sorted: [0] is the minimum
     __syncthreads();
@@ -779,7 +778,7 @@ __global__ void __launch_bounds__(256) sweep_init_kernel(SweepDev S) {
         if (S.aux2) S.aux2[(size_t)e * k + i] = 0.0;
     }
     if (threadIdx.x == 0) st.flags = 0;
-    finish_init(S, e, redi);
+    finish_init(S, e, redi, x);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -862,7 +861,7 @@ __device__ void pinv_solve_warp(double* M, int ldm, double* V, int ldv, int na, 
 // ---------------------------------------------------------------------------------------------
 // STLSQ: persistent small-support kernel (one CTA per target)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) stlsq_small_kernel(SweepDev S, int small_max) {
+__global__ void __launch_bounds__(256) stlsq_small_kernel(SweepDev S, int small_max, int x_in_smem) {
     const int e = blockIdx.x;
     const int k = S.k, W = S.W;
     extern __shared__ double smem[];
@@ -873,21 +872,35 @@ __global__ void __launch_bounds__(256) stlsq_small_kernel(SweepDev S, int small_
     __shared__ int redi[32];
     __shared__ int s_tmp[4];
     EqState& st = S.eq[e];
-    double* x = S.x + (size_t)e * k;
-    double* xp = S.xprev + (size_t)e * k;
+    double* xg = S.x + (size_t)e * k;
+    double* xpg = S.xprev + (size_t)e * k;
+    // The target's coefficient vectors live in shared memory for the whole run of the kernel when they fit (every step
+    // makes several passes over all k entries: previous iterate, threshold / difference norms, candidate comparison --
+    // from global memory each pass costs an L2 round trip, and a noise-free sweep is ~80 such steps in a row)
+    double* x = x_in_smem ? reinterpret_cast<double*>(idx + small_max + (small_max & 1)) : xg;
+    double* xp = x_in_smem ? x + k : xpg;
+    if (x_in_smem) {
+        for (int i = threadIdx.x; i < k; i += blockDim.x) x[i] = xg[i], xp[i] = xpg[i];
+    }
     const uint32_t* act = S.active + (size_t)e * W;
     const double* rs = S.rs + (size_t)e * k;
     const int ldm = small_max + 1;
 
     while (true) {
         __syncthreads();
-        if (st.status != kEqRunning) break;
+        if (st.status != kEqRunning) {
+            if (x_in_smem)  // the blocked path and the selector read the iterate from global memory
+                for (int i = threadIdx.x; i < k; i += blockDim.x) xg[i] = x[i], xpg[i] = xp[i];
+            break;
+        }
         const int na = st.na;
         if (na > small_max) {
             if (threadIdx.x == 0) {
                 st.status = kEqNeedBig;
                 atomicAdd(&S.counters[3], 1);
             }
+            if (x_in_smem)
+                for (int i = threadIdx.x; i < k; i += blockDim.x) xg[i] = x[i], xpg[i] = xp[i];
             break;
         }
         // X_prev .= X   (STLSQ.jl:120)
@@ -1018,9 +1031,9 @@ __global__ void __launch_bounds__(256) stlsq_small_kernel(SweepDev S, int small_
             __syncthreads();
         }
         if (st.pad[0])
-            finish_init(S, e, redi);  // that was the initial solve of an implicit target, not a step
+            finish_init(S, e, redi, x);  // that was the initial solve of an implicit target, not a step
         else
-            finish_step(S, e, red, redi, s_tmp);
+            finish_step(S, e, red, redi, s_tmp, x, xp);
     }
 }
 
@@ -1088,9 +1101,9 @@ __global__ void __launch_bounds__(256) stlsq_big_finish_kernel(SweepDev S, const
     }
     __syncthreads();
     if (S.eq[e].pad[0])
-        finish_init(S, e, redi);  // initial solve of an implicit target
+        finish_init(S, e, redi, x);  // initial solve of an implicit target
     else
-        finish_step(S, e, red, redi, s_tmp);
+        finish_step(S, e, red, redi, s_tmp, x, S.xprev + (size_t)e * k);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1206,7 +1219,7 @@ __global__ void __launch_bounds__(256) relax_finish_kernel(SweepDev S) {
         }
     }
     __syncthreads();
-    finish_step(S, e, red, redi, s_tmp);
+    finish_step(S, e, red, redi, s_tmp, x, S.xprev + (size_t)e * k);
 }
 
 __global__ void count_status_kernel(const EqState* eq, int n_t, int* counters) {
@@ -1590,10 +1603,12 @@ int sweep_run(ddb_ctx* ctx, const ddb_sweep_params* prm, const double* lambdas, 
     // ---- the sweep -----------------------------------------------------------------------------
     int h_shared_fail = 0;
     if (prm->algorithm == DDB_ALG_STLSQ) {
-        const size_t small_smem = ((size_t)kSmallMax * (kSmallMax + 1) + kSmallMax) * sizeof(double) + kSmallMax * sizeof(int);
+        const size_t base_smem = ((size_t)kSmallMax * (kSmallMax + 1) + kSmallMax) * sizeof(double) + (kSmallMax + 2) * sizeof(int);
+        const int x_in_smem = base_smem + 2 * (size_t)k * sizeof(double) <= 200 * 1024;
+        const size_t small_smem = base_smem + (x_in_smem ? 2 * (size_t)k * sizeof(double) : 0);
         DDB_CUDA_TRY(cudaFuncSetAttribute(stlsq_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem));
         for (int round = 0;; ++round) {
-            stlsq_small_kernel<<<n_t, 256, small_smem, st>>>(D, kSmallMax);
+            stlsq_small_kernel<<<n_t, 256, small_smem, st>>>(D, kSmallMax, x_in_smem);
             count_status_kernel<<<1, 32, 0, st>>>(D.eq, n_t, D.counters);
             launches += 2;
             DDB_CUDA_TRY(cudaMemcpyAsync(h_counters, S->counters.p, sizeof(h_counters), cudaMemcpyDeviceToHost, st));

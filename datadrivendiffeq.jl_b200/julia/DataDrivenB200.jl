@@ -7,7 +7,12 @@
 # Usage (drop-in, the reference's `solve` API is unchanged):
 #
 #     using DataDrivenDiffEq, DataDrivenSparse, DataDrivenB200
-#     res = solve(prob, basis, B200Sparse(STLSQ(exp10.(-5:0.1:-1))))
+#     res = solve(prob, basis, B200Sparse(STLSQ(exp10.(-5:0.1:-1))))                # one GPU
+#     res = solve(prob, basis, B200Sparse(STLSQ(exp10.(-5:0.1:-1)); ngpus = 8))     # the node's eight GPUs
+#
+# `ngpus > 1`: ONE Julia process drives N GPUs through a `ddb_group` (N contexts + `ncclCommInitAll` inside the
+# library); `ddb_group_solve_sparse` cuts X / Y into N sample ranges, each GPU contracts its own range, the packed
+# normal-equation blocks and the candidate-rss table are summed with one `ncclAllReduce` each on the compute streams.
 #
 # The backend is a new algorithm type.  It defines exactly the two methods the reference's plug-in
 # mechanism dispatches on (SURVEY.md section 8b): `get_fit_targets` (src/commonsolve.jl:74-81) so that
@@ -31,8 +36,10 @@ end
 struct B200Sparse{A <: Union{STLSQ, ADMM, SR3, ImplicitOptimizer}} <: DataDrivenSparse.AbstractSparseRegressionAlgorithm
     inner::A
     device::Int
+    ngpus::Int
 end
-B200Sparse(inner) = B200Sparse(inner, 0)
+B200Sparse(inner; device::Int = 0, ngpus::Int = 1) = B200Sparse(inner, device, ngpus)
+B200Sparse(inner, device::Int) = B200Sparse(inner, device, 1)
 Base.summary(x::B200Sparse) = "B200(" * summary(x.inner) * ")"
 
 function check(status::Cint)
@@ -151,12 +158,14 @@ function CommonSolve.solve!(ps::InternalDataDrivenProblem{<:B200Sparse})
     (; alg, basis, traindata, testdata, problem, options) = ps
     options.denoise && throw(ArgumentError("B200Sparse: denoise=true is not supported"))
     # `init` fitted the normalisation on what get_fit_targets returned -- the RAW states, not Theta -- so anything
-    # but the identity transform would silently change the problem (the Python host layer implements ZScore on the
-    # Gram blocks, `ddb_gram_scale_terms`; this glue does not yet)
+    # but the identity transform would silently change the problem.  The library implements ZScore and UnitRange on
+    # the Gram blocks (`ddb_gram_scale_terms`, `ddb_term_minmax` + `ddb_gram_affine_terms`), train / test views
+    # (`ddb_set_sample_range`), shuffles (`ddb_permute_samples`) and test errors (`ddb_residual`); the orchestration
+    # of those calls exists in the tested Python mirror (`api.py: _solve_processed`) and is not restated here yet.
     options.normalize isa DataDrivenDiffEq.DataNormalization{Nothing} ||
-        throw(ArgumentError("B200Sparse: only DataNormalization() (no normalisation) is supported by the Julia glue"))
+        throw(ArgumentError("B200Sparse: only DataNormalization() (no normalisation) is wired up in the Julia glue"))
     options.data_processing.split == 1.0 && options.data_processing.batchsize <= 0 ||
-        throw(ArgumentError("B200Sparse: train/test split and mini-batches are not supported"))
+        throw(ArgumentError("B200Sparse: train/test split and mini-batches are not wired up in the Julia glue"))
     X, Y = first(traindata)          # single batch; column order is irrelevant to the Gram sums
     X = Matrix{Float64}(X); Y = Matrix{Float64}(Y)
     n, m = size(X); n_t = size(Y, 1)
@@ -167,22 +176,42 @@ function CommonSolve.solve!(ps::InternalDataDrivenProblem{<:B200Sparse})
     prm = Ref(SweepParams(alg_id(inner), prox_id(prox), selector_id(options.selector), options.maxiters,
         options.abstol, options.reltol, relax(inner), prox isa ClippedAbsoluteDeviation ? Float64(prox.ρ) : NaN))
     coef = zeros(n_t, k); lam = zeros(n_t); iters = zeros(Int32, n_t); rss = zeros(n_t); dof = zeros(Int32, n_t)
-    ctx = Ref{Ptr{Cvoid}}(C_NULL)
-    check(ccall((:ddb_ctx_create, LIB), Cint, (Cint, Ptr{Ptr{Cvoid}}), alg.device, ctx))
-    try
-        GC.@preserve X Y E lambdas coef lam iters rss dof begin
-            check(ccall((:ddb_set_library_monomial, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}), ctx[], n, k, E))
-            check(ccall((:ddb_solve_sparse, LIB), Cint,
-                (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cint, Int64, Ptr{SweepParams}, Ptr{Float64}, Cint,
-                 Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Float64}, Ptr{Int32}, Ptr{UInt32}),
-                ctx[], X, Y, n_t, m, prm, lambdas, length(lambdas), coef, lam, iters, rss, dof, C_NULL))
+    flags = zeros(Int32, n_t)
+    if alg.ngpus > 1
+        # one process, N GPUs: contexts + NCCL communicators live in the group (ddb.h, "multi-GPU")
+        grp = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:ddb_group_create, LIB), Cint, (Cint, Ptr{Cint}, Ptr{Ptr{Cvoid}}), alg.ngpus, C_NULL, grp))
+        try
+            GC.@preserve X Y E lambdas coef lam iters rss dof flags begin
+                check(ccall((:ddb_group_set_library_monomial, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}), grp[], n, k, E))
+                check(ccall((:ddb_group_solve_sparse, LIB), Cint,
+                    (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cint, Int64, Ptr{SweepParams}, Ptr{Float64}, Cint,
+                     Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Float64}, Ptr{Int32}, Ptr{UInt32}, Ptr{Int32}),
+                    grp[], X, Y, n_t, m, prm, lambdas, length(lambdas), coef, lam, iters, rss, dof, C_NULL, flags))
+            end
+        finally
+            ccall((:ddb_group_destroy, LIB), Cint, (Ptr{Cvoid},), grp[])
         end
-    finally
-        ccall((:ddb_ctx_destroy, LIB), Cint, (Ptr{Cvoid},), ctx[])
+    else
+        ctx = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:ddb_ctx_create, LIB), Cint, (Cint, Ptr{Ptr{Cvoid}}), alg.device, ctx))
+        try
+            GC.@preserve X Y E lambdas coef lam iters rss dof flags begin
+                check(ccall((:ddb_set_library_monomial, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}), ctx[], n, k, E))
+                check(ccall((:ddb_solve_sparse, LIB), Cint,
+                    (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cint, Int64, Ptr{SweepParams}, Ptr{Float64}, Cint,
+                     Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Float64}, Ptr{Int32}, Ptr{UInt32}, Ptr{Int32}),
+                    ctx[], X, Y, n_t, m, prm, lambdas, length(lambdas), coef, lam, iters, rss, dof, C_NULL, flags))
+            end
+        finally
+            ccall((:ddb_ctx_destroy, LIB), Cint, (Ptr{Cvoid},), ctx[])
+        end
     end
-    # finish exactly like the reference (lib/DataDrivenSparse/src/commonsolve.jl:13-24, 37-55)
+    # finish exactly like the reference (lib/DataDrivenSparse/src/commonsolve.jl:13-24, 37-55); a target whose
+    # factorisation broke down (flags bit 0) maps to DDReturnCode(2) (src/DataDrivenDiffEq.jl:60-67)
+    retcode = any(!iszero, flags .& Int32(1)) ? DDReturnCode(2) : DDReturnCode(1)
     result = DataDrivenSparse.SparseRegressionResult(coef, sum(abs.(coef) .> 0.0), lam, Int.(iters), nothing,
-        sum(rss), DDReturnCode(1))
+        sum(rss), retcode)
     new_basis = __construct_basis(copy(coef), basis, problem, options)
     return DataDrivenSolution(new_basis, problem, alg, [result], ps, result.retcode)
 end
@@ -218,7 +247,9 @@ function dmd_blocks(alg::B200DMD, x::Matrix{Float64}; want_K::Bool = true)
     return P, Q, K
 end
 
-# (alg::B200DMD)(x): x = [X Y[:, end]] -- one resident copy serves X and Y
+# (alg::B200DMD)(x): x = [X Y[:, end]] -- one resident copy serves X and Y.  The eigen-decompositions are dense
+# n x n LAPACK work on the host here (LinearAlgebra); `ddb_dmd_eig_sym` / `ddb_dmd_eig` / `ddb_dmd_residual` /
+# `ddb_gemm_nt` offer the same steps on the device for state counts where that matters (see INTEGRATION.md).
 function (alg::B200DMD)(x::AbstractMatrix)
     xs = Matrix{Float64}(x)
     if alg.truncation == 0
