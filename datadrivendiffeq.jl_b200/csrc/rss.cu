@@ -15,6 +15,7 @@
 // the read-only path (warp-uniform addresses), so the inner loop is loads + multiplies only.
 // HBM-bound when the candidates are sparse: algorithmic bytes = 8 (n + n_t) per sample.
 #include "common.cuh"
+#include "mma_common.cuh"
 #include "sweep.cuh"
 #include <cmath>
 #include <cstdlib>
@@ -292,6 +293,115 @@ __global__ void __launch_bounds__(kRssWarps * 32) rss_kernel(const RssArgs a) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Few sparse candidates on wide samples (the STLSQ result at C3: 64 models of 4 terms, 1 KB per sample): lane = CANDIDATE.
+//
+// The kernel above maps lanes to samples, which needs the tile transposed on the way into shared memory (4096 8-byte
+// cp.async with index arithmetic per 32 samples) and walks every candidate's term list with loads and branches: it is
+// instruction bound (35 % of the HBM rate).  Here every lane keeps ITS candidate -- up to 8 (coefficient, factor,
+// factor) triples -- in registers for the whole pass, the sample tile stays in its natural layout ([sample][state]:
+// exactly the global layout), so a tile is fetched by TWO bulk copies through the TMA unit (X part, Y part) into a
+// 3-deep ring, and a sample costs a warp 4 instructions per term with no loop overhead.  Warps 0-3 serve candidates
+// 0-31, warps 4-7 candidates 32-63 of a pass; the four warps of a group take the samples of a tile round robin.
+// Per-candidate sums: lane register -> fixed-order sum over the group's warps -> per-CTA partial (deterministic).
+constexpr int kLaneTile = 32;    // samples per tile
+constexpr int kLaneStages = 3;
+constexpr int kLaneTerms = 8;    // terms per candidate held in registers
+
+template <int NT>
+__global__ void __launch_bounds__(256, 2) rss_lane_kernel(const RssArgs a) {
+    extern __shared__ __align__(128) unsigned char lsm_raw[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(lsm_raw);           // [kLaneStages]
+    double* ring = reinterpret_cast<double*>(lsm_raw + 128);
+    const int n = a.n, n_t = a.n_t, w = n + n_t;
+    const int tile_doubles = kLaneTile * w;
+    __shared__ double part[8][32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int grp = warp >> 2, sub = warp & 3;
+    const int c = blockIdx.y * 64 + grp * 32 + lane;
+    const bool live = c < a.ncand;
+    // this lane's candidate: coefficients and factor columns (a missing factor is the constant 1)
+    double val[NT];
+    int fa[NT], fb[NT];
+    int eq = 0;
+    double shift = 0.0;
+    {
+        const int nnz = live ? a.cand_nnz[c] : 0;
+        const RssTerm* t = live ? a.terms + a.cand_off[c] : nullptr;
+        const int ones = n + n_t;
+#pragma unroll
+        for (int q = 0; q < NT; ++q) {
+            val[q] = 0.0;
+            fa[q] = fb[q] = -1;
+            if (q < nnz) {
+                val[q] = t[q].val;
+                fa[q] = t[q].o16[0] == ones ? -1 : (int)t[q].o16[0];
+                fb[q] = t[q].o16[1] == ones ? -1 : (int)t[q].o16[1];
+            }
+        }
+        if (live) eq = a.cand_eq[c];
+        if (live && a.cand_shift) shift = a.cand_shift[c];
+    }
+    if (tid == 0) {
+        for (int i = 0; i < kLaneStages; ++i) mbar_init(&full[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int64_t ntiles = (a.m + kLaneTile - 1) / kLaneTile;
+    const int64_t t_lo = ntiles * blockIdx.x / gridDim.x, t_hi = ntiles * (blockIdx.x + 1) / gridDim.x;
+    const int64_t full_tiles = a.m / kLaneTile;  // tiles below this index hold kLaneTile samples (bulk copies)
+    auto request = [&](int64_t tile) {  // thread 0: fetch `tile` into its ring slot
+        const int slot = (int)((tile - t_lo) % kLaneStages);
+        double* dst = ring + (size_t)slot * tile_doubles;
+        const int64_t s0 = tile * kLaneTile;
+        mbar_expect_tx(&full[slot], (uint32_t)(tile_doubles * sizeof(double)));
+        bulk_g2s(dst, a.X + s0 * n, (uint32_t)(kLaneTile * n * sizeof(double)), &full[slot]);
+        bulk_g2s(dst + kLaneTile * n, a.Y + s0 * n_t, (uint32_t)(kLaneTile * n_t * sizeof(double)), &full[slot]);
+    };
+    if (tid == 0)
+        for (int i = 0; i < kLaneStages - 1 && t_lo + i < t_hi && t_lo + i < full_tiles; ++i) request(t_lo + i);
+    double acc = 0.0;
+    for (int64_t tile = t_lo; tile < t_hi; ++tile) {
+        const int it = (int)(tile - t_lo);
+        const int slot = it % kLaneStages;
+        double* xs = ring + (size_t)slot * tile_doubles;
+        int valid = kLaneTile;
+        if (tile < full_tiles) {
+            // refill the slot the previous iteration finished with (every warp passed the barrier at its end)
+            if (tid == 0 && tile + kLaneStages - 1 < t_hi && tile + kLaneStages - 1 < full_tiles) request(tile + kLaneStages - 1);
+            mbar_wait(&full[slot], (uint32_t)((it / kLaneStages) & 1));
+        } else {  // ragged last tile of the data set: plain loads (a bulk copy needs 16-byte multiples)
+            valid = (int)(a.m - tile * kLaneTile);
+            const int64_t s0 = tile * kLaneTile;
+            for (int e = tid; e < valid * n; e += 256) xs[e] = a.X[s0 * n + e];
+            for (int e = tid; e < valid * n_t; e += 256) xs[kLaneTile * n + e] = a.Y[s0 * n_t + e];
+            __syncthreads();
+        }
+        const double* ys = xs + kLaneTile * n;
+        for (int sidx = sub; sidx < valid; sidx += 4) {
+            const double* x = xs + sidx * n;
+            double fit = shift;
+#pragma unroll
+            for (int q = 0; q < NT; ++q) {
+                const double xa = fa[q] >= 0 ? x[fa[q]] : 1.0;
+                const double xb = fb[q] >= 0 ? x[fb[q]] : 1.0;
+                fit = fma(val[q], xa * xb, fit);
+            }
+            const double res = fit - ys[sidx * n_t + eq];
+            acc = fma(res, res, acc);
+        }
+        __syncthreads();  // the slot may be refilled
+    }
+    part[warp][lane] = acc;
+    __syncthreads();
+    if (sub == 0 && live) {
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) s += part[4 * grp + q][lane];
+        a.partials[(size_t)blockIdx.x * a.ncand + c] = s;
+    }
+}
+
 __global__ void rss_reduce_kernel(const double* __restrict__ partials, int nparts, int ncand, double* __restrict__ rss) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncand) return;
@@ -376,6 +486,49 @@ static int rss_core(ddb_ctx* ctx, const RssCand& c, const int32_t* map, const Rs
                                                               ctx->d_cand_shift.as<double>());
         ++*launches;
         cand_shift = ctx->d_cand_shift.as<double>();
+    }
+    // few sparse candidates on wide samples: the lane-per-candidate kernel (see rss_lane_kernel)
+    const char* lenv = getenv("DDB_RSS_LANE");
+    const bool lane_ok = !(lenv && atoi(lenv) == 0) && !targets && ctx->max_degree <= 2 && ncand > 0 && ncand <= 128 &&
+                         (size_t)(ctx->n + ctx->n_t) * 8 >= 512 && ctx->m >= 4 * kLaneTile &&
+                         ((size_t)kLaneTile * ctx->n * 8) % 16 == 0 && ((size_t)kLaneTile * ctx->n_t * 8) % 16 == 0 &&
+                         (((uintptr_t)ctx->dX) & 15) == 0 && (((uintptr_t)ctx->dY) & 15) == 0;
+    if (lane_ok) {
+        std::vector<int32_t> h_nnz(ncand);
+        DDB_CUDA_TRY(cudaMemcpyAsync(h_nnz.data(), c.nnz, (size_t)ncand * 4, cudaMemcpyDeviceToHost, st));
+        DDB_CUDA_TRY(cudaStreamSynchronize(st));
+        int nnz_max = 0;
+        for (int v : h_nnz) nnz_max = std::max(nnz_max, v);
+        const size_t lsmem = 128 + (size_t)kLaneStages * kLaneTile * (ctx->n + ctx->n_t) * sizeof(double);
+        if (nnz_max <= kLaneTerms && lsmem <= 110 * 1024) {
+            const int64_t lt = (ctx->m + kLaneTile - 1) / kLaneTile;
+            const int nparts = (int)std::min<int64_t>(lt, (int64_t)ctx->sm_count * 2);
+            DDB_TRY(partials.reserve((size_t)nparts * ncand * 8));
+            RssArgs a;
+            a.X = ctx->dX;
+            a.Y = ctx->dY;
+            a.n = ctx->n;
+            a.n_t = ctx->n_t;
+            a.m = ctx->m;
+            a.ncand = ncand;
+            a.cand_off = c.off;
+            a.cand_nnz = c.nnz;
+            a.cand_eq = c.eq;
+            a.terms = terms.as<RssTerm>();
+            a.targets = nullptr;
+            a.cand_shift = cand_shift;
+            a.term_cap = 0;
+            a.sub = 1;
+            a.pitch = pitch;
+            a.partials = partials.as<double>();
+            auto kern = nnz_max <= 4 ? rss_lane_kernel<4> : rss_lane_kernel<kLaneTerms>;
+            DDB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));
+            kern<<<dim3(nparts, (ncand + 63) / 64), 256, lsmem, st>>>(a);
+            rss_reduce_kernel<<<(ncand + 255) / 256, 256, 0, st>>>(partials.as<double>(), nparts, ncand, dRss);
+            *launches += 2;
+            DDB_CUDA_TRY(cudaGetLastError());
+            return DDB_OK;
+        }
     }
     const int passes = (ncand + kRssWarps * kRssAcc - 1) / (kRssWarps * kRssAcc);
     const int rows_all = ctx->n + ctx->n_t + 1;
