@@ -34,7 +34,7 @@ FP64_DMMA_PEAK_TFLOPS = 37.0
 CUBLAS_DGEMM_TFLOPS = 35.9
 # ncu dram__bytes_read.sum + dram__bytes_write.sum of the Gram kernels per sample at C3 (1e6-sample captures, per
 # schedule; see profiles/): moment schedule gram_kernel; ring schedule gram_ring_kernel + diagonal-pair pass
-DRAM_BYTES_PER_SAMPLE = {2: ((6928822016 + 69605632) / 1e6, "profiles/gram_traffic_r1o_c3_1e6.csv"),
+DRAM_BYTES_PER_SAMPLE = {2: ((8502591000 + 70482688) / 1e6, "profiles/step_r2e_ncu_summary.txt"),
                          1: ((1041148928 + 1886253824) / 1e6, "profiles/gram_traffic_r1g_c3_1e6.csv")}
 
 WORKLOADS = {
