@@ -49,6 +49,7 @@ int main(int argc, char** argv) {
     for (auto& v : rhs) v = nd(rng);
     ddb_ctx ctx;
     CK(cudaStreamCreateWithFlags(&ctx.stream, cudaStreamNonBlocking));
+    ctx.sm_count = 148;
     double *dA0, *dA, *dX;
     int* dfail;
     CK(cudaMalloc(&dA0, stride * 8));
@@ -78,10 +79,10 @@ int main(int argc, char** argv) {
     }
     {   // the same factorisation with an event pair around every launch: time per kernel class
         long long* dtrace;
-        CK(cudaMalloc(&dtrace, 64));
-        CK(cudaMemset(dtrace, 0, 64));
+        CK(cudaMalloc(&dtrace, 128));
+        CK(cudaMemset(dtrace, 0, 128));
         CholBatch cb{dA, stride, k, nullptr, k, dfail, nrhs, k, dtrace};
-        const size_t dsmem = (size_t)kCB * kCP * 8, psmem = (size_t)(kCB + 32) * kCP * 8, gsmem = 2 * (size_t)kCStage * 8;
+        const size_t dsmem = (size_t)kCB * kCP * 8, psmem = (size_t)(kCB + 64) * kCP * 8, gsmem = 2 * (size_t)kCStage * 8;
         std::vector<cudaEvent_t> ev(4 * ((k + 127) / 128) + 4);
         for (auto& evt : ev) CK(cudaEventCreate(&evt));
         for (int r = 0; r < 5; ++r) {
@@ -96,7 +97,11 @@ int main(int argc, char** argv) {
                 const int rem = std::max(k - j0 - kCB, 0);
                 if (rem + nrhs <= 0) break;
                 const int Tr = (rem + nrhs + kCB - 1) / kCB, Tc = (rem + kCB - 1) / kCB;
-                chol_panel128_kernel<<<dim3(Tr, batch), 256, psmem, ctx.stream>>>(cb, j0);
+                if ((long long)Tr * batch < 148) {
+                    const size_t p32smem = ((size_t)kCB * kPT + 2 * 32 * kCP) * 8;
+                    chol_panel32_kernel<<<dim3((rem + nrhs + kPR - 1) / kPR, batch), 128, p32smem, ctx.stream>>>(cb, j0);
+                } else
+                    chol_panel128_kernel<<<dim3(Tr, batch), 256, psmem, ctx.stream>>>(cb, j0);
                 CK(cudaEventRecord(ev[ne++], ctx.stream));
                 cls.push_back(1);
                 if (Tc > 0) {
@@ -113,8 +118,11 @@ int main(int argc, char** argv) {
                     tcls[cls[i]] += ms / 3.0;
                 }
         }
-        long long tr[8];
-        CK(cudaMemcpy(tr, dtrace, 64, cudaMemcpyDeviceToHost));
+        long long tr[16];
+        CK(cudaMemcpy(tr, dtrace, 128, cudaMemcpyDeviceToHost));
+        if (tr[12] > 0)
+            printf("panel kernel, CTA 0, cycles per call: load/wait %lld, product %lld, substitution %lld, store %lld (%lld calls)\n",
+                   tr[8] / tr[12], tr[9] / tr[12], tr[10] / tr[12], tr[11] / tr[12], tr[12]);
         if (tr[5] > 0)
             printf("diag kernel, CTA 0, cycles per call: load %lld, pivot %lld, rows below %lld, in-block update %lld, store %lld (%lld calls)\n",
                    tr[0] / tr[5], tr[1] / tr[5], tr[2] / tr[5], tr[3] / tr[5], tr[4] / tr[5], tr[5]);
