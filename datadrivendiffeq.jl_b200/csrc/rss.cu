@@ -556,9 +556,12 @@ static int rss_core(ddb_ctx* ctx, const RssCand& c, const int32_t* map, const Rs
         set_error("ddb_rss: n + n_t too large for the shared-memory sample tile");
         return DDB_UNSUPPORTED;
     }
-    // candidate metadata + as many term records as keep two CTAs per SM (about 112 KB each)
+    // candidate metadata + as many term records as keep two CTAs per SM: 228 KB per SM, 1 KB reserved per CTA and
+    // 2.2 KB of static shared memory (s_shift, s_scan) leave 110 KB of dynamic shared memory each.  (112 KB -- the
+    // figure before s_shift existed -- silently dropped the kernel to ONE CTA per SM: C4 / ADMM 56 -> 98 ms.)
     const size_t smem_meta = (size_t)kRssWarps * kRssAcc * sizeof(int4);
-    const size_t budget = smem_tiles + smem_meta < 112 * 1024 ? 112 * 1024 - smem_tiles - smem_meta : 0;
+    constexpr size_t kRssDynBudget = 110 * 1024;
+    const size_t budget = smem_tiles + smem_meta < kRssDynBudget ? kRssDynBudget - smem_tiles - smem_meta : 0;
     a.term_cap = (int)std::min<size_t>(budget / sizeof(RssTerm), 1u << 15);
     const size_t smem = smem_tiles + smem_meta + (size_t)a.term_cap * sizeof(RssTerm);
     auto kern = ctx->max_degree <= 2 ? rss_kernel<2> : rss_kernel<kMaxFactors>;
