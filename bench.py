@@ -334,7 +334,7 @@ def run_sparse(env, wl, alg, noise, steps, warmup, want_e2e, want_clocks):
     if alg == "STLSQ" and noise == 0.0:  # never report a number for wrong results
         expect = [4] * n_t if wl["system"] == 1 else [2, 3, 2]
         assert dof == expect, f"unexpected model: dof {dof}"
-    stage = {key: float(np.mean(v)) for key, v in live.items()}
+    stage = {key: float(np.mean(v[-steps:])) for key, v in live.items()}  # timed steps only (the first all-reduce sets NCCL up)
     F = gram_flops_per_sample(k, n_t)
     gram_s = stage["gram_ms"] * 1e-3
     syrk_equiv = F * m_local / gram_s * 1e-12
