@@ -6,6 +6,7 @@
 #include <cmath>
 #include <condition_variable>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <thread>
 
@@ -210,6 +211,9 @@ int ddb_ctx_destroy(ddb_ctx* ctx) {
         if (ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->chunk_ev)
         if (ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->stage_ev)
+        if (ev) cudaEventDestroy(ev);
+    if (ctx->stage_host) cudaFreeHost(ctx->stage_host);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -378,6 +382,91 @@ __global__ void packed_add_kernel(double* __restrict__ acc, const double* __rest
     if (i < count) acc[i] = first ? part[i] : acc[i] + part[i];
 }
 
+// Pageable host memory -> device through our own page-locked bounce buffers.  cudaMemcpyAsync on pageable memory
+// stages through the driver's buffers with ONE host thread (~10 GB/s on these boxes: a 10 GB upload then outlasts the
+// 0.7 s Gram stage it should hide behind -- e2e 10.1e6 samples/s against 13.9e6 from pinned memory); here a small
+// thread pool fills a 32 MB piece of a 3-deep ring while the DMA engine drains the previous ones.
+constexpr size_t kStageBytes = 32u << 20;
+constexpr int kStagePieces = 3;
+struct StagePool {
+    int nthreads;
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv_go, cv_done;
+    int gen = 0, done = 0;
+    bool stop = false;
+    char* dst = nullptr;
+    const char* src = nullptr;
+    size_t len = 0;
+    explicit StagePool(int n) : nthreads(n) {
+        for (int t = 1; t < nthreads; ++t)
+            workers.emplace_back([this, t] {
+                int seen = 0;
+                for (;;) {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv_go.wait(lk, [&] { return stop || gen != seen; });
+                    if (stop) return;
+                    seen = gen;
+                    char* d = dst;
+                    const char* s = src;
+                    const size_t n = len;
+                    lk.unlock();
+                    slice(d, s, n, t);
+                    lk.lock();
+                    ++done;
+                    cv_done.notify_one();
+                }
+            });
+    }
+    void slice(char* d, const char* s, size_t n, int t) const {
+        const size_t per = ((n + nthreads - 1) / nthreads + 63) & ~size_t(63);
+        const size_t lo = std::min(n, per * t), hi = std::min(n, per * (t + 1));
+        if (hi > lo) memcpy(d + lo, s + lo, hi - lo);
+    }
+    void copy(char* d, const char* s, size_t n) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            dst = d, src = s, len = n, done = 0;
+            ++gen;
+        }
+        cv_go.notify_all();
+        slice(d, s, n, 0);
+        std::unique_lock<std::mutex> lk(mu);
+        cv_done.wait(lk, [&] { return done == nthreads - 1; });
+    }
+    ~StagePool() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            stop = true;
+        }
+        cv_go.notify_all();
+        for (auto& w : workers) w.join();
+    }
+};
+// Measured on a 16-core box (tools/pageable_probe.py, C3 end to end from pageable arrays, 718 ms from pinned ones):
+// 1 thread 786 ms, 2: 747, 4: 738, 8: 727, 16: 723.  Half the cores divided by the ranks that share the node.
+static int stage_threads(const ddb_ctx* ctx) {
+    if (const char* e = getenv("DDB_STAGE_THREADS")) return std::max(1, std::min(16, atoi(e)));
+    const unsigned hc = std::max(2u, std::thread::hardware_concurrency());
+    const unsigned ranks = (unsigned)std::max(1, ctx->nranks);
+    return (int)std::max(2u, std::min(8u, hc / (2 * ranks)));
+}
+// host (pageable) -> device, `bytes` bytes, on ctx->copy_stream through the bounce ring; *piece counts ring slots used
+static cudaError_t staged_h2d(ddb_ctx* ctx, StagePool& pool, void* dst, const void* src, size_t bytes, int* piece) {
+    for (size_t off = 0; off < bytes; off += kStageBytes) {
+        const size_t len = std::min(kStageBytes, bytes - off);
+        const int b = (*piece)++ % kStagePieces;
+        cudaError_t e = cudaEventSynchronize(ctx->stage_ev[b]);  // the DMA that last read this slot has finished
+        if (e != cudaSuccess) return e;
+        char* slot = static_cast<char*>(ctx->stage_host) + (size_t)b * kStageBytes;
+        pool.copy(slot, static_cast<const char*>(src) + off, len);
+        e = cudaMemcpyAsync(static_cast<char*>(dst) + off, slot, len, cudaMemcpyHostToDevice, ctx->copy_stream);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->stage_ev[b], ctx->copy_stream);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
 // Host buffers -> device (kept resident, as ddb_upload) with the copies overlapped by the Gram stage: the
 // samples are cut into chunks, chunk c + 1 travels on a copy stream while the Gram kernels run on chunk c;
 // the per-chunk blocks are added in chunk order (deterministic).  With pinned host memory the transfer
@@ -433,10 +522,10 @@ int ddb_upload_gram(ddb_ctx* ctx, const double* X, const double* Y, int n_t, int
         dIn = ctx->raw_X.as<double>();
     }
     // Page-locked host buffers: all copies are queued up front on the copy stream (event c fires when chunk c is
-    // resident) and the DMA engine runs ahead of the kernels.  PAGEABLE buffers (a Julia `Matrix`, a NumPy array):
-    // cudaMemcpyAsync stages them through the driver's pinned bounce buffers and blocks the calling thread while it
-    // does, so the copies are issued by a helper thread -- the calling thread keeps launching the Gram kernels of
-    // the chunks that have landed, and the transfer still hides behind the tensor work.
+    // resident) and the DMA engine runs ahead of the kernels.  PAGEABLE buffers (a Julia `Matrix`, a NumPy array) go
+    // through the library's own bounce ring (staged_h2d), filled by a helper thread and its pool -- the calling thread
+    // keeps launching the Gram kernels of the chunks that have landed, and the transfer still hides behind the tensor
+    // work.
     auto is_pinned = [](const void* p) {
         cudaPointerAttributes at;
         if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
@@ -450,14 +539,27 @@ int ddb_upload_gram(ddb_ctx* ctx, const double* X, const double* Y, int n_t, int
     std::condition_variable cv;
     int landed = 0;                 // chunks whose copies have been issued and whose event is recorded
     cudaError_t copy_err = cudaSuccess;
+    if (!pinned && !ctx->stage_host) {
+        DDB_CUDA_TRY(cudaHostAlloc(&ctx->stage_host, kStagePieces * kStageBytes, cudaHostAllocDefault));
+        for (int b = 0; b < kStagePieces; ++b) DDB_CUDA_TRY(cudaEventCreateWithFlags(&ctx->stage_ev[b], cudaEventDisableTiming));
+    }
     auto issue_copies = [&](bool notify) {
+        std::unique_ptr<StagePool> pool;
+        int piece = 0;
+        if (notify) pool.reset(new StagePool(stage_threads(ctx)));  // pageable caller: this is the helper thread
         for (int c = 0; c < nchunks; ++c) {
             const int64_t s0 = c * chunk, mc = std::min(chunk, m - s0);
-            cudaError_t e = cudaMemcpyAsync(dIn + s0 * n_in, X + s0 * n_in, (size_t)mc * n_in * sizeof(double),
-                                            cudaMemcpyHostToDevice, ctx->copy_stream);
-            if (e == cudaSuccess)
-                e = cudaMemcpyAsync(dY + s0 * n_t, Y + s0 * n_t, (size_t)mc * n_t * sizeof(double), cudaMemcpyHostToDevice,
+            cudaError_t e;
+            if (pool) {
+                e = staged_h2d(ctx, *pool, dIn + s0 * n_in, X + s0 * n_in, (size_t)mc * n_in * sizeof(double), &piece);
+                if (e == cudaSuccess) e = staged_h2d(ctx, *pool, dY + s0 * n_t, Y + s0 * n_t, (size_t)mc * n_t * sizeof(double), &piece);
+            } else {
+                e = cudaMemcpyAsync(dIn + s0 * n_in, X + s0 * n_in, (size_t)mc * n_in * sizeof(double), cudaMemcpyHostToDevice,
                                     ctx->copy_stream);
+                if (e == cudaSuccess)
+                    e = cudaMemcpyAsync(dY + s0 * n_t, Y + s0 * n_t, (size_t)mc * n_t * sizeof(double), cudaMemcpyHostToDevice,
+                                        ctx->copy_stream);
+            }
             if (e == cudaSuccess) e = cudaEventRecord(ctx->chunk_ev[c], ctx->copy_stream);
             if (notify) {
                 std::lock_guard<std::mutex> lk(mu);

@@ -89,6 +89,8 @@ struct ddb_ctx {
     cudaEvent_t ev[8] = {};
     cudaStream_t copy_stream = nullptr;  // host->device copies of ddb_upload_gram (overlap with the Gram kernels)
     std::vector<cudaEvent_t> chunk_ev;   // chunk c has landed
+    void* stage_host = nullptr;          // page-locked bounce buffers of ddb_upload_gram for pageable callers (kStagePieces x kStageBytes)
+    cudaEvent_t stage_ev[4] = {};        // bounce buffer b may be rewritten
     ddb::DevBuf d_chunk_packed;          // blocks of one chunk before they are added to the total
 
     // library

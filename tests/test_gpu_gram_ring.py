@@ -105,6 +105,17 @@ def test_upload_gram_chunked_overlap_matches_plain(ctx, n, deg, m):
     ctx.upload_gram_raw(Xp.data_ptr(), Yp.data_ptr(), n, m)  # deterministic
     G2, _, _ = ctx.gram_download()
     np.testing.assert_array_equal(G1, G2)
+    # pageable host memory (what a Julia Matrix or a NumPy array is): the library's own bounce ring, filled by a
+    # thread pool -- same chunks, so the blocks are bit-identical, and the resident data are the caller's
+    Xh, Yh = np.ascontiguousarray(X.T), np.ascontiguousarray(Y.T)
+    ctx.upload_gram_raw(Xh.ctypes.data, Yh.ctypes.data, n, m)
+    G3, R3, y3 = ctx.gram_download()
+    np.testing.assert_array_equal(G1, G3)
+    np.testing.assert_array_equal(R1, R3)
+    np.testing.assert_array_equal(y1, y3)
+    Xd, Yd = ctx.download_data()
+    np.testing.assert_array_equal(Xd, X)
+    np.testing.assert_array_equal(Yd, Y)
 
 
 @pytest.mark.parametrize("n,n_t", [(65, 65), (66, 66), (70, 3), (64, 1), (72, 72)])
