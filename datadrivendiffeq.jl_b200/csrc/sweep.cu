@@ -427,6 +427,7 @@ int chol_back_batched(ddb_ctx* ctx, double* base, size_t stride, int ld, const i
 int chol_factor_shared(ddb_ctx* ctx, double* A, int k, int* d_fail, int extra, int* launches);
 int chol_solve_many(ddb_ctx* ctx, const double* L, int k, double* Z, int nrhs, int* launches);
 void comm_collect_time(ddb_ctx* ctx);  // comm.cu: duration of the last queued all-reduce -> timings (after a sync)
+int comm_allreduce(ddb_ctx* ctx, double* d, int64_t count);  // comm.cu: in-place sum over the ranks on the compute stream
 
 // ---------------------------------------------------------------------------------------------
 // per-target state and the shared post-solve step logic
@@ -1039,9 +1040,15 @@ __global__ void __launch_bounds__(256) stlsq_small_kernel(SweepDev S, int small_
 
 // big path, STLSQ: gather masked systems of the flagged targets into global workspaces
 // grid (row splits, number of flagged targets); dynamic shared memory: k ints
+// Sharded runs (nr ranks, this is rank rk): every rank rebuilds the index lists of ALL parked targets (the finish step
+// needs them everywhere) but gathers -- and later factorises -- only the systems of slots rk, rk + nr, ...; local slot
+// slot / nr of the workspace, its order / global slot recorded in na_loc / map_loc.
 __global__ void __launch_bounds__(256) stlsq_big_gather_kernel(SweepDev S, const int* big_list, double* ws,
-                                                               size_t ws_stride, int* idx_all, int* na_out, int rhs_row) {
+                                                               size_t ws_stride, int* idx_all, int* na_out, int rhs_row,
+                                                               int nr, int rk, int* na_loc, int* map_loc) {
     const int slot = blockIdx.y;
+    const bool mine = (slot % nr) == rk;
+    if (!mine && blockIdx.x != 0) return;
     const int e = big_list[slot];
     const int k = S.k, W = S.W;
     const uint32_t* act = S.active + (size_t)e * W;
@@ -1061,25 +1068,45 @@ __global__ void __launch_bounds__(256) stlsq_big_gather_kernel(SweepDev S, const
     }
     __syncthreads();
     const int na = s_na;
-    double* A = ws + (size_t)slot * ws_stride;
-    for (int i = blockIdx.x; i < na; i += gridDim.x) {
-        const double* src = S.As + (size_t)sidx[i] * k;
-        for (int j = threadIdx.x; j <= i; j += blockDim.x) A[(size_t)i * k + j] = src[sidx[j]];
-    }
+    double* A = ws + (size_t)(slot / nr) * ws_stride;
+    if (mine)
+        for (int i = blockIdx.x; i < na; i += gridDim.x) {
+            const double* src = S.As + (size_t)sidx[i] * k;
+            for (int j = threadIdx.x; j <= i; j += blockDim.x) A[(size_t)i * k + j] = src[sidx[j]];
+        }
     if (blockIdx.x == 0) {
         int* idx = idx_all + (size_t)slot * k;
         double* x = S.x + (size_t)e * k;
         double* xp = S.xprev + (size_t)e * k;
         double* z = S.znew + (size_t)e * k;
         const double* rs = S.rs + (size_t)e * k;
-        if (threadIdx.x == 0) na_out[slot] = na;
+        if (threadIdx.x == 0) {
+            na_out[slot] = na;
+            if (mine && na_loc) na_loc[slot / nr] = na, map_loc[slot / nr] = slot;
+        }
         for (int i = threadIdx.x; i < na; i += blockDim.x) idx[i] = sidx[i];
         for (int i = threadIdx.x; i < k; i += blockDim.x) xp[i] = x[i];  // X_prev .= X
         // rhs_row: the right-hand side goes to row k of the slot's matrix buffer (it rides through the blocked
         // factorisation); otherwise to znew (solved in place by chol_solve_kernel)
-        double* zdst = rhs_row ? A + (size_t)k * k : z;
-        for (int i = threadIdx.x; i < na; i += blockDim.x) zdst[i] = rs[sidx[i]];
+        if (mine) {
+            double* zdst = rhs_row ? A + (size_t)k * k : z;
+            for (int i = threadIdx.x; i < na; i += blockDim.x) zdst[i] = rs[sidx[i]];
+        }
     }
+}
+
+// sharded big steps: failure flags of my slots into the exchange buffer / solutions and flags of ALL slots out of it
+__global__ void big_fail_pack_kernel(const int* fail_loc, const int* map_loc, int nloc, double* xbuf, int k) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nloc) xbuf[(size_t)map_loc[b] * (k + 1) + k] = fail_loc[b] ? 1.0 : 0.0;
+}
+__global__ void __launch_bounds__(256) big_unpack_kernel(const double* xbuf, const int* big_list, const int* na_arr, int k,
+                                                         double* znew, int* fail) {
+    const int slot = blockIdx.x;
+    const double* src = xbuf + (size_t)slot * (k + 1);
+    double* z = znew + (size_t)big_list[slot] * k;
+    for (int i = threadIdx.x; i < na_arr[slot]; i += blockDim.x) z[i] = src[i];
+    if (threadIdx.x == 0) fail[slot] = src[k] != 0.0;
 }
 
 __global__ void __launch_bounds__(256) stlsq_big_finish_kernel(SweepDev S, const int* big_list, const int* idx_all,
@@ -1373,7 +1400,7 @@ void SweepState::release_all() {
     DevBuf* all[] = {&As, &Lfac, &dinv, &rs, &x, &xprev, &aux1, &aux2, &znew, &active, &eq, &lambdas_d, &cand_idx,
                      &cand_val, &cand_off, &cand_nnz, &cand_dof, &cand_eq, &counters, &pool_used_d, &run_cand,
                      &run_jfirst, &run_j, &path_support, &path_coef, &path_iters, &big_ws, &big_idx, &big_na,
-                     &big_list, &big_fail, &active_matrix, &shared_fail, &rss, &rss_partials, &out_tmp, &cand_terms,
+                     &big_list, &big_fail, &big_loc, &big_xbuf, &active_matrix, &shared_fail, &rss, &rss_partials, &out_tmp, &cand_terms,
                      &Ninv, &tgt_terms, &rss_corr, &grp_buf, &rep_buf, &zsol, &canon_tmp};
     for (DevBuf* b : all) b->release();
 }
@@ -1622,15 +1649,42 @@ int sweep_run(ddb_ctx* ctx, const ddb_sweep_params* prm, const double* lambdas, 
             // ---- big step: targets whose active set does not fit the shared-memory solver ----------
             ++big_steps;
             const size_t ws_stride = chol_fma ? kk : kk + (size_t)k;  // + one row: the right-hand side
-            DDB_TRY(S->big_ws.reserve((size_t)nbig * ws_stride * 8));
+            // Sharded run: the parked targets are dealt to the ranks round robin (SURVEY 8e "equations per GPU"), every
+            // rank factorises its share and ONE sum all-reduce of [solution | failure flag] per parked target (zeros for
+            // the slots of the other ranks, so the sum is exact and every rank ends up with bit-identical iterates)
+            // replaces nranks redundant copies of the same factorisations.
+            const bool shard_big = ctx->comm && ctx->nranks > 1 && !chol_fma && nbig >= 2;
+            const int nr = shard_big ? ctx->nranks : 1, rk = shard_big ? ctx->rank : 0;
+            const int nloc = nbig > rk ? (nbig - rk + nr - 1) / nr : 0;
+            DDB_TRY(S->big_ws.reserve((size_t)std::max(1, nloc) * ws_stride * 8));
             DDB_TRY(S->big_idx.reserve((size_t)nbig * k * 4));
+            int *na_loc = nullptr, *fail_loc = nullptr, *map_loc = nullptr;
+            if (shard_big) {
+                DDB_TRY(S->big_loc.reserve((size_t)3 * n_t * 4));
+                DDB_TRY(S->big_xbuf.reserve((size_t)nbig * (k + 1) * 8));
+                na_loc = S->big_loc.as<int>(), fail_loc = na_loc + n_t, map_loc = fail_loc + n_t;
+                DDB_CUDA_TRY(cudaMemsetAsync(fail_loc, 0, (size_t)n_t * 4, st));
+                DDB_CUDA_TRY(cudaMemsetAsync(S->big_xbuf.p, 0, (size_t)nbig * (k + 1) * 8, st));
+            }
             list_big_kernel<<<1, 32, 0, st>>>(D.eq, n_t, S->big_list.as<int>(), S->big_list.as<int>() + n_t);
             DDB_CUDA_TRY(cudaMemsetAsync(S->big_fail.p, 0, (size_t)n_t * 4, st));
             stlsq_big_gather_kernel<<<dim3(64, nbig), 256, (size_t)k * sizeof(int), st>>>(
                 D, S->big_list.as<int>(), S->big_ws.as<double>(), ws_stride, S->big_idx.as<int>(), S->big_na.as<int>(),
-                chol_fma ? 0 : 1);
+                chol_fma ? 0 : 1, nr, rk, na_loc, map_loc);
             launches += 2;
-            if (chol_fma) {
+            if (shard_big) {
+                if (nloc > 0) {
+                    DDB_TRY(chol128_batched(ctx, S->big_ws.as<double>(), ws_stride, k, na_loc, k, nloc, fail_loc, 1, k, &launches));
+                    DDB_TRY(chol_back_batched(ctx, S->big_ws.as<double>(), ws_stride, k, na_loc, k, nloc, k, 1,
+                                              S->big_xbuf.as<double>(), (size_t)k + 1, 0, map_loc, nullptr));
+                    big_fail_pack_kernel<<<(nloc + 63) / 64, 64, 0, st>>>(fail_loc, map_loc, nloc, S->big_xbuf.as<double>(), k);
+                    launches += 2;
+                }
+                DDB_TRY(comm_allreduce(ctx, S->big_xbuf.as<double>(), (int64_t)nbig * (k + 1)));
+                big_unpack_kernel<<<nbig, 256, 0, st>>>(S->big_xbuf.as<double>(), S->big_list.as<int>(), S->big_na.as<int>(), k,
+                                                        S->znew.as<double>(), S->big_fail.as<int>());
+                ++launches;
+            } else if (chol_fma) {
                 DDB_TRY(chol_batched(ctx, S->big_ws.as<double>(), kk, k, S->big_na.as<int>(), k, nbig,
                                      S->big_fail.as<int>(), &launches));
                 chol_solve_kernel<<<dim3(1, nbig), 256, solve_smem, st>>>(S->big_ws.as<double>(), kk, k,

@@ -139,6 +139,37 @@ def test_group_two_gpus(alg):
 
 
 @pytest.mark.skipif(_ngpus() < 2, reason="needs 2 GPUs")
+def test_group_two_gpus_parked_targets():
+    """Noisy data on a 190-term library: active sets beyond the shared-memory solver park their targets, and in a
+    sharded run the parked targets are dealt to the ranks (each factorises its share, one all-reduce of the solutions;
+    ``stlsq_big_gather_kernel``).  Two GPUs against one: same supports and iteration counts, coefficients to the
+    accuracy the differently-summed blocks allow."""
+    n, m = 18, 5000
+    X, D = systems.lorenz96_ensemble(m, n=n, seed=5, samples_per_traj=500)
+    D = D + 0.5 * np.random.default_rng(4).standard_normal(D.shape)
+    basis = ddb200.polynomial_basis(n, 2)
+    lams = 10.0 ** np.arange(-4, -0.4, 0.25)
+    with ddb200.Context(0) as one:
+        one.set_library(basis.exponents)
+        prm = one.make_params("STLSQ")
+        ref = one.solve_sparse(X, D, prm, lams)
+        assert one.timings()["big_steps"] > 0
+    with ddb200.Group(2) as grp:
+        grp.set_library(basis.exponents)
+        out = grp.solve_sparse(X, D, prm, lams)
+        t = grp.timings()
+        out2 = grp.solve_sparse(X, D, prm, lams)
+    assert t["big_steps"] > 0 and t["allreduce_calls"] > 2  # Gram, rss and one exchange per big step
+    np.testing.assert_array_equal(out.coefficients != 0, ref.coefficients != 0)
+    np.testing.assert_array_equal(out.iterations, ref.iterations)
+    np.testing.assert_array_equal(out.dof, ref.dof)
+    np.testing.assert_allclose(out.coefficients, ref.coefficients, rtol=1e-8, atol=1e-12)
+    np.testing.assert_allclose(out.lambda_opt, ref.lambda_opt, rtol=1e-15)
+    np.testing.assert_allclose(out.rss, ref.rss, rtol=1e-9)
+    np.testing.assert_array_equal(out.coefficients, out2.coefficients)  # bit-reproducible from call to call
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs 2 GPUs")
 @pytest.mark.parametrize("alg", ["STLSQ", "ADMM"])
 def test_torchrun_two_ranks(alg, tmp_path):
     """One process per GPU (the way bench.py is launched): communicator from ``ddb_comm_init_rank``."""
