@@ -583,6 +583,15 @@ static int rss_core(ddb_ctx* ctx, const RssCand& c, const int32_t* map, const Rs
 // y - c'theta then loses its leading digits).  Supports of more than kGroupMax terms and singletons are
 // streamed directly.
 constexpr int kGroupMax = 16;
+// Candidates with many terms are scored by the DMMA pass of rss_dense.cu.  Its cost per candidate and sample is that
+// of ALL library terms at the tensor rate (2 k / 512 DMMAs, ~53 SM cycles at k = 2145 and the measured 66 % of the DMMA
+// peak); the term-by-term kernels above cost ~0.34 SM cycles per term: break-even near k / 14 terms.
+constexpr int kDenseMin = 96;
+static int dense_threshold(int k) { return std::max(kDenseMin, k / 14); }
+bool rss_dense_ok(const ddb_ctx* ctx);
+int rss_dense_run(ddb_ctx* ctx, const int32_t* ids, int nd, const int64_t* off, const int32_t* nnz, const int32_t* eq,
+                  const int32_t* idx, const double* val, const double* scale, const int32_t* map, const double* shift,
+                  DevBuf& work, double* out, int* launches);
 
 __global__ void gather_gss_kernel(const double* __restrict__ packed, int k, int n_t, const int32_t* __restrict__ gidx,
                                   const int32_t* __restrict__ gsize, const int32_t* __restrict__ geq,
@@ -796,6 +805,10 @@ int rss_run(ddb_ctx* ctx, SweepState* S, double* dRss) {
         DDB_CUDA_TRY(cudaMemcpyAsync(yy_h.data(), yy_dev, (size_t)n_t * 8, cudaMemcpyDeviceToHost, st));
         DDB_CUDA_TRY(cudaStreamSynchronize(st));
         std::vector<int32_t> rep(ncand);
+        // dense candidates (explicit libraries, no affine term shift): scored on the tensor pipe, see rss_dense.cu
+        const bool dense_on = !implicit && !mu && rss_dense_ok(ctx);
+        const int dense_min = dense_threshold(ctx->k);
+        std::vector<int32_t> dense_ids;
         for (int c = 0; c < ncand; ++c) {
             const int g = group[c];
             if (nnz[c] == 0) {  // a zero model: rss = yy[target], never streamed
@@ -813,6 +826,9 @@ int rss_run(ddb_ctx* ctx, SweepState* S, double* dRss) {
                     acc += d[i] * (gd - 2.0L * g0[(size_t)q * kGroupMax + i]);
                 }
                 corr[c] = (double)acc;
+            } else if (dense_on && nnz[c] >= dense_min) {
+                rep[c] = -2 - (int)dense_ids.size();  // placed behind the streamed representatives below
+                dense_ids.push_back(c);
             } else {
                 rep[c] = (int)r_off.size();
                 r_off.push_back((int64_t)r_idx.size());
@@ -824,7 +840,10 @@ int rss_run(ddb_ctx* ctx, SweepState* S, double* dRss) {
                 }
             }
         }
-        const int nrep = (int)r_off.size();
+        const int nsparse = (int)r_off.size(), nd = (int)dense_ids.size();
+        for (int c = 0; c < ncand; ++c)
+            if (rep[c] <= -2) rep[c] = nsparse + (-2 - rep[c]);
+        const int nrep = nsparse + nd;  // results: [streamed representatives | dense candidates]
         const int64_t rterms = (int64_t)r_idx.size();
         const size_t o_nnz = (size_t)nrep * 8, o_eq = o_nnz + (size_t)nrep * 4, o_idx = (o_eq + (size_t)nrep * 4 + 7) & ~size_t(7);
         const size_t o_val = (o_idx + (size_t)std::max<int64_t>(1, rterms) * 4 + 7) & ~size_t(7);
@@ -832,21 +851,30 @@ int rss_run(ddb_ctx* ctx, SweepState* S, double* dRss) {
         const size_t o_map = o_rep + (size_t)nrep * 8;
         DDB_TRY(S->rep_buf.reserve(o_map + (size_t)ncand * 4 + 64));
         unsigned char* rb = static_cast<unsigned char*>(S->rep_buf.p);
-        DDB_CUDA_TRY(cudaMemcpyAsync(rb, r_off.data(), (size_t)nrep * 8, cudaMemcpyHostToDevice, st));
-        DDB_CUDA_TRY(cudaMemcpyAsync(rb + o_nnz, r_nnz.data(), (size_t)nrep * 4, cudaMemcpyHostToDevice, st));
-        DDB_CUDA_TRY(cudaMemcpyAsync(rb + o_eq, r_eq.data(), (size_t)nrep * 4, cudaMemcpyHostToDevice, st));
+        if (nsparse) {
+            DDB_CUDA_TRY(cudaMemcpyAsync(rb, r_off.data(), (size_t)nsparse * 8, cudaMemcpyHostToDevice, st));
+            DDB_CUDA_TRY(cudaMemcpyAsync(rb + o_nnz, r_nnz.data(), (size_t)nsparse * 4, cudaMemcpyHostToDevice, st));
+            DDB_CUDA_TRY(cudaMemcpyAsync(rb + o_eq, r_eq.data(), (size_t)nsparse * 4, cudaMemcpyHostToDevice, st));
+        }
         if (rterms) {
             DDB_CUDA_TRY(cudaMemcpyAsync(rb + o_idx, r_idx.data(), (size_t)rterms * 4, cudaMemcpyHostToDevice, st));
             DDB_CUDA_TRY(cudaMemcpyAsync(rb + o_val, r_val.data(), (size_t)rterms * 8, cudaMemcpyHostToDevice, st));
         }
         DDB_CUDA_TRY(cudaMemcpyAsync(rb + o_map, rep.data(), (size_t)ncand * 4, cudaMemcpyHostToDevice, st));
         DDB_CUDA_TRY(cudaMemcpyAsync(S->rss_corr.p, corr.data(), (size_t)ncand * 8, cudaMemcpyHostToDevice, st));
-        RssCand c{nrep, rterms, reinterpret_cast<const int64_t*>(rb), reinterpret_cast<const int32_t*>(rb + o_nnz),
+        RssCand c{nsparse, rterms, reinterpret_cast<const int64_t*>(rb), reinterpret_cast<const int32_t*>(rb + o_nnz),
                   reinterpret_cast<const int32_t*>(rb + o_eq), reinterpret_cast<const int32_t*>(rb + o_idx),
                   reinterpret_cast<const double*>(rb + o_val)};
-        if (nrep > 0)
+        if (nsparse > 0)
             DDB_TRY(rss_core(ctx, c, map, targets, scale, S->cand_terms, S->rss_partials, reinterpret_cast<double*>(rb + o_rep),
                              &launches, mu));
+        if (nd > 0) {
+            DDB_TRY(S->dense_ids.reserve((size_t)nd * 4));
+            DDB_CUDA_TRY(cudaMemcpyAsync(S->dense_ids.p, dense_ids.data(), (size_t)nd * 4, cudaMemcpyHostToDevice, st));
+            DDB_TRY(rss_dense_run(ctx, S->dense_ids.as<int32_t>(), nd, S->cand_off.as<int64_t>(), S->cand_nnz.as<int32_t>(),
+                                  S->cand_eq.as<int32_t>(), S->cand_idx.as<int32_t>(), S->cand_val.as<double>(), scale, nullptr,
+                                  nullptr, S->dense_work, reinterpret_cast<double*>(rb + o_rep) + nsparse, &launches));
+        }
         scatter_group_rss_kernel<<<(ncand + 255) / 256, 256, 0, st>>>(reinterpret_cast<const double*>(rb + o_rep),
                                                                       reinterpret_cast<const int32_t*>(rb + o_map), ncand, dRss);
         ++launches;
@@ -855,8 +883,8 @@ int rss_run(ddb_ctx* ctx, SweepState* S, double* dRss) {
         ctx->timings.candidates = ncand;
         S->nstreamed = nrep;
         if (getenv("DDB_RSS_DEBUG"))
-            fprintf(stderr, "rss grouping: %d candidates (%lld terms) -> %d streamed (%lld terms), %d shared groups\n", ncand,
-                    (long long)nterms, nrep, (long long)rterms, ns);
+            fprintf(stderr, "rss grouping: %d candidates (%lld terms) -> %d streamed (%lld terms) + %d dense, %d shared groups\n",
+                    ncand, (long long)nterms, nsparse, (long long)rterms, nd, ns);
     }
     DDB_CUDA_TRY(cudaEventRecord(ctx->ev[5], st));
     DDB_CUDA_TRY(cudaStreamSynchronize(st));

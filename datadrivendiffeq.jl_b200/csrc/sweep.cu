@@ -1400,7 +1400,7 @@ void SweepState::release_all() {
     DevBuf* all[] = {&As, &Lfac, &dinv, &rs, &x, &xprev, &aux1, &aux2, &znew, &active, &eq, &lambdas_d, &cand_idx,
                      &cand_val, &cand_off, &cand_nnz, &cand_dof, &cand_eq, &counters, &pool_used_d, &run_cand,
                      &run_jfirst, &run_j, &path_support, &path_coef, &path_iters, &big_ws, &big_idx, &big_na,
-                     &big_list, &big_fail, &big_loc, &big_xbuf, &active_matrix, &shared_fail, &rss, &rss_partials, &out_tmp, &cand_terms,
+                     &big_list, &big_fail, &big_loc, &big_xbuf, &dense_ids, &dense_work, &active_matrix, &shared_fail, &rss, &rss_partials, &out_tmp, &cand_terms,
                      &Ninv, &tgt_terms, &rss_corr, &grp_buf, &rep_buf, &zsol, &canon_tmp};
     for (DevBuf* b : all) b->release();
 }

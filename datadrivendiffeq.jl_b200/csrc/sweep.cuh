@@ -40,6 +40,7 @@ struct SweepState {
     DevBuf path_support, path_coef, path_iters;
     DevBuf big_ws, big_idx, big_na, big_list, big_fail, active_matrix, shared_fail;
     DevBuf big_loc;   // sharded big steps: [na of my slots | fail of my slots | global slot of my slots] (3 x n_t ints)
+    DevBuf dense_ids, dense_work;  // rss pass of dense candidates (rss_dense.cu): candidate ids; coefficient matrix + partial sums
     DevBuf big_xbuf;  // sharded big steps: per parked target [solution (k) | failure flag], summed over the ranks
     DevBuf rss, rss_partials, out_tmp, cand_terms, Ninv, tgt_terms, rss_corr, grp_buf, rep_buf, zsol, canon_tmp;
     int nstreamed = 0;    // candidates actually streamed by the last rss pass (group representatives)
