@@ -172,11 +172,17 @@ __global__ void __launch_bounds__(256, 1) rss_dense_kernel(const DenseArgs a) {
         for (int b = 0; b < nblk; ++b) {
             const double* Cc = Cs + (b & 1) * kDC * kDP;
             const double* Tc = Ts + (b & 1) * kDS * kDP;
-            if (b + 1 < nblk) {  // the next block travels / is multiplied out underneath this one's DMMAs
-                fetch_c(b + 1, Cs + ((b + 1) & 1) * kDC * kDP);
-                build(rw, Ts + ((b + 1) & 1) * kDS * kDP);
-                if (b + 2 < nblk) load_factors(b + 2);
-            }
+            // The next block travels / is multiplied out underneath this one's DMMAs.  A warp issues in order, so its
+            // build (loads feeding multiplies) stalls its own DMMAs: the two warps of a sub-partition (w and w + 4) take
+            // the two jobs in OPPOSITE order, one builds while the other keeps the tensor pipe busy.
+            auto prefetch = [&]() {
+                if (b + 1 < nblk) {
+                    fetch_c(b + 1, Cs + ((b + 1) & 1) * kDC * kDP);
+                    build(rw, Ts + ((b + 1) & 1) * kDS * kDP);
+                    if (b + 2 < nblk) load_factors(b + 2);
+                }
+            };
+            if (warp < 4) prefetch();
             const double* pa = Cc + (wc * 32 + g) * kDP + t;
             const double* pb = Tc + (ws * 16 + g) * kDP + t;
 #pragma unroll 4
@@ -191,6 +197,7 @@ __global__ void __launch_bounds__(256, 1) rss_dense_kernel(const DenseArgs a) {
 #pragma unroll
                     for (int j = 0; j < 2; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
             }
+            if (warp >= 4) prefetch();
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncthreads();
         }
