@@ -57,3 +57,31 @@ def test_dense_pass_matches_term_by_term(n, deg, m, noise):
     theta = oracle.evaluate_library(basis.exponents, X)
     res = out_d.coefficients @ theta - D
     np.testing.assert_allclose(out_d.rss, np.sum(res * res, axis=1), rtol=1e-10)
+
+
+def test_dense_pass_with_term_normalisation():
+    """ZScore normalisation: the candidates live in the scaled space, the dense pass divides the coefficients by the
+    scales like the term-by-term pass does (``dense_fill_kernel``)."""
+    n, m = 18, 4000
+    X, D = systems.lorenz96_ensemble(m, n=n, seed=9, samples_per_traj=500)
+    D = D + 0.5 * np.random.default_rng(5).standard_normal(D.shape)
+    basis = ddb200.polynomial_basis(n, 2)
+    lams = 10.0 ** np.arange(-4, -0.4, 0.25)
+    opts = ddb200.DataDrivenCommonOptions(normalize="ZScoreTransform")
+    prob = ddb200.ContinuousDataDrivenProblem(X, DX=D)
+    sols = []
+    for dense in ("1", "0"):
+        old = os.environ.get("DDB_RSS_DENSE")
+        os.environ["DDB_RSS_DENSE"] = dense
+        try:
+            sols.append(ddb200.solve(prob, basis, ddb200.B200Sparse(ddb200.STLSQ(lams)), opts))
+        finally:
+            if old is None:
+                os.environ.pop("DDB_RSS_DENSE", None)
+            else:
+                os.environ["DDB_RSS_DENSE"] = old
+    a, b = sols
+    np.testing.assert_array_equal(a.coefficients, b.coefficients)
+    np.testing.assert_allclose(a.results[0].trainerror, b.results[0].trainerror, rtol=1e-10)
+    np.testing.assert_allclose(a.rss, b.rss, rtol=1e-10)
+    assert a.timings["big_steps"] > 0  # candidates of more than 128 terms exist: the dense pass had work
