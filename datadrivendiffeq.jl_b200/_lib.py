@@ -97,6 +97,7 @@ PROTOTYPES = {
     "ddb_residual": (C.c_int, [_P, _P, _P]),
     "ddb_residual_affine": (C.c_int, [_P, _P, _P, _P]),
     "ddb_term_minmax": (C.c_int, [_P, _P, _P]),
+    "ddb_term_css": (C.c_int, [_P, _P, _P]),
     "ddb_gram_affine_terms": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64]),
     "ddb_target_stats": (C.c_int, [_P, C.c_int64, _P, _P]),
     "ddb_group_target_stats": (C.c_int, [_P, _P, _P]),

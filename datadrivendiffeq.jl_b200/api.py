@@ -706,13 +706,14 @@ def _needs_processing(options: DataDrivenCommonOptions) -> bool:
     return options.normalize is not None or options.split != 1.0 or options.batchsize > 0
 
 
-def zscore_scales(G: np.ndarray, sums: np.ndarray, m: int) -> np.ndarray:
-    """Scales of ``fit(ZScoreTransform, Theta, dims = 2, center = false)`` (``data_processing.jl:75-80``) from
-    the Gram blocks: sigma_j = sqrt((sum theta_j^2 - (sum theta_j)^2 / m) / (m - 1)), constants scaled with 1."""
-    var = (np.diag(G) - sums * sums / m) / (m - 1)
-    sig = np.sqrt(np.maximum(var, 0.0))
-    # a constant row has zero spread up to the rounding of the two sums
-    sig[var <= 1e-14 * np.maximum(np.diag(G) / m, 1e-300)] = 1.0
+def zscore_scales(css: np.ndarray, m: int) -> np.ndarray:
+    """Scales of ``fit(ZScoreTransform, Theta, dims = 2, center = false)`` (``data_processing.jl:75-80``):
+    sigma_j = sqrt(css_j / (m - 1)) with the CENTRED sums of squares ``css_j = sum (theta_j - mean_j)^2`` of
+    ``ddb_term_css`` (two passes, like ``std`` of the materialised row in the reference: the one-pass form
+    ``sum theta^2 - (sum theta)^2 / m`` cancels for terms whose mean dwarfs their spread); an exactly zero spread --
+    a constant row -- is scaled with 1, the reference's ``iszero`` rule."""
+    sig = np.sqrt(np.maximum(css, 0.0) / (m - 1))
+    sig[sig == 0.0] = 1.0
     return sig
 
 
@@ -758,7 +759,7 @@ def _solve_processed(prob, basis, alg, options, X, Y, paths=False):
             ctx.gram()
             sums = ctx.gram_download()[1][:, 0].copy()
             ctx.upload(X, Y)
-        sigma = zscore_scales(G, sums, m)
+        sigma = zscore_scales(ctx.term_css(sums / m), m)
     # order of the training samples: shuffled by the DataLoader (data_processing.jl:38)
     batchsize = m_train if options.batchsize <= 0 else int(options.batchsize)
     perm = None
@@ -866,7 +867,7 @@ def _solve_processed_sharded(prob, basis, alg, options, X, Y):
             ctx.allreduce_gram()
             sums = ctx.gram_download()[1][:, 0].copy()
             ctx.upload(X, Y)
-        sigma = zscore_scales(G, sums, m)
+        sigma = zscore_scales(dist.allreduce_host_sum(ctx, ctx.term_css(sums / m), grp), m)
     batchsize = m_train if options.batchsize <= 0 else int(options.batchsize)
     perm = None
     if options.perm is not None:

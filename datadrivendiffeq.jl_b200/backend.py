@@ -162,6 +162,14 @@ class Context:
         _lib.check(self._lib.ddb_term_minmax(self._ctx, _lib.ptr(mn), _lib.ptr(mx)))
         return mn, mx
 
+    def term_css(self, center) -> np.ndarray:
+        """``ddb_term_css``: sum over the current sample view of ``(theta_j - center_j)^2`` for every library term."""
+        c = np.ascontiguousarray(center, dtype=np.float64)
+        assert c.size == self.k
+        out = np.zeros(self.k)
+        _lib.check(self._lib.ddb_term_css(self._ctx, _lib.ptr(c), _lib.ptr(out)))
+        return out
+
     def gram_affine_terms(self, shift, scale, tsum, ysum, m_total: int):
         """``ddb_gram_affine_terms``: the sweep then runs on ``(Theta_j - shift_j) / scale_j`` (UnitRangeTransform)."""
         a = [np.ascontiguousarray(v, dtype=np.float64) for v in (shift, scale, tsum, ysum)]

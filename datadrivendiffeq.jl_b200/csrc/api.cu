@@ -883,6 +883,102 @@ int ddb_term_minmax(ddb_ctx* ctx, double* mn, double* mx) {
     return DDB_OK;
 }
 
+// Centred sums of squares of every library term over the current view: css_j = sum_s (theta_j(s) - center_j)^2, the
+// second pass of a two-pass variance (what `std` of the materialised row does in the reference; the one-pass form
+// (sum theta^2 - (sum theta)^2 / m) cancels when a term's mean is much larger than its spread).  Per-CTA partial sums,
+// added in CTA order on the host: bit-reproducible.
+__global__ void __launch_bounds__(256) term_css_kernel(const double* __restrict__ X, int n, int64_t m, const uint16_t* __restrict__ factors,
+                                                       int k, const double* __restrict__ center, double* __restrict__ partial) {
+    extern __shared__ double xs[];  // kMMSamples x (n + 1): the states of the tile, then 1.0 (missing factors)
+    const int tid = threadIdx.x;
+    const int pitch = n + 1;
+    double acc[kMMTerms];
+#pragma unroll
+    for (int q = 0; q < kMMTerms; ++q) acc[q] = 0.0;
+    const int64_t ntiles = (m + kMMSamples - 1) / kMMSamples;
+    for (int64_t tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
+        const int64_t s0 = tl * kMMSamples;
+        const int valid = (int)min((int64_t)kMMSamples, m - s0);
+        __syncthreads();
+        for (int e = tid; e < valid * n; e += 256) xs[(e / n) * pitch + e % n] = X[s0 * n + e];
+        for (int s = tid; s < valid; s += 256) xs[s * pitch + n] = 1.0;
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < kMMTerms; ++q) {
+            const int j = tid + 256 * q;
+            if (j >= k) break;
+            const uint4 w4 = *reinterpret_cast<const uint4*>(factors + (size_t)j * kMaxFactors);
+            const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+            int f[kMaxFactors];
+#pragma unroll
+            for (int d = 0; d < kMaxFactors; ++d) {
+                const uint32_t c = (w[d >> 1] >> (16 * (d & 1))) & 0xFFFFu;
+                f[d] = (c == kNoFactor) ? n : (int)c;
+            }
+            const double cj = center[j];
+            for (int s = 0; s < valid; ++s) {
+                const double* xr = xs + s * pitch;
+                double p = xr[f[0]];
+#pragma unroll
+                for (int d = 1; d < kMaxFactors; ++d) p *= xr[f[d]];
+                const double r = p - cj;
+                acc[q] = fma(r, r, acc[q]);
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < kMMTerms; ++q) {
+        const int j = tid + 256 * q;
+        if (j < k) partial[(size_t)blockIdx.x * k + j] = acc[q];
+    }
+}
+
+int ddb_term_css(ddb_ctx* ctx, const double* center, double* css) {
+    CHECK_CTX(ctx);
+    if (!center || !css || ctx->k <= 0) {
+        set_error("ddb_term_css: library must be set, center and css non-null");
+        return DDB_INVALID_ARG;
+    }
+    const int k = ctx->k, n = ctx->n;
+    if (ctx->view_empty) {  // no sample in this rank's view
+        for (int j = 0; j < k; ++j) css[j] = 0.0;
+        return DDB_OK;
+    }
+    if (!ctx->dX || ctx->m <= 0) {
+        set_error("ddb_term_css: no data bound");
+        return DDB_BAD_STATE;
+    }
+    if (k > 256 * kMMTerms) {
+        set_error("ddb_term_css: libraries of more than %d terms are not supported", 256 * kMMTerms);
+        return DDB_UNSUPPORTED;
+    }
+    if (ctx->factors_nt != ctx->n_t || !ctx->d_factors.p) DDB_TRY(gram_ensure_factors(ctx, ((k + ctx->n_t + 127) / 128) * 128));
+    const size_t smem = (size_t)kMMSamples * (n + 1) * sizeof(double);
+    if (smem > 200 * 1024) {
+        set_error("ddb_term_css: too many states for the shared-memory tile");
+        return DDB_UNSUPPORTED;
+    }
+    const int64_t ntiles = (ctx->m + kMMSamples - 1) / kMMSamples;
+    const int nblk = (int)std::min<int64_t>(ntiles, (int64_t)ctx->sm_count * 4);
+    DDB_TRY(ctx->d_stats.reserve(((size_t)nblk + 1) * k * 8));
+    double* d_center = ctx->d_stats.as<double>();
+    double* d_part = d_center + k;
+    cudaStream_t st = ctx->stream;
+    DDB_CUDA_TRY(cudaMemcpyAsync(d_center, center, (size_t)k * 8, cudaMemcpyHostToDevice, st));
+    DDB_CUDA_TRY(cudaFuncSetAttribute(term_css_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    term_css_kernel<<<nblk, 256, smem, st>>>(ctx->dX, n, ctx->m, ctx->d_factors.as<uint16_t>(), k, d_center, d_part);
+    DDB_CUDA_TRY(cudaGetLastError());
+    std::vector<double> part((size_t)nblk * k);
+    DDB_CUDA_TRY(cudaMemcpyAsync(part.data(), d_part, part.size() * 8, cudaMemcpyDeviceToHost, st));
+    DDB_CUDA_TRY(cudaStreamSynchronize(st));
+    for (int j = 0; j < k; ++j) {
+        double s = 0.0;
+        for (int b = 0; b < nblk; ++b) s += part[(size_t)b * k + j];  // fixed order
+        css[j] = s;
+    }
+    return DDB_OK;
+}
+
 // G~ = S (G - mu t' - t mu' + m mu mu') S,  R~ = S (R - mu ysum'),  S = diag(1 / scale): the blocks of
 // theta~_j = (theta_j - mu_j) / scale_j from those of theta  (t = Theta 1, ysum = Y 1)
 __global__ void affine_terms_kernel(double* __restrict__ packed, int k, int n_t, const double* __restrict__ mu,

@@ -238,6 +238,12 @@ int ddb_residual(ddb_ctx* ctx, const double* coef, double* rss);
  * ddb_residual_affine: ddb_residual with a constant per target added to the fit (offset, n_t): residuals of a model
  *   given in the transformed space. */
 int ddb_term_minmax(ddb_ctx* ctx, double* mn, double* mx);
+/* css[j] = sum over the current sample view of (theta_j - center[j])^2 for every library term (host arrays, k each):
+ * the second pass of the two-pass standard deviation `fit(ZScoreTransform, Theta, dims = 2)` takes on the materialised
+ * Theta (src/utils/data_processing.jl:75-80); center = (sum theta_j) / m from the Gram blocks.  One HBM pass over the
+ * states, Theta is not built; per-CTA partial sums added in a fixed order (bit-reproducible); sum over the ranks of a
+ * sharded run. */
+int ddb_term_css(ddb_ctx* ctx, const double* center, double* css);
 int ddb_gram_affine_terms(ddb_ctx* ctx, const double* shift, const double* scale, const double* tsum, const double* ysum,
                           int64_t m_total);
 int ddb_residual_affine(ddb_ctx* ctx, const double* coef, const double* offset, double* rss);

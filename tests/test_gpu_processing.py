@@ -220,3 +220,28 @@ def test_term_minmax(ctx):
     mn, mx = ctx.term_minmax()
     np.testing.assert_allclose(mn, Th[:, 100:777].min(axis=1), rtol=1e-14)
     ctx.set_sample_range(0, -1)
+
+
+def test_zscore_scales_are_two_pass(ctx):
+    """the one-pass variance ``(sum theta^2 - (sum theta)^2 / m) / (m - 1)`` cancels for terms whose mean
+    dwarfs their spread (monomials of offset states).  The scales come from ``ddb_term_css`` -- centred sums of squares,
+    the second pass of ``std`` in the reference (``data_processing.jl:75-80``) -- and only an exactly zero spread is a
+    constant."""
+    rng = np.random.default_rng(12)
+    m = 5001
+    X = np.array([[1000.0], [3.0], [0.0]]) + np.array([[1e-2], [1.0], [2.0]]) * rng.standard_normal((3, m))
+    basis = ddb200.polynomial_basis(3, 3)
+    Th = oracle.evaluate_library(basis.exponents, X)
+    ctx.set_library(basis.exponents)
+    ctx.upload(X, X)
+    mean = Th.mean(axis=1)
+    css = ctx.term_css(mean)
+    ref = np.sum((Th - mean[:, None]) ** 2, axis=1)
+    np.testing.assert_allclose(css, ref, rtol=1e-11, atol=0.0)
+    assert css[0] == 0.0  # the constant term: exactly zero spread
+    sigma = ddb200.api.zscore_scales(css, m)
+    np.testing.assert_allclose(sigma, oracle.zscore_fit(Th), rtol=1e-11)
+    # the one-pass form is visibly wrong here: x1^3 has mean 1e9 and spread 3e4
+    onepass = np.sqrt(np.maximum((np.sum(Th * Th, axis=1) - Th.sum(axis=1) ** 2 / m) / (m - 1), 0.0))
+    j = int(np.argmax(np.abs(mean)))
+    assert abs(onepass[j] / sigma[j] - 1.0) > 1e-9 > abs(np.sqrt(ref[j] / (m - 1)) / sigma[j] - 1.0)
