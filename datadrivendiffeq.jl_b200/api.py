@@ -834,8 +834,6 @@ def _solve_processed_sharded(prob, basis, alg, options, X, Y):
     the library).  ZScore scales come from the all-reduced blocks of all samples."""
     from . import dist
 
-    if options.normalize == "UnitRangeTransform":
-        raise ValueError("B200Sparse: UnitRangeTransform is not available on the sharded path (it needs a min / max exchange)")
     ctx = alg.context()
     grp = alg.group
     if not dist._has_comm(ctx):
@@ -852,8 +850,25 @@ def _solve_processed_sharded(prob, basis, alg, options, X, Y):
     if m_train <= 0:
         raise ValueError("B200Sparse: the training split is empty")
     lt = min(max(m_train - lo, 0), m_local)  # this rank's training samples: local [0, lt); test part: [lt, m_local)
+    unit = options.normalize == "UnitRangeTransform"
+    if unit:  # a row of ones rides along as one more target (see _solve_processed)
+        Y = np.vstack([Y, np.ones((1, m_local))])
     ctx.upload(X, Y)
     sigma = None
+    umin = udiv = None
+    if unit:
+        # extrema over ALL samples: the only exchange primitive of the ABI is a sum, so every rank writes its own
+        # (min, max) into its slot of a zero vector and the sum is the gather (adding zeros is exact)
+        import torch.distributed as tdist
+
+        rank, world = tdist.get_rank(grp), tdist.get_world_size(grp)
+        mn, mx = ctx.term_minmax()
+        slots = np.zeros((world, 2, k))
+        slots[rank, 0], slots[rank, 1] = mn, mx
+        slots = dist.allreduce_host_sum(ctx, slots.ravel(), grp).reshape(world, 2, k)
+        umin, umax = slots[:, 0].min(axis=0), slots[:, 1].max(axis=0)
+        rng = umax - umin
+        udiv = np.where(rng > 0.0, rng, 1.0)
     if options.normalize == "ZScoreTransform":
         ctx.gram()
         ctx.allreduce_gram()
@@ -896,16 +911,28 @@ def _solve_processed_sharded(prob, basis, alg, options, X, Y):
         ctx.allreduce_gram()
         if sigma is not None:
             ctx.gram_scale_terms(sigma)
+        if unit:
+            tsum = ctx.gram_download()[1][:, n_t].copy()       # Theta 1 over this batch, all ranks (the ones target)
+            ysum = ctx.target_stats(b1 - b0)[0] * (b1 - b0)     # Y 1 (all-reduced inside)
+            ctx.gram_affine_terms(umin, udiv, tsum, ysum, b1 - b0)
         ctx.sweep(prm, lambdas, b1 - b0)
         ctx.rss()
         ctx.allreduce_rss()
         out = ctx.select()
+        if unit:  # drop the auxiliary ones target
+            out.coefficients, out.lambda_opt, out.iterations = out.coefficients[:n_t], out.lambda_opt[:n_t], out.iterations[:n_t]
+            out.rss, out.dof, out.flags = out.rss[:n_t], out.dof[:n_t], out.flags[:n_t]
         Cs = out.coefficients
-        Cu = Cs / sigma[None, :] if sigma is not None else Cs
+        Cu = Cs / sigma[None, :] if sigma is not None else (Cs / udiv[None, :] if unit else Cs)
         testerror = None
         if m_train < m:
             ctx.set_sample_range(lt, m_local)
-            testerror = float(np.sum(dist.allreduce_host_sum(ctx, ctx.residual(Cu), grp)))
+            if unit:
+                off = np.concatenate([-(Cu @ umin), [0.0]])
+                part = ctx.residual_affine(np.vstack([Cu, np.zeros((1, k))]), off)[:n_t]
+            else:
+                part = ctx.residual(Cu)
+            testerror = float(np.sum(dist.allreduce_host_sum(ctx, part, grp)))
         results.append(SparseRegressionResult(coefficients=Cs, dof=int(np.sum(np.abs(Cs) > 0.0)), lambda_=out.lambda_opt,
                                               iterations=out.iterations, testerror=testerror,
                                               trainerror=float(np.sum(out.rss)), retcode=1 if not np.any(out.flags & 1) else 2))
@@ -914,11 +941,15 @@ def _solve_processed_sharded(prob, basis, alg, options, X, Y):
                    else results[i].trainerror)
     results = [results[i] for i in order]
     best = results[0]
-    C = best.coefficients / sigma[None, :] if sigma is not None else best.coefficients
+    if unit:
+        C = (best.coefficients - umin[None, :]) / udiv[None, :]  # lib commonsolve.jl:19-21, as written
+    else:
+        C = best.coefficients / sigma[None, :] if sigma is not None else best.coefficients
     Cr = construct_coefficients(C, options.digits)
-    rss_all = float(np.sum(dist.allreduce_host_sum(ctx, ctx.residual(Cr), grp)))
+    part = ctx.residual(np.vstack([Cr, np.zeros((1, k))]))[:n_t] if unit else ctx.residual(Cr)
+    rss_all = float(np.sum(dist.allreduce_host_sum(ctx, part, grp)))
     t = ctx.timings()
-    null_ss = float(np.sum(ctx.target_stats(m)[1]))
+    null_ss = float(np.sum(ctx.target_stats(m)[1][:n_t]))
     return DataDrivenSolution(basis=basis, coefficients=Cr, results=results, rss=rss_all, dof=int(np.sum(Cr != 0.0)),
                               nobs=int(n_t * m), retcode=best.retcode, timings=t, null_ss=null_ss)
 

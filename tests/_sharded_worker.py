@@ -37,14 +37,15 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
         return
-    if alg == "PROCESSED":  # ZScore + split + shuffled batches on shards against the single-GPU run
+    if alg in ("PROCESSED", "PROCESSED_UNIT"):  # normalisation + split + shuffled batches on shards against the single-GPU run
         Xs, Ds = systems.lorenz_ensemble(2001, seed=1, samples_per_traj=500)
         Xs, Ds = Xs[:, :1901], Ds[:, :1901] + 0.05 * np.random.default_rng(1).standard_normal((3, 1901))
         mm = Xs.shape[1]
         basis = ddb200.polynomial_basis(3, 3)
         lam = 10.0 ** np.arange(-1, 1.01, 0.25)
         m_train = int(round(0.8 * mm))
-        opts = ddb200.DataDrivenCommonOptions(normalize="ZScoreTransform", split=0.8, batchsize=400, partial=True,
+        opts = ddb200.DataDrivenCommonOptions(normalize="ZScoreTransform" if alg == "PROCESSED" else "UnitRangeTransform",
+                                              split=0.8, batchsize=400, partial=True,
                                               perm=np.random.default_rng(3).permutation(m_train))
         lo, hi = ddb200.dist.shard_range(mm, rank, world)
         sol = ddb200.solve(ddb200.ContinuousDataDrivenProblem(Xs[:, lo:hi], DX=Ds[:, lo:hi]), basis,

@@ -207,12 +207,14 @@ def test_torchrun_two_ranks_dmd(tmp_path):
 
 
 @pytest.mark.skipif(_ngpus() < 2, reason="needs 2 GPUs")
-def test_torchrun_two_ranks_processing_options(tmp_path):
-    """ZScore normalisation + train/test split + shuffled mini-batches on the sharded path (``src/commonsolve.jl:
-    92-139`` options on row shards): same batches, same ranking by test error, same models as one GPU."""
+@pytest.mark.parametrize("mode", ["PROCESSED", "PROCESSED_UNIT"])
+def test_torchrun_two_ranks_processing_options(tmp_path, mode):
+    """ZScore / UnitRange normalisation + train/test split + shuffled mini-batches on the sharded path
+    (``src/commonsolve.jl:92-139`` options on row shards): same batches, same ranking by test error, same models as one
+    GPU.  (UnitRange: the extrema of all samples are gathered through the sum all-reduce, one slot per rank.)"""
     out = tmp_path / "proc.npz"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29613", os.path.join(ROOT, "tests", "_sharded_worker.py"), str(out), "PROCESSED"]
+           "--master-port", "29613" if mode == "PROCESSED" else "29614", os.path.join(ROOT, "tests", "_sharded_worker.py"), str(out), mode]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     z = np.load(out)
