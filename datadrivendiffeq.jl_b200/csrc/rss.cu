@@ -402,6 +402,77 @@ __global__ void __launch_bounds__(256, 2) rss_lane_kernel(const RssArgs a) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Few candidates on NARROW samples (C2: Lorenz, 3 states + 3 targets = 48 bytes per sample, three models of 2-3 terms):
+// thread = SAMPLE.  The tiled kernels above pay a transposing stage-in and per-tile barriers that only amortise over
+// many candidates; here a thread reads its sample straight from global memory (a warp's samples are contiguous), keeps
+// it in a private shared-memory row (odd pitch: dynamic factor indices without bank conflicts), and walks the
+// candidates' term records, which sit in shared memory once per CTA.  Per-candidate sums: thread -> warp shuffle tree
+// -> CTA (fixed order) -> per-CTA partial -> rss_reduce_kernel.  C2: 0.70 -> see DESIGN 4.3 (HBM time 0.07 ms).
+constexpr int kNarrowStates = 16;   // n + n_t
+constexpr int kNarrowCands = 32;
+constexpr int kNarrowTerms = 256;
+
+template <int NF>
+__global__ void __launch_bounds__(256) rss_narrow_kernel(const RssArgs a) {
+    __shared__ RssTerm s_terms[kNarrowTerms];
+    __shared__ int s_off[kNarrowCands + 1], s_eq[kNarrowCands];
+    __shared__ double s_shift[kNarrowCands];
+    __shared__ double s_red[8][kNarrowCands];
+    extern __shared__ double rows[];  // 256 x pitch: [x_0 .. x_(n-1) | y_0 .. y_(n_t-1) | 1.0], then ncand x 256 sums
+    const int n = a.n, n_t = a.n_t, w = n + n_t;
+    const int pitch = (w + 1) | 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nc = a.ncand;
+    if (tid == 0) {  // compact copy of the candidates' records (their pool offsets are arbitrary)
+        int o = 0;
+        for (int c = 0; c < nc; ++c) s_off[c] = o, o += a.cand_nnz[c];
+        s_off[nc] = min(o, kNarrowTerms);
+    }
+    if (tid < nc) {
+        s_eq[tid] = a.cand_eq[tid];
+        s_shift[tid] = a.cand_shift ? a.cand_shift[tid] : 0.0;
+    }
+    __syncthreads();
+    for (int c = 0; c < nc; ++c)
+        for (int t = tid; t < s_off[c + 1] - s_off[c]; t += 256) s_terms[s_off[c] + t] = a.terms[a.cand_off[c] + t];
+    double* row = rows + tid * pitch;
+    row[w] = 1.0;
+    __syncthreads();
+    double* acc = rows + 256 * pitch + tid;  // [candidate][thread]: this thread's running sums (conflict-free)
+    for (int c = 0; c < nc; ++c) acc[c * 256] = 0.0;
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    for (int64_t s = (int64_t)blockIdx.x * 256 + tid; s < a.m; s += stride) {
+        for (int i = 0; i < n; ++i) row[i] = a.X[s * n + i];
+        for (int i = 0; i < n_t; ++i) row[n + i] = a.Y[s * n_t + i];
+        for (int c = 0; c < nc; ++c) {
+            double fit = s_shift[c];
+            for (int t = s_off[c]; t < s_off[c + 1]; ++t) {
+                const RssTerm& r = s_terms[t];
+                double p = row[r.o16[0]];
+#pragma unroll
+                for (int d = 1; d < NF; ++d) p *= row[r.o16[d]];  // factors beyond the library's degree are ones
+                fit = fma(r.val, p, fit);
+            }
+            const double res = fit - row[n + s_eq[c]];
+            acc[c * 256] = fma(res, res, acc[c * 256]);
+        }
+    }
+    for (int c = 0; c < nc; ++c) {
+        double v = acc[c * 256];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) s_red[warp][c] = v;
+    }
+    __syncthreads();
+    if (tid < nc) {
+        double v = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v += s_red[q][tid];
+        a.partials[(size_t)blockIdx.x * nc + tid] = v;
+    }
+}
+
 __global__ void rss_reduce_kernel(const double* __restrict__ partials, int nparts, int ncand, double* __restrict__ rss) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncand) return;
@@ -486,6 +557,43 @@ static int rss_core(ddb_ctx* ctx, const RssCand& c, const int32_t* map, const Rs
                                                               ctx->d_cand_shift.as<double>());
         ++*launches;
         cand_shift = ctx->d_cand_shift.as<double>();
+    }
+    // few candidates on narrow samples: thread = sample (see rss_narrow_kernel)
+    {
+        const char* nenv = getenv("DDB_RSS_NARROW");
+        const int w = ctx->n + ctx->n_t;
+        if (!(nenv && atoi(nenv) == 0) && !targets && w <= kNarrowStates && ncand > 0 && ncand <= kNarrowCands &&
+            c.nterms <= kNarrowTerms && ctx->m >= 4096) {
+            const int pitch_n = (w + 1) | 1;
+            const int nparts = (int)std::min<int64_t>((ctx->m + 255) / 256, (int64_t)ctx->sm_count * 8);
+            DDB_TRY(partials.reserve((size_t)nparts * ncand * 8));
+            auto nkern = ctx->max_degree <= 2 ? rss_narrow_kernel<2> : ctx->max_degree <= 3 ? rss_narrow_kernel<3>
+                         : ctx->max_degree <= 5 ? rss_narrow_kernel<5> : rss_narrow_kernel<kMaxFactors>;
+            DDB_CUDA_TRY(cudaFuncSetAttribute(nkern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)((size_t)256 * (pitch_n + ncand) * sizeof(double))));
+            RssArgs a;
+            a.X = ctx->dX;
+            a.Y = ctx->dY;
+            a.n = ctx->n;
+            a.n_t = ctx->n_t;
+            a.m = ctx->m;
+            a.ncand = ncand;
+            a.cand_off = c.off;
+            a.cand_nnz = c.nnz;
+            a.cand_eq = c.eq;
+            a.terms = terms.as<RssTerm>();
+            a.targets = nullptr;
+            a.cand_shift = cand_shift;
+            a.term_cap = 0;
+            a.sub = 1;
+            a.pitch = pitch;
+            a.partials = partials.as<double>();
+            nkern<<<nparts, 256, (size_t)256 * (pitch_n + ncand) * sizeof(double), st>>>(a);
+            rss_reduce_kernel<<<(ncand + 255) / 256, 256, 0, st>>>(partials.as<double>(), nparts, ncand, dRss);
+            *launches += 2;
+            DDB_CUDA_TRY(cudaGetLastError());
+            return DDB_OK;
+        }
     }
     // few sparse candidates on wide samples: the lane-per-candidate kernel (see rss_lane_kernel)
     const char* lenv = getenv("DDB_RSS_LANE");
