@@ -37,7 +37,7 @@ def _solve(X, D, basis, lams, dense):
             os.environ["DDB_RSS_DENSE"] = old
 
 
-@pytest.mark.parametrize("n,deg,m,noise", [(18, 2, 5000, 0.5), (15, 2, 4001, 0.3), (8, 3, 3000, 0.5)])
+@pytest.mark.parametrize("n,deg,m,noise", [(18, 2, 5000, 0.5), (15, 2, 4001, 0.3), (8, 3, 3000, 0.5), (64, 2, 6113, 1.0)])
 def test_dense_pass_matches_term_by_term(n, deg, m, noise):
     X, D = systems.lorenz96_ensemble(m, n=n, seed=7, samples_per_traj=500)
     D = D + noise * np.random.default_rng(3).standard_normal(D.shape)
