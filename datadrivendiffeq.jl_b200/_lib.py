@@ -108,6 +108,7 @@ PROTOTYPES = {
     "ddb_gram_buffer": (C.c_int, [_P, C.POINTER(_P)]),
     "ddb_gram_download": (C.c_int, [_P, _P, _P, _P]),
     "ddb_moment_wave_describe": (C.c_int64, [C.c_int, C.c_int, _P, C.c_int, C.c_int64, C.c_int, _P, C.c_int64, _P]),
+    "ddb_moment_builder_describe": (C.c_int64, [C.c_int, C.c_int, _P, C.c_int, _P, C.c_int64, _P, C.c_int64, _P, C.c_int64]),
     "ddb_moment_plan_describe": (C.c_int64, [C.c_int, C.c_int, _P, C.c_int, _P, C.c_int64, _P, C.c_int64, _P, C.c_int64, _P]),
     "ddb_gram_upload": (C.c_int, [_P, _P, _P, _P, C.c_int]),
     "ddb_implicit_select": (C.c_int, [_P, _P, C.c_int]),

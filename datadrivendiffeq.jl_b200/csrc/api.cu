@@ -112,6 +112,8 @@ int64_t moment_wave_describe(const uint8_t* exps, int n, int k, int n_t, int64_t
                              int64_t cap, double* info);
 int64_t moment_plan_describe(const uint8_t* exps, int n, int k, int n_t, int32_t* src, int64_t src_cap, uint16_t* tab,
                              int64_t tab_cap, int32_t* pairs, int64_t pairs_cap, int64_t* info);
+int64_t moment_builder_describe(const uint8_t* exps, int n, int k, int n_t, uint32_t* optab, int64_t optab_cap,
+                                uint8_t* opcnt, int64_t opcnt_cap, int32_t* block_ops, int64_t block_cap);
 void trsm_free(ddb_ctx* ctx);
 void comm_free(ddb_ctx* ctx);
 void userfeat_free(ddb_ctx* ctx);
@@ -1185,6 +1187,15 @@ int64_t ddb_moment_plan_describe(int n, int k, const uint8_t* exps, int n_t, int
         return DDB_INVALID_ARG;
     }
     return moment_plan_describe(exps, n, k, n_t, src, src_cap, factors, factors_cap, pairs, pairs_cap, info);
+}
+
+int64_t ddb_moment_builder_describe(int n, int k, const uint8_t* exps, int n_t, uint32_t* optab, int64_t optab_cap,
+                                    uint8_t* opcnt, int64_t opcnt_cap, int32_t* block_ops, int64_t block_cap) {
+    if (n <= 0 || k <= 0 || n_t <= 0 || !exps) {
+        set_error("ddb_moment_builder_describe: n, k, n_t must be positive and exps non-null");
+        return DDB_INVALID_ARG;
+    }
+    return moment_builder_describe(exps, n, k, n_t, optab, optab_cap, opcnt, opcnt_cap, block_ops, block_cap);
 }
 
 int64_t ddb_moment_wave_describe(int n, int k, const uint8_t* exps, int n_t, int64_t m, int nctas, int64_t* segments,

@@ -61,7 +61,6 @@ struct GramCfg {
 // with fewer than NF factors reads ones[s] for the missing ones (stride 1) and a padding row of the
 // library reads the 0.0 (stride 0): every Theta entry is a product of exactly NF shared-memory values,
 // no predicates in the hot loop.
-constexpr int kVOnes = 0, kVZero = 16, kVX = 18;
 __host__ __device__ inline size_t gram_vbytes(int n, int n_t) {
     size_t v = (size_t)(kVX + kKS * (n + n_t)) * sizeof(double);
     return (v + 127) & ~size_t(127);
@@ -394,6 +393,297 @@ __global__ void __launch_bounds__(GramCfg<BT>::kThreads, GramCfg<BT>::kMinBlocks
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tensor-pipe builder (moment schedule, virtual terms of at most two factors: degree-2 libraries)
+// ---------------------------------------------------------------------------------------------
+// An FP64 multiply issued between DMMAs costs the tensor pipe almost a whole DMMA slot (tools/dmma_probe.cu:
+// 36.6 -> 32.1 TFLOP/s with the four products per thread and k-step of gram_kernel).  Here the PRODUCTS THEMSELVES
+// run on the tensor pipe: one DMMA with a one-hot A operand multiplies 8 first factors v_j with 2 second factors u_r
+// for 4 samples,
+//     A[(s, r)][k] = u_r(s) if k == s else 0,   B[k][j] = v_j(s_k),   C = 0   ->   D[(s, r)][j] = u_r(s) v_j(s),
+// every output one correctly rounded product (all other addends are exact zeros), i.e. 64 library values per
+// instruction instead of 32 per DMUL, and no FP64-pipe instruction at all in the loop (probe: 34.1 TFLOP/s with two
+// such ops per k-step).  Which (u, v) rectangles cover the terms of a block is the host's job (cover_block in
+// gram_moment.cu); the kernel only sees, per warp and stage, up to kMbOpSlots ops as per-lane tables of four 16-bit
+// byte offsets: A source and B source inside the raw-sample slot (lanes that hold a zero of the one-hot operand
+// point at the slot's 0.0), and the two destinations inside the Theta stage (unused outputs go to the pad columns).
+// Library values that are a single raw value (targets, degree-1 terms, the constant) are not multiplied at all:
+// up to kMbCopySlots copy slots per warp and stage move one double per lane.
+// Everything else (TMA ring, tile ring, barriers, MMA patches, flush) is gram_kernel<128, 2> for off-diagonal pairs.
+template <uint32_t MASK>
+__device__ __forceinline__ void stage_body_mb(double (&acc)[8][4][2], const double* __restrict__ pa,
+                                              const double* __restrict__ pb, const unsigned char* __restrict__ v,
+                                              unsigned char* __restrict__ tn, const uint2* __restrict__ wtab,
+                                              const uint32_t* __restrict__ ctab, const uint32_t ncopy) {
+    constexpr int LDT = GramCfg<128>::kPitch;
+    // straight-line code: three ops in k-steps 0..2, two in the last (unused slots hold ops that multiply zeros
+    // into the pad columns), so that ptxas can hoist the table -> operand load chains under the DMMAs
+#pragma unroll
+    for (int kk = 0; kk < kKS / 4; ++kk) {
+        constexpr int kMaxOps = 3;
+        const int nops = (kk < 3) ? 3 : 2;
+        uint2 e[kMaxOps];
+        double ua[kMaxOps], vb[kMaxOps], d[kMaxOps][2];
+#pragma unroll
+        for (int o = 0; o < kMaxOps; ++o)
+            if (o < nops) {
+                e[o] = wtab[(kk * 3 + o) * 32];
+                ua[o] = *reinterpret_cast<const double*>(v + (e[o].x & 0xFFFFu));
+                vb[o] = *reinterpret_cast<const double*>(v + (e[o].x >> 16));
+            }
+        double a[8], b[4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if ((MASK >> (4 * i)) & 0xFu) a[i] = pa[kk * 4 * LDT + 8 * i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if ((MASK >> j) & 0x11111111u) b[j] = pb[kk * 4 * LDT + 8 * j];
+#pragma unroll
+        for (int o = 0; o < kMaxOps; ++o)
+            if (o < nops) {
+                d[o][0] = d[o][1] = 0.0;
+                dmma884(d[o][0], d[o][1], ua[o], vb[o]);
+            }
+        if (kk == 0) {  // one copy slot is always there (an unused one moves a zero into a pad column)
+            const uint32_t c = ctab[0];
+            *reinterpret_cast<double*>(tn + (c >> 16)) = *reinterpret_cast<const double*>(v + (c & 0xFFFFu));
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if ((MASK >> (i * 4 + j)) & 1u) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            if (i == 1) {
+#pragma unroll
+                for (int o = 0; o < kMaxOps; ++o)
+                    if (o < nops) {
+                        *reinterpret_cast<double*>(tn + (e[o].y & 0xFFFFu)) = d[o][0];
+                        *reinterpret_cast<double*>(tn + (e[o].y >> 16)) = d[o][1];
+                    }
+            }
+        }
+    }
+    if (ncopy > 1) {  // warp-uniform; only pairs with a block of targets have more than one copy slot per warp
+#pragma unroll 1
+        for (uint32_t q = 1; q < ncopy; ++q) {
+            const uint32_t c = ctab[q * 32];
+            *reinterpret_cast<double*>(tn + (c >> 16)) = *reinterpret_cast<const double*>(v + (c & 0xFFFFu));
+        }
+    }
+}
+
+inline size_t gram_mb_smem_bytes(int n, int n_t) {
+    return 128 + kNVS * gram_mb_vbytes(n, n_t) + (size_t)kNTS * GramCfg<128>::kStageDoubles * sizeof(double) +
+           (size_t)kMbPairWords * sizeof(uint32_t);
+}
+
+__global__ void __launch_bounds__(GramCfg<128>::kThreads, 1) gram_mb_kernel(const GramArgs args) {
+    using Cfg = GramCfg<128>;
+    constexpr int BT = 128;
+    constexpr int LDT = Cfg::kPitch;
+    constexpr int KS = kKS;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+
+    const int n = args.n, n_t = args.n_t;
+    const uint32_t xrow_bytes = (uint32_t)(n * sizeof(double));
+    const uint32_t ybytes = (uint32_t)(KS * n_t * sizeof(double));
+    const int px = mb_pitch(n);
+    const int vdoubles = (int)(gram_mb_vbytes(n, n_t) / sizeof(double));
+
+    uint64_t* vfull = reinterpret_cast<uint64_t*>(smem_raw);  // [kNVS] raw samples landed
+    uint64_t* tfull = vfull + kNVS;                           // [kNTS] Theta stage built by all warps
+    double* vring = reinterpret_cast<double*>(smem_raw + 128);
+    double* tring = vring + kNVS * vdoubles;
+    uint32_t* otab = reinterpret_cast<uint32_t*>(tring + kNTS * Cfg::kStageDoubles);
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    uint32_t* wwords = otab + warp * kMbWarpWords;                     // this warp's tables
+    const uint2* wtab = reinterpret_cast<const uint2*>(wwords) + lane;  // ops, this lane's column
+    const uint32_t* ctab = wwords + kMbOpSlots * 64 + lane;             // copy slots
+
+    if (tid == 0) {
+        for (int i = 0; i < kNVS; ++i) mbar_init(&vfull[i], 1);
+        for (int i = 0; i < kNTS; ++i) mbar_init(&tfull[i], Cfg::kWarps);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int e = tid; e < kNVS * kVX; e += Cfg::kThreads) {
+        const int w = e % kVX;
+        vring[(e / kVX) * vdoubles + w] = (w < kVZero) ? 1.0 : 0.0;
+    }
+    // columns no op writes (terms past the end of the virtual library) stay 0.0 for the whole launch
+    for (int e = tid; e < kNTS * Cfg::kStageDoubles; e += Cfg::kThreads) tring[e] = 0.0;
+    __syncthreads();
+
+    const int64_t nstages_total = (args.m + KS - 1) / KS;
+    const int seg_begin = args.cta_seg_begin[blockIdx.x];
+    const int seg_end = args.cta_seg_begin[blockIdx.x + 1];
+    int total = 0;
+    for (int sg = seg_begin; sg < seg_end; ++sg) total += (int)(args.segs[sg].stage_end - args.segs[sg].stage_begin);
+    if (total == 0) return;
+
+    // ---- raw-sample cursor (as gram_kernel) -----------------------------------------------------------------
+    int tma_seg = seg_begin;
+    int tma_stage = (int)args.segs[seg_begin].stage_begin, tma_seg_end = (int)args.segs[seg_begin].stage_end;
+    int tma_item = 0;
+    uint32_t ragged_slots = 0;
+    const int ragged_stage = (args.m % KS) ? (int)(nstages_total - 1) : -1;
+    auto request_samples = [&]() {
+        if (tma_item >= total) return;
+        const int slot = tma_item & (kNVS - 1);
+        const bool mine = (tma_item % Cfg::kWarps) == warp;
+        if (tma_stage != ragged_stage) {
+            if ((ragged_slots >> slot) & 1) {
+                ragged_slots &= ~(1u << slot);
+                if (mine) {
+                    if (lane < KS) vring[slot * vdoubles + kVOnes + lane] = 1.0;
+                    __syncwarp();
+                }
+            }
+            if (mine) {  // the X tile row by row (padded pitch), the Y tile in one piece
+                double* dst = vring + slot * vdoubles + kVX;
+                const int64_t s0 = (int64_t)tma_stage * KS;
+                if (lane == 0) mbar_expect_tx(&vfull[slot], KS * xrow_bytes + ybytes);
+                __syncwarp();
+                if (lane < KS) bulk_g2s(dst + lane * px, args.X + (s0 + lane) * n, xrow_bytes, &vfull[slot]);
+                if (lane == 0) bulk_g2s(dst + KS * px, args.Y + s0 * n_t, ybytes, &vfull[slot]);
+            }
+        } else {
+            ragged_slots |= 1u << slot;
+            if (mine) {
+                double* dst = vring + slot * vdoubles;
+                const int64_t s0 = (int64_t)tma_stage * KS;
+                const int valid = (int)(args.m - s0);
+                for (int e = lane; e < KS * n; e += 32)
+                    dst[kVX + (e / n) * px + e % n] = (e < valid * n) ? args.X[s0 * n + e] : 0.0;
+                for (int e = lane; e < KS * n_t; e += 32)
+                    dst[kVX + KS * px + e] = (e < valid * n_t) ? args.Y[s0 * n_t + e] : 0.0;
+                if (lane < KS) dst[kVOnes + lane] = (lane < valid) ? 1.0 : 0.0;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&vfull[slot]);
+            }
+        }
+        ++tma_item;
+        if (++tma_stage == tma_seg_end && ++tma_seg < seg_end) {
+            tma_stage = (int)args.segs[tma_seg].stage_begin;
+            tma_seg_end = (int)args.segs[tma_seg].stage_end;
+        }
+    };
+
+    // ---- build cursor: this warp's op table of the pair whose Theta tiles are built next -----------------------
+    int bseg = seg_begin;
+    int64_t bstage = 0, bseg_end = 0;
+    uint32_t bcnt = 0;  // copy slots in use
+    auto load_ops = [&]() {
+        const GramSegment seg = args.segs[bseg];
+        bstage = seg.stage_begin;
+        bseg_end = seg.stage_end;
+        const int pair = seg.pad >> 8;
+        const uint32_t* src = args.optab + (size_t)pair * kMbPairWords + warp * kMbWarpWords;
+        __syncwarp();
+#pragma unroll 1
+        for (int e = lane; e < kMbWarpWords; e += 32) wwords[e] = src[e];
+        bcnt = args.opcnt[pair * Cfg::kWarps + warp] >> 4;
+        __syncwarp();
+    };
+    auto advance_build = [&]() {
+        if (++bstage == bseg_end && ++bseg < seg_end) load_ops();
+    };
+
+    // ---- prologue: request the first raw tiles, build Theta(0..kAhead-1) completely ------------------------------
+#pragma unroll 1
+    for (int i = 0; i < kNVS; ++i) request_samples();
+    load_ops();
+#pragma unroll 1
+    for (int it = 0; it < kAhead && it < total; ++it) {
+        mbar_wait(&vfull[it], 0);
+        const unsigned char* v = reinterpret_cast<const unsigned char*>(vring + it * vdoubles);
+        unsigned char* tn = reinterpret_cast<unsigned char*>(tring + it * Cfg::kStageDoubles);
+#pragma unroll 1
+        for (int q = 0; q < kMbOpSlots; ++q) {
+            const uint2 e = wtab[q * 32];
+            const double ua = *reinterpret_cast<const double*>(v + (e.x & 0xFFFFu));
+            const double vb = *reinterpret_cast<const double*>(v + (e.x >> 16));
+            double d0 = 0.0, d1 = 0.0;
+            dmma884(d0, d1, ua, vb);
+            *reinterpret_cast<double*>(tn + (e.y & 0xFFFFu)) = d0;
+            *reinterpret_cast<double*>(tn + (e.y >> 16)) = d1;
+        }
+#pragma unroll 1
+        for (int q = 0; q < (int)max(bcnt, 1u); ++q) {
+            const uint32_t c = ctab[q * 32];
+            *reinterpret_cast<double*>(tn + (c >> 16)) = *reinterpret_cast<const double*>(v + (c & 0xFFFFu));
+        }
+        advance_build();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tfull[it]);
+    }
+
+    // ---- MMA cursor ---------------------------------------------------------------------------------------------
+    const int wm = (0x4B >> warp) & 1;  // as gram_kernel
+    const int wn = (0x7E84 >> (2 * warp)) & 3;
+    int item = 0;
+    bool ready_t = false, ready_v = false;
+    for (int sg = seg_begin; sg < seg_end; ++sg) {
+        const GramSegment seg = args.segs[sg];
+        const bool flat = (seg.pad & 3) != 0;
+        const int row0 = flat ? 0 : wm * 64;
+        const int col0 = flat ? warp * 16 : wn * 32;
+        const int shape = !flat ? 0 : (seg.pad & 2) ? 2 : 1;
+        const uint32_t mask = shape == 0 ? kShapeFull : shape == 1 ? kShapeFlat : kShapeQuarter;
+
+        double acc[8][4][2];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+        const int nst = (int)(seg.stage_end - seg.stage_begin);
+        for (int q = 0; q < nst; ++q, ++item) {
+            const int tslot = item & (kNTS - 1);
+            if (!ready_t) mbar_wait(&tfull[tslot], (uint32_t)((item / kNTS) & 1));
+            request_samples();
+            const int nitem = item + kAhead;
+            const bool have_next = (nitem < total);
+            if (have_next && !ready_v) mbar_wait(&vfull[nitem & (kNVS - 1)], (uint32_t)((nitem / kNVS) & 1));
+            ready_t = (item + 1 < total) ? mbar_test(&tfull[(item + 1) & (kNTS - 1)], (uint32_t)(((item + 1) / kNTS) & 1)) : true;
+            ready_v = (nitem + 1 < total) ? mbar_test(&vfull[(nitem + 1) & (kNVS - 1)], (uint32_t)(((nitem + 1) / kNVS) & 1)) : true;
+
+            const double* tI = tring + tslot * Cfg::kStageDoubles;
+            const double* tJ = tI + KS * LDT;
+            const double* pa = tI + t * LDT + row0 + g;
+            const double* pb = tJ + t * LDT + col0 + g;
+            // past the last item the ops run once more on stale data into a stage nobody reads (harmless)
+            const unsigned char* v = reinterpret_cast<const unsigned char*>(vring + (nitem & (kNVS - 1)) * vdoubles);
+            unsigned char* tn = reinterpret_cast<unsigned char*>(tring + (nitem & (kNTS - 1)) * Cfg::kStageDoubles);
+            switch (shape) {
+                case 0: stage_body_mb<kShapeFull>(acc, pa, pb, v, tn, wtab, ctab, bcnt); break;
+                case 1: stage_body_mb<kShapeFlat>(acc, pa, pb, v, tn, wtab, ctab, bcnt); break;
+                default: stage_body_mb<kShapeQuarter>(acc, pa, pb, v, tn, wtab, ctab, bcnt); break;
+            }
+            if (have_next) {
+                advance_build();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tfull[nitem & (kNTS - 1)]);
+            }
+        }
+
+        double* out = args.partials + (size_t)seg.slot * BT * BT;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int row = row0 + 8 * i + g;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = col0 + 8 * j + 2 * t;
+                if ((mask >> (i * 4 + j)) & 1)
+                    *reinterpret_cast<double2*>(out + (size_t)row * BT + c) = make_double2(acc[i][j][0], acc[i][j][1]);
+            }
+        }
+    }
+}
+
 // Adds the partial tiles of each block pair in slot order and scatters into [G | R | yy].
 __global__ void __launch_bounds__(256) gram_reduce_kernel(const double* __restrict__ partials,
                                                           const int2* __restrict__ pairs,
@@ -632,6 +922,18 @@ int gram_launch_bt128(ddb_ctx* ctx, const GramArgs& args, int nctas) {
     GramKernel kern = pick_gram_kernel<128>(ctx->max_degree);
     DDB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<nctas, GramCfg<128>::kThreads, smem, ctx->stream>>>(args);
+    DDB_CUDA_TRY(cudaGetLastError());
+    return DDB_OK;
+}
+// The tensor-pipe builder variant (args.optab / args.opcnt set by gram_moment.cu); false if it does not fit.
+bool gram_mb_fits(int n, int n_t) {
+    // rows of the X tile are separate bulk copies: 16-byte multiples
+    return n % 2 == 0 && gram_mb_smem_bytes(n, n_t) <= 227 * 1024 && gram_mb_vbytes(n, n_t) <= 65528;
+}
+int gram_launch_mb128(ddb_ctx* ctx, const GramArgs& args, int nctas) {
+    const size_t smem = gram_mb_smem_bytes(args.n, args.n_t);
+    DDB_CUDA_TRY(cudaFuncSetAttribute(gram_mb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gram_mb_kernel<<<nctas, GramCfg<128>::kThreads, smem, ctx->stream>>>(args);
     DDB_CUDA_TRY(cudaGetLastError());
     return DDB_OK;
 }

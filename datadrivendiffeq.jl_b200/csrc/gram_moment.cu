@@ -38,6 +38,8 @@
 namespace ddb {
 
 int gram_launch_bt128(ddb_ctx* ctx, const GramArgs& args, int nctas);
+int gram_launch_mb128(ddb_ctx* ctx, const GramArgs& args, int nctas);
+bool gram_mb_fits(int n, int n_t);
 int gram_ensure_factors(ddb_ctx* ctx, int kaug_pad);
 
 namespace {
@@ -84,6 +86,8 @@ struct MomentState {
     std::vector<std::pair<int, int>> pairs;  // (row block, nrb + column block), whole pairs first
     int nfull = 0, nhalf = 0;                // pairs [nfull, nfull + nhalf) only need rows 0..63, the rest rows 0..31
     DevBuf factors, src;
+    bool mb = false;      // tensor-pipe builder tables present (degree <= 2, every pair within the kernel's slots)
+    DevBuf optab, opcnt;  // [npairs][kMbPairWords] uint32, [npairs][8] uint8
     // sample-count-dependent part: a few wave plans are kept (the chunked upload of ddb_upload_gram alternates
     // between the chunk length and the length of the last chunk on every call)
     struct DevPlan {
@@ -111,7 +115,227 @@ struct MomentMap {
     std::vector<uint8_t> rows_used;          // 128, or 64 / 32: only that many leading rows of the first operand block are needed
     std::vector<int32_t> src;                // per packed entry: (pair << 14) | (row-in-tile * 128 + column-in-tile)
     std::vector<uint16_t> tab;               // (nrb + ncb) * 128 virtual terms x kMaxFactors factor codes
+    // tensor-pipe builder (gram_mb_kernel): empty when the library does not qualify
+    std::vector<uint32_t> optab;             // npairs x kMbPairWords
+    std::vector<uint8_t> opcnt;              // npairs x 8: bits 0..2 = k-step kk runs a third op, bits 4..7 = copy slots
+    std::vector<int> block_ops;              // ops per virtual block (diagnostics)
 };
+
+// ---------------------------------------------------------------------------------------------
+// Tensor-pipe builder: cover of a block's terms by (2 second factors) x (8 first factors) rectangles
+// ---------------------------------------------------------------------------------------------
+// Factor ids: 0 = the constant (the slot's ones column), 1..n = states, n+1..n+n_t = targets, -1 = nothing (0.0).
+struct MbOp {
+    int u[2];
+    int v[8];
+    int dst[2][8];  // tile column of u[r] * v[j], -1 = not needed
+};
+
+// Greedy cover of the term graph (vertices = factors, edges = terms {f, g}, loops = squares) by K(2,8) bicliques:
+// the vertex with the most uncovered terms, the partner and the eight neighbours that cover most.
+static void cover_block(const std::vector<std::array<int, 3>>& terms /* column, f, g */, std::vector<MbOp>* ops) {
+    ops->clear();
+    std::vector<std::array<int, 3>> left = terms;
+    auto other = [](const std::array<int, 3>& e, int u) { return e[1] == u ? e[2] : e[1]; };
+    while (!left.empty()) {
+        std::vector<int> verts;
+        for (const auto& e : left) {
+            verts.push_back(e[1]);
+            verts.push_back(e[2]);
+        }
+        std::sort(verts.begin(), verts.end());
+        verts.erase(std::unique(verts.begin(), verts.end()), verts.end());
+        auto neighbours = [&](int u) {
+            std::vector<int> nb;
+            for (const auto& e : left)
+                if (e[1] == u || e[2] == u) nb.push_back(other(e, u));
+            std::sort(nb.begin(), nb.end());
+            return nb;
+        };
+        int u1 = verts[0];
+        size_t deg1 = 0;
+        for (int u : verts) {
+            const size_t d = neighbours(u).size();
+            if (d >= deg1) deg1 = d, u1 = u;
+        }
+        const std::vector<int> n1 = neighbours(u1);
+        int best_u2 = -1, best_cov = -1;
+        std::vector<int> best_vs;
+        auto has = [](const std::vector<int>& sorted, int x) { return std::binary_search(sorted.begin(), sorted.end(), x); };
+        for (size_t c = 0; c <= verts.size(); ++c) {
+            const int u2 = c < verts.size() ? verts[c] : -1;
+            if (u2 == u1) continue;
+            const std::vector<int> n2 = u2 >= 0 ? neighbours(u2) : std::vector<int>();
+            std::vector<int> cand = n1;
+            cand.insert(cand.end(), n2.begin(), n2.end());
+            std::sort(cand.begin(), cand.end());
+            cand.erase(std::unique(cand.begin(), cand.end()), cand.end());
+            std::stable_sort(cand.begin(), cand.end(), [&](int x, int y) {
+                return (has(n1, x) + has(n2, x)) > (has(n1, y) + has(n2, y));
+            });
+            if (cand.size() > 8) cand.resize(8);
+            // terms covered (an edge {u1, u2} reachable both ways counts once)
+            int cov = 0;
+            for (const auto& e : left) {
+                bool hit = false;
+                for (int v : cand)
+                    if ((e[1] == u1 && e[2] == v) || (e[2] == u1 && e[1] == v) || (u2 >= 0 && ((e[1] == u2 && e[2] == v) || (e[2] == u2 && e[1] == v))))
+                        hit = true;
+                cov += hit;
+            }
+            if (cov > best_cov) best_cov = cov, best_u2 = u2, best_vs = cand;
+        }
+        MbOp op;
+        op.u[0] = u1;
+        op.u[1] = best_u2;
+        for (int j = 0; j < 8; ++j) {
+            op.v[j] = j < (int)best_vs.size() ? best_vs[j] : -1;
+            op.dst[0][j] = op.dst[1][j] = -1;
+        }
+        for (int r = 0; r < 2; ++r)
+            for (int j = 0; j < 8; ++j) {
+                if (op.u[r] < 0 || op.v[j] < 0) continue;
+                for (size_t i = 0; i < left.size(); ++i) {
+                    const auto& e = left[i];
+                    if ((e[1] == op.u[r] && e[2] == op.v[j]) || (e[2] == op.u[r] && e[1] == op.v[j])) {
+                        op.dst[r][j] = e[0];
+                        left.erase(left.begin() + i);
+                        break;
+                    }
+                }
+            }
+        ops->push_back(op);
+    }
+}
+
+// Per-pair warp tables of gram_mb_kernel (layout: mma_common.cuh).  false: a virtual term has three factors, or some
+// pair needs more ops / copy slots per warp than the kernel provides.
+static bool build_mb_tables(MomentMap* M, int n, int n_t) {
+    constexpr int kPitch = kBT + 4, kStage = kKS * kPitch;
+    const int nblocks = M->nrb + M->ncb;
+    const int row_terms = M->nrows + n_t, col_terms = n_t + M->ncols;
+    auto factor_id = [&](uint16_t code) {
+        if (code == kNoFactor) return 0;
+        return (code & kFactorIsY) ? n + 1 + (int)(code & 0x7FFF) : (int)code + 1;
+    };
+    std::vector<std::vector<MbOp>> ops(nblocks);
+    std::vector<std::vector<std::pair<int, int>>> singles(nblocks);  // (column, factor): values that are copied
+    M->block_ops.assign(nblocks, 0);
+    for (int b = 0; b < nblocks; ++b) {
+        std::vector<std::array<int, 3>> terms;
+        for (int c = 0; c < kBT; ++c) {
+            const int idx = b * kBT + c;
+            const bool valid = b < M->nrb ? idx < row_terms : idx - M->nrb * kBT < col_terms;
+            if (!valid) continue;
+            const uint16_t* f = &M->tab[(size_t)idx * kMaxFactors];
+            if (f[2] != kNoFactor) return false;  // three factors: not a single product
+            const int f0 = factor_id(f[0]), f1 = factor_id(f[1]);
+            if (f0 == 0 || f1 == 0) singles[b].push_back({c, f0 == 0 ? f1 : f0});
+            else terms.push_back({c, f0, f1});
+        }
+        cover_block(terms, &ops[b]);
+        // a block of targets has more single values than the copy slots of a warp take: the rest is multiplied by
+        // the constant, eight at a time
+        const size_t keep = (size_t)(8 * kMbCopySlots * 32 / kKS) / 2;
+        while (singles[b].size() > keep) {
+            MbOp op;
+            op.u[0] = 0;
+            op.u[1] = -1;
+            for (int j = 0; j < 8; ++j) {
+                op.v[j] = op.dst[0][j] = op.dst[1][j] = -1;
+                if (singles[b].size() > keep) {
+                    op.v[j] = singles[b].back().second;
+                    op.dst[0][j] = singles[b].back().first;
+                    singles[b].pop_back();
+                }
+            }
+            ops[b].push_back(op);
+        }
+        M->block_ops[b] = (int)ops[b].size();
+    }
+    auto src_off = [&](int f, int s) -> uint32_t {  // byte offset inside a raw-sample slot
+        if (f < 0) return kVZero * 8;
+        if (f == 0) return (uint32_t)(kVOnes + s) * 8;
+        if (f <= n) return (uint32_t)(kVX + s * mb_pitch(n) + (f - 1)) * 8;
+        return (uint32_t)(kVX + kKS * mb_pitch(n) + s * n_t + (f - n - 1)) * 8;
+    };
+    const int npairs = (int)M->pairs.size();
+    M->optab.assign((size_t)npairs * kMbPairWords, 0u);
+    M->opcnt.assign((size_t)npairs * 8, 0);
+    for (int p = 0; p < npairs; ++p) {
+        struct Inst {
+            int tile, sg;
+            const MbOp* op;
+        };
+        std::vector<Inst> inst;
+        std::vector<uint32_t> copies;  // source | destination << 16
+        const int blk[2] = {M->pairs[p].first, M->pairs[p].second};
+        const int used = M->rows_used[p];
+        for (int sg = 0; sg < kKS / 4; ++sg)
+            for (int tile = 0; tile < 2; ++tile)
+                for (const MbOp& op : ops[blk[tile]]) {
+                    bool live = false;
+                    for (int r = 0; r < 2; ++r)
+                        for (int j = 0; j < 8; ++j) live |= op.dst[r][j] >= 0 && (tile == 1 || op.dst[r][j] < used);
+                    if (live) inst.push_back({tile, sg, &op});
+                }
+        for (int tile = 0; tile < 2; ++tile)
+            for (int s = 0; s < kKS; ++s)
+                for (const auto& cf : singles[blk[tile]])
+                    if (tile == 1 || cf.first < used)
+                        copies.push_back(src_off(cf.second, s) | ((uint32_t)(tile * kStage + s * kPitch + cf.first) * 8) << 16);
+        const int ncslots = ((int)copies.size() + 31) / 32;
+        if ((int)inst.size() > 8 * kMbOpSlots || ncslots > 8 * kMbCopySlots) {
+            if (getenv("DDB_GRAM_DEBUG"))
+                fprintf(stderr, "[ddb] tensor-pipe builder: pair %d (blocks %d, %d) needs %d ops and %d copy slots per stage\n", p,
+                        blk[0], blk[1], (int)inst.size(), ncslots);
+            return false;
+        }
+        uint32_t* tab = &M->optab[(size_t)p * kMbPairWords];
+        for (int w = 0; w < 8; ++w) {
+            uint32_t* wt = tab + (size_t)w * kMbWarpWords;
+            for (int j = 0; j < kMbOpSlots; ++j) {
+                const int idx = j * 8 + w;           // instances are dealt to the warps round-robin
+                const int kk = j % 4, slot = j / 4;  // a warp's first four are slot 0 of k-steps 0..3, the next four slot 1
+                const Inst* in = idx < (int)inst.size() ? &inst[idx] : nullptr;
+                if (in && slot == 2) M->opcnt[(size_t)p * 8 + w] |= (uint8_t)(1u << kk);
+                for (int lane = 0; lane < 32; ++lane) {
+                    // lane (g, t) holds A[g][t] = v_g(sample t), B[t][g] with column g = (sample g / 2, second factor
+                    // g % 2) one-hot in t, and D[g][2t], D[g][2t + 1] = v_g u_0, v_g u_1 at sample t: the stores of a
+                    // run of consecutive columns hit the banks like the fragment loads do (pitch = 4 mod 16)
+                    const int g = lane >> 2, t = lane & 3;
+                    const int sl = g >> 1, r = g & 1;
+                    uint32_t offA = kVZero * 8, offB = kVZero * 8, d0, d1;
+                    const int tile = in ? in->tile : 0, s0 = in ? in->sg * 4 : 0;
+                    d0 = d1 = (uint32_t)(tile * kStage + (s0 + t) * kPitch + kBT + (g & 3)) * 8;  // pad columns: never read
+                    if (in) {
+                        const MbOp& op = *in->op;
+                        offA = src_off(op.v[g], s0 + t);
+                        if (t == sl) offB = src_off(op.u[r], s0 + sl);
+                        const int c0 = op.dst[0][g], c1 = op.dst[1][g];
+                        if (c0 >= 0 && (tile == 1 || c0 < used)) d0 = (uint32_t)(tile * kStage + (s0 + t) * kPitch + c0) * 8;
+                        if (c1 >= 0 && (tile == 1 || c1 < used)) d1 = (uint32_t)(tile * kStage + (s0 + t) * kPitch + c1) * 8;
+                    }
+                    uint32_t* e = wt + ((kk * 3 + slot) * 32 + lane) * 2;
+                    e[0] = offA | (offB << 16);
+                    e[1] = d0 | (d1 << 16);
+                }
+            }
+            int mine = 0;
+            for (int j = 0; j < kMbCopySlots; ++j) {
+                const int idx = j * 8 + w;
+                if (idx < ncslots) mine = j + 1;
+                for (int lane = 0; lane < 32; ++lane) {
+                    const size_t ci = (size_t)idx * 32 + lane;
+                    const uint32_t dump = (uint32_t)(kBT + (lane & 3)) * 8;
+                    wt[kMbOpSlots * 64 + j * 32 + lane] = (idx < ncslots && ci < copies.size()) ? copies[ci] : (kVZero * 8) | (dump << 16);
+                }
+            }
+            M->opcnt[(size_t)p * 8 + w] |= (uint8_t)(mine << 4);
+        }
+    }
+    return true;
+}
 
 static void analyse_library(const uint8_t* exps, int n, int k, int n_t, int D, MomentMap* M) {
     M->worth = false;
@@ -314,6 +538,11 @@ static void analyse_library(const uint8_t* exps, int n, int k, int n_t, int D, M
     }
     for (int i = 0; i < ncols; ++i) put(nrb * kBT + cpos[i], cols[i]);
     M->worth = true;
+    // products on the tensor pipe: virtual terms of at most two factors
+    if (D > 2 || !build_mb_tables(M, n, n_t)) {
+        M->optab.clear();
+        M->opcnt.clear();
+    }
 }
 
 static int install_library(ddb_ctx* ctx, MomentState* M) {
@@ -337,6 +566,19 @@ static int install_library(ddb_ctx* ctx, MomentState* M) {
                                  ctx->stream));
     DDB_CUDA_TRY(cudaMemcpyAsync(M->src.p, map.src.data(), map.src.size() * sizeof(int32_t), cudaMemcpyHostToDevice,
                                  ctx->stream));
+    M->mb = !map.optab.empty() && gram_mb_fits(ctx->n, ctx->n_t);
+    if (M->mb) {
+        DDB_TRY(M->optab.reserve(map.optab.size() * sizeof(uint32_t)));
+        DDB_TRY(M->opcnt.reserve(map.opcnt.size()));
+        DDB_CUDA_TRY(cudaMemcpyAsync(M->optab.p, map.optab.data(), map.optab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                                     ctx->stream));
+        DDB_CUDA_TRY(cudaMemcpyAsync(M->opcnt.p, map.opcnt.data(), map.opcnt.size(), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (getenv("DDB_GRAM_DEBUG")) {
+        fprintf(stderr, "[ddb] moment schedule: tensor-pipe builder %s; ops per block:", M->mb ? "on" : "off");
+        for (int c : map.block_ops) fprintf(stderr, " %d", c);
+        fprintf(stderr, "\n");
+    }
     DDB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // `map` is a stack-lifetime host buffer
     M->eligible = true;
     for (auto& pl : M->plans) pl.m = -1;
@@ -370,6 +612,27 @@ int64_t moment_plan_describe(const uint8_t* exps, int n, int k, int n_t, int32_t
             pairs[3 * i + 2] = map.rows_used[i];
         }
     return (int64_t)map.src.size();
+}
+
+// Host-only view of the tensor-pipe builder tables for ddb_moment_builder_describe (api.cu).
+int64_t moment_builder_describe(const uint8_t* exps, int n, int k, int n_t, uint32_t* optab, int64_t optab_cap,
+                                uint8_t* opcnt, int64_t opcnt_cap, int32_t* block_ops, int64_t block_cap) {
+    int D = 0;
+    for (int j = 0; j < k; ++j) {
+        int d = 0;
+        for (int i = 0; i < n; ++i) d += exps[(size_t)i + (size_t)n * j];
+        D = std::max(D, d);
+    }
+    MomentMap map;
+    analyse_library(exps, n, k, n_t, D, &map);
+    if (!map.worth || map.optab.empty() || !gram_mb_fits(n, n_t)) return 0;
+    if (optab)
+        for (int64_t i = 0; i < std::min<int64_t>(optab_cap, (int64_t)map.optab.size()); ++i) optab[i] = map.optab[i];
+    if (opcnt)
+        for (int64_t i = 0; i < std::min<int64_t>(opcnt_cap, (int64_t)map.opcnt.size()); ++i) opcnt[i] = map.opcnt[i];
+    if (block_ops)
+        for (int64_t i = 0; i < std::min<int64_t>(block_cap, (int64_t)map.block_ops.size()); ++i) block_ops[i] = map.block_ops[i];
+    return (int64_t)map.pairs.size();
 }
 
 // Lock-step waves.  A wave gives every one of its block pairs a number of equal sample ranges, one CTA per
@@ -460,7 +723,7 @@ static void plan_waves(const std::vector<std::pair<int, int>>& pairs, int nfull,
             sg.bi = pairs[p].first;
             sg.bj = pairs[p].second;
             sg.slot = W->nslots++;
-            sg.pad = cls_of(p);  // 1: 64 x 128 patch, 2: 32 x 128 patch
+            sg.pad = cls_of(p) | (p << 8);  // bits 0..1: 1 = 64 x 128 patch, 2 = 32 x 128 patch; bits 8..: pair index
             sg.stage_begin = ns * r / nr;
             sg.stage_end = ns * (r + 1) / nr;
             W->per_cta[(*cta)++].push_back(sg);
@@ -563,7 +826,17 @@ int gram_moment_run(ddb_ctx* ctx, double* dPacked, bool* handled) {
     a.cta_seg_begin = reinterpret_cast<const int32_t*>(base + P->off_cta);
     a.partials = M->partials.as<double>();
     DDB_CUDA_TRY(cudaEventRecord(ctx->ev[0], ctx->stream));
-    DDB_TRY(gram_launch_bt128(ctx, a, ctx->sm_count));
+    // opt-in (DDB_GRAM_MB=1): bit-identical, the tensor pipe runs 3.4 points busier without the FP64 multiplies, but at
+    // the 11 ops per warp and stage the greedy cover needs at C3 the extra DMMAs cost more than the multiplies did
+    // (150.9 against 139.7 ms per 2e6 samples, profiles/gram_mb_experiment_r2.txt)
+    const char* mb_env = getenv("DDB_GRAM_MB");
+    if (M->mb && mb_env && atoi(mb_env) == 1) {
+        a.optab = M->optab.as<uint32_t>();
+        a.opcnt = M->opcnt.as<uint8_t>();
+        DDB_TRY(gram_launch_mb128(ctx, a, ctx->sm_count));
+    } else {
+        DDB_TRY(gram_launch_bt128(ctx, a, ctx->sm_count));
+    }
     const int64_t count = ddb_gram_count(ctx);
     moment_gather_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(
         M->partials.as<double>(), reinterpret_cast<const int32_t*>(base + P->off_psb), M->src.as<int32_t>(), count,
@@ -608,7 +881,7 @@ int64_t moment_wave_describe(const uint8_t* exps, int n, int k, int n_t, int64_t
             if (segments && w < cap) {
                 int64_t* o = segments + 7 * w;
                 o[0] = c, o[1] = g.bi, o[2] = g.bj, o[3] = g.slot, o[4] = g.stage_begin, o[5] = g.stage_end;
-                o[6] = g.pad == 0 ? 128 : g.pad == 1 ? 64 : 32;
+                o[6] = (g.pad & 3) == 0 ? 128 : (g.pad & 3) == 1 ? 64 : 32;
             }
             ++w;
         }
@@ -619,6 +892,8 @@ void moment_free(ddb_ctx* ctx) {
     if (ctx->moment) {
         ctx->moment->factors.release();
         ctx->moment->src.release();
+        ctx->moment->optab.release();
+        ctx->moment->opcnt.release();
         for (auto& pl : ctx->moment->plans) pl.buf.release();
         ctx->moment->partials.release();
         delete ctx->moment;

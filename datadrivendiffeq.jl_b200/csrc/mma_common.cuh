@@ -5,6 +5,8 @@
 namespace ddb {
 
 constexpr int kKS = 16;  // samples per stage
+// raw-sample slot of the Gram kernels (doubles): [ones(16) | 0.0 | pad | X tile | Y tile], see gram.cu
+constexpr int kVOnes = 0, kVZero = 16, kVX = 18;
 
 struct GramArgs {
     const double* X;
@@ -16,8 +18,27 @@ struct GramArgs {
     const GramSegment* segs;
     const int32_t* cta_seg_begin;
     double* partials;
+    // tensor-pipe builder (gram_mb_kernel, moment schedule of degree-2 libraries): per block pair and warp a table of
+    // per-lane operand / destination offsets (kMbPairWords words) and a flag byte per warp
+    const uint32_t* optab = nullptr;
+    const uint8_t* opcnt = nullptr;
 };
 
+// Tensor-pipe builder, per warp and 16-sample stage: product ops (two in every k-step + a third in k-steps 0..2) as
+// 32 lanes x {A offset | B offset << 16, destination 0 | destination 1 << 16}, then copy slots (library values that are
+// a single raw value: one double per lane) as 32 lanes x {source | destination << 16}; all byte offsets.
+constexpr int kMbOpSlots = 11;
+constexpr int kMbCopySlots = 5;
+constexpr int kMbWarpWords = kMbOpSlots * 64 + kMbCopySlots * 32;
+constexpr int kMbPairWords = 8 * kMbWarpWords;
+// Row pitch (doubles) of the X tile inside gram_mb_kernel's raw-sample slot: = 4 (mod 16), so that an op's operand
+// load (8 consecutive states x 4 consecutive samples) touches every shared-memory bank once.  The Y tile keeps pitch
+// n_t (targets are only ever copied).  Slot: [ones(16) | 0.0 | pad | X 16 x pitch | Y 16 x n_t].
+__host__ __device__ inline int mb_pitch(int n) { return n + ((4 - n % 16) + 16) % 16; }
+__host__ __device__ inline size_t gram_mb_vbytes(int n, int n_t) {
+    size_t v = (size_t)(kVX + kKS * (mb_pitch(n) + n_t)) * sizeof(double);
+    return (v + 127) & ~size_t(127);
+}
 
 // ---------------------------------------------------------------------------------------------
 // PTX helpers

@@ -444,6 +444,20 @@ int64_t ddb_gram_plan_describe(int kaug, int64_t m, int nctas, int64_t* segments
 int64_t ddb_moment_plan_describe(int n, int k, const uint8_t* exps, int n_t, int32_t* src, int64_t src_cap, uint16_t* factors,
                                  int64_t factors_cap, int32_t* pairs, int64_t pairs_cap, int64_t* info);
 
+/* Host-only: the tensor-pipe builder of the moment schedule (csrc/gram.cu: gram_mb_kernel).  For libraries whose
+ * virtual terms have at most two factors (total degree <= 2) the library values are not multiplied out on the FP64
+ * pipe: one DMMA with a one-hot first operand forms 4 samples x 2 second factors x 8 first factors = 64 products,
+ * each a single correctly rounded multiplication (same bits as the multiply it replaces).  Which products an op
+ * forms is decided on the host: the terms of every virtual block are covered by (2 x 8)-factor rectangles.  Writes,
+ * per block pair of ddb_moment_plan_describe and in the same order, optab: 8 warps x 12 op slots x 32 lanes x 2
+ * words {A-operand offset | B-operand offset << 16, destination 0 | destination 1 << 16} (byte offsets inside a
+ * raw-sample slot [ones(16) | 0.0 | pad | X tile 16 x n | Y tile 16 x n_t] resp. inside a stage of two 16 x 132
+ * tiles; slot index = 3 * k-step + {0, 1, 2}), opcnt: 8 bytes per pair, bit kk set = the warp runs the third slot of
+ * k-step kk, block_ops: ops per virtual block.  Returns the number of block pairs, 0 if the library keeps the
+ * FP64-pipe builder (degree > 2, a pair that needs more than 12 ops per warp, or samples too wide).  Needs no GPU. */
+int64_t ddb_moment_builder_describe(int n, int k, const uint8_t* exps, int n_t, uint32_t* optab, int64_t optab_cap,
+                                    uint8_t* opcnt, int64_t opcnt_cap, int32_t* block_ops, int64_t block_cap);
+
 /* Host-only: the work plan of the moment schedule for m local samples on nctas persistent CTAs (0 = 148): the block
  * pairs of ddb_moment_plan_describe run in lock-step waves, every pair over a number of equal sample ranges.
  * Writes up to cap segments as 7 int64 each {cta, first_block, second_block, slot, stage_begin, stage_end, rows}

@@ -163,3 +163,30 @@ def test_library_change_with_same_size_rebuilds_the_moment_map(ctx):
     ex2[:, 5], ex2[:, 200] = ex[:, 200].copy(), ex[:, 5].copy()  # swap two terms
     ex2[0, 17] += 1  # and raise one to degree <= 3
     _check(ctx, ex2, X, Y, tol=2e-13)
+
+
+@pytest.mark.parametrize("n,n_t,m", [(64, 64, 4096), (64, 64, 50_003), (40, 5, 7001), (30, 30, 2500)])
+def test_tensor_pipe_builder_is_bit_identical_to_the_fp64_pipe_builder(ctx, n, n_t, m):
+    """Degree-2 libraries form their library values on the tensor pipe (gram_mb_kernel: one DMMA with a one-hot
+    operand = 64 single products; targets / degree-1 terms are copied).  Every value is the same correctly rounded
+    product the FP64-pipe builder (DDB_GRAM_MB=0: gram_kernel's multiplies) forms, and the contraction order is
+    unchanged, so the packed blocks must agree bit for bit."""
+    rng = np.random.default_rng(n + m)
+    X = rng.standard_normal((n, m)) * 3.0
+    Y = rng.standard_normal((n_t, m))
+    ctx.set_library(oracle.polynomial_exponents(n, 2))
+    ctx.upload(X, Y)
+    old = os.environ.get("DDB_GRAM_MB")
+    try:
+        os.environ["DDB_GRAM_MB"] = "1"
+        (G1, R1, y1), _ = _gram(ctx, True)
+        os.environ["DDB_GRAM_MB"] = "0"
+        (G0, R0, y0), _ = _gram(ctx, True)
+    finally:
+        if old is None:
+            del os.environ["DDB_GRAM_MB"]
+        else:
+            os.environ["DDB_GRAM_MB"] = old
+    np.testing.assert_array_equal(G1, G0)
+    np.testing.assert_array_equal(R1, R0)
+    np.testing.assert_array_equal(y1, y0)

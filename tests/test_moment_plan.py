@@ -215,3 +215,107 @@ def test_moment_plan_random_libraries():
         np.testing.assert_array_equal(hv[row] + hv[col], want)
         assert ((off // 128) < pairs[pair, 2]).all()
     assert used >= 15
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Tensor-pipe builder tables (ddb_moment_builder_describe): the ops of every block pair, replayed on the host
+# ---------------------------------------------------------------------------------------------------------------
+_OPS, _COPIES = 11, 5                      # kMbOpSlots, kMbCopySlots (csrc/mma_common.cuh)
+_WARP_WORDS = _OPS * 64 + _COPIES * 32
+
+
+def _builder_tables(ex, n_t, npairs, nblocks):
+    lib = _lib.load()
+    n, k = ex.shape
+    exf = np.asfortranarray(ex.astype(np.uint8))
+    optab = np.zeros((npairs, 8, _WARP_WORDS), dtype=np.uint32)
+    opcnt = np.zeros((npairs, 8), dtype=np.uint8)
+    block_ops = np.zeros(nblocks, dtype=np.int32)
+    got = lib.ddb_moment_builder_describe(n, k, _lib.ptr(exf), n_t, _lib.ptr(optab), optab.size, _lib.ptr(opcnt), opcnt.size,
+                                          _lib.ptr(block_ops), block_ops.size)
+    return got, optab, opcnt, block_ops
+
+
+def _replay_builder(optab, opcnt, raw):
+    """What gram_mb_kernel's ops leave in a Theta stage (2 tiles x 16 samples x 132 columns): every product op is one
+    DMMA m8n8k4 with A[g][t] and B[t][g] read through the per-lane offsets, lane (g, t) stores D[g][2t], D[g][2t+1];
+    every copy slot moves one double per lane."""
+    stage = np.zeros(2 * 16 * 132)
+    lanes = np.arange(32)
+    g, t = lanes >> 2, lanes & 3
+    nops = 0
+    for w in range(8):
+        ops = optab[w, :_OPS * 64].reshape(_OPS, 32, 2)
+        cps = optab[w, _OPS * 64:].reshape(_COPIES, 32)
+        for q in range(_OPS):
+            kk, slot = q // 3, q % 3
+            if slot == 2 and not (opcnt[w] >> kk) & 1:
+                continue
+            e = ops[q]
+            offa, offb = e[:, 0] & 0xFFFF, e[:, 0] >> 16
+            d0, d1 = e[:, 1] & 0xFFFF, e[:, 1] >> 16
+            assert not (offa % 8).any() and not (offb % 8).any() and not (d0 % 8).any() and not (d1 % 8).any()
+            A = np.zeros((8, 4))
+            B = np.zeros((4, 8))
+            A[g, t] = raw[offa // 8]
+            B[t, g] = raw[offb // 8]
+            assert ((A != 0).astype(int) @ (B != 0).astype(int) <= 1).all()  # one-hot operand: every output is a single product
+            D = A @ B
+            stage[d0 // 8] = D[g, 2 * t]
+            stage[d1 // 8] = D[g, 2 * t + 1]
+            nops += 1
+        for q in range(int(opcnt[w]) >> 4):
+            c = cps[q]
+            stage[(c >> 16) // 8] = raw[(c & 0xFFFF) // 8]
+    return stage.reshape(2, 16, 132), nops
+
+
+@pytest.mark.parametrize("n,deg,n_t", [(64, 2, 64), (40, 2, 5), (30, 2, 30)])
+def test_builder_tables_form_every_virtual_term(n, deg, n_t):
+    """Degree-2 libraries: replaying the op tables of every block pair on random samples fills both Theta tiles with
+    the virtual terms' values (bitwise: each is a single product), unused rows of half / quarter pairs excepted."""
+    ex = oracle.polynomial_exponents(n, deg)
+    plan = _moment_plan(ex, n_t)
+    assert plan is not None
+    nblocks = plan["nrb"] + plan["ncb"]
+    got, optab, opcnt, block_ops = _builder_tables(ex, n_t, plan["npairs"], nblocks)
+    assert got == plan["npairs"]
+    assert block_ops.min() >= 0 and block_ops.max() <= 16
+    rng = np.random.default_rng(5)
+    X = rng.standard_normal((16, n))
+    Y = rng.standard_normal((16, n_t))
+    px = n + (4 - n % 16) % 16  # mb_pitch: the X tile's rows are padded to a pitch = 4 (mod 16)
+    Xp = np.full((16, px), np.nan)
+    Xp[:, :n] = X
+    raw = np.concatenate([np.ones(16), [0.0, 0.0], Xp.ravel(), Y.ravel()])
+    # value of every virtual term on the 16 samples (product of its factor codes; missing factors = 1)
+    tab = plan["tab"]
+    vals = np.ones((tab.shape[0], 16))
+    nfac = np.zeros(tab.shape[0], dtype=int)
+    for r in range(tab.shape[0]):
+        for f in tab[r]:
+            if f == 0xFFFF:
+                continue
+            vals[r] = vals[r] * (Y[:, f & 0x7FFF] if (f & 0x8000) else X[:, f])
+            nfac[r] += 1
+    row_terms, col_terms = plan["nrows"] + n_t, n_t + plan["ncols"]
+    for p in range(plan["npairs"]):
+        b0, b1, used = plan["pairs"][p]
+        stage, nops = _replay_builder(optab[p], opcnt[p], raw)
+        assert 64 <= nops <= 8 * _OPS
+        for tile, blk in enumerate((b0, b1)):
+            for c in range(128):
+                idx = blk * 128 + c
+                valid = idx < row_terms if blk < plan["nrb"] else idx - plan["nrb"] * 128 < col_terms
+                if tile == 0 and c >= used:
+                    continue
+                want = vals[idx] if valid else np.zeros(16)
+                assert np.array_equal(stage[tile, :, c], want), (p, tile, c)
+
+
+def test_builder_tables_absent_for_cubic_libraries():
+    ex = oracle.polynomial_exponents(20, 3)
+    plan = _moment_plan(ex, 20)
+    assert plan is not None
+    got, _, _, _ = _builder_tables(ex, 20, plan["npairs"], plan["nrb"] + plan["ncb"])
+    assert got == 0

@@ -424,6 +424,99 @@ __global__ void __launch_bounds__(256) k_phase(double* out, int stages, int n) {
     if (s == 12345.678) out[0] = s;
 }
 
+// (G) Theta build on the tensor pipe itself: a product tile u_r(s) * v_j(s) (4 samples x 2 second factors x 8 first
+// factors = 64 products) is ONE DMMA with a one-hot A operand (A[(s,r)][k] = u_r(s) if k == s else 0, B[k][j] = v_j(s_k),
+// C = 0: every output is a single correctly rounded product).  NOPS ops per k-step replace the 4 DMULs of k_build.
+// TAB 0: per-lane offsets in registers, 1: one LDS.128 per op from a per-warp table in shared memory.
+template <int NOPS, int TAB>
+__global__ void __launch_bounds__(256) k_buildmma(double* out, int stages, int n) {
+    constexpr int LDT = 132, KS = 16, NA = 8, NB = 4;
+    extern __shared__ double sm[];
+    double* tile = sm;                       // 2 * KS * LDT
+    double* scratch = tile + 2 * KS * LDT;   // 2 * KS * LDT
+    double* raw = scratch + 2 * KS * LDT;    // KS * 2n
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(raw + KS * 2 * n);
+    int4* tab = reinterpret_cast<int4*>(bar + 2);  // [8 warps][4 kk][NOPS][32 lanes]
+    for (int e = threadIdx.x; e < 4 * KS * LDT + KS * 2 * n; e += blockDim.x) sm[e] = 1.0 + 1e-6 * e;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(&bar[0])), "r"(8));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(&bar[1])), "r"(8));
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const int wm = warp & 1, wn = (warp >> 1) & 3;
+    const int srow = g >> 1, r = g & 1;  // row i = g of the A operand: sample srow, second factor r
+    const bool hot = (t == srow);
+    int offA[NOPS], offB[NOPS], dstc[NOPS];
+#pragma unroll
+    for (int o = 0; o < NOPS; ++o) {
+        const int q = (warp * 5 + o * 11 + r * 3) & 63;           // second factor of row r
+        const int p = (warp * 7 + o * 16 + g) & 63;               // first factor j = g (B operand column)
+        offA[o] = q + srow * n;
+        offB[o] = p + t * n;
+        dstc[o] = (warp >> 2) * KS * LDT + ((warp & 3) * 32 + ((o & 1) * 16 + r * 8 + 2 * t)) + srow * LDT;
+        if (TAB)
+            for (int kk = 0; kk < 4; ++kk)
+                tab[((warp * 4 + kk) * NOPS + o) * 32 + lane] =
+                    make_int4((offA[o] + kk * 4 * n) * 8, (offB[o] + kk * 4 * n) * 8, (dstc[o] + kk * 4 * LDT) * 8, 0);
+    }
+    __syncthreads();
+    const unsigned raw32 = s32(raw), scr32 = s32(scratch);
+    double acc[NA][NB][2];
+    for (int i = 0; i < NA; ++i) for (int j = 0; j < NB; ++j) acc[i][j][0] = acc[i][j][1] = 0;
+    for (int st = 0; st < stages; ++st) {
+        const double* pa = tile + t * LDT + wm * (8 * NA) + g;
+        const double* pb = tile + KS * LDT + t * LDT + wn * (8 * NB) + g;
+#pragma unroll
+        for (int kk = 0; kk < KS / 4; ++kk) {
+            double ua[NOPS], vb[NOPS];
+            unsigned dsta[NOPS];
+#pragma unroll
+            for (int o = 0; o < NOPS; ++o) {
+                if (TAB) {
+                    const int4 e = tab[((warp * 4 + kk) * NOPS + o) * 32 + lane];
+                    ua[o] = 0.0;
+                    if (hot) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(ua[o]) : "r"(raw32 + e.x));
+                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(vb[o]) : "r"(raw32 + e.y));
+                    dsta[o] = scr32 + e.z;
+                } else {
+                    ua[o] = 0.0;
+                    if (hot) ua[o] = raw[offA[o] + kk * 4 * n];
+                    vb[o] = raw[offB[o] + kk * 4 * n];
+                    dsta[o] = scr32 + (dstc[o] + kk * 4 * LDT) * 8;
+                }
+            }
+            double a[NA], b[NB];
+#pragma unroll
+            for (int i = 0; i < NA; ++i) a[i] = pa[kk * 4 * LDT + 8 * i];
+#pragma unroll
+            for (int j = 0; j < NB; ++j) b[j] = pb[kk * 4 * LDT + 8 * j];
+#pragma unroll
+            for (int o = 0; o < NOPS; ++o) {
+                double d0 = 0.0, d1 = 0.0;
+                dmma884(d0, d1, ua[o], vb[o]);
+                asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(dsta[o]), "d"(d0), "d"(d1) : "memory");
+            }
+#pragma unroll
+            for (int i = 0; i < NA; ++i)
+#pragma unroll
+                for (int j = 0; j < NB; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+        {
+            unsigned long long* b = &bar[st & 1];
+            const unsigned parity = (st >> 1) & 1;
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(b)) : "memory");
+            unsigned done;
+            do {
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(s32(b)), "r"(parity) : "memory");
+            } while (!done);
+        }
+    }
+    double s = 0;
+    for (int i = 0; i < NA; ++i) for (int j = 0; j < NB; ++j) s += acc[i][j][0] + acc[i][j][1];
+    if (s == 12345.678) out[0] = s;
+}
+
 template <class F> float time_ms(F f) {
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     f(); f(); CK(cudaDeviceSynchronize());
@@ -478,6 +571,13 @@ int main() {
         { auto k = k_phase<16>; CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
           float ms = time_ms([&] { k<<<sms, 256, smem>>>(out, stages, n); }); printf("\"phase_chunk16\": %.2f, ", 512.0 * 32 * 4 * stages * sms * 8 / ms * 1e-9); }
         RUNB(8, 47, "build_vol_after") RUNB(8, 63, "build_vol_sprinkle")
+        {
+            const size_t smem2 = smem + 8 * 4 * 3 * 32 * 16 + 64;
+#define RUNM(NOPS, TAB, name) { auto k = k_buildmma<NOPS, TAB>; CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); \
+        float ms = time_ms([&] { k<<<sms, 256, smem2>>>(out, stages, n); }); printf("\"" name "\": %.2f, ", 512.0 * 32 * 4 * stages * sms * 8 / ms * 1e-9); }
+            RUNM(2, 0, "buildmma_2ops_reg") RUNM(2, 1, "buildmma_2ops_tab") RUNM(3, 0, "buildmma_3ops_reg") RUNM(3, 1, "buildmma_3ops_tab")
+            RUNM(1, 0, "buildmma_1op_reg")
+        }
     }
     printf("\"sms\": %d}\n", sms);
     return 0;
