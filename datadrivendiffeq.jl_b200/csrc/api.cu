@@ -486,11 +486,29 @@ int ddb_upload_gram(ddb_ctx* ctx, const double* X, const double* Y, int n_t, int
     const int n = ctx->n;
     const int n_in = ctx->n_raw > 0 ? ctx->n_raw : n;  // states per sample in the caller's buffer
     const size_t row_bytes = (size_t)(n_in + n_t) * sizeof(double);
-    // at most 16 chunks of at least ~64 MB (the first chunk's copy is the only exposed one), chunk boundaries
-    // on multiples of 64 samples
-    int nchunks = (int)std::min<int64_t>(16, std::max<int64_t>(1, (int64_t)((double)m * row_bytes / (64.0 * 1024 * 1024))));
-    int64_t chunk = ((m + nchunks - 1) / nchunks + 63) / 64 * 64;
-    nchunks = (int)((m + chunk - 1) / chunk);
+    // At most 16 chunks of at least ~64 MB, chunk boundaries on multiples of 64 samples.  Only the first chunk's copy
+    // is exposed, so large uploads start with two short chunks (1/128 and 1/32 of the samples: the copy of the second
+    // takes about as long as the Gram kernels of the first, the host link being ~4 x faster than the Gram stage
+    // consumes samples) and split the rest evenly; the plans of the four chunk lengths are cached.
+    std::vector<int64_t> starts;  // chunk c = samples [starts[c], starts[c + 1])
+    {
+        const double total_mb = (double)m * row_bytes / (1024.0 * 1024.0);
+        auto round64 = [](int64_t v) { return std::max<int64_t>(64, (v + 63) / 64 * 64); };
+        starts.push_back(0);
+        int64_t rest_begin = 0;
+        int even = (int)std::min<int64_t>(16, std::max<int64_t>(1, (int64_t)(total_mb / 64.0)));
+        const char* front_env = getenv("DDB_UPLOAD_FRONT_MB");  // uploads from this size on start with the short chunks
+        if (total_mb >= (front_env ? atof(front_env) : 2048.0) && m >= 128 * 64) {
+            starts.push_back(round64(m / 128));
+            starts.push_back(starts.back() + round64(m / 32));
+            rest_begin = starts.back();
+            even = 14;
+        }
+        const int64_t each = round64((m - rest_begin + even - 1) / even);
+        for (int64_t s0 = rest_begin + each; s0 < m; s0 += each) starts.push_back(s0);
+        starts.push_back(m);
+    }
+    const int nchunks = (int)starts.size() - 1;
     if (nchunks <= 1) {
         DDB_TRY(ddb_upload(ctx, X, Y, n_t, m));
         return gram_run(ctx, dPacked);
@@ -550,7 +568,7 @@ int ddb_upload_gram(ddb_ctx* ctx, const double* X, const double* Y, int n_t, int
         int piece = 0;
         if (notify) pool.reset(new StagePool(stage_threads(ctx)));  // pageable caller: this is the helper thread
         for (int c = 0; c < nchunks; ++c) {
-            const int64_t s0 = c * chunk, mc = std::min(chunk, m - s0);
+            const int64_t s0 = starts[c], mc = starts[c + 1] - s0;
             cudaError_t e;
             if (pool) {
                 e = staged_h2d(ctx, *pool, dIn + s0 * n_in, X + s0 * n_in, (size_t)mc * n_in * sizeof(double), &piece);
@@ -589,7 +607,7 @@ int ddb_upload_gram(ddb_ctx* ctx, const double* X, const double* Y, int n_t, int
     int launches = 0, status = DDB_OK;
     cudaError_t cerr = pinned ? copy_err : cudaSuccess;
     for (int c = 0; c < nchunks && status == DDB_OK && cerr == cudaSuccess; ++c) {
-        const int64_t s0 = c * chunk, mc = std::min(chunk, m - s0);
+        const int64_t s0 = starts[c], mc = starts[c + 1] - s0;
         if (!pinned) {
             std::unique_lock<std::mutex> lk(mu);
             cv.wait(lk, [&] { return landed > c; });

@@ -88,8 +88,8 @@ struct MomentState {
     DevBuf factors, src;
     bool mb = false;      // tensor-pipe builder tables present (degree <= 2, every pair within the kernel's slots)
     DevBuf optab, opcnt;  // [npairs][kMbPairWords] uint32, [npairs][8] uint8
-    // sample-count-dependent part: a few wave plans are kept (the chunked upload of ddb_upload_gram alternates
-    // between the chunk length and the length of the last chunk on every call)
+    // sample-count-dependent part: a few wave plans are kept (the chunked upload of ddb_upload_gram walks through
+    // four chunk lengths on every call: two short first chunks, the regular one, the last one)
     struct DevPlan {
         int64_t m = -1;
         int nctas = -1;
@@ -98,7 +98,7 @@ struct MomentState {
         size_t off_cta = 0, off_psb = 0;
         uint64_t stamp = 0;
     };
-    static constexpr int kPlans = 3;
+    static constexpr int kPlans = 6;
     DevPlan plans[kPlans];
     uint64_t clock = 0;
     DevBuf partials;

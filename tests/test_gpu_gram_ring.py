@@ -116,6 +116,21 @@ def test_upload_gram_chunked_overlap_matches_plain(ctx, n, deg, m):
     Xd, Yd = ctx.download_data()
     np.testing.assert_array_equal(Xd, X)
     np.testing.assert_array_equal(Yd, Y)
+    # large uploads (2 GB and more; here forced) start with two short chunks so that less of the first copy is exposed
+    import os
+    os.environ["DDB_UPLOAD_FRONT_MB"] = "1"
+    try:
+        for px, py in ((Xp.data_ptr(), Yp.data_ptr()), (Xh.ctypes.data, Yh.ctypes.data)):
+            ctx.upload_gram_raw(px, py, n, m)
+            G4, R4, y4 = ctx.gram_download()
+            assert np.max(np.abs(G4 - G0) / sc) < 1e-13
+            assert np.max(np.abs(R4 - R0)) < 1e-13 * np.sqrt(np.max(np.diag(G0)) * np.max(y0))
+            np.testing.assert_allclose(y4, y0, rtol=1e-13)
+            Xd, Yd = ctx.download_data()
+            np.testing.assert_array_equal(Xd, X)
+            np.testing.assert_array_equal(Yd, Y)
+    finally:
+        del os.environ["DDB_UPLOAD_FRONT_MB"]
 
 
 @pytest.mark.parametrize("n,n_t", [(65, 65), (66, 66), (70, 3), (64, 1), (72, 72)])
