@@ -122,6 +122,10 @@ struct ddb_ctx {
     int64_t plan_m = -1;
     int plan_kaug = -1;
     bool have_gram = false;
+    // prefix-product builder of the single-pair Gram kernel (gram.cu: gram_tree_kernel)
+    ddb::DevBuf d_tree;                  // 4 programs x tree_nsteps words
+    uint64_t tree_lib_version = ~0ull;
+    int tree_nt = -1, tree_nsteps = 0;   // 0 = the library is not closed under "drop the last factor"
 
     // term normalisation (ddb_gram_scale_terms): the blocks in d_packed are those of Theta_j / scale_j
     ddb::DevBuf d_term_scale;            // divisor per term

@@ -34,6 +34,7 @@
 #include <algorithm>
 #include <cstring>
 #include <cstdlib>
+#include <map>
 
 namespace ddb {
 
@@ -684,6 +685,277 @@ __global__ void __launch_bounds__(GramCfg<128>::kThreads, 1) gram_mb_kernel(cons
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Prefix-product builder (libraries of at most 64 augmented rows that are closed under "drop the last factor")
+// ---------------------------------------------------------------------------------------------
+// gram_kernel<64, NF> multiplies every library value out from its NF staged factors: NF - 1 FP64 multiplies per
+// value, each costing the tensor pipe most of a DMMA slot (C2: 4 multiplies and 5 loads per value against 2.25
+// DMMAs).  A term is its parent (the term without its last factor) times that factor: ONE multiply per value, the
+// same association as the left-to-right product, i.e. the same bits.  The dependency is kept inside a thread: thread
+// (sample s, quarter q) walks program q -- a contiguous piece of the depth-first order of the term tree, preceded by
+// the ancestors of its first node -- through row s of the tile; a parent is always a value the same thread stored
+// earlier (program order, no barrier).  Ancestors shared by two quarters are stored by both with identical bits.
+// Everything else is gram_kernel<64> on the single diagonal pair.
+constexpr int kTreeQuarters = 4;
+inline size_t gram_tree_smem_bytes(int n, int n_t, int nsteps) {
+    return gram_smem_bytes<64>(n, n_t) + (size_t)64 * nsteps * sizeof(uint2);
+}
+
+// Steps of a k-step form four groups (one per pair of sub-tile rows); the host guarantees that a step's parent is
+// stored by an EARLIER group, so a group's loads are issued together, ahead of its multiplies and stores.
+template <int G>
+struct TreeGroup {
+    uint2 e[G > 0 ? G : 1];
+    double par[G > 0 ? G : 1], fac[G > 0 ? G : 1];
+    __device__ __forceinline__ void load(const uint2* __restrict__ prog, int first, const unsigned char* __restrict__ v,
+                                         const unsigned char* tn) {
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            e[j] = prog[(first + j) * 64];
+            const unsigned char* pbase = (e[j].y >> 31) ? v : tn;  // no parent: the slot's ones column
+            par[j] = *reinterpret_cast<const double*>(pbase + (e[j].x >> 16));
+            fac[j] = *reinterpret_cast<const double*>(v + (e[j].y & 0xFFFFu));
+        }
+    }
+    __device__ __forceinline__ void store(unsigned char* tn) const {
+#pragma unroll
+        for (int j = 0; j < G; ++j) *reinterpret_cast<double*>(tn + (e[j].x & 0xFFFFu)) = par[j] * fac[j];
+    }
+};
+
+__host__ __device__ constexpr int tree_group_size(int spk, int g) { return spk / 4 + (g < spk % 4 ? 1 : 0); }
+__host__ __device__ constexpr int tree_group_first(int spk, int g) {
+    int f = 0;
+    for (int h = 0; h < g; ++h) f += tree_group_size(spk, h);
+    return f;
+}
+
+template <int NSTEP, uint32_t MASK>
+__device__ __forceinline__ void stage_body_tree(double (&acc)[8][4][2], const double* __restrict__ pa,
+                                                const double* __restrict__ pb, const unsigned char* __restrict__ v,
+                                                unsigned char* tn, const uint2* __restrict__ prog) {
+    constexpr int LDT = GramCfg<64>::kPitch;
+    constexpr int SPK = NSTEP / 4;  // program steps per k-step, in four groups (one per pair of sub-tile rows)
+#pragma unroll
+    for (int kk = 0; kk < kKS / 4; ++kk) {
+        double a[8], b[4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if ((MASK >> (4 * i)) & 0xFu) a[i] = pa[kk * 4 * LDT + 8 * i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if ((MASK >> j) & 0x11111111u) b[j] = pb[kk * 4 * LDT + 8 * j];
+        auto rows = [&](int i0) {
+#pragma unroll
+            for (int i = i0; i < i0 + 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if ((MASK >> (i * 4 + j)) & 1u) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        };
+        {
+            TreeGroup<tree_group_size(SPK, 0)> grp;
+            grp.load(prog, kk * SPK + tree_group_first(SPK, 0), v, tn);
+            rows(0);
+            grp.store(tn);
+        }
+        {
+            TreeGroup<tree_group_size(SPK, 1)> grp;
+            grp.load(prog, kk * SPK + tree_group_first(SPK, 1), v, tn);
+            rows(2);
+            grp.store(tn);
+        }
+        {
+            TreeGroup<tree_group_size(SPK, 2)> grp;
+            grp.load(prog, kk * SPK + tree_group_first(SPK, 2), v, tn);
+            rows(4);
+            grp.store(tn);
+        }
+        {
+            TreeGroup<tree_group_size(SPK, 3)> grp;
+            grp.load(prog, kk * SPK + tree_group_first(SPK, 3), v, tn);
+            rows(6);
+            grp.store(tn);
+        }
+    }
+}
+
+template <int NSTEP>
+__global__ void __launch_bounds__(64, 4) gram_tree_kernel(const GramArgs args) {
+    using Cfg = GramCfg<64>;
+    constexpr int BT = 64;
+    constexpr int LDT = Cfg::kPitch;
+    constexpr int KS = kKS;
+    static_assert(NSTEP % 4 == 0 && NSTEP / 4 <= 8, "steps are spread over the 8 sub-tile rows of a k-step");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+
+    const int n = args.n, n_t = args.n_t;
+    const uint32_t xbytes = (uint32_t)(KS * n * sizeof(double));
+    const uint32_t ybytes = (uint32_t)(KS * n_t * sizeof(double));
+    const int vdoubles = (int)(gram_vbytes(n, n_t) / sizeof(double));
+
+    uint64_t* vfull = reinterpret_cast<uint64_t*>(smem_raw);
+    uint64_t* tfull = vfull + kNVS;
+    double* vring = reinterpret_cast<double*>(smem_raw + 128);
+    double* tring = vring + kNVS * vdoubles;
+    uint2* progs = reinterpret_cast<uint2*>(tring + kNTS * Cfg::kStageDoubles);  // [NSTEP][64 threads]
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+
+    if (tid == 0) {
+        for (int i = 0; i < kNVS; ++i) mbar_init(&vfull[i], 1);
+        for (int i = 0; i < kNTS; ++i) mbar_init(&tfull[i], Cfg::kWarps);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int e = tid; e < kNVS * kVX; e += Cfg::kThreads) {
+        const int w = e % kVX;
+        vring[(e / kVX) * vdoubles + w] = (w < kVZero) ? 1.0 : 0.0;
+    }
+    // rows past the end of the library: no step writes them
+    for (int e = tid; e < kNTS * Cfg::kStageDoubles; e += Cfg::kThreads) tring[e] = 0.0;
+    {   // this thread's program, resolved for its sample: byte offsets inside a Theta stage / a raw-sample slot
+        const int s = tid & 15, q = tid >> 4;
+        for (int j = 0; j < NSTEP; ++j) {
+            const uint32_t w = args.tree[q * NSTEP + j];
+            const uint32_t dst = w & 0xFFu, par = (w >> 8) & 0xFFu, code = w >> 16;
+            uint32_t foff;
+            if (code == kNoFactor) foff = (uint32_t)(kVOnes + s) * 8;
+            else if (code & kFactorIsY) foff = (uint32_t)(kVX + KS * n + s * n_t + (int)(code & 0x7FFF)) * 8;
+            else foff = (uint32_t)(kVX + s * n + (int)code) * 8;
+            const bool root = (par == 0xFFu);
+            const uint32_t poff = root ? (uint32_t)(kVOnes + s) * 8 : (uint32_t)(s * LDT + (int)par) * 8;
+            progs[j * 64 + tid] = make_uint2((uint32_t)(s * LDT + (int)dst) * 8 | (poff << 16), foff | (root ? 0x80000000u : 0u));
+        }
+    }
+    __syncthreads();
+    const uint2* prog = progs + tid;
+
+    const int64_t nstages_total = (args.m + KS - 1) / KS;
+    const int seg_begin = args.cta_seg_begin[blockIdx.x];
+    const int seg_end = args.cta_seg_begin[blockIdx.x + 1];
+    int total = 0;
+    for (int sg = seg_begin; sg < seg_end; ++sg) total += (int)(args.segs[sg].stage_end - args.segs[sg].stage_begin);
+    if (total == 0) return;
+
+    int tma_seg = seg_begin;
+    int tma_stage = (int)args.segs[seg_begin].stage_begin, tma_seg_end = (int)args.segs[seg_begin].stage_end;
+    int tma_item = 0;
+    uint32_t ragged_slots = 0;
+    const int ragged_stage = (args.m % KS) ? (int)(nstages_total - 1) : -1;
+    auto request_samples = [&]() {
+        if (tma_item >= total) return;
+        const int slot = tma_item & (kNVS - 1);
+        const bool mine = (tma_item % Cfg::kWarps) == warp;
+        if (tma_stage != ragged_stage) {
+            if ((ragged_slots >> slot) & 1) {
+                ragged_slots &= ~(1u << slot);
+                if (mine) {
+                    if (lane < KS) vring[slot * vdoubles + kVOnes + lane] = 1.0;
+                    __syncwarp();
+                }
+            }
+            if (mine && lane == 0) {
+                double* dst = vring + slot * vdoubles + kVX;
+                const int64_t s0 = (int64_t)tma_stage * KS;
+                mbar_expect_tx(&vfull[slot], xbytes + ybytes);
+                bulk_g2s(dst, args.X + s0 * n, xbytes, &vfull[slot]);
+                bulk_g2s(dst + KS * n, args.Y + s0 * n_t, ybytes, &vfull[slot]);
+            }
+        } else {
+            ragged_slots |= 1u << slot;
+            if (mine) {
+                double* dst = vring + slot * vdoubles;
+                const int64_t s0 = (int64_t)tma_stage * KS;
+                const int valid = (int)(args.m - s0);
+                for (int e = lane; e < KS * n; e += 32) dst[kVX + e] = (e < valid * n) ? args.X[s0 * n + e] : 0.0;
+                for (int e = lane; e < KS * n_t; e += 32)
+                    dst[kVX + KS * n + e] = (e < valid * n_t) ? args.Y[s0 * n_t + e] : 0.0;
+                if (lane < KS) dst[kVOnes + lane] = (lane < valid) ? 1.0 : 0.0;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&vfull[slot]);
+            }
+        }
+        ++tma_item;
+        if (++tma_stage == tma_seg_end && ++tma_seg < seg_end) {
+            tma_stage = (int)args.segs[tma_seg].stage_begin;
+            tma_seg_end = (int)args.segs[tma_seg].stage_end;
+        }
+    };
+
+    // ---- prologue: the first raw tiles, Theta(0..kAhead-1) completely ---------------------------------------------
+#pragma unroll 1
+    for (int i = 0; i < kNVS; ++i) request_samples();
+#pragma unroll 1
+    for (int it = 0; it < kAhead && it < total; ++it) {
+        mbar_wait(&vfull[it], 0);
+        const unsigned char* v = reinterpret_cast<const unsigned char*>(vring + it * vdoubles);
+        unsigned char* tn = reinterpret_cast<unsigned char*>(tring + it * Cfg::kStageDoubles);
+#pragma unroll 1
+        for (int j = 0; j < NSTEP; ++j) {
+            const uint2 e = prog[j * 64];
+            const unsigned char* pbase = (e.y >> 31) ? v : tn;
+            const double par = *reinterpret_cast<const volatile double*>(pbase + (e.x >> 16));
+            const double fac = *reinterpret_cast<const double*>(v + (e.y & 0xFFFFu));
+            *reinterpret_cast<volatile double*>(tn + (e.x & 0xFFFFu)) = par * fac;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tfull[it]);
+    }
+
+    // ---- MMA cursor: warp w owns columns 32 w .. 32 w + 31 of the diagonal pair --------------------------------------
+    const int col0 = warp * 32;
+    const int shape = (warp == 0) ? 1 : 2;  // diagonal offset 0 / -4
+    const uint32_t mask = shape == 1 ? kShapeDiag0 : kShapeDiagM4;
+    int item = 0;
+    bool ready_t = false, ready_v = false;
+    for (int sg = seg_begin; sg < seg_end; ++sg) {
+        const GramSegment seg = args.segs[sg];
+        double acc[8][4][2];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+        const int nst = (int)(seg.stage_end - seg.stage_begin);
+        for (int q = 0; q < nst; ++q, ++item) {
+            const int tslot = item & (kNTS - 1);
+            if (!ready_t) mbar_wait(&tfull[tslot], (uint32_t)((item / kNTS) & 1));
+            request_samples();
+            const int nitem = item + kAhead;
+            const bool have_next = (nitem < total);
+            if (have_next && !ready_v) mbar_wait(&vfull[nitem & (kNVS - 1)], (uint32_t)((nitem / kNVS) & 1));
+            ready_t = (item + 1 < total) ? mbar_test(&tfull[(item + 1) & (kNTS - 1)], (uint32_t)(((item + 1) / kNTS) & 1)) : true;
+            ready_v = (nitem + 1 < total) ? mbar_test(&vfull[(nitem + 1) & (kNVS - 1)], (uint32_t)(((nitem + 1) / kNVS) & 1)) : true;
+
+            const double* tI = tring + tslot * Cfg::kStageDoubles;
+            const double* pa = tI + t * LDT + g;
+            const double* pb = tI + t * LDT + col0 + g;
+            const unsigned char* v = reinterpret_cast<const unsigned char*>(vring + (nitem & (kNVS - 1)) * vdoubles);
+            unsigned char* tn = reinterpret_cast<unsigned char*>(tring + (nitem & (kNTS - 1)) * Cfg::kStageDoubles);
+            if (shape == 1) stage_body_tree<NSTEP, kShapeDiag0>(acc, pa, pb, v, tn, prog);
+            else stage_body_tree<NSTEP, kShapeDiagM4>(acc, pa, pb, v, tn, prog);
+            if (have_next) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tfull[nitem & (kNTS - 1)]);
+            }
+        }
+
+        double* out = args.partials + (size_t)seg.slot * BT * BT;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int row = 8 * i + g;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = col0 + 8 * j + 2 * t;
+                if ((mask >> (i * 4 + j)) & 1)
+                    *reinterpret_cast<double2*>(out + (size_t)row * BT + c) = make_double2(acc[i][j][0], acc[i][j][1]);
+            }
+        }
+    }
+}
+
 // Adds the partial tiles of each block pair in slot order and scatters into [G | R | yy].
 __global__ void __launch_bounds__(256) gram_reduce_kernel(const double* __restrict__ partials,
                                                           const int2* __restrict__ pairs,
@@ -946,6 +1218,120 @@ int gram_ensure_factors(ddb_ctx* ctx, int rows);
 int gram_ring_run(ddb_ctx* ctx, double* dPacked, bool* handled);
 int gram_moment_run(ddb_ctx* ctx, double* dPacked, bool* handled);
 
+// Programs of gram_tree_kernel for the installed library and n_t targets: the term tree (parent = the term without
+// its last factor; the targets hang under the constant) in depth-first order, cut into four contiguous quarters,
+// each preceded by the ancestors of its first node.  Returns the steps per program (a multiple of 4), 0 if the
+// library has no constant, is not closed under "drop the last factor", or repeats a term.  words: 4 x steps of
+// dst column | parent column << 8 (255: none) | factor code << 16.
+int gram_tree_program(const uint8_t* exps, int n, int k, int n_t, std::vector<uint32_t>* words) {
+    const int kaug = k + n_t;
+    if (kaug > 64 || k < 1) return 0;
+    std::vector<std::vector<uint16_t>> fac(k);
+    std::map<std::vector<uint16_t>, int> col_of;
+    for (int j = 0; j < k; ++j) {
+        for (int i = 0; i < n; ++i)
+            for (int e = 0; e < exps[(size_t)i + (size_t)n * j]; ++e) fac[j].push_back((uint16_t)i);
+        if (!col_of.emplace(fac[j], j).second) return 0;
+    }
+    const auto rootit = col_of.find(std::vector<uint16_t>());
+    if (rootit == col_of.end()) return 0;
+    const int root = rootit->second;
+    std::vector<int> parent(kaug, -1);
+    std::vector<uint16_t> code(kaug, kNoFactor);
+    std::vector<std::vector<int>> children(kaug);
+    for (int j = 0; j < k; ++j) {
+        if (j == root) continue;
+        std::vector<uint16_t> pf(fac[j].begin(), fac[j].end() - 1);
+        const auto it = col_of.find(pf);
+        if (it == col_of.end()) return 0;
+        parent[j] = it->second;
+        code[j] = fac[j].back();
+        children[it->second].push_back(j);
+    }
+    for (int i = 0; i < n_t; ++i) {
+        parent[k + i] = root;
+        code[k + i] = (uint16_t)(kFactorIsY | i);
+        children[root].push_back(k + i);
+    }
+    std::vector<int> order, depth(kaug, 0), stack = {root};
+    while (!stack.empty()) {
+        const int u = stack.back();
+        stack.pop_back();
+        order.push_back(u);
+        for (auto it = children[u].rbegin(); it != children[u].rend(); ++it) {
+            depth[*it] = depth[u] + 1;
+            stack.push_back(*it);
+        }
+    }
+    if ((int)order.size() != kaug) return 0;
+    const int seglen = (kaug + kTreeQuarters - 1) / kTreeQuarters;
+    std::vector<std::vector<int>> nodes(kTreeQuarters);  // ancestor-closed node sets, by depth then depth-first index
+    std::vector<int> dfs_pos(kaug, 0);
+    for (int i = 0; i < kaug; ++i) dfs_pos[order[i]] = i;
+    for (int q = 0; q < kTreeQuarters; ++q) {
+        const int b = q * seglen, e = std::min(kaug, b + seglen);
+        if (b >= e) continue;
+        for (int u = parent[order[b]]; u >= 0; u = parent[u]) nodes[q].push_back(u);
+        for (int i = b; i < e; ++i) nodes[q].push_back(order[i]);
+        std::sort(nodes[q].begin(), nodes[q].end(), [&](int x, int y) {
+            return depth[x] != depth[y] ? depth[x] < depth[y] : dfs_pos[x] < dfs_pos[y];
+        });
+    }
+    // the kernel runs the steps of a k-step in four groups (tree_group_size); a node goes into the first group after
+    // its parent's.  Smallest step count (a multiple of 4, at most 24) that takes all four programs.
+    const uint32_t idle = 64u | (255u << 8) | ((uint32_t)kNoFactor << 16);  // multiplies ones into a pad column
+    for (int steps = 4; steps <= 24; steps += 4) {
+        const int spk = steps / 4;
+        words->assign((size_t)kTreeQuarters * steps, idle);
+        bool fits = true;
+        for (int q = 0; q < kTreeQuarters && fits; ++q) {
+            std::vector<int> group_of(kaug, -1);
+            int grp = 0, used = 0;  // group index (four per k-step), slots used in it
+            for (int u : nodes[q]) {
+                const int need = parent[u] < 0 ? 0 : group_of[parent[u]] + 1;
+                while (grp < 16 && (grp < need || used >= tree_group_size(spk, grp % 4))) ++grp, used = 0;
+                if (grp >= 16) {
+                    fits = false;
+                    break;
+                }
+                group_of[u] = grp;
+                (*words)[(size_t)q * steps + (grp / 4) * spk + tree_group_first(spk, grp % 4) + used++] =
+                    (uint32_t)u | ((uint32_t)(parent[u] < 0 ? 255 : parent[u]) << 8) | ((uint32_t)code[u] << 16);
+            }
+        }
+        if (fits) return steps;
+    }
+    return 0;
+}
+
+static GramKernel pick_tree_kernel(int steps) {
+    switch (steps) {
+        case 4: return gram_tree_kernel<4>;
+        case 8: return gram_tree_kernel<8>;
+        case 12: return gram_tree_kernel<12>;
+        case 16: return gram_tree_kernel<16>;
+        case 20: return gram_tree_kernel<20>;
+        default: return gram_tree_kernel<24>;
+    }
+}
+
+// (Re)builds the programs when the library or the number of targets changed; ctx->tree_nsteps = 0: not applicable.
+static int ensure_tree_program(ddb_ctx* ctx) {
+    if (ctx->tree_lib_version == ctx->lib_version && ctx->tree_nt == ctx->n_t) return DDB_OK;
+    std::vector<uint32_t> words;
+    const int steps = gram_tree_program(ctx->exps.data(), ctx->n, ctx->k, ctx->n_t, &words);
+    if (steps > 0) {
+        DDB_TRY(ctx->d_tree.reserve(words.size() * sizeof(uint32_t)));
+        DDB_CUDA_TRY(cudaMemcpyAsync(ctx->d_tree.p, words.data(), words.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        DDB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    if (getenv("DDB_GRAM_DEBUG")) fprintf(stderr, "[ddb] prefix-product builder: %d steps per program (0 = not applicable)\n", steps);
+    ctx->tree_nsteps = steps;
+    ctx->tree_lib_version = ctx->lib_version;
+    ctx->tree_nt = ctx->n_t;
+    return DDB_OK;
+}
+
 int gram_run(ddb_ctx* ctx, double* dPacked) {
     if (ctx->k <= 0) {
         set_error("ddb_gram: no library installed (call ddb_set_library_monomial first)");
@@ -995,10 +1381,25 @@ int gram_run(ddb_ctx* ctx, double* dPacked) {
         DDB_TRY(gram_ring_run(ctx, dPacked, &handled));
         if (handled) return DDB_OK;
     }
+    // single diagonal pair of a library that is closed under "drop the last factor": one multiply per library value
+    // (gram_tree_kernel).  Opt-in (DDB_GRAM_TREE=1): bit-identical and 24 instead of 64 multiplies per thread and stage
+    // at C2, but the parent -> child chains through shared memory cost more than the multiplies saved (2.57 ms in
+    // depth-first order, 2.67 ms in groups of independent steps, against 2.45 ms; profiles/gram_tree_experiment_r2.txt)
+    GramKernel tree_kern = nullptr;
+    if (bt == 64 && ctx->max_degree >= 2) {
+        const char* tenv = getenv("DDB_GRAM_TREE");
+        if (tenv && atoi(tenv) == 1) {
+            DDB_TRY(ensure_tree_program(ctx));
+            if (ctx->tree_nsteps > 0 && gram_tree_smem_bytes(n, n_t, ctx->tree_nsteps) <= 56 * 1024)
+                tree_kern = pick_tree_kernel(ctx->tree_nsteps);
+        }
+    }
+    const size_t smem_launch = tree_kern ? gram_tree_smem_bytes(n, n_t, ctx->tree_nsteps) : smem;
     // persistent grid: CTAs per SM from the occupancy calculator (1 for BT=128, up to 3 for BT=64)
     int occ = 1;
     {
-        GramKernel kern = pick_gram_kernel(bt, ctx->max_degree);
+        GramKernel kern = tree_kern ? tree_kern : pick_gram_kernel(bt, ctx->max_degree);
+        const size_t smem = smem_launch;
         DDB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
             &occ, kern, bt == 64 ? GramCfg<64>::kThreads : GramCfg<128>::kThreads, smem);
@@ -1059,8 +1460,14 @@ int gram_run(ddb_ctx* ctx, double* dPacked) {
     args.partials = ctx->d_partials.as<double>();
 
     DDB_CUDA_TRY(cudaEventRecord(ctx->ev[0], ctx->stream));
-    const int st = launch_gram(ctx, bt, args, smem);
-    DDB_TRY(st);
+    if (tree_kern) {
+        args.tree = ctx->d_tree.as<uint32_t>();
+        tree_kern<<<ctx->plan.nctas, GramCfg<64>::kThreads, smem_launch, ctx->stream>>>(args);
+        DDB_CUDA_TRY(cudaGetLastError());
+    } else {
+        const int st = launch_gram(ctx, bt, args, smem);
+        DDB_TRY(st);
+    }
     dim3 rgrid(pl.npairs, (bt * bt + 255) / 256);
     gram_reduce_kernel<<<rgrid, 256, 0, ctx->stream>>>(ctx->d_partials.as<double>(),
                                                        reinterpret_cast<const int2*>(base + off_pairs),

@@ -22,6 +22,9 @@ struct GramArgs {
     // per-lane operand / destination offsets (kMbPairWords words) and a flag byte per warp
     const uint32_t* optab = nullptr;
     const uint8_t* opcnt = nullptr;
+    // prefix-product builder (gram_tree_kernel, single 64 x 64 diagonal pair): 4 programs x nsteps x {dst column,
+    // parent column (255 = none: the slot's ones column), factor code}
+    const uint32_t* tree = nullptr;
 };
 
 // Tensor-pipe builder, per warp and 16-sample stage: product ops (two in every k-step + a third in k-steps 0..2) as
