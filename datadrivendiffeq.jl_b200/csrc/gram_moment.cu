@@ -75,6 +75,10 @@ __global__ void __launch_bounds__(256) moment_gather_kernel(const double* __rest
     packed[e] = s;
 }
 
+// cost of a pair that needs its first `rows` rows, relative to a whole pair; class bits of GramSegment::pad
+inline double pair_cost(int rows) { return rows == 128 ? 1.0 : rows == 64 ? kHalfCost : kQuarterCost; }
+inline int pair_class(int rows) { return rows == 128 ? 0 : rows == 64 ? 1 : 2; }
+
 }  // namespace
 
 struct MomentState {
@@ -84,7 +88,7 @@ struct MomentState {
     bool eligible = false;
     int nrb = 0, ncb = 0, nvirt = 0, npairs = 0;
     std::vector<std::pair<int, int>> pairs;  // (row block, nrb + column block), whole pairs first
-    int nfull = 0, nhalf = 0;                // pairs [nfull, nfull + nhalf) only need rows 0..63, the rest rows 0..31
+    std::vector<uint8_t> rows_used;          // per pair: 128, or 64 / 32 leading rows of the first block (sorted descending)
     DevBuf factors, src;
     bool mb = false;      // tensor-pipe builder tables present (degree <= 2, every pair within the kernel's slots)
     DevBuf optab, opcnt;  // [npairs][kMbPairWords] uint32, [npairs][8] uint8
@@ -473,6 +477,8 @@ static void analyse_library(const uint8_t* exps, int n, int k, int n_t, int D, M
                 int& cell = pair_of[(size_t)I * ncb + J];
                 if (cell <= 0) continue;
                 const int re = extent(cell & 15), ce = extent((cell >> 4) & 15);
+                // (a 96-row class was built and measured in round 2: the 96 x 128 patch costs 0.92 of a whole pair for
+                // 0.75 of its flops, and the seventh patch shape alone made gram_kernel 2.8 % slower -- not kept)
                 const int rcls = re <= 32 ? 32 : re <= 64 ? 64 : 128, ccls = ce <= 32 ? 32 : ce <= 64 ? 64 : 128;
                 const int used = std::min(rcls, ccls);
                 if (used != (pass == 0 ? 128 : pass == 1 ? 64 : 32)) continue;
@@ -499,7 +505,7 @@ static void analyse_library(const uint8_t* exps, int n, int k, int n_t, int D, M
                 (int)std::count(M->rows_used.begin(), M->rows_used.end(), (uint8_t)64),
                 (int)std::count(M->rows_used.begin(), M->rows_used.end(), (uint8_t)32), plain);
     double cost = 0.0;
-    for (uint8_t h : M->rows_used) cost += h == 128 ? 1.0 : h == 64 ? kHalfCost : kQuarterCost;
+    for (uint8_t h : M->rows_used) cost += pair_cost(h);
     if (npairs >= (1 << 17) || cost > 0.9 * plain) return;
 
     // gather map of the packed [G | R | yy]
@@ -555,8 +561,7 @@ static int install_library(ddb_ctx* ctx, MomentState* M) {
     if (!map.worth) return DDB_OK;
     M->pairs = map.pairs;
     M->npairs = (int)map.pairs.size();
-    M->nfull = (int)std::count(map.rows_used.begin(), map.rows_used.end(), (uint8_t)128);
-    M->nhalf = (int)std::count(map.rows_used.begin(), map.rows_used.end(), (uint8_t)64);
+    M->rows_used = map.rows_used;
     M->nrb = map.nrb;
     M->ncb = map.ncb;
     M->nvirt = map.nvirt;
@@ -650,11 +655,11 @@ struct WavePlan {
     double time = 0.0;  // pair streams per CTA (1.0 = one whole pair over all samples)
 };
 
-static void plan_waves(const std::vector<std::pair<int, int>>& pairs, int nfull, int nhalf, int64_t ns, int nctas,
-                       WavePlan* W) {
+static void plan_waves(const std::vector<std::pair<int, int>>& pairs, const std::vector<uint8_t>& rows_used, int64_t ns,
+                       int nctas, WavePlan* W) {
     const int npairs = (int)pairs.size();
-    auto cls_of = [&](int p) { return p < nfull ? 0 : p < nfull + nhalf ? 1 : 2; };
-    auto cost_of = [&](int p) { return p < nfull ? 1.0 : p < nfull + nhalf ? kHalfCost : kQuarterCost; };
+    auto cls_of = [&](int p) { return pair_class(rows_used[p]); };
+    auto cost_of = [&](int p) { return pair_cost(rows_used[p]); };
     const int64_t max_r = std::max<int64_t>(1, ns);
     double ideal = 0.0;
     for (int p = 0; p < npairs; ++p) ideal += cost_of(p) / nctas;
@@ -685,8 +690,9 @@ static void plan_waves(const std::vector<std::pair<int, int>>& pairs, int nfull,
     };
     // homogeneous wave from `first` with nr ranges per pair: how many pairs it takes (0 = not possible)
     auto class_end = [&](int first) {
-        const int c = cls_of(first);
-        return c == 0 ? nfull : c == 1 ? nfull + nhalf : npairs;
+        int e = first;
+        while (e < npairs && rows_used[e] == rows_used[first]) ++e;
+        return e;
     };
     auto homogeneous = [&](int first, int nr) { return std::min(class_end(first) - first, nctas / nr); };
     // best[first] = least time for the pairs [first, npairs) (every wave also pays kWavePenalty);
@@ -716,37 +722,103 @@ static void plan_waves(const std::vector<std::pair<int, int>>& pairs, int nfull,
     W->psb.assign(npairs + 1, 0);
     W->nslots = 0;
     W->nwaves = 0;
-    auto emit = [&](int p, int nr, int* cta) {
-        W->psb[p] = W->nslots;
-        for (int r = 0; r < nr; ++r) {
-            GramSegment sg;
-            sg.bi = pairs[p].first;
-            sg.bj = pairs[p].second;
-            sg.slot = W->nslots++;
-            sg.pad = cls_of(p) | (p << 8);  // bits 0..1: 1 = 64 x 128 patch, 2 = 32 x 128 patch; bits 8..: pair index
-            sg.stage_begin = ns * r / nr;
-            sg.stage_end = ns * (r + 1) / nr;
-            W->per_cta[(*cta)++].push_back(sg);
-        }
+    std::vector<double> used(nctas, 0.0);  // pair streams a CTA has been given so far
+    auto push = [&](int p, int cta, int64_t b, int64_t e) {
+        GramSegment sg;
+        sg.bi = pairs[p].first;
+        sg.bj = pairs[p].second;
+        sg.slot = W->nslots++;
+        sg.pad = cls_of(p) | (p << 8);  // bits 0..1: 1 = 64 x 128 patch, 2 = 32 x 128 patch; bits 8..: pair index
+        sg.stage_begin = b;
+        sg.stage_end = e;
+        W->per_cta[cta].push_back(sg);
+        used[cta] += cost_of(p) * (double)(e - b) / (double)max_r;
     };
     int first = 0;
     while (first < npairs) {
-        int cta = 0;
         ++W->nwaves;
-        if (choice[first] == 0) {
+        if (choice[first] != 0) {
+            const int nr = choice[first], np = homogeneous(first, nr);
+            int cta = 0;
+            for (int p = first; p < first + np; ++p) {
+                W->psb[p] = W->nslots;
+                for (int r = 0; r < nr; ++r) push(p, cta++, ns * r / nr, ns * (r + 1) / nr);
+            }
+            first += np;
+            continue;
+        }
+        // Final wave.  The DP sized it as "pair p over ceil(cost_p / T) equal ranges"; it is dealt out as ONE stream
+        // (pair after pair, stage after stage) that fills every CTA up to a common finishing time, the CTAs the
+        // earlier waves left idle included: no quantisation by class, at the price of CTAs that change pair inside the
+        // wave (a flush and a pipeline fill, microseconds against a wave of tens of milliseconds).
+        if (getenv("DDB_MOMENT_STREAM") && atoi(getenv("DDB_MOMENT_STREAM")) == 0) {  // as sized: equal ranges per pair
             std::vector<int> ranges;
             double T;
             final_wave(first, &ranges, &T);
-            for (int p = first; p < npairs; ++p) emit(p, ranges[p - first], &cta);
+            int cta = 0;
+            for (int p = first; p < npairs; ++p) {
+                W->psb[p] = W->nslots;
+                for (int r = 0; r < ranges[p - first]; ++r) push(p, cta++, ns * r / ranges[p - first], ns * (r + 1) / ranges[p - first]);
+            }
             first = npairs;
-        } else {
-            const int nr = choice[first], np = homogeneous(first, nr);
-            for (int p = 0; p < np; ++p) emit(first + p, nr, &cta);
-            first += np;
+            continue;
         }
+        double work = 0.0;
+        for (int p = first; p < npairs; ++p) work += cost_of(p);
+        std::vector<double> sorted_used = used;
+        std::sort(sorted_used.begin(), sorted_used.end());
+        double level = sorted_used[0] + work, prefix = 0.0;  // water level: sum_c max(0, level - used_c) = work
+        for (int c = 0; c < nctas; ++c) {
+            prefix += sorted_used[c];
+            const double lv = (work + prefix) / (c + 1);
+            if (c + 1 == nctas || lv <= sorted_used[c + 1]) {
+                level = lv;
+                break;
+            }
+        }
+        // CTAs in the order of the homogeneous waves; a piece shorter than kMinPiece stages is not worth a segment.
+        // Pieces are whole stages, so with few stages per pair the last CTA would collect what the roundings left
+        // over: the level is raised (bisection on a dry run) until the stream ends within it.
+        const int64_t kMinPiece = std::max<int64_t>(1, std::min<int64_t>(32, ns / 64));
+        auto deal = [&](double lvl, bool dry) {  // returns the finishing time of the last CTA used
+            std::vector<double> u = used;
+            int cta = 0;
+            for (int p = first; p < npairs; ++p) {
+                if (!dry) W->psb[p] = W->nslots;
+                const double per_stage = cost_of(p) / (double)max_r;
+                int64_t st = 0;
+                while (st < ns) {
+                    while (cta < nctas - 1 && lvl - u[cta] < per_stage * (double)std::min<int64_t>(kMinPiece, ns - st)) ++cta;
+                    int64_t take = ns - st;
+                    if (cta < nctas - 1) {
+                        take = std::min<int64_t>(take, (int64_t)std::floor((lvl - u[cta]) / per_stage + 0.5));
+                        if (ns - st - take < kMinPiece && ns - st - take > 0) take = ns - st;  // no crumbs at a pair's end
+                        take = std::max<int64_t>(take, 1);
+                    }
+                    if (!dry) push(p, cta, st, st + take);
+                    u[cta] += per_stage * (double)take;
+                    st += take;
+                }
+            }
+            return u[cta];
+        };
+        double max_stage = 0.0;
+        for (int p = first; p < npairs; ++p) max_stage = std::max(max_stage, cost_of(p) / (double)max_r);
+        double lo = level, hi = level + 2.0 * max_stage * (double)kMinPiece + 1e-12;
+        while (deal(hi, true) > hi + 0.5 * max_stage) hi += max_stage * (double)kMinPiece;  // (ends: one CTA can take everything)
+        if (deal(lo, true) > lo + 0.5 * max_stage) {
+            for (int it = 0; it < 40; ++it) {
+                const double mid = 0.5 * (lo + hi);
+                if (deal(mid, true) > mid + 0.5 * max_stage) lo = mid;
+                else hi = mid;
+            }
+            level = hi;
+        }
+        deal(level, false);
+        first = npairs;
     }
     W->psb[npairs] = W->nslots;
-    W->time = best[0] - kWavePenalty * W->nwaves;
+    W->time = *std::max_element(used.begin(), used.end());
 }
 
 static int build_wave_plan(ddb_ctx* ctx, MomentState* M, MomentState::DevPlan** out) {
@@ -764,7 +836,7 @@ static int build_wave_plan(ddb_ctx* ctx, MomentState* M, MomentState::DevPlan** 
         if (pl.stamp < P->stamp) P = &pl;  // least recently used
     const int64_t ns = (ctx->m + kKS - 1) / kKS;
     WavePlan W;
-    plan_waves(M->pairs, M->nfull, M->nhalf, ns, nctas, &W);
+    plan_waves(M->pairs, M->rows_used, ns, nctas, &W);
     const std::vector<std::vector<GramSegment>>& per_cta = W.per_cta;
     const std::vector<int32_t>& psb = W.psb;
     const int nslots = W.nslots;
@@ -849,7 +921,9 @@ int gram_moment_run(ddb_ctx* ctx, double* dPacked, bool* handled) {
     ctx->timings.gram_ms = ms;
     ctx->timings.gram_launches = 2;
     ctx->timings.gram_schedule = 2;
-    ctx->timings.gram_dmma_flops = 2.0 * kBT * kBT * (M->nfull + 0.5 * M->nhalf + 0.25 * (M->npairs - M->nfull - M->nhalf));
+    double live_rows = 0.0;
+    for (uint8_t h : M->rows_used) live_rows += h;
+    ctx->timings.gram_dmma_flops = 2.0 * kBT * live_rows;
     ctx->have_gram = (dPacked == ctx->d_packed.as<double>());
     ctx->imp_k = 0;
     *handled = true;
@@ -868,12 +942,10 @@ int64_t moment_wave_describe(const uint8_t* exps, int n, int k, int n_t, int64_t
     MomentMap map;
     analyse_library(exps, n, k, n_t, D, &map);
     if (!map.worth) return 0;
-    const int nfull = (int)std::count(map.rows_used.begin(), map.rows_used.end(), (uint8_t)128);
-    const int nhalf = (int)std::count(map.rows_used.begin(), map.rows_used.end(), (uint8_t)64);
     WavePlan W;
-    plan_waves(map.pairs, nfull, nhalf, (m + kKS - 1) / kKS, nctas, &W);
+    plan_waves(map.pairs, map.rows_used, (m + kKS - 1) / kKS, nctas, &W);
     double cost = 0.0;
-    for (uint8_t h : map.rows_used) cost += h == 128 ? 1.0 : h == 64 ? kHalfCost : kQuarterCost;
+    for (uint8_t h : map.rows_used) cost += pair_cost(h);
     if (info) info[0] = W.time, info[1] = cost / nctas, info[2] = W.nwaves, info[3] = W.nslots;
     int64_t w = 0;
     for (int c = 0; c < nctas; ++c)

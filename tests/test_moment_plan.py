@@ -60,7 +60,7 @@ def _check_plan(ex, n_t, complete):
     col = pairs[pair, 1] * 128 + off % 128
     assert ((pairs[:, 0] < nrb) != (pairs[:, 1] < nrb)).all()  # a row block and a column block, either order
     assert (pairs[pairs[:, 2] == 128, 0] < nrb).all()
-    # pairs at the edge of the staircase that only use their first 64 rows come last and are marked
+    # pairs at the edge of the staircase that only use their first 64 / 32 rows come last and are marked
     assert set(pairs[:, 2].tolist()) <= {32, 64, 128} and (np.diff(pairs[:, 2]) <= 0).all()
     assert ((off // 128) < pairs[pair, 2]).all()
     top = np.zeros(plan["npairs"], dtype=np.int64)  # largest row / column used per pair: the class is the tightest
@@ -168,18 +168,26 @@ def test_moment_wave_plan_covers_every_pair_and_stage_once(n, deg, n_t, m, nctas
         assert all(ranges[i][1] == ranges[i + 1][0] for i in range(len(ranges) - 1))
         assert [r[2] for r in ranges] == list(range(ranges[0][2], ranges[0][2] + len(ranges)))
     assert sorted(seg[:, 3].tolist()) == list(range(seg.shape[0])) and info[3] == seg.shape[0]
-    # every CTA takes part in a wave at most once: its k-th segment belongs to wave k or later
+    # a CTA takes part in every homogeneous wave at most once; the final wave is one stream cut where the CTAs'
+    # common finishing time falls, so a CTA may change pair a few times there
     per_cta = np.bincount(seg[:, 0], minlength=nctas)
-    assert per_cta.max() <= info[2]
+    assert per_cta.max() <= info[2] + 4
+    # planned finishing time = the busiest CTA's share, recomputed here from the segments
+    cost_of = {128: 1.0, 64: 0.53, 32: 0.45}
+    busy = np.zeros(nctas)
+    for cta, bi, bj, slot, b, e, rows in seg.tolist():
+        busy[cta] += cost_of[rows] * (e - b) / nstages
+    assert abs(busy.max() - info[0]) < 1e-9
     if nstages >= 64 * nctas:
         assert info[1] <= info[0] <= 1.02 * info[1]
 
 
 def test_moment_wave_plan_lorenz96_is_within_one_percent_of_a_perfect_split():
-    """C3 at full size: four waves (37 whole pairs x 4 ranges, 21 x 7, 2 x 74, then the last 2 whole, 6 half and
-    10 quarter pairs in one mixed wave): 0.473 pair streams per CTA against 69.7 / 148 = 0.471."""
+    """C3 at full size: three homogeneous waves of whole pairs (37 x 4 ranges, 21 x 7, 2 x 74), then the last 2 whole,
+    6 half and 10 quarter pairs as one stream that fills every CTA to a common finishing time: 69.7 / 148 = 0.471
+    pair streams per CTA to a tenth of a percent."""
     seg, info = _wave_plan(oracle.polynomial_exponents(64, 2), 64, 10_000_000)
-    assert info[2] <= 4 and info[0] <= 1.01 * info[1]
+    assert info[2] <= 4 and info[0] <= 1.001 * info[1]
 
 
 def test_moment_plan_random_libraries():
