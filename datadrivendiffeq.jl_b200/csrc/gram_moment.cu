@@ -37,7 +37,7 @@
 
 namespace ddb {
 
-int gram_launch_bt128(ddb_ctx* ctx, const GramArgs& args, int nctas);
+int gram_launch_bt128(ddb_ctx* ctx, const GramArgs& args, int nctas, bool offdiag_only);
 int gram_launch_mb128(ddb_ctx* ctx, const GramArgs& args, int nctas);
 bool gram_mb_fits(int n, int n_t);
 int gram_ensure_factors(ddb_ctx* ctx, int kaug_pad);
@@ -907,7 +907,7 @@ int gram_moment_run(ddb_ctx* ctx, double* dPacked, bool* handled) {
         a.opcnt = M->opcnt.as<uint8_t>();
         DDB_TRY(gram_launch_mb128(ctx, a, ctx->sm_count));
     } else {
-        DDB_TRY(gram_launch_bt128(ctx, a, ctx->sm_count));
+        DDB_TRY(gram_launch_bt128(ctx, a, ctx->sm_count, true));
     }
     const int64_t count = ddb_gram_count(ctx);
     moment_gather_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(

@@ -540,7 +540,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) gram_ring_kernel(const RingAr
 // ---------------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------------
-int gram_launch_bt128(ddb_ctx* ctx, const GramArgs& args, int nctas);
+int gram_launch_bt128(ddb_ctx* ctx, const GramArgs& args, int nctas, bool offdiag_only);
 void gram_reduce_launch(ddb_ctx* ctx, const double* partials, const int2* pairs, const int32_t* pair_slot_begin,
                         int npairs, int bt, int k, int n_t, double* packed);
 int gram_ensure_factors(ddb_ctx* ctx, int rows);
@@ -759,7 +759,7 @@ int gram_ring_run(ddb_ctx* ctx, double* dPacked, bool* handled) {
         g.segs = reinterpret_cast<const GramSegment*>(base + R->off_segs);
         g.cta_seg_begin = reinterpret_cast<const int32_t*>(base + R->off_cta);
         g.partials = R->partials.as<double>();
-        DDB_TRY(gram_launch_bt128(ctx, g, ctx->sm_count));
+        DDB_TRY(gram_launch_bt128(ctx, g, ctx->sm_count, false));
         ++launches;
     }
     gram_reduce_launch(ctx, R->partials.as<double>(), reinterpret_cast<const int2*>(base + R->off_pairs),
