@@ -747,10 +747,10 @@ static void plan_waves(const std::vector<std::pair<int, int>>& pairs, const std:
             first += np;
             continue;
         }
-        // Final wave.  The DP sized it as "pair p over ceil(cost_p / T) equal ranges"; it is dealt out as ONE stream
-        // (pair after pair, stage after stage) that fills every CTA up to a common finishing time, the CTAs the
-        // earlier waves left idle included: no quantisation by class, at the price of CTAs that change pair inside the
-        // wave (a flush and a pipeline fill, microseconds against a wave of tens of milliseconds).
+        // Final wave.  The DP sized it as "pair p over ceil(cost_p / T) equal ranges"; it is dealt out so that every CTA
+        // finishes at a common time (the water level below), the CTAs the earlier waves left idle included: no
+        // quantisation by class, at the price of a few CTAs that change pair inside the wave (a flush and a pipeline
+        // fill, microseconds against a wave of tens of milliseconds).
         if (getenv("DDB_MOMENT_STREAM") && atoi(getenv("DDB_MOMENT_STREAM")) == 0) {  // as sized: equal ranges per pair
             std::vector<int> ranges;
             double T;
@@ -776,45 +776,101 @@ static void plan_waves(const std::vector<std::pair<int, int>>& pairs, const std:
                 break;
             }
         }
-        // CTAs in the order of the homogeneous waves; a piece shorter than kMinPiece stages is not worth a segment.
-        // Pieces are whole stages, so with few stages per pair the last CTA would collect what the roundings left
-        // over: the level is raised (bisection on a dry run) until the stream ends within it.
+        // Two phases.  (1) Aligned pieces: a CTA with the standard room B (every CTA that took part in all earlier waves)
+        // takes L_p = B / (cost per stage) stages of ONE pair, at a multiple of L_p -- the pairs of a cost class then walk
+        // the same samples at the same time and share their X / Y tiles through L2, as in the homogeneous waves.
+        // (2) What is left of every pair (less than one piece) is dealt out as a stream over the remaining CTAs, each up
+        // to the level; a piece shorter than kMinPiece stages is not worth a segment.  Pieces are whole stages, so with
+        // few stages per pair the last CTA would collect what the roundings left over: the level is raised (bisection
+        // on a dry run) until the stream ends within it.
         const int64_t kMinPiece = std::max<int64_t>(1, std::min<int64_t>(32, ns / 64));
-        auto deal = [&](double lvl, bool dry) {  // returns the finishing time of the last CTA used
+        struct Piece {
+            int p, cta;
+            int64_t b, e;
+        };
+        double std_used = 0.0;  // the most common load so far
+        {
+            int best_n = 0;
+            for (int c = 0; c < nctas; ++c) {
+                int cnt = 0;
+                for (int d = 0; d < nctas; ++d) cnt += std::fabs(used[d] - used[c]) < 1e-12;
+                if (cnt > best_n) best_n = cnt, std_used = used[c];
+            }
+        }
+        auto deal = [&](double lvl, std::vector<Piece>* out) {  // returns the finishing time of the last CTA of the stream
             std::vector<double> u = used;
-            int cta = 0;
+            std::vector<char> taken(nctas, 0);
+            std::vector<int64_t> rest(npairs - first, 0);  // first stage of the pair that phase 1 left
+            const double room_std = lvl - std_used;
+            int next_std = 0;
             for (int p = first; p < npairs; ++p) {
-                if (!dry) W->psb[p] = W->nslots;
                 const double per_stage = cost_of(p) / (double)max_r;
+                const int64_t L = (int64_t)std::floor(room_std / per_stage + 1e-9);
                 int64_t st = 0;
+                while (L >= std::max<int64_t>(kMinPiece, 1) && ns - st >= L) {
+                    while (next_std < nctas && (taken[next_std] || std::fabs(used[next_std] - std_used) >= 1e-12)) ++next_std;
+                    if (next_std >= nctas) break;
+                    taken[next_std] = 1;
+                    u[next_std] += per_stage * (double)L;
+                    if (out) out->push_back({p, next_std, st, st + L});
+                    st += L;
+                }
+                rest[p - first] = st;
+            }
+            std::vector<int> free_ctas;
+            for (int c = 0; c < nctas; ++c)
+                if (!taken[c]) free_ctas.push_back(c);
+            if (free_ctas.empty()) free_ctas.push_back((int)(std::min_element(u.begin(), u.end()) - u.begin()));
+            size_t fi = 0;
+            for (int p = first; p < npairs; ++p) {
+                const double per_stage = cost_of(p) / (double)max_r;
+                int64_t st = rest[p - first];
                 while (st < ns) {
-                    while (cta < nctas - 1 && lvl - u[cta] < per_stage * (double)std::min<int64_t>(kMinPiece, ns - st)) ++cta;
+                    while (fi + 1 < free_ctas.size() && lvl - u[free_ctas[fi]] < per_stage * (double)std::min<int64_t>(kMinPiece, ns - st)) ++fi;
+                    const int cta = free_ctas[fi];
                     int64_t take = ns - st;
-                    if (cta < nctas - 1) {
+                    if (fi + 1 < free_ctas.size()) {
                         take = std::min<int64_t>(take, (int64_t)std::floor((lvl - u[cta]) / per_stage + 0.5));
                         if (ns - st - take < kMinPiece && ns - st - take > 0) take = ns - st;  // no crumbs at a pair's end
                         take = std::max<int64_t>(take, 1);
                     }
-                    if (!dry) push(p, cta, st, st + take);
+                    if (out) out->push_back({p, cta, st, st + take});
                     u[cta] += per_stage * (double)take;
                     st += take;
                 }
             }
-            return u[cta];
+            return u[free_ctas[fi]];
         };
         double max_stage = 0.0;
         for (int p = first; p < npairs; ++p) max_stage = std::max(max_stage, cost_of(p) / (double)max_r);
         double lo = level, hi = level + 2.0 * max_stage * (double)kMinPiece + 1e-12;
-        while (deal(hi, true) > hi + 0.5 * max_stage) hi += max_stage * (double)kMinPiece;  // (ends: one CTA can take everything)
-        if (deal(lo, true) > lo + 0.5 * max_stage) {
+        while (deal(hi, nullptr) > hi + 0.5 * max_stage) hi += max_stage * (double)kMinPiece;  // (ends: one CTA can take everything)
+        if (deal(lo, nullptr) > lo + 0.5 * max_stage) {
             for (int it = 0; it < 40; ++it) {
                 const double mid = 0.5 * (lo + hi);
-                if (deal(mid, true) > mid + 0.5 * max_stage) lo = mid;
+                if (deal(mid, nullptr) > mid + 0.5 * max_stage) lo = mid;
                 else hi = mid;
             }
             level = hi;
         }
-        deal(level, false);
+        std::vector<Piece> pieces;
+        deal(level, &pieces);
+        // slots of a pair: contiguous, in stage order
+        std::vector<int> order(pieces.size()), slot_of(pieces.size());
+        for (size_t i = 0; i < pieces.size(); ++i) order[i] = (int)i;
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+            return pieces[x].p != pieces[y].p ? pieces[x].p < pieces[y].p : pieces[x].b < pieces[y].b;
+        });
+        for (size_t i = 0; i < order.size(); ++i) {
+            const Piece& pc = pieces[order[i]];
+            if (i == 0 || pieces[order[i - 1]].p != pc.p) W->psb[pc.p] = W->nslots + (int)i;
+            slot_of[order[i]] = W->nslots + (int)i;
+        }
+        for (size_t i = 0; i < pieces.size(); ++i) {
+            const Piece& pc = pieces[i];
+            push(pc.p, pc.cta, pc.b, pc.e);
+            W->per_cta[pc.cta].back().slot = slot_of[i];
+        }
         first = npairs;
     }
     W->psb[npairs] = W->nslots;

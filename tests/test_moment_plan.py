@@ -168,10 +168,11 @@ def test_moment_wave_plan_covers_every_pair_and_stage_once(n, deg, n_t, m, nctas
         assert all(ranges[i][1] == ranges[i + 1][0] for i in range(len(ranges) - 1))
         assert [r[2] for r in ranges] == list(range(ranges[0][2], ranges[0][2] + len(ranges)))
     assert sorted(seg[:, 3].tolist()) == list(range(seg.shape[0])) and info[3] == seg.shape[0]
-    # a CTA takes part in every homogeneous wave at most once; the final wave is one stream cut where the CTAs'
-    # common finishing time falls, so a CTA may change pair a few times there
+    # a CTA takes part in every homogeneous wave at most once; in the final wave most CTAs take one aligned piece of
+    # one pair, the rest share the pairs' remainders as a stream cut where the common finishing time falls, so a
+    # CTA may change pair a few times there
     per_cta = np.bincount(seg[:, 0], minlength=nctas)
-    assert per_cta.max() <= info[2] + 4
+    assert per_cta.max() <= info[2] + 8
     # planned finishing time = the busiest CTA's share, recomputed here from the segments
     cost_of = {128: 1.0, 64: 0.53, 32: 0.45}
     busy = np.zeros(nctas)
