@@ -148,6 +148,11 @@ done:
     return status;
 }
 
+// sweep.cu (minimum-norm steps of rank-deficient masked systems beyond the shared-memory Jacobi solver): eigenvectors
+// of the symmetric n x n matrix dA (lower triangle read, column-major == row-major) overwrite it as columns,
+// eigenvalues ascending to dW
+int eig_sym_device(ddb_ctx* ctx, double* dA, int n, double* dW) { return eig_run(ctx, 0, dA, n, dW, nullptr); }
+
 }  // namespace ddb
 
 using namespace ddb;

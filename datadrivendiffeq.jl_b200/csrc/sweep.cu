@@ -428,6 +428,7 @@ int chol_factor_shared(ddb_ctx* ctx, double* A, int k, int* d_fail, int extra, i
 int chol_solve_many(ddb_ctx* ctx, const double* L, int k, double* Z, int nrhs, int* launches);
 void comm_collect_time(ddb_ctx* ctx);  // comm.cu: duration of the last queued all-reduce -> timings (after a sync)
 int comm_allreduce(ddb_ctx* ctx, double* d, int64_t count);  // comm.cu: in-place sum over the ranks on the compute stream
+int eig_sym_device(ddb_ctx* ctx, double* dA, int n, double* dW);  // dmd_post.cu: symmetric eigen-decomposition (cuSOLVER Xsyevd)
 
 // ---------------------------------------------------------------------------------------------
 // per-target state and the shared post-solve step logic
@@ -725,6 +726,7 @@ __device__ void finish_init(const SweepDev& S, int e, int* redi, const double* x
         st.last_cand = -1;
         st.dof0 = na;  // dof of the zeroed best cache = mask of the initial solution (solver.jl:82-83)
         st.pad[0] = 0;  // initial solve done
+        st.pad[1] = 0;  // not parked for a minimum-norm big step
         // candidate e is the zero model of target e
         S.cand_off[e] = 0;
         S.cand_nnz[e] = 0;
@@ -765,6 +767,7 @@ __global__ void __launch_bounds__(256) sweep_init_kernel(SweepDev S) {
             st.dof0 = 0;
             st.flags = 0;
             st.pad[0] = 1;  // initial solve pending
+            st.pad[1] = 0;
         }
         return;
     }
@@ -895,7 +898,7 @@ __global__ void __launch_bounds__(256) stlsq_small_kernel(SweepDev S, int small_
             break;
         }
         const int na = st.na;
-        if (na > small_max) {
+        if (na > small_max || st.pad[1]) {  // pad[1]: a rank-deficient system beyond the Jacobi solver (see below)
             if (threadIdx.x == 0) {
                 st.status = kEqNeedBig;
                 atomicAdd(&S.counters[3], 1);
@@ -970,6 +973,15 @@ __global__ void __launch_bounds__(256) stlsq_small_kernel(SweepDev S, int small_
             __syncthreads();
         }
         const bool try_pinv = suspicious && na <= kPinvMax && S.algorithm == DDB_ALG_STLSQ;
+        if (suspicious && !try_pinv && S.algorithm == DDB_ALG_STLSQ) {
+            // possibly rank deficient with more than kPinvMax active terms: nothing of the step has been published yet
+            // (X_prev = X is repeated by the big path's gather) -- park the target; the next big step factorises it
+            // again and, when that breaks down (pivot <= kPivotTol of chol.cu), takes the minimum-norm step in global
+            // memory (pinv_big_*)
+            __syncthreads();
+            if (threadIdx.x == 0) st.pad[1] = 1;
+            continue;
+        }
         if (bad && !try_pinv && threadIdx.x == 0) st.flags |= 1;
         // forward / backward substitution by warp 0 (na <= small_max: serial over columns, lanes over rows)
         if (threadIdx.x < 32) {
@@ -1125,12 +1137,70 @@ __global__ void __launch_bounds__(256) stlsq_big_finish_kernel(SweepDev S, const
     if (threadIdx.x == 0) {
         if (fail[slot]) S.eq[e].flags |= 1;
         S.eq[e].status = kEqRunning;
+        S.eq[e].pad[1] = 0;
     }
     __syncthreads();
     if (S.eq[e].pad[0])
         finish_init(S, e, redi, x);  // initial solve of an implicit target
     else
         finish_step(S, e, red, redi, s_tmp, x, S.xprev + (size_t)e * k);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Minimum-norm big steps: rank-deficient masked systems of more than kPinvMax active terms
+// ---------------------------------------------------------------------------------------------
+// Same rule as pinv_solve_warp (x_p = G_pp^+ r_p on the UN-scaled block, eigenvalues below na * 16 eps * max count
+// as zero), for systems that live in global memory: the block is gathered un-scaled, diagonalised by the symmetric
+// eigen-solver behind eig_sym_device, and the pseudo-inverse applied by two small kernels.  Only reached when the
+// batched Cholesky factorisation of a parked target broke down (fewer samples than active terms, collinear terms),
+// i.e. where the reference's `A[p, :]' \ b` (STLSQ.jl:93-99, 135-140) returns its minimum-norm solution.
+__global__ void __launch_bounds__(256) pinv_big_gather_kernel(SweepDev S, int e, const int* __restrict__ idx, int na,
+                                                              double* __restrict__ G, double* __restrict__ b) {
+    const int k = S.k;
+    const int i = blockIdx.x;
+    const double di = S.dinv[idx[i]];
+    const double* src = S.As + (size_t)idx[i] * k;
+    for (int j = threadIdx.x; j < na; j += blockDim.x) {
+        const double dj = S.dinv[idx[j]];
+        G[(size_t)i * na + j] = (di > 0.0 && dj > 0.0) ? src[idx[j]] / (di * dj) : 0.0;
+    }
+    if (threadIdx.x == 0) b[i] = di > 0.0 ? S.rs[(size_t)e * k + idx[i]] / di : 0.0;
+}
+
+// c_i = [lambda_i > tol] (v_i' b) / lambda_i ; one warp per eigenvector (column i of V: V[j + na * i])
+__global__ void __launch_bounds__(256) pinv_big_project_kernel(const double* __restrict__ V, const double* __restrict__ lam,
+                                                               int na, const double* __restrict__ b, double* __restrict__ c) {
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (i >= na) return;
+    const double tol = (double)na * 16.0 * 2.220446049250313e-16 * fmax(lam[na - 1], 0.0);  // ascending eigenvalues
+    const double li = lam[i];
+    double d = 0.0;
+    if (li > tol) {
+        const double* v = V + (size_t)i * na;
+        for (int j = lane; j < na; j += 32) d = fma(v[j], b[j], d);
+        for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+        d /= li;
+    }
+    if (lane == 0) c[i] = d;
+}
+
+// x = V c, handed to the finish step in the scaled form it expects (x_j = z_j dinv_j); the slot's failure flag is
+// cleared and bit 1 of the target's flags records that a minimum-norm solution was used
+__global__ void __launch_bounds__(256) pinv_big_expand_kernel(SweepDev S, int e, int slot, const int* __restrict__ idx, int na,
+                                                              const double* __restrict__ V, const double* __restrict__ c,
+                                                              int* fail) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < na) {
+        double x = 0.0;
+        for (int i = 0; i < na; ++i) x = fma(V[(size_t)i * na + j], c[i], x);
+        const double dj = S.dinv[idx[j]];
+        S.znew[(size_t)e * S.k + j] = dj > 0.0 ? x / dj : 0.0;
+    }
+    if (j == 0) {
+        fail[slot] = 0;
+        S.eq[e].flags |= 2;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1401,7 +1471,7 @@ void SweepState::release_all() {
                      &cand_val, &cand_off, &cand_nnz, &cand_dof, &cand_eq, &counters, &pool_used_d, &run_cand,
                      &run_jfirst, &run_j, &path_support, &path_coef, &path_iters, &big_ws, &big_idx, &big_na,
                      &big_list, &big_fail, &big_loc, &big_xbuf, &dense_ids, &dense_work, &active_matrix, &shared_fail, &rss, &rss_partials, &out_tmp, &cand_terms,
-                     &Ninv, &tgt_terms, &rss_corr, &grp_buf, &rep_buf, &zsol, &canon_tmp};
+                     &Ninv, &tgt_terms, &rss_corr, &grp_buf, &rep_buf, &zsol, &canon_tmp, &pinv_ws};
     for (DevBuf* b : all) b->release();
 }
 
@@ -1540,7 +1610,7 @@ int sweep_run(ddb_ctx* ctx, const ddb_sweep_params* prm, const double* lambdas, 
     DDB_TRY(S->shared_fail.reserve(16));
 
     cudaStream_t st = ctx->stream;
-    int launches = 0, big_steps = 0;
+    int launches = 0, big_steps = 0, pinv_steps = 0;
     DDB_CUDA_TRY(cudaMemcpyAsync(S->lambdas_d.p, S->lambdas.data(), (size_t)L * 8, cudaMemcpyHostToDevice, st));
     int h_counters[8] = {n_t, 0, 0, 0, 0, 0, 0, 0};  // candidates 0..n_t-1 are the zero models
     DDB_CUDA_TRY(cudaMemcpyAsync(S->counters.p, h_counters, sizeof(h_counters), cudaMemcpyHostToDevice, st));
@@ -1611,9 +1681,10 @@ int sweep_run(ddb_ctx* ctx, const ddb_sweep_params* prm, const double* lambdas, 
     }
     SweepDev D = make_dev(ctx, S);
     if (use_inverse) D.zsol = S->zsol.as<double>();
-    if (shared_factor && prm->algorithm == DDB_ALG_STLSQ && k <= kPinvMax) {
-        // small libraries: a factorisation that broke down (fewer samples than terms, collinear terms) is not an error --
-        // the initial least squares then runs as a masked solve with the minimum-norm fallback (pinv_solve_warp)
+    if (shared_factor && prm->algorithm == DDB_ALG_STLSQ) {
+        // a factorisation that broke down (fewer samples than terms, collinear terms) is not an error -- the initial
+        // least squares then runs as a masked solve with the minimum-norm fallback (pinv_solve_warp up to kPinvMax
+        // terms, pinv_big_* through a big step beyond)
         int h_fail = 0;
         DDB_CUDA_TRY(cudaMemcpyAsync(&h_fail, S->shared_fail.p, 4, cudaMemcpyDeviceToHost, st));
         DDB_CUDA_TRY(cudaStreamSynchronize(st));
@@ -1634,6 +1705,7 @@ int sweep_run(ddb_ctx* ctx, const ddb_sweep_params* prm, const double* lambdas, 
         const int x_in_smem = base_smem + 2 * (size_t)k * sizeof(double) <= 200 * 1024;
         const size_t small_smem = base_smem + (x_in_smem ? 2 * (size_t)k * sizeof(double) : 0);
         DDB_CUDA_TRY(cudaFuncSetAttribute(stlsq_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem));
+        std::vector<int> h_big;
         for (int round = 0;; ++round) {
             stlsq_small_kernel<<<n_t, 256, small_smem, st>>>(D, kSmallMax, x_in_smem);
             count_status_kernel<<<1, 32, 0, st>>>(D.eq, n_t, D.counters);
@@ -1695,6 +1767,36 @@ int sweep_run(ddb_ctx* ctx, const ddb_sweep_params* prm, const double* lambdas, 
                                         S->big_fail.as<int>(), 1, k, &launches));
                 DDB_TRY(chol_back_batched(ctx, S->big_ws.as<double>(), ws_stride, k, S->big_na.as<int>(), k, nbig, k, 1,
                                           S->znew.as<double>(), (size_t)k, 0, S->big_list.as<int>(), nullptr));
+            }
+            {   // factorisations that broke down: minimum-norm steps (pinv_big_*), as `A[p, :]' \ b` takes in the reference.
+                // Sharded runs: the flags are the all-reduced ones, every rank repeats the same few fallback solves.
+                h_big.resize((size_t)3 * nbig);
+                DDB_CUDA_TRY(cudaMemcpyAsync(h_big.data(), S->big_fail.p, (size_t)nbig * 4, cudaMemcpyDeviceToHost, st));
+                DDB_CUDA_TRY(cudaStreamSynchronize(st));
+                bool any_fail = false;
+                for (int b = 0; b < nbig; ++b) any_fail |= h_big[b] != 0;
+                if (any_fail) {
+                    int h_nf = 0;
+                    DDB_CUDA_TRY(cudaMemcpyAsync(&h_nf, S->shared_fail.as<int>() + 1, 4, cudaMemcpyDeviceToHost, st));
+                    DDB_CUDA_TRY(cudaMemcpyAsync(h_big.data() + nbig, S->big_na.p, (size_t)nbig * 4, cudaMemcpyDeviceToHost, st));
+                    DDB_CUDA_TRY(cudaMemcpyAsync(h_big.data() + 2 * nbig, S->big_list.p, (size_t)nbig * 4, cudaMemcpyDeviceToHost, st));
+                    DDB_CUDA_TRY(cudaStreamSynchronize(st));
+                    for (int b = 0; b < nbig && !h_nf; ++b) {  // NaN / Inf in the blocks: reported below, nothing to solve
+                        if (!h_big[b]) continue;
+                        const int na = h_big[nbig + b], e = h_big[2 * nbig + b];
+                        DDB_TRY(S->pinv_ws.reserve(((size_t)na * na + 3 * (size_t)na) * 8));
+                        double* Gp = S->pinv_ws.as<double>();
+                        double *lam = Gp + (size_t)na * na, *bp = lam + na, *cp = bp + na;
+                        const int* idx = S->big_idx.as<int>() + (size_t)b * k;
+                        pinv_big_gather_kernel<<<na, 256, 0, st>>>(D, e, idx, na, Gp, bp);
+                        DDB_CUDA_TRY(cudaGetLastError());
+                        DDB_TRY(eig_sym_device(ctx, Gp, na, lam));
+                        pinv_big_project_kernel<<<(na + 7) / 8, 256, 0, st>>>(Gp, lam, na, bp, cp);
+                        pinv_big_expand_kernel<<<(na + 255) / 256, 256, 0, st>>>(D, e, b, idx, na, Gp, cp, S->big_fail.as<int>());
+                        launches += 3;
+                        ++pinv_steps;
+                    }
+                }
             }
             stlsq_big_finish_kernel<<<nbig, 256, 0, st>>>(D, S->big_list.as<int>(), S->big_idx.as<int>(),
                                                           S->big_na.as<int>(), S->big_fail.as<int>());

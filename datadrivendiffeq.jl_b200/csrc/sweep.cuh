@@ -39,6 +39,7 @@ struct SweepState {
     DevBuf run_cand, run_jfirst, run_j;
     DevBuf path_support, path_coef, path_iters;
     DevBuf big_ws, big_idx, big_na, big_list, big_fail, active_matrix, shared_fail;
+    DevBuf pinv_ws;       // un-scaled masked block, eigenvalues and two vectors of a minimum-norm big step
     DevBuf big_loc;   // sharded big steps: [na of my slots | fail of my slots | global slot of my slots] (3 x n_t ints)
     DevBuf dense_ids, dense_work;  // rss pass of dense candidates (rss_dense.cu): candidate ids; coefficient matrix + partial sums
     DevBuf big_xbuf;  // sharded big steps: per parked target [solution (k) | failure flag], summed over the ranks

@@ -264,8 +264,8 @@ def test_zero_target_and_zero_library_term(ctx):
 
 def test_rank_deficient_library(ctx):
     """15 terms, 10 samples: the Gram matrix is singular.  Small libraries (<= 64 terms) follow the reference through
-    its minimum-norm steps (see test_skinny_fewer_samples_than_terms); larger ones are reported as
-    DDB_NOT_POSITIVE_DEFINITE -- never a silent fallback, never a garbage solution from a tiny pivot."""
+    its minimum-norm steps in shared memory (see test_skinny_fewer_samples_than_terms); larger ones take them in global
+    memory (test_rank_deficient_library_beyond_jacobi) -- never a garbage solution from a tiny pivot."""
     rng = np.random.default_rng(4)
     X = rng.standard_normal((2, 10))
     ex = oracle.polynomial_exponents(2, 4)
@@ -283,14 +283,53 @@ def test_rank_deficient_library(ctx):
         np.testing.assert_array_equal(out.support_path[i], np.stack(traces[i].support_path))
     np.testing.assert_allclose(out.coefficients, ref.coefficients, rtol=1e-6, atol=1e-9)
     assert not (out.flags & 1).any() and (out.flags & 2).all()  # bit 1: minimum-norm steps were taken
-    # 91 terms, 50 samples: beyond the shared-memory pseudo-inverse
-    X = rng.standard_normal((12, 50))
-    ctx.set_library(oracle.polynomial_exponents(12, 2))
-    ctx.upload(X, X[:2].copy())
+
+
+def _min_norm_case(ctx, ex, X, Y, lams, rtol=1e-6):
+    """STLSQ on a rank-deficient library against the oracle: supports at every step, coefficients, flags."""
+    traces = []
+    ref = oracle.sparse_regression(oracle.STLSQ(lams), oracle.evaluate_library(ex, X), Y, traces=traces)
+    ctx.set_features(0, None)
+    ctx.set_library(ex)
+    ctx.upload(X, Y)
     ctx.gram()
-    with pytest.raises(ddb200._lib.DDBError) as ei:
-        ctx.sweep(ctx.make_params("STLSQ"), np.array([0.1]))
-    assert ei.value.status == -5  # DDB_NOT_POSITIVE_DEFINITE
+    ctx.sweep(ctx.make_params("STLSQ"), lams)
+    ctx.rss()
+    out = ctx.select(paths=True)
+    for i in range(Y.shape[0]):
+        np.testing.assert_array_equal(out.support_path[i], np.stack(traces[i].support_path))
+    np.testing.assert_allclose(out.coefficients, ref.coefficients, rtol=rtol, atol=1e-9)
+    assert not (out.flags & 1).any() and (out.flags & 2).all()  # bit 1: minimum-norm steps were taken
+    return out, ref
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nstates,m", [(12, 50), (20, 100)])
+def test_rank_deficient_library_beyond_jacobi(ctx, nstates, m):
+    """Fewer samples than terms with MORE than 64 terms (91 over 50 samples: parked by the shared-memory kernel; 231
+    over 100: the initial solve is a big step itself): the factorisation of the masked system breaks down and the step
+    is the minimum-norm solution of the un-scaled block (sweep.cu: pinv_big_*), as `A[p, :]' \\ b` returns in the
+    reference (STLSQ.jl:93-99, 135-140)."""
+    rng = np.random.default_rng(40 + nstates)
+    X = rng.standard_normal((nstates, m))
+    ex = oracle.polynomial_exponents(nstates, 2)
+    assert ex.shape[1] > 64 and ex.shape[1] > m
+    Y = np.stack([X[0] * X[1] - 0.5 * X[2], 2.0 * X[3] + X[4] * X[4]])
+    out, ref = _min_norm_case(ctx, ex, X, Y, np.array([0.05, 0.1, 0.3]))
+    assert (ref.coefficients != 0).sum() > 0
+
+
+@pytest.mark.gpu
+def test_collinear_big_library_minimum_norm(ctx):
+    """150 'states' as an identity library, two of them exact sums of others, MORE samples than terms: every step whose
+    active set still holds a dependent triple is a minimum-norm step."""
+    rng = np.random.default_rng(7)
+    m, ns = 400, 150
+    Th = rng.standard_normal((ns, m))
+    Th[10] = Th[3] + Th[4]
+    Th[77] = Th[5] - Th[140]
+    Y = (1.5 * Th[3] + 0.7 * Th[4] - 2.0 * Th[5] + 0.9 * Th[100])[None, :] + 1e-3 * rng.standard_normal((1, m))
+    _min_norm_case(ctx, np.eye(ns, dtype=np.uint8), Th, Y, np.array([0.005, 0.02, 0.5]))
 
 
 # ------------------------------------------------------------------------------------------------
