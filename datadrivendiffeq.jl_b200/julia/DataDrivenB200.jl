@@ -23,8 +23,12 @@ module DataDrivenB200
 using DataDrivenDiffEq, DataDrivenSparse, CommonSolve
 using DataDrivenDiffEq: InternalDataDrivenProblem, DataDrivenSolution, DDReturnCode, get_implicit_data,
                         get_oop_args, __construct_basis, states, equations
+using DataDrivenDiffEq: DataDrivenCommonOptions, DataNormalization, DataProcessing
 import Symbolics
 import LinearAlgebra
+import Random
+import Parameters
+import StatsBase: ZScoreTransform, UnitRangeTransform
 
 const LIB = get(ENV, "DDB200_LIB", joinpath(@__DIR__, "..", "libddb200.so"))
 
@@ -56,6 +60,27 @@ function DataDrivenDiffEq.get_fit_targets(::B200Sparse, prob::DataDrivenDiffEq.A
     Y = get_implicit_data(prob)
     return X, Y
 end
+
+# HOOK 0: `init` (src/commonsolve.jl:92-139).  The reference's `init` fits the normalisation on what get_fit_targets
+# returns, APPLIES it in place and cuts the batches out of it -- all of which is meant for Theta, not for the raw states
+# this backend hands over.  So the generic `init` runs with neutral pre-processing options (identity transform, one
+# batch: the data stay where they are, nothing is copied or scaled) and the internal problem then carries the CALLER'S
+# options; normalisation, train / test split and shuffled mini-batches are done on the resident data by `solve!` below
+# (`solve_processed`), call for call like `api.py: _solve_processed`.
+function CommonSolve.init(prob::DataDrivenDiffEq.AbstractDataDrivenProblem, basis::DataDrivenDiffEq.AbstractBasis,
+        alg::B200Sparse; options::DataDrivenCommonOptions = DataDrivenCommonOptions(), kwargs...)
+    options.denoise && throw(ArgumentError("B200Sparse: denoise = true needs Theta materialised and is not supported"))
+    neutral = Parameters.reconstruct(options; normalize = DataNormalization(), data_processing = DataProcessing())
+    ps = invoke(CommonSolve.init,
+        Tuple{DataDrivenDiffEq.AbstractDataDrivenProblem, DataDrivenDiffEq.AbstractBasis,
+              DataDrivenDiffEq.AbstractDataDrivenAlgorithm},
+        prob, basis, alg; options = neutral, kwargs...)
+    return InternalDataDrivenProblem(ps.alg, ps.testdata, ps.traindata, ps.transform, ps.control_idx, ps.implicit_idx,
+        ps.parameter_idx, ps.state_idx, options, ps.basis, ps.problem, ps.kwargs)
+end
+
+needs_processing(o::DataDrivenCommonOptions) = !(o.normalize isa DataNormalization{Nothing}) ||
+    o.data_processing.split < 1.0 || o.data_processing.batchsize > 0
 
 # exponent table of a monomial basis, n x k, in the basis' own term order
 function exponent_table(basis; implicits::Bool = false)
@@ -96,10 +121,12 @@ end
 # every candidate row on the others (ddb_implicit_select) and the best left-hand side is chosen here exactly
 # as the reference does (dof >= 2, touches a necessary term, smallest AICc).
 function CommonSolve.solve!(ps::InternalDataDrivenProblem{<:B200Sparse{<:ImplicitOptimizer}})
-    (; alg, basis, traindata, problem, options, implicit_idx) = ps
+    (; alg, basis, problem, options, implicit_idx) = ps
     @assert DataDrivenDiffEq.is_implicit(basis) "The provided `Basis` does not have implicit variables!"
-    X, Y = first(traindata)
-    XA = Matrix{Float64}(vcat(X, Y)); Y = Matrix{Float64}(Y)
+    needs_processing(options) &&
+        throw(ArgumentError("B200Sparse: normalisation / split / batches are not supported with an ImplicitOptimizer"))
+    X, Y = DataDrivenDiffEq.get_fit_targets(alg, problem, basis)   # the raw data themselves (no shuffled copy)
+    XA = Matrix{Float64}(vcat(X, Y)); Y = convert(Matrix{Float64}, Y)
     n, m = size(XA); n_t = size(Y, 1)
     E = exponent_table(basis; implicits = true); k = size(E, 2)
     inner = alg.inner.optimizer
@@ -155,19 +182,12 @@ end
 
 # HOOK 2
 function CommonSolve.solve!(ps::InternalDataDrivenProblem{<:B200Sparse})
-    (; alg, basis, traindata, testdata, problem, options) = ps
+    (; alg, basis, problem, options) = ps
     options.denoise && throw(ArgumentError("B200Sparse: denoise=true is not supported"))
-    # `init` fitted the normalisation on what get_fit_targets returned -- the RAW states, not Theta -- so anything
-    # but the identity transform would silently change the problem.  The library implements ZScore and UnitRange on
-    # the Gram blocks (`ddb_gram_scale_terms`, `ddb_term_minmax` + `ddb_gram_affine_terms`), train / test views
-    # (`ddb_set_sample_range`), shuffles (`ddb_permute_samples`) and test errors (`ddb_residual`); the orchestration
-    # of those calls exists in the tested Python mirror (`api.py: _solve_processed`) and is not restated here yet.
-    options.normalize isa DataDrivenDiffEq.DataNormalization{Nothing} ||
-        throw(ArgumentError("B200Sparse: only DataNormalization() (no normalisation) is wired up in the Julia glue"))
-    options.data_processing.split == 1.0 && options.data_processing.batchsize <= 0 ||
-        throw(ArgumentError("B200Sparse: train/test split and mini-batches are not wired up in the Julia glue"))
-    X, Y = first(traindata)          # single batch; column order is irrelevant to the Gram sums
-    X = Matrix{Float64}(X); Y = Matrix{Float64}(Y)
+    # the raw data themselves: with the neutral `init` above `traindata` is one batch of ALL samples, and taking it from
+    # the DataLoader would only add a shuffled host copy (the column order is irrelevant to the Gram sums)
+    X, Y = DataDrivenDiffEq.get_fit_targets(alg, problem, basis)
+    X = convert(Matrix{Float64}, X); Y = convert(Matrix{Float64}, Y)   # no copy when they already are
     n, m = size(X); n_t = size(Y, 1)
     E = exponent_table(basis); k = size(E, 2)
     inner = alg.inner
@@ -175,6 +195,11 @@ function CommonSolve.solve!(ps::InternalDataDrivenProblem{<:B200Sparse})
     prox = DataDrivenSparse.get_proximal(inner)
     prm = Ref(SweepParams(alg_id(inner), prox_id(prox), selector_id(options.selector), options.maxiters,
         options.abstol, options.reltol, relax(inner), prox isa ClippedAbsoluteDeviation ? Float64(prox.ρ) : NaN))
+    if needs_processing(options)
+        alg.ngpus > 1 && throw(ArgumentError("B200Sparse: normalisation / split / batches with ngpus > 1 run through the " *
+            "per-rank entry points (`ddb_comm_*`, api.py: _solve_processed_sharded), not through a ddb_group"))
+        return solve_processed(ps, X, Y, E, prm, lambdas)
+    end
     coef = zeros(n_t, k); lam = zeros(n_t); iters = zeros(Int32, n_t); rss = zeros(n_t); dof = zeros(Int32, n_t)
     flags = zeros(Int32, n_t)
     if alg.ngpus > 1
@@ -215,6 +240,129 @@ function CommonSolve.solve!(ps::InternalDataDrivenProblem{<:B200Sparse})
     new_basis = __construct_basis(copy(coef), basis, problem, options)
     return DataDrivenSolution(new_basis, problem, alg, [result], ps, result.retcode)
 end
+
+# `solve!` with the reference's pre-processing options on the RESIDENT data (src/commonsolve.jl:128-139,
+# src/utils/data_processing.jl:29-39, 64-80, lib/DataDrivenSparse/src/commonsolve.jl:1-55): the transform is fitted on the
+# library rows of ALL samples without building them (`ddb_term_css` / `ddb_term_minmax`), the contiguous train / test
+# split and the shuffled mini-batches are views (`ddb_set_sample_range`) of the data after one device-side gather
+# (`ddb_permute_samples`), every batch is regressed in the transformed space (`ddb_gram_scale_terms` /
+# `ddb_gram_affine_terms` act on the normal-equation blocks), test errors come from `ddb_residual(_affine)`, and the
+# result with the smallest test (or train) error wins.  Mirrors `api.py: _solve_processed` call for call.
+function solve_processed(ps, X::Matrix{Float64}, Y::Matrix{Float64}, E::Matrix{UInt8}, prm, lambdas::Vector{Float64})
+    (; alg, basis, problem, options) = ps
+    dp = options.data_processing
+    n, m = size(X); n_t = size(Y, 1); k = size(E, 2); L = length(lambdas)
+    split = clamp(Float64(dp.split), 0.0, 1.0)
+    m_train = clamp(round(Int, split * m), 0, m)                 # MLUtils.splitobs(at = split, shuffle = false)
+    m_train > 0 || throw(ArgumentError("B200Sparse: the training split is empty"))
+    unit = options.normalize isa DataNormalization{UnitRangeTransform}
+    zs = options.normalize isa DataNormalization{ZScoreTransform}
+    # UnitRange: a row of ones rides along as one more target, R[:, end] = Theta * 1 of every batch view
+    Yd = unit ? vcat(Y, ones(1, m)) : Y
+    ntd = size(Yd, 1)
+    sigma = ones(k); umin = zeros(k); udiv = ones(k)
+    results = DataDrivenSparse.SparseRegressionResult[]
+    ctx = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:ddb_ctx_create, LIB), Cint, (Cint, Ptr{Ptr{Cvoid}}), alg.device, ctx))
+    upload(Ym) = check(ccall((:ddb_upload, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cint, Int64),
+        ctx[], X, Ym, size(Ym, 1), m))
+    gram() = check(ccall((:ddb_gram, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), ctx[], C_NULL))
+    setview(a, b) = check(ccall((:ddb_set_sample_range, LIB), Cint, (Ptr{Cvoid}, Int64, Int64), ctx[], a, b))
+    try
+        GC.@preserve X Y Yd E lambdas begin
+            check(ccall((:ddb_set_library_monomial, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}), ctx[], n, k, E))
+            upload(Yd)
+            if unit
+                # fit(UnitRangeTransform, Theta, dims = 2) on ALL samples; an infinite scale (constant row) becomes 1
+                mx = zeros(k)
+                check(ccall((:ddb_term_minmax, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), ctx[], umin, mx))
+                udiv .= [r > 0.0 ? r : 1.0 for r in (mx .- umin)]
+            elseif zs
+                # fit(ZScoreTransform, Theta, dims = 2, center = false): two-pass standard deviation of every row
+                gram()
+                sums = zeros(k)
+                c = findfirst(j -> all(iszero, view_col(E, j)), 1:k)
+                if c !== nothing               # row of the constant term = sum over the samples of every term
+                    G = zeros(k, k)
+                    check(ccall((:ddb_gram_download, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                        ctx[], G, C_NULL, C_NULL))
+                    sums .= G[:, c]
+                else                           # one more pass with a row of ones as the target: R[:, 1] = Theta * 1
+                    upload(ones(1, m)); gram()
+                    R1 = zeros(k, 1)
+                    check(ccall((:ddb_gram_download, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                        ctx[], C_NULL, R1, C_NULL))
+                    sums .= R1[:, 1]
+                    upload(Yd)
+                end
+                center = sums ./ m; css = zeros(k)
+                check(ccall((:ddb_term_css, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), ctx[], center, css))
+                sigma .= sqrt.(max.(css, 0.0) ./ (m - 1))
+                sigma[sigma .== 0.0] .= 1.0    # constants are scaled with 1 (data_processing.jl:75-80)
+            end
+            batchsize = dp.batchsize <= 0 ? m_train : dp.batchsize
+            if batchsize < m_train             # DataLoader(shuffle = true, rng = rng) (data_processing.jl:38)
+                perm = Int64.(vcat(Random.randperm(dp.rng, m_train) .- 1, m_train:(m - 1)))
+                GC.@preserve perm check(ccall((:ddb_permute_samples, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}), ctx[], perm))
+            end
+            starts = collect(0:batchsize:(m_train - 1))
+            (!dp.partial && m_train % batchsize != 0) && pop!(starts)
+            for b0 in starts
+                b1 = min(b0 + batchsize, m_train); mb = b1 - b0
+                setview(b0, b1); gram()
+                zs && check(ccall((:ddb_gram_scale_terms, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), ctx[], sigma))
+                if unit
+                    R = zeros(k, ntd); ymean = zeros(ntd); ycss = zeros(ntd)
+                    check(ccall((:ddb_gram_download, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                        ctx[], C_NULL, R, C_NULL))
+                    check(ccall((:ddb_target_stats, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}),
+                        ctx[], mb, ymean, ycss))
+                    tsum = R[:, ntd]; ysum = ymean .* mb
+                    check(ccall((:ddb_gram_affine_terms, LIB), Cint,
+                        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64),
+                        ctx[], umin, udiv, tsum, ysum, mb))
+                end
+                coef = zeros(ntd, k); lam = zeros(ntd); iters = zeros(Int32, ntd); rssv = zeros(ntd)
+                dof = zeros(Int32, ntd); flags = zeros(Int32, ntd)
+                check(ccall((:ddb_sweep, LIB), Cint, (Ptr{Cvoid}, Ptr{SweepParams}, Ptr{Float64}, Cint, Int64),
+                    ctx[], prm, lambdas, L, mb))
+                check(ccall((:ddb_rss, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), ctx[], C_NULL))
+                check(ccall((:ddb_select, LIB), Cint,
+                    (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Float64}, Ptr{Int32}, Ptr{UInt32},
+                     Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
+                    ctx[], coef, lam, iters, rssv, dof, C_NULL, C_NULL, C_NULL, flags))
+                Cs = coef[1:n_t, :]            # in the transformed space; the auxiliary ones target is dropped
+                Cu = zs ? Cs ./ sigma' : (unit ? Cs ./ udiv' : Cs)
+                testerror = nothing
+                if m_train < m
+                    setview(m_train, m)
+                    r = zeros(ntd)
+                    if unit                    # the transformed-space model on the transformed test rows, on the raw data
+                        off = vcat(-(Cu * umin), 0.0); Cfull = vcat(Cu, zeros(1, k))
+                        check(ccall((:ddb_residual_affine, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                            ctx[], Cfull, off, r))
+                    else
+                        check(ccall((:ddb_residual, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), ctx[], Cu, r))
+                    end
+                    testerror = sum(r[1:n_t])
+                end
+                retcode = any(!iszero, flags[1:n_t] .& Int32(1)) ? DDReturnCode(2) : DDReturnCode(1)
+                push!(results, DataDrivenSparse.SparseRegressionResult(Cs, sum(abs.(Cs) .> 0.0), lam[1:n_t],
+                    Int.(iters[1:n_t]), testerror, sum(rssv[1:n_t]), retcode))
+            end
+        end
+    finally
+        ccall((:ddb_ctx_destroy, LIB), Cint, (Ptr{Cvoid},), ctx[])
+    end
+    # lib/DataDrivenSparse/src/commonsolve.jl:13-24
+    sort!(results, by = DataDrivenSparse.l2error)
+    best = first(results)
+    C = copy(DataDrivenSparse.get_coefficients(best))
+    C = unit ? (C .- umin') ./ udiv' : (zs ? C ./ sigma' : C)   # apply_transform on the transposed coefficients, as written
+    new_basis = __construct_basis(C, basis, problem, options)
+    return DataDrivenSolution(new_basis, problem, alg, results, ps, best.retcode)
+end
+view_col(E, j) = @view E[:, j]
 
 # ------------------------------------------------------------------------------------------------------
 # DataDrivenDMD: `B200DMD <: AbstractKoopmanAlgorithm` implementing the `alg(X, Y) -> (K::Eigen, B)` contract of
