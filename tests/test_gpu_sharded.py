@@ -170,6 +170,31 @@ def test_group_two_gpus_parked_targets():
 
 
 @pytest.mark.skipif(_ngpus() < 2, reason="needs 2 GPUs")
+def test_group_two_gpus_rank_deficient():
+    """231 terms over 100 samples: the initial least squares of both targets is a parked big step whose factorisation
+    breaks down; in a sharded run each rank factorises one of them, the failure flags travel with the solutions through
+    the all-reduce, and every rank then takes the same minimum-norm steps (``pinv_big_*``).  Two GPUs against one."""
+    rng = np.random.default_rng(60)
+    X = rng.standard_normal((20, 100))
+    Y = np.stack([X[0] * X[1] - 0.5 * X[2], 2.0 * X[3] + X[4] * X[4]])
+    basis = ddb200.polynomial_basis(20, 2)
+    lams = np.array([0.05, 0.1, 0.3])
+    with ddb200.Context(0) as one:
+        one.set_library(basis.exponents)
+        prm = one.make_params("STLSQ")
+        ref = one.solve_sparse(X, Y, prm, lams)
+        assert one.timings()["big_steps"] > 0
+    with ddb200.Group(2) as grp:
+        grp.set_library(basis.exponents)
+        out = grp.solve_sparse(X, Y, prm, lams)
+    assert (ref.coefficients != 0).any()
+    np.testing.assert_array_equal(out.coefficients != 0, ref.coefficients != 0)
+    np.testing.assert_array_equal(out.iterations, ref.iterations)
+    np.testing.assert_allclose(out.coefficients, ref.coefficients, rtol=1e-7, atol=1e-10)
+    assert not (out.flags & 1).any() and (out.flags & 2).all()
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs 2 GPUs")
 @pytest.mark.parametrize("alg", ["STLSQ", "ADMM"])
 def test_torchrun_two_ranks(alg, tmp_path):
     """One process per GPU (the way bench.py is launched): communicator from ``ddb_comm_init_rank``."""
