@@ -446,8 +446,9 @@ struct SweepDev {
     // equilibrated system matrix; a solve with the full matrix and entry e of the right-hand side zeroed,
     // followed by z -= Ninv[:, e] * z[e] / Ninv[e, e], is the solve with row and column e deleted.
     int implicit;
-    int init_masked;        // the initial full least squares runs as a masked solve in the persistent kernel (the
-                            // shared factorisation broke down: rank-deficient library / fewer samples than terms)
+    const int* init_masked; // device flag (or null): when set, the initial full least squares runs as a masked solve through
+                            // the step kernels (the shared factorisation broke down: rank-deficient library / fewer
+                            // samples than terms); decided on the device, the host does not wait for the flag
     const double* Ninv;     // k x k (symmetric) or null
     // per target
     double* x;              // n_t x k
@@ -744,7 +745,7 @@ __global__ void __launch_bounds__(256) sweep_init_kernel(SweepDev S) {
     double* x = S.x + (size_t)e * k;
     double* xp = S.xprev + (size_t)e * k;
     const double* z = S.znew + (size_t)e * k;
-    if ((S.implicit || S.init_masked) && S.algorithm == DDB_ALG_STLSQ) {
+    if ((S.implicit || (S.init_masked && *S.init_masked)) && S.algorithm == DDB_ALG_STLSQ) {
         // Implicit STLSQ: the initial least squares of target e runs on the library WITHOUT row e.  With an
         // exact implicit relation in the data the full Gram matrix is singular (that is the point of the
         // method) while G without a row of the relation is not, so there is no shared factorisation here: the
@@ -1685,13 +1686,7 @@ int sweep_run(ddb_ctx* ctx, const ddb_sweep_params* prm, const double* lambdas, 
         // a factorisation that broke down (fewer samples than terms, collinear terms) is not an error -- the initial
         // least squares then runs as a masked solve with the minimum-norm fallback (pinv_solve_warp up to kPinvMax
         // terms, pinv_big_* through a big step beyond)
-        int h_fail = 0;
-        DDB_CUDA_TRY(cudaMemcpyAsync(&h_fail, S->shared_fail.p, 4, cudaMemcpyDeviceToHost, st));
-        DDB_CUDA_TRY(cudaStreamSynchronize(st));
-        if (h_fail) {
-            D.init_masked = 1;
-            DDB_CUDA_TRY(cudaMemsetAsync(S->shared_fail.p, 0, 4, st));
-        }
+        D.init_masked = S->shared_fail.as<int>();
     }
     sweep_init_kernel<<<n_t, 256, 0, st>>>(D);
     ++launches;
@@ -1882,7 +1877,7 @@ int sweep_run(ddb_ctx* ctx, const ddb_sweep_params* prm, const double* lambdas, 
         set_error("ddb_sweep: the normal-equation blocks contain NaN or Inf (one or more measurements contain `NaN` or `Inf`)");
         return DDB_NONFINITE_INPUT;
     }
-    if (h_shared_fail) {
+    if (h_shared_fail && !(shared_factor && prm->algorithm == DDB_ALG_STLSQ)) {  // STLSQ: solved by masked minimum-norm steps
         set_error("ddb_sweep: the equilibrated normal matrix is not positive definite (rank-deficient library "
                   "or fewer samples than terms); this backend solves through the Gram matrix and has no QR fallback");
         return DDB_NOT_POSITIVE_DEFINITE;
