@@ -196,6 +196,7 @@ int ddb_ctx_destroy(ddb_ctx* ctx) {
     ctx->d_partials.release();
     ctx->d_plan.release();
     ctx->d_tree.release();
+    ctx->d_pow_factors.release();
     ctx->d_chunk_packed.release();
     ctx->d_term_scale.release();
     ctx->d_term_shift.release();

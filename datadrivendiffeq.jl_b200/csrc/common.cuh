@@ -126,6 +126,9 @@ struct ddb_ctx {
     ddb::DevBuf d_tree;                  // 4 programs x tree_nsteps words
     uint64_t tree_lib_version = ~0ull;
     int tree_nt = -1, tree_nsteps = 0;   // 0 = the library is not closed under "drop the last factor"
+    ddb::DevBuf d_pow_factors;           // power-table builder (gram_pow_kernel): factor codes into the table of powers
+    uint64_t pow_lib_version = ~0ull;
+    int pow_nt = -1, pow_nf = 0;         // 0 = not applicable (more than 3 states, degree < 3)
 
     // term normalisation (ddb_gram_scale_terms): the blocks in d_packed are those of Theta_j / scale_j
     ddb::DevBuf d_term_scale;            // divisor per term

@@ -25,6 +25,11 @@ struct GramArgs {
     // prefix-product builder (gram_tree_kernel, single 64 x 64 diagonal pair): 4 programs x nsteps x {dst column,
     // parent column (255 = none: the slot's ones column), factor code}
     const uint32_t* tree = nullptr;
+    // power-table builder (gram_pow_kernel, single 64 x 64 diagonal pair, at most 3 states): factor codes that point
+    // into a per-stage table of powers x_i^1 .. x_i^pow_deg (pseudo-state i * pow_deg + e - 1), kaug_pad x kMaxFactors
+    const uint16_t* pow_factors = nullptr;
+    int pow_deg = 0;
+    int swap_mode = 0;  // which of a CTA's two warps takes the heavy (26 sub-tiles) patch, see gram_pow_kernel
 };
 
 // Tensor-pipe builder, per warp and 16-sample stage: product ops (two in every k-step + a third in k-steps 0..2) as

@@ -23,11 +23,17 @@ def ctx():
 
 def _gram(ctx, tree):
     old = os.environ.get("DDB_GRAM_TREE")
+    oldp = os.environ.get("DDB_GRAM_POW")
     os.environ["DDB_GRAM_TREE"] = "1" if tree else "0"
+    os.environ["DDB_GRAM_POW"] = "0"  # the comparison is with the factor-by-factor builder, not the power-table one
     try:
         ctx.gram()
         return ctx.gram_download()
     finally:
+        if oldp is None:
+            del os.environ["DDB_GRAM_POW"]
+        else:
+            os.environ["DDB_GRAM_POW"] = oldp
         if old is None:
             del os.environ["DDB_GRAM_TREE"]
         else:
