@@ -345,8 +345,8 @@ def run_sparse(env, wl, alg, noise, steps, warmup, want_e2e, want_clocks):
         1: "Gram stage = ddb::gram_ring_kernel (producer SMs + TMA-fed FP64 DMMA.8x8x4 consumers) + ddb::gram_kernel (diagonal pairs) + reduce",
         4: "Gram stage = ddb::gram_w4_kernel (single 64 x 64 diagonal pair, 36 live sub-tiles dealt 9 + 9 + 9 + 9 to four warps; "
            "TMA-fed X/Y tiles, terms multiplied out in shared memory, FP64 DMMA.8x8x4) + reduce",
-        3: "Gram stage = ddb::gram_pow_kernel (self-building from a per-stage table of powers x_i^e: one factor per state instead of one per degree; "
-           "TMA-fed X/Y tiles, FP64 DMMA.8x8x4) + reduce",
+        3: "Gram stage = ddb::gram_pow_kernel (single 64 x 64 diagonal pair, 36 live sub-tiles dealt 9 + 9 + 9 + 9 to four warps; builder reads a "
+           "per-stage table of powers x_i^e: one factor per state instead of one per degree; TMA-fed X/Y tiles, FP64 DMMA.8x8x4) + reduce",
         2: "Gram stage = ddb::gram_kernel over the moment staircase (every distinct moment of the monomial library contracted once; "
            "TMA-fed X/Y tiles, virtual terms multiplied out in shared memory, FP64 DMMA.8x8x4) + ddb::moment_gather_kernel",
     }
@@ -358,7 +358,7 @@ def run_sparse(env, wl, alg, noise, steps, warmup, want_e2e, want_clocks):
                           "the kernel is tensor bound: this is 3.4 % of the HBM rate, the X / Y tiles are re-read once per wave and cost class by design")
     hbm, hbm_src = hbm_peak_gbs()
     roofline = {
-        "bound": "tensor", "kernel": kernels.get(sched, kernels[0]), "schedule": {0: "self-building", 1: "ring", 2: "moment", 3: "self-building (power table)", 4: "self-building (four balanced warps)"}.get(sched, "?"),
+        "bound": "tensor", "kernel": kernels.get(sched, kernels[0]), "schedule": {0: "self-building", 1: "ring", 2: "moment", 3: "self-building (four balanced warps, power table)", 4: "self-building (four balanced warps)"}.get(sched, "?"),
         # achieved = FP64 tensor-core flops the kernel ISSUED (512 per DMMA.8x8x4, counted by the plan and confirmed by ncu's
         # DMMA instruction count) / its CUDA-event duration; frac = its share of the DMMA issue-rate peak
         "achieved": executed, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": executed / FP64_DMMA_PEAK_TFLOPS,

@@ -998,235 +998,7 @@ inline size_t gram_pow_smem_bytes(int n, int n_t, int deg) {
            (size_t)kNTS * GramCfg<64>::kStageDoubles * sizeof(double);
 }
 
-template <int NF>
-__global__ void __launch_bounds__(64, 4) gram_pow_kernel(const GramArgs args) {
-    using Cfg = GramCfg<64>;
-    constexpr int BT = 64;
-    constexpr int LDT = Cfg::kPitch;
-    constexpr int KS = kKS;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-
-    const int n = args.n, n_t = args.n_t, deg = args.pow_deg;
-    const int np = n * deg;  // pseudo states
-    const uint32_t xbytes = (uint32_t)(KS * n * sizeof(double));
-    const uint32_t ybytes = (uint32_t)(KS * n_t * sizeof(double));
-    const int vdoubles = (int)(gram_vbytes(n, n_t) / sizeof(double));
-    const int pdoubles = (int)(gram_vbytes(np, n_t) / sizeof(double));
-
-    uint64_t* vfull = reinterpret_cast<uint64_t*>(smem_raw);  // [kPowNVS] raw samples landed
-    uint64_t* tfull = vfull + kPowNVS;                        // [kNTS] Theta stage built by both warps
-    double* vring = reinterpret_cast<double*>(smem_raw + 128);
-    double* pring = vring + kPowNVS * vdoubles;
-    double* tring = pring + kPowNPS * pdoubles;
-
-    const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    const int warp = tid >> 5;
-    const int g = lane >> 2, t = lane & 3;
-
-    if (tid == 0) {
-        for (int i = 0; i < kPowNVS; ++i) mbar_init(&vfull[i], 1);
-        for (int i = 0; i < kNTS; ++i) mbar_init(&tfull[i], Cfg::kWarps);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    for (int e = tid; e < kPowNVS * kVX; e += Cfg::kThreads) {
-        const int w = e % kVX;
-        vring[(e / kVX) * vdoubles + w] = (w < kVZero) ? 1.0 : 0.0;
-    }
-    for (int e = tid; e < kPowNPS * kVX; e += Cfg::kThreads) {
-        const int w = e % kVX;
-        pring[(e / kVX) * pdoubles + w] = (w < kVZero) ? 1.0 : 0.0;
-    }
-    __shared__ int s_swap;
-    if (tid == 0) {
-        unsigned wid;
-        asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
-        const int md = args.swap_mode;
-        s_swap = md == 1 ? (int)((wid >> 2) & 1u) : md == 2 ? (int)((blockIdx.x / 148) & 1) : md == 3 ? (int)((blockIdx.x / 296) & 1)
-                 : md == 4 ? (int)((wid >> 1) & 1u) : md == 5 ? (int)(((wid >> 2) ^ (wid >> 1)) & 1u) : 0;
-    }
-    __syncthreads();
-    const int role = warp ^ s_swap;
-
-    const int64_t nstages_total = (args.m + KS - 1) / KS;
-    const int seg_begin = args.cta_seg_begin[blockIdx.x];
-    const int seg_end = args.cta_seg_begin[blockIdx.x + 1];
-    int total = 0;
-    for (int sg = seg_begin; sg < seg_end; ++sg) total += (int)(args.segs[sg].stage_end - args.segs[sg].stage_begin);
-    if (total == 0) return;
-
-    int tma_seg = seg_begin;
-    int tma_stage = (int)args.segs[seg_begin].stage_begin, tma_seg_end = (int)args.segs[seg_begin].stage_end;
-    int tma_item = 0;
-    uint32_t ragged_slots = 0;
-    const int ragged_stage = (args.m % KS) ? (int)(nstages_total - 1) : -1;
-    auto request_samples = [&]() {
-        if (tma_item >= total) return;
-        const int slot = tma_item & (kPowNVS - 1);
-        const bool mine = (tma_item % Cfg::kWarps) == warp;
-        if (tma_stage != ragged_stage) {
-            if ((ragged_slots >> slot) & 1) {
-                ragged_slots &= ~(1u << slot);
-                if (mine) {
-                    if (lane < KS) vring[slot * vdoubles + kVOnes + lane] = 1.0;
-                    __syncwarp();
-                }
-            }
-            if (mine && lane == 0) {
-                double* dst = vring + slot * vdoubles + kVX;
-                const int64_t s0 = (int64_t)tma_stage * KS;
-                mbar_expect_tx(&vfull[slot], xbytes + ybytes);
-                bulk_g2s(dst, args.X + s0 * n, xbytes, &vfull[slot]);
-                bulk_g2s(dst + KS * n, args.Y + s0 * n_t, ybytes, &vfull[slot]);
-            }
-        } else {
-            ragged_slots |= 1u << slot;
-            if (mine) {
-                double* dst = vring + slot * vdoubles;
-                const int64_t s0 = (int64_t)tma_stage * KS;
-                const int valid = (int)(args.m - s0);
-                for (int e = lane; e < KS * n; e += 32) dst[kVX + e] = (e < valid * n) ? args.X[s0 * n + e] : 0.0;
-                for (int e = lane; e < KS * n_t; e += 32)
-                    dst[kVX + KS * n + e] = (e < valid * n_t) ? args.Y[s0 * n_t + e] : 0.0;
-                if (lane < KS) dst[kVOnes + lane] = (lane < valid) ? 1.0 : 0.0;
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&vfull[slot]);
-            }
-        }
-        ++tma_item;
-        if (++tma_stage == tma_seg_end && ++tma_seg < seg_end) {
-            tma_stage = (int)args.segs[tma_seg].stage_begin;
-            tma_seg_end = (int)args.segs[tma_seg].stage_end;
-        }
-    };
-
-    // ---- the table of powers of item `pit`: thread = (sample, group); groups 0 .. n - 1 one state each, group 3 the
-    // targets and the ones column (zero for the padding samples of a ragged last stage)
-    const int es = tid & 15, eq = tid >> 4;
-    auto expand = [&](int pit) {
-        const double* rv = vring + (pit & (kPowNVS - 1)) * vdoubles;
-        double* pv = pring + (pit & (kPowNPS - 1)) * pdoubles;
-        if (eq < n) {
-            const double x = rv[kVX + es * n + eq];
-            double* dst = pv + kVX + es * np + eq * deg;
-            double p = x;
-            dst[0] = p;
-            for (int d = 1; d < deg; ++d) {
-                p *= x;
-                dst[d] = p;
-            }
-        } else if (eq == 3) {
-            for (int e = 0; e < n_t; ++e) pv[kVX + KS * np + es * n_t + e] = rv[kVX + KS * n + es * n_t + e];
-            pv[kVOnes + es] = rv[kVOnes + es];
-        }
-    };
-
-    // ---- this thread's column of the single diagonal pair (all segments of the plan are pair (0, 0))
-    BuildJobs<Cfg::kJobs, NF> jb;
-    {
-        jb.live = true;
-        jb.s0 = 0;
-        jb.dst[0] = tid;
-        jb.dst[1] = KS * LDT + tid;  // (unused: one tile)
-        const int term = tid;
-        const uint4 q = *reinterpret_cast<const uint4*>(args.pow_factors + (size_t)term * kMaxFactors);
-        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-        const bool dead = term >= args.kaug;
-#pragma unroll
-        for (int d = 0; d < NF; ++d) {
-            const uint32_t f = (w[d >> 1] >> (16 * (d & 1))) & 0xFFFFu;
-            int off = kVOnes, str = 1;
-            if (f != kNoFactor) {
-                const bool isy = (f & kFactorIsY) != 0;
-                off = isy ? kVX + KS * np + (int)(f & 0x7FFF) : kVX + (int)f;
-                str = isy ? n_t : np;
-            }
-            if (dead) off = kVZero, str = 0;
-            jb.off[0][d] = off, jb.str[0][d] = str;
-            jb.off[1][d] = kVZero, jb.str[1][d] = 0;
-        }
-    }
-
-    // ---- prologue: raw tiles, the tables of items 0 .. 3, Theta(0 .. kAhead - 1) completely
-#pragma unroll 1
-    for (int i = 0; i < kPowNVS; ++i) request_samples();
-#pragma unroll 1
-    for (int it = 0; it < 2 * kAhead && it < total; ++it) {
-        mbar_wait(&vfull[it], 0);
-        expand(it);
-    }
-    __syncthreads();
-#pragma unroll 1
-    for (int it = 0; it < kAhead && it < total; ++it) {
-        const double* v = pring + it * pdoubles;
-        double* dstt = tring + it * Cfg::kStageDoubles;
-        for (int s = 0; s < KS; ++s) {
-            double p = v[jb.off[0][0] + s * jb.str[0][0]];
-#pragma unroll
-            for (int d = 1; d < NF; ++d) p *= v[jb.off[0][d] + s * jb.str[0][d]];
-            dstt[jb.dst[0] + s * LDT] = p;
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tfull[it]);
-    }
-
-    // ---- MMA cursor: warp w owns columns 32 w .. 32 w + 31 of the diagonal pair
-    const int col0 = role * 32;
-    const int shape = (role == 0) ? 1 : 2;  // diagonal offset 0 / -4
-    const uint32_t mask = shape == 1 ? kShapeDiag0 : kShapeDiagM4;
-    int item = 0;
-    bool ready_t = false, ready_v = false;
-    for (int sg = seg_begin; sg < seg_end; ++sg) {
-        const GramSegment seg = args.segs[sg];
-        double acc[8][4][2];
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-        const int nst = (int)(seg.stage_end - seg.stage_begin);
-        for (int q = 0; q < nst; ++q, ++item) {
-            const int tslot = item & (kNTS - 1);
-            if (!ready_t) mbar_wait(&tfull[tslot], (uint32_t)((item / kNTS) & 1));
-            // every warp has finished stage item - 2 here: the raw slot of item (read by expand four stages ago) and
-            // the table slot of item (read by the builder two stages ago) are free
-            request_samples();
-            const int nitem = item + kAhead;      // the item whose Theta tile this stage builds (table: two stages old)
-            const int pitem = item + 2 * kAhead;  // the item whose table of powers this stage writes
-            const bool have_next = (nitem < total);
-            if (pitem < total) {
-                if (!ready_v) mbar_wait(&vfull[pitem & (kPowNVS - 1)], (uint32_t)((pitem / kPowNVS) & 1));
-                expand(pitem);
-            }
-            ready_t = (item + 1 < total) ? mbar_test(&tfull[(item + 1) & (kNTS - 1)], (uint32_t)(((item + 1) / kNTS) & 1)) : true;
-            ready_v = (pitem + 1 < total) ? mbar_test(&vfull[(pitem + 1) & (kPowNVS - 1)], (uint32_t)(((pitem + 1) / kPowNVS) & 1)) : true;
-
-            const double* tI = tring + tslot * Cfg::kStageDoubles;
-            const double* pa = tI + t * LDT + g;
-            const double* pb = tI + t * LDT + col0 + g;
-            const double* v = pring + (nitem & (kPowNPS - 1)) * pdoubles;
-            double* tnext = tring + (nitem & (kNTS - 1)) * Cfg::kStageDoubles;  // (stale but harmless at the end)
-            if (shape == 1) stage_body<BT, NF, kShapeDiag0, true>(acc, pa, pb, v, tnext, jb);
-            else stage_body<BT, NF, kShapeDiagM4, true>(acc, pa, pb, v, tnext, jb);
-            if (have_next) {
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tfull[nitem & (kNTS - 1)]);
-            }
-        }
-
-        double* out = args.partials + (size_t)seg.slot * BT * BT;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int row = 8 * i + g;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int c = col0 + 8 * j + 2 * t;
-                if ((mask >> (i * 4 + j)) & 1)
-                    *reinterpret_cast<double2*>(out + (size_t)row * BT + c) = make_double2(acc[i][j][0], acc[i][j][1]);
-            }
-        }
-    }
-}
+// (the kernel itself follows gram_w4_kernel, whose warp layout and stage body it shares)
 
 // ---------------------------------------------------------------------------------------------
 // Four balanced warps on the single 64 x 64 diagonal pair (libraries of at most 64 augmented rows: config C2)
@@ -1272,8 +1044,8 @@ __device__ __forceinline__ void stage_body_w4(double (&accA)[8][2], double (&acc
 }
 
 constexpr int kW4Threads = 128;
-template <int NF>
-__global__ void __launch_bounds__(kW4Threads, 4) gram_w4_kernel(const GramArgs args) {
+template <int NF, int MB = 4>
+__global__ void __launch_bounds__(kW4Threads, MB) gram_w4_kernel(const GramArgs args) {
     using Cfg = GramCfg<64>;
     constexpr int BT = 64;
     constexpr int LDT = Cfg::kPitch;
@@ -1436,6 +1208,223 @@ __global__ void __launch_bounds__(kW4Threads, 4) gram_w4_kernel(const GramArgs a
         }
 
         // flush: sub-tile rows 7 - warp (columns 0 .. 7 - warp) and warp (columns 0 .. warp)
+        double* out = args.partials + (size_t)seg.slot * BT * BT;
+        const int rA = 7 - warp, rB = warp;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (j <= rA)
+                *reinterpret_cast<double2*>(out + (size_t)(8 * rA + g) * BT + 8 * j + 2 * t) = make_double2(accA[j][0], accA[j][1]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (j <= rB)
+                *reinterpret_cast<double2*>(out + (size_t)(8 * rB + g) * BT + 8 * j + 2 * t) = make_double2(accB[j][0], accB[j][1]);
+    }
+}
+
+// Power-table builder on the four-warp layout (see the comment above gram_pow_smem_bytes): gram_w4_kernel whose builder
+// reads a per-stage table of powers with NF = min(n, degree) factors per term.
+template <int NF>
+__global__ void __launch_bounds__(kW4Threads, 4) gram_pow_kernel(const GramArgs args) {
+    using Cfg = GramCfg<64>;
+    constexpr int BT = 64;
+    constexpr int LDT = Cfg::kPitch;
+    constexpr int KS = kKS;
+    constexpr int NW = kW4Threads / 32;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+
+    const int n = args.n, n_t = args.n_t, deg = args.pow_deg;
+    const int np = n * deg;  // pseudo states
+    const uint32_t xbytes = (uint32_t)(KS * n * sizeof(double));
+    const uint32_t ybytes = (uint32_t)(KS * n_t * sizeof(double));
+    const int vdoubles = (int)(gram_vbytes(n, n_t) / sizeof(double));
+    const int pdoubles = (int)(gram_vbytes(np, n_t) / sizeof(double));
+
+    uint64_t* vfull = reinterpret_cast<uint64_t*>(smem_raw);  // [kPowNVS] raw samples landed
+    uint64_t* tfull = vfull + kPowNVS;                        // [kNTS] Theta stage built by all warps
+    double* vring = reinterpret_cast<double*>(smem_raw + 128);
+    double* pring = vring + kPowNVS * vdoubles;
+    double* tring = pring + kPowNPS * pdoubles;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+
+    if (tid == 0) {
+        for (int i = 0; i < kPowNVS; ++i) mbar_init(&vfull[i], 1);
+        for (int i = 0; i < kNTS; ++i) mbar_init(&tfull[i], NW);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int e = tid; e < kPowNVS * kVX; e += kW4Threads) {
+        const int w = e % kVX;
+        vring[(e / kVX) * vdoubles + w] = (w < kVZero) ? 1.0 : 0.0;
+    }
+    for (int e = tid; e < kPowNPS * kVX; e += kW4Threads) {
+        const int w = e % kVX;
+        pring[(e / kVX) * pdoubles + w] = (w < kVZero) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+
+    const int64_t nstages_total = (args.m + KS - 1) / KS;
+    const int seg_begin = args.cta_seg_begin[blockIdx.x];
+    const int seg_end = args.cta_seg_begin[blockIdx.x + 1];
+    int total = 0;
+    for (int sg = seg_begin; sg < seg_end; ++sg) total += (int)(args.segs[sg].stage_end - args.segs[sg].stage_begin);
+    if (total == 0) return;
+
+    int tma_seg = seg_begin;
+    int tma_stage = (int)args.segs[seg_begin].stage_begin, tma_seg_end = (int)args.segs[seg_begin].stage_end;
+    int tma_item = 0;
+    uint32_t ragged_slots = 0;
+    const int ragged_stage = (args.m % KS) ? (int)(nstages_total - 1) : -1;
+    auto request_samples = [&]() {
+        if (tma_item >= total) return;
+        const int slot = tma_item & (kPowNVS - 1);
+        const bool mine = (tma_item % NW) == warp;
+        if (tma_stage != ragged_stage) {
+            if ((ragged_slots >> slot) & 1) {
+                ragged_slots &= ~(1u << slot);
+                if (mine) {
+                    if (lane < KS) vring[slot * vdoubles + kVOnes + lane] = 1.0;
+                    __syncwarp();
+                }
+            }
+            if (mine && lane == 0) {
+                double* dst = vring + slot * vdoubles + kVX;
+                const int64_t s0 = (int64_t)tma_stage * KS;
+                mbar_expect_tx(&vfull[slot], xbytes + ybytes);
+                bulk_g2s(dst, args.X + s0 * n, xbytes, &vfull[slot]);
+                bulk_g2s(dst + KS * n, args.Y + s0 * n_t, ybytes, &vfull[slot]);
+            }
+        } else {
+            ragged_slots |= 1u << slot;
+            if (mine) {
+                double* dst = vring + slot * vdoubles;
+                const int64_t s0 = (int64_t)tma_stage * KS;
+                const int valid = (int)(args.m - s0);
+                for (int e = lane; e < KS * n; e += 32) dst[kVX + e] = (e < valid * n) ? args.X[s0 * n + e] : 0.0;
+                for (int e = lane; e < KS * n_t; e += 32)
+                    dst[kVX + KS * n + e] = (e < valid * n_t) ? args.Y[s0 * n_t + e] : 0.0;
+                if (lane < KS) dst[kVOnes + lane] = (lane < valid) ? 1.0 : 0.0;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&vfull[slot]);
+            }
+        }
+        ++tma_item;
+        if (++tma_stage == tma_seg_end && ++tma_seg < seg_end) {
+            tma_stage = (int)args.segs[tma_seg].stage_begin;
+            tma_seg_end = (int)args.segs[tma_seg].stage_end;
+        }
+    };
+
+    // ---- the table of powers of item `pit`: thread = (sample, group of 16 threads); groups 0 .. n - 1 one state each,
+    // group 7 the targets and the ones column (zero for the padding samples of a ragged last stage)
+    const int es = tid & 15, eq = tid >> 4;
+    auto expand = [&](int pit) {
+        const double* rv = vring + (pit & (kPowNVS - 1)) * vdoubles;
+        double* pv = pring + (pit & (kPowNPS - 1)) * pdoubles;
+        if (eq < n) {
+            const double x = rv[kVX + es * n + eq];
+            double* dstp = pv + kVX + es * np + eq * deg;
+            double p = x;
+            dstp[0] = p;
+            for (int d = 1; d < deg; ++d) {
+                p *= x;
+                dstp[d] = p;
+            }
+        } else if (eq == 7) {
+            for (int e = 0; e < n_t; ++e) pv[kVX + KS * np + es * n_t + e] = rv[kVX + KS * n + es * n_t + e];
+            pv[kVOnes + es] = rv[kVOnes + es];
+        }
+    };
+
+    // ---- this thread's share of a Theta tile: column tid mod 64, samples (tid / 64) * 8 .. + 7
+    int off[NF], str[NF];
+    const int dst = tid & 63, s0 = (tid >> 6) * (KS / 2);
+    {
+        const int term = tid & 63;
+        const uint4 q = *reinterpret_cast<const uint4*>(args.pow_factors + (size_t)term * kMaxFactors);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        const bool dead = term >= args.kaug;
+#pragma unroll
+        for (int d = 0; d < NF; ++d) {
+            const uint32_t f = (w[d >> 1] >> (16 * (d & 1))) & 0xFFFFu;
+            int o = kVOnes, st = 1;
+            if (f != kNoFactor) {
+                const bool isy = (f & kFactorIsY) != 0;
+                o = isy ? kVX + KS * np + (int)(f & 0x7FFF) : kVX + (int)f;
+                st = isy ? n_t : np;
+            }
+            if (dead) o = kVZero, st = 0;
+            off[d] = o, str[d] = st;
+        }
+    }
+
+    // ---- prologue: raw tiles, the tables of items 0 .. 3, Theta(0 .. kAhead - 1) completely
+#pragma unroll 1
+    for (int i = 0; i < kPowNVS; ++i) request_samples();
+#pragma unroll 1
+    for (int it = 0; it < 2 * kAhead && it < total; ++it) {
+        mbar_wait(&vfull[it], 0);
+        expand(it);
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int it = 0; it < kAhead && it < total; ++it) {
+        const double* v = pring + it * pdoubles;
+        double* dstt = tring + it * Cfg::kStageDoubles;
+        for (int s = s0; s < s0 + KS / 2; ++s) {
+            double p = v[off[0] + s * str[0]];
+#pragma unroll
+            for (int d = 1; d < NF; ++d) p *= v[off[d] + s * str[d]];
+            dstt[dst + s * LDT] = p;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tfull[it]);
+    }
+
+    int item = 0;
+    bool ready_t = false, ready_v = false;
+    for (int sg = seg_begin; sg < seg_end; ++sg) {
+        const GramSegment seg = args.segs[sg];
+        double accA[8][2], accB[4][2];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) accA[j][0] = accA[j][1] = 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) accB[j][0] = accB[j][1] = 0.0;
+
+        const int nst = (int)(seg.stage_end - seg.stage_begin);
+        for (int q = 0; q < nst; ++q, ++item) {
+            const int tslot = item & (kNTS - 1);
+            if (!ready_t) mbar_wait(&tfull[tslot], (uint32_t)((item / kNTS) & 1));
+            // every warp has finished stage item - 2 here: the raw slot of item (read by expand four stages ago) and
+            // the table slot of item (read by the builder two stages ago) are free
+            request_samples();
+            const int nitem = item + kAhead;      // the item whose Theta tile this stage builds (table: two stages old)
+            const int pitem = item + 2 * kAhead;  // the item whose table of powers this stage writes
+            const bool have_next = (nitem < total);
+            if (pitem < total) {
+                if (!ready_v) mbar_wait(&vfull[pitem & (kPowNVS - 1)], (uint32_t)((pitem / kPowNVS) & 1));
+                expand(pitem);
+            }
+            ready_t = (item + 1 < total) ? mbar_test(&tfull[(item + 1) & (kNTS - 1)], (uint32_t)(((item + 1) / kNTS) & 1)) : true;
+            ready_v = (pitem + 1 < total) ? mbar_test(&vfull[(pitem + 1) & (kPowNVS - 1)], (uint32_t)(((pitem + 1) / kPowNVS) & 1)) : true;
+
+            const double* tI = tring + tslot * Cfg::kStageDoubles;
+            const double* v = pring + (nitem & (kPowNPS - 1)) * pdoubles;
+            double* tnext = tring + (nitem & (kNTS - 1)) * Cfg::kStageDoubles;  // (stale but harmless at the end)
+            switch (warp) {
+                case 0: stage_body_w4<NF, 0>(accA, accB, tI, v, tnext, off, str, dst, s0, g, t); break;
+                case 1: stage_body_w4<NF, 1>(accA, accB, tI, v, tnext, off, str, dst, s0, g, t); break;
+                case 2: stage_body_w4<NF, 2>(accA, accB, tI, v, tnext, off, str, dst, s0, g, t); break;
+                default: stage_body_w4<NF, 3>(accA, accB, tI, v, tnext, off, str, dst, s0, g, t); break;
+            }
+            if (have_next) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tfull[nitem & (kNTS - 1)]);
+            }
+        }
+
         double* out = args.partials + (size_t)seg.slot * BT * BT;
         const int rA = 7 - warp, rB = warp;
 #pragma unroll
@@ -1928,27 +1917,32 @@ int gram_run(ddb_ctx* ctx, double* dPacked) {
         }
     }
     // at most 3 states, degree >= 3 (C2): one power per state instead of one factor per degree (gram_pow_kernel).
-    // Opt-in (DDB_GRAM_POW=1): 2 instead of 4 multiplies per value at C2 and no faster (2.28 against 2.25 ms with the
-    // same warp placement) -- the third builder to show that the multiply count is not what limits this shape
+    // On the two-warp layout the multiply count did not matter (2.28 against 2.25 ms); with four warps per sub-partition
+    // it does: C2 2.015 -> 1.947 ms (profiles/gram_c2_experiments_r2.txt).  DDB_GRAM_POW=0 keeps the factor builder.
     GramKernel pow_kern = nullptr;
     if (bt == 64 && !tree_kern) {
         const char* penv = getenv("DDB_GRAM_POW");
-        if (penv && atoi(penv) == 1) {
+        const char* wenv0 = getenv("DDB_GRAM_W4");
+        if (!(penv && atoi(penv) == 0) && !(wenv0 && atoi(wenv0) == 0)) {
             DDB_TRY(ensure_pow_factors(ctx));
             if (ctx->pow_nf > 0 && gram_pow_smem_bytes(n, n_t, ctx->max_degree) <= 56 * 1024)
                 pow_kern = ctx->pow_nf == 1 ? gram_pow_kernel<1> : ctx->pow_nf == 2 ? gram_pow_kernel<2> : gram_pow_kernel<3>;
         }
     }
-    if (pow_kern) tree_kern = pow_kern;  // launched the same way (64 threads, its own shared-memory size)
     // default for single-pair libraries: four balanced warps (gram_w4_kernel); DDB_GRAM_W4=0 keeps gram_kernel<64>
     int kern_threads = GramCfg<64>::kThreads;
     bool w4 = false;
+    if (pow_kern) {
+        tree_kern = pow_kern;  // launched the same way (its own thread count and shared-memory size)
+        kern_threads = kW4Threads;
+    }
     if (bt == 64 && !tree_kern) {
         const char* wenv = getenv("DDB_GRAM_W4");
         if (!(wenv && atoi(wenv) == 0)) {
             const int dg = ctx->max_degree;
             tree_kern = dg <= 2 ? gram_w4_kernel<2> : dg <= 3 ? gram_w4_kernel<3> : dg <= 4 ? gram_w4_kernel<4>
                         : dg <= 5 ? gram_w4_kernel<5> : gram_w4_kernel<kMaxFactors>;
+            // (five CTAs per SM -- 96 registers, no spills -- is slower: 2.14 against 2.04 ms at C2)
             kern_threads = kW4Threads;
             w4 = true;
         }

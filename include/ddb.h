@@ -93,9 +93,9 @@ typedef struct ddb_timings {
     int32_t candidates;     /* unique (equation, support, coefficients) candidates scored */
     double gram_dmma_flops; /* FP64 tensor-core flops the last Gram stage issued PER SAMPLE (512 per DMMA.8x8x4);
                                below the algorithmic k(k+1) + 2 k n_t + 2 n_t when the moment schedule ran */
-    int32_t gram_schedule;  /* schedule of the last Gram stage: 0 self-building, 1 ring, 2 moment, 3 self-building from a
-                               per-stage table of powers (opt-in), 4 self-building with four balanced warps
-                               (single-pair libraries, k + n_t <= 64) */
+    int32_t gram_schedule;  /* schedule of the last Gram stage: 0 self-building, 1 ring, 2 moment, 3 single-pair libraries (k + n_t <= 64)
+                               of at most 3 states and degree >= 3: four balanced warps, builder reads a per-stage
+                               table of powers, 4 other single-pair libraries: four balanced warps */
     int32_t allreduce_calls; /* NCCL all-reduces queued by the last sharded solve / since the last reset */
     double allreduce_ms;    /* their duration on the compute stream (includes waiting for the slowest rank) */
     double allreduce_bytes; /* payload per rank */

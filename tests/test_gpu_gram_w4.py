@@ -23,11 +23,17 @@ def ctx():
 
 def _gram(ctx, w4):
     old = os.environ.get("DDB_GRAM_W4")
+    oldp = os.environ.get("DDB_GRAM_POW")
     os.environ["DDB_GRAM_W4"] = "1" if w4 else "0"
+    os.environ["DDB_GRAM_POW"] = "0"  # the factor-by-factor builder on both layouts
     try:
         ctx.gram()
         return ctx.gram_download(), ctx.timings()["gram_schedule"]
     finally:
+        if oldp is None:
+            del os.environ["DDB_GRAM_POW"]
+        else:
+            os.environ["DDB_GRAM_POW"] = oldp
         if old is None:
             del os.environ["DDB_GRAM_W4"]
         else:
