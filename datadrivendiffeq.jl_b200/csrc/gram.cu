@@ -1014,7 +1014,9 @@ inline size_t gram_pow_smem_bytes(int n, int n_t, int deg) {
 template <int NF, int W>
 __device__ __forceinline__ void stage_body_w4(double (&accA)[8][2], double (&accB)[4][2], const double* __restrict__ tI,
                                               const double* __restrict__ v, double* __restrict__ tnext,
-                                              const int (&off)[NF], const int (&str)[NF], int dst, int s0, int g, int t) {
+                                              const int (&off)[NF], const int (&str)[NF], int dst, int g, int t) {
+    // off / dst already point at this thread's first sample (the callers fold s0 in): the sample index below is a
+    // compile-time constant
     constexpr int LDT = GramCfg<64>::kPitch;
     constexpr int RA = 7 - W, RB = W;
 #pragma unroll
@@ -1023,7 +1025,7 @@ __device__ __forceinline__ void stage_body_w4(double (&accA)[8][2], double (&acc
 #pragma unroll
         for (int q = 0; q < 2; ++q)
 #pragma unroll
-            for (int d = 0; d < NF; ++d) fv[q][d] = v[off[d] + (s0 + kk * 2 + q) * str[d]];
+            for (int d = 0; d < NF; ++d) fv[q][d] = v[off[d] + (kk * 2 + q) * str[d]];
         const double* row = tI + (kk * 4 + t) * LDT + g;
         const double aA = row[8 * RA], aB = row[8 * RB];
         double b[8];
@@ -1034,7 +1036,7 @@ __device__ __forceinline__ void stage_body_w4(double (&accA)[8][2], double (&acc
             double p = fv[q][0];
 #pragma unroll
             for (int d = 1; d < NF; ++d) p *= fv[q][d];
-            tnext[dst + (s0 + kk * 2 + q) * LDT] = p;
+            tnext[dst + (kk * 2 + q) * LDT] = p;
         }
 #pragma unroll
         for (int j = 0; j <= RA; ++j) dmma884(accA[j][0], accA[j][1], aA, b[j]);
@@ -1153,6 +1155,10 @@ __global__ void __launch_bounds__(kW4Threads, MB) gram_w4_kernel(const GramArgs 
             off[d] = o, str[d] = st;
         }
     }
+    int off0[NF];
+#pragma unroll
+    for (int d = 0; d < NF; ++d) off0[d] = off[d] + s0 * str[d];
+    const int dst0 = dst + s0 * LDT;
 
 #pragma unroll 1
     for (int i = 0; i < kNVS; ++i) request_samples();
@@ -1196,10 +1202,10 @@ __global__ void __launch_bounds__(kW4Threads, MB) gram_w4_kernel(const GramArgs 
             const double* v = vring + (nitem & (kNVS - 1)) * vdoubles;
             double* tnext = tring + (nitem & (kNTS - 1)) * Cfg::kStageDoubles;  // (stale but harmless at the end)
             switch (warp) {
-                case 0: stage_body_w4<NF, 0>(accA, accB, tI, v, tnext, off, str, dst, s0, g, t); break;
-                case 1: stage_body_w4<NF, 1>(accA, accB, tI, v, tnext, off, str, dst, s0, g, t); break;
-                case 2: stage_body_w4<NF, 2>(accA, accB, tI, v, tnext, off, str, dst, s0, g, t); break;
-                default: stage_body_w4<NF, 3>(accA, accB, tI, v, tnext, off, str, dst, s0, g, t); break;
+                case 0: stage_body_w4<NF, 0>(accA, accB, tI, v, tnext, off0, str, dst0, g, t); break;
+                case 1: stage_body_w4<NF, 1>(accA, accB, tI, v, tnext, off0, str, dst0, g, t); break;
+                case 2: stage_body_w4<NF, 2>(accA, accB, tI, v, tnext, off0, str, dst0, g, t); break;
+                default: stage_body_w4<NF, 3>(accA, accB, tI, v, tnext, off0, str, dst0, g, t); break;
             }
             if (have_next) {
                 __syncwarp();
@@ -1223,7 +1229,7 @@ __global__ void __launch_bounds__(kW4Threads, MB) gram_w4_kernel(const GramArgs 
 
 // Power-table builder on the four-warp layout (see the comment above gram_pow_smem_bytes): gram_w4_kernel whose builder
 // reads a per-stage table of powers with NF = min(n, degree) factors per term.
-template <int NF>
+template <int NF, int DEG = 0>  // DEG: the library's degree when instantiated for it (3, 4, 5), 0 = read from args
 __global__ void __launch_bounds__(kW4Threads, 4) gram_pow_kernel(const GramArgs args) {
     using Cfg = GramCfg<64>;
     constexpr int BT = 64;
@@ -1232,7 +1238,7 @@ __global__ void __launch_bounds__(kW4Threads, 4) gram_pow_kernel(const GramArgs 
     constexpr int NW = kW4Threads / 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
 
-    const int n = args.n, n_t = args.n_t, deg = args.pow_deg;
+    const int n = args.n, n_t = args.n_t, deg = DEG > 0 ? DEG : args.pow_deg;
     const int np = n * deg;  // pseudo states
     const uint32_t xbytes = (uint32_t)(KS * n * sizeof(double));
     const uint32_t ybytes = (uint32_t)(KS * n_t * sizeof(double));
@@ -1328,9 +1334,17 @@ __global__ void __launch_bounds__(kW4Threads, 4) gram_pow_kernel(const GramArgs 
             double* dstp = pv + kVX + es * np + eq * deg;
             double p = x;
             dstp[0] = p;
-            for (int d = 1; d < deg; ++d) {
-                p *= x;
-                dstp[d] = p;
+            if constexpr (DEG > 0) {
+#pragma unroll
+                for (int d = 1; d < DEG; ++d) {
+                    p *= x;
+                    dstp[d] = p;
+                }
+            } else {
+                for (int d = 1; d < deg; ++d) {
+                    p *= x;
+                    dstp[d] = p;
+                }
             }
         } else if (eq == 7) {
             for (int e = 0; e < n_t; ++e) pv[kVX + KS * np + es * n_t + e] = rv[kVX + KS * n + es * n_t + e];
@@ -1359,6 +1373,10 @@ __global__ void __launch_bounds__(kW4Threads, 4) gram_pow_kernel(const GramArgs 
             off[d] = o, str[d] = st;
         }
     }
+    int off0[NF];
+#pragma unroll
+    for (int d = 0; d < NF; ++d) off0[d] = off[d] + s0 * str[d];
+    const int dst0 = dst + s0 * LDT;
 
     // ---- prologue: raw tiles, the tables of items 0 .. 3, Theta(0 .. kAhead - 1) completely
 #pragma unroll 1
@@ -1414,10 +1432,10 @@ __global__ void __launch_bounds__(kW4Threads, 4) gram_pow_kernel(const GramArgs 
             const double* v = pring + (nitem & (kPowNPS - 1)) * pdoubles;
             double* tnext = tring + (nitem & (kNTS - 1)) * Cfg::kStageDoubles;  // (stale but harmless at the end)
             switch (warp) {
-                case 0: stage_body_w4<NF, 0>(accA, accB, tI, v, tnext, off, str, dst, s0, g, t); break;
-                case 1: stage_body_w4<NF, 1>(accA, accB, tI, v, tnext, off, str, dst, s0, g, t); break;
-                case 2: stage_body_w4<NF, 2>(accA, accB, tI, v, tnext, off, str, dst, s0, g, t); break;
-                default: stage_body_w4<NF, 3>(accA, accB, tI, v, tnext, off, str, dst, s0, g, t); break;
+                case 0: stage_body_w4<NF, 0>(accA, accB, tI, v, tnext, off0, str, dst0, g, t); break;
+                case 1: stage_body_w4<NF, 1>(accA, accB, tI, v, tnext, off0, str, dst0, g, t); break;
+                case 2: stage_body_w4<NF, 2>(accA, accB, tI, v, tnext, off0, str, dst0, g, t); break;
+                default: stage_body_w4<NF, 3>(accA, accB, tI, v, tnext, off0, str, dst0, g, t); break;
             }
             if (have_next) {
                 __syncwarp();
@@ -1824,6 +1842,19 @@ static int ensure_tree_program(ddb_ctx* ctx) {
     return DDB_OK;
 }
 
+template <int NF>
+static GramKernel pick_pow_kernel_deg(int deg) {
+    switch (deg) {
+        case 3: return gram_pow_kernel<NF, 3>;
+        case 4: return gram_pow_kernel<NF, 4>;
+        case 5: return gram_pow_kernel<NF, 5>;
+        default: return gram_pow_kernel<NF, 0>;
+    }
+}
+static GramKernel pick_pow_kernel(int nf, int deg) {
+    return nf == 1 ? pick_pow_kernel_deg<1>(deg) : nf == 2 ? pick_pow_kernel_deg<2>(deg) : pick_pow_kernel_deg<3>(deg);
+}
+
 // Power-table builder: (re)builds the factor codes when the library or the number of targets changed;
 // ctx->pow_nf = 0: not applicable (more than 3 states -- the table is written by (sample, state) threads, the fourth
 // group copies the targets --, or degree < 3 where a power per state saves no multiply).
@@ -1926,7 +1957,7 @@ int gram_run(ddb_ctx* ctx, double* dPacked) {
         if (!(penv && atoi(penv) == 0) && !(wenv0 && atoi(wenv0) == 0)) {
             DDB_TRY(ensure_pow_factors(ctx));
             if (ctx->pow_nf > 0 && gram_pow_smem_bytes(n, n_t, ctx->max_degree) <= 56 * 1024)
-                pow_kern = ctx->pow_nf == 1 ? gram_pow_kernel<1> : ctx->pow_nf == 2 ? gram_pow_kernel<2> : gram_pow_kernel<3>;
+                pow_kern = pick_pow_kernel(ctx->pow_nf, ctx->max_degree);
         }
     }
     // default for single-pair libraries: four balanced warps (gram_w4_kernel); DDB_GRAM_W4=0 keeps gram_kernel<64>
