@@ -18,8 +18,8 @@ struct EqState {
     int nruns;      // recorded runs (maximal step sequences with unchanged cache content)
     int last_cand;  // candidate id of the current run
     int dof0;       // dof of the zeroed best cache
-    int flags;      // bit 0: a factorisation broke down
-    int pad[3];
+    int flags;      // bit 0: a factorisation broke down (no fallback applied), bit 1: minimum-norm steps were taken
+    int pad[3];     // [0]: the initial solve is pending (runs as a masked step), [1]: parked for a minimum-norm big step
 };
 
 struct SweepState {

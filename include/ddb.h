@@ -302,7 +302,10 @@ int ddb_rss_buffer(ddb_ctx* ctx, double** dRss);
  * support_path n_t x L x ceil(k/32) uint32 words (converged support at every threshold,
  * index ((i*L + j)*W + w)); coef_path n_t x L x k doubles (coefficients of the cache when the
  * inner loop of threshold j stopped, index ((i*L + j)*k + t)); iters_path n_t x L;
- * flags n_t (bit 0: a factorisation broke down for that target). */
+ * flags n_t (bit 0: a factorisation broke down for that target and no fallback applied -- ADMM / SR3, non-finite
+ * blocks; bit 1: STLSQ took minimum-norm steps for it, i.e. some masked system was rank deficient -- fewer samples than
+ * active terms or collinear terms -- and was solved as `A[p, :]' \ b` solves it in the reference, STLSQ.jl:93-99:
+ * Jacobi pseudo-inverse in shared memory up to 64 active terms, symmetric eigen-decomposition in global memory beyond). */
 int ddb_select(ddb_ctx* ctx, double* coef, double* lambda_opt, int32_t* iters, double* rss,
                int32_t* dof, uint32_t* support_path, double* coef_path, int32_t* iters_path,
                int32_t* flags);
