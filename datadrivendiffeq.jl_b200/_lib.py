@@ -150,6 +150,7 @@ PROTOTYPES = {
     "ddb_dmd_eig_sym": (C.c_int, [_P, _P, C.c_int, _P]),
     "ddb_dmd_eig": (C.c_int, [_P, _P, C.c_int, _P, _P]),
     "ddb_gemm_nt": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int64, _P, C.c_int64, C.c_int, C.c_int, C.c_int]),
+    "ddb_pow_factors_describe": (C.c_int, [C.c_int, C.c_int, _P, C.c_int, _P, _P]),
     "ddb_gram_plan_describe": (C.c_int64, [C.c_int, C.c_int64, C.c_int, _P, C.c_int64, _P]),
     "ddb_get_timings": (C.c_int, [_P, C.POINTER(Timings)]),
     "ddb_get_stream": (C.c_int, [_P, C.POINTER(_P)]),

@@ -116,6 +116,7 @@ int64_t moment_builder_describe(const uint8_t* exps, int n, int k, int n_t, uint
                                 uint8_t* opcnt, int64_t opcnt_cap, int32_t* block_ops, int64_t block_cap);
 void trsm_free(ddb_ctx* ctx);
 void comm_free(ddb_ctx* ctx);
+int gram_pow_factors(const uint8_t* exps, int n, int k, int n_t, int deg, std::vector<uint16_t>* tab);  // gram.cu
 void userfeat_free(ddb_ctx* ctx);
 int userfeat_nfeat(const ddb_ctx* ctx);
 int userfeat_expand(ddb_ctx* ctx, const double* d_raw, int64_t mc, double* out, cudaStream_t st);
@@ -1216,6 +1217,24 @@ int64_t ddb_moment_builder_describe(int n, int k, const uint8_t* exps, int n_t, 
         return DDB_INVALID_ARG;
     }
     return moment_builder_describe(exps, n, k, n_t, optab, optab_cap, opcnt, opcnt_cap, block_ops, block_cap);
+}
+
+int ddb_pow_factors_describe(int n, int k, const uint8_t* exps, int n_t, uint16_t* factors, int* degree) {
+    if (n <= 0 || k <= 0 || n_t <= 0 || !exps) {
+        set_error("ddb_pow_factors_describe: n, k, n_t must be positive and exps non-null");
+        return DDB_INVALID_ARG;
+    }
+    int maxdeg = 0;
+    for (int j = 0; j < k; ++j) {
+        int d = 0;
+        for (int i = 0; i < n; ++i) d += exps[(size_t)i + (size_t)n * j];
+        maxdeg = std::max(maxdeg, d);
+    }
+    if (degree) *degree = maxdeg;
+    std::vector<uint16_t> tab;
+    const int nf = ddb::gram_pow_factors(exps, n, k, n_t, maxdeg, &tab);
+    if (nf > 0 && factors) memcpy(factors, tab.data(), tab.size() * sizeof(uint16_t));
+    return nf;
 }
 
 int64_t ddb_moment_wave_describe(int n, int k, const uint8_t* exps, int n_t, int64_t m, int nctas, int64_t* segments,

@@ -1858,22 +1858,31 @@ static GramKernel pick_pow_kernel(int nf, int deg) {
 // Power-table builder: (re)builds the factor codes when the library or the number of targets changed;
 // ctx->pow_nf = 0: not applicable (more than 3 states -- the table is written by (sample, state) threads, the fourth
 // group copies the targets --, or degree < 3 where a power per state saves no multiply).
+// Factor codes of the power-table builder for a monomial library: per augmented row (64 rows x kMaxFactors codes) one
+// code per state with a non-zero exponent, state * deg + exponent - 1 (an index into the stage's table of powers), the
+// targets as kFactorIsY | t, kNoFactor elsewhere.  Returns the number of factors per term the kernel needs (1 .. 3), 0
+// when the builder does not apply.  Host only (also behind ddb_pow_factors_describe for the CPU tests).
+int gram_pow_factors(const uint8_t* exps, int n, int k, int n_t, int deg, std::vector<uint16_t>* tab) {
+    if (n > 3 || deg < 3 || deg > kMaxFactors || k + n_t > 64) return 0;
+    tab->assign((size_t)64 * kMaxFactors, kNoFactor);
+    int nf = 1;
+    for (int j = 0; j < k; ++j) {
+        int d = 0;
+        for (int i = 0; i < n; ++i) {
+            const int e = exps[(size_t)i + (size_t)n * j];
+            if (e > 0) (*tab)[(size_t)j * kMaxFactors + d++] = (uint16_t)(i * deg + e - 1);
+        }
+        nf = std::max(nf, d);
+    }
+    for (int i = 0; i < n_t; ++i) (*tab)[(size_t)(k + i) * kMaxFactors] = (uint16_t)(kFactorIsY | i);
+    return nf;
+}
+
 static int ensure_pow_factors(ddb_ctx* ctx) {
     if (ctx->pow_lib_version == ctx->lib_version && ctx->pow_nt == ctx->n_t) return DDB_OK;
-    const int k = ctx->k, n = ctx->n, n_t = ctx->n_t, deg = ctx->max_degree;
-    int nf = 0;
-    if (n <= 3 && deg >= 3 && k + n_t <= 64) {
-        std::vector<uint16_t> tab((size_t)64 * kMaxFactors, kNoFactor);
-        for (int j = 0; j < k; ++j) {
-            int d = 0;
-            for (int i = 0; i < n; ++i) {
-                const int e = ctx->exps[(size_t)i + (size_t)n * j];
-                if (e > 0) tab[(size_t)j * kMaxFactors + d++] = (uint16_t)(i * deg + e - 1);
-            }
-            nf = std::max(nf, d);
-        }
-        for (int i = 0; i < n_t; ++i) tab[(size_t)(k + i) * kMaxFactors] = (uint16_t)(kFactorIsY | i);
-        nf = std::max(nf, 1);
+    std::vector<uint16_t> tab;
+    const int nf = gram_pow_factors(ctx->exps.data(), ctx->n, ctx->k, ctx->n_t, ctx->max_degree, &tab);
+    if (nf > 0) {
         DDB_TRY(ctx->d_pow_factors.reserve(tab.size() * sizeof(uint16_t)));
         DDB_CUDA_TRY(cudaMemcpyAsync(ctx->d_pow_factors.p, tab.data(), tab.size() * sizeof(uint16_t), cudaMemcpyHostToDevice,
                                      ctx->stream));
@@ -1881,7 +1890,7 @@ static int ensure_pow_factors(ddb_ctx* ctx) {
     }
     ctx->pow_nf = nf;
     ctx->pow_lib_version = ctx->lib_version;
-    ctx->pow_nt = n_t;
+    ctx->pow_nt = ctx->n_t;
     return DDB_OK;
 }
 

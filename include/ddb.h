@@ -472,6 +472,15 @@ int64_t ddb_moment_builder_describe(int n, int k, const uint8_t* exps, int n_t, 
 int64_t ddb_moment_wave_describe(int n, int k, const uint8_t* exps, int n_t, int64_t m, int nctas, int64_t* segments,
                                  int64_t cap, double* info);
 
+/* Host-only: the builder of the single-pair Gram kernel for libraries of at most 3 states and degree >= 3
+ * (csrc/gram.cu: gram_pow_kernel).  Every 16-sample stage gets a table of powers x_i^e (e = 1 .. degree) and a library
+ * value is the product of ONE table entry per state, x^a y^b z^c, instead of one staged state per unit of degree.
+ * Writes 64 rows x 8 factor codes (library terms, then the targets): state * degree + exponent - 1 for every state with
+ * a non-zero exponent, 0x8000 | target for a target row, 0xFFFF = no factor; *degree receives the library's total degree.
+ * Returns the number of factors per term the kernel is instantiated for (1 .. 3), 0 when the builder does not apply
+ * (more than 3 states, degree < 3, k + n_t > 64: nothing is written), negative on invalid arguments.  Needs no GPU. */
+int ddb_pow_factors_describe(int n, int k, const uint8_t* exps, int n_t, uint16_t* factors, int* degree);
+
 int ddb_get_timings(const ddb_ctx* ctx, ddb_timings* out);
 /* The context's CUDA stream (cudaStream_t) so a caller can order its own work after ours. */
 int ddb_get_stream(ddb_ctx* ctx, void** stream);

@@ -328,3 +328,63 @@ def test_builder_tables_absent_for_cubic_libraries():
     assert plan is not None
     got, _, _, _ = _builder_tables(ex, 20, plan["npairs"], plan["nrb"] + plan["ncb"])
     assert got == 0
+
+
+# ------------------------------------------------------------------------------------------------
+# power-table builder of the single-pair kernel (csrc/gram.cu: gram_pow_kernel), host logic only
+# ------------------------------------------------------------------------------------------------
+def _pow_factors(ex, n_t):
+    lib = _lib.load()
+    n, k = ex.shape
+    exf = np.asfortranarray(ex.astype(np.uint8))
+    tab = np.full((64, 8), 0xFFFF, dtype=np.uint16)
+    deg = np.zeros(1, dtype=np.int32)
+    nf = lib.ddb_pow_factors_describe(n, k, _lib.ptr(exf), n_t, _lib.ptr(tab), _lib.ptr(deg))
+    return nf, int(deg[0]), tab
+
+
+@pytest.mark.parametrize("n,deg,n_t", [(3, 5, 3), (2, 8, 2), (1, 7, 1), (3, 3, 6), (3, 4, 1)])
+def test_pow_factors_replay(n, deg, n_t):
+    """Replays the table on the CPU: every library value is the product of one table-of-powers entry per state with a
+    non-zero exponent (powers formed left to right, as the kernel's (sample, state) threads form them), targets are
+    single raw values, rows past the library have no factor."""
+    ex = oracle.polynomial_exponents(n, deg)
+    k = ex.shape[1]
+    nf, d, tab = _pow_factors(ex, n_t)
+    assert d == deg and nf == min(n, deg)
+    rng = np.random.default_rng(n * 10 + deg)
+    x = rng.standard_normal(n) * 1.5
+    powers = np.empty(n * deg)
+    for i in range(n):
+        p = x[i]
+        powers[i * deg] = p
+        for e in range(1, deg):
+            p = p * x[i]
+            powers[i * deg + e] = p
+    for j in range(k):
+        codes = [int(c) for c in tab[j] if c != 0xFFFF]
+        assert len(codes) == int(np.count_nonzero(ex[:, j])) <= nf
+        assert sorted(c // deg for c in codes) == [i for i in range(n) if ex[i, j] > 0]  # one code per state, state order
+        for c in codes:
+            assert c % deg + 1 == ex[c // deg, j]
+        val = 1.0
+        for c in codes:
+            val *= powers[c]
+        ref = float(np.prod(x ** ex[:, j].astype(float)))
+        assert abs(val - ref) <= 1e-13 * max(1.0, abs(ref))
+    for t in range(n_t):
+        assert tab[k + t, 0] == (0x8000 | t) and (tab[k + t, 1:] == 0xFFFF).all()
+    assert (tab[k + n_t:] == 0xFFFF).all()
+
+
+def test_pow_factors_step_aside():
+    """More than 3 states, degree below 3, or more than 64 augmented rows: the builder does not apply."""
+    for n, deg, n_t in [(5, 3, 5), (3, 2, 3), (6, 2, 1), (3, 5, 9), (4, 3, 2)]:
+        nf, d, tab = _pow_factors(oracle.polynomial_exponents(n, deg), n_t)
+        assert nf == 0 and d == deg and (tab == 0xFFFF).all()
+    # a hand-picked library without pure powers
+    ex = np.array([[2, 1, 0], [0, 3, 1], [1, 1, 1], [4, 0, 1], [0, 0, 5], [1, 0, 0]], dtype=np.uint8).T.copy()
+    nf, d, tab = _pow_factors(ex, 2)
+    assert nf == 3 and d == 5
+    assert [int(c) for c in tab[0] if c != 0xFFFF] == [0 * 5 + 1, 1 * 5 + 0]
+    assert [int(c) for c in tab[4] if c != 0xFFFF] == [2 * 5 + 4]
