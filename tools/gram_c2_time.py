@@ -11,4 +11,5 @@ with ddb200.Context(0) as ctx:
     for _ in range(reps):
         ctx.gram()
         ts.append(ctx.timings()["gram_ms"])
-    print(os.environ.get("DDB_GRAM_W4_TIMING_NF"), os.environ.get("DDB_GRAM_W4"), "gram_ms min %.4f median %.4f" % (min(ts), float(np.median(ts))), ctx.timings()["gram_schedule"])
+    print("DDB_GRAM_POW=%s DDB_GRAM_W4=%s" % (os.environ.get("DDB_GRAM_POW"), os.environ.get("DDB_GRAM_W4")),
+          "gram_ms min %.4f median %.4f" % (min(ts), float(np.median(ts))), "schedule", ctx.timings()["gram_schedule"])
