@@ -20,6 +20,14 @@ import sys
 import threading
 import time
 
+if "reference" in sys.argv[1:] or os.environ.get("WORLD_SIZE", "1") == "1":  # (N = 1: the cpu_baseline leg of our arm)
+    # The CPU arm uses every host core.  torch.distributed.run exports OMP_NUM_THREADS=1 to its workers, and OpenBLAS
+    # sizes its thread pool from the environment when NumPy / SciPy load it: raising the limit afterwards
+    # (threadpoolctl) reports the full count but still ran the pivoted-QR sweep 5x slower (6.4 against 31 samples/s on
+    # the same 8 cores), so the variables are set BEFORE NumPy is imported.
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
